@@ -1,0 +1,79 @@
+"""ctypes binding of libmmfn_b200.so.  Prototypes are read from include/mmfn_b200.h so the
+Python side can never drift from the C ABI.  There is no fallback: a missing library or a
+failing call raises."""
+import ctypes
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(os.path.dirname(HERE), "include", "mmfn_b200.h")
+LIB_PATH = os.path.join(HERE, "lib", "libmmfn_b200.so")
+
+_CTYPES = {
+    "int": ctypes.c_int, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64,
+    "float": ctypes.c_float, "double": ctypes.c_double, "cudaStream_t": ctypes.c_void_p,
+}
+_PROTO = re.compile(r"^int\s+(mmfn_\w+)\s*\(([^)]*)\)\s*;", re.M)
+
+
+def parse_header(path=HEADER):
+    """-> {name: [(ctype, argname), ...]} for every function the header declares."""
+    protos = {}
+    for name, args in _PROTO.findall(open(path).read()):
+        sig = []
+        args = args.strip()
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    sig.append((ctypes.c_void_p, a.split("*")[-1].strip()))
+                else:
+                    toks = [t for t in a.split() if t != "const"]
+                    sig.append((_CTYPES[toks[0]], toks[1]))
+        protos[name] = sig
+    return protos
+
+
+class MmfnError(RuntimeError):
+    pass
+
+
+class _Lib:
+    def __init__(self):
+        if not os.path.exists(LIB_PATH):
+            raise MmfnError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU or eager fallback)")
+        self._dll = ctypes.CDLL(LIB_PATH)
+        self.protos = parse_header()
+        self.launches = 0
+        for name, sig in self.protos.items():
+            fn = getattr(self._dll, name)      # AttributeError if the .so lacks a declared symbol
+            fn.restype = ctypes.c_int
+            fn.argtypes = [t for t, _ in sig]
+            if name not in ("mmfn_version", "mmfn_last_error"):
+                setattr(self, name[len("mmfn_"):], self._wrap(name, fn))
+        self.version = self._dll.mmfn_version()
+
+    def last_error(self):
+        buf = ctypes.create_string_buffer(512)
+        self._dll.mmfn_last_error(buf, 512)
+        return buf.value.decode()
+
+    def _wrap(self, name, fn):
+        def call(*args):
+            rc = fn(*args)
+            self.launches += 1
+            if rc != 0:
+                raise MmfnError(f"{name} failed (code {rc}): {self.last_error()}")
+        call.__name__ = name
+        return call
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _Lib()
+    return _lib

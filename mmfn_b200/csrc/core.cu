@@ -1,0 +1,128 @@
+// Library bookkeeping + the GEMM / convolution C-ABI entries of libmmfn_b200.so.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <type_traits>
+#include "gemm_simt.cuh"
+
+static thread_local char g_err[512] = "";
+
+void mmfn_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+MMFN_API int mmfn_version(void) { return 100; }
+
+// Copies the calling thread's last error string (empty if none) into buf.
+MMFN_API int mmfn_last_error(char* buf, int64_t len) {
+  if (!buf || len <= 0) return MMFN_BAD_ARG;
+  strncpy(buf, g_err, (size_t)len - 1);
+  buf[len - 1] = 0;
+  return 0;
+}
+
+using namespace mmfn;
+
+// C[b0,b1](M,N) (+)= alpha * A(M,K) * B(N,K)^T with fused epilogue; all operands strided.
+MMFN_API int mmfn_gemm_f32(const float* A, int64_t a_sr, int64_t a_sk, int64_t a_sb0, int64_t a_sb1,
+                           const float* B, int64_t b_sr, int64_t b_sk, int64_t b_sb0, int64_t b_sb1,
+                           float* C, int64_t ldc, int64_t c_sb0, int64_t c_sb1,
+                           int M, int N, int K, int nb0, int nb1,
+                           const float* bias, const float* res, const float* mask,
+                           float alpha, int act, int accum, float drop_p, uint64_t drop_seed,
+                           int splitk, cudaStream_t stream) {
+  MMFN_CHECK_ARG(A && B && C, "gemm: null operand");
+  MMFN_CHECK_ARG(M >= 0 && N >= 0 && K >= 0 && nb0 >= 1 && nb1 >= 1, "gemm: bad sizes");
+  MMFN_CHECK_ARG(splitk >= 1, "gemm: splitk must be >= 1");
+  MMFN_CHECK_ARG(splitk == 1 || (accum == 2 && act == 0 && !mask && drop_p == 0.f),
+                 "gemm: split-K needs a linear atomic epilogue");
+  MMFN_CHECK_ARG((int64_t)nb0 * nb1 * splitk <= 65535, "gemm: too many batches");
+  DenseLoader a{A, a_sr, a_sk, a_sb0, a_sb1, M, K};
+  DenseLoader b{B, b_sr, b_sk, b_sb0, b_sb1, N, K};
+  Epilogue e{C, ldc, c_sb0, c_sb1, bias, res, mask, alpha, act, accum, drop_p, drop_seed};
+  return launch_gemm_simt(a, b, M, N, K, e, nb0, nb1, splitk, stream);
+}
+
+static int check_geom(const ConvGeom& g) {
+  MMFN_CHECK_ARG(g.N > 0 && g.H > 0 && g.W > 0 && g.C > 0 && g.Co > 0, "conv: bad tensor sizes");
+  MMFN_CHECK_ARG(g.R > 0 && g.S > 0 && g.stride > 0 && g.pad >= 0, "conv: bad filter");
+  MMFN_CHECK_ARG(g.Ho == (g.H + 2 * g.pad - g.R) / g.stride + 1 &&
+                 g.Wo == (g.W + 2 * g.pad - g.S) / g.stride + 1, "conv: inconsistent output size");
+  MMFN_CHECK_ARG((int64_t)g.N * g.H * g.W < (1ll << 31) && (int64_t)g.N * g.Ho * g.Wo < (1ll << 31),
+                 "conv: pixel count overflows int32");
+  return 0;
+}
+
+// y(N,Ho,Wo,Co) = conv(x(N,H,W,C), w(Co,R,S,C)); NHWC activations, KRSC filters.
+MMFN_API int mmfn_conv2d_fwd_f32(const float* x, const float* w, float* y,
+                                 int N, int H, int W, int C, int Co, int R, int S, int stride, int pad,
+                                 int Ho, int Wo, cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && w && y, "conv_fwd: null pointer");
+  ConvGeom g{N, H, W, C, R, S, stride, pad, Ho, Wo, Co};
+  if (int rc = check_geom(g)) return rc;
+  int K = R * S * C;
+  Im2colLoader<true> a{x, g};
+  DenseLoader b{w, K, 1, 0, 0, Co, K};
+  Epilogue e{y, Co, 0, 0, nullptr, nullptr, nullptr, 1.f, 0, 0, 0.f, 0};
+  return launch_gemm_simt(a, b, N * Ho * Wo, Co, K, e, 1, 1, 1, stream);
+}
+
+// dx(N,H,W,C) = conv_transpose(dy(N,Ho,Wo,Co), wt(C,R,S,Co)) [+ res]; wt is the CRSK
+// permutation of the filters (mmfn_filter_krsc_to_crsk).
+MMFN_API int mmfn_conv2d_dgrad_f32(const float* dy, const float* wt, float* dx, const float* res,
+                                   int N, int H, int W, int C, int Co, int R, int S, int stride, int pad,
+                                   int Ho, int Wo, cudaStream_t stream) {
+  MMFN_CHECK_ARG(dy && wt && dx, "conv_dgrad: null pointer");
+  ConvGeom g{N, H, W, C, R, S, stride, pad, Ho, Wo, Co};
+  if (int rc = check_geom(g)) return rc;
+  int K = R * S * Co;
+  DgradLoader a{dy, g};
+  DenseLoader b{wt, K, 1, 0, 0, C, K};
+  Epilogue e{dx, C, 0, 0, nullptr, res, nullptr, 1.f, 0, 0, 0.f, 0};
+  return launch_gemm_simt(a, b, N * H * W, C, K, e, 1, 1, 1, stream);
+}
+
+// dw(Co,R,S,C) += dy^T * im2col(x); split-K over the pixel dimension, atomic accumulate.
+MMFN_API int mmfn_conv2d_wgrad_f32(const float* dy, const float* x, float* dw,
+                                   int N, int H, int W, int C, int Co, int R, int S, int stride, int pad,
+                                   int Ho, int Wo, int splitk, cudaStream_t stream) {
+  MMFN_CHECK_ARG(dy && x && dw, "conv_wgrad: null pointer");
+  ConvGeom g{N, H, W, C, R, S, stride, pad, Ho, Wo, Co};
+  if (int rc = check_geom(g)) return rc;
+  int Kt = R * S * C, P = N * Ho * Wo;
+  if (splitk <= 0) {
+    int tiles = ((Co + BM - 1) / BM) * ((Kt + BN - 1) / BN);
+    splitk = max(1, min(min(1024, (P + 4 * BK - 1) / (4 * BK)), (148 * 4 + tiles - 1) / tiles));
+  }
+  DenseLoader a{dy, 1, Co, 0, 0, Co, P};          // A(co, pix) = dy[pix*Co + co]
+  Im2colLoader<false> b{x, g};                    // B(tap, pix)
+  Epilogue e{dw, Kt, 0, 0, nullptr, nullptr, nullptr, 1.f, 0, 2, 0.f, 0};
+  return launch_gemm_simt(a, b, Co, Kt, P, e, 1, 1, splitk, stream);
+}
+
+namespace {
+__global__ void krsc_to_crsk_kernel(const float* __restrict__ w, float* __restrict__ wt,
+                                    int Co, int RS, int C) {
+  int64_t n = (int64_t)Co * RS * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int co = (int)(i % Co);
+    int64_t t = i / Co;
+    int rs = (int)(t % RS);
+    int c = (int)(t / RS);
+    wt[i] = w[((int64_t)co * RS + rs) * C + c];
+  }
+}
+}  // namespace
+
+// wt[c][r][s][co] = w[co][r][s][c]
+MMFN_API int mmfn_filter_krsc_to_crsk(const float* w, float* wt, int Co, int R, int S, int C,
+                                      cudaStream_t stream) {
+  MMFN_CHECK_ARG(w && wt && Co > 0 && R > 0 && S > 0 && C > 0, "filter permute: bad args");
+  int64_t n = (int64_t)Co * R * S * C;
+  int blocks = grid_1d(n, 256);
+  krsc_to_crsk_kernel<<<blocks, 256, 0, stream>>>(w, wt, Co, R * S, C);
+  return mmfn_launch_status("krsc_to_crsk");
+}

@@ -1,0 +1,217 @@
+// Waypoint head: 4-step GRUCell roll-out + Linear(64,2) + cumulative waypoints
+// (model_rad.py:679-693), fused L1 loss (run_steps/phase2_train_net.py:104) and AdamW
+// (phase2_train_net.py:256,:110; torch.optim.AdamW defaults).
+#include "common.cuh"
+
+namespace {
+
+constexpr int HID = 64;
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// block per sample, 64 threads.  saved: (B, steps, 5, 64) = h_prev, r, z, n, gh_n ; xin: (B, steps, 2)
+__global__ void gru_head_fwd_kernel(const float* __restrict__ z0, const float* __restrict__ target,
+                                    const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                    const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                    const float* __restrict__ w_out, const float* __restrict__ b_out,
+                                    int steps, float* __restrict__ pred, float* __restrict__ saved,
+                                    float* __restrict__ xin_saved, float* __restrict__ hlast) {
+  __shared__ float h[HID], hn[HID];
+  __shared__ float x[2], xin[2];
+  int b = blockIdx.x, j = threadIdx.x;
+  h[j] = z0[b * HID + j];
+  if (j < 2) x[j] = 0.f;
+  __syncthreads();
+  for (int t = 0; t < steps; ++t) {
+    if (j < 2) { xin[j] = x[j] + target[b * 2 + j]; xin_saved[(b * steps + t) * 2 + j] = xin[j]; }
+    __syncthreads();
+    float gi[3], gh[3];
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      int row = g * HID + j;
+      gi[g] = w_ih[row * 2] * xin[0] + w_ih[row * 2 + 1] * xin[1] + b_ih[row];
+      float a = b_hh[row];
+      const float* wr = w_hh + row * HID;
+      for (int k = 0; k < HID; ++k) a += wr[k] * h[k];
+      gh[g] = a;
+    }
+    float r = sigmoidf_(gi[0] + gh[0]);
+    float zg = sigmoidf_(gi[1] + gh[1]);
+    float n = tanhf(gi[2] + r * gh[2]);
+    float hnew = (1.f - zg) * n + zg * h[j];
+    float* sv = saved + ((int64_t)(b * steps + t) * 5) * HID;
+    sv[j] = h[j]; sv[HID + j] = r; sv[2 * HID + j] = zg; sv[3 * HID + j] = n; sv[4 * HID + j] = gh[2];
+    hn[j] = hnew;
+    __syncthreads();
+    h[j] = hnew;
+    if (j < 2) {
+      float d = b_out[j];
+      for (int k = 0; k < HID; ++k) d += w_out[j * HID + k] * hn[k];
+      x[j] += d;
+      pred[(b * steps + t) * 2 + j] = x[j];
+    }
+    __syncthreads();
+  }
+  hlast[b * HID + j] = h[j];
+}
+
+__global__ void gru_head_bwd_kernel(const float* __restrict__ dpred, const float* __restrict__ saved,
+                                    const float* __restrict__ xin_saved, const float* __restrict__ hlast,
+                                    const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                                    const float* __restrict__ w_out, int steps,
+                                    float* __restrict__ dz0, float* __restrict__ dw_ih, float* __restrict__ dw_hh,
+                                    float* __restrict__ db_ih, float* __restrict__ db_hh,
+                                    float* __restrict__ dw_out, float* __restrict__ db_out) {
+  __shared__ float dgi[3 * HID], dgh[3 * HID], hprev[HID];
+  __shared__ float gx[2], dxin[2], dxc[2];
+  __shared__ float red[2][HID];
+  int b = blockIdx.x, j = threadIdx.x;
+  float dh = 0.f;
+  if (j < 2) dxc[j] = 0.f;
+  __syncthreads();
+  for (int t = steps - 1; t >= 0; --t) {
+    const float* sv = saved + ((int64_t)(b * steps + t) * 5) * HID;
+    float hp = sv[j], r = sv[HID + j], zg = sv[2 * HID + j], n = sv[3 * HID + j], ghn = sv[4 * HID + j];
+    // h' of this step = h_prev of next step (or hlast)
+    float hnew = (t == steps - 1) ? hlast[b * HID + j] : saved[((int64_t)(b * steps + t + 1) * 5) * HID + j];
+    if (j < 2) gx[j] = dpred[(b * steps + t) * 2 + j] + dxc[j];
+    hprev[j] = hp;
+    __syncthreads();
+    // output layer
+    atomicAdd(dw_out + j, gx[0] * hnew);
+    atomicAdd(dw_out + HID + j, gx[1] * hnew);
+    if (j < 2) atomicAdd(db_out + j, gx[j]);
+    float dhn = dh + w_out[j] * gx[0] + w_out[HID + j] * gx[1];
+    float dn = dhn * (1.f - zg), dzg = dhn * (hp - n);
+    float dhp = dhn * zg;
+    float dan = dn * (1.f - n * n);
+    float dr = dan * ghn;
+    float daz = dzg * zg * (1.f - zg);
+    float dar = dr * r * (1.f - r);
+    dgi[j] = dar; dgi[HID + j] = daz; dgi[2 * HID + j] = dan;
+    dgh[j] = dar; dgh[HID + j] = daz; dgh[2 * HID + j] = dan * r;
+    const float xi0 = xin_saved[(b * steps + t) * 2], xi1 = xin_saved[(b * steps + t) * 2 + 1];
+    __syncthreads();
+    // parameter gradients
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      int row = g * HID + j;
+      atomicAdd(dw_ih + row * 2, dgi[row] * xi0);
+      atomicAdd(dw_ih + row * 2 + 1, dgi[row] * xi1);
+      atomicAdd(db_ih + row, dgi[row]);
+      atomicAdd(db_hh + row, dgh[row]);
+    }
+    for (int row = 0; row < 3 * HID; ++row) atomicAdd(dw_hh + row * HID + j, dgh[row] * hprev[j]);
+    // dh_prev += W_hh^T dgh ; dx_in = W_ih^T dgi
+    float acc = dhp;
+    for (int row = 0; row < 3 * HID; ++row) acc += w_hh[row * HID + j] * dgh[row];
+    float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+      int row = g * HID + j;
+      p0 += w_ih[row * 2] * dgi[row];
+      p1 += w_ih[row * 2 + 1] * dgi[row];
+    }
+    red[0][j] = p0; red[1][j] = p1;
+    __syncthreads();
+    if (j < 2) {
+      float s = 0.f;
+      for (int k = 0; k < HID; ++k) s += red[j][k];
+      dxin[j] = s;
+      dxc[j] = gx[j] + s;
+    }
+    dh = acc;
+    __syncthreads();
+  }
+  dz0[b * HID + j] = dh;
+}
+
+// loss = mean |pred - gt| ; dpred = sign(pred - gt) * gscale / n
+__global__ void l1_loss_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int n,
+                               float* __restrict__ loss, float* __restrict__ dpred, float gscale) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float d = pred[i] - gt[i];
+    s += fabsf(d);
+    if (dpred) dpred[i] = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * gscale / (float)n;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) *loss = s / (float)n;
+}
+
+// state: [0] = step count (as float), [1] = 1-beta1^t, [2] = 1-beta2^t
+__global__ void adamw_advance_kernel(float* state, float beta1, float beta2) {
+  float t = state[0] + 1.f;
+  state[0] = t;
+  state[1] = (float)(1.0 - pow((double)beta1, (double)t));
+  state[2] = (float)(1.0 - pow((double)beta2, (double)t));
+}
+
+__global__ void adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                             float4* __restrict__ v, int64_t n4, float lr, float beta1, float beta2, float eps,
+                             float wd, const float* __restrict__ state, float gscale) {
+  float bc1 = state[1], bc2 = state[2];
+  float step_size = lr / bc1, rbc2 = 1.0f / sqrtf(bc2), decay = 1.0f - lr * wd;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+    float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float gr = ga[k] * gscale;
+      float pk = pa[k] * decay;
+      ma[k] = beta1 * ma[k] + (1.f - beta1) * gr;
+      va[k] = beta2 * va[k] + (1.f - beta2) * gr * gr;
+      float denom = sqrtf(va[k]) * rbc2 + eps;
+      pa[k] = pk - step_size * (ma[k] / denom);
+    }
+    p[i] = pp; m[i] = mm; v[i] = vv;
+  }
+}
+
+}  // namespace
+
+MMFN_API int mmfn_gru_head_fwd(const float* z0, const float* target, const float* w_ih, const float* w_hh,
+                               const float* b_ih, const float* b_hh, const float* w_out, const float* b_out,
+                               int B, int steps, float* pred, float* saved, float* xin_saved, float* hlast,
+                               cudaStream_t stream) {
+  MMFN_CHECK_ARG(z0 && target && w_ih && w_hh && b_ih && b_hh && w_out && b_out && pred && saved && xin_saved && hlast,
+                 "gru_head_fwd: null pointer");
+  MMFN_CHECK_ARG(B > 0 && steps > 0, "gru_head_fwd: bad sizes");
+  gru_head_fwd_kernel<<<B, HID, 0, stream>>>(z0, target, w_ih, w_hh, b_ih, b_hh, w_out, b_out, steps, pred, saved, xin_saved, hlast);
+  return mmfn_launch_status("gru_head_fwd");
+}
+
+// All parameter gradients are accumulated (atomicAdd).
+MMFN_API int mmfn_gru_head_bwd(const float* dpred, const float* saved, const float* xin_saved, const float* hlast,
+                               const float* w_ih, const float* w_hh, const float* w_out, int B, int steps,
+                               float* dz0, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh,
+                               float* dw_out, float* db_out, cudaStream_t stream) {
+  MMFN_CHECK_ARG(dpred && saved && xin_saved && hlast && w_ih && w_hh && w_out && dz0 && dw_ih && dw_hh && db_ih && db_hh &&
+                 dw_out && db_out, "gru_head_bwd: null pointer");
+  MMFN_CHECK_ARG(B > 0 && steps > 0, "gru_head_bwd: bad sizes");
+  gru_head_bwd_kernel<<<B, HID, 0, stream>>>(dpred, saved, xin_saved, hlast, w_ih, w_hh, w_out, steps, dz0, dw_ih, dw_hh,
+                                             db_ih, db_hh, dw_out, db_out);
+  return mmfn_launch_status("gru_head_bwd");
+}
+
+// loss (1 float, device) = mean|pred-gt| over n; dpred (nullable) = d(loss*gscale)/dpred.
+MMFN_API int mmfn_l1_loss(const float* pred, const float* gt, int n, float* loss, float* dpred, float gscale,
+                          cudaStream_t stream) {
+  MMFN_CHECK_ARG(pred && gt && loss && n > 0, "l1_loss: bad args");
+  l1_loss_kernel<<<1, 256, 0, stream>>>(pred, gt, n, loss, dpred, gscale);
+  return mmfn_launch_status("l1_loss");
+}
+
+// state: 3 device floats {t, 1-beta1^t, 1-beta2^t}; advanced on device so a captured graph replays correctly.
+MMFN_API int mmfn_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, float* state, float grad_scale,
+                             cudaStream_t stream) {
+  MMFN_CHECK_ARG(p && g && m && v && state && n >= 0 && n % 4 == 0, "adamw: n must be a multiple of 4");
+  MMFN_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adamw: buffers must be 16B aligned");
+  adamw_advance_kernel<<<1, 1, 0, stream>>>(state, beta1, beta2);
+  if (n > 0)
+    adamw_kernel<<<grid_1d(n / 4, 256), 256, 0, stream>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v, n / 4, lr,
+                                                           beta1, beta2, eps, weight_decay, state, grad_scale);
+  return mmfn_launch_status("adamw");
+}

@@ -1,0 +1,229 @@
+// Small HBM-bound helpers: bias-gradient column sums, ELU, dropout, VectorNet polyline
+// vectorisation + segment max-pool (model_rad.py:270-283, :369-382), the radar
+// log-softmax with the reference's (8,8,512)->transpose(1,3) relayout (:883-884).
+#include "common.cuh"
+
+namespace {
+
+// out[n] (+)= sum_m x[m*ld + n];  blockDim (32, 8), grid.x over column groups, grid.y over row slabs
+__global__ void colsum_kernel(const float* __restrict__ x, int64_t ld, int64_t M, int N, float* __restrict__ out) {
+  __shared__ float s[8][33];
+  int n = blockIdx.x * 32 + threadIdx.x;
+  int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
+  int64_t r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float a = 0.f;
+  if (n < N)
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) a += __ldg(x + r * ld + n);
+  s[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) a += s[i][threadIdx.x];
+    atomicAdd(out + n, a);
+  }
+}
+
+__global__ void elu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    y[i] = v > 0.f ? v : expm1f(v);
+  }
+}
+// dx = dy * (y > 0 ? 1 : y + 1)  (alpha = 1; uses the forward OUTPUT y)
+__global__ void elu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = y[i];
+    dx[i] = dy[i] * (v > 0.f ? 1.f : v + 1.f);
+  }
+}
+
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float p, uint64_t seed) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = x[i] * mmfn_dropout_scale(p, seed, (uint64_t)i);
+}
+
+__global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, float a, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] += a * x[i];
+}
+
+// lane (G, P, F>=5) -> vec (G*(P-1), 7) = [x_i, y_i, x_{i+1}, y_{i+1}, attr_{i+1}[0..2]]
+__global__ void lane_to_vector_kernel(const float* __restrict__ lane, float* __restrict__ vec, int64_t G, int P) {
+  int V = P - 1;
+  int64_t n = G * V;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t g = i / V;
+    int v = (int)(i - g * V);
+    const float* a = lane + (g * P + v) * 5;
+    const float* b = a + 5;
+    float* o = vec + i * 7;
+    o[0] = a[0]; o[1] = a[1]; o[2] = b[0]; o[3] = b[1]; o[4] = b[2]; o[5] = b[3]; o[6] = b[4];
+  }
+}
+
+// y[g,v,:C] = x[g,v,:], y[g,v,C:] = max_v x[g,v,:]; arg[g,c] = first argmax
+__global__ void subgraph_pool_fwd_kernel(const float* __restrict__ x, int64_t G, int V, int C,
+                                         float* __restrict__ y, int* __restrict__ arg) {
+  int64_t n = G * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t g = i / C;
+    int c = (int)(i - g * C);
+    const float* xr = x + g * V * C + c;
+    float best = xr[0];
+    int bi = 0;
+    for (int v = 1; v < V; ++v) { float t = xr[(int64_t)v * C]; if (t > best || t != t) { best = t; bi = v; } }
+    arg[i] = bi;
+    float* yr = y + g * V * 2 * C + c;
+    for (int v = 0; v < V; ++v) { yr[(int64_t)v * 2 * C] = xr[(int64_t)v * C]; yr[(int64_t)v * 2 * C + C] = best; }
+  }
+}
+__global__ void subgraph_pool_bwd_kernel(const float* __restrict__ dy, const int* __restrict__ arg,
+                                         int64_t G, int V, int C, float* __restrict__ dx) {
+  int64_t n = G * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t g = i / C;
+    int c = (int)(i - g * C);
+    const float* gr = dy + g * V * 2 * C + c;
+    float s = 0.f;
+    for (int v = 0; v < V; ++v) s += gr[(int64_t)v * 2 * C + C];
+    int a = arg[i];
+    float* dr = dx + g * V * C + c;
+    for (int v = 0; v < V; ++v) dr[(int64_t)v * C] = gr[(int64_t)v * 2 * C] + (v == a ? s : 0.f);
+  }
+}
+__global__ void segmax_fwd_kernel(const float* __restrict__ x, int64_t G, int V, int C,
+                                  float* __restrict__ out, int* __restrict__ arg) {
+  int64_t n = G * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t g = i / C;
+    int c = (int)(i - g * C);
+    const float* xr = x + g * V * C + c;
+    float best = xr[0];
+    int bi = 0;
+    for (int v = 1; v < V; ++v) { float t = xr[(int64_t)v * C]; if (t > best || t != t) { best = t; bi = v; } }
+    arg[i] = bi;
+    out[i] = best;
+  }
+}
+__global__ void segmax_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ arg,
+                                  int64_t G, int V, int C, float* __restrict__ dx) {
+  int64_t n = G * V * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int v = (int)(t % V);
+    int64_t g = t / V;
+    dx[i] = arg[g * C + c] == v ? dout[g * C + c] : 0.f;
+  }
+}
+
+// y[b, j*8+i, :] = log_softmax(v[b, i*8+j, :]) over C channels; block per (b, row)
+__global__ void radar_logsoftmax_fwd_kernel(const float* __restrict__ v, float* __restrict__ y, int C) {
+  __shared__ float red[32];
+  int b = blockIdx.x >> 6, r = blockIdx.x & 63;
+  int i = r >> 3, j = r & 7;
+  const float* src = v + ((int64_t)b * 64 + r) * C;
+  float* dst = y + ((int64_t)b * 64 + j * 8 + i) * C;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, src[c]);
+  mx = block_max(mx, red);
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s += expf(src[c] - mx);
+  s = block_sum(s, red);
+  float lse = mx + logf(s);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) dst[c] = src[c] - lse;
+}
+// dv[b, i*8+j, c] = dy[b, j*8+i, c] - exp(y[b, j*8+i, c]) * sum_c dy
+__global__ void radar_logsoftmax_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                            float* __restrict__ dv, int C) {
+  __shared__ float red[32];
+  int b = blockIdx.x >> 6, r = blockIdx.x & 63;
+  int i = r >> 3, j = r & 7;
+  const float* g = dy + ((int64_t)b * 64 + j * 8 + i) * C;
+  const float* yy = y + ((int64_t)b * 64 + j * 8 + i) * C;
+  float* dst = dv + ((int64_t)b * 64 + r) * C;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s += g[c];
+  s = block_sum(s, red);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) dst[c] = g[c] - expf(yy[c]) * s;
+}
+
+}  // namespace
+
+// out[n] += sum_m x[m*ld + n]   (out must be initialised by the caller)
+MMFN_API int mmfn_colsum_f32(const float* x, int64_t ld, int64_t M, int N, float* out, cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && out && M >= 0 && N > 0 && ld >= N, "colsum: bad args");
+  if (M == 0) return 0;
+  int64_t slabs = ceil_div64(M, 256);
+  if (slabs > 1024) slabs = 1024;
+  dim3 grid((N + 31) / 32, (unsigned)slabs);
+  colsum_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, ld, M, N, out);
+  return mmfn_launch_status("colsum");
+}
+
+MMFN_API int mmfn_elu_fwd(const float* x, float* y, int64_t n, cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && y && n >= 0, "elu_fwd: bad args");
+  if (n == 0) return 0;
+  elu_fwd_kernel<<<grid_1d(n, 256), 256, 0, stream>>>(x, y, n);
+  return mmfn_launch_status("elu_fwd");
+}
+MMFN_API int mmfn_elu_bwd(const float* dy, const float* y, float* dx, int64_t n, cudaStream_t stream) {
+  MMFN_CHECK_ARG(dy && y && dx && n >= 0, "elu_bwd: bad args");
+  if (n == 0) return 0;
+  elu_bwd_kernel<<<grid_1d(n, 256), 256, 0, stream>>>(dy, y, dx, n);
+  return mmfn_launch_status("elu_bwd");
+}
+// y = x * keep_scale(p, seed, index); same call regenerates the mask in backward.
+MMFN_API int mmfn_dropout_f32(const float* x, float* y, int64_t n, float p, uint64_t seed, cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && y && n >= 0 && p >= 0.f && p < 1.f, "dropout: bad args");
+  if (n == 0) return 0;
+  dropout_kernel<<<grid_1d(n, 256), 256, 0, stream>>>(x, y, n, p, seed);
+  return mmfn_launch_status("dropout");
+}
+MMFN_API int mmfn_axpy_f32(const float* x, float* y, float a, int64_t n, cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && y && n >= 0, "axpy: bad args");
+  if (n == 0) return 0;
+  axpy_kernel<<<grid_1d(n, 256), 256, 0, stream>>>(x, y, a, n);
+  return mmfn_launch_status("axpy");
+}
+MMFN_API int mmfn_lane_to_vector(const float* lane, float* vec, int64_t G, int P, cudaStream_t stream) {
+  MMFN_CHECK_ARG(lane && vec && G >= 0 && P >= 2, "lane_to_vector: bad args");
+  if (G == 0) return 0;
+  lane_to_vector_kernel<<<grid_1d(G * (P - 1), 256), 256, 0, stream>>>(lane, vec, G, P);
+  return mmfn_launch_status("lane_to_vector");
+}
+MMFN_API int mmfn_subgraph_pool_fwd(const float* x, int64_t G, int V, int C, float* y, int* arg, cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && y && arg && G >= 0 && V > 0 && C > 0, "subgraph_pool_fwd: bad args");
+  if (G == 0) return 0;
+  subgraph_pool_fwd_kernel<<<grid_1d(G * C, 256), 256, 0, stream>>>(x, G, V, C, y, arg);
+  return mmfn_launch_status("subgraph_pool_fwd");
+}
+MMFN_API int mmfn_subgraph_pool_bwd(const float* dy, const int* arg, int64_t G, int V, int C, float* dx, cudaStream_t stream) {
+  MMFN_CHECK_ARG(dy && dx && arg && G >= 0 && V > 0 && C > 0, "subgraph_pool_bwd: bad args");
+  if (G == 0) return 0;
+  subgraph_pool_bwd_kernel<<<grid_1d(G * C, 256), 256, 0, stream>>>(dy, arg, G, V, C, dx);
+  return mmfn_launch_status("subgraph_pool_bwd");
+}
+MMFN_API int mmfn_segmax_fwd(const float* x, int64_t G, int V, int C, float* out, int* arg, cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && out && arg && G >= 0 && V > 0 && C > 0, "segmax_fwd: bad args");
+  if (G == 0) return 0;
+  segmax_fwd_kernel<<<grid_1d(G * C, 256), 256, 0, stream>>>(x, G, V, C, out, arg);
+  return mmfn_launch_status("segmax_fwd");
+}
+MMFN_API int mmfn_segmax_bwd(const float* dout, const int* arg, int64_t G, int V, int C, float* dx, cudaStream_t stream) {
+  MMFN_CHECK_ARG(dout && dx && arg && G >= 0 && V > 0 && C > 0, "segmax_bwd: bad args");
+  if (G == 0) return 0;
+  segmax_bwd_kernel<<<grid_1d(G * V * C, 256), 256, 0, stream>>>(dout, arg, G, V, C, dx);
+  return mmfn_launch_status("segmax_bwd");
+}
+// v: (B, 64, C) rows r = i*8+j ; y: NHWC (B, 8, 8, C) with y[b, j, i, :] = log_softmax(v[b, r, :])
+MMFN_API int mmfn_radar_logsoftmax_fwd(const float* v, float* y, int B, int C, cudaStream_t stream) {
+  MMFN_CHECK_ARG(v && y && B > 0 && C > 0, "radar_logsoftmax_fwd: bad args");
+  radar_logsoftmax_fwd_kernel<<<B * 64, 128, 0, stream>>>(v, y, C);
+  return mmfn_launch_status("radar_logsoftmax_fwd");
+}
+MMFN_API int mmfn_radar_logsoftmax_bwd(const float* dy, const float* y, float* dv, int B, int C, cudaStream_t stream) {
+  MMFN_CHECK_ARG(dy && y && dv && B > 0 && C > 0, "radar_logsoftmax_bwd: bad args");
+  radar_logsoftmax_bwd_kernel<<<B * 64, 128, 0, stream>>>(dy, y, dv, C);
+  return mmfn_launch_status("radar_logsoftmax_bwd");
+}

@@ -1,0 +1,303 @@
+// Train-mode BatchNorm2d over NHWC row matrices (torchvision BasicBlock BNs; call sites
+// model_rad.py:512-525, :542-544, :560-562, :577-579) and LayerNorm (+ReLU/GELU) rows
+// (model_rad.py:117-118, :162, :253, :336, :346, :353).  HBM-bound kernels.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ BatchNorm
+// blockDim = (32 channels, 8 row lanes); block covers ROWS_PER_BLOCK rows of one 32-channel group.
+constexpr int BN_ROWS_PER_BLOCK = 512;
+
+__global__ void bn_partial_kernel(const float* __restrict__ x, int64_t M, int C, double* __restrict__ ws) {
+  __shared__ double s1[8][33], s2[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  int64_t r0 = (int64_t)blockIdx.y * BN_ROWS_PER_BLOCK;
+  int64_t r1 = min(M, r0 + BN_ROWS_PER_BLOCK);
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      float v = __ldg(x + r * C + c);
+      a += v;
+      b += (double)v * v;
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
+    atomicAdd(ws + c, a);
+    atomicAdd(ws + C + c, b);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ ws, int64_t M, int C, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ rstd,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double m = ws[c] / (double)M;
+  double var = ws[C + c] / (double)M - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)m;
+  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
+    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+  }
+}
+
+__global__ void bn_apply_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n4, int C4,
+                                const float4* __restrict__ mean, const float4* __restrict__ rstd,
+                                const float4* __restrict__ gamma, const float4* __restrict__ beta,
+                                const float4* __restrict__ res, int relu) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4);
+    float4 v = __ldg(x + i), m = __ldg(mean + c), r = __ldg(rstd + c), g = __ldg(gamma + c), b = __ldg(beta + c);
+    float4 o;
+    o.x = (v.x - m.x) * r.x * g.x + b.x;
+    o.y = (v.y - m.y) * r.y * g.y + b.y;
+    o.z = (v.z - m.z) * r.z * g.z + b.z;
+    o.w = (v.w - m.w) * r.w * g.w + b.w;
+    if (res) { float4 q = __ldg(res + i); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    y[i] = o;
+  }
+}
+
+// sums over rows of dy' and dy'*xhat where dy' = dy * (y > 0) when a ReLU followed.
+__global__ void bn_bwd_partial_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                      const float* __restrict__ yout, const float* __restrict__ mean,
+                                      const float* __restrict__ rstd, int64_t M, int C, double* __restrict__ ws) {
+  __shared__ double s1[8][33], s2[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  int64_t r0 = (int64_t)blockIdx.y * BN_ROWS_PER_BLOCK;
+  int64_t r1 = min(M, r0 + BN_ROWS_PER_BLOCK);
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    float m = mean[c], rs = rstd[c];
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      float g = __ldg(dy + r * C + c);
+      if (yout && !(__ldg(yout + r * C + c) > 0.f)) g = 0.f;
+      float xh = (__ldg(x + r * C + c) - m) * rs;
+      a += g;
+      b += (double)g * xh;
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
+    atomicAdd(ws + c, a);
+    atomicAdd(ws + C + c, b);
+  }
+}
+
+__global__ void bn_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                 const float* __restrict__ yout, const float* __restrict__ mean,
+                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                 const double* __restrict__ ws, int64_t M, int C,
+                                 float* __restrict__ dx, float* __restrict__ dres,
+                                 float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  int64_t n = M * C;
+  double invM = 1.0 / (double)M;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    float g = __ldg(dy + i);
+    if (yout && !(__ldg(yout + i) > 0.f)) g = 0.f;
+    float rs = rstd[c];
+    float xh = (__ldg(x + i) - mean[c]) * rs;
+    float sdy = (float)(ws[c] * invM), sdx = (float)(ws[C + c] * invM);
+    dx[i] = gamma[c] * rs * (g - sdy - xh * sdx);
+    if (dres) dres[i] = g;
+  }
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      dbeta[c] += (float)ws[c];
+      dgamma[c] += (float)ws[C + c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm
+__device__ __forceinline__ float act_fwd(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+  return v;
+}
+__device__ __forceinline__ float act_grad(float v, int act) {
+  if (act == 1) return v > 0.f ? 1.f : 0.f;
+  if (act == 2) {
+    float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752440f));
+    float pdf = 0.39894228040143267794f * expf(-0.5f * v * v);
+    return cdf + v * pdf;
+  }
+  return 1.f;
+}
+
+// one warp per row
+__global__ void ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float* __restrict__ y,
+                              float* __restrict__ mean, float* __restrict__ rstd,
+                              int64_t M, int C, float eps, int act) {
+  int lane = threadIdx.x & 31;
+  int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* xr = x + row * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+  float mu = warp_sum(s) / (float)C;
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) { float d = xr[c] - mu; v += d * d; }
+  float rs = rsqrtf(warp_sum(v) / (float)C + eps);
+  if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+  float* yr = y + row * C;
+  for (int c = lane; c < C; c += 32) yr[c] = act_fwd((xr[c] - mu) * rs * gamma[c] + beta[c], act);
+}
+
+// dx = LN'(dy * act'(ln)) (+ dres); dgamma/dbeta accumulated with atomics.
+template <int MAXC32>
+__global__ void ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                              const float* __restrict__ mean, const float* __restrict__ rstd,
+                              const float* __restrict__ dres, float* __restrict__ dx,
+                              float* __restrict__ dgamma, float* __restrict__ dbeta,
+                              int64_t M, int C, int act) {
+  extern __shared__ float sh[];  // 2*C floats
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  float pg[MAXC32], pb[MAXC32];
+#pragma unroll
+  for (int j = 0; j < MAXC32; ++j) { pg[j] = 0.f; pb[j] = 0.f; }
+  for (int64_t row = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); row < M; row += (int64_t)gridDim.x * wpb) {
+    const float* xr = x + row * C;
+    const float* gr = dy + row * C;
+    float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+    float gv[MAXC32], xh[MAXC32];
+#pragma unroll
+    for (int j = 0; j < MAXC32; ++j) {
+      int c = lane + 32 * j;
+      gv[j] = 0.f; xh[j] = 0.f;
+      if (c < C) {
+        xh[j] = (xr[c] - mu) * rs;
+        float g = gr[c];
+        if (act) g *= act_grad(xh[j] * gamma[c] + beta[c], act);
+        pg[j] += g * xh[j];
+        pb[j] += g;
+        gv[j] = g * gamma[c];
+        s1 += gv[j];
+        s2 += gv[j] * xh[j];
+      }
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+    for (int j = 0; j < MAXC32; ++j) {
+      int c = lane + 32 * j;
+      if (c < C) {
+        float d = rs * (gv[j] - s1 - xh[j] * s2);
+        if (dres) d += dres[row * C + c];
+        dx[row * C + c] = d;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MAXC32; ++j) {
+    int c = lane + 32 * j;
+    if (c < C) { atomicAdd(&sh[c], pg[j]); atomicAdd(&sh[C + c], pb[j]); }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(dgamma + c, sh[c]);
+    atomicAdd(dbeta + c, sh[C + c]);
+  }
+}
+
+}  // namespace
+
+// x,y: (M,C) NHWC rows. ws: 2*C doubles of scratch. Writes mean/rstd (C each) and, when
+// running_* are non-null, the momentum update with the unbiased variance.
+MMFN_API int mmfn_bn_train_fwd(const float* x, float* y, int64_t M, int C,
+                               const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, float momentum, float eps,
+                               float* mean, float* rstd, const float* res, int relu,
+                               double* ws, cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && y && gamma && beta && mean && rstd && ws, "bn_fwd: null pointer");
+  MMFN_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "bn_fwd: C must be a positive multiple of 4");
+  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, stream);
+  dim3 grid((C + 31) / 32, (unsigned)ceil_div64(M, BN_ROWS_PER_BLOCK));
+  bn_partial_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, M, C, ws);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws, M, C, eps, momentum, mean, rstd, running_mean, running_var);
+  int64_t n4 = M * C / 4;
+  bn_apply_kernel<<<grid_1d(n4, 256), 256, 0, stream>>>((const float4*)x, (float4*)y, n4, C / 4,
+      (const float4*)mean, (const float4*)rstd, (const float4*)gamma, (const float4*)beta, (const float4*)res, relu);
+  return mmfn_launch_status("bn_train_fwd");
+}
+
+// yout: post-ReLU output of the forward (null when no ReLU followed). dres (nullable)
+// receives the ReLU-masked dy for the residual branch.  dgamma/dbeta are accumulated.
+MMFN_API int mmfn_bn_train_bwd(const float* dy, const float* x, const float* yout,
+                               const float* mean, const float* rstd, const float* gamma,
+                               int64_t M, int C, float* dx, float* dres, float* dgamma, float* dbeta,
+                               double* ws, cudaStream_t stream) {
+  MMFN_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && ws, "bn_bwd: null pointer");
+  MMFN_CHECK_ARG(M > 0 && C > 0, "bn_bwd: bad sizes");
+  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, stream);
+  dim3 grid((C + 31) / 32, (unsigned)ceil_div64(M, BN_ROWS_PER_BLOCK));
+  bn_bwd_partial_kernel<<<grid, dim3(32, 8), 0, stream>>>(dy, x, yout, mean, rstd, M, C, ws);
+  bn_bwd_dx_kernel<<<grid_1d(M * C, 256), 256, 0, stream>>>(dy, x, yout, mean, rstd, gamma, ws, M, C, dx, dres, dgamma, dbeta);
+  return mmfn_launch_status("bn_train_bwd");
+}
+
+namespace {
+__global__ void bn_eval_stats_kernel(const float* rm, const float* rv, float eps, float* mean, float* rstd, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) { mean[c] = rm[c]; rstd[c] = 1.0f / sqrtf(rv[c] + eps); }
+}
+}  // namespace
+
+// Inference-mode BN: y = (x - running_mean) / sqrt(running_var + eps) * gamma + beta (+res, relu).
+MMFN_API int mmfn_bn_eval_fwd(const float* x, float* y, int64_t M, int C, const float* gamma, const float* beta,
+                              const float* running_mean, const float* running_var, float eps,
+                              float* mean, float* rstd, const float* res, int relu, cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && y && gamma && beta && running_mean && running_var && mean && rstd, "bn_eval: null pointer");
+  MMFN_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "bn_eval: C must be a positive multiple of 4");
+  bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, stream>>>(running_mean, running_var, eps, mean, rstd, C);
+  int64_t n4 = M * C / 4;
+  bn_apply_kernel<<<grid_1d(n4, 256), 256, 0, stream>>>((const float4*)x, (float4*)y, n4, C / 4,
+      (const float4*)mean, (const float4*)rstd, (const float4*)gamma, (const float4*)beta, (const float4*)res, relu);
+  return mmfn_launch_status("bn_eval_fwd");
+}
+
+// act: 0 none, 1 ReLU, 2 exact GELU applied to the LayerNorm output.
+MMFN_API int mmfn_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y,
+                                float* mean, float* rstd, int64_t M, int C, float eps, int act,
+                                cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && gamma && beta && y && mean && rstd, "ln_fwd: null pointer");
+  MMFN_CHECK_ARG(M >= 0 && C > 0, "ln_fwd: bad sizes");
+  if (M == 0) return 0;
+  ln_fwd_kernel<<<(unsigned)ceil_div64(M, 8), 256, 0, stream>>>(x, gamma, beta, y, mean, rstd, M, C, eps, act);
+  return mmfn_launch_status("layernorm_fwd");
+}
+
+MMFN_API int mmfn_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* beta,
+                                const float* mean, const float* rstd, const float* dres, float* dx,
+                                float* dgamma, float* dbeta, int64_t M, int C, int act, cudaStream_t stream) {
+  MMFN_CHECK_ARG(dy && x && gamma && beta && mean && rstd && dx && dgamma && dbeta, "ln_bwd: null pointer");
+  MMFN_CHECK_ARG(M >= 0 && C > 0 && C <= 512, "ln_bwd: C must be in (0, 512]");
+  if (M == 0) return 0;
+  int64_t nb = ceil_div64(M, 8); int blocks = (int)(nb < 148 * 4 ? nb : 148 * 4);
+  size_t smem = sizeof(float) * 2 * C;
+  if (C <= 128)
+    ln_bwd_kernel<4><<<blocks, 256, smem, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, dgamma, dbeta, M, C, act);
+  else
+    ln_bwd_kernel<16><<<blocks, 256, smem, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, dgamma, dbeta, M, C, act);
+  return mmfn_launch_status("layernorm_bwd");
+}

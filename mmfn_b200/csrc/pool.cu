@@ -1,0 +1,347 @@
+// Layout / pooling / resampling kernels around the fusion transformers (HBM-bound):
+//   NCHW->NHWC (+ImageNet normalise, model_rad.py:33-44), MaxPool 3x3/2 (:515,:521),
+//   AdaptiveAvgPool(8,8) + token assembly (+pos_emb +vel_emb +dropout, :224-236, :530-533),
+//   bilinear align_corners upsample + residual add (:534-539 ...), final pool+sum (:590-609).
+#include "common.cuh"
+
+namespace {
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                    int B, int C, int64_t HW, const float* __restrict__ mean,
+                                    const float* __restrict__ stdv) {
+  int64_t n = (int64_t)B * HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = i / HW, p = i - b * HW;
+    for (int c = 0; c < C; ++c) {
+      float v = __ldg(x + (b * C + c) * HW + p);
+      if (mean) v = (v - mean[c]) / stdv[c];
+      y[i * C + c] = v;
+    }
+  }
+}
+
+// tiled batched transpose: out[b][c][r] = in[b][r][c]
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc) {
+  __shared__ float t[32][33];
+  const float* ib = in + (int64_t)blockIdx.z * R * Cc;
+  float* ob = out + (int64_t)blockIdx.z * R * Cc;
+  int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < R && c < Cc) t[j][threadIdx.x] = ib[(int64_t)r * Cc + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) ob[(int64_t)c * R + r] = t[threadIdx.x][j];
+  }
+}
+
+__global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ idx,
+                                   int B, int H, int W, int C, int Ho, int Wo) {
+  int64_t n = (int64_t)B * Ho * Wo * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int wo = (int)(t % Wo); t /= Wo;
+    int ho = (int)(t % Ho);
+    int b = (int)(t / Ho);
+    float best = -INFINITY;
+    int bi = -1;
+    for (int r = 0; r < 3; ++r) {
+      int h = ho * 2 - 1 + r;
+      if (h < 0 || h >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        int w = wo * 2 - 1 + s;
+        if (w < 0 || w >= W) continue;
+        float v = __ldg(x + (((int64_t)b * H + h) * W + w) * C + c);
+        if (bi < 0 || v > best || v != v) { best = v; bi = r * 3 + s; }
+      }
+    }
+    y[i] = best;
+    idx[i] = (uint8_t)bi;
+  }
+}
+
+__global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx,
+                                   float* __restrict__ dx, int B, int H, int W, int C, int Ho, int Wo) {
+  int64_t n = (int64_t)B * H * W * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t = i / C;
+    int w = (int)(t % W); t /= W;
+    int h = (int)(t % H);
+    int b = (int)(t / H);
+    float g = 0.f;
+    int ho_lo = h / 2, ho_hi = (h + 1) / 2;     // windows ho with ho*2-1 <= h <= ho*2+1
+    int wo_lo = w / 2, wo_hi = (w + 1) / 2;
+    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+      if (ho >= Ho) continue;
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        if (wo >= Wo) continue;
+        int tap = (h - (ho * 2 - 1)) * 3 + (w - (wo * 2 - 1));
+        int64_t o = (((int64_t)b * Ho + ho) * Wo + wo) * C + c;
+        if (idx[o] == tap) g += __ldg(dy + o);
+      }
+    }
+    dx[i] = g;
+  }
+}
+
+struct FeatPtrs { const float* p[4]; };
+struct FeatPtrsW { float* p[4]; };
+
+// tokens[b, m*64 + ph*8 + pw, c] = drop(mean_{k x k} feat_m + pos_emb + vel_w*v[b] + vel_b)
+__global__ void tokens_fwd_kernel(FeatPtrs f, int nmod, int B, int H, int W, int C,
+                                  const float* __restrict__ pos, const float* __restrict__ vel_w,
+                                  const float* __restrict__ vel_b, const float* __restrict__ vel,
+                                  float* __restrict__ tok, float drop_p, uint64_t seed) {
+  int T = nmod * 64, kh = H / 8, kw = W / 8;
+  float inv = 1.0f / (float)(kh * kw);
+  int64_t n = (int64_t)B * T * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t2 = i / C;
+    int t = (int)(t2 % T);
+    int b = (int)(t2 / T);
+    int m = t >> 6, ph = (t >> 3) & 7, pw = t & 7;
+    const float* src = f.p[m] + (((int64_t)b * H + ph * kh) * W + pw * kw) * C + c;
+    float s = 0.f;
+    for (int r = 0; r < kh; ++r)
+      for (int q = 0; q < kw; ++q) s += __ldg(src + ((int64_t)r * W + q) * C);
+    float v = s * inv + pos[(int64_t)t * C + c] + vel_w[c] * vel[b] + vel_b[c];
+    tok[i] = v * mmfn_dropout_scale(drop_p, seed, (uint64_t)i);
+  }
+}
+
+// dfeat_m[b,h,w,c] += dtok'[b, m*64 + (h/kh)*8 + w/kw, c] / (kh*kw)   (dtok' = dropout-masked dtok)
+__global__ void tokens_bwd_feat_kernel(FeatPtrsW df, int m, int B, int H, int W, int C, int T,
+                                       const float* __restrict__ dtok, float drop_p, uint64_t seed) {
+  int kh = H / 8, kw = W / 8;
+  float inv = 1.0f / (float)(kh * kw);
+  int64_t n = (int64_t)B * H * W * C;
+  float* dst = df.p[m];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t2 = i / C;
+    int w = (int)(t2 % W); t2 /= W;
+    int h = (int)(t2 % H);
+    int b = (int)(t2 / H);
+    int64_t ti = ((int64_t)b * T + m * 64 + (h / kh) * 8 + (w / kw)) * C + c;
+    dst[i] += __ldg(dtok + ti) * mmfn_dropout_scale(drop_p, seed, (uint64_t)ti) * inv;
+  }
+}
+
+__global__ void tokens_bwd_param_kernel(const float* __restrict__ dtok, const float* __restrict__ vel,
+                                        int B, int T, int C, float* __restrict__ dpos,
+                                        float* __restrict__ dvel_w, float* __restrict__ dvel_b,
+                                        float drop_p, uint64_t seed) {
+  int n = T * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int c = i % C;
+    float s = 0.f, sv = 0.f;
+    for (int b = 0; b < B; ++b) {
+      int64_t ti = (int64_t)b * n + i;
+      float g = __ldg(dtok + ti) * mmfn_dropout_scale(drop_p, seed, (uint64_t)ti);
+      s += g;
+      sv += g * vel[b];
+    }
+    dpos[i] += s;
+    atomicAdd(dvel_b + c, s);
+    atomicAdd(dvel_w + c, sv);
+  }
+}
+
+__device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int& i0, int& i1, float& l0, float& l1) {
+  float src = scale * (float)dst;
+  i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+  l0 = 1.0f - l1;
+}
+
+// out = feat + bilinear_up(tok[:, m*64:(m+1)*64, :] as 8x8xC -> HxW), align_corners=True
+__global__ void upsample_add_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ tok,
+                                        float* __restrict__ out, int m, int T, int B, int H, int W, int C) {
+  float sh = H > 1 ? 7.0f / (float)(H - 1) : 0.f, sw = W > 1 ? 7.0f / (float)(W - 1) : 0.f;
+  int64_t n = (int64_t)B * H * W * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t2 = i / C;
+    int w = (int)(t2 % W); t2 /= W;
+    int h = (int)(t2 % H);
+    int b = (int)(t2 / H);
+    int h0, h1, w0, w1; float a0, a1, b0, b1;
+    bilinear_src(h, sh, 8, h0, h1, a0, a1);
+    bilinear_src(w, sw, 8, w0, w1, b0, b1);
+    const float* tb = tok + ((int64_t)b * T + m * 64) * C + c;
+    float v = a0 * (b0 * __ldg(tb + (h0 * 8 + w0) * C) + b1 * __ldg(tb + (h0 * 8 + w1) * C)) +
+              a1 * (b0 * __ldg(tb + (h1 * 8 + w0) * C) + b1 * __ldg(tb + (h1 * 8 + w1) * C));
+    out[i] = __ldg(feat + i) + v;
+  }
+}
+
+// dtok[b, m*64+p, c] = sum_{h,w} wy(p|h) wx(p|w) dA[b,h,w,c]
+__global__ void upsample_add_bwd_kernel(const float* __restrict__ dA, float* __restrict__ dtok,
+                                        int m, int T, int B, int H, int W, int C) {
+  float sh = H > 1 ? 7.0f / (float)(H - 1) : 0.f, sw = W > 1 ? 7.0f / (float)(W - 1) : 0.f;
+  int64_t n = (int64_t)B * 64 * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t2 = i / C;
+    int p = (int)(t2 % 64);
+    int b = (int)(t2 / 64);
+    int py = p >> 3, px = p & 7;
+    int hlo = 0, hhi = H - 1, wlo = 0, whi = W - 1;
+    if (sh > 0.f) { hlo = max(0, (int)floorf((py - 1) / sh) - 1); hhi = min(H - 1, (int)ceilf((py + 1) / sh) + 1); }
+    if (sw > 0.f) { wlo = max(0, (int)floorf((px - 1) / sw) - 1); whi = min(W - 1, (int)ceilf((px + 1) / sw) + 1); }
+    float acc = 0.f;
+    for (int h = hlo; h <= hhi; ++h) {
+      int h0, h1; float a0, a1;
+      bilinear_src(h, sh, 8, h0, h1, a0, a1);
+      float wy = (h0 == py ? a0 : 0.f) + (h1 == py ? a1 : 0.f);
+      if (wy == 0.f) continue;
+      for (int w = wlo; w <= whi; ++w) {
+        int w0, w1; float b0, b1;
+        bilinear_src(w, sw, 8, w0, w1, b0, b1);
+        float wx = (w0 == px ? b0 : 0.f) + (w1 == px ? b1 : 0.f);
+        if (wx == 0.f) continue;
+        acc += wy * wx * __ldg(dA + (((int64_t)b * H + h) * W + w) * C + c);
+      }
+    }
+    dtok[((int64_t)b * T + m * 64 + p) * C + c] = acc;
+  }
+}
+
+// fused[b,c] = sum_m mean_p (feat_m[b,p,c] + tok[b, m*64+p, c]),  P = 64 positions
+__global__ void pool_sum_fwd_kernel(FeatPtrs f, int nmod, const float* __restrict__ tok, int B, int C,
+                                    float* __restrict__ fused) {
+  int n = B * C, T = nmod * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int c = i % C, b = i / C;
+    float tot = 0.f;
+    for (int m = 0; m < nmod; ++m) {
+      float s = 0.f;
+      for (int p = 0; p < 64; ++p)
+        s += __ldg(f.p[m] + ((int64_t)b * 64 + p) * C + c) + __ldg(tok + ((int64_t)b * T + m * 64 + p) * C + c);
+      tot += s * (1.0f / 64.0f);
+    }
+    fused[i] = tot;
+  }
+}
+
+__global__ void pool_sum_bwd_kernel(const float* __restrict__ dfused, FeatPtrsW df, int nmod,
+                                    float* __restrict__ dtok, int B, int C) {
+  int T = nmod * 64;
+  int64_t n = (int64_t)B * T * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    int64_t t2 = i / C;
+    int t = (int)(t2 % T);
+    int b = (int)(t2 / T);
+    float g = __ldg(dfused + b * C + c) * (1.0f / 64.0f);
+    dtok[i] = g;
+    df.p[t >> 6][((int64_t)b * 64 + (t & 63)) * C + c] = g;
+  }
+}
+
+}  // namespace
+
+// y(B,H,W,C) = transpose(x(B,C,H,W)); with mean/std (C floats each, device) also (x-mean)/std.
+MMFN_API int mmfn_nchw_to_nhwc_f32(const float* x, float* y, int B, int C, int H, int W,
+                                   const float* mean, const float* stdv, cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && y && B > 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: bad args");
+  MMFN_CHECK_ARG((mean == nullptr) == (stdv == nullptr), "nchw_to_nhwc: mean/std must come together");
+  int64_t n = (int64_t)B * H * W;
+  nchw_to_nhwc_kernel<<<grid_1d(n, 256), 256, 0, stream>>>(x, y, B, C, (int64_t)H * W, mean, stdv);
+  return mmfn_launch_status("nchw_to_nhwc");
+}
+
+// out[b][c][r] = in[b][r][c]
+MMFN_API int mmfn_transpose_f32(const float* in, float* out, int nb, int R, int Cc, cudaStream_t stream) {
+  MMFN_CHECK_ARG(in && out && nb > 0 && R > 0 && Cc > 0 && nb <= 65535, "transpose: bad args");
+  dim3 grid((Cc + 31) / 32, (R + 31) / 32, nb);
+  MMFN_CHECK_ARG(grid.y <= 65535, "transpose: too many rows");
+  transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(in, out, R, Cc);
+  return mmfn_launch_status("transpose");
+}
+
+MMFN_API int mmfn_maxpool3x3s2_fwd(const float* x, float* y, uint8_t* idx, int B, int H, int W, int C,
+                                   cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && y && idx && B > 0 && H > 0 && W > 0 && C > 0, "maxpool_fwd: bad args");
+  int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  maxpool_fwd_kernel<<<grid_1d((int64_t)B * Ho * Wo * C, 256), 256, 0, stream>>>(x, y, idx, B, H, W, C, Ho, Wo);
+  return mmfn_launch_status("maxpool_fwd");
+}
+
+MMFN_API int mmfn_maxpool3x3s2_bwd(const float* dy, const uint8_t* idx, float* dx, int B, int H, int W, int C,
+                                   cudaStream_t stream) {
+  MMFN_CHECK_ARG(dy && dx && idx && B > 0 && H > 0 && W > 0 && C > 0, "maxpool_bwd: bad args");
+  int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  maxpool_bwd_kernel<<<grid_1d((int64_t)B * H * W * C, 256), 256, 0, stream>>>(dy, idx, dx, B, H, W, C, Ho, Wo);
+  return mmfn_launch_status("maxpool_bwd");
+}
+
+// feats: nmod device pointers (each (B,H,W,C) NHWC); tokens: (B, nmod*64, C).
+MMFN_API int mmfn_tokens_fwd(const float* f0, const float* f1, const float* f2, const float* f3, int nmod,
+                             int B, int H, int W, int C, const float* pos_emb, const float* vel_w,
+                             const float* vel_b, const float* velocity, float* tokens,
+                             float drop_p, uint64_t seed, cudaStream_t stream) {
+  MMFN_CHECK_ARG(nmod >= 1 && nmod <= 4 && f0 && (nmod < 2 || f1) && (nmod < 3 || f2) && (nmod < 4 || f3),
+                 "tokens_fwd: bad modality pointers");
+  MMFN_CHECK_ARG(pos_emb && vel_w && vel_b && velocity && tokens, "tokens_fwd: null pointer");
+  MMFN_CHECK_ARG(B > 0 && C > 0 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0, "tokens_fwd: H,W must be multiples of 8");
+  FeatPtrs f{{f0, f1, f2, f3}};
+  tokens_fwd_kernel<<<grid_1d((int64_t)B * nmod * 64 * C, 256), 256, 0, stream>>>(f, nmod, B, H, W, C, pos_emb, vel_w, vel_b,
+                                                                          velocity, tokens, drop_p, seed);
+  return mmfn_launch_status("tokens_fwd");
+}
+
+// df*: feature-map gradients, accumulated in place.  dpos/dvel_w/dvel_b accumulated.
+MMFN_API int mmfn_tokens_bwd(const float* dtokens, float* df0, float* df1, float* df2, float* df3, int nmod,
+                             int B, int H, int W, int C, const float* velocity,
+                             float* dpos_emb, float* dvel_w, float* dvel_b,
+                             float drop_p, uint64_t seed, cudaStream_t stream) {
+  MMFN_CHECK_ARG(nmod >= 1 && nmod <= 4 && dtokens && velocity && dpos_emb && dvel_w && dvel_b, "tokens_bwd: null pointer");
+  MMFN_CHECK_ARG(B > 0 && C > 0 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0, "tokens_bwd: H,W must be multiples of 8");
+  FeatPtrsW df{{df0, df1, df2, df3}};
+  int T = nmod * 64;
+  for (int m = 0; m < nmod; ++m) {
+    if (!df.p[m]) continue;   // modality without a gradient consumer
+    tokens_bwd_feat_kernel<<<grid_1d((int64_t)B * H * W * C, 256), 256, 0, stream>>>(df, m, B, H, W, C, T, dtokens, drop_p, seed);
+  }
+  tokens_bwd_param_kernel<<<grid_1d((int64_t)T * C, 128), 128, 0, stream>>>(dtokens, velocity, B, T, C, dpos_emb, dvel_w, dvel_b, drop_p, seed);
+  return mmfn_launch_status("tokens_bwd");
+}
+
+MMFN_API int mmfn_upsample_add_fwd(const float* feat, const float* tokens, float* out, int m, int T,
+                                   int B, int H, int W, int C, cudaStream_t stream) {
+  MMFN_CHECK_ARG(feat && tokens && out && B > 0 && H >= 8 && W >= 8 && C > 0 && m >= 0 && (m + 1) * 64 <= T, "upsample_add_fwd: bad args");
+  upsample_add_fwd_kernel<<<grid_1d((int64_t)B * H * W * C, 256), 256, 0, stream>>>(feat, tokens, out, m, T, B, H, W, C);
+  return mmfn_launch_status("upsample_add_fwd");
+}
+
+MMFN_API int mmfn_upsample_add_bwd(const float* dA, float* dtokens, int m, int T, int B, int H, int W, int C,
+                                   cudaStream_t stream) {
+  MMFN_CHECK_ARG(dA && dtokens && B > 0 && H >= 8 && W >= 8 && C > 0 && m >= 0 && (m + 1) * 64 <= T, "upsample_add_bwd: bad args");
+  upsample_add_bwd_kernel<<<grid_1d((int64_t)B * 64 * C, 128), 128, 0, stream>>>(dA, dtokens, m, T, B, H, W, C);
+  return mmfn_launch_status("upsample_add_bwd");
+}
+
+MMFN_API int mmfn_pool_sum_fwd(const float* f0, const float* f1, const float* f2, const float* f3, int nmod,
+                               const float* tokens, int B, int C, float* fused, cudaStream_t stream) {
+  MMFN_CHECK_ARG(nmod >= 1 && nmod <= 4 && f0 && tokens && fused && B > 0 && C > 0, "pool_sum_fwd: bad args");
+  FeatPtrs f{{f0, f1, f2, f3}};
+  pool_sum_fwd_kernel<<<grid_1d((int64_t)B * C, 128), 128, 0, stream>>>(f, nmod, tokens, B, C, fused);
+  return mmfn_launch_status("pool_sum_fwd");
+}
+
+MMFN_API int mmfn_pool_sum_bwd(const float* dfused, float* df0, float* df1, float* df2, float* df3, int nmod,
+                               float* dtokens, int B, int C, cudaStream_t stream) {
+  MMFN_CHECK_ARG(nmod >= 1 && nmod <= 4 && dfused && df0 && dtokens && B > 0 && C > 0, "pool_sum_bwd: bad args");
+  MMFN_CHECK_ARG((nmod < 2 || df1) && (nmod < 3 || df2) && (nmod < 4 || df3), "pool_sum_bwd: null modality gradient");
+  FeatPtrsW df{{df0, df1, df2, df3}};
+  pool_sum_bwd_kernel<<<grid_1d((int64_t)B * nmod * 64 * C, 256), 256, 0, stream>>>(dfused, df, nmod, dtokens, B, C);
+  return mmfn_launch_status("pool_sum_bwd");
+}

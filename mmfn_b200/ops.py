@@ -1,0 +1,424 @@
+"""Thin torch-tensor wrappers over the C ABI (include/mmfn_b200.h).
+
+torch supplies device memory and the current stream only; every arithmetic op below is a
+kernel of libmmfn_b200.so.  Tensors are fp32 CUDA tensors; activations are NHWC.
+"""
+import torch
+
+from ._lib import lib, MmfnError  # noqa: F401
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, name="tensor"):
+    if t is not None and not (t.is_cuda and t.dtype == torch.float32):
+        raise MmfnError(f"{name}: expected a CUDA float32 tensor, got {t.device}/{t.dtype}")
+
+
+def gemm(A, B, C, *, bias=None, res=None, mask=None, alpha=1.0, act=0, accum=0,
+         drop_p=0.0, seed=0, splitk=1):
+    """C[..., M, N] (+)= alpha * A[..., M, K] @ B[..., N, K]^T  with up to two leading batch dims.
+
+    A and B may be arbitrary strided views; C needs unit column stride.  res/mask index like C.
+    """
+    for t in (A, B, C, bias, res, mask):
+        _chk(t)
+    nbd = C.dim() - 2
+    assert A.dim() == C.dim() and B.dim() == C.dim() and 0 <= nbd <= 2
+    M, K = A.shape[-2], A.shape[-1]
+    N = B.shape[-2]
+    assert B.shape[-1] == K and C.shape[-2] == M and C.shape[-1] == N, (A.shape, B.shape, C.shape)
+    assert C.stride(-1) == 1 or N == 1
+    bs = list(C.shape[:nbd])
+    nb = [1] * (2 - nbd) + bs
+
+    def bstr(t):
+        s = [t.stride(i) if t.shape[i] > 1 else 0 for i in range(nbd)]
+        for i in range(nbd):
+            assert t.shape[i] == bs[i] or t.shape[i] == 1
+        return [0] * (2 - nbd) + s
+
+    a_b, b_b, c_b = bstr(A), bstr(B), bstr(C)
+    for t in (res, mask):
+        if t is not None:
+            assert t.shape == C.shape and t.stride() == C.stride()
+    lib().gemm_f32(_p(A), A.stride(-2), A.stride(-1), a_b[0], a_b[1],
+                   _p(B), B.stride(-2), B.stride(-1), b_b[0], b_b[1],
+                   _p(C), C.stride(-2), c_b[0], c_b[1],
+                   M, N, K, nb[0], nb[1], _p(bias), _p(res), _p(mask),
+                   float(alpha), int(act), int(accum), float(drop_p), int(seed), int(splitk), _st())
+    return C
+
+
+def colsum_(x2d, out):
+    """out[n] += sum_m x2d[m, n]"""
+    assert x2d.stride(1) == 1
+    lib().colsum_f32(_p(x2d), x2d.stride(0), x2d.shape[0], x2d.shape[1], _p(out), _st())
+
+
+# ------------------------------------------------------------------ convolution (NHWC / KRSC)
+def conv_out_hw(H, W, R, S, stride, pad):
+    return (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
+
+
+def conv2d_fwd(x, w_krsc, stride, pad):
+    N, H, W, C = x.shape
+    Co, R, S, C2 = w_krsc.shape
+    assert C2 == C and x.is_contiguous() and w_krsc.is_contiguous()
+    Ho, Wo = conv_out_hw(H, W, R, S, stride, pad)
+    y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
+    lib().conv2d_fwd_f32(_p(x), _p(w_krsc), _p(y), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, _st())
+    return y
+
+
+def filter_crsk(w_krsc):
+    Co, R, S, C = w_krsc.shape
+    wt = torch.empty((C, R, S, Co), device=w_krsc.device, dtype=torch.float32)
+    lib().filter_krsc_to_crsk(_p(w_krsc), _p(wt), Co, R, S, C, _st())
+    return wt
+
+
+def conv2d_dgrad(dy, w_krsc, x_shape, stride, pad, res=None):
+    N, H, W, C = x_shape
+    Co, R, S, _ = w_krsc.shape
+    _, Ho, Wo, _ = dy.shape
+    wt = filter_crsk(w_krsc)
+    dx = torch.empty(x_shape, device=dy.device, dtype=torch.float32)
+    lib().conv2d_dgrad_f32(_p(dy), _p(wt), _p(dx), _p(res), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, _st())
+    return dx
+
+
+def conv2d_wgrad_(dy, x, dw_krsc, stride, pad):
+    """dw_krsc += wgrad"""
+    N, H, W, C = x.shape
+    Co, R, S, _ = dw_krsc.shape
+    _, Ho, Wo, _ = dy.shape
+    assert dw_krsc.is_contiguous()
+    lib().conv2d_wgrad_f32(_p(dy), _p(x), _p(dw_krsc), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, 0, _st())
+
+
+# ------------------------------------------------------------------ normalisation
+_ws = {}
+
+
+def _bn_ws(dev):
+    if dev not in _ws:
+        _ws[dev] = torch.empty(2 * 4096, device=dev, dtype=torch.float64)
+    return _ws[dev]
+
+
+def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5, res=None, relu=False):
+    C = x.shape[-1]
+    M = x.numel() // C
+    y = torch.empty_like(x)
+    mean = torch.empty(C, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(C, device=x.device, dtype=torch.float32)
+    lib().bn_train_fwd(_p(x), _p(y), M, C, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                       momentum, eps, _p(mean), _p(rstd), _p(res), int(relu), _p(_bn_ws(x.device)), _st())
+    return y, mean, rstd
+
+
+def bn_eval_fwd(x, gamma, beta, running_mean, running_var, eps=1e-5, res=None, relu=False):
+    C = x.shape[-1]
+    M = x.numel() // C
+    y = torch.empty_like(x)
+    mean = torch.empty(C, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(C, device=x.device, dtype=torch.float32)
+    lib().bn_eval_fwd(_p(x), _p(y), M, C, _p(gamma), _p(beta), _p(running_mean), _p(running_var), eps,
+                      _p(mean), _p(rstd), _p(res), int(relu), _st())
+    return y, mean, rstd
+
+
+def bn_train_bwd(dy, x, yout, mean, rstd, gamma, dgamma, dbeta, want_dres=False):
+    C = x.shape[-1]
+    M = x.numel() // C
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dres else None
+    lib().bn_train_bwd(_p(dy), _p(x), _p(yout), _p(mean), _p(rstd), _p(gamma), M, C, _p(dx), _p(dres),
+                       _p(dgamma), _p(dbeta), _p(_bn_ws(x.device)), _st())
+    return dx, dres
+
+
+def layernorm_fwd(x2d, gamma, beta, act=0, eps=1e-5, out=None):
+    M, C = x2d.shape
+    assert x2d.is_contiguous()
+    y = torch.empty_like(x2d) if out is None else out
+    mean = torch.empty(M, device=x2d.device, dtype=torch.float32)
+    rstd = torch.empty(M, device=x2d.device, dtype=torch.float32)
+    lib().layernorm_fwd(_p(x2d), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), M, C, eps, act, _st())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x2d, gamma, beta, mean, rstd, dgamma, dbeta, act=0, dres=None):
+    M, C = x2d.shape
+    assert dy.is_contiguous() and x2d.is_contiguous()
+    dx = torch.empty_like(x2d)
+    lib().layernorm_bwd(_p(dy), _p(x2d), _p(gamma), _p(beta), _p(mean), _p(rstd), _p(dres), _p(dx),
+                        _p(dgamma), _p(dbeta), M, C, act, _st())
+    return dx
+
+
+# ------------------------------------------------------------------ layout / pooling
+def nchw_to_nhwc(x, mean=None, std=None):
+    B, C, H, W = x.shape
+    assert x.is_contiguous()
+    y = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
+    lib().nchw_to_nhwc_f32(_p(x), _p(y), B, C, H, W, _p(mean), _p(std), _st())
+    return y
+
+
+def transpose(x3d):
+    """(nb, R, C) -> (nb, C, R)"""
+    nb, R, Cc = x3d.shape
+    assert x3d.is_contiguous()
+    y = torch.empty((nb, Cc, R), device=x3d.device, dtype=torch.float32)
+    lib().transpose_f32(_p(x3d), _p(y), nb, R, Cc, _st())
+    return y
+
+
+def maxpool_fwd(x):
+    B, H, W, C = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.float32)
+    idx = torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.uint8)
+    lib().maxpool3x3s2_fwd(_p(x), _p(y), idx.data_ptr(), B, H, W, C, _st())
+    return y, idx
+
+
+def maxpool_bwd(dy, idx, x_shape):
+    B, H, W, C = x_shape
+    dx = torch.empty(x_shape, device=dy.device, dtype=torch.float32)
+    lib().maxpool3x3s2_bwd(_p(dy), idx.data_ptr(), _p(dx), B, H, W, C, _st())
+    return dx
+
+
+def _four(ts):
+    ts = list(ts) + [None] * (4 - len(ts))
+    return [_p(t) for t in ts]
+
+
+def tokens_fwd(feats, pos_emb, vel_w, vel_b, velocity, drop_p=0.0, seed=0):
+    B, H, W, C = feats[0].shape
+    nmod = len(feats)
+    tok = torch.empty((B, nmod * 64, C), device=feats[0].device, dtype=torch.float32)
+    f = _four(feats)
+    lib().tokens_fwd(f[0], f[1], f[2], f[3], nmod, B, H, W, C, _p(pos_emb), _p(vel_w), _p(vel_b),
+                     _p(velocity), _p(tok), drop_p, seed, _st())
+    return tok
+
+
+def tokens_bwd_(dtok, dfeats, shape, velocity, dpos, dvel_w, dvel_b, drop_p=0.0, seed=0):
+    """dfeats[m] += pool_bwd(dtok) (entries may be None); parameter grads accumulated."""
+    B, H, W, C = shape
+    f = _four(dfeats)
+    lib().tokens_bwd(_p(dtok), f[0], f[1], f[2], f[3], len(dfeats), B, H, W, C, _p(velocity),
+                     _p(dpos), _p(dvel_w), _p(dvel_b), drop_p, seed, _st())
+
+
+def upsample_add_fwd(feat, tok, m):
+    B, H, W, C = feat.shape
+    out = torch.empty_like(feat)
+    lib().upsample_add_fwd(_p(feat), _p(tok), _p(out), m, tok.shape[1], B, H, W, C, _st())
+    return out
+
+
+def upsample_add_bwd_(dA, dtok, m):
+    B, H, W, C = dA.shape
+    lib().upsample_add_bwd(_p(dA), _p(dtok), m, dtok.shape[1], B, H, W, C, _st())
+
+
+def pool_sum_fwd(feats, tok):
+    B, _, _, C = feats[0].shape
+    fused = torch.empty((B, C), device=tok.device, dtype=torch.float32)
+    f = _four(feats)
+    lib().pool_sum_fwd(f[0], f[1], f[2], f[3], len(feats), _p(tok), B, C, _p(fused), _st())
+    return fused
+
+
+def pool_sum_bwd(dfused, nmod):
+    B, C = dfused.shape
+    dfe = [torch.empty((B, 8, 8, C), device=dfused.device, dtype=torch.float32) for _ in range(nmod)]
+    dtok = torch.empty((B, nmod * 64, C), device=dfused.device, dtype=torch.float32)
+    f = _four(dfe)
+    lib().pool_sum_bwd(_p(dfused), f[0], f[1], f[2], f[3], nmod, _p(dtok), B, C, _st())
+    return dfe, dtok
+
+
+# ------------------------------------------------------------------ softmax family
+def softmax_fwd(s, scale, drop_p=0.0, seed=0):
+    cols = s.shape[-1]
+    rows = s.numel() // cols
+    p = torch.empty_like(s)
+    pd = torch.empty_like(s) if drop_p > 0 else None
+    lib().softmax_fwd(_p(s), _p(p), _p(pd), rows, cols, scale, drop_p, seed, _st())
+    return p, (pd if pd is not None else p)
+
+
+def softmax_bwd(p, dpd, scale, drop_p=0.0, seed=0):
+    cols = p.shape[-1]
+    rows = p.numel() // cols
+    ds = torch.empty_like(p)
+    lib().softmax_bwd(_p(p), _p(dpd), _p(ds), rows, cols, scale, drop_p, seed, _st())
+    return ds
+
+
+def gat_softmax_fwd(z, adj, alpha, drop_p=0.0, seed=0):
+    cols = z.shape[-1]
+    rows = z.numel() // cols
+    att = torch.empty_like(z)
+    attd = torch.empty_like(z)
+    lib().gat_softmax_fwd(_p(z), _p(adj), _p(att), _p(attd), rows, cols, alpha, drop_p, seed, _st())
+    return att, attd
+
+
+def gat_softmax_bwd(z, adj, att, dattd, alpha, drop_p=0.0, seed=0):
+    cols = z.shape[-1]
+    rows = z.numel() // cols
+    dz = torch.empty_like(z)
+    lib().gat_softmax_bwd(_p(z), _p(adj), _p(att), _p(dattd), _p(dz), rows, cols, alpha, drop_p, seed, _st())
+    return dz
+
+
+def l2l_row0_fwd(qkv, lane_num_i32, heads, out):
+    """qkv (B,L,3*heads*64); writes out (B, heads*64) (may be a column slice); returns prob."""
+    B, L, _ = qkv.shape
+    prob = torch.empty((B, heads, L), device=qkv.device, dtype=torch.float32)
+    tmp = torch.empty((B, heads * 64), device=qkv.device, dtype=torch.float32)
+    lib().l2l_row0_fwd(_p(qkv), lane_num_i32.data_ptr(), B, L, heads, 64, _p(prob), _p(tmp), _st())
+    return prob, tmp
+
+
+def l2l_row0_bwd(qkv, lane_num_i32, prob, dout, heads):
+    B, L, _ = qkv.shape
+    assert dout.is_contiguous()
+    dqkv = torch.empty_like(qkv)
+    lib().l2l_row0_bwd(_p(qkv), lane_num_i32.data_ptr(), _p(prob), _p(dout), B, L, heads, 64, _p(dqkv), _st())
+    return dqkv
+
+
+# ------------------------------------------------------------------ misc
+def elu_fwd(x):
+    y = torch.empty_like(x)
+    lib().elu_fwd(_p(x), _p(y), x.numel(), _st())
+    return y
+
+
+def elu_bwd(dy, y):
+    dx = torch.empty_like(y)
+    lib().elu_bwd(_p(dy), _p(y), _p(dx), y.numel(), _st())
+    return dx
+
+
+def dropout(x, p, seed):
+    if p <= 0:
+        return x
+    y = torch.empty_like(x)
+    lib().dropout_f32(_p(x), _p(y), x.numel(), p, seed, _st())
+    return y
+
+
+def axpy_(x, y, a=1.0):
+    assert x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
+    lib().axpy_f32(_p(x), _p(y), a, x.numel(), _st())
+
+
+def lane_to_vector(lane):
+    """(B, L, P, 5) -> (B*L*(P-1), 7)"""
+    B, L, P, F = lane.shape
+    assert F == 5 and lane.is_contiguous()
+    vec = torch.empty((B * L * (P - 1), 7), device=lane.device, dtype=torch.float32)
+    lib().lane_to_vector(_p(lane), _p(vec), B * L, P, _st())
+    return vec
+
+
+def subgraph_pool_fwd(x, G, V):
+    C = x.shape[-1]
+    y = torch.empty((G * V, 2 * C), device=x.device, dtype=torch.float32)
+    arg = torch.empty((G, C), device=x.device, dtype=torch.int32)
+    lib().subgraph_pool_fwd(_p(x), G, V, C, _p(y), arg.data_ptr(), _st())
+    return y, arg
+
+
+def subgraph_pool_bwd(dy, arg, G, V):
+    C = arg.shape[-1]
+    dx = torch.empty((G * V, C), device=dy.device, dtype=torch.float32)
+    lib().subgraph_pool_bwd(_p(dy), arg.data_ptr(), G, V, C, _p(dx), _st())
+    return dx
+
+
+def segmax_fwd(x, G, V):
+    C = x.shape[-1]
+    out = torch.empty((G, C), device=x.device, dtype=torch.float32)
+    arg = torch.empty((G, C), device=x.device, dtype=torch.int32)
+    lib().segmax_fwd(_p(x), G, V, C, _p(out), arg.data_ptr(), _st())
+    return out, arg
+
+
+def segmax_bwd(dout, arg, G, V):
+    C = arg.shape[-1]
+    dx = torch.empty((G * V, C), device=dout.device, dtype=torch.float32)
+    lib().segmax_bwd(_p(dout), arg.data_ptr(), G, V, C, _p(dx), _st())
+    return dx
+
+
+def radar_logsoftmax_fwd(v, B, C):
+    y = torch.empty((B, 8, 8, C), device=v.device, dtype=torch.float32)
+    lib().radar_logsoftmax_fwd(_p(v), _p(y), B, C, _st())
+    return y
+
+
+def radar_logsoftmax_bwd(dy, y):
+    B, _, _, C = y.shape
+    dv = torch.empty((B, 64, C), device=y.device, dtype=torch.float32)
+    lib().radar_logsoftmax_bwd(_p(dy), _p(y), _p(dv), B, C, _st())
+    return dv
+
+
+def bev_scatter(points, strips=0):
+    """points (frames, n, 3|4) f32 -> (frames, 2, 256, 256) f32, reference layout [c, xbin, ybin]."""
+    _chk(points, "points")
+    assert points.dim() == 3 and points.is_contiguous()
+    F, n, s = points.shape
+    out = torch.empty((F, 2, 256, 256), device=points.device, dtype=torch.float32)
+    lib().bev_scatter(_p(points), F, n, s, _p(out), strips, _st())
+    return out
+
+
+def gru_head_fwd(z0, target, w_ih, w_hh, b_ih, b_hh, w_out, b_out, steps):
+    B = z0.shape[0]
+    dev = z0.device
+    pred = torch.empty((B, steps, 2), device=dev, dtype=torch.float32)
+    saved = torch.empty((B, steps, 5, 64), device=dev, dtype=torch.float32)
+    xin = torch.empty((B, steps, 2), device=dev, dtype=torch.float32)
+    hlast = torch.empty((B, 64), device=dev, dtype=torch.float32)
+    lib().gru_head_fwd(_p(z0), _p(target), _p(w_ih), _p(w_hh), _p(b_ih), _p(b_hh), _p(w_out), _p(b_out),
+                       B, steps, _p(pred), _p(saved), _p(xin), _p(hlast), _st())
+    return pred, (saved, xin, hlast)
+
+
+def gru_head_bwd(dpred, ctx, w_ih, w_hh, w_out, dw_ih, dw_hh, db_ih, db_hh, dw_out, db_out):
+    saved, xin, hlast = ctx
+    B, steps = saved.shape[0], saved.shape[1]
+    dz0 = torch.empty((B, 64), device=dpred.device, dtype=torch.float32)
+    lib().gru_head_bwd(_p(dpred), _p(saved), _p(xin), _p(hlast), _p(w_ih), _p(w_hh), _p(w_out), B, steps,
+                       _p(dz0), _p(dw_ih), _p(dw_hh), _p(db_ih), _p(db_hh), _p(dw_out), _p(db_out), _st())
+    return dz0
+
+
+def l1_loss(pred, gt, gscale=1.0, want_grad=True):
+    loss = torch.empty((), device=pred.device, dtype=torch.float32)
+    dpred = torch.empty_like(pred) if want_grad else None
+    assert pred.is_contiguous() and gt.is_contiguous()
+    lib().l1_loss(_p(pred), _p(gt), pred.numel(), _p(loss), _p(dpred), gscale, _st())
+    return loss, dpred
+
+
+def adamw_step_(p, g, m, v, state, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, grad_scale=1.0):
+    lib().adamw_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay,
+                     _p(state), grad_scale, _st())
