@@ -37,6 +37,12 @@ __global__ void elu_bwd_kernel(const float* __restrict__ dy, const float* __rest
   }
 }
 
+// dx = dy * (y > 0)
+__global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float p, uint64_t seed) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = x[i] * mmfn_dropout_scale(p, seed, (uint64_t)i);
@@ -172,6 +178,12 @@ MMFN_API int mmfn_elu_bwd(const float* dy, const float* y, float* dx, int64_t n,
   if (n == 0) return 0;
   elu_bwd_kernel<<<grid_1d(n, 256), 256, 0, stream>>>(dy, y, dx, n);
   return mmfn_launch_status("elu_bwd");
+}
+MMFN_API int mmfn_relu_bwd(const float* dy, const float* y, float* dx, int64_t n, cudaStream_t stream) {
+  MMFN_CHECK_ARG(dy && y && dx && n >= 0, "relu_bwd: bad args");
+  if (n == 0) return 0;
+  relu_bwd_kernel<<<grid_1d(n, 256), 256, 0, stream>>>(dy, y, dx, n);
+  return mmfn_launch_status("relu_bwd");
 }
 // y = x * keep_scale(p, seed, index); same call regenerates the mask in backward.
 MMFN_API int mmfn_dropout_f32(const float* x, float* y, int64_t n, float p, uint64_t seed, cudaStream_t stream) {

@@ -6,14 +6,15 @@
 
 namespace {
 
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y,
+template <typename TIn>
+__global__ void nchw_to_nhwc_kernel(const TIn* __restrict__ x, float* __restrict__ y,
                                     int B, int C, int64_t HW, const float* __restrict__ mean,
                                     const float* __restrict__ stdv) {
   int64_t n = (int64_t)B * HW;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t b = i / HW, p = i - b * HW;
     for (int c = 0; c < C; ++c) {
-      float v = __ldg(x + (b * C + c) * HW + p);
+      float v = (float)__ldg(x + (b * C + c) * HW + p);
       if (mean) v = (v - mean[c]) / stdv[c];
       y[i * C + c] = v;
     }
@@ -254,8 +255,18 @@ MMFN_API int mmfn_nchw_to_nhwc_f32(const float* x, float* y, int B, int C, int H
   MMFN_CHECK_ARG(x && y && B > 0 && C > 0 && H > 0 && W > 0, "nchw_to_nhwc: bad args");
   MMFN_CHECK_ARG((mean == nullptr) == (stdv == nullptr), "nchw_to_nhwc: mean/std must come together");
   int64_t n = (int64_t)B * H * W;
-  nchw_to_nhwc_kernel<<<grid_1d(n, 256), 256, 0, stream>>>(x, y, B, C, (int64_t)H * W, mean, stdv);
+  nchw_to_nhwc_kernel<float><<<grid_1d(n, 256), 256, 0, stream>>>(x, y, B, C, (int64_t)H * W, mean, stdv);
   return mmfn_launch_status("nchw_to_nhwc");
+}
+
+// Same for uint8 camera frames (the collated `fronts`, phase2_train_net.py:80 casts them to float).
+MMFN_API int mmfn_nchw_u8_to_nhwc_f32(const uint8_t* x, float* y, int B, int C, int H, int W,
+                                      const float* mean, const float* stdv, cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && y && B > 0 && C > 0 && H > 0 && W > 0, "nchw_u8_to_nhwc: bad args");
+  MMFN_CHECK_ARG((mean == nullptr) == (stdv == nullptr), "nchw_u8_to_nhwc: mean/std must come together");
+  int64_t n = (int64_t)B * H * W;
+  nchw_to_nhwc_kernel<uint8_t><<<grid_1d(n, 256), 256, 0, stream>>>(x, y, B, C, (int64_t)H * W, mean, stdv);
+  return mmfn_launch_status("nchw_u8_to_nhwc");
 }
 
 // out[b][c][r] = in[b][r][c]

@@ -1,0 +1,102 @@
+"""Training-step engine: the B200-native equivalent of Engine.train's loop body
+(run_steps/phase2_train_net.py:60-110) plus the optimizer/DDP wiring of main() (:256-269).
+
+One step = [one packed H2D copy] -> BEV scatter -> forward -> L1 loss -> backward ->
+[ONE all-reduce over the flat gradient buffer] -> ONE fused AdamW launch over the flat
+parameter buffer.  Data parallelism is one process per GPU (torch.distributed, NCCL); every
+rank keeps a full replica, BatchNorm statistics stay rank-local as in the reference (no SyncBN).
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+_FIELDS = (  # name, dtype, per-sample shape builder
+    ("rgb_u8", torch.uint8), ("points", torch.float32), ("lane", torch.float32), ("lane_num", torch.int32),
+    ("radar", torch.float32), ("radar_adj", torch.float32), ("velocity", torch.float32),
+    ("target_point", torch.float32), ("gt_waypoints", torch.float32),
+)
+
+
+class BatchStager:
+    """Packs a host batch (dict of CPU tensors, see synthetic.synth_batch) into ONE pinned buffer and
+    moves it with ONE async H2D copy; the reference issues ~25 separate .to(device) copies per step
+    (phase2_train_net.py:78-97)."""
+
+    def __init__(self, example, device):
+        self.device = torch.device(device)
+        self.layout, off = [], 0
+        for name, dtype in _FIELDS:
+            t = example[name]
+            nbytes = t.numel() * t.element_size()
+            self.layout.append((name, dtype, tuple(t.shape), off, nbytes))
+            off += (nbytes + 255) // 256 * 256
+        self.nbytes = off
+        self.host = [torch.empty(off, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.dev = [torch.empty(off, dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.flip = 0
+
+    def _views(self, buf):
+        out = {}
+        for name, dtype, shape, off, nbytes in self.layout:
+            out[name] = buf[off: off + nbytes].view(dtype).view(shape)
+        return out
+
+    def stage(self, batch):
+        """host dict -> device dict (views into one device buffer); asynchronous on the current stream."""
+        self.flip ^= 1
+        h, d = self.host[self.flip], self.dev[self.flip]
+        hv = self._views(h)
+        for name, dtype, shape, _, _ in self.layout:
+            hv[name].copy_(batch[name].to(dtype))
+        d.copy_(h, non_blocking=True)
+        return self._views(d)
+
+
+class TrainEngine:
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, process_group=None):
+        self.model, self.net, self.st = model, model.net, model.store
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        n = self.st.n_active
+        dev = self.st.device
+        self.m = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.v = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.state = torch.zeros(3, device=dev, dtype=torch.float32)
+        self.p_active = self.st.flat[:n]
+        self.g_active = self.st.flat_grad[:n]
+        self.last_pred = None
+
+    def broadcast_parameters(self, src=0):
+        """What DistributedDataParallel's constructor does (phase2_train_net.py:269)."""
+        if self.world > 1:
+            dist.broadcast(self.st.flat, src, group=self.pg)
+            dist.broadcast(self.st.flat_buf, src, group=self.pg)
+
+    def forward_backward(self, b):
+        """b: device batch. Returns the loss (0-d device tensor); gradients land in store.flat_grad."""
+        model = self.model
+        model.train()
+        self.st.flat_grad.zero_()
+        lidar = b["lidar"] if "lidar" in b else ops.bev_scatter(b["points"])
+        image = b["rgb_u8"] if "rgb_u8" in b else b["image"]
+        model.seed += 1000
+        self.st.flat_nbt.add_(model._nbt_step())
+        pred = self.net.forward(image, lidar, b["lane"], b["lane_num"], b["radar"], b["radar_adj"],
+                                b["target_point"], b["velocity"], model.seed, True)
+        loss, dpred = ops.l1_loss(pred, b["gt_waypoints"])
+        self.net.backward(dpred)
+        self.last_pred = pred
+        return loss
+
+    def optimizer_step(self):
+        if self.world > 1:
+            dist.all_reduce(self.g_active, op=dist.ReduceOp.SUM, group=self.pg)   # ONE collective per step
+        ops.adamw_step_(self.p_active, self.g_active, self.m, self.v, self.state, self.lr, self.betas[0],
+                        self.betas[1], self.eps, self.wd, grad_scale=1.0 / self.world)
+
+    def step(self, device_batch):
+        loss = self.forward_backward(device_batch)
+        self.optimizer_step()
+        return loss

@@ -1,0 +1,609 @@
+"""B200-native MMFN (RGB + LiDAR-BEV + VectorNet map + radar GAT -> 4 fusion transformers -> GRU
+waypoint head).  Drop-in for team_code/mmfn_utils/models/model_rad.py:MMFN (:639-739):
+
+    MMFN(config, device)
+    forward(image_list, lidar_list, maps_list, vectormaps_list, radar_list, radar_adj,
+            target_point, velocity) -> (B, pred_len, 2)
+    control_pid(waypoints, velocity)
+
+with the reference's state_dict keys/shapes, selectable through the reference plugin hook
+(train_agent.entry_point = "mmfn_b200.model_rad:MMFN", run_steps/utils.py:68-72).
+
+Nothing here uses torch autograd or ATen math: forward and backward are explicit schedules of
+libmmfn_b200.so kernels over NHWC fp32 activations; torch provides memory, streams and the
+nn.Module/Parameter bookkeeping.  `loss.backward()` still works for callers that want it (one
+autograd.Function around the whole network), but the fast path is engine.TrainEngine.
+"""
+import math
+from collections import deque
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import ops
+from .params import ParamStore, RESNET18, RESNET34, WIDTHS, is_unused
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+# --------------------------------------------------------------------------- building blocks
+class ConvBN:
+    """conv (bias-free) -> BatchNorm2d [-> + residual] [-> ReLU]; torchvision BasicBlock pieces."""
+
+    def __init__(self, st, conv_key, bn_key, stride, pad):
+        self.w, self.dw = st.p(conv_key), st.g(conv_key)
+        self.gam, self.dgam = st.p(bn_key + ".weight"), st.g(bn_key + ".weight")
+        self.bet, self.dbet = st.p(bn_key + ".bias"), st.g(bn_key + ".bias")
+        self.rm, self.rv = st.buf(bn_key + ".running_mean"), st.buf(bn_key + ".running_var")
+        self.stride, self.pad = stride, pad
+
+    def fwd(self, x, res=None, relu=True, train=True):
+        self.x, self.relu = x, relu
+        self.z = ops.conv2d_fwd(x, self.w, self.stride, self.pad)
+        if train:
+            self.y, self.mean, self.rstd = ops.bn_train_fwd(self.z, self.gam, self.bet, self.rm, self.rv, res=res, relu=relu)
+        else:
+            self.y, self.mean, self.rstd = ops.bn_eval_fwd(self.z, self.gam, self.bet, self.rm, self.rv, res=res, relu=relu)
+        return self.y
+
+    def bwd(self, dy, need_dx=True, want_dres=False, dx_res=None):
+        dz, dres = ops.bn_train_bwd(dy, self.z, self.y if self.relu else None, self.mean, self.rstd, self.gam,
+                                    self.dgam, self.dbet, want_dres)
+        ops.conv2d_wgrad_(dz, self.x, self.dw, self.stride, self.pad)
+        dx = ops.conv2d_dgrad(dz, self.w, self.x.shape, self.stride, self.pad, res=dx_res) if need_dx else None
+        self.x = self.z = self.y = None
+        return dx, dres
+
+
+class BasicBlock:
+    def __init__(self, st, prefix, stride, downsample):
+        self.c1 = ConvBN(st, prefix + ".conv1.weight", prefix + ".bn1", stride, 1)
+        self.c2 = ConvBN(st, prefix + ".conv2.weight", prefix + ".bn2", 1, 1)
+        self.ds = ConvBN(st, prefix + ".downsample.0.weight", prefix + ".downsample.1", stride, 0) if downsample else None
+
+    def fwd(self, x, train):
+        a = self.c1.fwd(x, relu=True, train=train)
+        idn = self.ds.fwd(x, relu=False, train=train) if self.ds else x
+        return self.c2.fwd(a, res=idn, relu=True, train=train)
+
+    def bwd(self, dout):
+        da, didn = self.c2.bwd(dout, want_dres=True)
+        if self.ds:
+            didn, _ = self.ds.bwd(didn)
+        dx, _ = self.c1.bwd(da, dx_res=didn)
+        return dx
+
+
+class ResLayer:
+    def __init__(self, st, prefix, nblocks, stride):
+        self.blocks = [BasicBlock(st, f"{prefix}.{i}", stride if i == 0 else 1, i == 0 and stride != 1)
+                       for i in range(nblocks)]
+
+    def fwd(self, x, train):
+        for b in self.blocks:
+            x = b.fwd(x, train)
+        return x
+
+    def bwd(self, d):
+        for b in reversed(self.blocks):
+            d = b.bwd(d)
+        return d
+
+
+class Stem:
+    """conv7x7/2 -> BN -> ReLU -> MaxPool3x3/2 on the (already NHWC) network input; no dgrad."""
+
+    def __init__(self, st, prefix):
+        self.cb = ConvBN(st, prefix + ".conv1.weight", prefix + ".bn1", 2, 3)
+
+    def fwd(self, x, train):
+        y = self.cb.fwd(x, relu=True, train=train)
+        self.in_shape = y.shape
+        out, self.idx = ops.maxpool_fwd(y)
+        return out
+
+    def bwd(self, d):
+        dy = ops.maxpool_bwd(d, self.idx, self.in_shape)
+        self.cb.bwd(dy, need_dx=False)
+        self.idx = None
+
+
+class Linear:
+    def __init__(self, st, prefix, bias=True, keys=None):
+        if keys is None:
+            self.w, self.dw = st.p(prefix + ".weight"), st.g(prefix + ".weight")
+            self.b, self.db = (st.p(prefix + ".bias"), st.g(prefix + ".bias")) if bias else (None, None)
+        else:       # several adjacent reference Linears fused into one GEMM
+            self.w, self.dw = st.fused([k + ".weight" for k in keys]), st.fused([k + ".weight" for k in keys], True)
+            self.b, self.db = st.fused([k + ".bias" for k in keys]), st.fused([k + ".bias" for k in keys], True)
+
+    def fwd(self, x, out=None, act=0, res=None, drop_p=0.0, seed=0):
+        """x (M,K) -> (M,N) = drop(act(x W^T + b)) + res"""
+        self.x, self.act = x, act
+        y = out if out is not None else torch.empty((x.shape[0], self.w.shape[0]), device=x.device, dtype=torch.float32)
+        ops.gemm(x, self.w, y, bias=self.b, res=res, act=act, drop_p=drop_p, seed=seed)
+        self.y = y if act else None
+        return y
+
+    def bwd(self, dy, need_dx=True, dx_mask=None, masked=False):
+        """dy: gradient of this layer's output (dropout mask already applied by the caller).  The
+        ReLU derivative is applied here from the saved output unless `masked`.  dx_mask fuses the
+        ReLU mask of the PRODUCER of x into the dgrad GEMM epilogue."""
+        if self.act == 1 and not masked:
+            dy = ops.relu_bwd(dy, self.y)
+        if self.db is not None:
+            ops.colsum_(dy, self.db)
+        ops.gemm(dy.t(), self.x.t(), self.dw, accum=1)
+        dx = None
+        if need_dx:
+            dx = torch.empty((dy.shape[0], self.w.shape[1]), device=dy.device, dtype=torch.float32)
+            ops.gemm(dy, self.w.t(), dx, mask=dx_mask)
+        self.x = self.y = None
+        return dx
+
+
+class LayerNorm:
+    def __init__(self, st, prefix, act=0):
+        self.g, self.dg = st.p(prefix + ".weight"), st.g(prefix + ".weight")
+        self.b, self.db = st.p(prefix + ".bias"), st.g(prefix + ".bias")
+        self.act = act
+
+    def fwd(self, x, out=None):
+        self.x = x
+        y, self.mean, self.rstd = ops.layernorm_fwd(x, self.g, self.b, act=self.act, out=out)
+        return y
+
+    def bwd(self, dy, dres=None):
+        dx = ops.layernorm_bwd(dy, self.x, self.g, self.b, self.mean, self.rstd, self.dg, self.db, act=self.act, dres=dres)
+        self.x = None
+        return dx
+
+
+class Block:
+    """Pre-LN transformer block (model_rad.py:112-133) with fused QKV GEMM."""
+
+    def __init__(self, st, prefix, C, n_head, attn_p, resid_p):
+        self.C, self.nh, self.hs = C, n_head, C // n_head
+        self.attn_p, self.resid_p = attn_p, resid_p
+        self.ln1, self.ln2 = LayerNorm(st, prefix + ".ln1"), LayerNorm(st, prefix + ".ln2")
+        self.qkv = Linear(st, None, keys=[f"{prefix}.attn.{n}" for n in ("key", "query", "value")])
+        self.proj = Linear(st, prefix + ".attn.proj")
+        self.fc1, self.fc2 = Linear(st, prefix + ".mlp.0"), Linear(st, prefix + ".mlp.2")
+
+    def _heads(self, t2d, B, T, col0):
+        """(B*T, 3C) column slice -> (B, nh, T, hs) view"""
+        return t2d[:, col0: col0 + self.C].view(B, T, self.nh, self.hs).permute(0, 2, 1, 3)
+
+    def fwd(self, x, B, T, seed, train):
+        C, nh, hs = self.C, self.nh, self.hs
+        ap, rp = (self.attn_p, self.resid_p) if train else (0.0, 0.0)
+        self.B, self.T, self.seed, self.ap, self.rp = B, T, seed, ap, rp
+        h1 = self.ln1.fwd(x)
+        qkv = self.qkv.fwd(h1)                                       # columns [key | query | value]
+        k, q, v = (self._heads(qkv, B, T, i * C) for i in range(3))
+        S = torch.empty((B, nh, T, T), device=x.device, dtype=torch.float32)
+        ops.gemm(q, k, S)
+        self.P, self.Pd = ops.softmax_fwd(S, 1.0 / math.sqrt(hs), ap, seed)
+        y = torch.empty((B * T, C), device=x.device, dtype=torch.float32)
+        ops.gemm(self.Pd, v.transpose(-1, -2), y.view(B, T, nh, hs).permute(0, 2, 1, 3))
+        self.qkv_out = qkv
+        x1 = self.proj.fwd(y, res=x, drop_p=rp, seed=seed + 1)
+        h2 = self.ln2.fwd(x1)
+        a = self.fc1.fwd(h2, act=1)
+        return self.fc2.fwd(a, res=x1, drop_p=rp, seed=seed + 2)
+
+    def bwd(self, dx2):
+        B, T, C, nh, hs = self.B, self.T, self.C, self.nh, self.hs
+        a = self.fc1.y
+        dz = ops.dropout(dx2, self.rp, self.seed + 2)
+        da = self.fc2.bwd(dz, dx_mask=a)                              # ReLU mask fused into the dgrad GEMM
+        dh2 = self.fc1.bwd(da, masked=True)
+        dx1 = self.ln2.bwd(dh2, dres=dx2)
+        dzp = ops.dropout(dx1, self.rp, self.seed + 1)
+        dy = self.proj.bwd(dzp)
+        qkv = self.qkv_out
+        k, q, v = (self._heads(qkv, B, T, i * C) for i in range(3))
+        dqkv = torch.empty_like(qkv)
+        dk, dq, dv = (self._heads(dqkv, B, T, i * C) for i in range(3))
+        dyh = dy.view(B, T, nh, hs).permute(0, 2, 1, 3)
+        dPd = torch.empty((B, nh, T, T), device=dy.device, dtype=torch.float32)
+        ops.gemm(dyh, v, dPd)
+        ops.gemm(self.Pd.transpose(-1, -2), dyh.transpose(-1, -2), dv)
+        dS = ops.softmax_bwd(self.P, dPd, 1.0 / math.sqrt(hs), self.ap, self.seed)
+        ops.gemm(dS, k.transpose(-1, -2), dq)
+        ops.gemm(dS.transpose(-1, -2), q.transpose(-1, -2), dk)
+        dh1 = self.qkv.bwd(dqkv)
+        self.P = self.Pd = self.qkv_out = None
+        return self.ln1.bwd(dh1, dres=dx1)
+
+
+class FusionGPT:
+    """GPT / RadarGPT (model_rad.py:136-247, :887-1000): pool to 8x8 anchors, add pos/vel
+    embeddings, n_layer blocks, ln_f.  Tokens are modality-major, (row, col) raster order."""
+
+    def __init__(self, st, prefix, C, nmod, cfg, site):
+        self.C, self.nmod, self.T = C, nmod, nmod * 64
+        self.pos, self.dpos = st.p(prefix + ".pos_emb")[0], st.g(prefix + ".pos_emb")[0]
+        self.vw, self.dvw = st.p(prefix + ".vel_emb.weight")[:, 0], st.g(prefix + ".vel_emb.weight")[:, 0]
+        self.vb, self.dvb = st.p(prefix + ".vel_emb.bias"), st.g(prefix + ".vel_emb.bias")
+        self.blocks = [Block(st, f"{prefix}.blocks.{i}", C, cfg.n_head, cfg.attn_pdrop, cfg.resid_pdrop)
+                       for i in range(cfg.n_layer)]
+        self.ln_f = LayerNorm(st, prefix + ".ln_f")
+        self.embd_p, self.site = cfg.embd_pdrop, site
+
+    def fwd(self, feats, velocity, seed, train):
+        B = feats[0].shape[0]
+        self.shape, self.vel = feats[0].shape, velocity
+        self.ep = self.embd_p if train else 0.0
+        self.seed = seed + self.site * 100
+        x = ops.tokens_fwd(feats, self.pos, self.vw, self.vb, velocity, self.ep, self.seed).view(B * self.T, self.C)
+        for i, blk in enumerate(self.blocks):
+            x = blk.fwd(x, B, self.T, self.seed + 3 * i + 1, train)
+        return self.ln_f.fwd(x).view(B, self.T, self.C)
+
+    def bwd(self, dtok_out, dfeats):
+        """dtok_out (B,T,C); dfeats: per-modality feature gradients, accumulated in place."""
+        d = self.ln_f.bwd(dtok_out.view(-1, self.C))
+        for blk in reversed(self.blocks):
+            d = blk.bwd(d)
+        ops.tokens_bwd_(d, dfeats, self.shape, self.vel, self.dpos, self.dvw, self.dvb, self.ep, self.seed)
+
+
+class VectorNet:
+    """VectornetEncoder (model_rad.py:327-417).  Lane-to-lane attention, agent fusion and the
+    generator are evaluated for lane token 0 only -- the only one consumed (:413)."""
+
+    def __init__(self, st, prefix):
+        sg = prefix + ".lane_subgraph.layers.mlp_"
+        self.sub = [(Linear(st, f"{sg}{i}.mlp.0"), LayerNorm(st, f"{sg}{i}.mlp.1", act=1)) for i in range(3)]
+        self.qkv = Linear(st, prefix + ".L2L.to_qkv", bias=False)
+        self.to_out = Linear(st, prefix + ".L2L.to_out.0")
+        self.pos0, self.pos_ln, self.pos3 = Linear(st, prefix + ".pos_emb.0"), LayerNorm(st, prefix + ".pos_emb.1", act=2), Linear(st, prefix + ".pos_emb.3")
+        self.af0, self.af_ln, self.af3 = Linear(st, prefix + ".agent_fusion.0"), LayerNorm(st, prefix + ".agent_fusion.1", act=2), Linear(st, prefix + ".agent_fusion.3")
+        self.g0, self.g_ln, self.g3 = Linear(st, prefix + ".generator.0"), LayerNorm(st, prefix + ".generator.1", act=2), Linear(st, prefix + ".generator.3")
+
+    def fwd(self, lane, lane_num):
+        B, L, P, _ = lane.shape
+        G, V = B * L, P - 1
+        self.G, self.V, self.B, self.L, self.lane_num = G, V, B, L, lane_num
+        x = ops.lane_to_vector(lane)
+        self.args = []
+        for lin, ln in self.sub:
+            x, arg = ops.subgraph_pool_fwd(ln.fwd(lin.fwd(x)), G, V)
+            self.args.append(arg)
+        tok, self.argf = ops.segmax_fwd(x, G, V)
+        self.qkv_out = self.qkv.fwd(tok).view(B, L, 384)
+        self.prob, att0 = ops.l2l_row0_fwd(self.qkv_out, lane_num, 2, None)
+        cat = torch.empty((B, 192), device=lane.device, dtype=torch.float32)
+        self.to_out.fwd(att0, out=cat[:, :128])
+        zeros = torch.zeros((B, 2), device=lane.device, dtype=torch.float32)
+        self.pos3.fwd(self.pos_ln.fwd(self.pos0.fwd(zeros)), out=cat[:, 128:])
+        f = self.af3.fwd(self.af_ln.fwd(self.af0.fwd(cat)))
+        g = self.g3.fwd(self.g_ln.fwd(self.g0.fwd(f)))                 # (B, 64*64*64) channel-major
+        return ops.transpose(g.view(B, 64, 4096)).view(B, 64, 64, 64)   # NHWC
+
+    def bwd(self, dmap):
+        B, L, G, V = self.B, self.L, self.G, self.V
+        dg = ops.transpose(dmap.view(B, 4096, 64)).view(B, 64 * 4096)
+        d = self.g0.bwd(self.g_ln.bwd(self.g3.bwd(dg)))
+        dcat = self.af0.bwd(self.af_ln.bwd(self.af3.bwd(d)))
+        self.pos0.bwd(self.pos_ln.bwd(self.pos3.bwd(dcat[:, 128:])), need_dx=False)
+        datt0 = self.to_out.bwd(dcat[:, :128])
+        dqkv = ops.l2l_row0_bwd(self.qkv_out, self.lane_num, self.prob, datt0, 2)
+        dtok = self.qkv.bwd(dqkv.view(G, 384))
+        d = ops.segmax_bwd(dtok, self.argf, G, V)
+        for i in (2, 1, 0):
+            lin, ln = self.sub[i]
+            d = ops.subgraph_pool_bwd(d, self.args[i], G, V)
+            d = lin.bwd(ln.bwd(d), need_dx=(i > 0))
+        self.args = self.qkv_out = self.prob = None
+
+
+class SpGAT:
+    """Radar graph-attention encoder (model_rad.py:778-884)."""
+
+    def __init__(self, st, prefix, cfg):
+        self.nh, self.hid, self.alpha, self.p = cfg.nb_heads, cfg.hidden, cfg.alpha, cfg.attn_pdrop
+        self.W = [(st.p(f"{prefix}.attention_{i}.W"), st.g(f"{prefix}.attention_{i}.W")) for i in range(self.nh)]
+        self.a = [(st.p(f"{prefix}.attention_{i}.a"), st.g(f"{prefix}.attention_{i}.a")) for i in range(self.nh)]
+        self.m1, self.m2 = Linear(st, prefix + ".mlp_1.0"), Linear(st, prefix + ".mlp_2.0")
+
+    def fwd(self, radar, adj, seed, train):
+        B, N, nh, hid = radar.shape[0], radar.shape[1], self.nh, self.hid
+        dev = radar.device
+        p = self.p if train else 0.0
+        self.pp, self.seed, self.adj, self.B = p, seed, adj, B
+        self.x = ops.dropout(radar, p, seed)
+        E = 2 * hid
+        self.Wh = torch.empty((nh, B, N, E), device=dev, dtype=torch.float32)
+        self.z = torch.empty((nh, B, N, N), device=dev, dtype=torch.float32)
+        hp = torch.empty((nh, B, N, E), device=dev, dtype=torch.float32)
+        self.att, self.attd = [], []
+        for i in range(nh):
+            ops.gemm(self.x, self.W[i][0].t().unsqueeze(0), self.Wh[i])
+            ops.gemm(self.Wh[i], self.a[i][0].t().unsqueeze(0), self.z[i])
+            att, attd = ops.gat_softmax_fwd(self.z[i], adj, self.alpha, p, seed + 1 + i)
+            self.att.append(att)
+            self.attd.append(attd)
+            ops.gemm(attd, self.Wh[i].transpose(-1, -2), hp[i])
+        self.e1 = ops.elu_fwd(hp)
+        e1d = ops.dropout(self.e1, p, seed + 5)
+        self.e2 = ops.elu_fwd(e1d)
+        o1 = torch.empty((B, nh * N, 256), device=dev, dtype=torch.float32)
+        for i in range(nh):
+            ops.gemm(self.e2[i], self.m1.w.unsqueeze(0), o1[:, i * N:(i + 1) * N, :], bias=self.m1.b)
+        self.o1d = ops.dropout(o1, p, seed + 6)
+        o2 = torch.empty((B, 256, 128), device=dev, dtype=torch.float32)
+        ops.gemm(self.o1d.transpose(1, 2), self.m2.w.unsqueeze(0), o2, bias=self.m2.b)
+        o2d = ops.dropout(o2, p, seed + 7)
+        self.y = ops.radar_logsoftmax_fwd(o2d, B, 512)
+        return self.y
+
+    def bwd(self, dy):
+        B, nh, N = self.B, self.nh, self.e2.shape[2]
+        p, seed = self.pp, self.seed
+        do2 = ops.dropout(ops.radar_logsoftmax_bwd(dy, self.y).view(B, 256, 128), p, seed + 7)
+        # o2 = o1d^T W2^T + b2
+        ops.colsum_(do2.view(B * 256, 128), self.m2.db)
+        ops.gemm(do2.transpose(1, 2), self.o1d, self.m2.dw.unsqueeze(0).expand(B, -1, -1), accum=2)   # sum over b
+        do1dT = torch.empty((B, 256, nh * N), device=dy.device, dtype=torch.float32)
+        ops.gemm(do2, self.m2.w.t().unsqueeze(0), do1dT)
+        do1 = ops.dropout(ops.transpose(do1dT), p, seed + 6)                  # (B, nh*N, 256)
+        ops.colsum_(do1.view(B * nh * N, 256), self.m1.db)
+        de2 = torch.empty_like(self.e2)
+        for i in range(nh):
+            sl = do1[:, i * N:(i + 1) * N, :]
+            ops.gemm(sl.transpose(1, 2), self.e2[i].transpose(1, 2), self.m1.dw.unsqueeze(0).expand(B, -1, -1), accum=2)
+            ops.gemm(sl, self.m1.w.t().unsqueeze(0), de2[i])
+        de1 = ops.elu_bwd(ops.dropout(ops.elu_bwd(de2, self.e2), p, seed + 5), self.e1)   # (nh,B,N,E)
+        for i in range(nh):
+            Wh, attd = self.Wh[i], self.attd[i]
+            dattd = torch.empty_like(attd)
+            ops.gemm(de1[i], Wh, dattd)                                        # d(attd) = dhp Wh^T
+            dWh = torch.empty_like(Wh)
+            ops.gemm(attd.transpose(-1, -2), de1[i].transpose(-1, -2), dWh)    # attd^T dhp
+            dz = ops.gat_softmax_bwd(self.z[i], self.adj, self.att[i], dattd, self.alpha, p, seed + 1 + i)
+            E = Wh.shape[-1]
+            ops.gemm(Wh.reshape(B * N, E).t(), dz.reshape(B * N, N).t(), self.a[i][1], accum=1)   # da = Wh^T dz
+            ops.gemm(dz, self.a[i][0].unsqueeze(0), dWh, accum=1)              # dWh += dz a^T
+            ops.gemm(self.x.reshape(B * N, -1).t(), dWh.reshape(B * N, E).t(), self.W[i][1], accum=1)   # dW = x^T dWh
+        self.Wh = self.z = self.att = self.attd = self.e1 = self.e2 = self.o1d = self.y = None
+
+
+class Head:
+    """join MLP + GRU waypoint roll-out + L1 loss (model_rad.py:655-695, phase2_train_net.py:104)."""
+
+    def __init__(self, st, pred_len):
+        self.j = [Linear(st, f"join.{i}") for i in (0, 2, 4)]
+        names = ("decoder.weight_ih", "decoder.weight_hh", "decoder.bias_ih", "decoder.bias_hh", "output.weight", "output.bias")
+        self.P = [st.p(n) for n in names]
+        self.G = [st.g(n) for n in names]
+        self.steps = pred_len
+
+    def fwd(self, fused, target_point):
+        z = fused
+        for lin in self.j:
+            z = lin.fwd(z, act=1)
+        pred, self.ctx = ops.gru_head_fwd(z, target_point, *self.P, self.steps)
+        return pred
+
+    def bwd(self, dpred):
+        P, G = self.P, self.G
+        d = ops.gru_head_bwd(dpred, self.ctx, P[0], P[1], P[4], G[0], G[1], G[2], G[3], G[4], G[5])
+        for lin in reversed(self.j):
+            d = lin.bwd(d)
+        self.ctx = None
+        return d
+
+
+# --------------------------------------------------------------------------- the network
+class _Net:
+    """Kernel schedule of Encoder.forward (model_rad.py:492-611) + head, forward and backward."""
+
+    def __init__(self, st, cfg):
+        e = "encoder."
+        self.cfg = cfg
+        ip, mp, lp = e + "image_encoder.features", e + "img_map_encoder.features", e + "lidar_encoder._model"
+        self.img_stem, self.lid_stem = Stem(st, ip), Stem(st, lp)
+        self.img_layers = [ResLayer(st, f"{ip}.layer{i + 1}", RESNET34[i], 1 if i == 0 else 2) for i in range(4)]
+        self.lid_layers = [ResLayer(st, f"{lp}.layer{i + 1}", RESNET18[i], 1 if i == 0 else 2) for i in range(4)]
+        self.map_layers = [None] + [ResLayer(st, f"{mp}.layer{i + 1}", RESNET34[i], 2) for i in range(1, 4)]
+        self.vectornet = VectorNet(st, e + "vectornet_encoder")
+        self.gat = SpGAT(st, e + "radar_encoder", cfg)
+        self.gpts = [FusionGPT(st, f"{e}transformer{i + 1}", WIDTHS[i], 3 if i < 3 else 4, cfg, i) for i in range(4)]
+        self.head = Head(st, cfg.pred_len)
+        dev = st.device
+        self.mean = torch.tensor(IMAGENET_MEAN, device=dev, dtype=torch.float32)
+        self.std = torch.tensor(IMAGENET_STD, device=dev, dtype=torch.float32)
+
+    def forward(self, image, lidar, lane, lane_num, radar, radar_adj, target_point, velocity, seed, train):
+        img = self.img_stem.fwd(ops.nchw_to_nhwc(image, self.mean, self.std), train)
+        lid = self.lid_stem.fwd(ops.nchw_to_nhwc(lidar), train)
+        img = self.img_layers[0].fwd(img, train)
+        lid = self.lid_layers[0].fwd(lid, train)
+        mp = self.vectornet.fwd(lane, lane_num)
+        for s in range(3):
+            tok = self.gpts[s].fwd([img, lid, mp], velocity, seed, train)
+            img, lid, mp = (ops.upsample_add_fwd(f, tok, m) for m, f in enumerate((img, lid, mp)))
+            img = self.img_layers[s + 1].fwd(img, train)
+            mp = self.map_layers[s + 1].fwd(mp, train)
+            lid = self.lid_layers[s + 1].fwd(lid, train)
+        rad = self.gat.fwd(radar, radar_adj, seed + 900, train)
+        feats = [img, lid, mp, rad]
+        tok = self.gpts[3].fwd(feats, velocity, seed, train)
+        fused = ops.pool_sum_fwd(feats, tok)
+        return self.head.fwd(fused, target_point)
+
+    def backward(self, dpred):
+        dfused = self.head.bwd(dpred)
+        dfe, dtok = ops.pool_sum_bwd(dfused, 4)
+        self.gpts[3].bwd(dtok, dfe)
+        self.gat.bwd(dfe[3])
+        dimg, dlid, dmp = dfe[0], dfe[1], dfe[2]
+        for s in (2, 1, 0):
+            dimg = self.img_layers[s + 1].bwd(dimg)
+            dmp = self.map_layers[s + 1].bwd(dmp)
+            dlid = self.lid_layers[s + 1].bwd(dlid)
+            B, H, W, C = dimg.shape
+            dtok = torch.empty((B, 192, C), device=dimg.device, dtype=torch.float32)
+            for m, d in enumerate((dimg, dlid, dmp)):
+                ops.upsample_add_bwd_(d, dtok, m)
+            self.gpts[s].bwd(dtok, [dimg, dlid, dmp])
+        self.vectornet.bwd(dmp)
+        self.img_stem.bwd(self.img_layers[0].bwd(dimg))
+        self.lid_stem.bwd(self.lid_layers[0].bwd(dlid))
+
+
+class _WholeNet(torch.autograd.Function):
+    """Lets `loss.backward()` (Engine.train, phase2_train_net.py:108) drive the hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, model, inputs, *params):
+        ctx.model = model
+        with torch.no_grad():
+            return model._forward_impl(*inputs)
+
+    @staticmethod
+    def backward(ctx, dpred):
+        m = ctx.model
+        m.store.flat_grad.zero_()
+        m.net.backward(dpred.contiguous())
+        grads = []
+        for k, p in m._param_items:
+            grads.append(None if is_unused(k) else m.store.torch_view(k, grad=True).clone())
+        return (None, None, *grads)
+
+
+class PIDController:
+    def __init__(self, K_P=1.0, K_I=0.0, K_D=0.0, n=20):
+        self._K_P, self._K_I, self._K_D = K_P, K_I, K_D
+        self._window = deque([0 for _ in range(n)], maxlen=n)
+
+    def step(self, error):
+        self._window.append(error)
+        if len(self._window) >= 2:
+            integral, derivative = np.mean(self._window), self._window[-1] - self._window[-2]
+        else:
+            integral, derivative = 0.0, 0.0
+        return self._K_P * error + self._K_I * integral + self._K_D * derivative
+
+
+class MMFN(nn.Module):
+    def __init__(self, config, device):
+        super().__init__()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ops.MmfnError("mmfn_b200.MMFN runs on CUDA (sm_100a) only; there is no CPU path")
+        self.config = config
+        self.pred_len = config.pred_len
+        self.turn_controller = PIDController(config.turn_KP, config.turn_KI, config.turn_KD, config.turn_n)
+        self.speed_controller = PIDController(config.speed_KP, config.speed_KI, config.speed_KD, config.speed_n)
+        self.store = ParamStore(config, self.device)
+        self.store.register(self)
+        self._param_items = list(self.named_parameters())
+        self.net = _Net(self.store, config)
+        self.seed = 0
+        self.reset_parameters()
+
+    # ---- initialisation following the reference constructors ---------------------------------
+    @torch.no_grad()
+    def reset_parameters(self, seed=42):
+        g = torch.Generator().manual_seed(seed)
+        for k, p in self._param_items:
+            shape, leaf = tuple(p.shape), k.split(".")[-1]
+            if p.dim() == 4:                                          # torchvision: kaiming_normal_(fan_out, relu)
+                t = torch.randn(shape, generator=g) * math.sqrt(2.0 / (shape[0] * shape[2] * shape[3]))
+            elif leaf == "pos_emb":
+                t = torch.zeros(shape)
+            elif leaf in ("W", "a"):                                  # xavier_normal_(gain=1.414), model_rad.py:790-794
+                t = torch.randn(shape, generator=g) * 1.414 * math.sqrt(2.0 / (shape[0] + shape[1]))
+            elif ".transformer" in k:                                 # GPT._init_weights, model_rad.py:170-177
+                t = torch.ones(shape) if (".ln" in k and leaf == "weight") else (
+                    torch.randn(shape, generator=g) * 0.02 if p.dim() == 2 else torch.zeros(shape))
+            elif p.dim() == 2:                                        # nn.Linear / GRUCell default
+                fan_in = 64 if k.startswith("decoder") else shape[1]
+                t = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan_in)
+            else:
+                is_norm = leaf == "weight"
+                if is_norm:
+                    t = torch.ones(shape)
+                elif ".bn" in k or "downsample.1" in k or _is_ln_bias(k):
+                    t = torch.zeros(shape)
+                else:
+                    fan_in = 64 if k.startswith("decoder") else self._fan_in_of_bias(k)
+                    t = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan_in)
+            p.copy_(t.to(self.device))
+        for k, b in self.named_buffers():
+            if k.endswith("running_mean"):
+                b.zero_()
+            elif k.endswith("running_var"):
+                b.fill_(1.0)
+            else:
+                b.zero_()
+
+    def _fan_in_of_bias(self, k):
+        w = k[: -len("bias")] + "weight"
+        return self.store.shapes[w][1] if w in self.store.shapes else 64
+
+    # ---- reference surface -----------------------------------------------------------------------
+    def forward(self, image_list, lidar_list, map_list, vectormaps_list, radar_list, radar_adj, target_point, velocity):
+        lane = vectormaps_list[0][0]
+        lane_num = vectormaps_list[1][0]
+        inputs = (image_list[0], lidar_list[0], lane, lane_num, radar_list[0], radar_adj[0], target_point, velocity)
+        if torch.is_grad_enabled() and self.training:
+            return _WholeNet.apply(self, inputs, *[p for _, p in self._param_items])
+        with torch.no_grad():
+            return self._forward_impl(*inputs)
+
+    def _forward_impl(self, image, lidar, lane, lane_num, radar, radar_adj, target_point, velocity):
+        f32 = lambda t: t.to(device=self.device, dtype=torch.float32).contiguous()
+        if image.dtype == torch.uint8:                     # camera bytes are converted inside the layout kernel
+            image = image.to(self.device).contiguous()
+        else:
+            image = f32(image)
+        lidar, lane, radar, radar_adj, target_point, velocity = map(
+            f32, (lidar, lane, radar, radar_adj, target_point, velocity))
+        lane_num = lane_num.to(device=self.device, dtype=torch.int32).contiguous()
+        if self.training:
+            self.seed += 1000
+            self.store.flat_nbt.add_(self._nbt_step())     # BatchNorm.num_batches_tracked
+        return self.net.forward(image, lidar, lane, lane_num, radar, radar_adj, target_point, velocity,
+                                self.seed, self.training)
+
+    def _nbt_step(self):
+        """+1 for every BatchNorm that runs; the map ResNet's stem/layer1 BNs never do (stay 0)."""
+        if not hasattr(self, "_nbt_inc"):
+            inc = [0 if is_unused(k) else 1 for k in self.store.nbt_index]
+            self._nbt_inc = torch.tensor(inc, device=self.device, dtype=torch.int64)
+        return self._nbt_inc
+
+    def control_pid(self, waypoints, velocity):
+        """PID steering/throttle from predicted waypoints (model_rad.py:697-739); CPU, inference only."""
+        assert waypoints.size(0) == 1
+        wp = waypoints[0].data.cpu().numpy()
+        wp[:, 1] *= -1                                     # forward is negative y in the waypoint frame
+        speed = velocity[0].data.cpu().numpy()
+        cfg = self.config
+        desired_speed = np.linalg.norm(wp[0] - wp[1]) * 2.0
+        brake = desired_speed < cfg.brake_speed or (speed / desired_speed) > cfg.brake_ratio
+        aim = (wp[1] + wp[0]) / 2.0
+        angle = np.degrees(np.pi / 2 - np.arctan2(aim[1], aim[0])) / 90
+        if speed < 0.01:
+            angle = np.array(0.0)
+        steer = np.clip(self.turn_controller.step(angle), -1.0, 1.0)
+        delta = np.clip(desired_speed - speed, 0.0, cfg.clip_delta)
+        throttle = np.clip(self.speed_controller.step(delta), 0.0, cfg.max_throttle)
+        throttle = throttle if not brake else 0.0
+        metadata = {
+            "speed": float(speed.astype(np.float64)), "steer": float(steer), "throttle": float(throttle),
+            "brake": float(brake), "wp_2": tuple(wp[1].astype(np.float64)), "wp_1": tuple(wp[0].astype(np.float64)),
+            "desired_speed": float(desired_speed.astype(np.float64)), "angle": float(angle.astype(np.float64)),
+            "aim": tuple(aim.astype(np.float64)), "delta": float(delta.astype(np.float64)),
+        }
+        return steer, throttle, brake, metadata
+
+
+def _is_ln_bias(k):
+    return any(s in k for s in ("mlp.1.bias", "pos_emb.1.bias", "agent_fusion.1.bias", "generator.1.bias"))

@@ -169,7 +169,11 @@ def nchw_to_nhwc(x, mean=None, std=None):
     B, C, H, W = x.shape
     assert x.is_contiguous()
     y = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
-    lib().nchw_to_nhwc_f32(_p(x), _p(y), B, C, H, W, _p(mean), _p(std), _st())
+    if x.dtype == torch.uint8:
+        lib().nchw_u8_to_nhwc_f32(x.data_ptr(), _p(y), B, C, H, W, _p(mean), _p(std), _st())
+    else:
+        _chk(x, "nchw input")
+        lib().nchw_to_nhwc_f32(_p(x), _p(y), B, C, H, W, _p(mean), _p(std), _st())
     return y
 
 
@@ -315,9 +319,17 @@ def elu_bwd(dy, y):
     return dx
 
 
+def relu_bwd(dy, y):
+    assert dy.is_contiguous() and y.is_contiguous()
+    dx = torch.empty_like(y)
+    lib().relu_bwd(_p(dy), _p(y), _p(dx), y.numel(), _st())
+    return dx
+
+
 def dropout(x, p, seed):
     if p <= 0:
         return x
+    assert x.is_contiguous()
     y = torch.empty_like(x)
     lib().dropout_f32(_p(x), _p(y), x.numel(), p, seed, _st())
     return y

@@ -1,0 +1,78 @@
+"""CPU: the C-ABI library loads and exports exactly what include/mmfn_b200.h declares; the header
+is in sync with the sources; the product package never imports the oracle."""
+import ctypes
+import glob
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_in_sync_with_sources():
+    assert subprocess.call([sys.executable, os.path.join(ROOT, "tools", "gen_header.py"), "--check"]) == 0
+
+
+def test_library_exports_every_declared_symbol():
+    from mmfn_b200._lib import LIB_PATH, parse_header
+    protos = parse_header()
+    assert len(protos) >= 45
+    dll = ctypes.CDLL(LIB_PATH)
+    for name in protos:
+        assert hasattr(dll, name), name
+    dll.mmfn_version.restype = ctypes.c_int
+    assert dll.mmfn_version() >= 100
+    out = subprocess.run(["nm", "-D", "--defined-only", LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (mmfn_\w+)", out))
+    assert exported == set(protos), exported ^ set(protos)
+
+
+def test_argument_validation_without_gpu():
+    """Bad arguments are rejected before any launch (so this runs on a CPU-only box)."""
+    from mmfn_b200._lib import lib, MmfnError
+    import pytest
+    with pytest.raises(MmfnError, match="pt_stride"):
+        lib().bev_scatter(16, 1, 10, 2, 16, 0, None)
+    with pytest.raises(MmfnError, match="null"):
+        lib().gemm_f32(0, 1, 1, 0, 0, 0, 1, 1, 0, 0, 0, 1, 0, 0, 4, 4, 4, 1, 1, 0, 0, 0, 1.0, 0, 0, 0.0, 0, 1, None)
+
+
+def test_product_never_imports_oracle():
+    for path in glob.glob(os.path.join(ROOT, "mmfn_b200", "**", "*.py"), recursive=True):
+        src = open(path).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), path
+
+
+def test_sass_is_sm100a():
+    from mmfn_b200._lib import LIB_PATH
+    out = subprocess.run(["cuobjdump", "-lelf", LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out[:200]
+
+
+def test_param_spec_matches_reference_state_dict():
+    import json
+    import torch
+    from mmfn_b200.config import GlobalConfig
+    from mmfn_b200.params import ParamStore, param_spec, is_unused
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_keys.json")))
+    spec = param_spec(GlobalConfig())
+    assert [k for k, _, _ in spec] == list(gold.keys())
+    for k, shape, kind in spec:
+        assert list(shape) == gold[k][0], k
+        assert gold[k][1] == ("torch.int64" if kind == "nbt" else "torch.float32")
+    st = ParamStore(GlobalConfig(), "cpu")
+    root = torch.nn.Module()
+    st.register(root)
+    sd = root.state_dict()
+    assert list(sd.keys()) == list(gold.keys())
+    assert sum(p.numel() for p in root.parameters()) == 104939738
+    assert sum(1 for k, _ in root.named_parameters() if is_unused(k)) == 21
+    # conv filters are stored KRSC but presented with the reference (K,C,R,S) shape
+    w = dict(root.named_parameters())["encoder.image_encoder.features.layer1.0.conv1.weight"]
+    assert tuple(w.shape) == (64, 64, 3, 3) and w.stride() == (576, 1, 192, 64)
+    # load_state_dict round trip keeps the aliasing with the flat buffer
+    from mmfn_b200 import synthetic
+    root.load_state_dict(synthetic.fill_golden_weights(sd, 1))
+    k = "encoder.transformer4.blocks.7.mlp.2.bias"
+    assert torch.equal(st.p(k), synthetic.fill_golden_weights({k: sd[k]}, 1)[k])
