@@ -59,14 +59,51 @@ class _Lib:
         self._dll.mmfn_last_error(buf, 512)
         return buf.value.decode()
 
+    # kernels launched per C-ABI call when it is not exactly one (for the bench's launch count)
+    KERNELS_PER_CALL = {"mmfn_bn_train_fwd": 3, "mmfn_bn_eval_fwd": 2, "mmfn_bn_train_bwd": 2,
+                        "mmfn_adamw_step": 2, "mmfn_tokens_bwd": 4}
+
     def _wrap(self, name, fn):
+        nk = self.KERNELS_PER_CALL.get(name, 1)
+        short = name[len("mmfn_"):]
+
         def call(*args):
-            rc = fn(*args)
-            self.launches += 1
+            prof = self.profile
+            if prof is not None:
+                import torch
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = fn(*args)
+                e1.record()
+                prof.append((short, self.next_work, e0, e1))
+            else:
+                rc = fn(*args)
+            self.next_work = None
+            self.launches += nk
             if rc != 0:
                 raise MmfnError(f"{name} failed (code {rc}): {self.last_error()}")
         call.__name__ = name
         return call
+
+    # ---- optional per-call device timing (bench.py roofline leg) -------------------------------
+    profile = None        # list of (fn, (flops, bytes) | None, start_event, end_event) while enabled
+    next_work = None      # set by ops wrappers right before a call: algorithmic (flops, bytes)
+
+    def start_profile(self):
+        self.profile = []
+
+    def stop_profile(self):
+        """-> {fn: dict(calls, ms, flops, bytes)}; caller must have synchronised the device."""
+        out = {}
+        for fn, work, e0, e1 in self.profile or []:
+            d = out.setdefault(fn, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
+            d["calls"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            if work:
+                d["flops"] += work[0]
+                d["bytes"] += work[1]
+        self.profile = None
+        return out
 
 
 _lib = None

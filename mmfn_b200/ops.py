@@ -48,6 +48,8 @@ def gemm(A, B, C, *, bias=None, res=None, mask=None, alpha=1.0, act=0, accum=0,
     for t in (res, mask):
         if t is not None:
             assert t.shape == C.shape and t.stride() == C.stride()
+    nbt = nb[0] * nb[1]
+    lib().next_work = (2.0 * M * N * K * nbt, 4.0 * nbt * (M * K + N * K + M * N))
     lib().gemm_f32(_p(A), A.stride(-2), A.stride(-1), a_b[0], a_b[1],
                    _p(B), B.stride(-2), B.stride(-1), b_b[0], b_b[1],
                    _p(C), C.stride(-2), c_b[0], c_b[1],
@@ -67,12 +69,18 @@ def conv_out_hw(H, W, R, S, stride, pad):
     return (H + 2 * pad - R) // stride + 1, (W + 2 * pad - S) // stride + 1
 
 
+def _conv_work(N, H, W, C, Co, R, S, Ho, Wo):
+    """algorithmic (flops, bytes) of one conv pass: 2*MACs; input + filter + output read/written once"""
+    return (2.0 * N * Ho * Wo * Co * R * S * C, 4.0 * (N * H * W * C + Co * R * S * C + N * Ho * Wo * Co))
+
+
 def conv2d_fwd(x, w_krsc, stride, pad):
     N, H, W, C = x.shape
     Co, R, S, C2 = w_krsc.shape
     assert C2 == C and x.is_contiguous() and w_krsc.is_contiguous()
     Ho, Wo = conv_out_hw(H, W, R, S, stride, pad)
     y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
+    lib().next_work = _conv_work(N, H, W, C, Co, R, S, Ho, Wo)
     lib().conv2d_fwd_f32(_p(x), _p(w_krsc), _p(y), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, _st())
     return y
 
@@ -90,6 +98,7 @@ def conv2d_dgrad(dy, w_krsc, x_shape, stride, pad, res=None):
     _, Ho, Wo, _ = dy.shape
     wt = filter_crsk(w_krsc)
     dx = torch.empty(x_shape, device=dy.device, dtype=torch.float32)
+    lib().next_work = _conv_work(N, H, W, C, Co, R, S, Ho, Wo)
     lib().conv2d_dgrad_f32(_p(dy), _p(wt), _p(dx), _p(res), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, _st())
     return dx
 
@@ -100,6 +109,7 @@ def conv2d_wgrad_(dy, x, dw_krsc, stride, pad):
     Co, R, S, _ = dw_krsc.shape
     _, Ho, Wo, _ = dy.shape
     assert dw_krsc.is_contiguous()
+    lib().next_work = _conv_work(N, H, W, C, Co, R, S, Ho, Wo)
     lib().conv2d_wgrad_f32(_p(dy), _p(x), _p(dw_krsc), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, 0, _st())
 
 
