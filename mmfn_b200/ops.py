@@ -21,6 +21,22 @@ def _chk(t, name="tensor"):
         raise MmfnError(f"{name}: expected a CUDA float32 tensor, got {t.device}/{t.dtype}")
 
 
+TF32 = True   # large aligned GEMMs/convs run on the tcgen05 TF32 path; False = exact fp32 SIMT everywhere
+
+
+def _major(t):
+    """-> (is_mn_major, pitch) when `t` (.., rows, red) is TMA-addressable as a 2-D fp32 matrix, else None."""
+    rows, red = t.shape[-2], t.shape[-1]
+    sr, sc = t.stride(-2), t.stride(-1)
+    if t.data_ptr() % 16:
+        return None
+    if sc == 1 and sr % 4 == 0 and sr >= red:
+        return (0, sr)
+    if sr == 1 and sc % 4 == 0 and sc >= rows:
+        return (1, sc)
+    return None
+
+
 def gemm(A, B, C, *, bias=None, res=None, mask=None, alpha=1.0, act=0, accum=0,
          drop_p=0.0, seed=0, splitk=1):
     """C[..., M, N] (+)= alpha * A[..., M, K] @ B[..., N, K]^T  with up to two leading batch dims.
@@ -50,6 +66,15 @@ def gemm(A, B, C, *, bias=None, res=None, mask=None, alpha=1.0, act=0, accum=0,
             assert t.shape == C.shape and t.stride() == C.stride()
     nbt = nb[0] * nb[1]
     lib().next_work = (2.0 * M * N * K * nbt, 4.0 * nbt * (M * K + N * K + M * N))
+    if TF32 and nbt == 1 and M >= 64 and K >= 32 and M * N * K >= (1 << 18):
+        am, bm = _major(A), _major(B)
+        if am is not None and bm is not None and C.stride(-1) == 1:
+            if accum == 1:          # plain += is a single-writer RMW; tensor-core path accumulates atomically
+                accum = 2
+            lib().gemm_tf32(_p(A), am[1], am[0], _p(B), bm[1], bm[0], _p(C), C.stride(-2), M, N, K,
+                            _p(bias), _p(res), _p(mask), float(alpha), int(act), int(accum), float(drop_p),
+                            int(seed), int(splitk) if splitk > 1 else 0, _st())
+            return C
     lib().gemm_f32(_p(A), A.stride(-2), A.stride(-1), a_b[0], a_b[1],
                    _p(B), B.stride(-2), B.stride(-1), b_b[0], b_b[1],
                    _p(C), C.stride(-2), c_b[0], c_b[1],

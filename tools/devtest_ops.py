@@ -331,8 +331,59 @@ def t_bev():
             print(("OK  " if ok else "FAIL"), f"bev_scatter n={n} stride={s} strips={strips} bit-exact={ok}", flush=True)
 
 
+
+
+def t_gemm_tc():
+    """tcgen05 TF32 GEMM: all four operand-major combinations, tails, epilogues, split-K."""
+    from mmfn_b200._lib import lib
+    st = torch.cuda.current_stream().cuda_stream
+    for (M, N, K) in [(128, 64, 32), (256, 128, 64), (3072, 192, 64), (200, 72, 100), (4096, 512, 2048), (512, 512, 4096)]:
+        for a_mn in (0, 1):
+            for b_mn in (0, 1):
+                A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev)
+                Ast = A.t().contiguous() if a_mn else A
+                Bst = B.t().contiguous() if b_mn else B
+                C = torch.empty(M, N, device=dev)
+                lib().gemm_tf32(Ast.data_ptr(), Ast.stride(0), a_mn, Bst.data_ptr(), Bst.stride(0), b_mn, C.data_ptr(), N,
+                                M, N, K, 0, 0, 0, 1.0, 0, 0, 0.0, 0, 1, st)
+                torch.cuda.synchronize()
+                ref = A.double() @ B.double().t()
+                err = (C.double() - ref).abs().max().item() / ref.abs().max().item()
+                ok = err < 2e-3
+                results.append((f"gemm_tc {M}x{N}x{K} a_mn{a_mn} b_mn{b_mn}", ok, err, 1))
+                print(("OK  " if ok else "FAIL"), f"gemm_tc {M}x{N}x{K} a_mn={a_mn} b_mn={b_mn} relerr={err:.2e}", flush=True)
+    # epilogue + split-K through ops.gemm
+    ops.TF32 = True
+    M, N, K = 3072, 256, 1024
+    A = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev) * 0.05
+    bias = torch.randn(N, device=dev); res = torch.randn(M, N, device=dev); msk = torch.randn(M, N, device=dev)
+    C = torch.empty(M, N, device=dev)
+    ops.gemm(A, W, C, bias=bias, res=res, act=1)
+    report("ops.gemm tc bias+relu+res", C, torch.relu(A @ W.t() + bias) + res, tol=3e-3)
+    ops.gemm(A, W, C, mask=msk, alpha=0.5)
+    report("ops.gemm tc mask+alpha", C, 0.5 * (A @ W.t()) * (msk > 0), tol=3e-3)
+    dY = torch.randn(M, N, device=dev)
+    dW = torch.ones(N, K, device=dev)
+    ops.gemm(dY.t(), A.t(), dW, accum=1)
+    report("ops.gemm tc wgrad (MN,MN) split-K", dW, 1 + dY.t() @ A, tol=3e-3)
+    dX = torch.empty(M, K, device=dev)
+    ops.gemm(dY, W.t(), dX)
+    report("ops.gemm tc dgrad (K,MN)", dX, dY @ W, tol=3e-3)
+    C1 = torch.empty(M, N, device=dev); C2 = torch.empty(M, N, device=dev)
+    ops.gemm(A, W, C1, drop_p=0.1, seed=5)
+    ops.TF32 = False
+    ops.gemm(A, W, C2, drop_p=0.1, seed=5)
+    same_mask = ((C1 == 0) == (C2 == 0)).float().mean().item()
+    results.append(("tc/simt dropout mask identical", same_mask == 1.0, same_mask, 1)); print("dropout mask agreement", same_mask)
+    ops.TF32 = True
+
+
 if __name__ == "__main__":
-    for fn in (t_gemm, t_conv, t_bn, t_ln, t_pool, t_tokens, t_softmax, t_misc, t_head, t_bev):
+    only = sys.argv[1:]
+    ops.TF32 = False
+    for fn in (t_gemm, t_conv, t_bn, t_ln, t_pool, t_tokens, t_softmax, t_misc, t_head, t_bev, t_gemm_tc):
+        if only and fn.__name__ not in only:
+            continue
         run(fn)
     bad = [r for r in results if not r[1]]
     print(f"\n{len(results) - len(bad)}/{len(results)} checks passed")
