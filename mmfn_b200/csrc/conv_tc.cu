@@ -1,0 +1,210 @@
+// TF32 tensor-core implicit-GEMM convolutions for the ResNet trunks (torchvision BasicBlock convs;
+// call sites model_rad.py:523-525, :542-544, :560-562, :577-579), NHWC activations, KRSC filters.
+//
+// No im2col buffer exists anywhere: the activation operand is fetched by 4-D TMA boxes
+// (channels x W x H x image) whose start coordinate carries the filter-tap offset; out-of-bounds
+// rows/columns (the zero padding) are filled by the TMA unit, strided convolutions use the tensor
+// map's traversal stride.
+//   forward / data-gradient : M = 128 output pixels (image x rows x cols patch), N = Co tile,
+//                             K loops over (tap, 32-channel chunk); both operands K-major.
+//   weight-gradient         : M = Co tile, N = Ci tile, K loops over 32-pixel patches; both operands
+//                             MN-major (pixels are the slow dimension of dY and x); one CTA per
+//                             (tap, split) accumulates atomically into dW.
+#include "tc_kernel.cuh"
+
+namespace {
+
+struct ConvGeomTc {
+  int N, H, W, C;        // input
+  int Co, R, S, stride, pad;
+  int Ho, Wo;
+  int BW, BH, BI;        // pixel patch of one tile / k-block
+  int tiles_w, tiles_h, tiles_n;
+};
+
+template <int TBN>
+struct ConvFwdOp {
+  static constexpr bool A_MN = false, B_MN = false;
+  ConvGeomTc g;
+  int w0, h0, i0, co0;
+  __device__ void setup() {
+    int t = blockIdx.y;
+    int tw = t % g.tiles_w; t /= g.tiles_w;
+    int th = t % g.tiles_h;
+    int tn = t / g.tiles_h;
+    w0 = tw * g.BW; h0 = th * g.BH; i0 = tn * g.BI;
+    co0 = blockIdx.x * TBN;
+  }
+  __device__ int kb_begin() const { return 0; }
+  __device__ int kb_end() const { return g.R * g.S * (g.C / 32); }
+  __device__ void load(int kb, uint8_t* sa, uint8_t* sb, uint64_t* bar, const CUtensorMap* ta, const CUtensorMap* tb) const {
+    int cch = g.C / 32;
+    int tap = kb / cch, cc = kb - tap * cch;
+    int r = tap / g.S, s = tap - r * g.S;
+    tc::tma_load_4d(sa, ta, bar, cc * 32, w0 * g.stride - g.pad + s, h0 * g.stride - g.pad + r, i0);
+    tc::tma_load_2d(sb, tb, bar, tap * g.C + cc * 32, co0);
+  }
+  __device__ bool out_row(int r, int64_t& off) const {
+    int per = g.BH * g.BW;
+    int img = r / per, rem = r - img * per;
+    int hh = rem / g.BW, ww = rem - hh * g.BW;
+    int n = i0 + img, h = h0 + hh, w = w0 + ww;
+    off = (((int64_t)n * g.Ho + h) * g.Wo + w) * g.Co;
+    return n < g.N && h < g.Ho && w < g.Wo;
+  }
+  __device__ int n_cols() const { return g.Co; }
+  __device__ int col0() const { return co0; }
+  __device__ bool first_split() const { return true; }
+};
+
+template <int TBN>
+struct ConvWgradOp {
+  static constexpr bool A_MN = true, B_MN = true;
+  ConvGeomTc g;
+  int splitk, pb_per_split;
+  int tap, r_tap, s_tap, co0, ci0, pb0, pb1;
+  __device__ void setup() {
+    tap = blockIdx.z / splitk;
+    int split = blockIdx.z - tap * splitk;
+    r_tap = tap / g.S; s_tap = tap - r_tap * g.S;
+    co0 = blockIdx.y * tc::TBM;
+    ci0 = blockIdx.x * TBN;
+    int npb = g.tiles_w * g.tiles_h * g.tiles_n;
+    pb0 = split * pb_per_split;
+    pb1 = min(npb, pb0 + pb_per_split);
+  }
+  __device__ int kb_begin() const { return pb0; }
+  __device__ int kb_end() const { return pb1; }
+  __device__ void load(int pb, uint8_t* sa, uint8_t* sb, uint64_t* bar, const CUtensorMap* ta, const CUtensorMap* tb) const {
+    int t = pb;
+    int tw = t % g.tiles_w; t /= g.tiles_w;
+    int th = t % g.tiles_h;
+    int tn = t / g.tiles_h;
+    int w0 = tw * g.BW, h0 = th * g.BH, i0 = tn * g.BI;
+    for (int i = 0; i < tc::TBM / 32; ++i) tc::tma_load_4d(sa + i * tc::BOX_BYTES, ta, bar, co0 + 32 * i, w0, h0, i0);
+    for (int j = 0; j < TBN / 32; ++j)
+      tc::tma_load_4d(sb + j * tc::BOX_BYTES, tb, bar, ci0 + 32 * j, w0 * g.stride - g.pad + s_tap, h0 * g.stride - g.pad + r_tap, i0);
+  }
+  __device__ bool out_row(int r, int64_t& off) const {
+    int co = co0 + r;
+    off = ((int64_t)co * g.R * g.S + tap) * g.C;
+    return co < g.Co;
+  }
+  __device__ int n_cols() const { return g.C; }
+  __device__ int col0() const { return ci0; }
+  __device__ bool first_split() const { return true; }
+};
+
+int check_tc_geom(const ConvGeomTc& g, const char* what) {
+  MMFN_CHECK_ARG(g.N > 0 && g.H > 0 && g.W > 0 && g.C > 0 && g.Co > 0 && g.R > 0 && g.S > 0 && g.stride > 0 && g.pad >= 0,
+                 "%s: bad sizes", what);
+  MMFN_CHECK_ARG(g.Ho == (g.H + 2 * g.pad - g.R) / g.stride + 1 && g.Wo == (g.W + 2 * g.pad - g.S) / g.stride + 1,
+                 "%s: inconsistent output size", what);
+  MMFN_CHECK_ARG(g.C % 32 == 0, "%s: input channels must be a multiple of 32 for the TF32 path", what);
+  MMFN_CHECK_ARG(g.Co % 4 == 0, "%s: output channels must be a multiple of 4", what);
+  return 0;
+}
+
+// activation tensor (N,H,W,C) as a 4-D map (C, W, H, N) with a (32, bw*stride, bh*stride, bi) box
+int make_act_tmap(CUtensorMap* m, const float* x, int N, int H, int W, int C, int bw, int bh, int bi, int stride, bool swz32) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  uint64_t strides[4] = {1, (uint64_t)C, (uint64_t)W * C, (uint64_t)H * W * C};
+  uint32_t box[4] = {32, (uint32_t)(bw * stride), (uint32_t)(bh * stride), (uint32_t)bi};
+  uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+  return mmfn_make_tmap_f32(m, x, 4, dims, strides, box, es, swz32);
+}
+
+__global__ void krsc_to_crsk_kernel(const float* __restrict__ w, float* __restrict__ wt, int Co, int R, int S, int C, int flip) {
+  int64_t n = (int64_t)Co * R * S * C;
+  int RS = R * S;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int co = (int)(i % Co);
+    int64_t t = i / Co;
+    int rs = (int)(t % RS);
+    int c = (int)(t / RS);
+    int src_rs = flip ? (RS - 1 - rs) : rs;
+    wt[i] = w[((int64_t)co * RS + src_rs) * C + c];
+  }
+}
+
+}  // namespace
+
+// wt[c][r][s][co] = w[co][r][s][c]; with flip != 0 the taps are mirrored (r,s -> R-1-r, S-1-s), which
+// turns a stride-1 data-gradient into a plain forward convolution of dy with wt.
+MMFN_API int mmfn_filter_krsc_to_crsk(const float* w, float* wt, int Co, int R, int S, int C, int flip,
+                                      cudaStream_t stream) {
+  MMFN_CHECK_ARG(w && wt && Co > 0 && R > 0 && S > 0 && C > 0, "filter permute: bad args");
+  int64_t n = (int64_t)Co * R * S * C;
+  krsc_to_crsk_kernel<<<grid_1d(n, 256), 256, 0, stream>>>(w, wt, Co, R, S, C, flip);
+  return mmfn_launch_status("krsc_to_crsk");
+}
+
+// y(N,Ho,Wo,Co) = conv(x(N,H,W,C), w(Co,R,S,C)) [+ res]; TF32 multiply, FP32 accumulate.  C % 32 == 0.
+MMFN_API int mmfn_conv2d_fwd_tf32(const float* x, const float* w, float* y, const float* res,
+                                  int N, int H, int W, int C, int Co, int R, int S, int stride, int pad,
+                                  int Ho, int Wo, cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && w && y, "conv_fwd_tf32: null pointer");
+  ConvGeomTc g{N, H, W, C, Co, R, S, stride, pad, Ho, Wo};
+  if (int rc = check_tc_geom(g, "conv_fwd_tf32")) return rc;
+  MMFN_CHECK_ARG((((uintptr_t)x | (uintptr_t)w) & 15) == 0, "conv_fwd_tf32: operands must be 16-byte aligned");
+  MMFN_CHECK_ARG(Wo >= 8 && Ho >= 8, "conv_fwd_tf32: output must be at least 8x8");
+  // 128-pixel tile: 8 rows x 16 cols of one image, or two whole 8x8 maps
+  g.BW = Wo >= 16 ? 16 : 8;
+  g.BH = 8;
+  g.BI = tc::TBM / (g.BW * g.BH);
+  MMFN_CHECK_ARG(g.BW * g.BH * g.BI == tc::TBM && g.BW * stride <= 256 && g.BH * stride <= 256, "conv_fwd_tf32: unsupported tile");
+  g.tiles_w = (Wo + g.BW - 1) / g.BW; g.tiles_h = (Ho + g.BH - 1) / g.BH; g.tiles_n = (N + g.BI - 1) / g.BI;
+  CUtensorMap ta, tb;
+  if (int rc = make_act_tmap(&ta, x, N, H, W, C, g.BW, g.BH, g.BI, stride, false)) return rc;
+  const int tbn = Co <= 64 ? 64 : 128;
+  {
+    uint64_t dims[2] = {(uint64_t)R * S * C, (uint64_t)Co}, strides[2] = {1, (uint64_t)R * S * C};
+    uint32_t box[2] = {32, (uint32_t)tbn};
+    if (int rc = mmfn_make_tmap_f32(&tb, w, 2, dims, strides, box, nullptr, false)) return rc;
+  }
+  tc::Epilogue e{y, nullptr, res, nullptr, 1.f, 0, 0, 0.f, 0};
+  int ptiles = g.tiles_w * g.tiles_h * g.tiles_n;
+  MMFN_CHECK_ARG(ptiles <= 65535, "conv_fwd_tf32: too many pixel tiles");
+  if (tbn == 64) {
+    ConvFwdOp<64> op{g};
+    return tc::launch<ConvFwdOp<64>, 64, 4>(ta, tb, op, e, dim3((Co + 63) / 64, ptiles, 1), stream, "conv_fwd_tf32");
+  }
+  ConvFwdOp<128> op{g};
+  return tc::launch<ConvFwdOp<128>, 128, 3>(ta, tb, op, e, dim3((Co + 127) / 128, ptiles, 1), stream, "conv_fwd_tf32");
+}
+
+// dw(Co,R,S,C) += dy^T * im2col(x), atomically; TF32 multiply, FP32 accumulate.  C % 32 == 0, Co % 4 == 0.
+MMFN_API int mmfn_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw,
+                                    int N, int H, int W, int C, int Co, int R, int S, int stride, int pad,
+                                    int Ho, int Wo, int splitk, cudaStream_t stream) {
+  MMFN_CHECK_ARG(dy && x && dw, "conv_wgrad_tf32: null pointer");
+  ConvGeomTc g{N, H, W, C, Co, R, S, stride, pad, Ho, Wo};
+  if (int rc = check_tc_geom(g, "conv_wgrad_tf32")) return rc;
+  MMFN_CHECK_ARG((((uintptr_t)x | (uintptr_t)dy) & 15) == 0, "conv_wgrad_tf32: operands must be 16-byte aligned");
+  MMFN_CHECK_ARG(Wo >= 8 && Ho >= 4, "conv_wgrad_tf32: output must be at least 4x8");
+  g.BW = Wo >= 16 ? 16 : 8;
+  g.BH = tc::TBK / g.BW;
+  g.BI = 1;
+  g.tiles_w = (Wo + g.BW - 1) / g.BW; g.tiles_h = (Ho + g.BH - 1) / g.BH; g.tiles_n = N;
+  CUtensorMap ta, tb;
+  if (int rc = make_act_tmap(&ta, dy, N, Ho, Wo, Co, g.BW, g.BH, g.BI, 1, true)) return rc;
+  if (int rc = make_act_tmap(&tb, x, N, H, W, C, g.BW, g.BH, g.BI, stride, true)) return rc;
+  const int tbn = C <= 64 ? 64 : 128;
+  int npb = g.tiles_w * g.tiles_h * g.tiles_n;
+  int co_tiles = (Co + tc::TBM - 1) / tc::TBM, ci_tiles = (C + tbn - 1) / tbn;
+  if (splitk <= 0) {
+    int ctas = co_tiles * ci_tiles * R * S;
+    splitk = max(1, min(npb / 8, (2 * 148 + ctas - 1) / ctas));
+  }
+  int pb_per = (npb + splitk - 1) / splitk;
+  splitk = (npb + pb_per - 1) / pb_per;
+  MMFN_CHECK_ARG(R * S * splitk <= 65535, "conv_wgrad_tf32: too many splits");
+  tc::Epilogue e{dw, nullptr, nullptr, nullptr, 1.f, 0, 2, 0.f, 0};
+  dim3 grid(ci_tiles, co_tiles, R * S * splitk);
+  if (tbn == 64) {
+    ConvWgradOp<64> op{g, splitk, pb_per};
+    return tc::launch<ConvWgradOp<64>, 64, 4>(ta, tb, op, e, grid, stream, "conv_wgrad_tf32");
+  }
+  ConvWgradOp<128> op{g, splitk, pb_per};
+  return tc::launch<ConvWgradOp<128>, 128, 3>(ta, tb, op, e, grid, stream, "conv_wgrad_tf32");
+}

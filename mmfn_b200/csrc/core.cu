@@ -102,27 +102,3 @@ MMFN_API int mmfn_conv2d_wgrad_f32(const float* dy, const float* x, float* dw,
   Epilogue e{dw, Kt, 0, 0, nullptr, nullptr, nullptr, 1.f, 0, 2, 0.f, 0};
   return launch_gemm_simt(a, b, Co, Kt, P, e, 1, 1, splitk, stream);
 }
-
-namespace {
-__global__ void krsc_to_crsk_kernel(const float* __restrict__ w, float* __restrict__ wt,
-                                    int Co, int RS, int C) {
-  int64_t n = (int64_t)Co * RS * C;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int co = (int)(i % Co);
-    int64_t t = i / Co;
-    int rs = (int)(t % RS);
-    int c = (int)(t / RS);
-    wt[i] = w[((int64_t)co * RS + rs) * C + c];
-  }
-}
-}  // namespace
-
-// wt[c][r][s][co] = w[co][r][s][c]
-MMFN_API int mmfn_filter_krsc_to_crsk(const float* w, float* wt, int Co, int R, int S, int C,
-                                      cudaStream_t stream) {
-  MMFN_CHECK_ARG(w && wt && Co > 0 && R > 0 && S > 0 && C > 0, "filter permute: bad args");
-  int64_t n = (int64_t)Co * R * S * C;
-  int blocks = grid_1d(n, 256);
-  krsc_to_crsk_kernel<<<blocks, 256, 0, stream>>>(w, wt, Co, R * S, C);
-  return mmfn_launch_status("krsc_to_crsk");
-}

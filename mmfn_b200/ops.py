@@ -99,21 +99,29 @@ def _conv_work(N, H, W, C, Co, R, S, Ho, Wo):
     return (2.0 * N * Ho * Wo * Co * R * S * C, 4.0 * (N * H * W * C + Co * R * S * C + N * Ho * Wo * Co))
 
 
-def conv2d_fwd(x, w_krsc, stride, pad):
+def _tc_conv_ok(C, Co, Ho, Wo):
+    return TF32 and C % 32 == 0 and Co % 32 == 0 and Ho >= 8 and Wo >= 8
+
+
+def conv2d_fwd(x, w_krsc, stride, pad, res=None):
     N, H, W, C = x.shape
     Co, R, S, C2 = w_krsc.shape
     assert C2 == C and x.is_contiguous() and w_krsc.is_contiguous()
     Ho, Wo = conv_out_hw(H, W, R, S, stride, pad)
     y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
     lib().next_work = _conv_work(N, H, W, C, Co, R, S, Ho, Wo)
-    lib().conv2d_fwd_f32(_p(x), _p(w_krsc), _p(y), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, _st())
+    if _tc_conv_ok(C, Co, Ho, Wo):
+        lib().conv2d_fwd_tf32(_p(x), _p(w_krsc), _p(y), _p(res), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, _st())
+    else:
+        assert res is None
+        lib().conv2d_fwd_f32(_p(x), _p(w_krsc), _p(y), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, _st())
     return y
 
 
-def filter_crsk(w_krsc):
+def filter_crsk(w_krsc, flip=False):
     Co, R, S, C = w_krsc.shape
     wt = torch.empty((C, R, S, Co), device=w_krsc.device, dtype=torch.float32)
-    lib().filter_krsc_to_crsk(_p(w_krsc), _p(wt), Co, R, S, C, _st())
+    lib().filter_krsc_to_crsk(_p(w_krsc), _p(wt), Co, R, S, C, int(flip), _st())
     return wt
 
 
@@ -121,6 +129,9 @@ def conv2d_dgrad(dy, w_krsc, x_shape, stride, pad, res=None):
     N, H, W, C = x_shape
     Co, R, S, _ = w_krsc.shape
     _, Ho, Wo, _ = dy.shape
+    if stride == 1 and _tc_conv_ok(Co, C, H, W):
+        # stride-1 data gradient == forward convolution of dy with the mirrored, channel-swapped filters
+        return conv2d_fwd(dy, filter_crsk(w_krsc, flip=True), 1, R - 1 - pad, res=res)
     wt = filter_crsk(w_krsc)
     dx = torch.empty(x_shape, device=dy.device, dtype=torch.float32)
     lib().next_work = _conv_work(N, H, W, C, Co, R, S, Ho, Wo)
@@ -133,9 +144,12 @@ def conv2d_wgrad_(dy, x, dw_krsc, stride, pad):
     N, H, W, C = x.shape
     Co, R, S, _ = dw_krsc.shape
     _, Ho, Wo, _ = dy.shape
-    assert dw_krsc.is_contiguous()
+    assert dw_krsc.is_contiguous() and dy.is_contiguous() and x.is_contiguous()
     lib().next_work = _conv_work(N, H, W, C, Co, R, S, Ho, Wo)
-    lib().conv2d_wgrad_f32(_p(dy), _p(x), _p(dw_krsc), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, 0, _st())
+    if _tc_conv_ok(C, Co, Ho, Wo):
+        lib().conv2d_wgrad_tf32(_p(dy), _p(x), _p(dw_krsc), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, 0, _st())
+    else:
+        lib().conv2d_wgrad_f32(_p(dy), _p(x), _p(dw_krsc), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, 0, _st())
 
 
 # ------------------------------------------------------------------ normalisation

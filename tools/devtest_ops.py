@@ -378,10 +378,36 @@ def t_gemm_tc():
     ops.TF32 = True
 
 
+def t_conv_tc():
+    """tcgen05 implicit-GEMM convolutions (fwd / stride-1 dgrad / wgrad) against torch fp32."""
+    ops.TF32 = True
+    for (N, H, C, Co, R, stride, pad) in [(2, 64, 64, 64, 3, 1, 1), (2, 64, 64, 128, 3, 2, 1), (2, 64, 64, 128, 1, 2, 0),
+                                          (4, 8, 512, 512, 3, 1, 1), (3, 16, 256, 256, 3, 1, 1), (2, 32, 128, 128, 3, 1, 1),
+                                          (5, 16, 256, 512, 3, 2, 1), (16, 32, 64, 128, 3, 2, 1)]:
+        x = torch.randn(N, C, H, H, device=dev)
+        w = torch.randn(Co, C, R, R, device=dev) * (2.0 / (C * R * R)) ** 0.5
+        xn = x.permute(0, 2, 3, 1).contiguous()
+        wk = w.permute(0, 2, 3, 1).contiguous()
+        y = ops.conv2d_fwd(xn, wk, stride, pad)
+        xr = x.clone().requires_grad_(True); wr = w.clone().requires_grad_(True)
+        yr = F.conv2d(xr, wr, stride=stride, padding=pad)
+        tag = f"N{N} H{H} C{C}->{Co} R{R} s{stride}"
+        report(f"conv_tc fwd {tag}", y.permute(0, 3, 1, 2), yr, tol=3e-3)
+        dy = torch.randn_like(yr)
+        yr.backward(dy)
+        dyn = dy.permute(0, 2, 3, 1).contiguous()
+        res = torch.randn_like(xn)
+        dx = ops.conv2d_dgrad(dyn, wk, xn.shape, stride, pad, res=res)
+        report(f"conv_tc dgrad {tag}", dx.permute(0, 3, 1, 2), xr.grad + res.permute(0, 3, 1, 2), tol=3e-3)
+        dw = torch.zeros_like(wk)
+        ops.conv2d_wgrad_(dyn, xn, dw, stride, pad)
+        report(f"conv_tc wgrad {tag}", dw.permute(0, 3, 1, 2), wr.grad, tol=3e-3)
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     ops.TF32 = False
-    for fn in (t_gemm, t_conv, t_bn, t_ln, t_pool, t_tokens, t_softmax, t_misc, t_head, t_bev, t_gemm_tc):
+    for fn in (t_gemm, t_conv, t_bn, t_ln, t_pool, t_tokens, t_softmax, t_misc, t_head, t_bev, t_gemm_tc, t_conv_tc):
         if only and fn.__name__ not in only:
             continue
         run(fn)
