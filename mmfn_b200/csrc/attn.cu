@@ -285,3 +285,5 @@ MMFN_API int mmfn_l2l_row0_bwd(const float* qkv, const int* lane_num, const floa
   l2l_row0_bwd_kernel<64><<<B * heads, 256, smem, stream>>>(qkv, lane_num, prob, dout, L, heads, 1.0f / sqrtf((float)dim_head), dqkv);
   return mmfn_launch_status("l2l_row0_bwd");
 }
+
+MMFN_DEFINE_RNG_BINDER(attn)

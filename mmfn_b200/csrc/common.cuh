@@ -46,9 +46,21 @@ __host__ __device__ __forceinline__ uint32_t mmfn_hash32(uint64_t seed, uint64_t
   z = z ^ (z >> 31);
   return (uint32_t)(z >> 32);
 }
+// Device-resident RNG offset (mmfn_rng_bind): added to every dropout seed on the device so that a
+// captured CUDA graph draws fresh masks on every replay.  One __constant__ pointer per translation unit.
+static __constant__ const unsigned long long* c_mmfn_rng = nullptr;
+#define MMFN_DEFINE_RNG_BINDER(tu)                                                     \
+  int mmfn_bind_rng_##tu(const unsigned long long* p) {                                \
+    return (int)cudaMemcpyToSymbol(c_mmfn_rng, &p, sizeof(p));                         \
+  }
+
 // keep-scale: 0 if dropped, 1/(1-p) if kept.  p == 0 -> always 1.
 __host__ __device__ __forceinline__ float mmfn_dropout_scale(float p, uint64_t seed, uint64_t idx) {
   if (p <= 0.f) return 1.f;
+#ifdef __CUDA_ARCH__
+  const unsigned long long* rng = c_mmfn_rng;
+  if (rng) seed += *rng;
+#endif
   float u = (float)(mmfn_hash32(seed, idx) >> 8) * (1.0f / 16777216.0f);
   return (u >= p) ? 1.0f / (1.0f - p) : 0.f;
 }

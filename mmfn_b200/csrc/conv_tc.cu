@@ -162,7 +162,7 @@ MMFN_API int mmfn_conv2d_fwd_tf32(const float* x, const float* w, float* y, cons
     uint32_t box[2] = {32, (uint32_t)tbn};
     if (int rc = mmfn_make_tmap_f32(&tb, w, 2, dims, strides, box, nullptr, false)) return rc;
   }
-  tc::Epilogue e{y, nullptr, res, nullptr, 1.f, 0, 0, 0.f, 0};
+  tc::Epilogue e{y, nullptr, res, nullptr, 1.f, 0, 0, 0.f, 0, mmfn_tc_trace_ptr()};
   int ptiles = g.tiles_w * g.tiles_h * g.tiles_n;
   MMFN_CHECK_ARG(ptiles <= 65535, "conv_fwd_tf32: too many pixel tiles");
   if (tbn == 64) {
@@ -199,7 +199,7 @@ MMFN_API int mmfn_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw,
   int pb_per = (npb + splitk - 1) / splitk;
   splitk = (npb + pb_per - 1) / pb_per;
   MMFN_CHECK_ARG(R * S * splitk <= 65535, "conv_wgrad_tf32: too many splits");
-  tc::Epilogue e{dw, nullptr, nullptr, nullptr, 1.f, 0, 2, 0.f, 0};
+  tc::Epilogue e{dw, nullptr, nullptr, nullptr, 1.f, 0, 2, 0.f, 0, mmfn_tc_trace_ptr()};
   dim3 grid(ci_tiles, co_tiles, R * S * splitk);
   if (tbn == 64) {
     ConvWgradOp<64> op{g, splitk, pb_per};
@@ -208,3 +208,5 @@ MMFN_API int mmfn_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw,
   ConvWgradOp<128> op{g, splitk, pb_per};
   return tc::launch<ConvWgradOp<128>, 128, 3>(ta, tb, op, e, grid, stream, "conv_wgrad_tf32");
 }
+
+MMFN_DEFINE_RNG_BINDER(conv_tc)

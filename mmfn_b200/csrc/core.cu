@@ -102,3 +102,24 @@ MMFN_API int mmfn_conv2d_wgrad_f32(const float* dy, const float* x, float* dw,
   Epilogue e{dw, Kt, 0, 0, nullptr, nullptr, nullptr, 1.f, 0, 2, 0.f, 0};
   return launch_gemm_simt(a, b, Co, Kt, P, e, 1, 1, splitk, stream);
 }
+
+MMFN_DEFINE_RNG_BINDER(core)
+int mmfn_bind_rng_attn(const unsigned long long*);
+int mmfn_bind_rng_gemm_tc(const unsigned long long*);
+int mmfn_bind_rng_conv_tc(const unsigned long long*);
+int mmfn_bind_rng_misc(const unsigned long long*);
+int mmfn_bind_rng_pool(const unsigned long long*);
+
+// Bind (or with null: unbind) a device-resident 64-bit offset that every dropout site adds to its
+// seed at run time.  The training engine bumps it on the device once per step, so the dropout masks
+// change between replays of a captured CUDA graph while forward/backward of one step stay consistent.
+MMFN_API int mmfn_rng_bind(const unsigned long long* dev_offset) {
+  int rc = mmfn_bind_rng_core(dev_offset);
+  if (!rc) rc = mmfn_bind_rng_attn(dev_offset);
+  if (!rc) rc = mmfn_bind_rng_gemm_tc(dev_offset);
+  if (!rc) rc = mmfn_bind_rng_conv_tc(dev_offset);
+  if (!rc) rc = mmfn_bind_rng_misc(dev_offset);
+  if (!rc) rc = mmfn_bind_rng_pool(dev_offset);
+  if (rc) mmfn_set_error("rng_bind: cudaMemcpyToSymbol failed (%d)", rc);
+  return rc;
+}

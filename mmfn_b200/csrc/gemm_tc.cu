@@ -60,6 +60,16 @@ int run_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, 
 }  // namespace
 
 // ---------------------------------------------------------------- host side
+static unsigned long long* g_trace = nullptr;
+unsigned long long* mmfn_tc_trace_ptr() { return g_trace; }
+
+// Developer aid: when buf (8 x uint64, device) is non-null every tensor-core kernel's CTA 0 writes
+// %globaltimer stamps of its pipeline phases there.  Pass null to switch it off (default).
+MMFN_API int mmfn_tc_set_trace(unsigned long long* buf) {
+  g_trace = buf;
+  return 0;
+}
+
 PFN_encodeTiled mmfn_get_encode_tiled() {
   static PFN_encodeTiled fn = nullptr;
   if (!fn) {
@@ -133,9 +143,11 @@ MMFN_API int mmfn_gemm_tf32(const float* A, int64_t lda, int a_mn, const float* 
     else       { dims[0] = N; dims[1] = K; box[0] = 32;      box[1] = tc::TBK; }
     if (int rc = mmfn_make_tmap_f32(&tb, B, 2, dims, strides, box, nullptr, b_mn != 0)) return rc;
   }
-  tc::Epilogue e{C, bias, res, mask, alpha, act, accum, drop_p, drop_seed};
+  tc::Epilogue e{C, bias, res, mask, alpha, act, accum, drop_p, drop_seed, mmfn_tc_trace_ptr()};
   if (!a_mn && !b_mn) return run_gemm<false, false>(ta, tb, M, N, K, ldc, tbn, splitk, e, stream);
   if (!a_mn && b_mn) return run_gemm<false, true>(ta, tb, M, N, K, ldc, tbn, splitk, e, stream);
   if (a_mn && !b_mn) return run_gemm<true, false>(ta, tb, M, N, K, ldc, tbn, splitk, e, stream);
   return run_gemm<true, true>(ta, tb, M, N, K, ldc, tbn, splitk, e, stream);
 }
+
+MMFN_DEFINE_RNG_BINDER(gemm_tc)

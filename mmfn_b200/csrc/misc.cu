@@ -239,3 +239,5 @@ MMFN_API int mmfn_radar_logsoftmax_bwd(const float* dy, const float* y, float* d
   radar_logsoftmax_bwd_kernel<<<B * 64, 128, 0, stream>>>(dy, y, dv, C);
   return mmfn_launch_status("radar_logsoftmax_bwd");
 }
+
+MMFN_DEFINE_RNG_BINDER(misc)

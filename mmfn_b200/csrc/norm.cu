@@ -7,7 +7,7 @@ namespace {
 
 // ------------------------------------------------------------------ BatchNorm
 // blockDim = (32 channels, 8 row lanes); block covers ROWS_PER_BLOCK rows of one 32-channel group.
-constexpr int BN_ROWS_PER_BLOCK = 512;
+constexpr int BN_ROWS_PER_BLOCK = 128;
 
 __global__ void bn_partial_kernel(const float* __restrict__ x, int64_t M, int C, double* __restrict__ ws) {
   __shared__ double s1[8][33], s2[8][33];

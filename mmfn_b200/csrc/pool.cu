@@ -356,3 +356,5 @@ MMFN_API int mmfn_pool_sum_bwd(const float* dfused, float* df0, float* df1, floa
   pool_sum_bwd_kernel<<<grid_1d((int64_t)B * nmod * 64 * C, 256), 256, 0, stream>>>(dfused, df, nmod, dtokens, B, C);
   return mmfn_launch_status("pool_sum_bwd");
 }
+
+MMFN_DEFINE_RNG_BINDER(pool)

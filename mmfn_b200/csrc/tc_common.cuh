@@ -128,6 +128,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled mmfn_get_encode_tiled();
+unsigned long long* mmfn_tc_trace_ptr();
 
 // fp32 tensor (rank <= 4) read as TF32 (TMA rounds to nearest), 128B swizzle, OOB -> 0.
 // dims/strides innermost first; strides in ELEMENTS for dims 1..rank-1.

@@ -3,7 +3,8 @@
 //
 //   warp 0   TMA producer    : Op::load() issues cp.async.bulk.tensor boxes for k-block kb
 //   warp 1   MMA issuer      : 4 x tcgen05.mma (K = 8 tf32 each) per 128-byte k-block, accumulator in TMEM
-//   warps 2-5 epilogue       : tcgen05.ld -> fused epilogue -> HBM, row addressing by Op::out_row()
+//   warps 2-9 epilogue       : tcgen05.ld -> smem re-tile -> fused epilogue -> HBM (coalesced float4),
+//                              row addressing by Op::out_row()
 //
 // The shared-memory ring holds STAGES x (A tile 128 rows + B tile TBN rows) x 128 bytes.
 // K-major tiles use SWIZZLE_128B; MN-major tiles are stacks of [32 k-rows][32 fp32] boxes in the
@@ -16,7 +17,7 @@ namespace tc {
 constexpr int TBM = 128;          // tile rows (UMMA M)
 constexpr int TBK = 32;           // fp32 elements per k-block = one 128-byte swizzle span
 constexpr int UMMA_K = 8;         // tf32
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;        // TMA warp + MMA warp + 8 epilogue warps
 constexpr int BOX_BYTES = 32 * 128;   // one MN-major box: 32 k-rows x 128 B
 
 struct Epilogue {
@@ -29,7 +30,15 @@ struct Epilogue {
   int accum;           // 0 store, 1 +=, 2 atomicAdd
   float drop_p;
   uint64_t drop_seed;
+  unsigned long long* trace;   // optional: 8 x %globaltimer stamps of CTA 0 (mmfn_tc_set_trace), else null
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(i) do { if (e.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) e.trace[i] = gtimer(); } while (0)
 
 template <int TBN, int STAGES>
 struct Smem {
@@ -37,7 +46,9 @@ struct Smem {
   static constexpr int B_BYTES = TBN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16 + 1024;   // + alignment slack
+  static constexpr int TOTAL = BAR_OFF + 128 + 1024;                          // barriers + alignment slack
+  // the epilogue re-uses the (by then idle) operand stages: 8 warps x [32][36] floats + 128 row offsets
+  static_assert(8 * 32 * 36 * 4 + 128 * 8 <= STAGES * STAGE_BYTES, "epilogue staging does not fit");
 };
 
 // Op contract (all __device__):
@@ -48,7 +59,9 @@ struct Smem {
 //   bool out_row(r, int64_t& off);                element offset of tile row r, column 0 of the OUTPUT row
 //   int n_cols();  int col0();                    valid output columns, first column of this tile
 //   bool first_split();                           bias / residual are added by the first split only
-template <class Op, int TBN, int STAGES>
+// FULL = false compiles the epilogue down to alpha*acc + bias + residual (most launches); the
+// ReLU / mask / dropout variant is a separate instantiation so its hash arithmetic is never if-converted in.
+template <class Op, int TBN, int STAGES, bool FULL>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Op op, Epilogue e) {
   using L = Smem<TBN, STAGES>;
@@ -62,6 +75,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   op.setup();
   const int kb0 = op.kb_begin(), kb1 = op.kb_end();
+  if (threadIdx.x == 0) TC_STAMP(0);                      // kernel entry
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -77,6 +91,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TC_STAMP(1);                      // barriers + TMEM ready
 
   if (warp == 0) {
     if (elect_one()) {                                   // ===== TMA producer =====
@@ -96,6 +111,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
+        if (kb == kb0) TC_STAMP(2);                      // first operands landed
         const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
         const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
@@ -109,67 +125,123 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       mma_commit(tmem_full);                             // accumulator complete
+      TC_STAMP(3);                                       // all MMAs issued
     }
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+    // ===== epilogue: 8 warps; warp w owns TMEM lane quarter (w % 4) and every other 32-column chunk =====
+    // tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns).  The rows are
+    // re-tiled through shared memory (the idle pipeline stages, 36-float pitch: conflict-free for
+    // 128-bit accesses) so that each warp instruction touches four fully coalesced 128-byte row
+    // segments: result stores / atomics, residual and mask loads all run as 16-byte vectors.
+    const int ew = warp - 2;                              // 0..7
     const int q = warp & 3;
-    const int r = q * 32 + lane;
-    int64_t off = 0;
-    const bool row_ok = op.out_row(r, off);
+    float* stg = reinterpret_cast<float*>(smem) + ew * (32 * 36);
+    int64_t* row_off = reinterpret_cast<int64_t*>(smem + 8 * 32 * 36 * 4);          // [128]
+    int64_t my_off = 0;
+    const bool my_ok = op.out_row(q * 32 + lane, my_off);
     const int N = op.n_cols(), n0 = op.col0();
     const bool first = op.first_split(), have_k = kb1 > kb0;
-    mbar_wait(tmem_full, 0);
+    const bool vec_ok = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0);
+    mbar_wait(tmem_full, 0);                              // all MMAs retired: TMEM valid, smem stages idle
     tc_fence_after();
+    if (ew < 4) row_off[q * 32 + lane] = my_ok ? my_off : -1;
+    asm volatile("bar.sync 1, 256;" ::: "memory");        // row_off visible to the 8 epilogue warps
+    if (threadIdx.x == 64) TC_STAMP(4);                   // accumulator visible to the epilogue
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll 1
-    for (int c = 0; c < TBN / 32; ++c) {
-      float v[32];
-      __syncwarp();                                      // tcgen05.ld is warp-collective (.sync.aligned)
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+    for (int c = ew >> 2; c < TBN / 32; c += 2) {
       const int col0 = n0 + c * 32;
-      if (!row_ok || col0 >= N) continue;                // re-converges at the __syncwarp above
-      const int64_t base = off + col0;
+      if (col0 >= N) break;                               // warp-uniform
+      {
+        float v[32];
+        __syncwarp();                                     // tcgen05.ld is warp-collective (.sync.aligned)
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = have_k ? e.alpha * v[j] : 0.f;
-        if (col0 + j < N) {
-          if (e.bias && first) x += __ldg(e.bias + col0 + j);
-          if (e.act == 1) x = fmaxf(x, 0.f);
-          if (e.mask) x = (__ldg(e.mask + base + j) > 0.f) ? x : 0.f;
-          if (e.drop_p > 0.f) x *= mmfn_dropout_scale(e.drop_p, e.drop_seed, (uint64_t)(base + j));
-          if (e.res && first) x += __ldg(e.res + base + j);
-        }
-        v[j] = x;
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
-      float* dst = e.C + base;
-      if (e.accum == 0 && col0 + 32 <= N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+      __syncwarp();
+      const int col = col0 + c4;
+      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e.bias && first && col + 3 < N) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+      else if (e.bias && first) {
+        if (col < N) bias4.x = __ldg(e.bias + col);
+        if (col + 1 < N) bias4.y = __ldg(e.bias + col + 1);
+        if (col + 2 < N) bias4.z = __ldg(e.bias + col + 2);
+      }
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
-        for (int j = 0; j < 32 && col0 + j < N; ++j) {
-          if (e.accum == 0) dst[j] = v[j];
-          else if (e.accum == 1) dst[j] += v[j];
-          else atomicAdd(dst + j, v[j]);
+      for (int rr = 0; rr < 8; ++rr) {
+        const int r = rr * 4 + rsub;
+        const int64_t off_r = row_off[q * 32 + r];
+        if (off_r < 0 || col >= N) continue;
+        const int64_t idx = off_r + col;
+        float4 a4 = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
+        float x[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float bb[4] = {bias4.x, bias4.y, bias4.z, bias4.w};
+        const bool full4 = vec_ok && (col + 3 < N) && ((idx & 3) == 0);
+        float m4[4] = {1.f, 1.f, 1.f, 1.f}, r4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (full4) {
+          if (FULL && e.mask) { float4 t = __ldg(reinterpret_cast<const float4*>(e.mask + idx)); m4[0] = t.x; m4[1] = t.y; m4[2] = t.z; m4[3] = t.w; }
+          if (e.res && first) { float4 t = __ldg(reinterpret_cast<const float4*>(e.res + idx)); r4[0] = t.x; r4[1] = t.y; r4[2] = t.z; r4[3] = t.w; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (col + j < N) {
+              if (FULL && e.mask) m4[j] = __ldg(e.mask + idx + j);
+              if (e.res && first) r4[j] = __ldg(e.res + idx + j);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float t = (have_k ? e.alpha * x[j] : 0.f) + bb[j];
+          if constexpr (FULL) {
+            if (e.act == 1) t = fmaxf(t, 0.f);
+            if (e.mask) t = m4[j] > 0.f ? t : 0.f;
+            if (e.drop_p > 0.f) t *= mmfn_dropout_scale(e.drop_p, e.drop_seed, (uint64_t)(idx + j));
+          }
+          x[j] = t + r4[j];
+        }
+        if (e.accum == 0 && full4) {
+          *reinterpret_cast<float4*>(e.C + idx) = make_float4(x[0], x[1], x[2], x[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (col + j < N) {
+              if (e.accum == 0) e.C[idx + j] = x[j];
+              else if (e.accum == 1) e.C[idx + j] += x[j];
+              else atomicAdd(e.C + idx + j, x[j]);
+            }
         }
       }
     }
   }
+  if (threadIdx.x == 64) TC_STAMP(5);                    // epilogue stores issued
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, TBN);
+  if (threadIdx.x == 64) TC_STAMP(6);                    // TMEM released
+}
+
+template <class Op, int TBN, int STAGES, bool FULL>
+static int launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const Op& op, const Epilogue& e, dim3 grid,
+                       cudaStream_t stream, const char* what) {
+  using L = Smem<TBN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(tc_kernel<Op, TBN, STAGES, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (ce != cudaSuccess) { mmfn_set_error("%s: smem attribute: %s", what, cudaGetErrorString(ce)); return (int)ce; }
+    attr_set = true;
+  }
+  tc_kernel<Op, TBN, STAGES, FULL><<<grid, TC_THREADS, L::TOTAL, stream>>>(ta, tb, op, e);
+  return mmfn_launch_status(what);
 }
 
 template <class Op, int TBN, int STAGES>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Op& op, const Epilogue& e, dim3 grid,
                   cudaStream_t stream, const char* what) {
-  using L = Smem<TBN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(tc_kernel<Op, TBN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
-    if (ce != cudaSuccess) { mmfn_set_error("%s: smem attribute: %s", what, cudaGetErrorString(ce)); return (int)ce; }
-    attr_set = true;
-  }
-  tc_kernel<Op, TBN, STAGES><<<grid, TC_THREADS, L::TOTAL, stream>>>(ta, tb, op, e);
-  return mmfn_launch_status(what);
+  if (e.act != 0 || e.mask != nullptr || e.drop_p > 0.f)
+    return launch_impl<Op, TBN, STAGES, true>(ta, tb, op, e, grid, stream, what);
+  return launch_impl<Op, TBN, STAGES, false>(ta, tb, op, e, grid, stream, what);
 }
 
 }  // namespace tc

@@ -3,15 +3,19 @@
 
 One step = [one packed H2D copy] -> BEV scatter -> forward -> L1 loss -> backward ->
 [ONE all-reduce over the flat gradient buffer] -> ONE fused AdamW launch over the flat
-parameter buffer.  Data parallelism is one process per GPU (torch.distributed, NCCL); every
-rank keeps a full replica, BatchNorm statistics stay rank-local as in the reference (no SyncBN).
+parameter buffer.  The forward/backward schedule (~1900 kernel launches) is captured once into
+a CUDA graph and replayed, so the step is not bound by host launch latency; dropout masks still
+change every step because every dropout site adds a device-resident offset to its seed.
+Data parallelism is one process per GPU (torch.distributed, NCCL); every rank keeps a full
+replica, BatchNorm statistics stay rank-local as in the reference (no SyncBN).
 """
 import torch
 import torch.distributed as dist
 
 from . import ops
+from ._lib import lib
 
-_FIELDS = (  # name, dtype, per-sample shape builder
+_FIELDS = (
     ("rgb_u8", torch.uint8), ("points", torch.float32), ("lane", torch.float32), ("lane_num", torch.int32),
     ("radar", torch.float32), ("radar_adj", torch.float32), ("velocity", torch.float32),
     ("target_point", torch.float32), ("gt_waypoints", torch.float32),
@@ -20,37 +24,35 @@ _FIELDS = (  # name, dtype, per-sample shape builder
 
 class BatchStager:
     """Packs a host batch (dict of CPU tensors, see synthetic.synth_batch) into ONE pinned buffer and
-    moves it with ONE async H2D copy; the reference issues ~25 separate .to(device) copies per step
-    (phase2_train_net.py:78-97)."""
+    moves it with ONE async H2D copy into a FIXED device buffer (graph-replay friendly); the reference
+    issues ~25 separate .to(device) copies per step (phase2_train_net.py:78-97)."""
 
     def __init__(self, example, device):
         self.device = torch.device(device)
         self.layout, off = [], 0
         for name, dtype in _FIELDS:
             t = example[name]
-            nbytes = t.numel() * t.element_size()
+            nbytes = t.numel() * dtype.itemsize
             self.layout.append((name, dtype, tuple(t.shape), off, nbytes))
             off += (nbytes + 255) // 256 * 256
         self.nbytes = off
         self.host = [torch.empty(off, dtype=torch.uint8).pin_memory() for _ in range(2)]
-        self.dev = [torch.empty(off, dtype=torch.uint8, device=self.device) for _ in range(2)]
+        self.dev = torch.empty(off, dtype=torch.uint8, device=self.device)
+        self.dev_views = self._views(self.dev)
         self.flip = 0
 
     def _views(self, buf):
-        out = {}
-        for name, dtype, shape, off, nbytes in self.layout:
-            out[name] = buf[off: off + nbytes].view(dtype).view(shape)
-        return out
+        return {name: buf[off: off + nbytes].view(dtype).view(shape) for name, dtype, shape, off, nbytes in self.layout}
 
     def stage(self, batch):
-        """host dict -> device dict (views into one device buffer); asynchronous on the current stream."""
+        """host dict -> device dict (views of the fixed device buffer); asynchronous on the current stream."""
         self.flip ^= 1
-        h, d = self.host[self.flip], self.dev[self.flip]
+        h = self.host[self.flip]
         hv = self._views(h)
-        for name, dtype, shape, _, _ in self.layout:
+        for name, dtype, _, _, _ in self.layout:
             hv[name].copy_(batch[name].to(dtype))
-        d.copy_(h, non_blocking=True)
-        return self._views(d)
+        self.dev.copy_(h, non_blocking=True)
+        return self.dev_views
 
 
 class TrainEngine:
@@ -67,6 +69,10 @@ class TrainEngine:
         self.p_active = self.st.flat[:n]
         self.g_active = self.st.flat_grad[:n]
         self.last_pred = None
+        # device-resident dropout offset, bumped once per step inside the (captured) schedule
+        self.rng = torch.zeros(1, device=dev, dtype=torch.int64)
+        lib().rng_bind(self.rng.data_ptr())
+        self._graph = None
 
     def broadcast_parameters(self, src=0):
         """What DistributedDataParallel's constructor does (phase2_train_net.py:269)."""
@@ -74,15 +80,16 @@ class TrainEngine:
             dist.broadcast(self.st.flat, src, group=self.pg)
             dist.broadcast(self.st.flat_buf, src, group=self.pg)
 
+    # ---- eager schedule ----------------------------------------------------------------------
     def forward_backward(self, b):
         """b: device batch. Returns the loss (0-d device tensor); gradients land in store.flat_grad."""
         model = self.model
         model.train()
         self.st.flat_grad.zero_()
+        self.rng.add_(1000003)
+        self.st.flat_nbt.add_(model._nbt_step())
         lidar = b["lidar"] if "lidar" in b else ops.bev_scatter(b["points"])
         image = b["rgb_u8"] if "rgb_u8" in b else b["image"]
-        model.seed += 1000
-        self.st.flat_nbt.add_(model._nbt_step())
         pred = self.net.forward(image, lidar, b["lane"], b["lane_num"], b["radar"], b["radar_adj"],
                                 b["target_point"], b["velocity"], model.seed, True)
         loss, dpred = ops.l1_loss(pred, b["gt_waypoints"])
@@ -100,3 +107,31 @@ class TrainEngine:
         loss = self.forward_backward(device_batch)
         self.optimizer_step()
         return loss
+
+    # ---- CUDA-graph schedule -----------------------------------------------------------------
+    def capture(self, static_batch, warmup=2):
+        """Capture forward+backward on `static_batch` (fixed device tensors, e.g. BatchStager.dev_views).
+        Later steps refill those tensors in place and call step_graph()."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):                      # sets kernel attributes, warms the allocator
+                self.step(static_batch)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        l0 = lib().launches
+        with torch.cuda.graph(g):
+            self._graph_loss = self.forward_backward(static_batch)
+            self._graph_pred = self.last_pred
+        self.graph_launches = lib().launches - l0
+        self._graph = g
+        return g
+
+    def step_graph(self):
+        """Replay the captured forward+backward, then all-reduce + AdamW.  Returns the loss tensor."""
+        self._graph.replay()
+        lib().launches += self.graph_launches
+        self.last_pred = self._graph_pred
+        self.optimizer_step()
+        return self._graph_loss

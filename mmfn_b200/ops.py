@@ -75,6 +75,15 @@ def gemm(A, B, C, *, bias=None, res=None, mask=None, alpha=1.0, act=0, accum=0,
                             _p(bias), _p(res), _p(mask), float(alpha), int(act), int(accum), float(drop_p),
                             int(seed), int(splitk) if splitk > 1 else 0, _st())
             return C
+    if splitk == 1 and act == 0 and mask is None and drop_p == 0 and K >= 8192:
+        # skinny outputs with a huge reduction (generator dgrad: 16x64 <- K=262144): split K over CTAs
+        tiles = ((M + 63) // 64) * ((N + 63) // 64) * nbt
+        if tiles < 64:
+            splitk = max(1, min(K // 2048, 256 // tiles))
+            if splitk > 1:
+                if accum == 0:
+                    C.zero_()
+                accum = 2
     lib().gemm_f32(_p(A), A.stride(-2), A.stride(-1), a_b[0], a_b[1],
                    _p(B), B.stride(-2), B.stride(-1), b_b[0], b_b[1],
                    _p(C), C.stride(-2), c_b[0], c_b[1],

@@ -59,8 +59,12 @@ def test_bev_scatter_full_size_properties(dev):
         assert np.array_equal(out[i].cpu().numpy(), bev_oracle.lidar_to_histogram_features(pts[i, :, :3].cpu().numpy()))
 
 
-def _setup(dev, B):
+def _setup(dev, B, tf32=False):
+    """tf32=False: exact-fp32 SIMT kernels everywhere (tight tolerances).  tf32=True: the production
+    path, large GEMMs/convs on the tcgen05 TF32 tensor-core kernels (north_star tolerance 1e-3)."""
+    from mmfn_b200 import ops
     from mmfn_b200.model_rad import MMFN
+    ops.TF32 = tf32
     cfg = GlobalConfig(embd_pdrop=0.0, attn_pdrop=0.0, resid_pdrop=0.0)
     model = MMFN(cfg, dev)
     sd = synthetic.fill_golden_weights(model.state_dict(), 42)
@@ -76,11 +80,15 @@ def _probe(t, n=16):
     return np.concatenate([[f.norm().item(), f.sum().item()], f[idx].numpy()])
 
 
-def test_train_step_matches_oracle_and_reference_goldens(dev, golden_dir):
+@pytest.mark.parametrize("tf32", [False, True], ids=["fp32-simt", "tf32-tcgen05"])
+def test_train_step_matches_oracle_and_reference_goldens(dev, golden_dir, tf32):
     """Reference-style call sequence (Engine.train): model(...) -> l1 -> loss.backward()."""
     from mmfn_b200 import ops
     B = 2
-    cfg, model, sd, b = _setup(dev, B)
+    cfg, model, sd, b = _setup(dev, B, tf32)
+    # measured on B200: waypoint L1 1.5e-7 (fp32) / 1.7e-4 (tf32); loss error 0 / 1e-6;
+    # worst per-tensor gradient error 1.5e-2 (fp32, B=2 train-mode BN amplifies fp32 noise) / 0.37 (tf32)
+    wp_tol, loss_tol, grad_tol, norm_tol = (2e-4, 2e-4, 2e-2, 2e-2) if not tf32 else (1e-3, 1e-3, 0.6, 0.25)
     lidar = ops.bev_scatter(b["points"].to(dev))
     lidar_ref = torch.from_numpy(np.stack([bev_oracle.lidar_to_histogram_features(p[:, :3].numpy()) for p in b["points"]]))
     assert torch.equal(lidar.cpu(), lidar_ref)
@@ -96,15 +104,16 @@ def test_train_step_matches_oracle_and_reference_goldens(dev, golden_dir):
               b["target_point"], b["velocity"])
     oloss, opred, ograds = mmfn_oracle.train_step(osd, cfg, dict(inputs=inputs, gt_waypoints=b["gt_waypoints"]))
     wp_l1 = (pred.detach().cpu() - opred).abs().mean().item()
-    assert wp_l1 < 2e-4, wp_l1                       # north_star bar: 1e-3
-    assert abs(loss.item() - oloss.item()) < 2e-4
+    assert wp_l1 < wp_tol, wp_l1                     # north_star bar: 1e-3
+    assert abs(loss.item() - oloss.item()) < loss_tol
 
     # goldens of the real reference
     gold = np.load(os.path.join(golden_dir, "mmfn_golden_b2.npz"))
-    assert np.abs(pred.detach().cpu().numpy() - gold["pred_wp"]).mean() < 2e-4
-    assert abs(loss.item() - float(gold["loss"])) < 2e-4
+    assert np.abs(pred.detach().cpu().numpy() - gold["pred_wp"]).mean() < wp_tol
+    assert abs(loss.item() - float(gold["loss"])) < loss_tol
 
     worst, worst_key = 0.0, None
+    dot = n1 = n2 = 0.0
     params = dict(model.named_parameters())
     for k, g in ograds.items():
         p = params[k]
@@ -116,9 +125,14 @@ def test_train_step_matches_oracle_and_reference_goldens(dev, golden_dir):
         err = (got - g).norm().item() / denom
         if err > worst:
             worst, worst_key = err, k
+        dot += (got.double() * g.double()).sum().item()
+        n1 += got.double().pow(2).sum().item()
+        n2 += g.double().pow(2).sum().item()
         ref = gold["grad/" + k]
-        assert abs(_probe(got, 6)[0] - ref[0]) <= 2e-2 * max(ref[0], 1e-6), k
-    assert worst < 2e-2, (worst, worst_key)
+        assert abs(_probe(got, 6)[0] - ref[0]) <= norm_tol * max(ref[0], 1e-6), k
+    assert worst < grad_tol, (worst, worst_key)
+    cosine = dot / (n1 ** 0.5 * n2 ** 0.5)           # whole-model gradient direction
+    assert cosine > (0.9999 if not tf32 else 0.97), cosine
 
     # BatchNorm running statistics after one training step
     msd = model.state_dict()
@@ -133,7 +147,7 @@ def test_engine_steps_match_oracle_adamw(dev):
     """Two full optimisation steps through TrainEngine (BEV scatter + fwd + bwd + fused AdamW)."""
     from mmfn_b200.engine import TrainEngine
     B = 2
-    cfg, model, sd, b = _setup(dev, B)
+    cfg, model, sd, b = _setup(dev, B, tf32=False)
     eng = TrainEngine(model, lr=1e-4)
     osd = {k: v.clone() for k, v in sd.items()}
     opt = {"t": 0, "m": {}, "v": {}}
@@ -171,10 +185,40 @@ def test_state_dict_interchange(dev):
         assert list(sd[k].shape) == shape and str(sd[k].dtype) == dtype, k
 
 
+def test_cuda_graph_replay_matches_eager_schedule(dev):
+    """The captured forward+backward graph replays to the same losses as launching kernel by kernel,
+    and dropout masks change between replays (device-resident seed offset)."""
+    from mmfn_b200.engine import BatchStager, TrainEngine
+    from mmfn_b200.model_rad import MMFN
+    B = 2
+    losses = {}
+    for mode in ("eager", "graph"):
+        cfg, model, sd, b = _setup(dev, B, tf32=True)
+        eng = TrainEngine(model, lr=1e-4)
+        stager = BatchStager(b, dev)
+        db = stager.stage(b)
+        torch.cuda.synchronize()
+        if mode == "graph":
+            model.load_state_dict(sd)                      # capture() ran warm-up steps: restart from the same weights
+            eng.capture(db, warmup=1)
+            model.load_state_dict(sd)
+            eng.m.zero_(); eng.v.zero_(); eng.state.zero_()
+        losses[mode] = [(eng.step_graph() if mode == "graph" else eng.step(db)).item() for _ in range(3)]
+    for a, g in zip(losses["eager"], losses["graph"]):
+        assert abs(a - g) < 2e-3, losses
+    # with the reference dropout (p = 0.1) two replays on identical weights/inputs must differ
+    model = MMFN(GlobalConfig(), dev)
+    model.load_state_dict(sd)
+    eng = TrainEngine(model, lr=0.0, weight_decay=0.0)
+    eng.capture(db, warmup=1)
+    l1, l2 = eng.step_graph().item(), eng.step_graph().item()
+    assert l1 != l2
+
+
 def test_eval_forward_matches_oracle(dev):
     """Inference path (BN running stats, no dropout) -- what the e2e agents call."""
     B = 1
-    cfg, model, sd, b = _setup(dev, B)
+    cfg, model, sd, b = _setup(dev, B, tf32=False)
     model.eval()
     lidar_ref = torch.from_numpy(np.stack([bev_oracle.lidar_to_histogram_features(p[:, :3].numpy()) for p in b["points"]]))
     vectormaps = [[b["lane"].to(dev)], [b["lane_num"].to(dev).float()], b["lane"].shape[1]]
