@@ -26,6 +26,7 @@ template <int TBN>
 struct ConvFwdOp {
   static constexpr bool A_MN = false, B_MN = false;
   ConvGeomTc g;
+  int kb_per_split;          // split-K over (tap, channel-chunk) blocks for layers with few pixel tiles
   int w0, h0, i0, co0;
   __device__ void setup() {
     int t = blockIdx.y;
@@ -35,8 +36,8 @@ struct ConvFwdOp {
     w0 = tw * g.BW; h0 = th * g.BH; i0 = tn * g.BI;
     co0 = blockIdx.x * TBN;
   }
-  __device__ int kb_begin() const { return 0; }
-  __device__ int kb_end() const { return g.R * g.S * (g.C / 32); }
+  __device__ int kb_begin() const { return blockIdx.z * kb_per_split; }
+  __device__ int kb_end() const { return min(g.R * g.S * (g.C / 32), (int)(blockIdx.z + 1) * kb_per_split); }
   __device__ void load(int kb, uint8_t* sa, uint8_t* sb, uint64_t* bar, const CUtensorMap* ta, const CUtensorMap* tb) const {
     int cch = g.C / 32;
     int tap = kb / cch, cc = kb - tap * cch;
@@ -54,7 +55,7 @@ struct ConvFwdOp {
   }
   __device__ int n_cols() const { return g.Co; }
   __device__ int col0() const { return co0; }
-  __device__ bool first_split() const { return true; }
+  __device__ bool first_split() const { return blockIdx.z == 0; }
 };
 
 template <int TBN>
@@ -127,7 +128,31 @@ __global__ void krsc_to_crsk_kernel(const float* __restrict__ w, float* __restri
   }
 }
 
+// y[n, 2h, 2w, :] = x[n, h, w, :], zeros elsewhere (y is (N, 2H, 2W, C)); float4 over channels
+__global__ void zero_upsample2_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int H, int W, int C4) {
+  int64_t n = (int64_t)N * 2 * H * 2 * W * C4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4);
+    int64_t t = i / C4;
+    int w = (int)(t % (2 * W)); t /= 2 * W;
+    int h = (int)(t % (2 * H));
+    int b = (int)(t / (2 * H));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!(h & 1) && !(w & 1)) v = __ldg(x + (((int64_t)b * H + (h >> 1)) * W + (w >> 1)) * C4 + c);
+    y[i] = v;
+  }
+}
+
 }  // namespace
+
+// y(N,2H,2W,C) = x(N,H,W,C) with zeros inserted between pixels: turns the data-gradient of a stride-2
+// convolution into a stride-1 forward convolution (of the up-sampled dy with the mirrored filters).
+MMFN_API int mmfn_zero_upsample2_f32(const float* x, float* y, int N, int H, int W, int C, cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "zero_upsample2: bad args (C % 4 == 0)");
+  int64_t n = (int64_t)N * 4 * H * W * (C / 4);
+  zero_upsample2_kernel<<<grid_1d(n, 256), 256, 0, stream>>>((const float4*)x, (float4*)y, N, H, W, C / 4);
+  return mmfn_launch_status("zero_upsample2");
+}
 
 // wt[c][r][s][co] = w[co][r][s][c]; with flip != 0 the taps are mirrored (r,s -> R-1-r, S-1-s), which
 // turns a stride-1 data-gradient into a plain forward convolution of dy with wt.
@@ -162,15 +187,27 @@ MMFN_API int mmfn_conv2d_fwd_tf32(const float* x, const float* w, float* y, cons
     uint32_t box[2] = {32, (uint32_t)tbn};
     if (int rc = mmfn_make_tmap_f32(&tb, w, 2, dims, strides, box, nullptr, false)) return rc;
   }
-  tc::Epilogue e{y, nullptr, res, nullptr, 1.f, 0, 0, 0.f, 0, mmfn_tc_trace_ptr()};
   int ptiles = g.tiles_w * g.tiles_h * g.tiles_n;
   MMFN_CHECK_ARG(ptiles <= 65535, "conv_fwd_tf32: too many pixel tiles");
-  if (tbn == 64) {
-    ConvFwdOp<64> op{g};
-    return tc::launch<ConvFwdOp<64>, 64, 4>(ta, tb, op, e, dim3((Co + 63) / 64, ptiles, 1), stream, "conv_fwd_tf32");
+  // deep layers at small batch have few output tiles (B=16: 64 / 32 CTAs at 16x16 / 8x8): split the
+  // (tap, channel) reduction across CTAs and accumulate atomically into a zeroed output
+  const int nkb = R * S * (C / 32);
+  const int ctas = ptiles * ((Co + tbn - 1) / tbn);
+  int splitk = 1;
+  if (ctas < 148) splitk = max(1, min(nkb / 8, (2 * 148 + ctas - 1) / ctas));
+  int kb_per = (nkb + splitk - 1) / splitk;
+  splitk = (nkb + kb_per - 1) / kb_per;
+  if (splitk > 1) {
+    cudaError_t ce = cudaMemsetAsync(y, 0, sizeof(float) * (size_t)N * Ho * Wo * Co, stream);
+    if (ce != cudaSuccess) { mmfn_set_error("conv_fwd_tf32: memset: %s", cudaGetErrorString(ce)); return (int)ce; }
   }
-  ConvFwdOp<128> op{g};
-  return tc::launch<ConvFwdOp<128>, 128, 3>(ta, tb, op, e, dim3((Co + 127) / 128, ptiles, 1), stream, "conv_fwd_tf32");
+  tc::Epilogue e{y, nullptr, res, nullptr, 1.f, 0, splitk > 1 ? 2 : 0, 0.f, 0, mmfn_tc_trace_ptr()};
+  if (tbn == 64) {
+    ConvFwdOp<64> op{g, kb_per};
+    return tc::launch<ConvFwdOp<64>, 64, 4>(ta, tb, op, e, dim3((Co + 63) / 64, ptiles, splitk), stream, "conv_fwd_tf32");
+  }
+  ConvFwdOp<128> op{g, kb_per};
+  return tc::launch<ConvFwdOp<128>, 128, 3>(ta, tb, op, e, dim3((Co + 127) / 128, ptiles, splitk), stream, "conv_fwd_tf32");
 }
 
 // dw(Co,R,S,C) += dy^T * im2col(x), atomically; TF32 multiply, FP32 accumulate.  C % 32 == 0, Co % 4 == 0.

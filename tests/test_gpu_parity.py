@@ -138,7 +138,8 @@ def test_train_step_matches_oracle_and_reference_goldens(dev, golden_dir, tf32):
     msd = model.state_dict()
     for k in osd:
         if k.endswith("running_mean") or k.endswith("running_var"):
-            assert torch.allclose(msd[k].cpu(), osd[k], rtol=1e-4, atol=1e-5), k
+            rt, at = (1e-4, 1e-5) if not tf32 else (1e-2, 2e-3)      # TF32 conv outputs feed the statistics
+            assert torch.allclose(msd[k].cpu(), osd[k], rtol=rt, atol=at), k
         if k.endswith("num_batches_tracked"):
             assert int(msd[k]) == int(osd[k]), k
 
