@@ -208,6 +208,9 @@ def run_native(args):
             eng.step(stager.dev_views)                     # eager schedule: one event pair per C-ABI call
         torch.cuda.synchronize()
         prof = lib().stop_profile()
+        top_shapes = [dict(call=list(k), n=n // prof_steps, ms_per_step=round(ms / prof_steps, 3),
+                           tflops=round(fl * n / (ms * 1e-3) / 1e12, 1) if ms > 0 else None)
+                      for k, n, ms, fl in lib().last_shapes[:14]]
         for d in prof.values():
             d["ms_per_step"] = d["ms"] / prof_steps
     barrier()
@@ -231,6 +234,7 @@ def run_native(args):
                 "frac": achieved / peak, "traffic": None, "peak_source": peaks["src"] +
                 (" (sustained bf16 / 2 for TF32-class fp32 math)" if tensor_bound else ""),
                 "share_of_step": d["ms"] / total_ms, "avg_launch_ms": d["ms"] / d["calls"],
+                "top_shapes": top_shapes,
                 "per_kernel_ms_per_step": {k: round(v["ms_per_step"], 3) for k, v in
                                            sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]}}
     sps = world * B * args.steps / (ms * 1e-3)

@@ -94,15 +94,20 @@ class _Lib:
 
     def stop_profile(self):
         """-> {fn: dict(calls, ms, flops, bytes)}; caller must have synchronised the device."""
-        out = {}
+        out, shapes = {}, {}
         for fn, work, e0, e1 in self.profile or []:
+            ms = e0.elapsed_time(e1)
             d = out.setdefault(fn, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
             d["calls"] += 1
-            d["ms"] += e0.elapsed_time(e1)
+            d["ms"] += ms
             if work:
                 d["flops"] += work[0]
                 d["bytes"] += work[1]
+                s = shapes.setdefault((fn,) + tuple(work[2:] if len(work) > 2 else work[:1]), [0, 0.0, work[0]])
+                s[0] += 1
+                s[1] += ms
         self.profile = None
+        self.last_shapes = sorted(([k, v[0], v[1], v[2]] for k, v in shapes.items()), key=lambda r: -r[2])
         return out
 
 

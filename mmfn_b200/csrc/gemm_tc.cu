@@ -11,50 +11,104 @@
 
 namespace {
 
+// Operand addressing: every operand is a rank-4 tensor map (inner, and three outer dimensions sorted
+// by stride on the host).  pos[0..2] = position (1..3) of the strided matrix dimension, batch-1 and
+// batch-0 coordinates inside that map.
+struct OperandPos { int row, b1, b0; };
+
 template <bool AMN, bool BMN, int TBN>
 struct GemmOp {
   static constexpr bool A_MN = AMN, B_MN = BMN;
-  int M, N, K, kb_per_split;
-  int64_t ldc;
-  int m0, n0, kb0, kb1;
+  int M, N, K, kb_per_split, splitk, nb1;
+  int64_t ldc, c_sb0, c_sb1;
+  OperandPos pa, pb;
+  int m0, n0, kb0, kb1, b0, b1;
   __device__ void setup() {
     m0 = blockIdx.y * tc::TBM;
     n0 = blockIdx.x * TBN;
+    int bz = blockIdx.z / splitk, split = blockIdx.z - bz * splitk;
+    b0 = bz / nb1; b1 = bz - b0 * nb1;
     int nkb = (K + tc::TBK - 1) / tc::TBK;
-    kb0 = blockIdx.z * kb_per_split;
+    kb0 = split * kb_per_split;
     kb1 = min(nkb, kb0 + kb_per_split);
   }
   __device__ int kb_begin() const { return kb0; }
   __device__ int kb_end() const { return kb1; }
+  __device__ static void issue(uint8_t* dst, const CUtensorMap* t, uint64_t* bar, const OperandPos& p, int inner, int row,
+                               int b1_, int b0_) {
+    int c[4];
+    c[0] = inner; c[p.row] = row; c[p.b1] = b1_; c[p.b0] = b0_;
+    tc::tma_load_4d(dst, t, bar, c[0], c[1], c[2], c[3]);
+  }
   __device__ void load(int kb, uint8_t* sa, uint8_t* sb, uint64_t* bar, const CUtensorMap* ta, const CUtensorMap* tb) const {
-    if constexpr (!AMN) tc::tma_load_2d(sa, ta, bar, kb * tc::TBK, m0);
+    if constexpr (!AMN) issue(sa, ta, bar, pa, kb * tc::TBK, m0, b1, b0);
     else
-      for (int i = 0; i < tc::TBM / 32; ++i) tc::tma_load_2d(sa + i * tc::BOX_BYTES, ta, bar, m0 + 32 * i, kb * tc::TBK);
-    if constexpr (!BMN) tc::tma_load_2d(sb, tb, bar, kb * tc::TBK, n0);
+      for (int i = 0; i < tc::TBM / 32; ++i) issue(sa + i * tc::BOX_BYTES, ta, bar, pa, m0 + 32 * i, kb * tc::TBK, b1, b0);
+    if constexpr (!BMN) issue(sb, tb, bar, pb, kb * tc::TBK, n0, b1, b0);
     else
-      for (int i = 0; i < TBN / 32; ++i) tc::tma_load_2d(sb + i * tc::BOX_BYTES, tb, bar, n0 + 32 * i, kb * tc::TBK);
+      for (int i = 0; i < TBN / 32; ++i) issue(sb + i * tc::BOX_BYTES, tb, bar, pb, n0 + 32 * i, kb * tc::TBK, b1, b0);
   }
   __device__ bool out_row(int r, int64_t& off) const {
-    off = (int64_t)(m0 + r) * ldc;
+    off = (int64_t)b0 * c_sb0 + (int64_t)b1 * c_sb1 + (int64_t)(m0 + r) * ldc;
     return m0 + r < M;
   }
   __device__ int n_cols() const { return N; }
   __device__ int col0() const { return n0; }
-  __device__ bool first_split() const { return blockIdx.z == 0; }
+  __device__ bool first_split() const { return (blockIdx.z % splitk) == 0; }
+};
+
+struct GemmArgs {
+  int M, N, K, nb0, nb1, splitk, tbn;
+  int64_t ldc, c_sb0, c_sb1;
+  OperandPos pa, pb;
 };
 
 template <bool AMN, bool BMN>
-int run_gemm(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, int64_t ldc, int tbn, int splitk,
-             const tc::Epilogue& e, cudaStream_t stream) {
-  int nkb = (K + tc::TBK - 1) / tc::TBK;
-  int kb_per = (nkb + splitk - 1) / splitk;
-  splitk = (nkb + kb_per - 1) / kb_per;
-  if (tbn == 64) {
-    GemmOp<AMN, BMN, 64> op{M, N, K, kb_per, ldc};
-    return tc::launch<GemmOp<AMN, BMN, 64>, 64, 4>(ta, tb, op, e, dim3((N + 63) / 64, (M + tc::TBM - 1) / tc::TBM, splitk), stream, "gemm_tf32");
+int run_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, const tc::Epilogue& e, cudaStream_t stream) {
+  int nkb = (g.K + tc::TBK - 1) / tc::TBK;
+  int kb_per = (nkb + g.splitk - 1) / g.splitk;
+  int splitk = (nkb + kb_per - 1) / kb_per;
+  unsigned gz = (unsigned)(g.nb0 * g.nb1 * splitk);
+  if (g.tbn == 64) {
+    GemmOp<AMN, BMN, 64> op{g.M, g.N, g.K, kb_per, splitk, g.nb1, g.ldc, g.c_sb0, g.c_sb1, g.pa, g.pb};
+    return tc::launch<GemmOp<AMN, BMN, 64>, 64, 4>(ta, tb, op, e, dim3((g.N + 63) / 64, (g.M + tc::TBM - 1) / tc::TBM, gz), stream, "gemm_tf32");
   }
-  GemmOp<AMN, BMN, 128> op{M, N, K, kb_per, ldc};
-  return tc::launch<GemmOp<AMN, BMN, 128>, 128, 3>(ta, tb, op, e, dim3((N + 127) / 128, (M + tc::TBM - 1) / tc::TBM, splitk), stream, "gemm_tf32");
+  GemmOp<AMN, BMN, 128> op{g.M, g.N, g.K, kb_per, splitk, g.nb1, g.ldc, g.c_sb0, g.c_sb1, g.pa, g.pb};
+  return tc::launch<GemmOp<AMN, BMN, 128>, 128, 3>(ta, tb, op, e, dim3((g.N + 127) / 128, (g.M + tc::TBM - 1) / tc::TBM, gz), stream, "gemm_tf32");
+}
+
+// rank-4 map of one operand.  inner_len x strided_len matrix per batch; outer dims sorted by stride.
+int make_operand_tmap(CUtensorMap* out, OperandPos* pos, const float* base, bool mn_major, int rows, int K, int64_t ld,
+                      int nb0, int nb1, int64_t sb0, int64_t sb1, int tile_rows) {
+  // logical outer dims: 0 = strided matrix dim, 1 = batch-1, 2 = batch-0
+  uint64_t len[3] = {(uint64_t)(mn_major ? K : rows), (uint64_t)nb1, (uint64_t)nb0};
+  int64_t str[3] = {ld, sb1, sb0};
+  uint32_t bx[3] = {(uint32_t)(mn_major ? tc::TBK : tile_rows), 1, 1};
+  uint64_t inner_len = (uint64_t)(mn_major ? rows : K);
+  // size-1 batch dims get a harmless stride that keeps the map monotonic
+  int64_t span = ld * (int64_t)len[0];
+  if (nb1 == 1) str[1] = span;
+  if (nb0 == 1) str[2] = (nb1 == 1 ? span : (str[1] * nb1 > span ? str[1] * nb1 : span));
+  int order[3] = {0, 1, 2};
+  for (int i = 0; i < 3; ++i)
+    for (int j = i + 1; j < 3; ++j)
+      if (str[order[j]] < str[order[i]]) { int t = order[i]; order[i] = order[j]; order[j] = t; }
+  uint64_t dims[4] = {inner_len, 0, 0, 0}, strides[4] = {1, 0, 0, 0};
+  uint32_t box[4] = {32, 0, 0, 0};
+  int where[3];
+  for (int i = 0; i < 3; ++i) {
+    dims[i + 1] = len[order[i]];
+    strides[i + 1] = (uint64_t)str[order[i]];
+    box[i + 1] = bx[order[i]];
+    where[order[i]] = i + 1;
+  }
+  pos->row = where[0]; pos->b1 = where[1]; pos->b0 = where[2];
+  for (int i = 1; i < 4; ++i)
+    if (strides[i] % 4 != 0 || strides[i] == 0) {
+      mmfn_set_error("gemm_tf32: operand strides must be non-zero multiples of 4 floats (got %lld)", (long long)strides[i]);
+      return MMFN_BAD_ARG;
+    }
+  return mmfn_make_tmap_f32(out, base, 4, dims, strides, box, nullptr, mn_major);
 }
 
 }  // namespace
@@ -103,51 +157,46 @@ int mmfn_make_tmap_f32(CUtensorMap* out, const float* base, int rank, const uint
   return 0;
 }
 
-// C(M,N) (+)= alpha * op(A) * op(B)^T on the tensor cores (TF32 multiply, FP32 accumulate).
-//   a_mn == 0: A is a row-major (M, K) matrix with row pitch lda;  a_mn == 1: A is stored (K, M), pitch lda.
-//   b_mn == 0: B is a row-major (N, K) matrix with row pitch ldb;  b_mn == 1: B is stored (K, N), pitch ldb.
-// Pitches must be multiples of 4 floats and bases 16-byte aligned (TMA).  Epilogue as mmfn_gemm_f32.
-// splitk <= 0 picks a split that fills the 148 SMs (needs accum == 2 and a linear epilogue).
-MMFN_API int mmfn_gemm_tf32(const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn,
-                            float* C, int64_t ldc, int M, int N, int K,
+// C[b0,b1](M,N) (+)= alpha * op(A) * op(B)^T on the tensor cores (TF32 multiply, FP32 accumulate), batched
+// over nb0 x nb1 problems with per-operand batch strides (elements).
+//   a_mn == 0: A[b] is a row-major (M, K) matrix with row pitch lda;  a_mn == 1: A[b] is stored (K, M), pitch lda.
+//   b_mn == 0: B[b] is a row-major (N, K) matrix with row pitch ldb;  b_mn == 1: B[b] is stored (K, N), pitch ldb.
+// Pitches and batch strides must be non-zero multiples of 4 floats and bases 16-byte aligned (TMA).
+// K and the MN extents need no alignment: the TMA unit zero-fills past the logical matrix edge (e.g. the
+// 16-wide heads of transformer1).  Epilogue as mmfn_gemm_f32.  splitk <= 0 picks a split that fills the SMs
+// (needs accum == 2 and a linear epilogue).
+MMFN_API int mmfn_gemm_tf32(const float* A, int64_t lda, int a_mn, int64_t a_sb0, int64_t a_sb1,
+                            const float* B, int64_t ldb, int b_mn, int64_t b_sb0, int64_t b_sb1,
+                            float* C, int64_t ldc, int64_t c_sb0, int64_t c_sb1,
+                            int M, int N, int K, int nb0, int nb1,
                             const float* bias, const float* res, const float* mask,
                             float alpha, int act, int accum, float drop_p, uint64_t drop_seed,
                             int splitk, cudaStream_t stream) {
   MMFN_CHECK_ARG(A && B && C, "gemm_tf32: null operand");
-  MMFN_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_tf32: bad sizes");
-  MMFN_CHECK_ARG(lda % 4 == 0 && ldb % 4 == 0, "gemm_tf32: operand pitches must be multiples of 4 floats");
+  MMFN_CHECK_ARG(M > 0 && N > 0 && K > 0 && nb0 >= 1 && nb1 >= 1, "gemm_tf32: bad sizes");
+  MMFN_CHECK_ARG(lda % 4 == 0 && ldb % 4 == 0 && lda > 0 && ldb > 0, "gemm_tf32: operand pitches must be multiples of 4 floats");
   MMFN_CHECK_ARG((((uintptr_t)A | (uintptr_t)B) & 15) == 0, "gemm_tf32: operands must be 16-byte aligned");
   const bool linear = (act == 0 && !mask && drop_p == 0.f);
+  const int nb = nb0 * nb1;
   if (splitk <= 0) {
     splitk = 1;
     if (accum == 2 && linear) {
-      int tiles = ((M + tc::TBM - 1) / tc::TBM) * ((N + 127) / 128);
+      int tiles = ((M + tc::TBM - 1) / tc::TBM) * ((N + 127) / 128) * nb;
       int nkb = (K + tc::TBK - 1) / tc::TBK;
       splitk = max(1, min(nkb / 4, (2 * 148 + tiles - 1) / tiles));
     }
   }
   MMFN_CHECK_ARG(splitk == 1 || (accum == 2 && linear), "gemm_tf32: split-K needs a linear atomic epilogue");
-  const int tbn = (N <= 64) ? 64 : 128;
+  MMFN_CHECK_ARG((int64_t)nb * splitk <= 65535, "gemm_tf32: too many batches x splits");
+  GemmArgs g{M, N, K, nb0, nb1, splitk, (N <= 64) ? 64 : 128, ldc, c_sb0, c_sb1};
   CUtensorMap ta, tb;
-  {
-    uint64_t dims[2], strides[2] = {1, (uint64_t)lda};
-    uint32_t box[2];
-    if (!a_mn) { dims[0] = K; dims[1] = M; box[0] = tc::TBK; box[1] = tc::TBM; }
-    else       { dims[0] = M; dims[1] = K; box[0] = 32;      box[1] = tc::TBK; }
-    if (int rc = mmfn_make_tmap_f32(&ta, A, 2, dims, strides, box, nullptr, a_mn != 0)) return rc;
-  }
-  {
-    uint64_t dims[2], strides[2] = {1, (uint64_t)ldb};
-    uint32_t box[2];
-    if (!b_mn) { dims[0] = K; dims[1] = N; box[0] = tc::TBK; box[1] = (uint32_t)tbn; }
-    else       { dims[0] = N; dims[1] = K; box[0] = 32;      box[1] = tc::TBK; }
-    if (int rc = mmfn_make_tmap_f32(&tb, B, 2, dims, strides, box, nullptr, b_mn != 0)) return rc;
-  }
+  if (int rc = make_operand_tmap(&ta, &g.pa, A, a_mn != 0, M, K, lda, nb0, nb1, a_sb0, a_sb1, tc::TBM)) return rc;
+  if (int rc = make_operand_tmap(&tb, &g.pb, B, b_mn != 0, N, K, ldb, nb0, nb1, b_sb0, b_sb1, g.tbn)) return rc;
   tc::Epilogue e{C, bias, res, mask, alpha, act, accum, drop_p, drop_seed, mmfn_tc_trace_ptr()};
-  if (!a_mn && !b_mn) return run_gemm<false, false>(ta, tb, M, N, K, ldc, tbn, splitk, e, stream);
-  if (!a_mn && b_mn) return run_gemm<false, true>(ta, tb, M, N, K, ldc, tbn, splitk, e, stream);
-  if (a_mn && !b_mn) return run_gemm<true, false>(ta, tb, M, N, K, ldc, tbn, splitk, e, stream);
-  return run_gemm<true, true>(ta, tb, M, N, K, ldc, tbn, splitk, e, stream);
+  if (!a_mn && !b_mn) return run_gemm<false, false>(ta, tb, g, e, stream);
+  if (!a_mn && b_mn) return run_gemm<false, true>(ta, tb, g, e, stream);
+  if (a_mn && !b_mn) return run_gemm<true, false>(ta, tb, g, e, stream);
+  return run_gemm<true, true>(ta, tb, g, e, stream);
 }
 
 MMFN_DEFINE_RNG_BINDER(gemm_tc)

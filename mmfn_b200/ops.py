@@ -65,13 +65,17 @@ def gemm(A, B, C, *, bias=None, res=None, mask=None, alpha=1.0, act=0, accum=0,
         if t is not None:
             assert t.shape == C.shape and t.stride() == C.stride()
     nbt = nb[0] * nb[1]
-    lib().next_work = (2.0 * M * N * K * nbt, 4.0 * nbt * (M * K + N * K + M * N))
-    if TF32 and nbt == 1 and M >= 64 and K >= 32 and M * N * K >= (1 << 18):
+    lib().next_work = (2.0 * M * N * K * nbt, 4.0 * nbt * (M * K + N * K + M * N), M, N, K, nbt)
+    if TF32 and M >= 64 and K >= 16 and M * N * K * nbt >= (1 << 18):
         am, bm = _major(A), _major(B)
-        if am is not None and bm is not None and C.stride(-1) == 1:
+        bs_ok = all(x % 4 == 0 for x in a_b + b_b)
+        if nbt > 1:      # TMA cannot express broadcast (stride-0) batches
+            bs_ok = bs_ok and all(x > 0 for i, x in enumerate(a_b + b_b) if ([nb[0], nb[1]] * 2)[i] > 1)
+        if am is not None and bm is not None and C.stride(-1) == 1 and bs_ok and nbt * max(1, splitk) <= 4096:
             if accum == 1:          # plain += is a single-writer RMW; tensor-core path accumulates atomically
                 accum = 2
-            lib().gemm_tf32(_p(A), am[1], am[0], _p(B), bm[1], bm[0], _p(C), C.stride(-2), M, N, K,
+            lib().gemm_tf32(_p(A), am[1], am[0], a_b[0], a_b[1], _p(B), bm[1], bm[0], b_b[0], b_b[1],
+                            _p(C), C.stride(-2), c_b[0], c_b[1], M, N, K, nb[0], nb[1],
                             _p(bias), _p(res), _p(mask), float(alpha), int(act), int(accum), float(drop_p),
                             int(seed), int(splitk) if splitk > 1 else 0, _st())
             return C
@@ -105,7 +109,8 @@ def conv_out_hw(H, W, R, S, stride, pad):
 
 def _conv_work(N, H, W, C, Co, R, S, Ho, Wo):
     """algorithmic (flops, bytes) of one conv pass: 2*MACs; input + filter + output read/written once"""
-    return (2.0 * N * Ho * Wo * Co * R * S * C, 4.0 * (N * H * W * C + Co * R * S * C + N * Ho * Wo * Co))
+    return (2.0 * N * Ho * Wo * Co * R * S * C, 4.0 * (N * H * W * C + Co * R * S * C + N * Ho * Wo * Co),
+            N, H, C, Co, R)
 
 
 def _tc_conv_ok(C, Co, Ho, Wo):

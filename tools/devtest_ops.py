@@ -344,8 +344,8 @@ def t_gemm_tc():
                 Ast = A.t().contiguous() if a_mn else A
                 Bst = B.t().contiguous() if b_mn else B
                 C = torch.empty(M, N, device=dev)
-                lib().gemm_tf32(Ast.data_ptr(), Ast.stride(0), a_mn, Bst.data_ptr(), Bst.stride(0), b_mn, C.data_ptr(), N,
-                                M, N, K, 0, 0, 0, 1.0, 0, 0, 0.0, 0, 1, st)
+                lib().gemm_tf32(Ast.data_ptr(), Ast.stride(0), a_mn, 0, 0, Bst.data_ptr(), Bst.stride(0), b_mn, 0, 0,
+                                C.data_ptr(), N, 0, 0, M, N, K, 1, 1, 0, 0, 0, 1.0, 0, 0, 0.0, 0, 1, st)
                 torch.cuda.synchronize()
                 ref = A.double() @ B.double().t()
                 err = (C.double() - ref).abs().max().item() / ref.abs().max().item()
@@ -378,6 +378,38 @@ def t_gemm_tc():
     ops.TF32 = True
 
 
+def t_attn_tc():
+    """Batched tensor-core GEMMs on the strided head views of a fused qkv buffer (attention fwd + bwd)."""
+    ops.TF32 = True
+    for (B, T, C, nh) in [(4, 192, 64, 4), (3, 192, 128, 4), (2, 192, 256, 4), (2, 256, 512, 4)]:
+        hs = C // nh
+        qkv = torch.randn(B * T, 3 * C, device=dev)
+        heads = lambda t2d, i: t2d[:, i * C:(i + 1) * C].view(B, T, nh, hs).permute(0, 2, 1, 3)
+        k, q, v = (heads(qkv, i) for i in range(3))
+        S = torch.empty(B, nh, T, T, device=dev)
+        ops.gemm(q, k, S)
+        report(f"attn_tc S=QK^T T{T} hs{hs}", S, q @ k.transpose(-1, -2), tol=3e-3)
+        P = torch.softmax(S / hs ** 0.5, -1)
+        y = torch.empty(B * T, C, device=dev)
+        yh = y.view(B, T, nh, hs).permute(0, 2, 1, 3)
+        ops.gemm(P, v.transpose(-1, -2), yh)
+        report(f"attn_tc O=PV T{T} hs{hs}", yh, P @ v, tol=3e-3)
+        dy = torch.randn(B * T, C, device=dev)
+        dyh = dy.view(B, T, nh, hs).permute(0, 2, 1, 3)
+        dP = torch.empty_like(S)
+        ops.gemm(dyh, v, dP)
+        report(f"attn_tc dP=dO V^T T{T} hs{hs}", dP, dyh @ v.transpose(-1, -2), tol=3e-3)
+        dqkv = torch.zeros_like(qkv)
+        dk, dq, dv = (heads(dqkv, i) for i in range(3))
+        ops.gemm(P.transpose(-1, -2), dyh.transpose(-1, -2), dv)
+        report(f"attn_tc dV=P^T dO T{T} hs{hs}", dv, P.transpose(-1, -2) @ dyh, tol=3e-3)
+        dS = torch.randn_like(S)
+        ops.gemm(dS, k.transpose(-1, -2), dq)
+        report(f"attn_tc dQ=dS K T{T} hs{hs}", dq, dS @ k, tol=3e-3)
+        ops.gemm(dS.transpose(-1, -2), q.transpose(-1, -2), dk)
+        report(f"attn_tc dK=dS^T Q T{T} hs{hs}", dk, dS.transpose(-1, -2) @ q, tol=3e-3)
+
+
 def t_conv_tc():
     """tcgen05 implicit-GEMM convolutions (fwd / stride-1 dgrad / wgrad) against torch fp32."""
     ops.TF32 = True
@@ -407,7 +439,7 @@ def t_conv_tc():
 if __name__ == "__main__":
     only = sys.argv[1:]
     ops.TF32 = False
-    for fn in (t_gemm, t_conv, t_bn, t_ln, t_pool, t_tokens, t_softmax, t_misc, t_head, t_bev, t_gemm_tc, t_conv_tc):
+    for fn in (t_gemm, t_conv, t_bn, t_ln, t_pool, t_tokens, t_softmax, t_misc, t_head, t_bev, t_gemm_tc, t_attn_tc, t_conv_tc):
         if only and fn.__name__ not in only:
             continue
         run(fn)
