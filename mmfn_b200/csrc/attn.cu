@@ -5,17 +5,18 @@
 
 namespace {
 
-// one warp per row; cols <= 1024
+// one warp per row; cols <= 32*J (J = 6 / 8 for the 192- / 256-token fusion transformers)
+template <int J>
 __global__ void softmax_fwd_kernel(const float* __restrict__ s, float* __restrict__ p, float* __restrict__ pd,
                                    int64_t rows, int cols, float scale, float drop_p, uint64_t seed) {
   int lane = threadIdx.x & 31;
   int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float* sr = s + row * cols;
-  float v[32];
+  float v[J];
   float mx = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < J; ++j) {
     int c = lane + 32 * j;
     v[j] = c < cols ? sr[c] * scale : -INFINITY;
     mx = fmaxf(mx, v[j]);
@@ -23,14 +24,14 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ s, float* __restric
   mx = warp_max(mx);
   float sum = 0.f;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < J; ++j) {
     int c = lane + 32 * j;
     v[j] = c < cols ? expf(v[j] - mx) : 0.f;
     sum += v[j];
   }
   float inv = 1.0f / warp_sum(sum);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < J; ++j) {
     int c = lane + 32 * j;
     if (c < cols) {
       float q = v[j] * inv;
@@ -41,15 +42,16 @@ __global__ void softmax_fwd_kernel(const float* __restrict__ s, float* __restric
 }
 
 // ds = scale * p * (dp - sum(dp*p)),  dp = dpd * dropout_scale
+template <int J>
 __global__ void softmax_bwd_kernel(const float* __restrict__ p, const float* __restrict__ dpd, float* __restrict__ ds,
                                    int64_t rows, int cols, float scale, float drop_p, uint64_t seed) {
   int lane = threadIdx.x & 31;
   int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  float pv[32], g[32];
+  float pv[J], g[J];
   float dot = 0.f;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < J; ++j) {
     int c = lane + 32 * j;
     pv[j] = 0.f; g[j] = 0.f;
     if (c < cols) {
@@ -61,7 +63,7 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ p, const float* __r
   }
   dot = warp_sum(dot);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < J; ++j) {
     int c = lane + 32 * j;
     if (c < cols) ds[row * cols + c] = scale * pv[j] * (g[j] - dot);
   }
@@ -235,7 +237,10 @@ MMFN_API int mmfn_softmax_fwd(const float* s, float* p, float* pd, int64_t rows,
                               float drop_p, uint64_t seed, cudaStream_t stream) {
   MMFN_CHECK_ARG(s && p && rows >= 0 && cols > 0 && cols <= 1024, "softmax_fwd: bad args (cols <= 1024)");
   if (rows == 0) return 0;
-  softmax_fwd_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, stream>>>(s, p, pd, rows, cols, scale, drop_p, seed);
+  unsigned grid = (unsigned)ceil_div64(rows, 8);
+  if (cols <= 192) softmax_fwd_kernel<6><<<grid, 256, 0, stream>>>(s, p, pd, rows, cols, scale, drop_p, seed);
+  else if (cols <= 256) softmax_fwd_kernel<8><<<grid, 256, 0, stream>>>(s, p, pd, rows, cols, scale, drop_p, seed);
+  else softmax_fwd_kernel<32><<<grid, 256, 0, stream>>>(s, p, pd, rows, cols, scale, drop_p, seed);
   return mmfn_launch_status("softmax_fwd");
 }
 
@@ -243,7 +248,10 @@ MMFN_API int mmfn_softmax_bwd(const float* p, const float* dpd, float* ds, int64
                               float drop_p, uint64_t seed, cudaStream_t stream) {
   MMFN_CHECK_ARG(p && dpd && ds && rows >= 0 && cols > 0 && cols <= 1024, "softmax_bwd: bad args (cols <= 1024)");
   if (rows == 0) return 0;
-  softmax_bwd_kernel<<<(unsigned)ceil_div64(rows, 8), 256, 0, stream>>>(p, dpd, ds, rows, cols, scale, drop_p, seed);
+  unsigned grid = (unsigned)ceil_div64(rows, 8);
+  if (cols <= 192) softmax_bwd_kernel<6><<<grid, 256, 0, stream>>>(p, dpd, ds, rows, cols, scale, drop_p, seed);
+  else if (cols <= 256) softmax_bwd_kernel<8><<<grid, 256, 0, stream>>>(p, dpd, ds, rows, cols, scale, drop_p, seed);
+  else softmax_bwd_kernel<32><<<grid, 256, 0, stream>>>(p, dpd, ds, rows, cols, scale, drop_p, seed);
   return mmfn_launch_status("softmax_bwd");
 }
 

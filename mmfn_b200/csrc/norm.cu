@@ -293,7 +293,7 @@ MMFN_API int mmfn_layernorm_bwd(const float* dy, const float* x, const float* ga
   MMFN_CHECK_ARG(dy && x && gamma && beta && mean && rstd && dx && dgamma && dbeta, "ln_bwd: null pointer");
   MMFN_CHECK_ARG(M >= 0 && C > 0 && C <= 512, "ln_bwd: C must be in (0, 512]");
   if (M == 0) return 0;
-  int64_t nb = ceil_div64(M, 8); int blocks = (int)(nb < 148 * 4 ? nb : 148 * 4);
+  int64_t nb = ceil_div64(M, 8); int blocks = (int)(nb < 148 ? nb : 148);   // one CTA per SM: fewer final atomics
   size_t smem = sizeof(float) * 2 * C;
   if (C <= 128)
     ln_bwd_kernel<4><<<blocks, 256, smem, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, dgamma, dbeta, M, C, act);

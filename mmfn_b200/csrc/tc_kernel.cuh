@@ -203,6 +203,9 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         if (e.accum == 0 && full4) {
           *reinterpret_cast<float4*>(e.C + idx) = make_float4(x[0], x[1], x[2], x[3]);
+        } else if (e.accum == 2 && full4) {
+          // split-K / weight-gradient accumulation: one 16-byte vector reduction instead of four scalar atomics
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(e.C + idx), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
