@@ -12,7 +12,7 @@ replica, BatchNorm statistics stay rank-local as in the reference (no SyncBN).
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import ops, parallel
 from ._lib import lib
 
 _FIELDS = (
@@ -76,9 +76,7 @@ class TrainEngine:
 
     def broadcast_parameters(self, src=0):
         """What DistributedDataParallel's constructor does (phase2_train_net.py:269)."""
-        if self.world > 1:
-            dist.broadcast(self.st.flat, src, group=self.pg)
-            dist.broadcast(self.st.flat_buf, src, group=self.pg)
+        parallel.broadcast_([self.st.flat, self.st.flat_buf], src, self.pg)
 
     # ---- eager schedule ----------------------------------------------------------------------
     def forward_backward(self, b):
@@ -98,8 +96,7 @@ class TrainEngine:
         return loss
 
     def optimizer_step(self):
-        if self.world > 1:
-            dist.all_reduce(self.g_active, op=dist.ReduceOp.SUM, group=self.pg)   # ONE collective per step
+        parallel.allreduce_sum_(self.g_active, self.pg)                           # ONE collective per step
         ops.adamw_step_(self.p_active, self.g_active, self.m, self.v, self.state, self.lr, self.betas[0],
                         self.betas[1], self.eps, self.wd, grad_scale=1.0 / self.world)
 
