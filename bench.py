@@ -205,7 +205,8 @@ def run_native(args):
         lib().start_profile()
         for i in range(prof_steps):
             stager.dev.copy_(packed[i % nbuf])
-            eng.step(stager.dev_views)                     # eager schedule: one event pair per C-ABI call
+            eng.forward_backward(stager.dev_views)         # eager schedule: one event pair per C-ABI call
+            eng.optimizer_step(collective=False)           # rank 0 only: must not enter a collective here
         torch.cuda.synchronize()
         prof = lib().stop_profile()
         top_shapes = [dict(call=list(k), n=n // prof_steps, ms_per_step=round(ms / prof_steps, 3),

@@ -137,14 +137,14 @@ PFN_encodeTiled mmfn_get_encode_tiled() {
 
 int mmfn_make_tmap_f32(CUtensorMap* out, const float* base, int rank, const uint64_t* dims,
                        const uint64_t* strides_elems, const uint32_t* box, const uint32_t* elem_strides,
-                       bool swizzle32) {
+                       bool swizzle32, bool as_tf32) {
   PFN_encodeTiled enc = mmfn_get_encode_tiled();
   if (!enc) { mmfn_set_error("cuTensorMapEncodeTiled is unavailable"); return (int)cudaErrorNotSupported; }
   cuuint64_t gd[5], gs[5];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 1; i < rank; ++i) gs[i - 1] = strides_elems[i] * sizeof(float);
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gd, gs, bx, es,
+  CUresult r = enc(out, as_tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gd, gs, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -95,8 +95,9 @@ class TrainEngine:
         self.last_pred = pred
         return loss
 
-    def optimizer_step(self):
-        parallel.allreduce_sum_(self.g_active, self.pg)                           # ONE collective per step
+    def optimizer_step(self, collective=True):
+        if collective:
+            parallel.allreduce_sum_(self.g_active, self.pg)                       # ONE collective per step
         ops.adamw_step_(self.p_active, self.g_active, self.m, self.v, self.state, self.lr, self.betas[0],
                         self.betas[1], self.eps, self.wd, grad_scale=1.0 / self.world)
 

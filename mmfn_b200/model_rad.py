@@ -182,12 +182,16 @@ class Block:
         self.B, self.T, self.seed, self.ap, self.rp = B, T, seed, ap, rp
         h1 = self.ln1.fwd(x)
         qkv = self.qkv.fwd(h1)                                       # columns [key | query | value]
-        k, q, v = (self._heads(qkv, B, T, i * C) for i in range(3))
-        S = torch.empty((B, nh, T, T), device=x.device, dtype=torch.float32)
-        ops.gemm(q, k, S)
-        self.P, self.Pd = ops.softmax_fwd(S, 1.0 / math.sqrt(hs), ap, seed)
-        y = torch.empty((B * T, C), device=x.device, dtype=torch.float32)
-        ops.gemm(self.Pd, v.transpose(-1, -2), y.view(B, T, nh, hs).permute(0, 2, 1, 3))
+        if ops.attention_fwd_ok(T, C, nh):
+            # S = QK^T -> softmax -> dropout -> PV in ONE tcgen05 kernel; only P (and Pd) reach HBM
+            y, self.P, self.Pd = ops.attention_fwd(qkv, B, T, C, nh, ap, seed)
+        else:
+            k, q, v = (self._heads(qkv, B, T, i * C) for i in range(3))
+            S = torch.empty((B, nh, T, T), device=x.device, dtype=torch.float32)
+            ops.gemm(q, k, S)
+            self.P, self.Pd = ops.softmax_fwd(S, 1.0 / math.sqrt(hs), ap, seed)
+            y = torch.empty((B * T, C), device=x.device, dtype=torch.float32)
+            ops.gemm(self.Pd, v.transpose(-1, -2), y.view(B, T, nh, hs).permute(0, 2, 1, 3))
         self.qkv_out = qkv
         x1 = self.proj.fwd(y, res=x, drop_p=rp, seed=seed + 1)
         h2 = self.ln2.fwd(x1)

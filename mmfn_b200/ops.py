@@ -324,6 +324,23 @@ def pool_sum_bwd(dfused, nmod):
 
 
 # ------------------------------------------------------------------ softmax family
+def attention_fwd(qkv, B, T, C, nh, drop_p=0.0, seed=0):
+    """Fused tcgen05 attention forward on the (B*T, 3C) [key|query|value] buffer.
+    -> y (B*T, C), P (B,nh,T,T) softmax probabilities, Pd (= P after dropout; P itself when drop_p == 0)."""
+    assert qkv.is_contiguous() and qkv.shape == (B * T, 3 * C)
+    y = torch.empty((B * T, C), device=qkv.device, dtype=torch.float32)
+    P = torch.empty((B, nh, T, T), device=qkv.device, dtype=torch.float32)
+    Pd = torch.empty_like(P) if drop_p > 0 else None
+    hs = C // nh
+    lib().next_work = (4.0 * B * nh * T * T * hs, 4.0 * (B * T * 4 * C + B * nh * T * T), B, T, C, nh)
+    lib().attention_fwd_tf32(_p(qkv), _p(y), _p(P), _p(Pd), B, T, C, nh, float(drop_p), int(seed), _st())
+    return y, P, (Pd if Pd is not None else P)
+
+
+def attention_fwd_ok(T, C, nh):
+    return TF32 and C % nh == 0 and (C // nh) in (16, 32, 64, 128) and T % 32 == 0 and 32 <= T <= 256
+
+
 def softmax_fwd(s, scale, drop_p=0.0, seed=0):
     cols = s.shape[-1]
     rows = s.numel() // cols

@@ -1,0 +1,307 @@
+"""GPU op-level parity: every C-ABI kernel family against a plain fp32 torch reference evaluated on
+the CPU, on the layer shapes the MMFN step uses.  Tolerances: exact-fp32 kernels 1e-4 relative to the
+tensor's max; TF32 tensor-core kernels 3e-3 (10-bit mantissa inputs, fp32 accumulate)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def close(got, ref, tol):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    err = (got - ref).abs().max().item()
+    scale = max(ref.abs().max().item(), 1.0)
+    assert err <= tol * scale, (err, scale)
+
+
+@pytest.fixture(autouse=True)
+def _seed():
+    torch.manual_seed(0)
+    from mmfn_b200 import ops
+    yield
+    ops.TF32 = True
+
+
+# fwd / dgrad / wgrad of every distinct conv geometry of the three trunks (B=4 to keep the CPU reference fast)
+CONVS = [(4, 64, 64, 64, 3, 1, 1), (4, 64, 64, 128, 3, 2, 1), (4, 64, 64, 128, 1, 2, 0), (4, 32, 128, 128, 3, 1, 1),
+         (4, 32, 128, 256, 3, 2, 1), (4, 32, 128, 256, 1, 2, 0), (4, 16, 256, 256, 3, 1, 1), (4, 16, 256, 512, 3, 2, 1),
+         (4, 16, 256, 512, 1, 2, 0), (4, 8, 512, 512, 3, 1, 1), (2, 256, 3, 64, 7, 2, 3), (2, 256, 2, 64, 7, 2, 3)]
+
+
+@pytest.mark.parametrize("tf32", [False, True], ids=["fp32", "tf32"])
+@pytest.mark.parametrize("geom", CONVS, ids=lambda g: f"N{g[0]}H{g[1]}C{g[2]}-{g[3]}R{g[4]}s{g[5]}")
+def test_conv_fwd_dgrad_wgrad(geom, tf32):
+    from mmfn_b200 import ops
+    N, H, C, Co, R, stride, pad = geom
+    if not tf32 and H * C * Co > 64 * 64 * 128:
+        pytest.skip("exact SIMT path is covered on the smaller geometries")
+    ops.TF32 = tf32
+    tol = 3e-3 if tf32 else 1e-4
+    x = torch.randn(N, C, H, H)
+    w = torch.randn(Co, C, R, R) * (2.0 / (C * R * R)) ** 0.5
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, stride=stride, padding=pad)
+    dy = torch.randn_like(yr)
+    yr.backward(dy)
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    wk = w.permute(0, 2, 3, 1).contiguous().to(DEV)
+    dyn = dy.permute(0, 2, 3, 1).contiguous().to(DEV)
+    close(ops.conv2d_fwd(xn, wk, stride, pad).permute(0, 3, 1, 2), yr, tol)
+    if C >= 32:                                     # the stems never need a data gradient
+        res = torch.randn_like(xn)
+        dx = ops.conv2d_dgrad(dyn, wk, xn.shape, stride, pad, res=res)
+        close(dx.permute(0, 3, 1, 2), xr.grad + res.cpu().permute(0, 3, 1, 2), tol)
+    dw = torch.zeros_like(wk)
+    ops.conv2d_wgrad_(dyn, xn, dw, stride, pad)
+    close(dw.permute(0, 3, 1, 2), wr.grad, tol)
+
+
+@pytest.mark.parametrize("C,T", [(64, 192), (128, 192), (256, 192), (512, 256)])
+def test_linear_gemms_and_epilogues_tf32(C, T):
+    """qkv / proj / mlp GEMM shapes of one fusion-transformer block, forward and both backward products."""
+    from mmfn_b200 import ops
+    B = 4
+    M = B * T
+    x = torch.randn(M, C)
+    for (N, K) in [(3 * C, C), (C, C), (4 * C, C), (C, 4 * C)]:
+        a = torch.randn(M, K)
+        w = torch.randn(N, K) * K ** -0.5
+        bias, res, dy = torch.randn(N), torch.randn(M, N), torch.randn(M, N)
+        A, W, Bi, Rs, dY = (t.to(DEV) for t in (a, w, bias, res, dy))
+        out = torch.empty(M, N, device=DEV)
+        ops.gemm(A, W, out, bias=Bi, res=Rs, act=1)
+        close(out, torch.relu(a @ w.t() + bias) + res, 3e-3)
+        dX = torch.empty(M, K, device=DEV)
+        ops.gemm(dY, W.t(), dX, mask=A)                     # dgrad with the ReLU mask of the producer
+        close(dX, (dy @ w) * (a > 0), 3e-3)
+        dW = torch.ones(N, K, device=DEV)
+        ops.gemm(dY.t(), A.t(), dW, accum=1)                # wgrad accumulates into the flat grad buffer
+        close(dW, 1 + dy.t() @ a, 3e-3)
+    assert x is not None
+
+
+@pytest.mark.parametrize("C,T", [(64, 192), (128, 192), (256, 192), (512, 256)])
+def test_attention_products_on_strided_heads(C, T):
+    from mmfn_b200 import ops
+    B, nh = 3, 4
+    hs = C // nh
+    qkv = torch.randn(B * T, 3 * C)
+    dy = torch.randn(B * T, C)
+    dS = torch.randn(B, nh, T, T)
+    heads = lambda t2d, i: t2d[:, i * C:(i + 1) * C].view(B, T, nh, hs).permute(0, 2, 1, 3)
+    k, q, v = (heads(qkv, i) for i in range(3))
+    P = torch.softmax(q @ k.transpose(-1, -2) / hs ** 0.5, -1)
+    dyh = dy.view(B, T, nh, hs).permute(0, 2, 1, 3)
+    g_qkv, g_dy, g_dS, g_P = qkv.to(DEV), dy.to(DEV), dS.to(DEV), P.to(DEV)
+    gk, gq, gv = (heads(g_qkv, i) for i in range(3))
+    S = torch.empty(B, nh, T, T, device=DEV)
+    ops.gemm(gq, gk, S)
+    close(S, q @ k.transpose(-1, -2), 3e-3)
+    y = torch.empty(B * T, C, device=DEV)
+    yh = y.view(B, T, nh, hs).permute(0, 2, 1, 3)
+    ops.gemm(g_P, gv.transpose(-1, -2), yh)
+    close(yh, P @ v, 3e-3)
+    g_dyh = g_dy.view(B, T, nh, hs).permute(0, 2, 1, 3)
+    dqkv = torch.zeros_like(g_qkv)
+    dk, dq, dv = (heads(dqkv, i) for i in range(3))
+    ops.gemm(g_P.transpose(-1, -2), g_dyh.transpose(-1, -2), dv)
+    ops.gemm(g_dS, gk.transpose(-1, -2), dq)
+    ops.gemm(g_dS.transpose(-1, -2), gq.transpose(-1, -2), dk)
+    close(dv, P.transpose(-1, -2) @ dyh, 3e-3)
+    close(dq, dS @ k, 3e-3)
+    close(dk, dS.transpose(-1, -2) @ q, 3e-3)
+    # softmax forward / backward (scale, no dropout)
+    p, pd = ops.softmax_fwd(S, hs ** -0.5)
+    close(p, torch.softmax(S.cpu() * hs ** -0.5, -1), 1e-5)
+    Sr = S.cpu().clone().requires_grad_(True)
+    torch.softmax(Sr * hs ** -0.5, -1).backward(dS)
+    close(ops.softmax_bwd(p, g_dS, hs ** -0.5), Sr.grad, 1e-4)
+
+
+def test_batchnorm_train_forward_backward():
+    from mmfn_b200 import ops
+    for (N, H, C) in [(4, 32, 128), (16, 8, 512), (2, 64, 64)]:
+        x = torch.randn(N, C, H, H) * 2 + 0.5
+        res = torch.randn(N, C, H, H)
+        bn = torch.nn.BatchNorm2d(C).train()
+        with torch.no_grad():
+            bn.weight.uniform_(0.5, 1.5); bn.bias.normal_()
+        rm, rv = bn.running_mean.clone().to(DEV), bn.running_var.clone().to(DEV)
+        xr, rr = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+        yr = torch.relu(bn(xr) + rr)
+        dy = torch.randn_like(yr)
+        yr.backward(dy)
+        xn, rn = (t.permute(0, 2, 3, 1).contiguous().to(DEV) for t in (x, res))
+        g, b = bn.weight.data.to(DEV), bn.bias.data.to(DEV)
+        y, mean, rstd = ops.bn_train_fwd(xn, g, b, rm, rv, res=rn, relu=True)
+        close(y.permute(0, 3, 1, 2), yr, 1e-4)
+        close(rm, bn.running_mean, 1e-5); close(rv, bn.running_var, 1e-5)
+        dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        dx, dres = ops.bn_train_bwd(dy.permute(0, 2, 3, 1).contiguous().to(DEV), xn, y, mean, rstd, g, dg, db, want_dres=True)
+        close(dx.permute(0, 3, 1, 2), xr.grad, 1e-4)
+        close(dres.permute(0, 3, 1, 2), rr.grad, 1e-5)
+        close(dg, bn.weight.grad, 1e-4); close(db, bn.bias.grad, 1e-4)
+
+
+def test_layernorm_variants():
+    from mmfn_b200 import ops
+    for C, act in [(64, 0), (64, 1), (128, 2), (512, 0)]:
+        x = torch.randn(300, C) * 1.5 + 0.3
+        ln = torch.nn.LayerNorm(C)
+        with torch.no_grad():
+            ln.weight.uniform_(0.5, 1.5); ln.bias.normal_()
+        xr = x.clone().requires_grad_(True)
+        yr = ln(xr)
+        yr = torch.relu(yr) if act == 1 else (F.gelu(yr) if act == 2 else yr)
+        dy, dres = torch.randn_like(yr), torch.randn_like(yr)
+        yr.backward(dy)
+        g, b = ln.weight.data.to(DEV), ln.bias.data.to(DEV)
+        y, mean, rstd = ops.layernorm_fwd(x.to(DEV), g, b, act=act)
+        close(y, yr, 1e-5)
+        dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        dx = ops.layernorm_bwd(dy.to(DEV), x.to(DEV), g, b, mean, rstd, dg, db, act=act, dres=dres.to(DEV))
+        close(dx, xr.grad + dres, 1e-4)
+        close(dg, ln.weight.grad, 1e-4); close(db, ln.bias.grad, 1e-4)
+
+
+def test_pool_token_upsample_kernels():
+    from mmfn_b200 import ops
+    B, C = 3, 32
+    for H in (64, 32, 16, 8):
+        feats = [torch.randn(B, C, H, H, requires_grad=True) for _ in range(3)]
+        pos = torch.randn(1, 192, C, requires_grad=True)
+        vw, vb = torch.randn(C, 1, requires_grad=True), torch.randn(C, requires_grad=True)
+        vel = torch.rand(B) * 10
+        pooled = [F.adaptive_avg_pool2d(f, (8, 8)) for f in feats]
+        tokr = torch.cat([p.view(B, 1, C, 8, 8) for p in pooled], 1).permute(0, 1, 3, 4, 2).reshape(B, -1, C)
+        tokr = pos + tokr + F.linear(vel.unsqueeze(1), vw, vb).unsqueeze(1)
+        dtok = torch.randn_like(tokr)
+        tokr.backward(dtok)
+        fn = [f.detach().permute(0, 2, 3, 1).contiguous().to(DEV) for f in feats]
+        tok = ops.tokens_fwd(fn, pos.detach()[0].to(DEV), vw.detach()[:, 0].contiguous().to(DEV), vb.detach().to(DEV), vel.to(DEV))
+        close(tok, tokr, 1e-5)
+        df = [torch.zeros_like(f) for f in fn]
+        dpos, dvw, dvb = torch.zeros(192, C, device=DEV), torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        ops.tokens_bwd_(dtok.to(DEV), df, fn[0].shape, vel.to(DEV), dpos, dvw, dvb)
+        for m in range(3):
+            close(df[m].permute(0, 3, 1, 2), feats[m].grad, 1e-5)
+        close(dpos, pos.grad[0], 1e-4); close(dvw, vw.grad[:, 0], 1e-4); close(dvb, vb.grad, 1e-4)
+        if H > 8:
+            feat = torch.randn(B, C, H, H)
+            tk = torch.randn(B, 192, C, requires_grad=True)
+            g = tk[:, 64:128].view(B, 8, 8, C).permute(0, 3, 1, 2)
+            outr = feat + F.interpolate(g, scale_factor=H // 8, mode="bilinear", align_corners=True)
+            dA = torch.randn_like(outr)
+            outr.backward(dA)
+            out = ops.upsample_add_fwd(feat.permute(0, 2, 3, 1).contiguous().to(DEV), tk.detach().to(DEV), 1)
+            close(out.permute(0, 3, 1, 2), outr, 1e-5)
+            dtk = torch.zeros(B, 192, C, device=DEV)
+            ops.upsample_add_bwd_(dA.permute(0, 2, 3, 1).contiguous().to(DEV), dtk, 1)
+            close(dtk[:, 64:128], tk.grad[:, 64:128], 1e-4)
+    x = torch.relu(torch.randn(2, 64, 128, 128))
+    xr = x.clone().requires_grad_(True)
+    yr = F.max_pool2d(xr, 3, 2, 1)
+    dy = torch.randn_like(yr)
+    yr.backward(dy)
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    y, idx = ops.maxpool_fwd(xn)
+    close(y.permute(0, 3, 1, 2), yr, 0)
+    close(ops.maxpool_bwd(dy.permute(0, 2, 3, 1).contiguous().to(DEV), idx, xn.shape).permute(0, 3, 1, 2), xr.grad, 1e-6)
+
+
+def test_gat_vectornet_and_head_kernels():
+    from mmfn_b200 import ops
+    # radar GAT masked softmax incl. fully-masked rows (uniform 1/81) and the log-softmax relayout
+    z, adj = torch.randn(3, 81, 81), torch.randn(3, 81, 81)
+    adj[:, 5] = -1
+    zr = z.clone().requires_grad_(True)
+    e = F.leaky_relu(zr, 0.2)
+    attr = torch.softmax(torch.where(adj > 0, e, torch.full_like(e, -9e15)), -1)
+    d = torch.randn_like(attr)
+    attr.backward(d)
+    att, _ = ops.gat_softmax_fwd(z.to(DEV), adj.to(DEV), 0.2)
+    close(att, attr, 1e-6)
+    assert abs(att[0, 5].sum().item() - 1.0) < 1e-5 and abs(att[0, 5, 0].item() - 1 / 81) < 1e-6
+    close(ops.gat_softmax_bwd(z.to(DEV), adj.to(DEV), att, d.to(DEV), 0.2), zr.grad, 1e-5)
+    v = torch.randn(3, 256, 128)
+    vr = v.clone().requires_grad_(True)
+    yr = F.log_softmax(vr.view(3, 8, 8, 512).transpose(1, 3), dim=1)
+    dy = torch.randn_like(yr)
+    yr.backward(dy)
+    yy = ops.radar_logsoftmax_fwd(v.to(DEV), 3, 512)
+    close(yy.permute(0, 3, 1, 2), yr, 1e-5)
+    close(ops.radar_logsoftmax_bwd(dy.permute(0, 2, 3, 1).contiguous().to(DEV), yy).view(3, 256, 128), vr.grad, 1e-5)
+    # VectorNet: lane-to-lane attention restricted to query row 0, with ragged lane counts (incl. 1 lane)
+    B, L = 3, 40
+    qkv = torch.randn(B, L, 384)
+    ln = torch.tensor([40, 17, 1], dtype=torch.int32)
+    qr = qkv.clone().requires_grad_(True)
+    q, k, vv = [t.view(B, L, 2, 64).transpose(1, 2) for t in qr.chunk(3, -1)]
+    dots = (q @ k.transpose(-1, -2) * 0.125).masked_fill((torch.arange(L)[None, :] >= ln[:, None]).view(B, 1, 1, L), -1e9)
+    o = (torch.softmax(dots, -1) @ vv).transpose(1, 2).reshape(B, L, 128)[:, 0]
+    do = torch.randn_like(o)
+    o.backward(do)
+    prob, out = ops.l2l_row0_fwd(qkv.to(DEV), ln.to(DEV), 2, None)
+    close(out, o, 1e-5)
+    close(ops.l2l_row0_bwd(qkv.to(DEV), ln.to(DEV), prob, do.contiguous().to(DEV), 2), qr.grad, 1e-5)
+    # Subgraph segment max-pool + concat
+    G, V, C = 12, 9, 64
+    h = torch.randn(G * V, C)
+    hr = h.clone().view(G, V, C).requires_grad_(True)
+    yr2 = torch.cat([hr, hr.max(1)[0].unsqueeze(1).expand(G, V, C)], -1)
+    dy2 = torch.randn_like(yr2)
+    yr2.backward(dy2)
+    yy2, arg = ops.subgraph_pool_fwd(h.to(DEV), G, V)
+    close(yy2.view(G, V, 2 * C), yr2, 0)
+    close(ops.subgraph_pool_bwd(dy2.reshape(G * V, 2 * C).to(DEV), arg, G, V).view(G, V, C), hr.grad, 1e-6)
+    # GRU waypoint head + L1 loss + AdamW
+    Bh = 5
+    gru, lin = torch.nn.GRUCell(2, 64), torch.nn.Linear(64, 2)
+    z0 = torch.randn(Bh, 64, requires_grad=True)
+    tp, gt = torch.randn(Bh, 2) * 5, torch.randn(Bh, 4, 2)
+    zc, xc, wps = z0, torch.zeros(Bh, 2), []
+    for _ in range(4):
+        zc = gru(xc + tp, zc); xc = lin(zc) + xc; wps.append(xc)
+    predr = torch.stack(wps, 1)
+    lossr = F.l1_loss(predr, gt, reduction="none").mean()
+    lossr.backward()
+    P = [p.detach().to(DEV) for p in (gru.weight_ih, gru.weight_hh, gru.bias_ih, gru.bias_hh, lin.weight, lin.bias)]
+    pred, ctx = ops.gru_head_fwd(z0.detach().to(DEV), tp.to(DEV), *P, 4)
+    close(pred, predr, 1e-5)
+    loss, dpred = ops.l1_loss(pred, gt.to(DEV))
+    close(loss, lossr, 1e-6)
+    Gd = [torch.zeros_like(p) for p in P]
+    close(ops.gru_head_bwd(dpred, ctx, P[0], P[1], P[4], *Gd), z0.grad, 1e-5)
+    for g, p in zip(Gd, (gru.weight_ih, gru.weight_hh, gru.bias_ih, gru.bias_hh, lin.weight, lin.bias)):
+        close(g, p.grad, 1e-5)
+    n = 4096
+    p0, g0 = torch.randn(n), torch.randn(n)
+    pr = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([pr], lr=1e-4)
+    p, g = p0.to(DEV), g0.to(DEV)
+    m, v2, st = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), torch.zeros(3, device=DEV)
+    for _ in range(3):
+        pr.grad = g0.clone(); opt.step()
+        ops.adamw_step_(p, g, m, v2, st, 1e-4)
+    close(p, pr, 1e-6)
+
+
+def test_dropout_masks_are_consistent_between_kernels_and_passes():
+    """The same (seed, index) hash drives the GEMM epilogue (SIMT and tcgen05) and the stand-alone kernel used
+    in backward, so forward and backward see identical masks; keep-rate ~ 1-p."""
+    from mmfn_b200 import ops
+    M, N, K = 1024, 256, 128
+    A, W = torch.randn(M, K, device=DEV), torch.randn(N, K, device=DEV)
+    c1, c2 = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+    ops.TF32 = True
+    ops.gemm(A, W, c1, drop_p=0.1, seed=5)
+    ops.TF32 = False
+    ops.gemm(A, W, c2, drop_p=0.1, seed=5)
+    ones = torch.ones(M, N, device=DEV)
+    mask = ops.dropout(ones, 0.1, 5)
+    assert torch.equal(c1 == 0, mask == 0) and torch.equal(c2 == 0, mask == 0)
+    assert abs((mask == 0).float().mean().item() - 0.1) < 0.01
+    assert torch.allclose(mask[mask != 0], torch.tensor(1 / 0.9, device=DEV))

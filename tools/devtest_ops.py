@@ -410,6 +410,28 @@ def t_attn_tc():
         report(f"attn_tc dK=dS^T Q T{T} hs{hs}", dk, dS.transpose(-1, -2) @ q, tol=3e-3)
 
 
+def t_attn_fused():
+    """Fused tcgen05 attention forward vs torch, all four transformer geometries, with and without dropout."""
+    ops.TF32 = True
+    for (B, T, C, nh) in [(2, 192, 64, 4), (3, 192, 128, 4), (2, 192, 256, 4), (2, 256, 512, 4), (16, 256, 512, 4)]:
+        hs = C // nh
+        qkv = torch.randn(B * T, 3 * C, device=dev)
+        heads = lambda t2d, i: t2d[:, i * C:(i + 1) * C].view(B, T, nh, hs).permute(0, 2, 1, 3)
+        k, q, v = (heads(qkv, i) for i in range(3))
+        Pr = torch.softmax(q @ k.transpose(-1, -2) / hs ** 0.5, -1)
+        yr = (Pr @ v).permute(0, 2, 1, 3).reshape(B * T, C)
+        y, P, Pd = ops.attention_fwd(qkv, B, T, C, nh)
+        torch.cuda.synchronize()
+        report(f"attn_fused P T{T} hs{hs} B{B}", P, Pr, tol=2e-3)
+        report(f"attn_fused y T{T} hs{hs} B{B}", y, yr, tol=3e-3)
+        y2, P2, Pd2 = ops.attention_fwd(qkv, B, T, C, nh, 0.1, 1234)
+        torch.cuda.synchronize()
+        mask = ops.dropout(torch.ones_like(P2), 0.1, 1234)
+        report(f"attn_fused P(drop) T{T} hs{hs}", P2, Pr, tol=2e-3)
+        report(f"attn_fused Pd == P*mask T{T} hs{hs}", Pd2, P2 * mask, tol=1e-6)
+        report(f"attn_fused y(drop) T{T} hs{hs}", y2, ((Pr * mask) @ v).permute(0, 2, 1, 3).reshape(B * T, C), tol=3e-3)
+
+
 def t_conv_tc():
     """tcgen05 implicit-GEMM convolutions (fwd / stride-1 dgrad / wgrad) against torch fp32."""
     ops.TF32 = True
@@ -439,7 +461,7 @@ def t_conv_tc():
 if __name__ == "__main__":
     only = sys.argv[1:]
     ops.TF32 = False
-    for fn in (t_gemm, t_conv, t_bn, t_ln, t_pool, t_tokens, t_softmax, t_misc, t_head, t_bev, t_gemm_tc, t_attn_tc, t_conv_tc):
+    for fn in (t_gemm, t_conv, t_bn, t_ln, t_pool, t_tokens, t_softmax, t_misc, t_head, t_bev, t_gemm_tc, t_attn_tc, t_attn_fused, t_conv_tc):
         if only and fn.__name__ not in only:
             continue
         run(fn)
