@@ -205,8 +205,11 @@ def test_cuda_graph_replay_matches_eager_schedule(dev):
             model.load_state_dict(sd)
             eng.m.zero_(); eng.v.zero_(); eng.state.zero_()
         losses[mode] = [(eng.step_graph() if mode == "graph" else eng.step(db)).item() for _ in range(3)]
-    for a, g in zip(losses["eager"], losses["graph"]):
-        assert abs(a - g) < 2e-3, losses
+    # step 1 runs identical arithmetic up to atomic-accumulation order; later steps start from weights that
+    # already differ by that noise times the AdamW sign step, so only a loose bound is meaningful
+    for i, (a, g) in enumerate(zip(losses["eager"], losses["graph"])):
+        assert abs(a - g) < (1e-3 if i == 0 else 3e-2), losses
+    assert losses["graph"][2] < losses["graph"][0]        # and the replayed schedule does train
     # with the reference dropout (p = 0.1) two replays on identical weights/inputs must differ
     model = MMFN(GlobalConfig(), dev)
     model.load_state_dict(sd)
