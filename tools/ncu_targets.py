@@ -1,0 +1,48 @@
+#!/usr/bin/env python3
+"""GPU: launch the headline kernels on their production shapes (B=16) a few times so that
+`ncu --set full -k regex:...` can capture them in isolation.  Shapes: RadarGPT mlp GEMM, layer-3 conv
+fwd / wgrad, RadarGPT fused attention, BEV scatter, fused AdamW."""
+import os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mmfn_b200 import ops, synthetic
+import numpy as np
+
+dev = "cuda"
+torch.manual_seed(0)
+B = 16
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+# flush buffer (> 126 MB L2) between launches so every capture starts from HBM
+flush = torch.empty(64 * 1024 * 1024, device=dev)
+
+def run(fn):
+    for _ in range(reps):
+        flush.zero_()
+        fn()
+    torch.cuda.synchronize()
+
+# 1. GEMM fc1 of transformer4: (4096 x 512) @ (2048 x 512)^T, bias + ReLU
+A = torch.randn(B * 256, 512, device=dev); W = torch.randn(2048, 512, device=dev) * 0.02; bias = torch.zeros(2048, device=dev)
+C = torch.empty(B * 256, 2048, device=dev)
+run(lambda: ops.gemm(A, W, C, bias=bias, act=1))
+# 2. wgrad GEMM of the same layer (MN-major operands, split-K atomics)
+dY = torch.randn(B * 256, 2048, device=dev); dW = torch.zeros(2048, 512, device=dev)
+run(lambda: ops.gemm(dY.t(), A.t(), dW, accum=2))
+# 3. conv 3x3 256->256 @16x16 (layer3), fwd + wgrad; and 64->64 @64x64 (layer1)
+for (H, Cc) in [(16, 256), (64, 64)]:
+    x = torch.randn(B, H, H, Cc, device=dev); w = torch.randn(Cc, 3, 3, Cc, device=dev) * 0.05
+    dy = torch.randn(B, H, H, Cc, device=dev); dw = torch.zeros_like(w)
+    run(lambda: ops.conv2d_fwd(x, w, 1, 1))
+    run(lambda: ops.conv2d_wgrad_(dy, x, dw, 1, 1))
+# 4. fused attention, transformer4 geometry
+qkv = torch.randn(B * 256, 3 * 512, device=dev)
+run(lambda: ops.attention_fwd(qkv, B, 256, 512, 4, 0.1, 7))
+# 5. BEV scatter, 16 frames x 32768 points
+pts = torch.from_numpy(np.stack([synthetic.synth_points(1234 + i) for i in range(B)])).to(dev)
+run(lambda: ops.bev_scatter(pts))
+# 6. fused AdamW over 104.7 M parameters
+n = 104708260
+p = torch.randn(n, device=dev); g = torch.randn(n, device=dev); m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
+st = torch.zeros(3, device=dev)
+run(lambda: ops.adamw_step_(p, g, m, v, st, 1e-4))
+print("done")
