@@ -160,63 +160,90 @@ __global__ void ln_fwd_kernel(const float* __restrict__ x, const float* __restri
   for (int c = lane; c < C; c += 32) yr[c] = act_fwd((xr[c] - mu) * rs * gamma[c] + beta[c], act);
 }
 
-// dx = LN'(dy * act'(ln)) (+ dres); dgamma/dbeta accumulated with atomics.
-template <int MAXC32>
-__global__ void ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                              const float* __restrict__ gamma, const float* __restrict__ beta,
-                              const float* __restrict__ mean, const float* __restrict__ rstd,
-                              const float* __restrict__ dres, float* __restrict__ dx,
-                              float* __restrict__ dgamma, float* __restrict__ dbeta,
-                              int64_t M, int C, int act) {
-  extern __shared__ float sh[];  // 2*C floats
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
-  int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-  float pg[MAXC32], pb[MAXC32];
+// dx = LN'(dy * act'(ln)) (+ dres).  One warp per row, float4 columns (C % 4 == 0, C <= 128 * NV).
+template <int NV>
+__global__ void ln_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                 const float* __restrict__ dres, float* __restrict__ dx, int64_t M, int C, int act) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float mu = mean[row], rs = rstd[row];
+  float gv[NV][4], xh[NV][4];
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int j = 0; j < MAXC32; ++j) { pg[j] = 0.f; pb[j] = 0.f; }
-  for (int64_t row = blockIdx.x * (int64_t)wpb + (threadIdx.x >> 5); row < M; row += (int64_t)gridDim.x * wpb) {
-    const float* xr = x + row * C;
-    const float* gr = dy + row * C;
-    float mu = mean[row], rs = rstd[row];
-    float s1 = 0.f, s2 = 0.f;
-    float gv[MAXC32], xh[MAXC32];
+  for (int j = 0; j < NV; ++j) {
+    const int c = (lane + 32 * j) * 4;
 #pragma unroll
-    for (int j = 0; j < MAXC32; ++j) {
-      int c = lane + 32 * j;
-      gv[j] = 0.f; xh[j] = 0.f;
-      if (c < C) {
-        xh[j] = (xr[c] - mu) * rs;
-        float g = gr[c];
-        if (act) g *= act_grad(xh[j] * gamma[c] + beta[c], act);
-        pg[j] += g * xh[j];
-        pb[j] += g;
-        gv[j] = g * gamma[c];
-        s1 += gv[j];
-        s2 += gv[j] * xh[j];
-      }
-    }
-    s1 = warp_sum(s1) / (float)C;
-    s2 = warp_sum(s2) / (float)C;
+    for (int k = 0; k < 4; ++k) { gv[j][k] = 0.f; xh[j][k] = 0.f; }
+    if (c < C) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + row * C + c));
+      const float4 gy = __ldg(reinterpret_cast<const float4*>(dy + row * C + c));
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ga[4] = {gy.x, gy.y, gy.z, gy.w}, gma[4] = {gm.x, gm.y, gm.z, gm.w};
+      float ba[4] = {0.f, 0.f, 0.f, 0.f};
+      if (act) { const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + c)); ba[0] = bt.x; ba[1] = bt.y; ba[2] = bt.z; ba[3] = bt.w; }
 #pragma unroll
-    for (int j = 0; j < MAXC32; ++j) {
-      int c = lane + 32 * j;
-      if (c < C) {
-        float d = rs * (gv[j] - s1 - xh[j] * s2);
-        if (dres) d += dres[row * C + c];
-        dx[row * C + c] = d;
+      for (int k = 0; k < 4; ++k) {
+        xh[j][k] = (xa[k] - mu) * rs;
+        float g = ga[k];
+        if (act) g *= act_grad(xh[j][k] * gma[k] + ba[k], act);
+        gv[j][k] = g * gma[k];
+        s1 += gv[j][k];
+        s2 += gv[j][k] * xh[j][k];
       }
     }
   }
+  s1 = warp_sum(s1) / (float)C;
+  s2 = warp_sum(s2) / (float)C;
 #pragma unroll
-  for (int j = 0; j < MAXC32; ++j) {
-    int c = lane + 32 * j;
-    if (c < C) { atomicAdd(&sh[c], pg[j]); atomicAdd(&sh[C + c], pb[j]); }
+  for (int j = 0; j < NV; ++j) {
+    const int c = (lane + 32 * j) * 4;
+    if (c < C) {
+      float4 o;
+      o.x = rs * (gv[j][0] - s1 - xh[j][0] * s2);
+      o.y = rs * (gv[j][1] - s1 - xh[j][1] * s2);
+      o.z = rs * (gv[j][2] - s1 - xh[j][2] * s2);
+      o.w = rs * (gv[j][3] - s1 - xh[j][3] * s2);
+      if (dres) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(dres + row * C + c));
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      *reinterpret_cast<float4*>(dx + row * C + c) = o;
+    }
   }
+}
+
+// dgamma[c] += sum_rows dy' * xhat, dbeta[c] += sum_rows dy'  (dy' = dy * act'(ln)).
+// blockDim (32 columns, 8 row lanes); grid (C/32, row slabs).
+__global__ void ln_bwd_param_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M, int C, int act) {
+  __shared__ float s1[8][33], s2[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float a = 0.f, b = 0.f;
+  if (c < C) {
+    const float gm = gamma[c], bt = beta[c];
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      const float xh = (__ldg(x + r * C + c) - mean[r]) * rstd[r];
+      float g = __ldg(dy + r * C + c);
+      if (act) g *= act_grad(xh * gm + bt, act);
+      a += g * xh;
+      b += g;
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = b;
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    atomicAdd(dgamma + c, sh[c]);
-    atomicAdd(dbeta + c, sh[C + c]);
+  if (threadIdx.y == 0 && c < C) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
+    atomicAdd(dgamma + c, a);
+    atomicAdd(dbeta + c, b);
   }
 }
 
@@ -291,13 +318,16 @@ MMFN_API int mmfn_layernorm_bwd(const float* dy, const float* x, const float* ga
                                 const float* mean, const float* rstd, const float* dres, float* dx,
                                 float* dgamma, float* dbeta, int64_t M, int C, int act, cudaStream_t stream) {
   MMFN_CHECK_ARG(dy && x && gamma && beta && mean && rstd && dx && dgamma && dbeta, "ln_bwd: null pointer");
-  MMFN_CHECK_ARG(M >= 0 && C > 0 && C <= 512, "ln_bwd: C must be in (0, 512]");
+  MMFN_CHECK_ARG(M >= 0 && C > 0 && C <= 512 && C % 4 == 0, "ln_bwd: C must be a multiple of 4 in (0, 512]");
+  MMFN_CHECK_ARG((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx | (uintptr_t)dres | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0,
+                 "ln_bwd: 16-byte alignment");
   if (M == 0) return 0;
-  int64_t nb = ceil_div64(M, 8); int blocks = (int)(nb < 148 ? nb : 148);   // one CTA per SM: fewer final atomics
-  size_t smem = sizeof(float) * 2 * C;
-  if (C <= 128)
-    ln_bwd_kernel<4><<<blocks, 256, smem, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, dgamma, dbeta, M, C, act);
-  else
-    ln_bwd_kernel<16><<<blocks, 256, smem, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, dgamma, dbeta, M, C, act);
+  unsigned blocks = (unsigned)ceil_div64(M, 8);
+  if (C <= 128) ln_bwd_dx_kernel<1><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act);
+  else if (C <= 256) ln_bwd_dx_kernel<2><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act);
+  else ln_bwd_dx_kernel<4><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act);
+  int64_t slabs = ceil_div64(M, 128);
+  if (slabs > 256) slabs = 256;
+  ln_bwd_param_kernel<<<dim3((C + 31) / 32, (unsigned)slabs), dim3(32, 8), 0, stream>>>(dy, x, gamma, beta, mean, rstd, dgamma, dbeta, M, C, act);
   return mmfn_launch_status("layernorm_bwd");
 }

@@ -79,11 +79,12 @@ def gemm(A, B, C, *, bias=None, res=None, mask=None, alpha=1.0, act=0, accum=0,
                             _p(bias), _p(res), _p(mask), float(alpha), int(act), int(accum), float(drop_p),
                             int(seed), int(splitk) if splitk > 1 else 0, _st())
             return C
-    if splitk == 1 and act == 0 and mask is None and drop_p == 0 and K >= 8192:
-        # skinny outputs with a huge reduction (generator dgrad: 16x64 <- K=262144): split K over CTAs
+    if splitk == 1 and act == 0 and mask is None and drop_p == 0 and K >= 2048:
+        # skinny outputs with a huge reduction (generator dgrad: 16x64 <- K=262144; polyline wgrad: 64x7 <-
+        # K=18432): split K over CTAs so the reduction is not one CTA's serial loop
         tiles = ((M + 63) // 64) * ((N + 63) // 64) * nbt
         if tiles < 64:
-            splitk = max(1, min(K // 2048, 256 // tiles))
+            splitk = max(1, min(K // 256, 296 // tiles))
             if splitk > 1:
                 if accum == 0:
                     C.zero_()
