@@ -419,22 +419,55 @@ class _Net:
         self.gpts = [FusionGPT(st, f"{e}transformer{i + 1}", WIDTHS[i], 3 if i < 3 else 4, cfg, i) for i in range(4)]
         self.head = Head(st, cfg.pred_len)
         dev = st.device
+        self.side = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        self.use_streams = True
         self.mean = torch.tensor(IMAGENET_MEAN, device=dev, dtype=torch.float32)
         self.std = torch.tensor(IMAGENET_STD, device=dev, dtype=torch.float32)
 
+    # ---- stream-level parallelism -----------------------------------------------------------
+    # Between two fusion points the image / LiDAR / map trunks (and VectorNet, the radar GAT) are
+    # independent, and at B=16 most of their kernels fill only part of the 148 SMs.  They are issued on
+    # side streams forked from / joined into the main stream with events, so the CUDA graph captured
+    # by the engine contains parallel branches instead of one 1900-node chain.
+    def _fork(self, n):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        for s in self.side[:n]:
+            s.wait_event(ev)
+
+    def _join(self, n):
+        main = torch.cuda.current_stream()
+        for s in self.side[:n]:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            main.wait_event(ev)
+
+    def _parallel(self, *fns):
+        """Run fns[0] on the main stream and fns[1:] on side streams; returns their results in order."""
+        if not self.use_streams or len(fns) == 1:
+            return [f() for f in fns]
+        n = len(fns) - 1
+        self._fork(n)
+        out = [None] * len(fns)
+        for i, f in enumerate(fns[1:]):
+            with torch.cuda.stream(self.side[i]):
+                out[i + 1] = f()
+        out[0] = fns[0]()
+        self._join(n)
+        return out
+
     def forward(self, image, lidar, lane, lane_num, radar, radar_adj, target_point, velocity, seed, train):
-        img = self.img_stem.fwd(ops.nchw_to_nhwc(image, self.mean, self.std), train)
-        lid = self.lid_stem.fwd(ops.nchw_to_nhwc(lidar), train)
-        img = self.img_layers[0].fwd(img, train)
-        lid = self.lid_layers[0].fwd(lid, train)
-        mp = self.vectornet.fwd(lane, lane_num)
+        img, lid, mp, rad = self._parallel(
+            lambda: self.img_layers[0].fwd(self.img_stem.fwd(ops.nchw_to_nhwc(image, self.mean, self.std), train), train),
+            lambda: self.lid_layers[0].fwd(self.lid_stem.fwd(ops.nchw_to_nhwc(lidar), train), train),
+            lambda: self.vectornet.fwd(lane, lane_num),
+            lambda: self.gat.fwd(radar, radar_adj, seed + 900, train))
         for s in range(3):
             tok = self.gpts[s].fwd([img, lid, mp], velocity, seed, train)
-            img, lid, mp = (ops.upsample_add_fwd(f, tok, m) for m, f in enumerate((img, lid, mp)))
-            img = self.img_layers[s + 1].fwd(img, train)
-            mp = self.map_layers[s + 1].fwd(mp, train)
-            lid = self.lid_layers[s + 1].fwd(lid, train)
-        rad = self.gat.fwd(radar, radar_adj, seed + 900, train)
+            img, lid, mp = self._parallel(
+                lambda: self.img_layers[s + 1].fwd(ops.upsample_add_fwd(img, tok, 0), train),
+                lambda: self.lid_layers[s + 1].fwd(ops.upsample_add_fwd(lid, tok, 1), train),
+                lambda: self.map_layers[s + 1].fwd(ops.upsample_add_fwd(mp, tok, 2), train))
         feats = [img, lid, mp, rad]
         tok = self.gpts[3].fwd(feats, velocity, seed, train)
         fused = ops.pool_sum_fwd(feats, tok)
@@ -444,20 +477,25 @@ class _Net:
         dfused = self.head.bwd(dpred)
         dfe, dtok = ops.pool_sum_bwd(dfused, 4)
         self.gpts[3].bwd(dtok, dfe)
-        self.gat.bwd(dfe[3])
         dimg, dlid, dmp = dfe[0], dfe[1], dfe[2]
         for s in (2, 1, 0):
-            dimg = self.img_layers[s + 1].bwd(dimg)
-            dmp = self.map_layers[s + 1].bwd(dmp)
-            dlid = self.lid_layers[s + 1].bwd(dlid)
-            B, H, W, C = dimg.shape
+            B, C = dimg.shape[0], dimg.shape[3] // 2
             dtok = torch.empty((B, 192, C), device=dimg.device, dtype=torch.float32)
-            for m, d in enumerate((dimg, dlid, dmp)):
-                ops.upsample_add_bwd_(d, dtok, m)
+
+            def trunk(layers, d, m):
+                def run():
+                    g = layers[s + 1].bwd(d)
+                    ops.upsample_add_bwd_(g, dtok, m)          # disjoint 64-token slices of dtok
+                    return g
+                return run
+            branches = [trunk(self.img_layers, dimg, 0), trunk(self.lid_layers, dlid, 1), trunk(self.map_layers, dmp, 2)]
+            if s == 2:
+                branches.append(lambda: self.gat.bwd(dfe[3]))  # same side stream as its forward
+            dimg, dlid, dmp = self._parallel(*branches)[:3]
             self.gpts[s].bwd(dtok, [dimg, dlid, dmp])
-        self.vectornet.bwd(dmp)
-        self.img_stem.bwd(self.img_layers[0].bwd(dimg))
-        self.lid_stem.bwd(self.lid_layers[0].bwd(dlid))
+        self._parallel(lambda: self.img_stem.bwd(self.img_layers[0].bwd(dimg)),
+                       lambda: self.lid_stem.bwd(self.lid_layers[0].bwd(dlid)),
+                       lambda: self.vectornet.bwd(dmp))
 
 
 class _WholeNet(torch.autograd.Function):

@@ -178,9 +178,11 @@ _ws = {}
 
 
 def _bn_ws(dev):
-    if dev not in _ws:
-        _ws[dev] = torch.empty(2 * 4096, device=dev, dtype=torch.float64)
-    return _ws[dev]
+    """fp64 scratch for the BatchNorm partial sums: one per stream, since trunks run concurrently."""
+    key = (dev, torch.cuda.current_stream().cuda_stream)
+    if key not in _ws:
+        _ws[key] = torch.empty(2 * 4096, device=dev, dtype=torch.float64)
+    return _ws[key]
 
 
 def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5, res=None, relu=False):
