@@ -29,6 +29,42 @@ IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
 # --------------------------------------------------------------------------- building blocks
+class _Aux:
+    """Weight-gradient side streams.  In backward only the data-gradient chain is sequential; every
+    weight/bias gradient (wgrad conv, dW GEMM, bias column sum) is a leaf.  They are issued on an
+    auxiliary stream paired with the current one, so they overlap the dgrad chain (as parallel graph
+    branches once captured).  Inputs are kept alive until join_all() -- no allocator reuse hazards."""
+    enabled = True
+    streams, used, keep = {}, {}, []
+
+    @classmethod
+    def run(cls, fn, *tensors):
+        if not cls.enabled:
+            fn()
+            return
+        prim = torch.cuda.current_stream()
+        aux = cls.streams.get(prim.cuda_stream)
+        if aux is None:
+            aux = cls.streams[prim.cuda_stream] = torch.cuda.Stream(device=prim.device)
+        ev = torch.cuda.Event()
+        ev.record(prim)
+        aux.wait_event(ev)
+        cls.keep.extend(tensors)
+        with torch.cuda.stream(aux):
+            fn()
+        cls.used[aux.cuda_stream] = aux
+
+    @classmethod
+    def join_all(cls):
+        main = torch.cuda.current_stream()
+        for aux in cls.used.values():
+            ev = torch.cuda.Event()
+            ev.record(aux)
+            main.wait_event(ev)
+        cls.used.clear()
+        cls.keep.clear()
+
+
 class ConvBN:
     """conv (bias-free) -> BatchNorm2d [-> + residual] [-> ReLU]; torchvision BasicBlock pieces."""
 
@@ -51,7 +87,8 @@ class ConvBN:
     def bwd(self, dy, need_dx=True, want_dres=False, dx_res=None):
         dz, dres = ops.bn_train_bwd(dy, self.z, self.y if self.relu else None, self.mean, self.rstd, self.gam,
                                     self.dgam, self.dbet, want_dres)
-        ops.conv2d_wgrad_(dz, self.x, self.dw, self.stride, self.pad)
+        x = self.x
+        _Aux.run(lambda: ops.conv2d_wgrad_(dz, x, self.dw, self.stride, self.pad), dz, x)
         dx = ops.conv2d_dgrad(dz, self.w, self.x.shape, self.stride, self.pad, res=dx_res) if need_dx else None
         self.x = self.z = self.y = None
         return dx, dres
@@ -133,9 +170,13 @@ class Linear:
         ReLU mask of the PRODUCER of x into the dgrad GEMM epilogue."""
         if self.act == 1 and not masked:
             dy = ops.relu_bwd(dy, self.y)
-        if self.db is not None:
-            ops.colsum_(dy, self.db)
-        ops.gemm(dy.t(), self.x.t(), self.dw, accum=1)
+        x = self.x
+
+        def wgrad():
+            if self.db is not None:
+                ops.colsum_(dy, self.db)
+            ops.gemm(dy.t(), x.t(), self.dw, accum=1)
+        _Aux.run(wgrad, dy, x)
         dx = None
         if need_dx:
             dx = torch.empty((dy.shape[0], self.w.shape[1]), device=dy.device, dtype=torch.float32)
@@ -496,6 +537,7 @@ class _Net:
         self._parallel(lambda: self.img_stem.bwd(self.img_layers[0].bwd(dimg)),
                        lambda: self.lid_stem.bwd(self.lid_layers[0].bwd(dlid)),
                        lambda: self.vectornet.bwd(dmp))
+        _Aux.join_all()
 
 
 class _WholeNet(torch.autograd.Function):
