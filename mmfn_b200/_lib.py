@@ -60,7 +60,7 @@ class _Lib:
         return buf.value.decode()
 
     # kernels launched per C-ABI call when it is not exactly one (for the bench's launch count)
-    KERNELS_PER_CALL = {"mmfn_bn_train_fwd": 3, "mmfn_bn_eval_fwd": 2, "mmfn_bn_train_bwd": 2,
+    KERNELS_PER_CALL = {"mmfn_bn_train_fwd": 2, "mmfn_bn_eval_fwd": 2, "mmfn_bn_train_bwd": 2,
                         "mmfn_adamw_step": 2, "mmfn_tokens_bwd": 4, "mmfn_layernorm_bwd": 2}
 
     def _wrap(self, name, fn):

@@ -33,30 +33,47 @@ __global__ void bn_partial_kernel(const float* __restrict__ x, int64_t M, int C,
   }
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ ws, int64_t M, int C, float eps, float momentum,
-                                   float* __restrict__ mean, float* __restrict__ rstd,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double m = ws[c] / (double)M;
-  double var = ws[C + c] / (double)M - m * m;
-  if (var < 0.0) var = 0.0;
-  mean[c] = (float)m;
-  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (running_mean) {
-    double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
-    running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * m);
-    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
-  }
-}
-
+// y = (x - mean) * rstd * gamma + beta (+res, ReLU).  With ws != null the batch statistics are finalised here
+// from the fp64 partial sums (every CTA recomputes the C means into shared memory; CTA 0 also publishes
+// mean/rstd for backward and applies the running-statistics momentum update) -- no separate finalize launch.
 __global__ void bn_apply_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n4, int C4,
-                                const float4* __restrict__ mean, const float4* __restrict__ rstd,
+                                float* __restrict__ mean, float* __restrict__ rstd,
                                 const float4* __restrict__ gamma, const float4* __restrict__ beta,
-                                const float4* __restrict__ res, int relu) {
+                                const float4* __restrict__ res, int relu,
+                                const double* __restrict__ ws, int64_t M, float eps, float momentum,
+                                float* __restrict__ running_mean, float* __restrict__ running_var) {
+  extern __shared__ float sm[];            // mean[C] | rstd[C]
+  const int C = C4 * 4;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float m, r;
+    if (ws) {
+      double md = ws[c] / (double)M;
+      double var = ws[C + c] / (double)M - md * md;
+      if (var < 0.0) var = 0.0;
+      m = (float)md;
+      r = (float)(1.0 / sqrt(var + (double)eps));
+      if (blockIdx.x == 0) {
+        mean[c] = m;
+        rstd[c] = r;
+        if (running_mean) {
+          double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+          running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * md);
+          running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+        }
+      }
+    } else {
+      m = mean[c];
+      r = rstd[c];
+    }
+    sm[c] = m;
+    sm[C + c] = r;
+  }
+  __syncthreads();
+  const float4* sm_mean = reinterpret_cast<const float4*>(sm);
+  const float4* sm_rstd = reinterpret_cast<const float4*>(sm + C);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C4);
-    float4 v = __ldg(x + i), m = __ldg(mean + c), r = __ldg(rstd + c), g = __ldg(gamma + c), b = __ldg(beta + c);
+    float4 v = __ldg(x + i), m = sm_mean[c], r = sm_rstd[c], g = __ldg(gamma + c), b = __ldg(beta + c);
     float4 o;
     o.x = (v.x - m.x) * r.x * g.x + b.x;
     o.y = (v.y - m.y) * r.y * g.y + b.y;
@@ -261,10 +278,10 @@ MMFN_API int mmfn_bn_train_fwd(const float* x, float* y, int64_t M, int C,
   cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, stream);
   dim3 grid((C + 31) / 32, (unsigned)ceil_div64(M, BN_ROWS_PER_BLOCK));
   bn_partial_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, M, C, ws);
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(ws, M, C, eps, momentum, mean, rstd, running_mean, running_var);
   int64_t n4 = M * C / 4;
-  bn_apply_kernel<<<grid_1d(n4, 256), 256, 0, stream>>>((const float4*)x, (float4*)y, n4, C / 4,
-      (const float4*)mean, (const float4*)rstd, (const float4*)gamma, (const float4*)beta, (const float4*)res, relu);
+  bn_apply_kernel<<<grid_1d(n4, 256), 256, 2 * C * sizeof(float), stream>>>((const float4*)x, (float4*)y, n4, C / 4,
+      mean, rstd, (const float4*)gamma, (const float4*)beta, (const float4*)res, relu,
+      ws, M, eps, momentum, running_mean, running_var);
   return mmfn_launch_status("bn_train_fwd");
 }
 
@@ -298,8 +315,9 @@ MMFN_API int mmfn_bn_eval_fwd(const float* x, float* y, int64_t M, int C, const 
   MMFN_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "bn_eval: C must be a positive multiple of 4");
   bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, stream>>>(running_mean, running_var, eps, mean, rstd, C);
   int64_t n4 = M * C / 4;
-  bn_apply_kernel<<<grid_1d(n4, 256), 256, 0, stream>>>((const float4*)x, (float4*)y, n4, C / 4,
-      (const float4*)mean, (const float4*)rstd, (const float4*)gamma, (const float4*)beta, (const float4*)res, relu);
+  bn_apply_kernel<<<grid_1d(n4, 256), 256, 2 * C * sizeof(float), stream>>>((const float4*)x, (float4*)y, n4, C / 4,
+      mean, rstd, (const float4*)gamma, (const float4*)beta, (const float4*)res, relu,
+      nullptr, M, eps, 0.f, nullptr, nullptr);
   return mmfn_launch_status("bn_eval_fwd");
 }
 

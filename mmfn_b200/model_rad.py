@@ -55,6 +55,24 @@ class _Aux:
         cls.used[aux.cuda_stream] = aux
 
     @classmethod
+    def fork(cls, fn, *tensors):
+        """Like run(), but returns an event the caller's stream can wait on (local fork/join)."""
+        if not cls.enabled:
+            fn()
+            return None
+        cls.run(fn, *tensors)
+        aux = cls.streams[torch.cuda.current_stream().cuda_stream]
+        ev = torch.cuda.Event()
+        ev.record(aux)
+        return ev
+
+    @staticmethod
+    def wait(*events):
+        for ev in events:
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+
+    @classmethod
     def join_all(cls):
         main = torch.cuda.current_stream()
         for aux in cls.used.values():
@@ -254,11 +272,14 @@ class Block:
         dk, dq, dv = (self._heads(dqkv, B, T, i * C) for i in range(3))
         dyh = dy.view(B, T, nh, hs).permute(0, 2, 1, 3)
         dPd = torch.empty((B, nh, T, T), device=dy.device, dtype=torch.float32)
+        # critical chain: dPd -> dS -> dQ; dV and dK are leaves until the qkv backward: side stream
         ops.gemm(dyh, v, dPd)
-        ops.gemm(self.Pd.transpose(-1, -2), dyh.transpose(-1, -2), dv)
+        Pd = self.Pd
+        ev_v = _Aux.fork(lambda: ops.gemm(Pd.transpose(-1, -2), dyh.transpose(-1, -2), dv), Pd, dy, dqkv)
         dS = ops.softmax_bwd(self.P, dPd, 1.0 / math.sqrt(hs), self.ap, self.seed)
+        ev_k = _Aux.fork(lambda: ops.gemm(dS.transpose(-1, -2), q.transpose(-1, -2), dk), dS, qkv, dqkv)
         ops.gemm(dS, k.transpose(-1, -2), dq)
-        ops.gemm(dS.transpose(-1, -2), q.transpose(-1, -2), dk)
+        _Aux.wait(ev_v, ev_k)
         dh1 = self.qkv.bwd(dqkv)
         self.P = self.Pd = self.qkv_out = None
         return self.ln1.bwd(dh1, dres=dx1)
