@@ -18,7 +18,7 @@ from ._lib import lib
 _FIELDS = (
     ("rgb_u8", torch.uint8), ("points", torch.float32), ("lane", torch.float32), ("lane_num", torch.int32),
     ("radar", torch.float32), ("radar_adj", torch.float32), ("velocity", torch.float32),
-    ("target_point", torch.float32), ("gt_waypoints", torch.float32),
+    ("target_point", torch.float32), ("gt_waypoints", torch.float32), ("lidar", torch.float32),
 )
 
 
@@ -31,6 +31,8 @@ class BatchStager:
         self.device = torch.device(device)
         self.layout, off = [], 0
         for name, dtype in _FIELDS:
+            if name not in example:                         # either raw `points` or a pre-built `lidar` histogram
+                continue
             t = example[name]
             nbytes = t.numel() * dtype.itemsize
             self.layout.append((name, dtype, tuple(t.shape), off, nbytes))

@@ -66,6 +66,25 @@ def synth_frame(index, n_lanes=128, n_nodes=10, n_points=N_POINTS):
                 velocity=velocity, target_point=target_point, gt_waypoints=gt)
 
 
+def synth_sample(index, bev_fn, n_lanes=128, n_nodes=10, n_points=N_POINTS):
+    """One sample in the dict layout CARLA_Data.__getitem__ / the phase-1 pickles use
+    (dataloader.py:183-268): per-timestep lists, tuples for waypoints and target point, python floats.
+    `bev_fn(points_xyz) -> (2,256,256)` supplies the LiDAR histogram the reference stores in the pickle."""
+    f = synth_frame(index, n_lanes, n_nodes, n_points)
+    wps = [(0.0, 0.0)] + [(float(x), float(y)) for x, y in f["gt_waypoints"].astype(np.float64)]
+    return {
+        "fronts": [torch.from_numpy(center_crop_chw(f["rgb"]))],
+        "lidars": [np.asarray(bev_fn(f["points"][:, :3]), dtype=np.float32)],
+        "vectormaps": [torch.from_numpy(f["lane"][: f["lane_num"]].astype(np.float64))],
+        "radar": [f["radar"].astype(np.float64)],
+        "maps": [torch.from_numpy(center_crop_chw(f["rgb"][::-1].copy()))],
+        "waypoints": wps,
+        "target_point": (float(f["target_point"][0]), float(f["target_point"][1])),
+        "steer": 0.1 * index, "throttle": 0.5, "brake": False, "command": 4,
+        "velocity": float(f["velocity"]),
+    }
+
+
 def center_crop_chw(rgb, crop=256):
     """scale_and_crop_image with scale=1 (dataloader.py:296-308): HWC uint8 -> CHW uint8 crop."""
     h, w = rgb.shape[:2]

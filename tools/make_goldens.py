@@ -104,6 +104,36 @@ def model(B=2):
     print("loss", loss.item(), "unused params", len(unused))
 
 
+def describe(x):
+    """Type/shape/dtype tree of a collated batch (lists, dicts, tensors, scalars)."""
+    if isinstance(x, torch.Tensor):
+        return ["tensor", list(x.shape), str(x.dtype)]
+    if isinstance(x, dict):
+        return {k: describe(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [describe(v) for v in x]
+    return [type(x).__name__, x if isinstance(x, (int, float, bool, str)) else None]
+
+
+def collate():
+    """Reference collate_single_cpu + PRE_Data adjacency on 3 synthetic samples with 70/128/93 lanes."""
+    from mmfn_utils.datasets.data_utils import collate_single_cpu
+    samples = [synthetic.synth_sample(i, lidar_to_histogram_features) for i in range(3)]
+    for smp in samples:                                     # PRE_Data.__getitem__, dataloader.py:379-384
+        rows = [smp["radar"][0][:, 1] - smp["radar"][0][i, 1] for i in range(81)]
+        smp["radar_adj"] = np.array(rows)
+    out = collate_single_cpu(samples)
+    json.dump(describe(out), open(os.path.join(GOLD, "collate_structure.json"), "w"), indent=0)
+    np.savez_compressed(os.path.join(GOLD, "collate_golden.npz"),
+                        lanes=out["vectormaps"][0][0].numpy(), lane_nums=out["vectormaps"][0][1].numpy(),
+                        lmax=np.int64(out["vectormaps"][0][2]), radar_adj=out["radar_adj"].numpy(),
+                        radar=out["radar"][0].numpy(), velocity=out["velocity"].numpy(),
+                        target_point=torch.stack(out["target_point"], 1).numpy(),
+                        waypoints=torch.stack([torch.stack(w, 1) for w in out["waypoints"]], 1).numpy(),
+                        fronts_sum=np.int64(out["fronts"][0].long().sum()), lidars_sum=np.float64(out["lidars"][0].double().sum()))
+
+
 if __name__ == "__main__":
     bev()
+    collate()
     model(2)
