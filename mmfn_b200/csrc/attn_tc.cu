@@ -35,7 +35,7 @@ __device__ __forceinline__ void sts_swizzled_row(uint8_t* tile, int row, const f
   // K-major SWIZZLE_128B tile: row r at r*128 bytes, 16-byte chunk c stored at position c ^ (r & 7)
 #pragma unroll
   for (int c = 0; c < 8; ++c)
-    *reinterpret_cast<float4*>(tile + row * 128 + ((c ^ (row & 7)) << 4)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    tc::sts128(tc::smem_u32(tile) + row * 128 + ((c ^ (row & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
 }
 
 __global__ void __launch_bounds__(AT_THREADS)

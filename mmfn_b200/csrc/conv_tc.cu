@@ -181,7 +181,9 @@ MMFN_API int mmfn_conv2d_fwd_tf32(const float* x, const float* w, float* y, cons
   g.tiles_w = (Wo + g.BW - 1) / g.BW; g.tiles_h = (Ho + g.BH - 1) / g.BH; g.tiles_n = (N + g.BI - 1) / g.BI;
   CUtensorMap ta, tb;
   if (int rc = make_act_tmap(&ta, x, N, H, W, C, g.BW, g.BH, g.BI, stride, false)) return rc;
-  const int tbn = Co <= 64 ? 64 : 128;
+  // 128-wide filter tiles unless that leaves SMs idle (deep layers at small batch): then twice as many 64-wide
+  // tiles, which halves both the per-CTA epilogue and the split-K factor needed to fill the chip
+  const int tbn = (Co <= 64 || g.tiles_w * g.tiles_h * g.tiles_n * ((Co + 127) / 128) < 148) ? 64 : 128;
   {
     uint64_t dims[2] = {(uint64_t)R * S * C, (uint64_t)Co}, strides[2] = {1, (uint64_t)R * S * C};
     uint32_t box[2] = {32, (uint32_t)tbn};
@@ -194,7 +196,7 @@ MMFN_API int mmfn_conv2d_fwd_tf32(const float* x, const float* w, float* y, cons
   const int nkb = R * S * (C / 32);
   const int ctas = ptiles * ((Co + tbn - 1) / tbn);
   int splitk = 1;
-  if (ctas < 148) splitk = max(1, min(nkb / 8, (2 * 148 + ctas - 1) / ctas));
+  if (ctas < 148) splitk = max(1, min(nkb / 8, (2 * 148) / ctas));   // whole grid co-resident: 2 CTAs per SM
   int kb_per = (nkb + splitk - 1) / splitk;
   splitk = (nkb + kb_per - 1) / kb_per;
   if (splitk > 1) {
@@ -231,7 +233,7 @@ MMFN_API int mmfn_conv2d_wgrad_tf32(const float* dy, const float* x, float* dw,
   int co_tiles = (Co + tc::TBM - 1) / tc::TBM, ci_tiles = (C + tbn - 1) / tbn;
   if (splitk <= 0) {
     int ctas = co_tiles * ci_tiles * R * S;
-    splitk = max(1, min(npb / 8, (2 * 148 + ctas - 1) / ctas));
+    splitk = max(1, min(npb / 8, (2 * 148) / ctas));
   }
   int pb_per = (npb + splitk - 1) / splitk;
   splitk = (npb + pb_per - 1) / pb_per;

@@ -178,17 +178,21 @@ MMFN_API int mmfn_gemm_tf32(const float* A, int64_t lda, int a_mn, int64_t a_sb0
   MMFN_CHECK_ARG((((uintptr_t)A | (uintptr_t)B) & 15) == 0, "gemm_tf32: operands must be 16-byte aligned");
   const bool linear = (act == 0 && !mask && drop_p == 0.f);
   const int nb = nb0 * nb1;
+  // Tile width: 128 x 128 unless that leaves most SMs idle -- the epilogue is bound by the per-SM store path
+  // (~1 us per 128 x 128 fp32 tile), so small problems finish sooner as twice as many 128 x 64 tiles.
+  const int mt = (M + tc::TBM - 1) / tc::TBM;
+  const int tbn = (N <= 64 || (int64_t)mt * ((N + 127) / 128) * nb * (splitk > 1 ? splitk : 1) < 148) ? 64 : 128;
   if (splitk <= 0) {
     splitk = 1;
     if (accum == 2 && linear) {
-      int tiles = ((M + tc::TBM - 1) / tc::TBM) * ((N + 127) / 128) * nb;
+      int tiles = mt * ((N + tbn - 1) / tbn) * nb;
       int nkb = (K + tc::TBK - 1) / tc::TBK;
-      splitk = max(1, min(nkb / 4, (2 * 148 + tiles - 1) / tiles));
+      splitk = max(1, min(nkb / 4, (2 * 148) / tiles));
     }
   }
   MMFN_CHECK_ARG(splitk == 1 || (accum == 2 && linear), "gemm_tf32: split-K needs a linear atomic epilogue");
   MMFN_CHECK_ARG((int64_t)nb * splitk <= 65535, "gemm_tf32: too many batches x splits");
-  GemmArgs g{M, N, K, nb0, nb1, splitk, (N <= 64) ? 64 : 128, ldc, c_sb0, c_sb1};
+  GemmArgs g{M, N, K, nb0, nb1, splitk, tbn, ldc, c_sb0, c_sb1};
   CUtensorMap ta, tb;
   if (int rc = make_operand_tmap(&ta, &g.pa, A, a_mn != 0, M, K, lda, nb0, nb1, a_sb0, a_sb1, tc::TBM)) return rc;
   if (int rc = make_operand_tmap(&tb, &g.pb, B, b_mn != 0, N, K, ldb, nb0, nb1, b_sb0, b_sb1, g.tbn)) return rc;

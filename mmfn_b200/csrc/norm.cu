@@ -182,7 +182,8 @@ template <int NV>
 __global__ void ln_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  const float* __restrict__ mean, const float* __restrict__ rstd,
-                                 const float* __restrict__ dres, float* __restrict__ dx, int64_t M, int C, int act) {
+                                 const float* __restrict__ dres, float* __restrict__ dx, int64_t M, int C, int act,
+                                 float* __restrict__ dx_drop, float drop_p, uint64_t drop_seed) {
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -228,6 +229,14 @@ __global__ void ln_bwd_dx_kernel(const float* __restrict__ dy, const float* __re
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
       *reinterpret_cast<float4*>(dx + row * C + c) = o;
+      if (dx_drop) {        // gradient entering the next residual branch's dropout (same hash as the forward mask)
+        const uint64_t i0 = (uint64_t)(row * C + c);
+        o.x *= mmfn_dropout_scale(drop_p, drop_seed, i0);
+        o.y *= mmfn_dropout_scale(drop_p, drop_seed, i0 + 1);
+        o.z *= mmfn_dropout_scale(drop_p, drop_seed, i0 + 2);
+        o.w *= mmfn_dropout_scale(drop_p, drop_seed, i0 + 3);
+        *reinterpret_cast<float4*>(dx_drop + row * C + c) = o;
+      }
     }
   }
 }
@@ -332,20 +341,30 @@ MMFN_API int mmfn_layernorm_fwd(const float* x, const float* gamma, const float*
   return mmfn_launch_status("layernorm_fwd");
 }
 
+// parts: bit 0 = data gradient dx (+ dres; optionally also dx_drop = dx * dropout_mask(drop_p, drop_seed), the
+// gradient entering the dropout of the next residual branch), bit 1 = parameter gradients (accumulated).  The two
+// halves are independent kernels so that a caller can put the parameter reduction on a side stream.
 MMFN_API int mmfn_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* beta,
                                 const float* mean, const float* rstd, const float* dres, float* dx,
-                                float* dgamma, float* dbeta, int64_t M, int C, int act, cudaStream_t stream) {
-  MMFN_CHECK_ARG(dy && x && gamma && beta && mean && rstd && dx && dgamma && dbeta, "ln_bwd: null pointer");
+                                float* dgamma, float* dbeta, int64_t M, int C, int act, int parts,
+                                float* dx_drop, float drop_p, uint64_t drop_seed, cudaStream_t stream) {
+  MMFN_CHECK_ARG(dy && x && gamma && beta && mean && rstd, "ln_bwd: null pointer");
+  MMFN_CHECK_ARG((parts & 3) != 0 && (!(parts & 1) || dx) && (!(parts & 2) || (dgamma && dbeta)), "ln_bwd: missing output for the requested parts");
   MMFN_CHECK_ARG(M >= 0 && C > 0 && C <= 512 && C % 4 == 0, "ln_bwd: C must be a multiple of 4 in (0, 512]");
-  MMFN_CHECK_ARG((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx | (uintptr_t)dres | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0,
+  MMFN_CHECK_ARG((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx | (uintptr_t)dres | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)dx_drop) & 15) == 0,
                  "ln_bwd: 16-byte alignment");
   if (M == 0) return 0;
-  unsigned blocks = (unsigned)ceil_div64(M, 8);
-  if (C <= 128) ln_bwd_dx_kernel<1><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act);
-  else if (C <= 256) ln_bwd_dx_kernel<2><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act);
-  else ln_bwd_dx_kernel<4><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act);
-  int64_t slabs = ceil_div64(M, 128);
-  if (slabs > 256) slabs = 256;
-  ln_bwd_param_kernel<<<dim3((C + 31) / 32, (unsigned)slabs), dim3(32, 8), 0, stream>>>(dy, x, gamma, beta, mean, rstd, dgamma, dbeta, M, C, act);
+  if (parts & 1) {
+    unsigned blocks = (unsigned)ceil_div64(M, 8);
+    if (drop_p <= 0.f) dx_drop = nullptr;
+    if (C <= 128) ln_bwd_dx_kernel<1><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act, dx_drop, drop_p, drop_seed);
+    else if (C <= 256) ln_bwd_dx_kernel<2><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act, dx_drop, drop_p, drop_seed);
+    else ln_bwd_dx_kernel<4><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act, dx_drop, drop_p, drop_seed);
+  }
+  if (parts & 2) {
+    int64_t slabs = ceil_div64(M, 128);
+    if (slabs > 256) slabs = 256;
+    ln_bwd_param_kernel<<<dim3((C + 31) / 32, (unsigned)slabs), dim3(32, 8), 0, stream>>>(dy, x, gamma, beta, mean, rstd, dgamma, dbeta, M, C, act);
+  }
   return mmfn_launch_status("layernorm_bwd");
 }

@@ -153,8 +153,15 @@ __global__ void tokens_bwd_param_kernel(const float* __restrict__ dtok, const fl
   }
 }
 
-__device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int& i0, int& i1, float& l0, float& l1) {
-  float src = scale * (float)dst;
+// align: src = dst * (in-1)/(out-1)  (F.interpolate(align_corners=True), model_rad.py:530-539);
+// otherwise the half-pixel rule src = max(0, (dst + 0.5) * in/out - 0.5)  (align_corners=False, the default used by
+// benchmarks/transfuser/model.py:338-339)
+__device__ __forceinline__ float bilinear_scale(int in_size, int out_size, int align) {
+  if (align) return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+  return (float)in_size / (float)out_size;
+}
+__device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int& i0, int& i1, float& l0, float& l1, int align = 1) {
+  float src = align ? scale * (float)dst : fmaxf(0.f, ((float)dst + 0.5f) * scale - 0.5f);
   i0 = (int)src;
   if (i0 > in_size - 1) i0 = in_size - 1;
   i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
@@ -162,10 +169,10 @@ __device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, 
   l0 = 1.0f - l1;
 }
 
-// out = feat + bilinear_up(tok[:, m*64:(m+1)*64, :] as 8x8xC -> HxW), align_corners=True
+// out = feat + bilinear_up(tok[:, m*64:(m+1)*64, :] as 8x8xC -> HxW)
 __global__ void upsample_add_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ tok,
-                                        float* __restrict__ out, int m, int T, int B, int H, int W, int C) {
-  float sh = H > 1 ? 7.0f / (float)(H - 1) : 0.f, sw = W > 1 ? 7.0f / (float)(W - 1) : 0.f;
+                                        float* __restrict__ out, int m, int T, int B, int H, int W, int C, int align) {
+  float sh = bilinear_scale(8, H, align), sw = bilinear_scale(8, W, align);
   int64_t n = (int64_t)B * H * W * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
@@ -174,8 +181,8 @@ __global__ void upsample_add_fwd_kernel(const float* __restrict__ feat, const fl
     int h = (int)(t2 % H);
     int b = (int)(t2 / H);
     int h0, h1, w0, w1; float a0, a1, b0, b1;
-    bilinear_src(h, sh, 8, h0, h1, a0, a1);
-    bilinear_src(w, sw, 8, w0, w1, b0, b1);
+    bilinear_src(h, sh, 8, h0, h1, a0, a1, align);
+    bilinear_src(w, sw, 8, w0, w1, b0, b1, align);
     const float* tb = tok + ((int64_t)b * T + m * 64) * C + c;
     float v = a0 * (b0 * __ldg(tb + (h0 * 8 + w0) * C) + b1 * __ldg(tb + (h0 * 8 + w1) * C)) +
               a1 * (b0 * __ldg(tb + (h1 * 8 + w0) * C) + b1 * __ldg(tb + (h1 * 8 + w1) * C));
@@ -185,8 +192,8 @@ __global__ void upsample_add_fwd_kernel(const float* __restrict__ feat, const fl
 
 // dtok[b, m*64+p, c] = sum_{h,w} wy(p|h) wx(p|w) dA[b,h,w,c]
 __global__ void upsample_add_bwd_kernel(const float* __restrict__ dA, float* __restrict__ dtok,
-                                        int m, int T, int B, int H, int W, int C) {
-  float sh = H > 1 ? 7.0f / (float)(H - 1) : 0.f, sw = W > 1 ? 7.0f / (float)(W - 1) : 0.f;
+                                        int m, int T, int B, int H, int W, int C, int align) {
+  float sh = bilinear_scale(8, H, align), sw = bilinear_scale(8, W, align);
   int64_t n = (int64_t)B * 64 * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
@@ -195,17 +202,19 @@ __global__ void upsample_add_bwd_kernel(const float* __restrict__ dA, float* __r
     int b = (int)(t2 / 64);
     int py = p >> 3, px = p & 7;
     int hlo = 0, hhi = H - 1, wlo = 0, whi = W - 1;
-    if (sh > 0.f) { hlo = max(0, (int)floorf((py - 1) / sh) - 1); hhi = min(H - 1, (int)ceilf((py + 1) / sh) + 1); }
-    if (sw > 0.f) { wlo = max(0, (int)floorf((px - 1) / sw) - 1); whi = min(W - 1, (int)ceilf((px + 1) / sw) + 1); }
+    // conservative window of output pixels whose two source taps can include anchor (py, px); the half-pixel rule
+    // shifts the window by up to 0.5 / scale pixels.  Exact weights come from bilinear_src below.
+    if (sh > 0.f) { int mg = align ? 1 : (int)ceilf(0.5f / sh) + 1; hlo = max(0, (int)floorf((py - 1) / sh) - mg); hhi = min(H - 1, (int)ceilf((py + 1) / sh) + mg); }
+    if (sw > 0.f) { int mg = align ? 1 : (int)ceilf(0.5f / sw) + 1; wlo = max(0, (int)floorf((px - 1) / sw) - mg); whi = min(W - 1, (int)ceilf((px + 1) / sw) + mg); }
     float acc = 0.f;
     for (int h = hlo; h <= hhi; ++h) {
       int h0, h1; float a0, a1;
-      bilinear_src(h, sh, 8, h0, h1, a0, a1);
+      bilinear_src(h, sh, 8, h0, h1, a0, a1, align);
       float wy = (h0 == py ? a0 : 0.f) + (h1 == py ? a1 : 0.f);
       if (wy == 0.f) continue;
       for (int w = wlo; w <= whi; ++w) {
         int w0, w1; float b0, b1;
-        bilinear_src(w, sw, 8, w0, w1, b0, b1);
+        bilinear_src(w, sw, 8, w0, w1, b0, b1, align);
         float wx = (w0 == px ? b0 : 0.f) + (w1 == px ? b1 : 0.f);
         if (wx == 0.f) continue;
         acc += wy * wx * __ldg(dA + (((int64_t)b * H + h) * W + w) * C + c);
@@ -327,16 +336,16 @@ MMFN_API int mmfn_tokens_bwd(const float* dtokens, float* df0, float* df1, float
 }
 
 MMFN_API int mmfn_upsample_add_fwd(const float* feat, const float* tokens, float* out, int m, int T,
-                                   int B, int H, int W, int C, cudaStream_t stream) {
+                                   int B, int H, int W, int C, int align_corners, cudaStream_t stream) {
   MMFN_CHECK_ARG(feat && tokens && out && B > 0 && H >= 8 && W >= 8 && C > 0 && m >= 0 && (m + 1) * 64 <= T, "upsample_add_fwd: bad args");
-  upsample_add_fwd_kernel<<<grid_1d((int64_t)B * H * W * C, 256), 256, 0, stream>>>(feat, tokens, out, m, T, B, H, W, C);
+  upsample_add_fwd_kernel<<<grid_1d((int64_t)B * H * W * C, 256), 256, 0, stream>>>(feat, tokens, out, m, T, B, H, W, C, align_corners);
   return mmfn_launch_status("upsample_add_fwd");
 }
 
 MMFN_API int mmfn_upsample_add_bwd(const float* dA, float* dtokens, int m, int T, int B, int H, int W, int C,
-                                   cudaStream_t stream) {
+                                   int align_corners, cudaStream_t stream) {
   MMFN_CHECK_ARG(dA && dtokens && B > 0 && H >= 8 && W >= 8 && C > 0 && m >= 0 && (m + 1) * 64 <= T, "upsample_add_bwd: bad args");
-  upsample_add_bwd_kernel<<<grid_1d((int64_t)B * 64 * C, 128), 128, 0, stream>>>(dA, dtokens, m, T, B, H, W, C);
+  upsample_add_bwd_kernel<<<grid_1d((int64_t)B * 64 * C, 128), 128, 0, stream>>>(dA, dtokens, m, T, B, H, W, C, align_corners);
   return mmfn_launch_status("upsample_add_bwd");
 }
 

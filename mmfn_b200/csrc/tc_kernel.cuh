@@ -27,7 +27,7 @@ struct Epilogue {
   const float* mask;   // same indexing as C: out *= (mask > 0)
   float alpha;
   int act;             // 0 none, 1 relu
-  int accum;           // 0 store, 1 +=, 2 atomicAdd
+  int accum;           // 0 store, != 0 atomic accumulate (split-K / weight gradients)
   float drop_p;
   uint64_t drop_seed;
   unsigned long long* trace;   // optional: 8 x %globaltimer stamps of CTA 0 (mmfn_tc_set_trace), else null
@@ -135,16 +135,20 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // segments: result stores / atomics, residual and mask loads all run as 16-byte vectors.
     const int ew = warp - 2;                              // 0..7
     const int q = warp & 3;
-    float* stg = reinterpret_cast<float*>(smem) + ew * (32 * 36);
-    int64_t* row_off = reinterpret_cast<int64_t*>(smem + 8 * 32 * 36 * 4);          // [128]
+    const uint32_t stg = smem_u32(smem) + ew * (32 * 36 * 4);                      // this warp's [32][36] staging tile
+    const uint32_t row_off = smem_u32(smem) + 8 * 32 * 36 * 4;                     // int64 [128]
     int64_t my_off = 0;
     const bool my_ok = op.out_row(q * 32 + lane, my_off);
     const int N = op.n_cols(), n0 = op.col0();
-    const bool first = op.first_split(), have_k = kb1 > kb0;
-    const bool vec_ok = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0);
+    const bool have_k = kb1 > kb0;
+    const float* bias = op.first_split() ? e.bias : nullptr;    // bias / residual are added by the first K split only
+    const float* res = op.first_split() ? e.res : nullptr;
+    // 16-byte path: every row of this warp's quarter starts on a float4 boundary and the tile is full in N
+    const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0) && (n0 + TBN <= N) &&
+                     __all_sync(0xffffffffu, !my_ok || (my_off & 3) == 0);
     mbar_wait(tmem_full, 0);                              // all MMAs retired: TMEM valid, smem stages idle
     tc_fence_after();
-    if (ew < 4) row_off[q * 32 + lane] = my_ok ? my_off : -1;
+    if (ew < 4) sts64(row_off + (q * 32 + lane) * 8, my_ok ? my_off : (int64_t)-1);
     asm volatile("bar.sync 1, 256;" ::: "memory");        // row_off visible to the 8 epilogue warps
     if (threadIdx.x == 64) TC_STAMP(4);                   // accumulator visible to the epilogue
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
@@ -156,66 +160,78 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         float v[32];
         __syncwarp();                                     // tcgen05.ld is warp-collective (.sync.aligned)
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+        if (threadIdx.x == 64 && c == 0) TC_STAMP(7);       // first accumulator chunk in registers
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          sts128(stg + (lane * 36 + j) * 4, v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
       __syncwarp();
+      if (threadIdx.x == 64 && c == 0) TC_STAMP(8);         // re-tiled in shared memory
       const int col = col0 + c4;
-      float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (e.bias && first && col + 3 < N) bias4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-      else if (e.bias && first) {
-        if (col < N) bias4.x = __ldg(e.bias + col);
-        if (col + 1 < N) bias4.y = __ldg(e.bias + col + 1);
-        if (col + 2 < N) bias4.z = __ldg(e.bias + col + 2);
-      }
+      if (vec) {
+        // ---- fast path: float4 everywhere; kept small on purpose (this code runs once per CTA, from a cold
+        // instruction cache -- a fully unrolled, branchy epilogue costs more in fetch stalls than it saves)
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
+#pragma unroll 2
+        for (int rr = 0; rr < 8; ++rr) {
+          const int r = rr * 4 + rsub;
+          const int64_t off_r = lds64(row_off + (q * 32 + r) * 8);
+          if (off_r < 0) continue;
+          const int64_t idx = off_r + col;
+          const float4 a4 = lds128(stg + (r * 36 + c4) * 4);
+          float x[4] = {a4.x, a4.y, a4.z, a4.w};
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int rr = 0; rr < 8; ++rr) {
-        const int r = rr * 4 + rsub;
-        const int64_t off_r = row_off[q * 32 + r];
-        if (off_r < 0 || col >= N) continue;
-        const int64_t idx = off_r + col;
-        float4 a4 = *reinterpret_cast<const float4*>(stg + r * 36 + c4);
-        float x[4] = {a4.x, a4.y, a4.z, a4.w};
-        const float bb[4] = {bias4.x, bias4.y, bias4.z, bias4.w};
-        const bool full4 = vec_ok && (col + 3 < N) && ((idx & 3) == 0);
-        float m4[4] = {1.f, 1.f, 1.f, 1.f}, r4[4] = {0.f, 0.f, 0.f, 0.f};
-        if (full4) {
-          if (FULL && e.mask) { float4 t = __ldg(reinterpret_cast<const float4*>(e.mask + idx)); m4[0] = t.x; m4[1] = t.y; m4[2] = t.z; m4[3] = t.w; }
-          if (e.res && first) { float4 t = __ldg(reinterpret_cast<const float4*>(e.res + idx)); r4[0] = t.x; r4[1] = t.y; r4[2] = t.z; r4[3] = t.w; }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (col + j < N) {
-              if (FULL && e.mask) m4[j] = __ldg(e.mask + idx + j);
-              if (e.res && first) r4[j] = __ldg(e.res + idx + j);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float t = (have_k ? e.alpha * x[j] : 0.f) + bb[j];
+          for (int j = 0; j < 4; ++j) x[j] = (have_k ? e.alpha * x[j] : 0.f) + bb[j];
           if constexpr (FULL) {
-            if (e.act == 1) t = fmaxf(t, 0.f);
-            if (e.mask) t = m4[j] > 0.f ? t : 0.f;
-            if (e.drop_p > 0.f) t *= mmfn_dropout_scale(e.drop_p, e.drop_seed, (uint64_t)(idx + j));
-          }
-          x[j] = t + r4[j];
-        }
-        if (e.accum == 0 && full4) {
-          *reinterpret_cast<float4*>(e.C + idx) = make_float4(x[0], x[1], x[2], x[3]);
-        } else if (e.accum == 2 && full4) {
-          // split-K / weight-gradient accumulation: one 16-byte vector reduction instead of four scalar atomics
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(e.C + idx), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
-        } else {
+            if (e.act == 1) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (col + j < N) {
-              if (e.accum == 0) e.C[idx + j] = x[j];
-              else if (e.accum == 1) e.C[idx + j] += x[j];
-              else atomicAdd(e.C + idx + j, x[j]);
+              for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
             }
+            if (e.mask) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(e.mask + idx));
+              const float m4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) x[j] = m4[j] > 0.f ? x[j] : 0.f;
+            }
+            if (e.drop_p > 0.f) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) x[j] *= mmfn_dropout_scale(e.drop_p, e.drop_seed, (uint64_t)(idx + j));
+            }
+          }
+          if (res) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(res + idx));
+            x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w;
+          }
+          if (e.accum == 0) *reinterpret_cast<float4*>(e.C + idx) = make_float4(x[0], x[1], x[2], x[3]);
+          else  // split-K / weight-gradient accumulation: one 16-byte vector reduction instead of four scalar atomics
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(e.C + idx), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
+        }
+      } else {
+        // ---- ragged / unaligned tiles: scalar, not unrolled
+#pragma unroll 1
+        for (int rr = 0; rr < 8; ++rr) {
+          const int r = rr * 4 + rsub;
+          const int64_t off_r = lds64(row_off + (q * 32 + r) * 8);
+          if (off_r < 0) continue;
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            if (col + j >= N) break;
+            const int64_t idx = off_r + col + j;
+            float t = (have_k ? e.alpha * lds32(stg + (r * 36 + c4 + j) * 4) : 0.f) + (bias ? __ldg(bias + col + j) : 0.f);
+            if constexpr (FULL) {
+              if (e.act == 1) t = fmaxf(t, 0.f);
+              if (e.mask) t = __ldg(e.mask + idx) > 0.f ? t : 0.f;
+              if (e.drop_p > 0.f) t *= mmfn_dropout_scale(e.drop_p, e.drop_seed, (uint64_t)idx);
+            }
+            if (res) t += __ldg(res + idx);
+            if (e.accum == 0) e.C[idx] = t;
+            else atomicAdd(e.C + idx, t);
+          }
         }
       }
+      if (threadIdx.x == 64 && c == 0) TC_STAMP(9);         // first chunk's stores issued
     }
   }
   if (threadIdx.x == 64) TC_STAMP(5);                    // epilogue stores issued

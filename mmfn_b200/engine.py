@@ -90,7 +90,8 @@ class TrainEngine:
         self.st.flat_nbt.add_(model._nbt_step())
         lidar = b["lidar"] if "lidar" in b else ops.bev_scatter(b["points"])
         image = b["rgb_u8"] if "rgb_u8" in b else b["image"]
-        pred = self.net.forward(image, lidar, b["lane"], b["lane_num"], b["radar"], b["radar_adj"],
+        # the RGB+LiDAR-only variant (transfuser.TransFuser) has no lane / radar inputs
+        pred = self.net.forward(image, lidar, b.get("lane"), b.get("lane_num"), b.get("radar"), b.get("radar_adj"),
                                 b["target_point"], b["velocity"], model.seed, True)
         loss, dpred = ops.l1_loss(pred, b["gt_waypoints"])
         self.net.backward(dpred)

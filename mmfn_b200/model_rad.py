@@ -86,7 +86,8 @@ class _Aux:
 class ConvBN:
     """conv (bias-free) -> BatchNorm2d [-> + residual] [-> ReLU]; torchvision BasicBlock pieces."""
 
-    def __init__(self, st, conv_key, bn_key, stride, pad):
+    def __init__(self, st, conv_key, bn_key, stride, pad, dgrad=True):
+        self.dgrad, self.wt, self.wt_ev = dgrad, None, None
         self.w, self.dw = st.p(conv_key), st.g(conv_key)
         self.gam, self.dgam = st.p(bn_key + ".weight"), st.g(bn_key + ".weight")
         self.bet, self.dbet = st.p(bn_key + ".bias"), st.g(bn_key + ".bias")
@@ -96,6 +97,12 @@ class ConvBN:
     def fwd(self, x, res=None, relu=True, train=True):
         self.x, self.relu = x, relu
         self.z = ops.conv2d_fwd(x, self.w, self.stride, self.pad)
+        if train and self.dgrad and ops.dgrad_uses_flipped_filter(self.w, x.shape, self.stride):
+            # the data-gradient conv reads the mirrored CRSK filters: a pure function of the weights, so
+            # the transform is issued here on the side stream instead of on the backward critical path
+            def flip():
+                self.wt = ops.filter_crsk(self.w, flip=True)
+            self.wt_ev = _Aux.fork(flip)
         if train:
             self.y, self.mean, self.rstd = ops.bn_train_fwd(self.z, self.gam, self.bet, self.rm, self.rv, res=res, relu=relu)
         else:
@@ -107,8 +114,13 @@ class ConvBN:
                                     self.dgam, self.dbet, want_dres)
         x = self.x
         _Aux.run(lambda: ops.conv2d_wgrad_(dz, x, self.dw, self.stride, self.pad), dz, x)
-        dx = ops.conv2d_dgrad(dz, self.w, self.x.shape, self.stride, self.pad, res=dx_res) if need_dx else None
-        self.x = self.z = self.y = None
+        dx = None
+        if need_dx:
+            _Aux.wait(self.wt_ev)
+            dx = ops.conv2d_dgrad(dz, self.w, self.x.shape, self.stride, self.pad, res=dx_res, wt_flipped=self.wt)
+            if self.wt is not None:
+                _Aux.keep.append(self.wt)                # allocated on the side stream: hold until join_all()
+        self.x = self.z = self.y = self.wt = self.wt_ev = None
         return dx, dres
 
 
@@ -151,7 +163,7 @@ class Stem:
     """conv7x7/2 -> BN -> ReLU -> MaxPool3x3/2 on the (already NHWC) network input; no dgrad."""
 
     def __init__(self, st, prefix):
-        self.cb = ConvBN(st, prefix + ".conv1.weight", prefix + ".bn1", 2, 3)
+        self.cb = ConvBN(st, prefix + ".conv1.weight", prefix + ".bn1", 2, 3, dgrad=False)
 
     def fwd(self, x, train):
         y = self.cb.fwd(x, relu=True, train=train)
@@ -214,10 +226,15 @@ class LayerNorm:
         y, self.mean, self.rstd = ops.layernorm_fwd(x, self.g, self.b, act=self.act, out=out)
         return y
 
-    def bwd(self, dy, dres=None):
-        dx = ops.layernorm_bwd(dy, self.x, self.g, self.b, self.mean, self.rstd, self.dg, self.db, act=self.act, dres=dres)
+    def bwd(self, dy, dres=None, drop=None):
+        """dx (and, with drop=(p, seed), also dx * dropout mask).  The parameter-gradient reduction is a
+        leaf of the backward graph: it runs on the auxiliary stream."""
+        x, mean, rstd = self.x, self.mean, self.rstd
+        _Aux.run(lambda: ops.layernorm_bwd(dy, x, self.g, self.b, mean, rstd, self.dg, self.db, act=self.act, parts=2),
+                 dy, x, mean, rstd)
+        out = ops.layernorm_bwd(dy, x, self.g, self.b, mean, rstd, None, None, act=self.act, dres=dres, parts=1, drop=drop)
         self.x = None
-        return dx
+        return out
 
 
 class Block:
@@ -257,14 +274,14 @@ class Block:
         a = self.fc1.fwd(h2, act=1)
         return self.fc2.fwd(a, res=x1, drop_p=rp, seed=seed + 2)
 
-    def bwd(self, dx2):
+    def bwd(self, dx2, dz, drop_prev=None):
+        """dx2: gradient of the block output; dz = dx2 * dropout mask of the fc2 branch (produced by the
+        LayerNorm backward that made dx2).  drop_prev=(p, seed) asks for the same pair for the block below."""
         B, T, C, nh, hs = self.B, self.T, self.C, self.nh, self.hs
         a = self.fc1.y
-        dz = ops.dropout(dx2, self.rp, self.seed + 2)
         da = self.fc2.bwd(dz, dx_mask=a)                              # ReLU mask fused into the dgrad GEMM
         dh2 = self.fc1.bwd(da, masked=True)
-        dx1 = self.ln2.bwd(dh2, dres=dx2)
-        dzp = ops.dropout(dx1, self.rp, self.seed + 1)
+        dx1, dzp = self.ln2.bwd(dh2, dres=dx2, drop=(self.rp, self.seed + 1))
         dy = self.proj.bwd(dzp)
         qkv = self.qkv_out
         k, q, v = (self._heads(qkv, B, T, i * C) for i in range(3))
@@ -282,7 +299,7 @@ class Block:
         _Aux.wait(ev_v, ev_k)
         dh1 = self.qkv.bwd(dqkv)
         self.P = self.Pd = self.qkv_out = None
-        return self.ln1.bwd(dh1, dres=dx1)
+        return self.ln1.bwd(dh1, dres=dx1, drop=drop_prev if drop_prev is not None else (0.0, 0))
 
 
 class FusionGPT:
@@ -311,9 +328,11 @@ class FusionGPT:
 
     def bwd(self, dtok_out, dfeats):
         """dtok_out (B,T,C); dfeats: per-modality feature gradients, accumulated in place."""
-        d = self.ln_f.bwd(dtok_out.view(-1, self.C))
-        for blk in reversed(self.blocks):
-            d = blk.bwd(d)
+        blocks = self.blocks
+        d, dz = self.ln_f.bwd(dtok_out.view(-1, self.C), drop=(blocks[-1].rp, blocks[-1].seed + 2))
+        for i in range(len(blocks) - 1, -1, -1):
+            below = (blocks[i - 1].rp, blocks[i - 1].seed + 2) if i > 0 else None
+            d, dz = blocks[i].bwd(d, dz, below)
         ops.tokens_bwd_(d, dfeats, self.shape, self.vel, self.dpos, self.dvw, self.dvb, self.ep, self.seed)
 
 
@@ -596,6 +615,9 @@ class PIDController:
 
 
 class MMFN(nn.Module):
+    VARIANT = "rad"          # parameter inventory (params.param_spec) and kernel schedule of this model variant
+    NET = _Net
+
     def __init__(self, config, device):
         super().__init__()
         self.device = torch.device(device)
@@ -605,10 +627,10 @@ class MMFN(nn.Module):
         self.pred_len = config.pred_len
         self.turn_controller = PIDController(config.turn_KP, config.turn_KI, config.turn_KD, config.turn_n)
         self.speed_controller = PIDController(config.speed_KP, config.speed_KI, config.speed_KD, config.speed_n)
-        self.store = ParamStore(config, self.device)
+        self.store = ParamStore(config, self.device, self.VARIANT)
         self.store.register(self)
         self._param_items = list(self.named_parameters())
-        self.net = _Net(self.store, config)
+        self.net = self.NET(self.store, config)
         self.seed = 0
         self.reset_parameters()
 

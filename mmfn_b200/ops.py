@@ -140,19 +140,29 @@ def filter_crsk(w_krsc, flip=False):
     return wt
 
 
-def conv2d_dgrad(dy, w_krsc, x_shape, stride, pad, res=None):
+def dgrad_uses_flipped_filter(w_krsc, x_shape, stride):
+    """True when conv2d_dgrad runs as a forward convolution with the mirrored CRSK filters (tensor-core path)."""
+    N, H, W, C = x_shape
+    Co = w_krsc.shape[0]
+    return stride in (1, 2) and _tc_conv_ok(Co, C, H, W) and (stride == 1 or (H % 2 == 0 and W % 2 == 0))
+
+
+def conv2d_dgrad(dy, w_krsc, x_shape, stride, pad, res=None, wt_flipped=None):
+    """wt_flipped: optional pre-computed filter_crsk(w_krsc, flip=True) (see dgrad_uses_flipped_filter)."""
     N, H, W, C = x_shape
     Co, R, S, _ = w_krsc.shape
     _, Ho, Wo, _ = dy.shape
     if stride == 1 and _tc_conv_ok(Co, C, H, W):
         # stride-1 data gradient == forward convolution of dy with the mirrored, channel-swapped filters
-        return conv2d_fwd(dy, filter_crsk(w_krsc, flip=True), 1, R - 1 - pad, res=res)
+        wt = wt_flipped if wt_flipped is not None else filter_crsk(w_krsc, flip=True)
+        return conv2d_fwd(dy, wt, 1, R - 1 - pad, res=res)
     if stride == 2 and _tc_conv_ok(Co, C, H, W) and H == 2 * Ho and W == 2 * Wo:
         # stride-2: the same, on dy with zeros inserted between pixels (75 % of the MMA work multiplies
         # zeros, but it runs on the tensor cores instead of the SIMT gather kernel)
         up = torch.empty((N, H, W, Co), device=dy.device, dtype=torch.float32)
         lib().zero_upsample2_f32(_p(dy), _p(up), N, Ho, Wo, Co, _st())
-        return conv2d_fwd(up, filter_crsk(w_krsc, flip=True), 1, R - 1 - pad, res=res)
+        wt = wt_flipped if wt_flipped is not None else filter_crsk(w_krsc, flip=True)
+        return conv2d_fwd(up, wt, 1, R - 1 - pad, res=res)
     wt = filter_crsk(w_krsc)
     dx = torch.empty(x_shape, device=dy.device, dtype=torch.float32)
     lib().next_work = _conv_work(N, H, W, C, Co, R, S, Ho, Wo)
@@ -227,12 +237,19 @@ def layernorm_fwd(x2d, gamma, beta, act=0, eps=1e-5, out=None):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x2d, gamma, beta, mean, rstd, dgamma, dbeta, act=0, dres=None):
+def layernorm_bwd(dy, x2d, gamma, beta, mean, rstd, dgamma, dbeta, act=0, dres=None, parts=3, drop=None):
+    """parts bit 0: dx (returned), bit 1: dgamma/dbeta accumulation.  drop=(p, seed): also return
+    dx * dropout_mask(p, seed) -- the gradient entering the dropout of the next residual branch."""
     M, C = x2d.shape
     assert dy.is_contiguous() and x2d.is_contiguous()
-    dx = torch.empty_like(x2d)
+    dx = torch.empty_like(x2d) if parts & 1 else None
+    dxd, p, seed = None, 0.0, 0
+    if drop is not None and drop[0] > 0 and parts & 1:
+        dxd, p, seed = torch.empty_like(x2d), drop[0], drop[1]
     lib().layernorm_bwd(_p(dy), _p(x2d), _p(gamma), _p(beta), _p(mean), _p(rstd), _p(dres), _p(dx),
-                        _p(dgamma), _p(dbeta), M, C, act, _st())
+                        _p(dgamma), _p(dbeta), M, C, act, parts, _p(dxd), float(p), int(seed), _st())
+    if drop is not None:
+        return dx, (dxd if dxd is not None else dx)
     return dx
 
 
@@ -297,16 +314,17 @@ def tokens_bwd_(dtok, dfeats, shape, velocity, dpos, dvel_w, dvel_b, drop_p=0.0,
                      _p(dpos), _p(dvel_w), _p(dvel_b), drop_p, seed, _st())
 
 
-def upsample_add_fwd(feat, tok, m):
+def upsample_add_fwd(feat, tok, m, align_corners=True):
+    """feat + bilinear upsample of tokens [m*64, (m+1)*64) viewed as an 8x8 map (F.interpolate semantics)."""
     B, H, W, C = feat.shape
     out = torch.empty_like(feat)
-    lib().upsample_add_fwd(_p(feat), _p(tok), _p(out), m, tok.shape[1], B, H, W, C, _st())
+    lib().upsample_add_fwd(_p(feat), _p(tok), _p(out), m, tok.shape[1], B, H, W, C, int(align_corners), _st())
     return out
 
 
-def upsample_add_bwd_(dA, dtok, m):
+def upsample_add_bwd_(dA, dtok, m, align_corners=True):
     B, H, W, C = dA.shape
-    lib().upsample_add_bwd(_p(dA), _p(dtok), m, dtok.shape[1], B, H, W, C, _st())
+    lib().upsample_add_bwd(_p(dA), _p(dtok), m, dtok.shape[1], B, H, W, C, int(align_corners), _st())
 
 
 def pool_sum_fwd(feats, tok):

@@ -64,8 +64,29 @@ def _gpt(prefix, c, n_tok, n_layer, block_exp):
     return spec + _ln(prefix + ".ln_f", c)
 
 
-def param_spec(cfg):
+def _head_spec():
+    spec = _linear("join.0", 256, 512) + _linear("join.2", 128, 256) + _linear("join.4", 64, 128)
+    spec += [("decoder.weight_ih", (192, 2), "f"), ("decoder.weight_hh", (192, 64), "f"),
+             ("decoder.bias_ih", (192,), "f"), ("decoder.bias_hh", (192,), "f")]
+    return spec + _linear("output", 2, 64)
+
+
+def transfuser_param_spec(cfg):
+    """state_dict of benchmarks/transfuser/model.py:TransFuser (:403-427): RGB + LiDAR trunks, four GPTs over
+    (n_views + 1) * seq_len * 64 tokens (:147), join MLP, GRU cell, output layer."""
+    e = "encoder."
+    spec = _resnet(e + "image_encoder.features", RESNET34, 3)
+    spec += _resnet(e + "lidar_encoder._model", RESNET18, 2)
+    ntok = (cfg.n_views + 1) * cfg.seq_len * cfg.vert_anchors * cfg.horz_anchors
+    for i, c in enumerate(WIDTHS, start=1):
+        spec += _gpt(f"{e}transformer{i}", c, ntok, cfg.n_layer, cfg.block_exp)
+    return spec + _head_spec()
+
+
+def param_spec(cfg, variant="rad"):
     """[(key, shape, kind)] in reference state_dict order. kind: conv | f | buf | nbt."""
+    if variant == "transfuser":
+        return transfuser_param_spec(cfg)
     e = "encoder."
     spec = _resnet(e + "image_encoder.features", RESNET34, 3)
     spec += _resnet(e + "img_map_encoder.features", RESNET34, 3)
@@ -88,11 +109,7 @@ def param_spec(cfg):
     for i, c in enumerate((64, 128, 256), start=1):
         spec += _gpt(f"{e}transformer{i}", c, ntok, cfg.n_layer, cfg.block_exp)
     spec += _gpt(e + "transformer4", 512, ntok + cfg.seq_len * cfg.vert_anchors * cfg.horz_anchors, cfg.n_layer, cfg.block_exp)
-    spec += _linear("join.0", 256, 512) + _linear("join.2", 128, 256) + _linear("join.4", 64, 128)
-    spec += [("decoder.weight_ih", (192, 2), "f"), ("decoder.weight_hh", (192, 64), "f"),
-             ("decoder.bias_ih", (192,), "f"), ("decoder.bias_hh", (192,), "f")]
-    spec += _linear("output", 2, 64)
-    return spec
+    return spec + _head_spec()
 
 
 def is_unused(key):
@@ -110,8 +127,8 @@ def _numel(shape):
 
 
 class ParamStore:
-    def __init__(self, cfg, device):
-        self.spec = param_spec(cfg)
+    def __init__(self, cfg, device, variant="rad"):
+        self.spec = param_spec(cfg, variant)
         self.device = torch.device(device)
         fkeys = [(k, s) for k, s, kind in self.spec if kind in ("conv", "f")]
         order = self._flat_order([k for k, _ in fkeys])

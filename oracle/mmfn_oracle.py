@@ -180,6 +180,11 @@ def encoder(sd, cfg, image, lidar, lane, lane_num, radar, radar_adj, velocity, t
 def forward(sd, cfg, image, lidar, lane, lane_num, radar, radar_adj, target_point, velocity, train=True, taps=None):
     """-> pred_wp (B, pred_len, 2).  image (B,3,256,256) 0..255, lidar (B,2,256,256)."""
     fused = encoder(sd, cfg, image, lidar, lane, lane_num, radar, radar_adj, velocity, train, taps)
+    return head(sd, cfg, fused, target_point)
+
+
+def head(sd, cfg, fused, target_point):
+    """join MLP + GRUCell waypoint roll-out (model_rad.py:676-695; identical in benchmarks/transfuser/model.py:440-458)."""
     z = fused
     for i in (0, 2, 4):
         z = F.relu(F.linear(z, sd[f"join.{i}.weight"], sd[f"join.{i}.bias"]))
@@ -207,14 +212,14 @@ def is_float_param(k, v):
     return v.dtype.is_floating_point and not (k.endswith("running_mean") or k.endswith("running_var"))
 
 
-def train_step(sd, cfg, batch, opt_state=None, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, wd=0.01):
+def train_step(sd, cfg, batch, opt_state=None, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, wd=0.01, forward_fn=None):
     """One Engine.train iteration on CPU.  Mutates sd (params + BN buffers) in place.
     Returns (loss, pred_wp, grads dict).  opt_state: {'t': int, 'm': {}, 'v': {}} or None (no update)."""
     names = [k for k, v in sd.items() if is_float_param(k, v)]
     leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in names}
     work = dict(sd)
     work.update(leaves)
-    pred = forward(work, cfg, *batch["inputs"], train=True)
+    pred = (forward_fn or forward)(work, cfg, *batch["inputs"], train=True)
     loss = l1_loss(pred, batch["gt_waypoints"])
     loss.backward()
     for k in sd:                      # BN buffers were updated inside `work`

@@ -165,6 +165,17 @@ def test_layernorm_variants():
         dx = ops.layernorm_bwd(dy.to(DEV), x.to(DEV), g, b, mean, rstd, dg, db, act=act, dres=dres.to(DEV))
         close(dx, xr.grad + dres, 1e-4)
         close(dg, ln.weight.grad, 1e-4); close(db, ln.bias.grad, 1e-4)
+        # split form: data gradient (+ the dropout-masked copy for the next residual branch) and parameter
+        # gradients as two independent launches
+        dg2, db2 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        assert ops.layernorm_bwd(dy.to(DEV), x.to(DEV), g, b, mean, rstd, dg2, db2, act=act, parts=2) is None
+        close(dg2, dg, 1e-5); close(db2, db, 1e-5)
+        dx1, dxd = ops.layernorm_bwd(dy.to(DEV), x.to(DEV), g, b, mean, rstd, None, None, act=act, dres=dres.to(DEV),
+                                     parts=1, drop=(0.25, 77))
+        assert torch.equal(dx1, dx)
+        assert torch.equal(dxd, ops.dropout(dx, 0.25, 77))
+        dx1, dxd = ops.layernorm_bwd(dy.to(DEV), x.to(DEV), g, b, mean, rstd, None, None, act=act, parts=1, drop=(0.0, 0))
+        assert dxd is dx1
 
 
 def test_pool_token_upsample_kernels():

@@ -237,3 +237,113 @@ def test_eval_forward_matches_oracle(dev):
     assert rel < 1e-5, rel
     steer, throttle, brake, meta = model.control_pid(pred, b["velocity"].to(dev))
     assert -1.0 <= steer <= 1.0 and 0.0 <= throttle <= 0.75
+
+
+def _vectornet_setup(dev, B, L, P, tf32):
+    from mmfn_b200 import ops
+    from mmfn_b200.model_rad import MMFN
+    ops.TF32 = tf32
+    cfg = GlobalConfig(embd_pdrop=0.0, attn_pdrop=0.0, resid_pdrop=0.0)
+    model = MMFN(cfg, dev)
+    sd = synthetic.fill_golden_weights(model.state_dict(), 42)
+    model.load_state_dict(sd)
+    b = synthetic.synth_batch(B, first_index=300, n_lanes=L, n_nodes=P, n_points=0)
+    return model, sd, b
+
+
+@pytest.mark.parametrize("tf32", [False, True], ids=["fp32-simt", "tf32-tcgen05"])
+def test_config5_vectornet_only_matches_oracle(dev, tf32):
+    """BASELINE configs[4]: VectornetEncoder alone (256 polylines x 19 vector nodes), forward + backward,
+    against the oracle's autograd on a batch the CPU finishes in seconds (B=4)."""
+    from mmfn_b200.model_rad import _Aux
+    B, L, P = 4, 256, 20
+    model, sd, b = _vectornet_setup(dev, B, L, P, tf32)
+    vn = model.net.vectornet
+    model.store.flat_grad.zero_()
+    out = vn.fwd(b["lane"].to(dev), b["lane_num"].to(dev))                  # (B, 64, 64, 64) NHWC
+    dmap = torch.randn(B, 64, 64, 64, generator=torch.Generator().manual_seed(5))   # NCHW, like the oracle output
+    vn.bwd(dmap.permute(0, 2, 3, 1).contiguous().to(dev))
+    _Aux.join_all()
+    torch.cuda.synchronize()
+
+    pre = "encoder.vectornet_encoder."
+    osd = {k: v.clone().requires_grad_(k.startswith(pre)) for k, v in sd.items() if k.startswith(pre)}
+    oout = mmfn_oracle.vectornet(b["lane"], b["lane_num"], mmfn_oracle.Params(osd, pre))
+    oout.backward(dmap)
+    err = (out.permute(0, 3, 1, 2).cpu() - oout.detach()).abs().max().item() / oout.detach().abs().max().item()
+    assert err < (1e-5 if not tf32 else 2e-3), err
+    worst = 0.0
+    for k, v in osd.items():
+        if v.grad is None:                     # pos_emb MLP sees a constant zero input but still gets bias grads
+            continue
+        got = model.store.torch_view(k, grad=True)
+        rel = (got.detach().cpu() - v.grad).norm().item() / max(v.grad.norm().item(), 1e-6)
+        worst = max(worst, rel)
+        assert rel < (1e-3 if not tf32 else 3e-2), (k, rel)     # measured 2.7e-4 (fp32: split-K atomics over 20k vectors)
+
+
+def test_config5_vectornet_full_size_properties(dev):
+    """Size-independent checks at BASELINE's size (B=128, 256 polylines x 19 nodes): samples are independent,
+    padded lanes do not influence the result, gradients are finite."""
+    from mmfn_b200.model_rad import _Aux
+    B, L, P = 128, 256, 20
+    model, sd, b = _vectornet_setup(dev, B, L, P, True)
+    vn = model.net.vectornet
+    lane, num = b["lane"].to(dev), b["lane_num"].to(dev)
+    out = vn.fwd(lane, num).clone()
+    vn.bwd(torch.ones_like(out))
+    _Aux.join_all()
+    assert torch.isfinite(out).all() and torch.isfinite(model.store.flat_grad).all()
+    one = vn.fwd(lane[17:18].contiguous(), num[17:18].contiguous())
+    assert torch.allclose(one[0], out[17], rtol=1e-4, atol=1e-5)
+    # garbage in the padded lanes (index >= lane_num) must not change anything
+    dirty = lane.clone()
+    for i in range(B):
+        dirty[i, int(num[i]):] = 123.0
+    out2 = vn.fwd(dirty, num)
+    assert torch.allclose(out2, out, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("tf32", [False, True], ids=["fp32-simt", "tf32-tcgen05"])
+def test_config4_transfuser_matches_oracle_and_reference_goldens(dev, golden_dir, tf32):
+    """BASELINE configs[3]: RGB+LiDAR only (map / radar branches off) = benchmarks/transfuser/model.py topology."""
+    from mmfn_b200 import ops
+    from mmfn_b200.transfuser import TransFuser
+    from oracle import transfuser_oracle
+    ops.TF32 = tf32
+    cfg = GlobalConfig(embd_pdrop=0.0, attn_pdrop=0.0, resid_pdrop=0.0)
+    model = TransFuser(cfg, dev)
+    keys = json.load(open(os.path.join(golden_dir, "transfuser_state_dict_keys.json")))
+    assert list(model.state_dict().keys()) == list(keys.keys())
+    sd = synthetic.fill_golden_weights(model.state_dict(), 42)
+    model.load_state_dict(sd)
+    model.train()
+    b = synthetic.synth_batch(2)
+    wp_tol, loss_tol, grad_tol = (2e-4, 2e-4, 2e-2) if not tf32 else (1e-3, 1e-3, 0.6)
+    lidar = ops.bev_scatter(b["points"].to(dev))
+    pred = model([b["rgb_u8"].to(dev).float()], [lidar], b["target_point"].to(dev), b["velocity"].to(dev))
+    loss = torch.nn.functional.l1_loss(pred, b["gt_waypoints"].to(dev), reduction="none").mean()
+    loss.backward()
+    gold = np.load(os.path.join(golden_dir, "transfuser_golden_b2.npz"))
+    assert np.abs(pred.detach().cpu().numpy() - gold["pred_wp"]).mean() < wp_tol
+    assert abs(loss.item() - float(gold["loss"])) < loss_tol
+    osd = {k: v.clone() for k, v in sd.items()}
+    batch = dict(inputs=(b["rgb_u8"].float(), lidar.cpu(), b["target_point"], b["velocity"]), gt_waypoints=b["gt_waypoints"])
+    oloss, opred, ograds = transfuser_oracle.train_step(osd, cfg, batch)
+    assert (pred.detach().cpu() - opred).abs().mean().item() < wp_tol
+    dot = n1 = n2 = worst = 0.0
+    for k, p in model.named_parameters():
+        g, got = ograds[k], p.grad.detach().cpu()
+        worst = max(worst, (got - g).norm().item() / max(g.norm().item(), 1e-6))
+        dot += (got.double() * g.double()).sum().item()
+        n1 += got.double().pow(2).sum().item()
+        n2 += g.double().pow(2).sum().item()
+    assert worst < grad_tol, worst
+    assert dot / (n1 ** 0.5 * n2 ** 0.5) > (0.9999 if not tf32 else 0.97)
+    # the engine path (BEV scatter + fwd + bwd + AdamW, CUDA graph capturable) runs on the same variant
+    from mmfn_b200.engine import TrainEngine
+    eng = TrainEngine(model, lr=1e-4)
+    db = {k: b[k].to(dev) for k in ("rgb_u8", "points", "velocity", "target_point", "gt_waypoints")}
+    model.load_state_dict(sd)
+    l0 = eng.step(db).item()
+    assert abs(l0 - oloss.item()) < loss_tol

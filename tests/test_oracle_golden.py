@@ -82,3 +82,35 @@ def test_model_oracle_matches_reference_goldens(golden_dir):
             # flip sign, so the plain sum (entry 1) is excluded and the norm gets a loose bound
             got, ref = probe(sd[k[5:]], 6), gold[k]
             assert np.allclose(got[2:], ref[2:], rtol=1e-5, atol=1e-6) and abs(got[0] - ref[0]) < 1e-4 * ref[0], k
+
+
+def test_transfuser_oracle_matches_reference_goldens(golden_dir):
+    """RGB+LiDAR-only variant (BASELINE configs[3]): oracle/transfuser_oracle.py vs the unmodified
+    benchmarks/transfuser/model.py:TransFuser (goldens by tools/make_goldens.py)."""
+    from mmfn_b200.params import param_spec
+    from oracle import transfuser_oracle
+    gold = np.load(os.path.join(golden_dir, "transfuser_golden_b2.npz"))
+    keys = json.load(open(os.path.join(golden_dir, "transfuser_state_dict_keys.json")))
+    cfg = GlobalConfig(embd_pdrop=0.0, attn_pdrop=0.0, resid_pdrop=0.0)
+    # the native parameter inventory reproduces the reference state_dict (order, shapes, dtypes)
+    spec = param_spec(cfg, "transfuser")
+    assert [k for k, _, _ in spec] == list(keys.keys())
+    for k, shape, kind in spec:
+        assert list(shape) == keys[k][0], k
+    shapes = {k: torch.empty(v[0], dtype=getattr(torch, v[1].split(".")[1])) for k, v in keys.items()}
+    sd = synthetic.fill_golden_weights(shapes, 42)
+    b = synthetic.synth_batch(2)
+    lidar = torch.from_numpy(np.stack([bev_oracle.lidar_to_histogram_features(p[:, :3].numpy()) for p in b["points"]]))
+    batch = dict(inputs=(b["rgb_u8"].float(), lidar, b["target_point"], b["velocity"]), gt_waypoints=b["gt_waypoints"])
+    loss, pred, grads = transfuser_oracle.train_step(sd, cfg, batch)
+    assert abs(loss.item() - float(gold["loss"])) < 1e-5
+    assert np.abs(pred.numpy() - gold["pred_wp"]).max() < 2e-5
+    worst = 0.0
+    for k, g in grads.items():
+        assert g is not None, k
+        ref, got = gold["grad/" + k], probe(g, 6)
+        worst = max(worst, np.abs(np.delete(got - ref, 1)).max() / max(abs(ref[0]), 1e-6))
+    assert worst < 5e-3, worst
+    for k in gold.files:
+        if k.startswith("buf/"):
+            assert np.allclose(probe(sd[k[4:]], 4), gold[k], rtol=1e-4, atol=1e-5), k

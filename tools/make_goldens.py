@@ -133,7 +133,41 @@ def collate():
                         fronts_sum=np.int64(out["fronts"][0].long().sum()), lidars_sum=np.float64(out["lidars"][0].double().sum()))
 
 
+def transfuser(B=2):
+    """benchmarks/transfuser/model.py:TransFuser (RGB + LiDAR only, BASELINE configs[3]) on synth_batch(2)."""
+    from benchmarks.transfuser import model as tf_model
+    from benchmarks.transfuser.config import GlobalConfig as TFConfig
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    cfg = TFConfig()
+    cfg.embd_pdrop = cfg.attn_pdrop = cfg.resid_pdrop = 0.0
+    net = tf_model.TransFuser(cfg, "cpu")
+    sd = net.state_dict()
+    json.dump({k: [list(v.shape), str(v.dtype)] for k, v in sd.items()},
+              open(os.path.join(GOLD, "transfuser_state_dict_keys.json"), "w"), indent=0)
+    net.load_state_dict(synthetic.fill_golden_weights(sd, 42))
+    net.train()
+    b = synthetic.synth_batch(B)
+    lidar = torch.from_numpy(np.stack([lidar_to_histogram_features(p[:, :3].numpy()) for p in b["points"]]))
+    pred = net([b["rgb_u8"].float()], [lidar], b["target_point"], b["velocity"])
+    loss = torch.nn.functional.l1_loss(pred, b["gt_waypoints"], reduction="none").mean()
+    loss.backward()
+    out = {"pred_wp": pred.detach().numpy(), "loss": np.float64(loss.item())}
+    for k, p in net.named_parameters():
+        assert p.grad is not None, k
+        out["grad/" + k] = probe(p.grad, 6)
+    for k, v in net.state_dict().items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            out["buf/" + k] = probe(v, 4)
+    np.savez_compressed(os.path.join(GOLD, f"transfuser_golden_b{B}.npz"), **out)
+    print("transfuser loss", loss.item())
+
+
 if __name__ == "__main__":
+    if "--transfuser-only" in sys.argv:
+        transfuser(2)
+        sys.exit(0)
     bev()
     collate()
     model(2)
+    transfuser(2)

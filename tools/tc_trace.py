@@ -7,8 +7,8 @@ from mmfn_b200 import ops
 from mmfn_b200._lib import lib
 
 dev = "cuda"
-buf = torch.zeros(8, dtype=torch.int64, device=dev)
-names = ["entry", "setup done", "first TMA landed", "MMAs issued", "acc visible", "stores issued", "tmem freed"]
+buf = torch.zeros(16, dtype=torch.int64, device=dev)
+names = ["entry", "setup done", "first TMA landed", "MMAs issued", "acc visible", "stores issued", "tmem freed", "chunk0 in regs", "chunk0 retiled", "chunk0 stored"]
 for (M, N, K) in [(3072, 128, 128), (3072, 64, 64), (4096, 2048, 512), (128, 128, 32)]:
     A = torch.randn(M, K, device=dev); B = torch.randn(N, K, device=dev); C = torch.empty(M, N, device=dev)
     for it in range(3):
