@@ -287,7 +287,7 @@ def test_config5_vectornet_full_size_properties(dev):
     padded lanes do not influence the result, gradients are finite."""
     from mmfn_b200.model_rad import _Aux
     B, L, P = 128, 256, 20
-    model, sd, b = _vectornet_setup(dev, B, L, P, True)
+    model, sd, b = _vectornet_setup(dev, B, L, P, False)     # exact-fp32 kernels: the comparisons below are tight
     vn = model.net.vectornet
     lane, num = b["lane"].to(dev), b["lane_num"].to(dev)
     out = vn.fwd(lane, num).clone()
