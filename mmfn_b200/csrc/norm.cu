@@ -6,31 +6,78 @@
 namespace {
 
 // ------------------------------------------------------------------ BatchNorm
-// blockDim = (32 channels, 8 row lanes); block covers ROWS_PER_BLOCK rows of one 32-channel group.
-constexpr int BN_ROWS_PER_BLOCK = 128;
+// Column (per-channel) reductions over the (M, C) NHWC row matrix, 4 channels per thread (float4 loads), fp64
+// accumulation.  256 threads = QPR channel-quads x (256 / QPR) row lanes, QPR = min(C/4, 32); blockIdx.x selects
+// the group of QPR quads, blockIdx.y a slab of `rows_per_block` rows.  BWD = false: sum x, sum x^2 (forward
+// statistics).  BWD = true: sum dy', sum dy' * xhat with dy' = dy * (y > 0) when a ReLU followed.
+constexpr int BN_THREADS = 256;
 
-__global__ void bn_partial_kernel(const float* __restrict__ x, int64_t M, int C, double* __restrict__ ws) {
-  __shared__ double s1[8][33], s2[8][33];
-  int c = blockIdx.x * 32 + threadIdx.x;
-  int64_t r0 = (int64_t)blockIdx.y * BN_ROWS_PER_BLOCK;
-  int64_t r1 = min(M, r0 + BN_ROWS_PER_BLOCK);
-  double a = 0.0, b = 0.0;
-  if (c < C) {
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
-      float v = __ldg(x + r * C + c);
-      a += v;
-      b += (double)v * v;
+template <bool BWD>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_colsum_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float4* __restrict__ yout,
+                 const float* __restrict__ mean, const float* __restrict__ rstd, int64_t M, int C4, int qpr,
+                 int64_t rows_per_block, double* __restrict__ ws) {
+  __shared__ double red[BN_THREADS][8];
+  const int q = threadIdx.x % qpr, rsub = threadIdx.x / qpr, nrs = BN_THREADS / qpr;
+  const int cq = blockIdx.x * qpr + q;                          // channel quad of this thread
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cq < C4) {
+    float m4[4] = {0.f, 0.f, 0.f, 0.f}, r4[4] = {1.f, 1.f, 1.f, 1.f};
+    if (BWD) {
+      const float4 mm = __ldg(reinterpret_cast<const float4*>(mean) + cq), rr = __ldg(reinterpret_cast<const float4*>(rstd) + cq);
+      m4[0] = mm.x; m4[1] = mm.y; m4[2] = mm.z; m4[3] = mm.w;
+      r4[0] = rr.x; r4[1] = rr.y; r4[2] = rr.z; r4[3] = rr.w;
+    }
+#pragma unroll 2
+    for (int64_t r = r0 + rsub; r < r1; r += nrs) {
+      const float4 xv = __ldg(x + r * C4 + cq);
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+      if (!BWD) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { acc[k] += xa[k]; acc[4 + k] += (double)xa[k] * xa[k]; }
+      } else {
+        const float4 gv = __ldg(dy + r * C4 + cq);
+        float ga[4] = {gv.x, gv.y, gv.z, gv.w};
+        if (yout) {
+          const float4 yv = __ldg(yout + r * C4 + cq);
+          if (!(yv.x > 0.f)) ga[0] = 0.f;
+          if (!(yv.y > 0.f)) ga[1] = 0.f;
+          if (!(yv.z > 0.f)) ga[2] = 0.f;
+          if (!(yv.w > 0.f)) ga[3] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { acc[k] += ga[k]; acc[4 + k] += (double)ga[k] * ((xa[k] - m4[k]) * r4[k]); }
+      }
     }
   }
-  s1[threadIdx.y][threadIdx.x] = a;
-  s2[threadIdx.y][threadIdx.x] = b;
-  __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
 #pragma unroll
-    for (int i = 1; i < 8; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
-    atomicAdd(ws + c, a);
-    atomicAdd(ws + C + c, b);
+  for (int k = 0; k < 8; ++k) red[threadIdx.x][k] = acc[k];
+  __syncthreads();
+  // thread t < qpr * 8 reduces one (quad, component) over the row lanes
+  if (threadIdx.x < qpr * 8) {
+    const int qq = threadIdx.x >> 3, k = threadIdx.x & 7;
+    const int cqq = blockIdx.x * qpr + qq;
+    if (cqq < C4) {
+      double t = 0.0;
+      for (int rs = 0; rs < nrs; ++rs) t += red[rs * qpr + qq][k];
+      atomicAdd(ws + (k < 4 ? 0 : (int64_t)C4 * 4) + cqq * 4 + (k & 3), t);
+    }
   }
+}
+
+static inline void bn_colsum_grid(int64_t M, int C, int& qpr, dim3& grid, int64_t& rows_per_block) {
+  const int C4 = C / 4;
+  qpr = C4 < 32 ? C4 : 32;
+  while (BN_THREADS % qpr) --qpr;                                // C4 = 16, 32, 64, 128 here; stay safe for odd widths
+  const int groups = (C4 + qpr - 1) / qpr;
+  const int nrs = BN_THREADS / qpr;
+  int64_t slabs = ceil_div64(M, (int64_t)nrs * 4);               // at least 4 rows per thread
+  const int64_t cap = (148 * 4 + groups - 1) / groups;
+  if (slabs > cap) slabs = cap;
+  if (slabs < 1) slabs = 1;
+  rows_per_block = ceil_div64(M, slabs);
+  grid = dim3((unsigned)groups, (unsigned)ceil_div64(M, rows_per_block));
 }
 
 // y = (x - mean) * rstd * gamma + beta (+res, ReLU).  With ws != null the batch statistics are finalised here
@@ -85,59 +132,54 @@ __global__ void bn_apply_kernel(const float4* __restrict__ x, float4* __restrict
   }
 }
 
-// sums over rows of dy' and dy'*xhat where dy' = dy * (y > 0) when a ReLU followed.
-__global__ void bn_bwd_partial_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                      const float* __restrict__ yout, const float* __restrict__ mean,
-                                      const float* __restrict__ rstd, int64_t M, int C, double* __restrict__ ws) {
-  __shared__ double s1[8][33], s2[8][33];
-  int c = blockIdx.x * 32 + threadIdx.x;
-  int64_t r0 = (int64_t)blockIdx.y * BN_ROWS_PER_BLOCK;
-  int64_t r1 = min(M, r0 + BN_ROWS_PER_BLOCK);
-  double a = 0.0, b = 0.0;
-  if (c < C) {
-    float m = mean[c], rs = rstd[c];
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
-      float g = __ldg(dy + r * C + c);
-      if (yout && !(__ldg(yout + r * C + c) > 0.f)) g = 0.f;
-      float xh = (__ldg(x + r * C + c) - m) * rs;
-      a += g;
-      b += (double)g * xh;
-    }
-  }
-  s1[threadIdx.y][threadIdx.x] = a;
-  s2[threadIdx.y][threadIdx.x] = b;
-  __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-#pragma unroll
-    for (int i = 1; i < 8; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
-    atomicAdd(ws + c, a);
-    atomicAdd(ws + C + c, b);
-  }
-}
-
-__global__ void bn_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                 const float* __restrict__ yout, const float* __restrict__ mean,
+// dx = gamma * rstd * (dy' - mean(dy') - xhat * mean(dy' * xhat)); dres = dy' (residual branch).  float4 over channels;
+// the per-channel coefficients are staged in shared memory once per CTA.  CTA 0 accumulates dgamma / dbeta.
+__global__ void bn_bwd_dx_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
+                                 const float4* __restrict__ yout, const float* __restrict__ mean,
                                  const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                 const double* __restrict__ ws, int64_t M, int C,
-                                 float* __restrict__ dx, float* __restrict__ dres,
+                                 const double* __restrict__ ws, int64_t M, int C4,
+                                 float4* __restrict__ dx, float4* __restrict__ dres,
                                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  int64_t n = M * C;
-  double invM = 1.0 / (double)M;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C);
-    float g = __ldg(dy + i);
-    if (yout && !(__ldg(yout + i) > 0.f)) g = 0.f;
-    float rs = rstd[c];
-    float xh = (__ldg(x + i) - mean[c]) * rs;
-    float sdy = (float)(ws[c] * invM), sdx = (float)(ws[C + c] * invM);
-    dx[i] = gamma[c] * rs * (g - sdy - xh * sdx);
-    if (dres) dres[i] = g;
-  }
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  extern __shared__ float sm[];            // mean[C] | rstd[C] | gamma*rstd[C] | mean(dy')[C] | mean(dy' xhat)[C]
+  const int C = C4 * 4;
+  const double invM = 1.0 / (double)M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float rs = rstd[c];
+    sm[c] = mean[c];
+    sm[C + c] = rs;
+    sm[2 * C + c] = gamma[c] * rs;
+    sm[3 * C + c] = (float)(ws[c] * invM);
+    sm[4 * C + c] = (float)(ws[C + c] * invM);
+    if (blockIdx.x == 0) {
       dbeta[c] += (float)ws[c];
       dgamma[c] += (float)ws[C + c];
     }
+  }
+  __syncthreads();
+  const float4* s_mean = reinterpret_cast<const float4*>(sm);
+  const float4* s_rstd = reinterpret_cast<const float4*>(sm + C);
+  const float4* s_k = reinterpret_cast<const float4*>(sm + 2 * C);
+  const float4* s_dy = reinterpret_cast<const float4*>(sm + 3 * C);
+  const float4* s_dx = reinterpret_cast<const float4*>(sm + 4 * C);
+  const int64_t n4 = M * C4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    float4 g = __ldg(dy + i);
+    if (yout) {
+      const float4 yv = __ldg(yout + i);
+      if (!(yv.x > 0.f)) g.x = 0.f;
+      if (!(yv.y > 0.f)) g.y = 0.f;
+      if (!(yv.z > 0.f)) g.z = 0.f;
+      if (!(yv.w > 0.f)) g.w = 0.f;
+    }
+    const float4 xv = __ldg(x + i), m = s_mean[c], r = s_rstd[c], k = s_k[c], a = s_dy[c], b = s_dx[c];
+    float4 o;
+    o.x = k.x * (g.x - a.x - (xv.x - m.x) * r.x * b.x);
+    o.y = k.y * (g.y - a.y - (xv.y - m.y) * r.y * b.y);
+    o.z = k.z * (g.z - a.z - (xv.z - m.z) * r.z * b.z);
+    o.w = k.w * (g.w - a.w - (xv.w - m.w) * r.w * b.w);
+    dx[i] = o;
+    if (dres) dres[i] = g;
   }
 }
 
@@ -284,9 +326,11 @@ MMFN_API int mmfn_bn_train_fwd(const float* x, float* y, int64_t M, int C,
                                double* ws, cudaStream_t stream) {
   MMFN_CHECK_ARG(x && y && gamma && beta && mean && rstd && ws, "bn_fwd: null pointer");
   MMFN_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "bn_fwd: C must be a positive multiple of 4");
+  MMFN_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0, "bn_fwd: 16-byte alignment");
   cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, stream);
-  dim3 grid((C + 31) / 32, (unsigned)ceil_div64(M, BN_ROWS_PER_BLOCK));
-  bn_partial_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, M, C, ws);
+  int qpr; dim3 grid; int64_t rpb;
+  bn_colsum_grid(M, C, qpr, grid, rpb);
+  bn_colsum_kernel<false><<<grid, BN_THREADS, 0, stream>>>((const float4*)x, nullptr, nullptr, nullptr, nullptr, M, C / 4, qpr, rpb, ws);
   int64_t n4 = M * C / 4;
   bn_apply_kernel<<<grid_1d(n4, 256), 256, 2 * C * sizeof(float), stream>>>((const float4*)x, (float4*)y, n4, C / 4,
       mean, rstd, (const float4*)gamma, (const float4*)beta, (const float4*)res, relu,
@@ -301,11 +345,15 @@ MMFN_API int mmfn_bn_train_bwd(const float* dy, const float* x, const float* you
                                int64_t M, int C, float* dx, float* dres, float* dgamma, float* dbeta,
                                double* ws, cudaStream_t stream) {
   MMFN_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && ws, "bn_bwd: null pointer");
-  MMFN_CHECK_ARG(M > 0 && C > 0, "bn_bwd: bad sizes");
+  MMFN_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "bn_bwd: C must be a positive multiple of 4");
+  MMFN_CHECK_ARG((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)yout | (uintptr_t)dx | (uintptr_t)dres | (uintptr_t)mean | (uintptr_t)rstd) & 15) == 0,
+                 "bn_bwd: 16-byte alignment");
   cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, stream);
-  dim3 grid((C + 31) / 32, (unsigned)ceil_div64(M, BN_ROWS_PER_BLOCK));
-  bn_bwd_partial_kernel<<<grid, dim3(32, 8), 0, stream>>>(dy, x, yout, mean, rstd, M, C, ws);
-  bn_bwd_dx_kernel<<<grid_1d(M * C, 256), 256, 0, stream>>>(dy, x, yout, mean, rstd, gamma, ws, M, C, dx, dres, dgamma, dbeta);
+  int qpr; dim3 grid; int64_t rpb;
+  bn_colsum_grid(M, C, qpr, grid, rpb);
+  bn_colsum_kernel<true><<<grid, BN_THREADS, 0, stream>>>((const float4*)x, (const float4*)dy, (const float4*)yout, mean, rstd, M, C / 4, qpr, rpb, ws);
+  bn_bwd_dx_kernel<<<grid_1d(M * C / 4, 256), 256, 5 * C * sizeof(float), stream>>>(
+      (const float4*)dy, (const float4*)x, (const float4*)yout, mean, rstd, gamma, ws, M, C / 4, (float4*)dx, (float4*)dres, dgamma, dbeta);
   return mmfn_launch_status("bn_train_bwd");
 }
 

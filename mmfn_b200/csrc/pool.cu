@@ -64,28 +64,36 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restric
   }
 }
 
+// 4 channels per thread (C % 4 == 0): float4 gradients, the four argmax bytes as one 32-bit load
 __global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx,
                                    float* __restrict__ dx, int B, int H, int W, int C, int Ho, int Wo) {
-  int64_t n = (int64_t)B * H * W * C;
+  const int C4 = C >> 2;
+  int64_t n = (int64_t)B * H * W * C4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C);
-    int64_t t = i / C;
+    int c = (int)(i % C4) * 4;
+    int64_t t = i / C4;
     int w = (int)(t % W); t /= W;
     int h = (int)(t % H);
     int b = (int)(t / H);
-    float g = 0.f;
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
     int ho_lo = h / 2, ho_hi = (h + 1) / 2;     // windows ho with ho*2-1 <= h <= ho*2+1
     int wo_lo = w / 2, wo_hi = (w + 1) / 2;
     for (int ho = ho_lo; ho <= ho_hi; ++ho) {
       if (ho >= Ho) continue;
       for (int wo = wo_lo; wo <= wo_hi; ++wo) {
         if (wo >= Wo) continue;
-        int tap = (h - (ho * 2 - 1)) * 3 + (w - (wo * 2 - 1));
+        uint32_t tap = (uint32_t)((h - (ho * 2 - 1)) * 3 + (w - (wo * 2 - 1)));
         int64_t o = (((int64_t)b * Ho + ho) * Wo + wo) * C + c;
-        if (idx[o] == tap) g += __ldg(dy + o);
+        uint32_t am = __ldg(reinterpret_cast<const uint32_t*>(idx + o));
+        if (((am & 0xffu) != tap) && (((am >> 8) & 0xffu) != tap) && (((am >> 16) & 0xffu) != tap) && ((am >> 24) != tap)) continue;
+        float4 d = __ldg(reinterpret_cast<const float4*>(dy + o));
+        if ((am & 0xffu) == tap) g[0] += d.x;
+        if (((am >> 8) & 0xffu) == tap) g[1] += d.y;
+        if (((am >> 16) & 0xffu) == tap) g[2] += d.z;
+        if ((am >> 24) == tap) g[3] += d.w;
       }
     }
-    dx[i] = g;
+    *reinterpret_cast<float4*>(dx + (i << 2)) = make_float4(g[0], g[1], g[2], g[3]);
   }
 }
 
@@ -116,20 +124,29 @@ __global__ void tokens_fwd_kernel(FeatPtrs f, int nmod, int B, int H, int W, int
 }
 
 // dfeat_m[b,h,w,c] += dtok'[b, m*64 + (h/kh)*8 + w/kw, c] / (kh*kw)   (dtok' = dropout-masked dtok)
-__global__ void tokens_bwd_feat_kernel(FeatPtrsW df, int m, int B, int H, int W, int C, int T,
+// One launch for all modalities (blockIdx.y), 4 channels per thread.
+__global__ void tokens_bwd_feat_kernel(FeatPtrsW df, int B, int H, int W, int C, int T,
                                        const float* __restrict__ dtok, float drop_p, uint64_t seed) {
-  int kh = H / 8, kw = W / 8;
-  float inv = 1.0f / (float)(kh * kw);
-  int64_t n = (int64_t)B * H * W * C;
+  const int m = blockIdx.y;
   float* dst = df.p[m];
+  if (!dst) return;                              // modality without a gradient consumer
+  int kh = H / 8, kw = W / 8, C4 = C >> 2;
+  float inv = 1.0f / (float)(kh * kw);
+  int64_t n = (int64_t)B * H * W * C4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C);
-    int64_t t2 = i / C;
+    int c = (int)(i % C4) * 4;
+    int64_t t2 = i / C4;
     int w = (int)(t2 % W); t2 /= W;
     int h = (int)(t2 % H);
     int b = (int)(t2 / H);
     int64_t ti = ((int64_t)b * T + m * 64 + (h / kh) * 8 + (w / kw)) * C + c;
-    dst[i] += __ldg(dtok + ti) * mmfn_dropout_scale(drop_p, seed, (uint64_t)ti) * inv;
+    float4 g = __ldg(reinterpret_cast<const float4*>(dtok + ti));
+    float4 d = *reinterpret_cast<const float4*>(dst + (i << 2));
+    d.x += g.x * mmfn_dropout_scale(drop_p, seed, (uint64_t)ti) * inv;
+    d.y += g.y * mmfn_dropout_scale(drop_p, seed, (uint64_t)ti + 1) * inv;
+    d.z += g.z * mmfn_dropout_scale(drop_p, seed, (uint64_t)ti + 2) * inv;
+    d.w += g.w * mmfn_dropout_scale(drop_p, seed, (uint64_t)ti + 3) * inv;
+    *reinterpret_cast<float4*>(dst + (i << 2)) = d;
   }
 }
 
@@ -169,14 +186,15 @@ __device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, 
   l0 = 1.0f - l1;
 }
 
-// out = feat + bilinear_up(tok[:, m*64:(m+1)*64, :] as 8x8xC -> HxW)
+// out = feat + bilinear_up(tok[:, m*64:(m+1)*64, :] as 8x8xC -> HxW); 4 channels per thread
 __global__ void upsample_add_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ tok,
                                         float* __restrict__ out, int m, int T, int B, int H, int W, int C, int align) {
   float sh = bilinear_scale(8, H, align), sw = bilinear_scale(8, W, align);
-  int64_t n = (int64_t)B * H * W * C;
+  const int C4 = C >> 2;
+  int64_t n = (int64_t)B * H * W * C4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C);
-    int64_t t2 = i / C;
+    int c = (int)(i % C4) * 4;
+    int64_t t2 = i / C4;
     int w = (int)(t2 % W); t2 /= W;
     int h = (int)(t2 % H);
     int b = (int)(t2 / H);
@@ -184,9 +202,16 @@ __global__ void upsample_add_fwd_kernel(const float* __restrict__ feat, const fl
     bilinear_src(h, sh, 8, h0, h1, a0, a1, align);
     bilinear_src(w, sw, 8, w0, w1, b0, b1, align);
     const float* tb = tok + ((int64_t)b * T + m * 64) * C + c;
-    float v = a0 * (b0 * __ldg(tb + (h0 * 8 + w0) * C) + b1 * __ldg(tb + (h0 * 8 + w1) * C)) +
-              a1 * (b0 * __ldg(tb + (h1 * 8 + w0) * C) + b1 * __ldg(tb + (h1 * 8 + w1) * C));
-    out[i] = __ldg(feat + i) + v;
+    const float4 t00 = __ldg(reinterpret_cast<const float4*>(tb + (h0 * 8 + w0) * C));
+    const float4 t01 = __ldg(reinterpret_cast<const float4*>(tb + (h0 * 8 + w1) * C));
+    const float4 t10 = __ldg(reinterpret_cast<const float4*>(tb + (h1 * 8 + w0) * C));
+    const float4 t11 = __ldg(reinterpret_cast<const float4*>(tb + (h1 * 8 + w1) * C));
+    float4 f = __ldg(reinterpret_cast<const float4*>(feat + (i << 2)));
+    f.x += a0 * (b0 * t00.x + b1 * t01.x) + a1 * (b0 * t10.x + b1 * t11.x);
+    f.y += a0 * (b0 * t00.y + b1 * t01.y) + a1 * (b0 * t10.y + b1 * t11.y);
+    f.z += a0 * (b0 * t00.z + b1 * t01.z) + a1 * (b0 * t10.z + b1 * t11.z);
+    f.w += a0 * (b0 * t00.w + b1 * t01.w) + a1 * (b0 * t10.w + b1 * t11.w);
+    *reinterpret_cast<float4*>(out + (i << 2)) = f;
   }
 }
 
@@ -297,9 +322,10 @@ MMFN_API int mmfn_maxpool3x3s2_fwd(const float* x, float* y, uint8_t* idx, int B
 
 MMFN_API int mmfn_maxpool3x3s2_bwd(const float* dy, const uint8_t* idx, float* dx, int B, int H, int W, int C,
                                    cudaStream_t stream) {
-  MMFN_CHECK_ARG(dy && dx && idx && B > 0 && H > 0 && W > 0 && C > 0, "maxpool_bwd: bad args");
+  MMFN_CHECK_ARG(dy && dx && idx && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "maxpool_bwd: bad args (C % 4 == 0)");
+  MMFN_CHECK_ARG((((uintptr_t)dy | (uintptr_t)dx) & 15) == 0 && ((uintptr_t)idx & 3) == 0, "maxpool_bwd: alignment");
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  maxpool_bwd_kernel<<<grid_1d((int64_t)B * H * W * C, 256), 256, 0, stream>>>(dy, idx, dx, B, H, W, C, Ho, Wo);
+  maxpool_bwd_kernel<<<grid_1d((int64_t)B * H * W * (C / 4), 256), 256, 0, stream>>>(dy, idx, dx, B, H, W, C, Ho, Wo);
   return mmfn_launch_status("maxpool_bwd");
 }
 
@@ -327,9 +353,12 @@ MMFN_API int mmfn_tokens_bwd(const float* dtokens, float* df0, float* df1, float
   MMFN_CHECK_ARG(B > 0 && C > 0 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0, "tokens_bwd: H,W must be multiples of 8");
   FeatPtrsW df{{df0, df1, df2, df3}};
   int T = nmod * 64;
-  for (int m = 0; m < nmod; ++m) {
-    if (!df.p[m]) continue;   // modality without a gradient consumer
-    tokens_bwd_feat_kernel<<<grid_1d((int64_t)B * H * W * C, 256), 256, 0, stream>>>(df, m, B, H, W, C, T, dtokens, drop_p, seed);
+  MMFN_CHECK_ARG(C % 4 == 0 && (((uintptr_t)dtokens | (uintptr_t)df0 | (uintptr_t)df1 | (uintptr_t)df2 | (uintptr_t)df3) & 15) == 0,
+                 "tokens_bwd: C % 4 == 0 and 16-byte aligned buffers");
+  {
+    int gx = grid_1d((int64_t)B * H * W * (C / 4), 256);
+    if (gx > 148 * 4) gx = 148 * 4;
+    tokens_bwd_feat_kernel<<<dim3(gx, nmod), 256, 0, stream>>>(df, B, H, W, C, T, dtokens, drop_p, seed);
   }
   tokens_bwd_param_kernel<<<grid_1d((int64_t)T * C, 128), 128, 0, stream>>>(dtokens, velocity, B, T, C, dpos_emb, dvel_w, dvel_b, drop_p, seed);
   return mmfn_launch_status("tokens_bwd");
@@ -338,7 +367,8 @@ MMFN_API int mmfn_tokens_bwd(const float* dtokens, float* df0, float* df1, float
 MMFN_API int mmfn_upsample_add_fwd(const float* feat, const float* tokens, float* out, int m, int T,
                                    int B, int H, int W, int C, int align_corners, cudaStream_t stream) {
   MMFN_CHECK_ARG(feat && tokens && out && B > 0 && H >= 8 && W >= 8 && C > 0 && m >= 0 && (m + 1) * 64 <= T, "upsample_add_fwd: bad args");
-  upsample_add_fwd_kernel<<<grid_1d((int64_t)B * H * W * C, 256), 256, 0, stream>>>(feat, tokens, out, m, T, B, H, W, C, align_corners);
+  MMFN_CHECK_ARG(C % 4 == 0 && (((uintptr_t)feat | (uintptr_t)tokens | (uintptr_t)out) & 15) == 0, "upsample_add_fwd: C % 4 == 0, 16-byte aligned");
+  upsample_add_fwd_kernel<<<grid_1d((int64_t)B * H * W * (C / 4), 256), 256, 0, stream>>>(feat, tokens, out, m, T, B, H, W, C, align_corners);
   return mmfn_launch_status("upsample_add_fwd");
 }
 

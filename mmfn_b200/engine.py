@@ -18,7 +18,7 @@ from ._lib import lib
 _FIELDS = (
     ("rgb_u8", torch.uint8), ("points", torch.float32), ("lane", torch.float32), ("lane_num", torch.int32),
     ("radar", torch.float32), ("radar_adj", torch.float32), ("velocity", torch.float32),
-    ("target_point", torch.float32), ("gt_waypoints", torch.float32), ("lidar", torch.float32),
+    ("target_point", torch.float32), ("gt_waypoints", torch.float32), ("lidar", torch.float32), ("map_u8", torch.uint8),
 )
 
 
@@ -91,7 +91,8 @@ class TrainEngine:
         lidar = b["lidar"] if "lidar" in b else ops.bev_scatter(b["points"])
         image = b["rgb_u8"] if "rgb_u8" in b else b["image"]
         # the RGB+LiDAR-only variant (transfuser.TransFuser) has no lane / radar inputs
-        pred = self.net.forward(image, lidar, b.get("lane"), b.get("lane_num"), b.get("radar"), b.get("radar_adj"),
+        lane = b["map_u8"] if model.VARIANT == "img" else b.get("lane")     # model_img: rasterised map image
+        pred = self.net.forward(image, lidar, lane, b.get("lane_num"), b.get("radar"), b.get("radar_adj"),
                                 b["target_point"], b["velocity"], model.seed, True)
         loss, dpred = ops.l1_loss(pred, b["gt_waypoints"])
         self.net.backward(dpred)

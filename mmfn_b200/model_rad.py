@@ -485,19 +485,28 @@ class Head:
 
 # --------------------------------------------------------------------------- the network
 class _Net:
-    """Kernel schedule of Encoder.forward (model_rad.py:492-611) + head, forward and backward."""
+    """Kernel schedule of Encoder.forward (model_rad.py:492-611) + head, forward and backward.
+    VARIANT "rad": camera + LiDAR + VectorNet map + radar GAT (model_rad.py);  "vec": the same without the radar
+    branch (model_vec.py:488-600);  "img": the map is a rasterised image run through the map ResNet's own stem and
+    layer1 instead of VectorNet, no radar (model_img.py:310-423)."""
+    VARIANT = "rad"
 
     def __init__(self, st, cfg):
         e = "encoder."
         self.cfg = cfg
+        var = self.VARIANT
         ip, mp, lp = e + "image_encoder.features", e + "img_map_encoder.features", e + "lidar_encoder._model"
         self.img_stem, self.lid_stem = Stem(st, ip), Stem(st, lp)
         self.img_layers = [ResLayer(st, f"{ip}.layer{i + 1}", RESNET34[i], 1 if i == 0 else 2) for i in range(4)]
         self.lid_layers = [ResLayer(st, f"{lp}.layer{i + 1}", RESNET18[i], 1 if i == 0 else 2) for i in range(4)]
         self.map_layers = [None] + [ResLayer(st, f"{mp}.layer{i + 1}", RESNET34[i], 2) for i in range(1, 4)]
-        self.vectornet = VectorNet(st, e + "vectornet_encoder")
-        self.gat = SpGAT(st, e + "radar_encoder", cfg)
-        self.gpts = [FusionGPT(st, f"{e}transformer{i + 1}", WIDTHS[i], 3 if i < 3 else 4, cfg, i) for i in range(4)]
+        self.map_stem = None
+        if var == "img":
+            self.map_stem = Stem(st, mp)
+            self.map_layers[0] = ResLayer(st, f"{mp}.layer1", RESNET34[0], 1)
+        self.vectornet = VectorNet(st, e + "vectornet_encoder") if var != "img" else None
+        self.gat = SpGAT(st, e + "radar_encoder", cfg) if var == "rad" else None
+        self.gpts = [FusionGPT(st, f"{e}transformer{i + 1}", WIDTHS[i], 3 if (i < 3 or var != "rad") else 4, cfg, i) for i in range(4)]
         self.head = Head(st, cfg.pred_len)
         dev = st.device
         self.side = [torch.cuda.Stream(device=dev) for _ in range(3)]
@@ -538,25 +547,33 @@ class _Net:
         return out
 
     def forward(self, image, lidar, lane, lane_num, radar, radar_adj, target_point, velocity, seed, train):
-        img, lid, mp, rad = self._parallel(
+        """`lane` is the padded lane tensor (rad / vec) or the rasterised map image (B,3,256,256) (img)."""
+        branches = [
             lambda: self.img_layers[0].fwd(self.img_stem.fwd(ops.nchw_to_nhwc(image, self.mean, self.std), train), train),
-            lambda: self.lid_layers[0].fwd(self.lid_stem.fwd(ops.nchw_to_nhwc(lidar), train), train),
-            lambda: self.vectornet.fwd(lane, lane_num),
-            lambda: self.gat.fwd(radar, radar_adj, seed + 900, train))
+            lambda: self.lid_layers[0].fwd(self.lid_stem.fwd(ops.nchw_to_nhwc(lidar), train), train)]
+        if self.map_stem is not None:          # model_img.py:337-340, :348 -- the map image is NOT ImageNet-normalised
+            branches.append(lambda: self.map_layers[0].fwd(self.map_stem.fwd(ops.nchw_to_nhwc(lane), train), train))
+        else:
+            branches.append(lambda: self.vectornet.fwd(lane, lane_num))
+        if self.gat is not None:
+            branches.append(lambda: self.gat.fwd(radar, radar_adj, seed + 900, train))
+        out = self._parallel(*branches)
+        img, lid, mp = out[:3]
         for s in range(3):
             tok = self.gpts[s].fwd([img, lid, mp], velocity, seed, train)
             img, lid, mp = self._parallel(
                 lambda: self.img_layers[s + 1].fwd(ops.upsample_add_fwd(img, tok, 0), train),
                 lambda: self.lid_layers[s + 1].fwd(ops.upsample_add_fwd(lid, tok, 1), train),
                 lambda: self.map_layers[s + 1].fwd(ops.upsample_add_fwd(mp, tok, 2), train))
-        feats = [img, lid, mp, rad]
+        feats = [img, lid, mp] + ([out[3]] if self.gat is not None else [])
         tok = self.gpts[3].fwd(feats, velocity, seed, train)
         fused = ops.pool_sum_fwd(feats, tok)
         return self.head.fwd(fused, target_point)
 
     def backward(self, dpred):
         dfused = self.head.bwd(dpred)
-        dfe, dtok = ops.pool_sum_bwd(dfused, 4)
+        nmod = 4 if self.gat is not None else 3
+        dfe, dtok = ops.pool_sum_bwd(dfused, nmod)
         self.gpts[3].bwd(dtok, dfe)
         dimg, dlid, dmp = dfe[0], dfe[1], dfe[2]
         for s in (2, 1, 0):
@@ -570,14 +587,23 @@ class _Net:
                     return g
                 return run
             branches = [trunk(self.img_layers, dimg, 0), trunk(self.lid_layers, dlid, 1), trunk(self.map_layers, dmp, 2)]
-            if s == 2:
+            if s == 2 and self.gat is not None:
                 branches.append(lambda: self.gat.bwd(dfe[3]))  # same side stream as its forward
             dimg, dlid, dmp = self._parallel(*branches)[:3]
             self.gpts[s].bwd(dtok, [dimg, dlid, dmp])
         self._parallel(lambda: self.img_stem.bwd(self.img_layers[0].bwd(dimg)),
                        lambda: self.lid_stem.bwd(self.lid_layers[0].bwd(dlid)),
-                       lambda: self.vectornet.bwd(dmp))
+                       (lambda: self.map_stem.bwd(self.map_layers[0].bwd(dmp))) if self.map_stem is not None
+                       else (lambda: self.vectornet.bwd(dmp)))
         _Aux.join_all()
+
+
+class _NetVec(_Net):
+    VARIANT = "vec"
+
+
+class _NetImg(_Net):
+    VARIANT = "img"
 
 
 class _WholeNet(torch.autograd.Function):
@@ -596,7 +622,7 @@ class _WholeNet(torch.autograd.Function):
         m.net.backward(dpred.contiguous())
         grads = []
         for k, p in m._param_items:
-            grads.append(None if is_unused(k) else m.store.torch_view(k, grad=True).clone())
+            grads.append(None if is_unused(k, m.VARIANT) else m.store.torch_view(k, grad=True).clone())
         return (None, None, *grads)
 
 
@@ -676,9 +702,14 @@ class MMFN(nn.Module):
 
     # ---- reference surface -----------------------------------------------------------------------
     def forward(self, image_list, lidar_list, map_list, vectormaps_list, radar_list, radar_adj, target_point, velocity):
-        lane = vectormaps_list[0][0]
-        lane_num = vectormaps_list[1][0]
-        inputs = (image_list[0], lidar_list[0], lane, lane_num, radar_list[0], radar_adj[0], target_point, velocity)
+        """Reference signature (model_rad.py:666, identical in model_vec.py:653 and model_img.py).  Inputs a variant
+        does not consume (maps_list for rad / vec, vectormaps for img, radar for vec / img) are ignored and may be None."""
+        if self.VARIANT == "img":
+            lane, lane_num = map_list[0], None
+        else:
+            lane, lane_num = vectormaps_list[0][0], vectormaps_list[1][0]
+        radar, adj = (radar_list[0], radar_adj[0]) if self.VARIANT == "rad" else (None, None)
+        inputs = (image_list[0], lidar_list[0], lane, lane_num, radar, adj, target_point, velocity)
         if torch.is_grad_enabled() and self.training:
             return _WholeNet.apply(self, inputs, *[p for _, p in self._param_items])
         with torch.no_grad():
@@ -690,9 +721,11 @@ class MMFN(nn.Module):
             image = image.to(self.device).contiguous()
         else:
             image = f32(image)
-        lidar, lane, radar, radar_adj, target_point, velocity = map(
-            f32, (lidar, lane, radar, radar_adj, target_point, velocity))
-        lane_num = lane_num.to(device=self.device, dtype=torch.int32).contiguous()
+        lidar, lane, target_point, velocity = map(f32, (lidar, lane, target_point, velocity))
+        if radar is not None:
+            radar, radar_adj = f32(radar), f32(radar_adj)
+        if lane_num is not None:
+            lane_num = lane_num.to(device=self.device, dtype=torch.int32).contiguous()
         if self.training:
             self.seed += 1000
             self.store.flat_nbt.add_(self._nbt_step())     # BatchNorm.num_batches_tracked
@@ -702,7 +735,7 @@ class MMFN(nn.Module):
     def _nbt_step(self):
         """+1 for every BatchNorm that runs; the map ResNet's stem/layer1 BNs never do (stay 0)."""
         if not hasattr(self, "_nbt_inc"):
-            inc = [0 if is_unused(k) else 1 for k in self.store.nbt_index]
+            inc = [0 if is_unused(k, self.VARIANT) else 1 for k in self.store.nbt_index]
             self._nbt_inc = torch.tensor(inc, device=self.device, dtype=torch.int64)
         return self._nbt_inc
 
@@ -730,6 +763,19 @@ class MMFN(nn.Module):
             "aim": tuple(aim.astype(np.float64)), "delta": float(delta.astype(np.float64)),
         }
         return steer, throttle, brake, metadata
+
+
+class MMFNVec(MMFN):
+    """Drop-in for team_code/mmfn_utils/models/model_vec.py:MMFN (camera + LiDAR + VectorNet map, no radar)."""
+    VARIANT = "vec"
+    NET = _NetVec
+
+
+class MMFNImg(MMFN):
+    """Drop-in for team_code/mmfn_utils/models/model_img.py:MMFN -- the DEFAULT train.yaml entry point
+    (run_steps/config/train.yaml:13): camera + LiDAR + rasterised map image."""
+    VARIANT = "img"
+    NET = _NetImg
 
 
 def _is_ln_bias(k):

@@ -84,37 +84,47 @@ def transfuser_param_spec(cfg):
 
 
 def param_spec(cfg, variant="rad"):
-    """[(key, shape, kind)] in reference state_dict order. kind: conv | f | buf | nbt."""
+    """[(key, shape, kind)] in reference state_dict order. kind: conv | f | buf | nbt.
+    variant: "rad" (model_rad.py: camera + LiDAR + VectorNet map + radar GAT), "vec" (model_vec.py: no radar),
+    "img" (model_img.py: rasterised map image through the map ResNet, no VectorNet, no radar),
+    "transfuser" (benchmarks/transfuser/model.py: camera + LiDAR only)."""
     if variant == "transfuser":
         return transfuser_param_spec(cfg)
+    assert variant in ("rad", "vec", "img"), variant
     e = "encoder."
     spec = _resnet(e + "image_encoder.features", RESNET34, 3)
     spec += _resnet(e + "img_map_encoder.features", RESNET34, 3)
     spec += _resnet(e + "lidar_encoder._model", RESNET18, 2)
-    v = e + "vectornet_encoder"
-    cin = 7
-    for i in range(3):
-        spec += _linear(f"{v}.lane_subgraph.layers.mlp_{i}.mlp.0", 64, cin) + _ln(f"{v}.lane_subgraph.layers.mlp_{i}.mlp.1", 64)
-        cin = 128
-    spec += _linear(v + ".pos_emb.0", 64, 2) + _ln(v + ".pos_emb.1", 64) + _linear(v + ".pos_emb.3", 64, 64)
-    spec += _linear(v + ".L2L.to_qkv", 384, 128, bias=False) + _linear(v + ".L2L.to_out.0", 128, 128)
-    spec += _linear(v + ".agent_fusion.0", 128, 192) + _ln(v + ".agent_fusion.1", 128) + _linear(v + ".agent_fusion.3", 128, 128)
-    spec += _linear(v + ".generator.0", 64, 128) + _ln(v + ".generator.1", 64) + _linear(v + ".generator.3", 64 * 64 * 64, 64)
-    r = e + "radar_encoder"
-    nh, hid = cfg.nb_heads, cfg.hidden
-    for i in range(nh):
-        spec += [(f"{r}.attention_{i}.W", (5, 2 * hid), "f"), (f"{r}.attention_{i}.a", (2 * hid, hid), "f")]
-    spec += _linear(r + ".mlp_1.0", 256, nh * hid) + _linear(r + ".mlp_2.0", 128, nh * hid)
+    if variant != "img":
+        v = e + "vectornet_encoder"
+        cin = 7
+        for i in range(3):
+            spec += _linear(f"{v}.lane_subgraph.layers.mlp_{i}.mlp.0", 64, cin) + _ln(f"{v}.lane_subgraph.layers.mlp_{i}.mlp.1", 64)
+            cin = 128
+        spec += _linear(v + ".pos_emb.0", 64, 2) + _ln(v + ".pos_emb.1", 64) + _linear(v + ".pos_emb.3", 64, 64)
+        spec += _linear(v + ".L2L.to_qkv", 384, 128, bias=False) + _linear(v + ".L2L.to_out.0", 128, 128)
+        spec += _linear(v + ".agent_fusion.0", 128, 192) + _ln(v + ".agent_fusion.1", 128) + _linear(v + ".agent_fusion.3", 128, 128)
+        spec += _linear(v + ".generator.0", 64, 128) + _ln(v + ".generator.1", 64) + _linear(v + ".generator.3", 64 * 64 * 64, 64)
+    if variant == "rad":
+        r = e + "radar_encoder"
+        nh, hid = cfg.nb_heads, cfg.hidden
+        for i in range(nh):
+            spec += [(f"{r}.attention_{i}.W", (5, 2 * hid), "f"), (f"{r}.attention_{i}.a", (2 * hid, hid), "f")]
+        spec += _linear(r + ".mlp_1.0", 256, nh * hid) + _linear(r + ".mlp_2.0", 128, nh * hid)
     ntok = (cfg.n_views + 2) * cfg.seq_len * cfg.vert_anchors * cfg.horz_anchors
     for i, c in enumerate((64, 128, 256), start=1):
         spec += _gpt(f"{e}transformer{i}", c, ntok, cfg.n_layer, cfg.block_exp)
-    spec += _gpt(e + "transformer4", 512, ntok + cfg.seq_len * cfg.vert_anchors * cfg.horz_anchors, cfg.n_layer, cfg.block_exp)
+    ntok4 = ntok + (cfg.seq_len * cfg.vert_anchors * cfg.horz_anchors if variant == "rad" else 0)
+    spec += _gpt(e + "transformer4", 512, ntok4, cfg.n_layer, cfg.block_exp)
     return spec + _head_spec()
 
 
-def is_unused(key):
-    """Parameters of the map ResNet that model_rad never touches (stem + layer1): they get no
-    gradient in the reference, so torch.optim skips them entirely (no weight decay either)."""
+def is_unused(key, variant="rad"):
+    """Parameters of the map ResNet that model_rad / model_vec never touch (stem + layer1; the VectorNet output
+    enters at layer2): they get no gradient in the reference, so torch.optim skips them entirely (no weight decay
+    either).  model_img runs the whole map ResNet; the TransFuser variant has none."""
+    if variant in ("img", "transfuser"):
+        return False
     p = "encoder.img_map_encoder.features."
     return key.startswith(p) and (key[len(p):].startswith(("conv1.", "bn1.", "layer1.")))
 
@@ -129,6 +139,7 @@ def _numel(shape):
 class ParamStore:
     def __init__(self, cfg, device, variant="rad"):
         self.spec = param_spec(cfg, variant)
+        self.variant = variant
         self.device = torch.device(device)
         fkeys = [(k, s) for k, s, kind in self.spec if kind in ("conv", "f")]
         order = self._flat_order([k for k, _ in fkeys])
@@ -139,7 +150,7 @@ class ParamStore:
             if pass_unused:
                 self.n_active = off
             for k in order:
-                if is_unused(k) != pass_unused:
+                if is_unused(k, variant) != pass_unused:
                     continue
                 self.offsets[k] = off
                 off += (_numel(shapes[k]) + 3) // 4 * 4

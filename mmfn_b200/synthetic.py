@@ -115,6 +115,16 @@ def synth_batch(batch_size, first_index=0, n_lanes=128, n_nodes=10, n_points=N_P
     )
 
 
+def synth_map_images(batch_size, first_index=0):
+    """(B,3,256,256) uint8 rasterised-map crops for the model_img variant (dataloader.py:214-216 stores the
+    `maps` image next to `fronts`): a second seeded image per frame."""
+    out = []
+    for i in range(batch_size):
+        rng = np.random.default_rng(777000 + first_index + i)
+        out.append(center_crop_chw(rng.integers(0, 256, size=(300, 400, 3), dtype=np.uint8)))
+    return torch.from_numpy(np.stack(out))
+
+
 def fill_golden_weights(state_dict, seed=42):
     """Deterministic, key-addressed weights (independent of construction order) so the reference
     module, the oracle and the CUDA module can be loaded with bit-identical parameters."""

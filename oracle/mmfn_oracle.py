@@ -146,7 +146,10 @@ def spgat(radar, adj, p, alpha, nheads):
     return F.log_softmax(x, dim=1)
 
 
-def encoder(sd, cfg, image, lidar, lane, lane_num, radar, radar_adj, velocity, train=True, taps=None):
+def encoder(sd, cfg, image, lidar, lane, lane_num, radar, radar_adj, velocity, train=True, taps=None, variant="rad"):
+    """variant "rad": model_rad.py:492-611; "vec": model_vec.py:488-600 (no radar branch, transformer4 is a plain
+    3-modality GPT); "img": model_img.py:310-423 (`lane` is the rasterised map image (B,3,256,256), fed
+    un-normalised through the map ResNet's stem and layer1; no VectorNet, no radar)."""
     p = Params(sd, "encoder.")
     mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
     std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
@@ -155,7 +158,10 @@ def encoder(sd, cfg, image, lidar, lane, lane_num, radar, radar_adj, velocity, t
     lid = _stem(lidar, lid_p, train)
     img = _res_layer(img, img_p.sub("layer1"), 3, 1, train)
     lid = _res_layer(lid, lid_p.sub("layer1"), 2, 1, train)
-    mp = vectornet(lane, lane_num, p.sub("vectornet_encoder"))
+    if variant == "img":
+        mp = _res_layer(_stem(lane, map_p, train), map_p.sub("layer1"), 3, 1, train)
+    else:
+        mp = vectornet(lane, lane_num, p.sub("vectornet_encoder"))
     if taps is not None:
         taps.update(img_l1=img, lid_l1=lid, map_gen=mp)
     pool = lambda t: F.adaptive_avg_pool2d(t, (8, 8))
@@ -169,6 +175,9 @@ def encoder(sd, cfg, image, lidar, lane, lane_num, radar, radar_adj, velocity, t
         img = _res_layer(img, img_p.sub(f"layer{s + 1}"), blocks["img"][s - 1], 2, train)
         mp = _res_layer(mp, map_p.sub(f"layer{s + 1}"), blocks["img"][s - 1], 2, train)
         lid = _res_layer(lid, lid_p.sub(f"layer{s + 1}"), blocks["lid"][s - 1], 2, train)
+    if variant != "rad":
+        outs = _gpt([pool(img), pool(lid), pool(mp)], velocity, p.sub("transformer4"), cfg)
+        return sum((f + o).mean(dim=(2, 3)) for f, o in zip((img, lid, mp), outs))
     rad = spgat(radar, radar_adj, p.sub("radar_encoder"), cfg.alpha, cfg.nb_heads)
     outs = _gpt([pool(img), pool(lid), pool(mp), rad], velocity, p.sub("transformer4"), cfg)
     feats = [img + outs[0], lid + outs[1], mp + outs[2], rad + outs[3]]
@@ -177,9 +186,10 @@ def encoder(sd, cfg, image, lidar, lane, lane_num, radar, radar_adj, velocity, t
     return sum(f.mean(dim=(2, 3)) for f in feats)
 
 
-def forward(sd, cfg, image, lidar, lane, lane_num, radar, radar_adj, target_point, velocity, train=True, taps=None):
+def forward(sd, cfg, image, lidar, lane, lane_num, radar, radar_adj, target_point, velocity, train=True, taps=None,
+            variant="rad"):
     """-> pred_wp (B, pred_len, 2).  image (B,3,256,256) 0..255, lidar (B,2,256,256)."""
-    fused = encoder(sd, cfg, image, lidar, lane, lane_num, radar, radar_adj, velocity, train, taps)
+    fused = encoder(sd, cfg, image, lidar, lane, lane_num, radar, radar_adj, velocity, train, taps, variant)
     return head(sd, cfg, fused, target_point)
 
 

@@ -114,3 +114,39 @@ def test_transfuser_oracle_matches_reference_goldens(golden_dir):
     for k in gold.files:
         if k.startswith("buf/"):
             assert np.allclose(probe(sd[k[4:]], 4), gold[k], rtol=1e-4, atol=1e-5), k
+
+
+def _variant_batch(variant, B=2):
+    b = synthetic.synth_batch(B)
+    lidar = torch.from_numpy(np.stack([bev_oracle.lidar_to_histogram_features(p[:, :3].numpy()) for p in b["points"]]))
+    lane = synthetic.synth_map_images(B).float() if variant == "img" else b["lane"]
+    inputs = (b["rgb_u8"].float(), lidar, lane, b["lane_num"], b["radar"], b["radar_adj"], b["target_point"], b["velocity"])
+    return dict(inputs=inputs, gt_waypoints=b["gt_waypoints"])
+
+
+def test_vec_and_img_variant_oracles_match_reference_goldens(golden_dir):
+    """model_vec.MMFN (no radar) and model_img.MMFN (rasterised map image, default train.yaml entry point)."""
+    import functools
+    from mmfn_b200.params import param_spec
+    cfg = GlobalConfig(embd_pdrop=0.0, attn_pdrop=0.0, resid_pdrop=0.0)
+    for variant, n_unused in (("vec", 21), ("img", 0)):
+        gold = np.load(os.path.join(golden_dir, f"{variant}_golden_b2.npz"))
+        keys = json.load(open(os.path.join(golden_dir, f"{variant}_state_dict_keys.json")))
+        spec = param_spec(cfg, variant)
+        assert [k for k, _, _ in spec] == list(keys.keys()), variant
+        assert all(list(shape) == keys[k][0] for k, shape, _ in spec), variant
+        shapes = {k: torch.empty(v[0], dtype=getattr(torch, v[1].split(".")[1])) for k, v in keys.items()}
+        sd = synthetic.fill_golden_weights(shapes, 42)
+        fwd = functools.partial(mmfn_oracle.forward, variant=variant)
+        loss, pred, grads = mmfn_oracle.train_step(sd, cfg, _variant_batch(variant), forward_fn=fwd)
+        assert abs(loss.item() - float(gold["loss"])) < 1e-5, variant
+        assert np.abs(pred.numpy() - gold["pred_wp"]).max() < 2e-5, variant
+        unused = set(gold["unused"].tolist())
+        assert {k for k, g in grads.items() if g is None} == unused and len(unused) == n_unused, variant
+        worst = 0.0
+        for k, g in grads.items():
+            if g is None:
+                continue
+            ref, got = gold["grad/" + k], probe(g, 6)
+            worst = max(worst, np.abs(np.delete(got - ref, 1)).max() / max(abs(ref[0]), 1e-6))
+        assert worst < 5e-3, (variant, worst)

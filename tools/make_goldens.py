@@ -133,6 +133,37 @@ def collate():
                         fronts_sum=np.int64(out["fronts"][0].long().sum()), lidars_sum=np.float64(out["lidars"][0].double().sum()))
 
 
+def variants(B=2):
+    """model_vec.MMFN (no radar) and model_img.MMFN (rasterised map image; the default train.yaml entry point)."""
+    from mmfn_utils.models import model_img, model_vec
+    b = synthetic.synth_batch(B)
+    lidar = torch.from_numpy(np.stack([lidar_to_histogram_features(p[:, :3].numpy()) for p in b["points"]]))
+    vectormaps = [[b["lane"]], [b["lane_num"].float()], b["lane"].shape[1]]
+    maps = [synthetic.synth_map_images(B).float()]
+    for name, mod in (("vec", model_vec), ("img", model_img)):
+        torch.manual_seed(0)
+        cfg = GlobalConfig(embd_pdrop=0.0, attn_pdrop=0.0, resid_pdrop=0.0)
+        net = mod.MMFN(cfg, "cpu")
+        sd = net.state_dict()
+        json.dump({k: [list(v.shape), str(v.dtype)] for k, v in sd.items()},
+                  open(os.path.join(GOLD, f"{name}_state_dict_keys.json"), "w"), indent=0)
+        net.load_state_dict(synthetic.fill_golden_weights(sd, 42))
+        net.train()
+        pred = net([b["rgb_u8"].float()], [lidar], maps, vectormaps, [b["radar"]], [b["radar_adj"]], b["target_point"], b["velocity"])
+        loss = torch.nn.functional.l1_loss(pred, b["gt_waypoints"], reduction="none").mean()
+        loss.backward()
+        out = {"pred_wp": pred.detach().numpy(), "loss": np.float64(loss.item())}
+        unused = []
+        for k, p in net.named_parameters():
+            if p.grad is None:
+                unused.append(k)
+            else:
+                out["grad/" + k] = probe(p.grad, 6)
+        out["unused"] = np.array(unused)
+        np.savez_compressed(os.path.join(GOLD, f"{name}_golden_b{B}.npz"), **out)
+        print(name, "loss", loss.item(), "unused params", len(unused))
+
+
 def transfuser(B=2):
     """benchmarks/transfuser/model.py:TransFuser (RGB + LiDAR only, BASELINE configs[3]) on synth_batch(2)."""
     from benchmarks.transfuser import model as tf_model
@@ -167,7 +198,11 @@ if __name__ == "__main__":
     if "--transfuser-only" in sys.argv:
         transfuser(2)
         sys.exit(0)
+    if "--variants-only" in sys.argv:
+        variants(2)
+        sys.exit(0)
     bev()
     collate()
     model(2)
     transfuser(2)
+    variants(2)
