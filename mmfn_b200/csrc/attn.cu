@@ -69,6 +69,45 @@ __global__ void softmax_bwd_kernel(const float* __restrict__ p, const float* __r
   }
 }
 
+// float4 variant (cols % 4 == 0, cols <= 128 * J4): lane handles 4 consecutive keys per step, one dropout hash per vector
+template <int J4>
+__global__ void softmax_bwd_v4_kernel(const float4* __restrict__ p, const float4* __restrict__ dpd, float4* __restrict__ ds,
+                                      int64_t rows, int cols4, float scale, float drop_p, uint64_t seed) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 pv[J4], g[J4];
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < J4; ++j) {
+    const int c = lane + 32 * j;
+    pv[j] = make_float4(0.f, 0.f, 0.f, 0.f); g[j] = pv[j];
+    if (c < cols4) {
+      const int64_t i = row * cols4 + c;
+      pv[j] = __ldg(p + i);
+      g[j] = __ldg(dpd + i);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < J4; ++j) {
+    const int c = lane + 32 * j;
+    if (c < cols4) {
+      float dsc[4];
+      mmfn_dropout_scale4(drop_p, seed, (uint64_t)(row * cols4 + c) << 2, dsc);
+      g[j].x *= dsc[0]; g[j].y *= dsc[1]; g[j].z *= dsc[2]; g[j].w *= dsc[3];
+      dot += pv[j].x * g[j].x + pv[j].y * g[j].y + pv[j].z * g[j].z + pv[j].w * g[j].w;
+    }
+  }
+  dot = warp_sum(dot);
+#pragma unroll
+  for (int j = 0; j < J4; ++j) {
+    const int c = lane + 32 * j;
+    if (c < cols4)
+      ds[row * cols4 + c] = make_float4(scale * pv[j].x * (g[j].x - dot), scale * pv[j].y * (g[j].y - dot),
+                                        scale * pv[j].z * (g[j].z - dot), scale * pv[j].w * (g[j].w - dot));
+  }
+}
+
 // GAT: att = softmax(where(adj > 0, leakyrelu(z), -9e15)); one warp per row, cols <= 128
 __global__ void gat_softmax_fwd_kernel(const float* __restrict__ z, const float* __restrict__ adj,
                                        float* __restrict__ att, float* __restrict__ attd,
@@ -249,7 +288,9 @@ MMFN_API int mmfn_softmax_bwd(const float* p, const float* dpd, float* ds, int64
   MMFN_CHECK_ARG(p && dpd && ds && rows >= 0 && cols > 0 && cols <= 1024, "softmax_bwd: bad args (cols <= 1024)");
   if (rows == 0) return 0;
   unsigned grid = (unsigned)ceil_div64(rows, 8);
-  if (cols <= 192) softmax_bwd_kernel<6><<<grid, 256, 0, stream>>>(p, dpd, ds, rows, cols, scale, drop_p, seed);
+  if (cols % 4 == 0 && cols <= 256 && (((uintptr_t)p | (uintptr_t)dpd | (uintptr_t)ds) & 15) == 0)
+    softmax_bwd_v4_kernel<2><<<grid, 256, 0, stream>>>((const float4*)p, (const float4*)dpd, (float4*)ds, rows, cols / 4, scale, drop_p, seed);
+  else if (cols <= 192) softmax_bwd_kernel<6><<<grid, 256, 0, stream>>>(p, dpd, ds, rows, cols, scale, drop_p, seed);
   else if (cols <= 256) softmax_bwd_kernel<8><<<grid, 256, 0, stream>>>(p, dpd, ds, rows, cols, scale, drop_p, seed);
   else softmax_bwd_kernel<32><<<grid, 256, 0, stream>>>(p, dpd, ds, rows, cols, scale, drop_p, seed);
   return mmfn_launch_status("softmax_bwd");

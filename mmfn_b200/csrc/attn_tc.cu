@@ -168,7 +168,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (drop) {
         sts_swizzled_row(p_tile, row, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] *= mmfn_dropout_scale(p.drop_p, p.seed, (uint64_t)(prow + jb * 32 + j));
+        for (int j = 0; j < 32; j += 4) {                     // prow % 32 == 0: one hash per four keys
+          float ds[4];
+          mmfn_dropout_scale4(p.drop_p, p.seed, (uint64_t)(prow + jb * 32 + j), ds);
+          v[j] *= ds[0]; v[j + 1] *= ds[1]; v[j + 2] *= ds[2]; v[j + 3] *= ds[3];
+        }
       }
       sts_swizzled_row(pd_tile, row, v);
       tc::fence_async_smem();                              // generic-proxy writes -> visible to UMMA / TMA

@@ -38,13 +38,13 @@ static inline int grid_1d(int64_t n, int threads) {
 }
 
 // Counter-based RNG used by every dropout site: the same (seed, index) pair is
-// re-evaluated in backward, so no mask tensor is ever stored.
-__host__ __device__ __forceinline__ uint32_t mmfn_hash32(uint64_t seed, uint64_t idx) {
+// re-evaluated in backward, so no mask tensor is ever stored.  ONE 64-bit hash serves FOUR consecutive
+// elements (16 random bits each): vector kernels pay a quarter of the hash arithmetic per element.
+__host__ __device__ __forceinline__ uint64_t mmfn_hash64(uint64_t seed, uint64_t idx) {
   uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (uint32_t)(z >> 32);
+  return z ^ (z >> 31);
 }
 // Device-resident RNG offset (mmfn_rng_bind): added to every dropout seed on the device so that a
 // captured CUDA graph draws fresh masks on every replay.  One __constant__ pointer per translation unit.
@@ -54,15 +54,34 @@ static __constant__ const unsigned long long* c_mmfn_rng = nullptr;
     return (int)cudaMemcpyToSymbol(c_mmfn_rng, &p, sizeof(p));                         \
   }
 
-// keep-scale: 0 if dropped, 1/(1-p) if kept.  p == 0 -> always 1.
-__host__ __device__ __forceinline__ float mmfn_dropout_scale(float p, uint64_t seed, uint64_t idx) {
-  if (p <= 0.f) return 1.f;
+__host__ __device__ __forceinline__ uint64_t mmfn_drop_seed(uint64_t seed) {
 #ifdef __CUDA_ARCH__
   const unsigned long long* rng = c_mmfn_rng;
   if (rng) seed += *rng;
 #endif
-  float u = (float)(mmfn_hash32(seed, idx) >> 8) * (1.0f / 16777216.0f);
-  return (u >= p) ? 1.0f / (1.0f - p) : 0.f;
+  return seed;
+}
+// drop iff the element's 16 random bits fall below p * 65536
+__host__ __device__ __forceinline__ uint32_t mmfn_drop_threshold(float p) { return (uint32_t)(p * 65536.0f); }
+
+// keep-scale: 0 if dropped, 1/(1-p) if kept.  p == 0 -> always 1.
+__host__ __device__ __forceinline__ float mmfn_dropout_scale(float p, uint64_t seed, uint64_t idx) {
+  if (p <= 0.f) return 1.f;
+  const uint64_t h = mmfn_hash64(mmfn_drop_seed(seed), idx >> 2);
+  const uint32_t u = (uint32_t)(h >> (16 * (idx & 3))) & 0xFFFFu;
+  return (u >= mmfn_drop_threshold(p)) ? 1.0f / (1.0f - p) : 0.f;
+}
+// the four keep-scales of elements idx .. idx + 3 (idx % 4 == 0): one hash
+__host__ __device__ __forceinline__ void mmfn_dropout_scale4(float p, uint64_t seed, uint64_t idx, float* s) {
+  if (p <= 0.f) { s[0] = s[1] = s[2] = s[3] = 1.f; return; }
+  const uint64_t h = mmfn_hash64(mmfn_drop_seed(seed), idx >> 2);
+  const uint32_t thr = mmfn_drop_threshold(p);
+  const float keep = 1.0f / (1.0f - p);
+  const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+  s[0] = ((lo & 0xFFFFu) >= thr) ? keep : 0.f;
+  s[1] = ((lo >> 16) >= thr) ? keep : 0.f;
+  s[2] = ((hi & 0xFFFFu) >= thr) ? keep : 0.f;
+  s[3] = ((hi >> 16) >= thr) ? keep : 0.f;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

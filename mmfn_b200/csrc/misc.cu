@@ -53,6 +53,51 @@ __global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, 
     y[i] += a * x[i];
 }
 
+// im2col for the two network stems (7x7 stride-2 convolutions on 3 / 2 input channels, model_rad.py:22, :58-62):
+// col[pixel, k] with k = (r*S + s)*C + c, rows padded with zeros to Kp (a multiple of 32 = one TMA k-block), so the
+// stem runs as ONE dense tensor-core GEMM (forward) and one split-K GEMM (weight gradient) over this matrix instead of
+// a SIMT gather-GEMM.  One thread writes 4 consecutive k (16-byte store); the gathers hit L1/L2 (the input is small).
+__global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int N, int H, int W, int C, int R, int S,
+                              int stride, int pad, int Ho, int Wo, int K, int Kp) {
+  const int kq = Kp >> 2;
+  const int64_t n4 = (int64_t)N * Ho * Wo * kq;
+  const int SC = S * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / kq;
+    const int k0 = (int)(i - pix * kq) * 4;
+    const int wo = (int)(pix % Wo);
+    const int64_t t = pix / Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const int h0 = ho * stride - pad, w0 = wo * stride - pad;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + j;
+      float val = 0.f;
+      if (k < K) {
+        const int r = k / SC, rem = k - r * SC;
+        const int sx = rem / C, c = rem - sx * C;
+        const int h = h0 + r, w = w0 + sx;
+        if (h >= 0 && h < H && w >= 0 && w < W) val = __ldg(x + (((int64_t)n * H + h) * W + w) * C + c);
+      }
+      v[j] = val;
+    }
+    *reinterpret_cast<float4*>(col + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// dst[r, c] (+)= src[r, c] for c < cols, between two row pitches (padded <-> packed filter matrices of the stems)
+__global__ void copy2d_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd,
+                              int rows, int cols, int accum) {
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+    const float v = src[r * lds + c];
+    if (accum) dst[r * ldd + c] += v; else dst[r * ldd + c] = v;
+  }
+}
+
 // lane (G, P, F>=5) -> vec (G*(P-1), 7) = [x_i, y_i, x_{i+1}, y_{i+1}, attr_{i+1}[0..2]]
 __global__ void lane_to_vector_kernel(const float* __restrict__ lane, float* __restrict__ vec, int64_t G, int P) {
   int V = P - 1;
@@ -241,3 +286,21 @@ MMFN_API int mmfn_radar_logsoftmax_bwd(const float* dy, const float* y, float* d
 }
 
 MMFN_DEFINE_RNG_BINDER(misc)
+
+// col: (N*Ho*Wo, Kp) row-major, Kp % 4 == 0, Kp >= R*S*C; columns [R*S*C, Kp) are written as zeros.
+MMFN_API int mmfn_im2col_nhwc(const float* x, float* col, int N, int H, int W, int C, int R, int S, int stride, int pad,
+                              int Ho, int Wo, int Kp, cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && col && N > 0 && H > 0 && W > 0 && C > 0 && R > 0 && S > 0 && stride > 0, "im2col: bad args");
+  MMFN_CHECK_ARG(Kp % 4 == 0 && Kp >= R * S * C && (((uintptr_t)col) & 15) == 0, "im2col: Kp must be a multiple of 4, >= R*S*C; col 16-byte aligned");
+  const int64_t n4 = (int64_t)N * Ho * Wo * (Kp / 4);
+  im2col_kernel<<<grid_1d(n4, 256), 256, 0, stream>>>(x, col, N, H, W, C, R, S, stride, pad, Ho, Wo, R * S * C, Kp);
+  return mmfn_launch_status("im2col_nhwc");
+}
+
+// dst[r*ldd + c] (+)= src[r*lds + c], r < rows, c < cols
+MMFN_API int mmfn_copy2d_f32(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, int accum,
+                             cudaStream_t stream) {
+  MMFN_CHECK_ARG(src && dst && rows > 0 && cols > 0 && lds >= cols && ldd >= cols, "copy2d: bad args");
+  copy2d_kernel<<<grid_1d((int64_t)rows * cols, 256), 256, 0, stream>>>(src, lds, dst, ldd, rows, cols, accum);
+  return mmfn_launch_status("copy2d_f32");
+}

@@ -10,17 +10,33 @@ namespace {
 // accumulation.  256 threads = QPR channel-quads x (256 / QPR) row lanes, QPR = min(C/4, 32); blockIdx.x selects
 // the group of QPR quads, blockIdx.y a slab of `rows_per_block` rows.  BWD = false: sum x, sum x^2 (forward
 // statistics).  BWD = true: sum dy', sum dy' * xhat with dy' = dy * (y > 0) when a ReLU followed.
+//
+// Scratch `ws` (doubles, zero on entry, left zero on exit -- no memset node per call):
+//   [0, BN_SLOTS * 2C)  partial sums; CTA (.., y) adds into slot y % BN_SLOTS, so at most gridDim.y / BN_SLOTS
+//                       fp64 atomics ever queue on one address (hundreds of CTAs hammering 2C addresses cost more
+//                       than the reduction itself);
+//   [BN_SLOTS * 2C]     arrival ticket: the LAST CTA to finish folds the slots, publishes the per-channel results
+//                       as floats (forward: mean / rstd + running statistics; backward: mean(dy'), mean(dy' xhat)
+//                       into ws_fin + dgamma / dbeta) and re-zeroes the scratch.
 constexpr int BN_THREADS = 256;
+constexpr int BN_SLOTS = 16;
+
+struct BnFinal {
+  float* mean; float* rstd; float* running_mean; float* running_var; float eps, momentum;   // forward
+  float* fin; float* dgamma; float* dbeta;                                                  // backward
+};
 
 template <bool BWD>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_colsum_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float4* __restrict__ yout,
                  const float* __restrict__ mean, const float* __restrict__ rstd, int64_t M, int C4, int qpr,
-                 int64_t rows_per_block, double* __restrict__ ws) {
+                 int64_t rows_per_block, double* __restrict__ ws, BnFinal fz) {
   __shared__ double red[BN_THREADS][8];
+  __shared__ bool last_cta;
   const int q = threadIdx.x % qpr, rsub = threadIdx.x / qpr, nrs = BN_THREADS / qpr;
   const int cq = blockIdx.x * qpr + q;                          // channel quad of this thread
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  const int C = C4 * 4;
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (cq < C4) {
     float m4[4] = {0.f, 0.f, 0.f, 0.f}, r4[4] = {1.f, 1.f, 1.f, 1.f};
@@ -29,7 +45,7 @@ bn_colsum_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, co
       m4[0] = mm.x; m4[1] = mm.y; m4[2] = mm.z; m4[3] = mm.w;
       r4[0] = rr.x; r4[1] = rr.y; r4[2] = rr.z; r4[3] = rr.w;
     }
-#pragma unroll 2
+#pragma unroll 4
     for (int64_t r = r0 + rsub; r < r1; r += nrs) {
       const float4 xv = __ldg(x + r * C4 + cq);
       const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
@@ -61,9 +77,48 @@ bn_colsum_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, co
     if (cqq < C4) {
       double t = 0.0;
       for (int rs = 0; rs < nrs; ++rs) t += red[rs * qpr + qq][k];
-      atomicAdd(ws + (k < 4 ? 0 : (int64_t)C4 * 4) + cqq * 4 + (k & 3), t);
+      double* slot = ws + (int64_t)(blockIdx.y % BN_SLOTS) * 2 * C;
+      atomicAdd(slot + (k < 4 ? 0 : C) + cqq * 4 + (k & 3), t);
     }
   }
+  // ---- last CTA: fold the slots, publish, re-zero
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(ws + (int64_t)BN_SLOTS * 2 * C);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last_cta = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (!last_cta) return;
+  __threadfence();
+  const double invM = 1.0 / (double)M;
+  for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < BN_SLOTS; ++sl) {
+      double* slot = ws + (int64_t)sl * 2 * C;
+      s1 += __ldcg(slot + c);
+      s2 += __ldcg(slot + C + c);
+      slot[c] = 0.0;
+      slot[C + c] = 0.0;
+    }
+    if (!BWD) {
+      const double md = s1 * invM;
+      double var = s2 * invM - md * md;
+      if (var < 0.0) var = 0.0;
+      fz.mean[c] = (float)md;
+      fz.rstd[c] = (float)(1.0 / sqrt(var + (double)fz.eps));
+      if (fz.running_mean) {
+        const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        fz.running_mean[c] = (float)((1.0 - fz.momentum) * fz.running_mean[c] + fz.momentum * md);
+        fz.running_var[c] = (float)((1.0 - fz.momentum) * fz.running_var[c] + fz.momentum * unbiased);
+      }
+    } else {
+      fz.fin[c] = (float)(s1 * invM);
+      fz.fin[C + c] = (float)(s2 * invM);
+      fz.dbeta[c] += (float)s1;
+      fz.dgamma[c] += (float)s2;
+    }
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
 }
 
 static inline void bn_colsum_grid(int64_t M, int C, int& qpr, dim3& grid, int64_t& rows_per_block) {
@@ -72,98 +127,77 @@ static inline void bn_colsum_grid(int64_t M, int C, int& qpr, dim3& grid, int64_
   while (BN_THREADS % qpr) --qpr;                                // C4 = 16, 32, 64, 128 here; stay safe for odd widths
   const int groups = (C4 + qpr - 1) / qpr;
   const int nrs = BN_THREADS / qpr;
-  int64_t slabs = ceil_div64(M, (int64_t)nrs * 4);               // at least 4 rows per thread
+  int64_t slabs = ceil_div64(M, (int64_t)nrs * 8);               // at least 8 rows per thread
   const int64_t cap = (148 * 4 + groups - 1) / groups;
   if (slabs > cap) slabs = cap;
   if (slabs < 1) slabs = 1;
   rows_per_block = ceil_div64(M, slabs);
   grid = dim3((unsigned)groups, (unsigned)ceil_div64(M, rows_per_block));
 }
+static inline float* bn_ws_fin(double* ws, int C) { return reinterpret_cast<float*>(ws + (int64_t)BN_SLOTS * 2 * C + 2); }
 
-// y = (x - mean) * rstd * gamma + beta (+res, ReLU).  With ws != null the batch statistics are finalised here
-// from the fp64 partial sums (every CTA recomputes the C means into shared memory; CTA 0 also publishes
-// mean/rstd for backward and applies the running-statistics momentum update) -- no separate finalize launch.
-__global__ void bn_apply_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n4, int C4,
-                                float* __restrict__ mean, float* __restrict__ rstd,
-                                const float4* __restrict__ gamma, const float4* __restrict__ beta,
-                                const float4* __restrict__ res, int relu,
-                                const double* __restrict__ ws, int64_t M, float eps, float momentum,
-                                float* __restrict__ running_mean, float* __restrict__ running_var) {
-  extern __shared__ float sm[];            // mean[C] | rstd[C]
-  const int C = C4 * 4;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float m, r;
-    if (ws) {
-      double md = ws[c] / (double)M;
-      double var = ws[C + c] / (double)M - md * md;
-      if (var < 0.0) var = 0.0;
-      m = (float)md;
-      r = (float)(1.0 / sqrt(var + (double)eps));
-      if (blockIdx.x == 0) {
-        mean[c] = m;
-        rstd[c] = r;
-        if (running_mean) {
-          double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
-          running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * md);
-          running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
-        }
-      }
-    } else {
-      m = mean[c];
-      r = rstd[c];
-    }
-    sm[c] = m;
-    sm[C + c] = r;
-  }
-  __syncthreads();
-  const float4* sm_mean = reinterpret_cast<const float4*>(sm);
-  const float4* sm_rstd = reinterpret_cast<const float4*>(sm + C);
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C4);
-    float4 v = __ldg(x + i), m = sm_mean[c], r = sm_rstd[c], g = __ldg(gamma + c), b = __ldg(beta + c);
+// y = (x - mean) * rstd * gamma + beta (+res, ReLU) from the published per-channel mean / rstd.  The grid stride is a
+// multiple of C/4 (power-of-two widths), so a thread keeps ONE channel quad: its coefficients live in registers and
+// the loop body is pure streaming (no per-element index division).
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n4, int C4,
+                const float* __restrict__ mean, const float* __restrict__ rstd,
+                const float4* __restrict__ gamma, const float4* __restrict__ beta,
+                const float4* __restrict__ res, int relu) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool fixed = stride % C4 == 0;
+  int c = (int)(i0 % C4);
+  float4 m, r, g, b;
+  auto coef = [&](int cq) {
+    m = __ldg(reinterpret_cast<const float4*>(mean) + cq);
+    r = __ldg(reinterpret_cast<const float4*>(rstd) + cq);
+    g = __ldg(gamma + cq);
+    b = __ldg(beta + cq);
+  };
+  coef(c);
+#pragma unroll 4
+  for (int64_t i = i0; i < n4; i += stride) {
+    if (!fixed) { c = (int)(i % C4); coef(c); }
+    const float4 v = __ldg(x + i);
     float4 o;
     o.x = (v.x - m.x) * r.x * g.x + b.x;
     o.y = (v.y - m.y) * r.y * g.y + b.y;
     o.z = (v.z - m.z) * r.z * g.z + b.z;
     o.w = (v.w - m.w) * r.w * g.w + b.w;
-    if (res) { float4 q = __ldg(res + i); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+    if (res) { const float4 q = __ldg(res + i); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     y[i] = o;
   }
 }
 
 // dx = gamma * rstd * (dy' - mean(dy') - xhat * mean(dy' * xhat)); dres = dy' (residual branch).  float4 over channels;
-// the per-channel coefficients are staged in shared memory once per CTA.  CTA 0 accumulates dgamma / dbeta.
-__global__ void bn_bwd_dx_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
-                                 const float4* __restrict__ yout, const float* __restrict__ mean,
-                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                 const double* __restrict__ ws, int64_t M, int C4,
-                                 float4* __restrict__ dx, float4* __restrict__ dres,
-                                 float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  extern __shared__ float sm[];            // mean[C] | rstd[C] | gamma*rstd[C] | mean(dy')[C] | mean(dy' xhat)[C]
+// fin = [mean(dy') | mean(dy' xhat)] published by the reduction kernel.  Same fixed-channel-quad streaming loop.
+__global__ void __launch_bounds__(256)
+bn_bwd_dx_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
+                 const float4* __restrict__ yout, const float* __restrict__ mean,
+                 const float* __restrict__ rstd, const float* __restrict__ gamma,
+                 const float* __restrict__ fin, int64_t M, int C4,
+                 float4* __restrict__ dx, float4* __restrict__ dres) {
   const int C = C4 * 4;
-  const double invM = 1.0 / (double)M;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float rs = rstd[c];
-    sm[c] = mean[c];
-    sm[C + c] = rs;
-    sm[2 * C + c] = gamma[c] * rs;
-    sm[3 * C + c] = (float)(ws[c] * invM);
-    sm[4 * C + c] = (float)(ws[C + c] * invM);
-    if (blockIdx.x == 0) {
-      dbeta[c] += (float)ws[c];
-      dgamma[c] += (float)ws[C + c];
-    }
-  }
-  __syncthreads();
-  const float4* s_mean = reinterpret_cast<const float4*>(sm);
-  const float4* s_rstd = reinterpret_cast<const float4*>(sm + C);
-  const float4* s_k = reinterpret_cast<const float4*>(sm + 2 * C);
-  const float4* s_dy = reinterpret_cast<const float4*>(sm + 3 * C);
-  const float4* s_dx = reinterpret_cast<const float4*>(sm + 4 * C);
   const int64_t n4 = M * C4;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool fixed = stride % C4 == 0;
+  int c = (int)(i0 % C4);
+  float4 m, r, k, a, b;
+  auto coef = [&](int cq) {
+    m = __ldg(reinterpret_cast<const float4*>(mean) + cq);
+    r = __ldg(reinterpret_cast<const float4*>(rstd) + cq);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + cq);
+    k = make_float4(g.x * r.x, g.y * r.y, g.z * r.z, g.w * r.w);
+    a = __ldg(reinterpret_cast<const float4*>(fin) + cq);
+    b = __ldg(reinterpret_cast<const float4*>(fin + C) + cq);
+  };
+  coef(c);
+#pragma unroll 4
+  for (int64_t i = i0; i < n4; i += stride) {
+    if (!fixed) { c = (int)(i % C4); coef(c); }
     float4 g = __ldg(dy + i);
     if (yout) {
       const float4 yv = __ldg(yout + i);
@@ -172,7 +206,7 @@ __global__ void bn_bwd_dx_kernel(const float4* __restrict__ dy, const float4* __
       if (!(yv.z > 0.f)) g.z = 0.f;
       if (!(yv.w > 0.f)) g.w = 0.f;
     }
-    const float4 xv = __ldg(x + i), m = s_mean[c], r = s_rstd[c], k = s_k[c], a = s_dy[c], b = s_dx[c];
+    const float4 xv = __ldg(x + i);
     float4 o;
     o.x = k.x * (g.x - a.x - (xv.x - m.x) * r.x * b.x);
     o.y = k.y * (g.y - a.y - (xv.y - m.y) * r.y * b.y);
@@ -182,6 +216,130 @@ __global__ void bn_bwd_dx_kernel(const float4* __restrict__ dy, const float4* __
     if (dres) dres[i] = g;
   }
 }
+
+// ---- small feature maps (M <= 2048 rows: layer 4 at B=16): ONE launch.  Such tensors (<= 4 MB) live in L2, so
+// the two-kernel scheme is pure launch/tail latency.  One CTA owns one channel quad: pass 1 reduces its column over
+// all rows, the CTA publishes the statistics, pass 2 re-reads the column (L2/L1 hits) and writes the result.
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+bn_small_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float4* __restrict__ yout,
+                const float4* __restrict__ res, float4* __restrict__ out, float4* __restrict__ dres,
+                float* __restrict__ mean, float* __restrict__ rstd, const float4* __restrict__ gamma,
+                const float4* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
+                float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int C4, float eps, float momentum, int relu) {
+  __shared__ double red[8][8];
+  __shared__ float fin[8];
+  const int cq = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m4[4] = {0.f, 0.f, 0.f, 0.f}, r4[4] = {1.f, 1.f, 1.f, 1.f};
+  if (BWD) {
+    const float4 mm = __ldg(reinterpret_cast<const float4*>(mean) + cq), rr = __ldg(reinterpret_cast<const float4*>(rstd) + cq);
+    m4[0] = mm.x; m4[1] = mm.y; m4[2] = mm.z; m4[3] = mm.w;
+    r4[0] = rr.x; r4[1] = rr.y; r4[2] = rr.z; r4[3] = rr.w;
+  }
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 8
+  for (int r = threadIdx.x; r < M; r += 256) {
+    const float4 xv = __ldg(x + (int64_t)r * C4 + cq);
+    const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+    if (!BWD) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { acc[k] += xa[k]; acc[4 + k] += (double)xa[k] * xa[k]; }
+    } else {
+      const float4 gv = __ldg(dy + (int64_t)r * C4 + cq);
+      float ga[4] = {gv.x, gv.y, gv.z, gv.w};
+      if (yout) {
+        const float4 yv = __ldg(yout + (int64_t)r * C4 + cq);
+        if (!(yv.x > 0.f)) ga[0] = 0.f;
+        if (!(yv.y > 0.f)) ga[1] = 0.f;
+        if (!(yv.z > 0.f)) ga[2] = 0.f;
+        if (!(yv.w > 0.f)) ga[3] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { acc[k] += ga[k]; acc[4 + k] += (double)ga[k] * ((xa[k] - m4[k]) * r4[k]); }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[warp][k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    const int k = threadIdx.x, c = cq * 4 + k;
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { s1 += red[w][k]; s2 += red[w][4 + k]; }
+    const double invM = 1.0 / (double)M;
+    if (!BWD) {
+      const double md = s1 * invM;
+      double var = s2 * invM - md * md;
+      if (var < 0.0) var = 0.0;
+      const float mf = (float)md, rf = (float)(1.0 / sqrt(var + (double)eps));
+      mean[c] = mf; rstd[c] = rf;
+      fin[k] = mf; fin[4 + k] = rf;
+      if (running_mean) {
+        const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * md);
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+      }
+    } else {
+      fin[k] = (float)(s1 * invM);
+      fin[4 + k] = (float)(s2 * invM);
+      dbeta[c] += (float)s1;
+      dgamma[c] += (float)s2;
+    }
+  }
+  __syncthreads();
+  const float4 g = __ldg(gamma + cq);
+  const float ga4[4] = {g.x, g.y, g.z, g.w};
+  if (!BWD) {
+    const float4 b = __ldg(beta + cq);
+    const float ba[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll 8
+    for (int r = threadIdx.x; r < M; r += 256) {
+      const int64_t i = (int64_t)r * C4 + cq;
+      const float4 v = __ldg(x + i);
+      float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = (o[k] - fin[k]) * fin[4 + k] * ga4[k] + ba[k];
+      if (res) { const float4 q = __ldg(res + i); o[0] += q.x; o[1] += q.y; o[2] += q.z; o[3] += q.w; }
+      if (relu) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = fmaxf(o[k], 0.f);
+      }
+      out[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  } else {
+    float kk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) kk[k] = ga4[k] * r4[k];
+#pragma unroll 8
+    for (int r = threadIdx.x; r < M; r += 256) {
+      const int64_t i = (int64_t)r * C4 + cq;
+      const float4 gv = __ldg(dy + i);
+      float gg[4] = {gv.x, gv.y, gv.z, gv.w};
+      if (yout) {
+        const float4 yv = __ldg(yout + i);
+        if (!(yv.x > 0.f)) gg[0] = 0.f;
+        if (!(yv.y > 0.f)) gg[1] = 0.f;
+        if (!(yv.z > 0.f)) gg[2] = 0.f;
+        if (!(yv.w > 0.f)) gg[3] = 0.f;
+      }
+      const float4 xv = __ldg(x + i);
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = kk[k] * (gg[k] - fin[k] - (xa[k] - m4[k]) * r4[k] * fin[4 + k]);
+      out[i] = make_float4(o[0], o[1], o[2], o[3]);
+      if (dres) dres[i] = make_float4(gg[0], gg[1], gg[2], gg[3]);
+    }
+  }
+}
+constexpr int BN_SMALL_ROWS = 2048;
 
 // ------------------------------------------------------------------ LayerNorm
 __device__ __forceinline__ float act_fwd(float v, int act) {
@@ -273,10 +431,9 @@ __global__ void ln_bwd_dx_kernel(const float* __restrict__ dy, const float* __re
       *reinterpret_cast<float4*>(dx + row * C + c) = o;
       if (dx_drop) {        // gradient entering the next residual branch's dropout (same hash as the forward mask)
         const uint64_t i0 = (uint64_t)(row * C + c);
-        o.x *= mmfn_dropout_scale(drop_p, drop_seed, i0);
-        o.y *= mmfn_dropout_scale(drop_p, drop_seed, i0 + 1);
-        o.z *= mmfn_dropout_scale(drop_p, drop_seed, i0 + 2);
-        o.w *= mmfn_dropout_scale(drop_p, drop_seed, i0 + 3);
+        float ds[4];
+        mmfn_dropout_scale4(drop_p, drop_seed, i0, ds);          // i0 % 4 == 0 (C % 4 == 0)
+        o.x *= ds[0]; o.y *= ds[1]; o.z *= ds[2]; o.w *= ds[3];
         *reinterpret_cast<float4*>(dx_drop + row * C + c) = o;
       }
     }
@@ -317,8 +474,9 @@ __global__ void ln_bwd_param_kernel(const float* __restrict__ dy, const float* _
 
 }  // namespace
 
-// x,y: (M,C) NHWC rows. ws: 2*C doubles of scratch. Writes mean/rstd (C each) and, when
-// running_* are non-null, the momentum update with the unbiased variance.
+// x,y: (M,C) NHWC rows.  ws: per-stream scratch of at least 34*C + 8 doubles that is ZERO on entry (zero it once
+// after allocation; every call leaves it zero again).  Writes mean/rstd (C each) and, when running_* are non-null,
+// the momentum update with the unbiased variance.
 MMFN_API int mmfn_bn_train_fwd(const float* x, float* y, int64_t M, int C,
                                const float* gamma, const float* beta,
                                float* running_mean, float* running_var, float momentum, float eps,
@@ -326,34 +484,45 @@ MMFN_API int mmfn_bn_train_fwd(const float* x, float* y, int64_t M, int C,
                                double* ws, cudaStream_t stream) {
   MMFN_CHECK_ARG(x && y && gamma && beta && mean && rstd && ws, "bn_fwd: null pointer");
   MMFN_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "bn_fwd: C must be a positive multiple of 4");
-  MMFN_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0, "bn_fwd: 16-byte alignment");
-  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, stream);
+  MMFN_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)mean | (uintptr_t)rstd) & 15) == 0,
+                 "bn_fwd: 16-byte alignment");
+  if (M <= BN_SMALL_ROWS) {
+    bn_small_kernel<false><<<C / 4, 256, 0, stream>>>((const float4*)x, nullptr, nullptr, (const float4*)res, (float4*)y, nullptr,
+        mean, rstd, (const float4*)gamma, (const float4*)beta, running_mean, running_var, nullptr, nullptr, (int)M, C / 4, eps, momentum, relu);
+    return mmfn_launch_status("bn_train_fwd");
+  }
   int qpr; dim3 grid; int64_t rpb;
   bn_colsum_grid(M, C, qpr, grid, rpb);
-  bn_colsum_kernel<false><<<grid, BN_THREADS, 0, stream>>>((const float4*)x, nullptr, nullptr, nullptr, nullptr, M, C / 4, qpr, rpb, ws);
+  BnFinal fz = {mean, rstd, running_mean, running_var, eps, momentum, nullptr, nullptr, nullptr};
+  bn_colsum_kernel<false><<<grid, BN_THREADS, 0, stream>>>((const float4*)x, nullptr, nullptr, nullptr, nullptr, M, C / 4, qpr, rpb, ws, fz);
   int64_t n4 = M * C / 4;
-  bn_apply_kernel<<<grid_1d(n4, 256), 256, 2 * C * sizeof(float), stream>>>((const float4*)x, (float4*)y, n4, C / 4,
-      mean, rstd, (const float4*)gamma, (const float4*)beta, (const float4*)res, relu,
-      ws, M, eps, momentum, running_mean, running_var);
+  bn_apply_kernel<<<grid_1d(n4, 256), 256, 0, stream>>>((const float4*)x, (float4*)y, n4, C / 4,
+      mean, rstd, (const float4*)gamma, (const float4*)beta, (const float4*)res, relu);
   return mmfn_launch_status("bn_train_fwd");
 }
 
 // yout: post-ReLU output of the forward (null when no ReLU followed). dres (nullable)
-// receives the ReLU-masked dy for the residual branch.  dgamma/dbeta are accumulated.
+// receives the ReLU-masked dy for the residual branch.  dgamma/dbeta are accumulated.  ws: as in mmfn_bn_train_fwd.
 MMFN_API int mmfn_bn_train_bwd(const float* dy, const float* x, const float* yout,
                                const float* mean, const float* rstd, const float* gamma,
                                int64_t M, int C, float* dx, float* dres, float* dgamma, float* dbeta,
                                double* ws, cudaStream_t stream) {
   MMFN_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && ws, "bn_bwd: null pointer");
   MMFN_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "bn_bwd: C must be a positive multiple of 4");
-  MMFN_CHECK_ARG((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)yout | (uintptr_t)dx | (uintptr_t)dres | (uintptr_t)mean | (uintptr_t)rstd) & 15) == 0,
+  MMFN_CHECK_ARG((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)yout | (uintptr_t)dx | (uintptr_t)dres | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma | (uintptr_t)ws) & 15) == 0,
                  "bn_bwd: 16-byte alignment");
-  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * C, stream);
+  if (M <= BN_SMALL_ROWS) {
+    bn_small_kernel<true><<<C / 4, 256, 0, stream>>>((const float4*)x, (const float4*)dy, (const float4*)yout, nullptr, (float4*)dx, (float4*)dres,
+        const_cast<float*>(mean), const_cast<float*>(rstd), (const float4*)gamma, nullptr, nullptr, nullptr, dgamma, dbeta, (int)M, C / 4, 0.f, 0.f, 0);
+    return mmfn_launch_status("bn_train_bwd");
+  }
   int qpr; dim3 grid; int64_t rpb;
   bn_colsum_grid(M, C, qpr, grid, rpb);
-  bn_colsum_kernel<true><<<grid, BN_THREADS, 0, stream>>>((const float4*)x, (const float4*)dy, (const float4*)yout, mean, rstd, M, C / 4, qpr, rpb, ws);
-  bn_bwd_dx_kernel<<<grid_1d(M * C / 4, 256), 256, 5 * C * sizeof(float), stream>>>(
-      (const float4*)dy, (const float4*)x, (const float4*)yout, mean, rstd, gamma, ws, M, C / 4, (float4*)dx, (float4*)dres, dgamma, dbeta);
+  float* fin = bn_ws_fin(ws, C);
+  BnFinal fz = {nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, fin, dgamma, dbeta};
+  bn_colsum_kernel<true><<<grid, BN_THREADS, 0, stream>>>((const float4*)x, (const float4*)dy, (const float4*)yout, mean, rstd, M, C / 4, qpr, rpb, ws, fz);
+  bn_bwd_dx_kernel<<<grid_1d(M * C / 4, 256), 256, 0, stream>>>(
+      (const float4*)dy, (const float4*)x, (const float4*)yout, mean, rstd, gamma, fin, M, C / 4, (float4*)dx, (float4*)dres);
   return mmfn_launch_status("bn_train_bwd");
 }
 
@@ -372,9 +541,8 @@ MMFN_API int mmfn_bn_eval_fwd(const float* x, float* y, int64_t M, int C, const 
   MMFN_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "bn_eval: C must be a positive multiple of 4");
   bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, stream>>>(running_mean, running_var, eps, mean, rstd, C);
   int64_t n4 = M * C / 4;
-  bn_apply_kernel<<<grid_1d(n4, 256), 256, 2 * C * sizeof(float), stream>>>((const float4*)x, (float4*)y, n4, C / 4,
-      mean, rstd, (const float4*)gamma, (const float4*)beta, (const float4*)res, relu,
-      nullptr, M, eps, 0.f, nullptr, nullptr);
+  bn_apply_kernel<<<grid_1d(n4, 256), 256, 0, stream>>>((const float4*)x, (float4*)y, n4, C / 4,
+      mean, rstd, (const float4*)gamma, (const float4*)beta, (const float4*)res, relu);
   return mmfn_launch_status("bn_eval_fwd");
 }
 

@@ -142,10 +142,12 @@ __global__ void tokens_bwd_feat_kernel(FeatPtrsW df, int B, int H, int W, int C,
     int64_t ti = ((int64_t)b * T + m * 64 + (h / kh) * 8 + (w / kw)) * C + c;
     float4 g = __ldg(reinterpret_cast<const float4*>(dtok + ti));
     float4 d = *reinterpret_cast<const float4*>(dst + (i << 2));
-    d.x += g.x * mmfn_dropout_scale(drop_p, seed, (uint64_t)ti) * inv;
-    d.y += g.y * mmfn_dropout_scale(drop_p, seed, (uint64_t)ti + 1) * inv;
-    d.z += g.z * mmfn_dropout_scale(drop_p, seed, (uint64_t)ti + 2) * inv;
-    d.w += g.w * mmfn_dropout_scale(drop_p, seed, (uint64_t)ti + 3) * inv;
+    float ds[4];
+    mmfn_dropout_scale4(drop_p, seed, (uint64_t)ti, ds);        // ti % 4 == 0 (C % 4 == 0)
+    d.x += g.x * ds[0] * inv;
+    d.y += g.y * ds[1] * inv;
+    d.z += g.z * ds[2] * inv;
+    d.w += g.w * ds[3] * inv;
     *reinterpret_cast<float4*>(dst + (i << 2)) = d;
   }
 }

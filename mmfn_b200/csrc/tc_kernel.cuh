@@ -62,7 +62,7 @@ struct Smem {
 // FULL = false compiles the epilogue down to alpha*acc + bias + residual (most launches); the
 // ReLU / mask / dropout variant is a separate instantiation so its hash arithmetic is never if-converted in.
 template <class Op, int TBN, int STAGES, bool FULL>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Op op, Epilogue e) {
   using L = Smem<TBN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -173,40 +173,59 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // instruction cache -- a fully unrolled, branchy epilogue costs more in fetch stalls than it saves)
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
-#pragma unroll 2
-        for (int rr = 0; rr < 8; ++rr) {
-          const int r = rr * 4 + rsub;
-          const int64_t off_r = lds64(row_off + (q * 32 + r) * 8);
-          if (off_r < 0) continue;
-          const int64_t idx = off_r + col;
-          const float4 a4 = lds128(stg + (r * 36 + c4) * 4);
-          float x[4] = {a4.x, a4.y, a4.z, a4.w};
-          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+        // per half (4 rows): the rows' offsets, then all residual / mask vectors, are requested before the first use --
+        // four independent 16-byte loads in flight per operand instead of one per (dependent) loop iteration.
+        // (All eight at once pushes the FULL variant past 102 registers = one CTA per SM.)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) x[j] = (have_k ? e.alpha * x[j] : 0.f) + bb[j];
-          if constexpr (FULL) {
-            if (e.act == 1) {
+        for (int hh = 0; hh < 2; ++hh) {
+          int64_t offs[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
-            }
-            if (e.mask) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(e.mask + idx));
-              const float m4[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) x[j] = m4[j] > 0.f ? x[j] : 0.f;
-            }
-            if (e.drop_p > 0.f) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) x[j] *= mmfn_dropout_scale(e.drop_p, e.drop_seed, (uint64_t)(idx + j));
-            }
-          }
+          for (int rr = 0; rr < 4; ++rr) offs[rr] = lds64(row_off + (q * 32 + (hh * 4 + rr) * 4 + rsub) * 8);
+          float4 r4[4], m4v[4];
           if (res) {
-            const float4 t = __ldg(reinterpret_cast<const float4*>(res + idx));
-            x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr)
+              r4[rr] = offs[rr] >= 0 ? __ldg(reinterpret_cast<const float4*>(res + offs[rr] + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
-          if (e.accum == 0) *reinterpret_cast<float4*>(e.C + idx) = make_float4(x[0], x[1], x[2], x[3]);
-          else  // split-K / weight-gradient accumulation: one 16-byte vector reduction instead of four scalar atomics
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(e.C + idx), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
+          if constexpr (FULL) {
+            if (e.mask) {
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr)
+                m4v[rr] = offs[rr] >= 0 ? __ldg(reinterpret_cast<const float4*>(e.mask + offs[rr] + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const int r = (hh * 4 + rr) * 4 + rsub;
+            if (offs[rr] < 0) continue;
+            const int64_t idx = offs[rr] + col;
+            const float4 a4 = lds128(stg + (r * 36 + c4) * 4);
+            float x[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = (have_k ? e.alpha * x[j] : 0.f) + bb[j];
+            if constexpr (FULL) {
+              if (e.act == 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
+              }
+              if (e.mask) {
+                const float mk[4] = {m4v[rr].x, m4v[rr].y, m4v[rr].z, m4v[rr].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = mk[j] > 0.f ? x[j] : 0.f;
+              }
+              if (e.drop_p > 0.f) {
+                float ds[4];
+                mmfn_dropout_scale4(e.drop_p, e.drop_seed, (uint64_t)idx, ds);   // idx % 4 == 0 on the vector path
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] *= ds[j];
+              }
+            }
+            if (res) { x[0] += r4[rr].x; x[1] += r4[rr].y; x[2] += r4[rr].z; x[3] += r4[rr].w; }
+            if (e.accum == 0) *reinterpret_cast<float4*>(e.C + idx) = make_float4(x[0], x[1], x[2], x[3]);
+            else  // split-K / weight-gradient accumulation: one 16-byte vector reduction instead of four scalar atomics
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(e.C + idx), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
+          }
         }
       } else {
         // ---- ragged / unaligned tiles: scalar, not unrolled

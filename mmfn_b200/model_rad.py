@@ -96,7 +96,12 @@ class ConvBN:
 
     def fwd(self, x, res=None, relu=True, train=True):
         self.x, self.relu = x, relu
-        self.z = ops.conv2d_fwd(x, self.w, self.stride, self.pad)
+        self.col = None
+        if ops.stem_uses_im2col(x, self.w):
+            # stems: im2col + one dense tensor-core GEMM; the column matrix is kept for the weight gradient
+            self.z, self.col, self.w_pad = ops.conv2d_fwd_im2col(x, self.w, self.stride, self.pad, getattr(self, "w_pad", None))
+        else:
+            self.z = ops.conv2d_fwd(x, self.w, self.stride, self.pad)
         if train and self.dgrad and ops.dgrad_uses_flipped_filter(self.w, x.shape, self.stride):
             # the data-gradient conv reads the mirrored CRSK filters: a pure function of the weights, so
             # the transform is issued here on the side stream instead of on the backward critical path
@@ -112,15 +117,18 @@ class ConvBN:
     def bwd(self, dy, need_dx=True, want_dres=False, dx_res=None):
         dz, dres = ops.bn_train_bwd(dy, self.z, self.y if self.relu else None, self.mean, self.rstd, self.gam,
                                     self.dgam, self.dbet, want_dres)
-        x = self.x
-        _Aux.run(lambda: ops.conv2d_wgrad_(dz, x, self.dw, self.stride, self.pad), dz, x)
+        x, col = self.x, self.col
+        if col is not None:
+            _Aux.run(lambda: ops.conv2d_wgrad_im2col_(dz, col, self.dw), dz, col)
+        else:
+            _Aux.run(lambda: ops.conv2d_wgrad_(dz, x, self.dw, self.stride, self.pad), dz, x)
         dx = None
         if need_dx:
             _Aux.wait(self.wt_ev)
             dx = ops.conv2d_dgrad(dz, self.w, self.x.shape, self.stride, self.pad, res=dx_res, wt_flipped=self.wt)
             if self.wt is not None:
                 _Aux.keep.append(self.wt)                # allocated on the side stream: hold until join_all()
-        self.x = self.z = self.y = self.wt = self.wt_ev = None
+        self.x = self.z = self.y = self.wt = self.wt_ev = self.col = None
         return dx, dres
 
 

@@ -79,12 +79,13 @@ def gemm(A, B, C, *, bias=None, res=None, mask=None, alpha=1.0, act=0, accum=0,
                             _p(bias), _p(res), _p(mask), float(alpha), int(act), int(accum), float(drop_p),
                             int(seed), int(splitk) if splitk > 1 else 0, _st())
             return C
-    if splitk == 1 and act == 0 and mask is None and drop_p == 0 and K >= 2048:
-        # skinny outputs with a huge reduction (generator dgrad: 16x64 <- K=262144; polyline wgrad: 64x7 <-
-        # K=18432): split K over CTAs so the reduction is not one CTA's serial loop
+    if splitk == 1 and act == 0 and mask is None and drop_p == 0 and K >= 512:
+        # skinny outputs with a long reduction (generator dgrad: 16x64 <- K=262144; polyline wgrad: 64x7 <-
+        # K=18432; radar GAT weight gradients: 5x162 <- K=1296): split K over CTAs so the reduction is not one
+        # CTA's serial loop
         tiles = ((M + 63) // 64) * ((N + 63) // 64) * nbt
         if tiles < 64:
-            splitk = max(1, min(K // 256, 296 // tiles))
+            splitk = max(1, min(K // 128, 296 // tiles))
             if splitk > 1:
                 if accum == 0:
                     C.zero_()
@@ -131,6 +132,39 @@ def conv2d_fwd(x, w_krsc, stride, pad, res=None):
         assert res is None
         lib().conv2d_fwd_f32(_p(x), _p(w_krsc), _p(y), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, _st())
     return y
+
+
+def stem_uses_im2col(x, w_krsc):
+    """The two stems (7x7/2 on 3 / 2 channels) cannot use the implicit-GEMM tensor-core path (channels % 32); with
+    TF32 enabled they run as im2col + ONE dense tensor-core GEMM instead of the SIMT gather-GEMM."""
+    return TF32 and x.shape[-1] < 32 and w_krsc.shape[0] % 4 == 0
+
+
+def conv2d_fwd_im2col(x, w_krsc, stride, pad, w_pad=None):
+    """-> (y, col, w_pad): col (N*Ho*Wo, Kp) is kept for the weight gradient; w_pad (Co, Kp) is the zero-padded filter
+    matrix (allocate once by passing None, then pass it back in)."""
+    N, H, W, C = x.shape
+    Co, R, S, _ = w_krsc.shape
+    Ho, Wo = conv_out_hw(H, W, R, S, stride, pad)
+    K = R * S * C
+    Kp = (K + 31) // 32 * 32
+    if w_pad is None:
+        w_pad = torch.zeros((Co, Kp), device=x.device, dtype=torch.float32)
+    lib().copy2d_f32(_p(w_krsc), K, _p(w_pad), Kp, Co, K, 0, _st())
+    col = torch.empty((N * Ho * Wo, Kp), device=x.device, dtype=torch.float32)
+    lib().im2col_nhwc(_p(x), _p(col), N, H, W, C, R, S, stride, pad, Ho, Wo, Kp, _st())
+    y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
+    gemm(col, w_pad, y.view(N * Ho * Wo, Co))
+    lib().next_work = None
+    return y, col, w_pad
+
+
+def conv2d_wgrad_im2col_(dy, col, dw_krsc):
+    """dw_krsc (Co, R, S, C) += dy^T col  -- one split-K tensor-core GEMM over all output pixels."""
+    Co = dw_krsc.shape[0]
+    K = dw_krsc.numel() // Co
+    M = col.shape[0]
+    gemm(dy.view(M, Co).t(), col[:, :K].t(), dw_krsc.view(Co, K), accum=2)
 
 
 def filter_crsk(w_krsc, flip=False):
@@ -185,24 +219,30 @@ def conv2d_wgrad_(dy, x, dw_krsc, stride, pad):
 
 # ------------------------------------------------------------------ normalisation
 _ws = {}
+BN_WS_MAX_C = 2048
+BN_SMALL_ROWS = 2048     # norm.cu: feature maps with at most this many rows take the single-launch kernel
 
 
 def _bn_ws(dev):
-    """fp64 scratch for the BatchNorm partial sums: one per stream, since trunks run concurrently."""
+    """fp64 scratch for the BatchNorm partial sums: one per stream, since trunks run concurrently.  Zeroed ONCE here;
+    the reduction kernel's last CTA leaves it zero again (34*C + 8 doubles, C <= BN_WS_MAX_C)."""
     key = (dev, torch.cuda.current_stream().cuda_stream)
     if key not in _ws:
-        _ws[key] = torch.empty(2 * 4096, device=dev, dtype=torch.float64)
+        _ws[key] = torch.zeros(34 * BN_WS_MAX_C + 8, device=dev, dtype=torch.float64)
     return _ws[key]
 
 
 def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5, res=None, relu=False):
     C = x.shape[-1]
+    assert C <= BN_WS_MAX_C
     M = x.numel() // C
     y = torch.empty_like(x)
     mean = torch.empty(C, device=x.device, dtype=torch.float32)
     rstd = torch.empty(C, device=x.device, dtype=torch.float32)
     lib().bn_train_fwd(_p(x), _p(y), M, C, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
                        momentum, eps, _p(mean), _p(rstd), _p(res), int(relu), _p(_bn_ws(x.device)), _st())
+    if M <= BN_SMALL_ROWS:
+        lib().launches -= 1
     return y, mean, rstd
 
 
@@ -219,11 +259,14 @@ def bn_eval_fwd(x, gamma, beta, running_mean, running_var, eps=1e-5, res=None, r
 
 def bn_train_bwd(dy, x, yout, mean, rstd, gamma, dgamma, dbeta, want_dres=False):
     C = x.shape[-1]
+    assert C <= BN_WS_MAX_C
     M = x.numel() // C
     dx = torch.empty_like(x)
     dres = torch.empty_like(x) if want_dres else None
     lib().bn_train_bwd(_p(dy), _p(x), _p(yout), _p(mean), _p(rstd), _p(gamma), M, C, _p(dx), _p(dres),
                        _p(dgamma), _p(dbeta), _p(_bn_ws(x.device)), _st())
+    if M <= BN_SMALL_ROWS:
+        lib().launches -= 1
     return dx, dres
 
 

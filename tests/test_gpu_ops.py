@@ -59,6 +59,32 @@ def test_conv_fwd_dgrad_wgrad(geom, tf32):
     close(dw.permute(0, 3, 1, 2), wr.grad, tol)
 
 
+@pytest.mark.parametrize("C", [3, 2])
+def test_stem_conv_as_im2col_tensor_core_gemm(C):
+    """The 7x7/2 stems on the production path: im2col + dense TF32 GEMM (forward), split-K GEMM over the kept
+    column matrix (weight gradient, accumulated into a packed (Co, R*S*C) filter gradient through ragged tiles)."""
+    from mmfn_b200 import ops
+    N, H, Co, R = 2, 256, 64, 7
+    x = torch.randn(N, C, H, H)
+    w = torch.randn(Co, C, R, R) * (2.0 / (C * R * R)) ** 0.5
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, stride=2, padding=3)
+    dy = torch.randn_like(yr)
+    yr.backward(dy)
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    wk = w.permute(0, 2, 3, 1).contiguous().to(DEV)
+    assert ops.stem_uses_im2col(xn, wk)
+    y, col, w_pad = ops.conv2d_fwd_im2col(xn, wk, 2, 3)
+    close(y.permute(0, 3, 1, 2), yr, 3e-3)
+    assert col.shape == (N * 128 * 128, (R * R * C + 31) // 32 * 32)
+    assert torch.count_nonzero(col[:, R * R * C:]).item() == 0
+    y2, _, w_pad2 = ops.conv2d_fwd_im2col(xn, wk, 2, 3, w_pad)          # re-used padded filter buffer
+    assert w_pad2 is w_pad and torch.equal(y2, y)
+    dw = torch.ones_like(wk)                                             # accumulates on top of existing gradient
+    ops.conv2d_wgrad_im2col_(dy.permute(0, 2, 3, 1).contiguous().to(DEV), col, dw)
+    close(dw.permute(0, 3, 1, 2) - 1.0, wr.grad, 3e-3)
+
+
 @pytest.mark.parametrize("C,T", [(64, 192), (128, 192), (256, 192), (512, 256)])
 def test_linear_gemms_and_epilogues_tf32(C, T):
     """qkv / proj / mlp GEMM shapes of one fusion-transformer block, forward and both backward products."""
@@ -123,7 +149,9 @@ def test_attention_products_on_strided_heads(C, T):
 
 def test_batchnorm_train_forward_backward():
     from mmfn_b200 import ops
-    for (N, H, C) in [(4, 32, 128), (16, 8, 512), (2, 64, 64)]:
+    # M = N*H*H <= 4096 rows: single-launch kernel; larger: two launches whose scratch must come back zeroed (the
+    # big shapes run back to back on one stream); C = 96 exercises the non-power-of-two channel-quad indexing
+    for (N, H, C) in [(4, 32, 128), (16, 8, 512), (2, 64, 64), (3, 72, 96), (2, 64, 64)]:
         x = torch.randn(N, C, H, H) * 2 + 0.5
         res = torch.randn(N, C, H, H)
         bn = torch.nn.BatchNorm2d(C).train()
