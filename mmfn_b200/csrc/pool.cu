@@ -38,29 +38,35 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
   }
 }
 
+// 4 channels per thread (C % 4 == 0): float4 loads, the four argmax taps packed into one 32-bit store
 __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ idx,
                                    int B, int H, int W, int C, int Ho, int Wo) {
-  int64_t n = (int64_t)B * Ho * Wo * C;
+  const int C4 = C >> 2;
+  const int64_t n = (int64_t)B * Ho * Wo * C4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C);
-    int64_t t = i / C;
-    int wo = (int)(t % Wo); t /= Wo;
-    int ho = (int)(t % Ho);
-    int b = (int)(t / Ho);
-    float best = -INFINITY;
-    int bi = -1;
+    const int cq = (int)(i % C4);
+    const int t = (int)(i / C4);                  // (b, ho, wo) flattened: < 2^31 pixels
+    const int wo = t % Wo, t2 = t / Wo;
+    const int ho = t2 % Ho, b = t2 / Ho;
+    float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int bi[4] = {-1, -1, -1, -1};
+#pragma unroll
     for (int r = 0; r < 3; ++r) {
-      int h = ho * 2 - 1 + r;
+      const int h = ho * 2 - 1 + r;
       if (h < 0 || h >= H) continue;
-      for (int s = 0; s < 3; ++s) {
-        int w = wo * 2 - 1 + s;
+#pragma unroll
+      for (int sx = 0; sx < 3; ++sx) {
+        const int w = wo * 2 - 1 + sx;
         if (w < 0 || w >= W) continue;
-        float v = __ldg(x + (((int64_t)b * H + h) * W + w) * C + c);
-        if (bi < 0 || v > best || v != v) { best = v; bi = r * 3 + s; }
+        const float4 v4 = __ldg(reinterpret_cast<const float4*>(x + (((int64_t)b * H + h) * W + w) * C) + cq);
+        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (bi[k] < 0 || v[k] > best[k] || v[k] != v[k]) { best[k] = v[k]; bi[k] = r * 3 + sx; }
       }
     }
-    y[i] = best;
-    idx[i] = (uint8_t)bi;
+    *reinterpret_cast<float4*>(y + (i << 2)) = make_float4(best[0], best[1], best[2], best[3]);
+    *reinterpret_cast<uint32_t*>(idx + (i << 2)) = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
   }
 }
 
@@ -70,11 +76,10 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* 
   const int C4 = C >> 2;
   int64_t n = (int64_t)B * H * W * C4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C4) * 4;
-    int64_t t = i / C4;
-    int w = (int)(t % W); t /= W;
-    int h = (int)(t % H);
-    int b = (int)(t / H);
+    const int c = (int)(i % C4) * 4;
+    const int t = (int)(i / C4);                  // (b, h, w) flattened: < 2^31 pixels
+    const int w = t % W, t2 = t / W;
+    const int h = t2 % H, b = t2 / H;
     float g[4] = {0.f, 0.f, 0.f, 0.f};
     int ho_lo = h / 2, ho_hi = (h + 1) / 2;     // windows ho with ho*2-1 <= h <= ho*2+1
     int wo_lo = w / 2, wo_hi = (w + 1) / 2;
@@ -217,54 +222,76 @@ __global__ void upsample_add_fwd_kernel(const float* __restrict__ feat, const fl
   }
 }
 
-// dtok[b, m*64+p, c] = sum_{h,w} wy(p|h) wx(p|w) dA[b,h,w,c]
-__global__ void upsample_add_bwd_kernel(const float* __restrict__ dA, float* __restrict__ dtok,
-                                        int m, int T, int B, int H, int W, int C, int align) {
-  float sh = bilinear_scale(8, H, align), sw = bilinear_scale(8, W, align);
-  int64_t n = (int64_t)B * 64 * C;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C);
-    int64_t t2 = i / C;
-    int p = (int)(t2 % 64);
-    int b = (int)(t2 / 64);
-    int py = p >> 3, px = p & 7;
-    int hlo = 0, hhi = H - 1, wlo = 0, whi = W - 1;
-    // conservative window of output pixels whose two source taps can include anchor (py, px); the half-pixel rule
-    // shifts the window by up to 0.5 / scale pixels.  Exact weights come from bilinear_src below.
-    if (sh > 0.f) { int mg = align ? 1 : (int)ceilf(0.5f / sh) + 1; hlo = max(0, (int)floorf((py - 1) / sh) - mg); hhi = min(H - 1, (int)ceilf((py + 1) / sh) + mg); }
-    if (sw > 0.f) { int mg = align ? 1 : (int)ceilf(0.5f / sw) + 1; wlo = max(0, (int)floorf((px - 1) / sw) - mg); whi = min(W - 1, (int)ceilf((px + 1) / sw) + mg); }
-    float acc = 0.f;
-    for (int h = hlo; h <= hhi; ++h) {
-      int h0, h1; float a0, a1;
+// dtok[b, m*64+p, c] = sum_{h,w} wy(p|h) wx(p|w) dA[b,h,w,c].
+// One CTA per (sample, anchor p): the (<= 2/scale + 3)^2 output pixels that can touch the anchor are spread over
+// 256 / (C/4) pixel lanes, 4 channels per thread (float4 loads), then reduced through shared memory.
+__global__ void __launch_bounds__(256)
+upsample_add_bwd_kernel(const float* __restrict__ dA, float* __restrict__ dtok,
+                        int m, int T, int B, int H, int W, int C, int align) {
+  extern __shared__ float4 red4[];                           // [lanes][C4]
+  const float sh = bilinear_scale(8, H, align), sw = bilinear_scale(8, W, align);
+  const int C4 = C >> 2;
+  const int b = blockIdx.x >> 6, p = blockIdx.x & 63;
+  const int py = p >> 3, px = p & 7;
+  const int lanes = blockDim.x / C4;                         // host guarantees >= 1
+  const int cq = threadIdx.x % C4, lane = threadIdx.x / C4;
+  int hlo = 0, hhi = H - 1, wlo = 0, whi = W - 1;
+  // conservative window of output pixels whose two source taps can include anchor (py, px); the half-pixel rule
+  // shifts the window by up to 0.5 / scale pixels.  Exact weights come from bilinear_src below.
+  if (sh > 0.f) { int mg = align ? 1 : (int)ceilf(0.5f / sh) + 1; hlo = max(0, (int)floorf((py - 1) / sh) - mg); hhi = min(H - 1, (int)ceilf((py + 1) / sh) + mg); }
+  if (sw > 0.f) { int mg = align ? 1 : (int)ceilf(0.5f / sw) + 1; wlo = max(0, (int)floorf((px - 1) / sw) - mg); whi = min(W - 1, (int)ceilf((px + 1) / sw) + mg); }
+  const int nw = whi - wlo + 1, npx = (hhi - hlo + 1) * nw;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane < lanes) {
+    for (int i = lane; i < npx; i += lanes) {
+      const int h = hlo + i / nw, w = wlo + i % nw;
+      int h0, h1, w0, w1; float a0, a1, b0, b1;
       bilinear_src(h, sh, 8, h0, h1, a0, a1, align);
-      float wy = (h0 == py ? a0 : 0.f) + (h1 == py ? a1 : 0.f);
-      if (wy == 0.f) continue;
-      for (int w = wlo; w <= whi; ++w) {
-        int w0, w1; float b0, b1;
-        bilinear_src(w, sw, 8, w0, w1, b0, b1, align);
-        float wx = (w0 == px ? b0 : 0.f) + (w1 == px ? b1 : 0.f);
-        if (wx == 0.f) continue;
-        acc += wy * wx * __ldg(dA + (((int64_t)b * H + h) * W + w) * C + c);
-      }
+      bilinear_src(w, sw, 8, w0, w1, b0, b1, align);
+      const float wy = (h0 == py ? a0 : 0.f) + (h1 == py ? a1 : 0.f);
+      const float wx = (w0 == px ? b0 : 0.f) + (w1 == px ? b1 : 0.f);
+      const float wt = wy * wx;
+      if (wt == 0.f) continue;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(dA + (((int64_t)b * H + h) * W + w) * C) + cq);
+      acc.x += wt * g.x; acc.y += wt * g.y; acc.z += wt * g.z; acc.w += wt * g.w;
     }
-    dtok[((int64_t)b * T + m * 64 + p) * C + c] = acc;
+    red4[lane * C4 + cq] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < C4) {
+    for (int l = 1; l < lanes; ++l) {
+      const float4 t = red4[l * C4 + cq];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    *reinterpret_cast<float4*>(dtok + ((int64_t)b * T + m * 64 + p) * C + cq * 4) = acc;
   }
 }
 
-// fused[b,c] = sum_m mean_p (feat_m[b,p,c] + tok[b, m*64+p, c]),  P = 64 positions
-__global__ void pool_sum_fwd_kernel(FeatPtrs f, int nmod, const float* __restrict__ tok, int B, int C,
-                                    float* __restrict__ fused) {
-  int n = B * C, T = nmod * 64;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    int c = i % C, b = i / C;
-    float tot = 0.f;
+// fused[b,c] = sum_m mean_p (feat_m[b,p,c] + tok[b, m*64+p, c]),  P = 64 positions.
+// One CTA per (sample, 32-channel group): 32 channel lanes x 8 position lanes, 8 loads in flight per thread.
+__global__ void __launch_bounds__(256)
+pool_sum_fwd_kernel(FeatPtrs f, int nmod, const float* __restrict__ tok, int B, int C,
+                    float* __restrict__ fused) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int groups = (C + 31) / 32;
+  const int b = blockIdx.x / groups, c = (blockIdx.x % groups) * 32 + cx;
+  const int T = nmod * 64;
+  float s = 0.f;
+  if (c < C) {
     for (int m = 0; m < nmod; ++m) {
-      float s = 0.f;
-      for (int p = 0; p < 64; ++p)
-        s += __ldg(f.p[m] + ((int64_t)b * 64 + p) * C + c) + __ldg(tok + ((int64_t)b * T + m * 64 + p) * C + c);
-      tot += s * (1.0f / 64.0f);
+      const float* fm = f.p[m] + (int64_t)b * 64 * C + c;
+      const float* tm = tok + ((int64_t)b * T + m * 64) * C + c;
+#pragma unroll
+      for (int p = py; p < 64; p += 8) s += __ldg(fm + (int64_t)p * C) + __ldg(tm + (int64_t)p * C);
     }
-    fused[i] = tot;
+  }
+  red[py][cx] = s;
+  __syncthreads();
+  if (py == 0 && c < C) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) s += red[i][cx];
+    fused[(int64_t)b * C + c] = s * (1.0f / 64.0f);
   }
 }
 
@@ -316,9 +343,10 @@ MMFN_API int mmfn_transpose_f32(const float* in, float* out, int nb, int R, int 
 
 MMFN_API int mmfn_maxpool3x3s2_fwd(const float* x, float* y, uint8_t* idx, int B, int H, int W, int C,
                                    cudaStream_t stream) {
-  MMFN_CHECK_ARG(x && y && idx && B > 0 && H > 0 && W > 0 && C > 0, "maxpool_fwd: bad args");
+  MMFN_CHECK_ARG(x && y && idx && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "maxpool_fwd: bad args (C % 4 == 0)");
+  MMFN_CHECK_ARG((((uintptr_t)x | (uintptr_t)y) & 15) == 0 && ((uintptr_t)idx & 3) == 0, "maxpool_fwd: alignment");
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  maxpool_fwd_kernel<<<grid_1d((int64_t)B * Ho * Wo * C, 256), 256, 0, stream>>>(x, y, idx, B, H, W, C, Ho, Wo);
+  maxpool_fwd_kernel<<<grid_1d((int64_t)B * Ho * Wo * (C / 4), 256), 256, 0, stream>>>(x, y, idx, B, H, W, C, Ho, Wo);
   return mmfn_launch_status("maxpool_fwd");
 }
 
@@ -377,7 +405,8 @@ MMFN_API int mmfn_upsample_add_fwd(const float* feat, const float* tokens, float
 MMFN_API int mmfn_upsample_add_bwd(const float* dA, float* dtokens, int m, int T, int B, int H, int W, int C,
                                    int align_corners, cudaStream_t stream) {
   MMFN_CHECK_ARG(dA && dtokens && B > 0 && H >= 8 && W >= 8 && C > 0 && m >= 0 && (m + 1) * 64 <= T, "upsample_add_bwd: bad args");
-  upsample_add_bwd_kernel<<<grid_1d((int64_t)B * 64 * C, 128), 128, 0, stream>>>(dA, dtokens, m, T, B, H, W, C, align_corners);
+  MMFN_CHECK_ARG(C % 4 == 0 && C <= 1024 && (((uintptr_t)dA | (uintptr_t)dtokens) & 15) == 0, "upsample_add_bwd: C % 4 == 0, C <= 1024, 16-byte aligned");
+  upsample_add_bwd_kernel<<<B * 64, 256, 256 * sizeof(float4), stream>>>(dA, dtokens, m, T, B, H, W, C, align_corners);
   return mmfn_launch_status("upsample_add_bwd");
 }
 
@@ -385,7 +414,7 @@ MMFN_API int mmfn_pool_sum_fwd(const float* f0, const float* f1, const float* f2
                                const float* tokens, int B, int C, float* fused, cudaStream_t stream) {
   MMFN_CHECK_ARG(nmod >= 1 && nmod <= 4 && f0 && tokens && fused && B > 0 && C > 0, "pool_sum_fwd: bad args");
   FeatPtrs f{{f0, f1, f2, f3}};
-  pool_sum_fwd_kernel<<<grid_1d((int64_t)B * C, 128), 128, 0, stream>>>(f, nmod, tokens, B, C, fused);
+  pool_sum_fwd_kernel<<<B * ((C + 31) / 32), 256, 0, stream>>>(f, nmod, tokens, B, C, fused);
   return mmfn_launch_status("pool_sum_fwd");
 }
 

@@ -31,21 +31,26 @@ IMAGENET_STD = (0.229, 0.224, 0.225)
 # --------------------------------------------------------------------------- building blocks
 class _Aux:
     """Weight-gradient side streams.  In backward only the data-gradient chain is sequential; every
-    weight/bias gradient (wgrad conv, dW GEMM, bias column sum) is a leaf.  They are issued on an
-    auxiliary stream paired with the current one, so they overlap the dgrad chain (as parallel graph
-    branches once captured).  Inputs are kept alive until join_all() -- no allocator reuse hazards."""
+    weight/bias gradient (wgrad conv, dW GEMM, bias column sum, LayerNorm parameter sums) is a LEAF of the
+    dependency graph.  Leaves are issued round-robin on a small pool of auxiliary streams paired with the current
+    one, so they overlap the dgrad chain and each other (parallel graph branches once captured) -- one FIFO
+    stream would chain ~65 us of leaf work per transformer layer behind a ~50 us critical path.  Work the
+    critical path re-joins soon (fork(): attention dK / dV, filter flips) gets its own stream pair so it never
+    queues behind leaves.  Inputs are kept alive until join_all() -- no allocator reuse hazards."""
     enabled = True
-    streams, used, keep = {}, {}, []
+    N_LEAF, N_FORK = 4, 2
+    pools, used, keep = {}, {}, []
 
     @classmethod
-    def run(cls, fn, *tensors):
-        if not cls.enabled:
-            fn()
-            return
-        prim = torch.cuda.current_stream()
-        aux = cls.streams.get(prim.cuda_stream)
-        if aux is None:
-            aux = cls.streams[prim.cuda_stream] = torch.cuda.Stream(device=prim.device)
+    def _pool(cls, prim):
+        pool = cls.pools.get(prim.cuda_stream)
+        if pool is None:
+            mk = lambda n: [torch.cuda.Stream(device=prim.device) for _ in range(n)]
+            pool = cls.pools[prim.cuda_stream] = {"leaf": mk(cls.N_LEAF), "fork": mk(cls.N_FORK), "i": 0, "j": 0}
+        return pool
+
+    @classmethod
+    def _issue(cls, aux, prim, fn, tensors):
         ev = torch.cuda.Event()
         ev.record(prim)
         aux.wait_event(ev)
@@ -55,13 +60,27 @@ class _Aux:
         cls.used[aux.cuda_stream] = aux
 
     @classmethod
+    def run(cls, fn, *tensors):
+        if not cls.enabled:
+            fn()
+            return
+        prim = torch.cuda.current_stream()
+        pool = cls._pool(prim)
+        aux = pool["leaf"][pool["i"] % cls.N_LEAF]
+        pool["i"] += 1
+        cls._issue(aux, prim, fn, tensors)
+
+    @classmethod
     def fork(cls, fn, *tensors):
-        """Like run(), but returns an event the caller's stream can wait on (local fork/join)."""
+        """Like run(), on the fork streams, and returns an event the caller's stream can wait on (local fork/join)."""
         if not cls.enabled:
             fn()
             return None
-        cls.run(fn, *tensors)
-        aux = cls.streams[torch.cuda.current_stream().cuda_stream]
+        prim = torch.cuda.current_stream()
+        pool = cls._pool(prim)
+        aux = pool["fork"][pool["j"] % cls.N_FORK]
+        pool["j"] += 1
+        cls._issue(aux, prim, fn, tensors)
         ev = torch.cuda.Event()
         ev.record(aux)
         return ev
