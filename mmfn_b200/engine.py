@@ -42,18 +42,46 @@ class BatchStager:
         self.dev = torch.empty(off, dtype=torch.uint8, device=self.device)
         self.dev_views = self._views(self.dev)
         self.flip = 0
+        self._copy_stream = self._ready = self._consumed = None
 
     def _views(self, buf):
         return {name: buf[off: off + nbytes].view(dtype).view(shape) for name, dtype, shape, off, nbytes in self.layout}
 
+    def pack(self, batch, slot):
+        """Collate-side work (what a DataLoader worker + pin_memory thread do in the reference): host dict ->
+        pinned buffer `slot`."""
+        hv = self._views(self.host[slot])
+        for name, dtype, _, _, _ in self.layout:
+            hv[name].copy_(batch[name].to(dtype))
+
     def stage(self, batch):
         """host dict -> device dict (views of the fixed device buffer); asynchronous on the current stream."""
         self.flip ^= 1
-        h = self.host[self.flip]
-        hv = self._views(h)
-        for name, dtype, _, _, _ in self.layout:
-            hv[name].copy_(batch[name].to(dtype))
-        self.dev.copy_(h, non_blocking=True)
+        self.pack(batch, self.flip)
+        self.dev.copy_(self.host[self.flip], non_blocking=True)
+        return self.dev_views
+
+    # ---- double-buffered input feed: the H2D copy of step i+1 rides a copy stream under step i's kernels ----
+    def prefetch(self, slot):
+        """Start the ONE packed H2D copy of pinned buffer `slot` into the device staging buffer (copy stream)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self.dev_next = torch.empty_like(self.dev)
+        cs = self._copy_stream
+        if self._consumed is not None:
+            cs.wait_event(self._consumed)              # the previous commit() has finished reading dev_next
+        with torch.cuda.stream(cs):
+            self.dev_next.copy_(self.host[slot], non_blocking=True)
+            self._ready = torch.cuda.Event()
+            self._ready.record(cs)
+
+    def commit(self):
+        """Make the prefetched batch the current one: device-to-device copy into the fixed (graph-captured) buffer."""
+        main = torch.cuda.current_stream()
+        main.wait_event(self._ready)
+        self.dev.copy_(self.dev_next, non_blocking=True)
+        self._consumed = torch.cuda.Event()
+        self._consumed.record(main)
         return self.dev_views
 
 

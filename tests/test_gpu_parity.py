@@ -176,6 +176,71 @@ def test_engine_steps_match_oracle_adamw(dev):
     assert torch.equal(msd[k].cpu(), sd[k])
 
 
+def test_edge_case_inputs_match_oracle(dev):
+    """Degenerate frames the reference data can contain: a single valid lane next to a full lane set (masking of
+    the padded lanes), a radar frame with no returns (all-zero rows -> every GAT edge masked), and a LiDAR sweep with
+    no point inside the BEV grid.  Exact-fp32 path against the CPU oracle."""
+    from mmfn_b200 import ops
+    from mmfn_b200.engine import TrainEngine
+    B = 2
+    cfg, model, sd, b = _setup(dev, B, tf32=False)
+    b["lane_num"] = torch.tensor([1, b["lane"].shape[1]], dtype=torch.int32)
+    b["lane"][0, 1:] = 0                                    # pad_sequence zero padding (data_utils.py:42-48)
+    b["radar"][0] = 0
+    b["radar_adj"][0] = 0
+    b["points"][1, :, 0] = 100.0                            # every point outside [-16, 16]
+    eng = TrainEngine(model, lr=1e-4)
+    db = {k: v.to(dev) for k, v in b.items()}
+    lidar = ops.bev_scatter(db["points"])
+    lidar_ref = torch.from_numpy(np.stack([bev_oracle.lidar_to_histogram_features(p[:, :3].numpy()) for p in b["points"]]))
+    assert torch.equal(lidar.cpu(), lidar_ref) and lidar_ref[1].abs().sum() == 0
+    loss = eng.forward_backward(db)
+    inputs = (b["rgb_u8"].float(), lidar_ref, b["lane"], b["lane_num"], b["radar"], b["radar_adj"],
+              b["target_point"], b["velocity"])
+    oloss, opred, ograds = mmfn_oracle.train_step({k: v.clone() for k, v in sd.items()}, cfg,
+                                                  dict(inputs=inputs, gt_waypoints=b["gt_waypoints"]))
+    assert (eng.last_pred.cpu() - opred).abs().mean().item() < 2e-4
+    assert abs(loss.item() - oloss.item()) < 2e-4
+    params = dict(model.named_parameters())
+    dot = n1 = n2 = 0.0
+    for k, g in ograds.items():
+        if g is None:
+            continue
+        got = model.store.torch_view(k, grad=True).detach().cpu().double()
+        assert torch.isfinite(got).all(), k
+        dot += (got * g.double()).sum().item(); n1 += got.pow(2).sum().item(); n2 += g.double().pow(2).sum().item()
+    assert dot / (n1 ** 0.5 * n2 ** 0.5) > 0.999
+
+
+def test_config2_full_size_properties(dev):
+    """BASELINE configs[1] at its full size (B=16, production TF32 path, dropout off): properties that need no
+    CPU oracle run -- finite outputs, bit-exact BEV for sampled frames, and batch-permutation equivariance (train-mode
+    BatchNorm statistics are order-invariant, so permuting the 16 frames must permute the waypoints and leave the
+    loss and the summed gradients unchanged up to accumulation order)."""
+    from mmfn_b200 import ops
+    from mmfn_b200.engine import TrainEngine
+    B = 16
+    cfg, model, sd, b = _setup(dev, B, tf32=True)
+    eng = TrainEngine(model, lr=1e-4)
+    db = {k: v.to(dev) for k, v in b.items()}
+    lidar = ops.bev_scatter(db["points"])
+    for i in (0, 15):
+        assert np.array_equal(lidar[i].cpu().numpy(), bev_oracle.lidar_to_histogram_features(b["points"][i, :, :3].numpy()))
+    loss = eng.forward_backward(db).item()
+    pred = eng.last_pred.clone()
+    grad = model.store.flat_grad[: model.store.n_active].clone()
+    assert np.isfinite(loss) and torch.isfinite(pred).all() and torch.isfinite(grad).all()
+    assert pred.shape == (B, 4, 2) and grad.abs().sum().item() > 0
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(3))
+    dbp = {k: v[perm.to(dev)].contiguous() for k, v in db.items()}
+    loss_p = eng.forward_backward(dbp).item()
+    assert abs(loss_p - loss) < 1e-4 * max(1.0, abs(loss))
+    assert (eng.last_pred - pred[perm.to(dev)]).abs().max().item() < 2e-3
+    grad_p = model.store.flat_grad[: model.store.n_active]
+    cos = torch.dot(grad_p.double(), grad.double()) / (grad_p.double().norm() * grad.double().norm())
+    assert cos.item() > 0.999, cos.item()
+
+
 def test_state_dict_interchange(dev):
     from mmfn_b200.model_rad import MMFN
     keys = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "state_dict_keys.json")))
