@@ -215,3 +215,22 @@ MMFN_API int mmfn_adamw_step(float* p, const float* g, float* m, float* v, int64
                                                            beta1, beta2, eps, weight_decay, state, grad_scale);
   return mmfn_launch_status("adamw");
 }
+
+// The two halves of mmfn_adamw_step for a bucketed optimizer: advance the step count / bias corrections ONCE per
+// step, then apply the update to any number of disjoint parameter ranges (each as soon as its gradients are final).
+MMFN_API int mmfn_adamw_advance(float* state, float beta1, float beta2, cudaStream_t stream) {
+  MMFN_CHECK_ARG(state, "adamw_advance: null state");
+  adamw_advance_kernel<<<1, 1, 0, stream>>>(state, beta1, beta2);
+  return mmfn_launch_status("adamw_advance");
+}
+
+MMFN_API int mmfn_adamw_apply(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, const float* state, float grad_scale,
+                              cudaStream_t stream) {
+  MMFN_CHECK_ARG(p && g && m && v && state && n >= 0 && n % 4 == 0, "adamw_apply: n must be a multiple of 4");
+  MMFN_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adamw_apply: buffers must be 16B aligned");
+  if (n > 0)
+    adamw_kernel<<<grid_1d(n / 4, 256), 256, 0, stream>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v, n / 4, lr,
+                                                           beta1, beta2, eps, weight_decay, state, grad_scale);
+  return mmfn_launch_status("adamw_apply");
+}

@@ -140,8 +140,10 @@ class TrainEngine:
 
     # ---- CUDA-graph schedule -----------------------------------------------------------------
     def capture(self, static_batch, warmup=2):
-        """Capture forward+backward on `static_batch` (fixed device tensors, e.g. BatchStager.dev_views).
-        Later steps refill those tensors in place and call step_graph()."""
+        """Capture forward+backward on `static_batch` (fixed device tensors, e.g. BatchStager.dev_views) as TWO graphs
+        split where the early gradient bucket (head, transformer4, radar encoder, layer4 of every trunk: the
+        contiguous range [n_late, n_active) of the flat buffer) is final, so that its all-reduce and AdamW update run
+        on a side stream under the second graph.  Later steps refill the static tensors in place and call step_graph()."""
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -149,19 +151,58 @@ class TrainEngine:
                 self.step(static_batch)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
+        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        pool = torch.cuda.graph_pool_handle()
         l0 = lib().launches
-        with torch.cuda.graph(g):
-            self._graph_loss = self.forward_backward(static_batch)
-            self._graph_pred = self.last_pred
+        cap = torch.cuda.Stream()
+        cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cap):
+            ga.capture_begin(pool=pool)
+
+            def split():
+                ga.capture_end()
+                gb.capture_begin(pool=pool)
+            self.net.mid_hook = split
+            try:
+                self._graph_loss = self.forward_backward(static_batch)
+                self._graph_pred = self.last_pred
+            finally:
+                self.net.mid_hook = None
+            gb.capture_end()
+        torch.cuda.current_stream().wait_stream(cap)
+        torch.cuda.synchronize()
         self.graph_launches = lib().launches - l0
-        self._graph = g
-        return g
+        self._graph = (ga, gb)
+        self._comm = torch.cuda.Stream()
+        return self._graph
+
+    def _bucket_update(self, lo, hi):
+        """all-reduce (data parallel) + AdamW of the flat range [lo, hi) on the current stream"""
+        if hi <= lo:
+            return
+        g = self.g_active[lo:hi]
+        parallel.allreduce_sum_(g, self.pg)
+        ops.adamw_apply_(self.p_active[lo:hi], g, self.m[lo:hi], self.v[lo:hi], self.state, self.lr, self.betas[0],
+                         self.betas[1], self.eps, self.wd, grad_scale=1.0 / self.world)
 
     def step_graph(self):
-        """Replay the captured forward+backward, then all-reduce + AdamW.  Returns the loss tensor."""
-        self._graph.replay()
+        """Replay the captured step.  Order on the device: graph A (zero grads, BEV, forward, backward down to the
+        last fusion stage) -> [side stream: early bucket all-reduce + AdamW] || graph B (rest of backward) ->
+        late bucket all-reduce + AdamW.  Returns the loss tensor."""
+        ga, gb = self._graph
+        main = torch.cuda.current_stream()
+        ops.adamw_advance_(self.state, self.betas[0], self.betas[1])
+        ga.replay()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._comm.wait_event(ev)
+        with torch.cuda.stream(self._comm):
+            self._bucket_update(self.st.n_late, self.st.n_active)
+            done = torch.cuda.Event()
+            done.record(self._comm)
+        gb.replay()
+        self._bucket_update(0, self.st.n_late)
+        main.wait_event(done)
         lib().launches += self.graph_launches
         self.last_pred = self._graph_pred
-        self.optimizer_step()
         return self._graph_loss

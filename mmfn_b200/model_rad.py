@@ -40,6 +40,7 @@ class _Aux:
     enabled = True
     N_LEAF, N_FORK = 4, 2
     pools, used, keep = {}, {}, []
+    epoch = 0            # bumped by join_all(): fork events of earlier epochs are already ordered before the caller
 
     @classmethod
     def _pool(cls, prim):
@@ -83,13 +84,13 @@ class _Aux:
         cls._issue(aux, prim, fn, tensors)
         ev = torch.cuda.Event()
         ev.record(aux)
-        return ev
+        return (ev, cls.epoch)
 
-    @staticmethod
-    def wait(*events):
-        for ev in events:
-            if ev is not None:
-                torch.cuda.current_stream().wait_event(ev)
+    @classmethod
+    def wait(cls, *events):
+        for e in events:
+            if e is not None and e[1] == cls.epoch:       # older epochs were joined (possibly in an earlier graph capture)
+                torch.cuda.current_stream().wait_event(e[0])
 
     @classmethod
     def join_all(cls):
@@ -100,6 +101,7 @@ class _Aux:
             main.wait_event(ev)
         cls.used.clear()
         cls.keep.clear()
+        cls.epoch += 1
 
 
 class ConvBN:
@@ -597,6 +599,16 @@ class _Net:
         fused = ops.pool_sum_fwd(feats, tok)
         return self.head.fwd(fused, target_point)
 
+    mid_hook = None
+
+    def _early_bucket_done(self):
+        """Backward has passed the last fusion stage: every gradient of params.is_early_bucket() is final once the
+        leaf streams are joined.  The engine hooks in here to split the captured step into two graphs and start the
+        early bucket's all-reduce + AdamW under the rest of backward."""
+        if self.mid_hook is not None:
+            _Aux.join_all()
+            self.mid_hook()
+
     def backward(self, dpred):
         dfused = self.head.bwd(dpred)
         nmod = 4 if self.gat is not None else 3
@@ -617,6 +629,8 @@ class _Net:
             if s == 2 and self.gat is not None:
                 branches.append(lambda: self.gat.bwd(dfe[3]))  # same side stream as its forward
             dimg, dlid, dmp = self._parallel(*branches)[:3]
+            if s == 2:
+                self._early_bucket_done()
             self.gpts[s].bwd(dtok, [dimg, dlid, dmp])
         self._parallel(lambda: self.img_stem.bwd(self.img_layers[0].bwd(dimg)),
                        lambda: self.lid_stem.bwd(self.lid_layers[0].bwd(dlid)),

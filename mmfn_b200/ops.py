@@ -584,3 +584,13 @@ def l1_loss(pred, gt, gscale=1.0, want_grad=True):
 def adamw_step_(p, g, m, v, state, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, grad_scale=1.0):
     lib().adamw_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay,
                      _p(state), grad_scale, _st())
+
+
+def adamw_advance_(state, beta1=0.9, beta2=0.999):
+    lib().adamw_advance(_p(state), beta1, beta2, _st())
+
+
+def adamw_apply_(p, g, m, v, state, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, grad_scale=1.0):
+    """AdamW on one parameter range; the step count in `state` must already be advanced (adamw_advance_)."""
+    lib().adamw_apply(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay,
+                      _p(state), grad_scale, _st())

@@ -129,6 +129,17 @@ def is_unused(key, variant="rad"):
     return key.startswith(p) and (key[len(p):].startswith(("conv1.", "bn1.", "layer1.")))
 
 
+EARLY_BUCKET_PREFIXES = ("encoder.image_encoder.features.layer4.", "encoder.img_map_encoder.features.layer4.",
+                         "encoder.lidar_encoder._model.layer4.", "encoder.radar_encoder.", "encoder.transformer4.",
+                         "join.", "decoder.", "output.")
+
+
+def is_early_bucket(key):
+    """Parameters whose gradients are complete once backward has passed the last fusion stage (model_rad.py:577-611
+    in reverse): the waypoint head, transformer4, the radar GAT and layer4 of the three ResNets."""
+    return key.startswith(EARLY_BUCKET_PREFIXES)
+
+
 def _numel(shape):
     n = 1
     for s in shape:
@@ -146,11 +157,17 @@ class ParamStore:
         shapes = dict(fkeys)
         self.offsets = {}
         off = 0
-        for pass_unused in (False, True):
-            if pass_unused:
+        # flat layout: [late bucket | early bucket | never-used].  "early" = parameters whose gradients are final
+        # first in backward (head, transformer4, radar encoder, layer4 of every trunk): they form ONE contiguous
+        # range [n_late, n_active), so their all-reduce + AdamW can start while the rest of backward still runs.
+        for group in ("late", "early", "unused"):
+            if group == "early":
+                self.n_late = off
+            if group == "unused":
                 self.n_active = off
             for k in order:
-                if is_unused(k, variant) != pass_unused:
+                g = "unused" if is_unused(k, variant) else ("early" if is_early_bucket(k) else "late")
+                if g != group:
                     continue
                 self.offsets[k] = off
                 off += (_numel(shapes[k]) + 3) // 4 * 4

@@ -64,6 +64,8 @@ class _NetTF(_Net):
                     return g
                 return run
             dimg, dlid = self._parallel(trunk(self.img_layers, dimg, 0), trunk(self.lid_layers, dlid, 1))
+            if s == 2:
+                self._early_bucket_done()
             self.gpts[s].bwd(dtok, [dimg, dlid])
         self._parallel(lambda: self.img_stem.bwd(self.img_layers[0].bwd(dimg)),
                        lambda: self.lid_stem.bwd(self.lid_layers[0].bwd(dlid)))
