@@ -27,31 +27,45 @@ bev_scatter_kernel(const float* __restrict__ pts, int n_pts, int pt_stride,
 
   const float* p = pts + (int64_t)frame * n_pts * pt_stride;
   const int x_lo = strip * ROWS;
-  for (int i = threadIdx.x; i < n_pts; i += blockDim.x) {
-    float x, y, z;
-    if (pt_stride == 4) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
-      x = v.x; y = v.y; z = v.z;
-    } else {
-      const float* q = p + (int64_t)i * pt_stride;
-      x = __ldg(q); y = __ldg(q + 1); z = __ldg(q + 2);
+  // four points per thread are requested before the first is binned: the loop is latency-bound otherwise
+  // (one dependent L2 round trip per point and thread)
+  constexpr int U = 4;
+  for (int i0 = threadIdx.x; i0 < n_pts; i0 += U * blockDim.x) {
+    float px[U], py[U], pz[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * blockDim.x;
+      px[u] = py[u] = pz[u] = __int_as_float(0x7fc00000);          // NaN: rejected below
+      if (i < n_pts) {
+        if (pt_stride == 4) {
+          float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+          px[u] = v.x; py[u] = v.y; pz[u] = v.z;
+        } else {
+          const float* q = p + (int64_t)i * pt_stride;
+          px[u] = __ldg(q); py[u] = __ldg(q + 1); pz[u] = __ldg(q + 2);
+        }
+      }
     }
-    // channel 0: z <= -2, channel 1: z > -2; NaN z matches neither.
-    bool in_chan = chan == 0 ? (z <= -2.0f) : (z > -2.0f);
-    // closed range test also rejects NaN; x*8 / y*8 are exact in fp32.
-    if (!in_chan || !(x >= -16.0f && x <= 16.0f && y >= -24.0f && y <= 8.0f)) continue;
-    int ix = (int)floorf(x * 8.0f) + 128;
-    int iy = (int)floorf(y * 8.0f) + 192;
-    ix = min(ix, GRID - 1);                        // right-most edge is inclusive
-    iy = min(iy, GRID - 1);
-    ix -= x_lo;
-    if (ix < 0 || ix >= ROWS) continue;
-    int bin = ix * GRID + iy;
-    uint32_t shift = (bin & 1) * 16;
-    // counts are clamped at 5 downstream: stop incrementing once a field reached 5 so
-    // a u16 field can never carry into its neighbour (<= 4 + blockDim.x increments).
-    if (((((volatile uint32_t*)cnt)[bin >> 1] >> shift) & 0xffffu) >= 5u) continue;
-    atomicAdd(&cnt[bin >> 1], 1u << shift);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float x = px[u], y = py[u], z = pz[u];
+      // channel 0: z <= -2, channel 1: z > -2; NaN z matches neither.
+      bool in_chan = chan == 0 ? (z <= -2.0f) : (z > -2.0f);
+      // closed range test also rejects NaN; x*8 / y*8 are exact in fp32.
+      if (!in_chan || !(x >= -16.0f && x <= 16.0f && y >= -24.0f && y <= 8.0f)) continue;
+      int ix = (int)floorf(x * 8.0f) + 128;
+      int iy = (int)floorf(y * 8.0f) + 192;
+      ix = min(ix, GRID - 1);                        // right-most edge is inclusive
+      iy = min(iy, GRID - 1);
+      ix -= x_lo;
+      if (ix < 0 || ix >= ROWS) continue;
+      int bin = ix * GRID + iy;
+      uint32_t shift = (bin & 1) * 16;
+      // counts are clamped at 5 downstream: stop incrementing once a field reached 5 so
+      // a u16 field can never carry into its neighbour (<= 4 + blockDim.x increments).
+      if (((((volatile uint32_t*)cnt)[bin >> 1] >> shift) & 0xffffu) >= 5u) continue;
+      atomicAdd(&cnt[bin >> 1], 1u << shift);
+    }
   }
   __syncthreads();
 

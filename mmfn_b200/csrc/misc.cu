@@ -87,6 +87,36 @@ __global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ c
   }
 }
 
+// Fast path for the stems (compile-time S, C): one warp per output pixel, lane l writes columns l, l+32, ... of the
+// pixel's row (fully coalesced 128-byte stores); a filter row is a contiguous run of S*C input floats, so the loads of
+// neighbouring lanes are contiguous too, and the only divisions are by compile-time constants.
+template <int S, int C>
+__global__ void __launch_bounds__(256)
+im2col_rows_kernel(const float* __restrict__ x, float* __restrict__ col, int N, int H, int W, int R,
+                   int stride, int pad, int Ho, int Wo, int Kp) {
+  constexpr int SC = S * C;
+  const int K = R * SC;
+  const int lane = threadIdx.x & 31;
+  const int npix = N * Ho * Wo;
+  const int wpg = (gridDim.x * blockDim.x) >> 5;
+  for (int pix = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pix < npix; pix += wpg) {
+    const int wo = pix % Wo, t = pix / Wo;
+    const int ho = t % Ho, n = t / Ho;
+    const int h0 = ho * stride - pad, w0 = wo * stride - pad;
+    const float* xn = x + (int64_t)n * H * W * C;
+    float* dst = col + (int64_t)pix * Kp;
+    for (int k = lane; k < Kp; k += 32) {
+      float v = 0.f;
+      if (k < K) {
+        const int r = k / SC, rem = k - r * SC;
+        const int h = h0 + r, w = w0 + rem / C;
+        if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(xn + ((int64_t)h * W + w0) * C + rem);
+      }
+      dst[k] = v;
+    }
+  }
+}
+
 // dst[r, c] (+)= src[r, c] for c < cols, between two row pitches (padded <-> packed filter matrices of the stems)
 __global__ void copy2d_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd,
                               int rows, int cols, int accum) {
@@ -293,6 +323,13 @@ MMFN_API int mmfn_im2col_nhwc(const float* x, float* col, int N, int H, int W, i
   MMFN_CHECK_ARG(x && col && N > 0 && H > 0 && W > 0 && C > 0 && R > 0 && S > 0 && stride > 0, "im2col: bad args");
   MMFN_CHECK_ARG(Kp % 4 == 0 && Kp >= R * S * C && (((uintptr_t)col) & 15) == 0, "im2col: Kp must be a multiple of 4, >= R*S*C; col 16-byte aligned");
   const int64_t n4 = (int64_t)N * Ho * Wo * (Kp / 4);
+  const int64_t npix = (int64_t)N * Ho * Wo;
+  if (S == 7 && (C == 3 || C == 2) && npix < (1ll << 31)) {
+    const int grid = grid_1d(npix * 32, 256);
+    if (C == 3) im2col_rows_kernel<7, 3><<<grid, 256, 0, stream>>>(x, col, N, H, W, R, stride, pad, Ho, Wo, Kp);
+    else im2col_rows_kernel<7, 2><<<grid, 256, 0, stream>>>(x, col, N, H, W, R, stride, pad, Ho, Wo, Kp);
+    return mmfn_launch_status("im2col_nhwc");
+  }
   im2col_kernel<<<grid_1d(n4, 256), 256, 0, stream>>>(x, col, N, H, W, C, R, S, stride, pad, Ho, Wo, R * S * C, Kp);
   return mmfn_launch_status("im2col_nhwc");
 }

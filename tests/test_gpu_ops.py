@@ -83,6 +83,11 @@ def test_stem_conv_as_im2col_tensor_core_gemm(C):
     dw = torch.ones_like(wk)                                             # accumulates on top of existing gradient
     ops.conv2d_wgrad_im2col_(dy.permute(0, 2, 3, 1).contiguous().to(DEV), col, dw)
     close(dw.permute(0, 3, 1, 2) - 1.0, wr.grad, 3e-3)
+    # generic (run-time filter geometry) column builder: 3x3 stride-1 on 4 channels
+    x4 = torch.randn(2, 4, 20, 20)
+    w4 = torch.randn(8, 4, 3, 3) * 0.2
+    y4, _, _ = ops.conv2d_fwd_im2col(x4.permute(0, 2, 3, 1).contiguous().to(DEV), w4.permute(0, 2, 3, 1).contiguous().to(DEV), 1, 1)
+    close(y4.permute(0, 3, 1, 2), F.conv2d(x4, w4, stride=1, padding=1), 3e-3)
 
 
 @pytest.mark.parametrize("C,T", [(64, 192), (128, 192), (256, 192), (512, 256)])

@@ -37,6 +37,22 @@ for (H, Cc) in [(16, 256), (64, 64)]:
 # 4. fused attention, transformer4 geometry
 qkv = torch.randn(B * 256, 3 * 512, device=dev)
 run(lambda: ops.attention_fwd(qkv, B, 256, 512, 4, 0.1, 7))
+# 4b. BatchNorm (train) forward + backward on the layer-1 map (16 x 64 x 64 x 64): reduction + apply kernels
+xb = torch.randn(B, 64, 64, 64, device=dev); g1 = torch.ones(64, device=dev); b1 = torch.zeros(64, device=dev)
+rm = torch.zeros(64, device=dev); rv = torch.ones(64, device=dev)
+yb, mean, rstd = ops.bn_train_fwd(xb, g1, b1, rm, rv, relu=True)
+dgm, dbt = torch.zeros(64, device=dev), torch.zeros(64, device=dev)
+run(lambda: ops.bn_train_fwd(xb, g1, b1, rm, rv, res=xb, relu=True))
+run(lambda: ops.bn_train_bwd(xb, xb, yb, mean, rstd, g1, dgm, dbt, True))
+# 4c. image stem: im2col + dense GEMM (forward), split-K GEMM (weight gradient)
+xs = torch.randn(B, 256, 256, 3, device=dev); ws = torch.randn(64, 7, 7, 3, device=dev) * 0.1
+ys, col, wpad = ops.conv2d_fwd_im2col(xs, ws, 2, 3)
+dws = torch.zeros_like(ws)
+run(lambda: ops.conv2d_fwd_im2col(xs, ws, 2, 3, wpad))
+run(lambda: ops.conv2d_wgrad_im2col_(ys, col, dws))
+# 4d. attention backward pieces at transformer4 geometry: softmax backward (float4)
+P = torch.softmax(torch.randn(B, 4, 256, 256, device=dev), -1); dP = torch.randn_like(P)
+run(lambda: ops.softmax_bwd(P, dP, 0.088, 0.1, 5))
 # 5. BEV scatter, 16 frames x 32768 points
 pts = torch.from_numpy(np.stack([synthetic.synth_points(1234 + i) for i in range(B)])).to(dev)
 run(lambda: ops.bev_scatter(pts))
