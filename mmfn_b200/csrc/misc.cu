@@ -12,8 +12,10 @@ __global__ void colsum_kernel(const float* __restrict__ x, int64_t ld, int64_t M
   int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
   int64_t r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
   float a = 0.f;
-  if (n < N)
+  if (n < N) {
+#pragma unroll 8
     for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) a += __ldg(x + r * ld + n);
+  }
   s[threadIdx.y][threadIdx.x] = a;
   __syncthreads();
   if (threadIdx.y == 0 && n < N) {
@@ -235,9 +237,13 @@ __global__ void radar_logsoftmax_bwd_kernel(const float* __restrict__ dy, const 
 MMFN_API int mmfn_colsum_f32(const float* x, int64_t ld, int64_t M, int N, float* out, cudaStream_t stream) {
   MMFN_CHECK_ARG(x && out && M >= 0 && N > 0 && ld >= N, "colsum: bad args");
   if (M == 0) return 0;
-  int64_t slabs = ceil_div64(M, 256);
-  if (slabs > 1024) slabs = 1024;
-  dim3 grid((N + 31) / 32, (unsigned)slabs);
+  // 64 rows (8 loads in flight per thread) per CTA unless that exceeds ~8 waves of CTAs
+  const int64_t colgroups = (N + 31) / 32;
+  int64_t slabs = ceil_div64(M, 64);
+  const int64_t cap = ceil_div64(148 * 8, colgroups);
+  if (slabs > cap) slabs = cap;
+  if (slabs > 65535) slabs = 65535;
+  dim3 grid((unsigned)colgroups, (unsigned)slabs);
   colsum_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, ld, M, N, out);
   return mmfn_launch_status("colsum");
 }

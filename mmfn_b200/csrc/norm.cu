@@ -453,8 +453,9 @@ __global__ void ln_bwd_param_kernel(const float* __restrict__ dy, const float* _
   float a = 0.f, b = 0.f;
   if (c < C) {
     const float gm = gamma[c], bt = beta[c];
+#pragma unroll 4
     for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
-      const float xh = (__ldg(x + r * C + c) - mean[r]) * rstd[r];
+      const float xh = (__ldg(x + r * C + c) - __ldg(mean + r)) * __ldg(rstd + r);
       float g = __ldg(dy + r * C + c);
       if (act) g *= act_grad(xh * gm + bt, act);
       a += g * xh;
@@ -578,8 +579,10 @@ MMFN_API int mmfn_layernorm_bwd(const float* dy, const float* x, const float* ga
     else ln_bwd_dx_kernel<4><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act, dx_drop, drop_p, drop_seed);
   }
   if (parts & 2) {
-    int64_t slabs = ceil_div64(M, 128);
-    if (slabs > 256) slabs = 256;
+    // 32 rows (4 row iterations per thread, all loads in flight) per CTA unless that exceeds ~8 waves of CTAs
+    int64_t slabs = ceil_div64(M, 32);
+    const int64_t cap = ceil_div64(148 * 8, (C + 31) / 32);
+    if (slabs > cap) slabs = cap;
     ln_bwd_param_kernel<<<dim3((C + 31) / 32, (unsigned)slabs), dim3(32, 8), 0, stream>>>(dy, x, gamma, beta, mean, rstd, dgamma, dbeta, M, C, act);
   }
   return mmfn_launch_status("layernorm_bwd");
