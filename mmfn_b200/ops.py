@@ -112,7 +112,7 @@ def conv_out_hw(H, W, R, S, stride, pad):
 def _conv_work(N, H, W, C, Co, R, S, Ho, Wo):
     """algorithmic (flops, bytes) of one conv pass: 2*MACs; input + filter + output read/written once"""
     return (2.0 * N * Ho * Wo * Co * R * S * C, 4.0 * (N * H * W * C + Co * R * S * C + N * Ho * Wo * Co),
-            N, H, C, Co, R)
+            N, H, C, Co, R, Ho)
 
 
 def _tc_conv_ok(C, Co, Ho, Wo):
