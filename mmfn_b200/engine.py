@@ -154,7 +154,7 @@ class TrainEngine:
         ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         pool = torch.cuda.graph_pool_handle()
         l0 = lib().launches
-        cap = torch.cuda.Stream()
+        cap = torch.cuda.Stream(priority=-1)     # critical chain: above the leaf (weight-gradient) streams
         cap.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(cap):
             ga.capture_begin(pool=pool)

@@ -46,8 +46,9 @@ class _Aux:
     def _pool(cls, prim):
         pool = cls.pools.get(prim.cuda_stream)
         if pool is None:
-            mk = lambda n: [torch.cuda.Stream(device=prim.device) for _ in range(n)]
-            pool = cls.pools[prim.cuda_stream] = {"leaf": mk(cls.N_LEAF), "fork": mk(cls.N_FORK), "i": 0, "j": 0}
+            # leaves at the lowest priority: their CTAs only fill SMs the data-gradient chain leaves idle
+            mk = lambda n, pr: [torch.cuda.Stream(device=prim.device, priority=pr) for _ in range(n)]
+            pool = cls.pools[prim.cuda_stream] = {"leaf": mk(cls.N_LEAF, 0), "fork": mk(cls.N_FORK, -1), "i": 0, "j": 0}
         return pool
 
     @classmethod
@@ -60,10 +61,28 @@ class _Aux:
             fn()
         cls.used[aux.cuda_stream] = aux
 
+    deferred = None      # list while a trunk phase defers its leaves to the following transformer phase
+
+    @classmethod
+    def defer_begin(cls):
+        if cls.enabled:
+            cls.deferred = []
+
+    @classmethod
+    def defer_flush(cls):
+        """Issue the deferred leaves from the current stream (after the trunk phase has re-joined it): they now overlap
+        the latency-bound fusion-transformer backward that follows instead of competing with the trunks' own chain."""
+        jobs, cls.deferred = cls.deferred, None
+        for fn, tensors in jobs or []:
+            cls.run(fn, *tensors)
+
     @classmethod
     def run(cls, fn, *tensors):
         if not cls.enabled:
             fn()
+            return
+        if cls.deferred is not None:
+            cls.deferred.append((fn, tensors))
             return
         prim = torch.cuda.current_stream()
         pool = cls._pool(prim)
@@ -538,7 +557,7 @@ class _Net:
         self.gpts = [FusionGPT(st, f"{e}transformer{i + 1}", WIDTHS[i], 3 if (i < 3 or var != "rad") else 4, cfg, i) for i in range(4)]
         self.head = Head(st, cfg.pred_len)
         dev = st.device
-        self.side = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        self.side = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(3)]
         self.use_streams = True
         self.mean = torch.tensor(IMAGENET_MEAN, device=dev, dtype=torch.float32)
         self.std = torch.tensor(IMAGENET_STD, device=dev, dtype=torch.float32)
@@ -628,7 +647,11 @@ class _Net:
             branches = [trunk(self.img_layers, dimg, 0), trunk(self.lid_layers, dlid, 1), trunk(self.map_layers, dmp, 2)]
             if s == 2 and self.gat is not None:
                 branches.append(lambda: self.gat.bwd(dfe[3]))  # same side stream as its forward
+            if s < 2:
+                _Aux.defer_begin()                             # layer3 / layer2 weight gradients: under the next GPT backward
             dimg, dlid, dmp = self._parallel(*branches)[:3]
+            if s < 2:
+                _Aux.defer_flush()
             if s == 2:
                 self._early_bucket_done()
             self.gpts[s].bwd(dtok, [dimg, dlid, dmp])

@@ -30,7 +30,7 @@ class _NetTF(_Net):
         self.gpts = [FusionGPT(st, f"{e}transformer{i + 1}", WIDTHS[i], 2, cfg, i) for i in range(4)]
         self.head = Head(st, cfg.pred_len)
         dev = st.device
-        self.side = [torch.cuda.Stream(device=dev) for _ in range(3)]
+        self.side = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(3)]
         self.use_streams = True
         self.mean = torch.tensor(IMAGENET_MEAN, device=dev, dtype=torch.float32)
         self.std = torch.tensor(IMAGENET_STD, device=dev, dtype=torch.float32)
