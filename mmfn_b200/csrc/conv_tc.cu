@@ -22,9 +22,12 @@ struct ConvGeomTc {
   int tiles_w, tiles_h, tiles_n;
 };
 
-template <int TBN>
+// DGRAD = true: the stride-1 DATA GRADIENT run as a forward convolution of dy -- here g.C = channels of dy (the conv's
+// Co), g.Co = channels of dx (the conv's C) -- reading the UNTRANSFORMED KRSC filters w[k = co][tap][n = ci] as an MN-major
+// B operand ([32 co][32 ci] boxes, SWIZZLE_128B_ATOM_32B) with mirrored taps: no CRSK filter copy is ever made.
+template <int TBN, bool DGRAD = false>
 struct ConvFwdOp {
-  static constexpr bool A_MN = false, B_MN = false;
+  static constexpr bool A_MN = false, B_MN = DGRAD;
   ConvGeomTc g;
   int kb_per_split;          // split-K over (tap, channel-chunk) blocks for layers with few pixel tiles
   int w0, h0, i0, co0;
@@ -43,7 +46,12 @@ struct ConvFwdOp {
     int tap = kb / cch, cc = kb - tap * cch;
     int r = tap / g.S, s = tap - r * g.S;
     tc::tma_load_4d(sa, ta, bar, cc * 32, w0 * g.stride - g.pad + s, h0 * g.stride - g.pad + r, i0);
-    tc::tma_load_2d(sb, tb, bar, tap * g.C + cc * 32, co0);
+    if constexpr (!DGRAD) tc::tma_load_2d(sb, tb, bar, tap * g.C + cc * 32, co0);
+    else {
+      const int ftap = g.R * g.S - 1 - tap;                              // mirrored tap of the original filter
+#pragma unroll
+      for (int j = 0; j < TBN / 32; ++j) tc::tma_load_2d(sb + j * tc::BOX_BYTES, tb, bar, ftap * g.Co + co0 + 32 * j, cc * 32);
+    }
   }
   __device__ bool out_row(int r, int64_t& off) const {
     int per = g.BH * g.BW;
@@ -56,6 +64,54 @@ struct ConvFwdOp {
   __device__ int n_cols() const { return g.Co; }
   __device__ int col0() const { return co0; }
   __device__ bool first_split() const { return blockIdx.z == 0; }
+};
+
+// Data gradient of a STRIDE-2 convolution without zero insertion: the input pixels split into four parity classes
+// (h % 2, w % 2); a class only ever meets the filter taps r = (h + pad) % 2 (mod 2) (and likewise s), so each class is a
+// small stride-1 implicit GEMM over dy with 1 / 2 / 2 / 4 of the 9 taps of a 3x3 filter (1 / 0 / 0 / 0 of a 1x1):
+//   dx[n, 2y+ph, 2x+pw, :] = sum_{(r,s) in class, co} dy[n, y + (ph+pad-r)/2, x + (pw+pad-s)/2, co] * w[co, r, s, :]
+// blockIdx.z = parity class; M = 128 pixels of the (H/2, W/2) sub-grid; B = the KRSC filters, MN-major.
+// A class without taps (1x1 filters, odd pixels) still runs its epilogue and writes zeros (+ residual).
+template <int TBN>
+struct ConvDgradS2Op {
+  static constexpr bool A_MN = false, B_MN = true;        // B = the KRSC filters themselves, [32 co][32 ci] boxes
+  ConvGeomTc g;              // g.H, g.W: dx (= conv input) size; g.Ho, g.Wo: dy size; g.C: dx channels; g.Co: dy channels
+  int unused_;
+  int w0, h0, i0, ci0, ph, pw, r0, s0, nr, ns;
+  __device__ void setup() {
+    int t = blockIdx.y;
+    int tw = t % g.tiles_w; t /= g.tiles_w;
+    int th = t % g.tiles_h;
+    int tn = t / g.tiles_h;
+    w0 = tw * g.BW; h0 = th * g.BH; i0 = tn * g.BI;
+    ci0 = blockIdx.x * TBN;
+    ph = blockIdx.z >> 1; pw = blockIdx.z & 1;
+    r0 = (ph + g.pad) & 1; s0 = (pw + g.pad) & 1;          // first tap of the class; taps step by 2
+    nr = r0 < g.R ? (g.R - r0 + 1) / 2 : 0;
+    ns = s0 < g.S ? (g.S - s0 + 1) / 2 : 0;
+  }
+  __device__ int kb_begin() const { return 0; }
+  __device__ int kb_end() const { return nr * ns * (g.Co / 32); }
+  __device__ void load(int kb, uint8_t* sa, uint8_t* sb, uint64_t* bar, const CUtensorMap* ta, const CUtensorMap* tb) const {
+    int cch = g.Co / 32;
+    int tap = kb / cch, cc = kb - tap * cch;
+    int r = r0 + 2 * (tap / ns), s = s0 + 2 * (tap % ns);
+    int oy = (ph + g.pad - r) / 2, ox = (pw + g.pad - s) / 2;   // exact: numerator is even (C++ division of negatives: -2/2)
+    tc::tma_load_4d(sa, ta, bar, cc * 32, w0 + ox, h0 + oy, i0);
+#pragma unroll
+    for (int j = 0; j < TBN / 32; ++j) tc::tma_load_2d(sb + j * tc::BOX_BYTES, tb, bar, (r * g.S + s) * g.C + ci0 + 32 * j, cc * 32);
+  }
+  __device__ bool out_row(int r, int64_t& off) const {
+    int per = g.BH * g.BW;
+    int img = r / per, rem = r - img * per;
+    int hh = rem / g.BW, ww = rem - hh * g.BW;
+    int n = i0 + img, h = 2 * (h0 + hh) + ph, w = 2 * (w0 + ww) + pw;
+    off = (((int64_t)n * g.H + h) * g.W + w) * g.C;
+    return n < g.N && h < g.H && w < g.W;
+  }
+  __device__ int n_cols() const { return g.C; }
+  __device__ int col0() const { return ci0; }
+  __device__ bool first_split() const { return true; }
 };
 
 template <int TBN>
@@ -113,6 +169,14 @@ int make_act_tmap(CUtensorMap* m, const float* x, int N, int H, int W, int C, in
   uint32_t box[4] = {32, (uint32_t)(bw * stride), (uint32_t)(bh * stride), (uint32_t)bi};
   uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
   return mmfn_make_tmap_f32(m, x, 4, dims, strides, box, es, swz32);
+}
+
+// KRSC filters w(Co,R,S,C) as the MN-major B operand of a data-gradient GEMM: a 2-D map with inner = (tap, ci)
+// (contiguous, R*S*C long) and outer = co; boxes of [32 co][32 ci] in the SWIZZLE_128B_ATOM_32B pattern.
+int make_krsc_b_tmap(CUtensorMap* m, const float* w, int Co, int R, int S, int C) {
+  uint64_t dims[2] = {(uint64_t)R * S * C, (uint64_t)Co}, strides[2] = {1, (uint64_t)R * S * C};
+  uint32_t box[2] = {32, 32};
+  return mmfn_make_tmap_f32(m, w, 2, dims, strides, box, nullptr, true);
 }
 
 __global__ void krsc_to_crsk_kernel(const float* __restrict__ w, float* __restrict__ wt, int Co, int R, int S, int C, int flip) {
@@ -210,6 +274,81 @@ MMFN_API int mmfn_conv2d_fwd_tf32(const float* x, const float* w, float* y, cons
   }
   ConvFwdOp<128> op{g, kb_per};
   return tc::launch<ConvFwdOp<128>, 128, 3>(ta, tb, op, e, dim3((Co + 127) / 128, ptiles, splitk), stream, "conv_fwd_tf32");
+}
+
+// Data gradient on the tensor cores straight from the KRSC filters w(Co,R,S,C) (no transposed / mirrored filter copy):
+// dx(N,H,W,C) = dgrad of y = conv(x, w, stride, pad) [+ res], from dy(N,Ho,Wo,Co).  stride 1 (any R, S, pad < R) or
+// stride 2 (H, W even).  Co % 32 == 0, C % 4 == 0.
+static int conv2d_dgrad_s2(const float* dy, const float* wt, float* dx, const float* res,
+                           int N, int H, int W, int C, int Co, int R, int S, int pad,
+                           int Ho, int Wo, cudaStream_t stream) {
+  MMFN_CHECK_ARG(dy && wt && dx, "conv_dgrad_s2_tf32: null pointer");
+  MMFN_CHECK_ARG(N > 0 && H > 0 && W > 0 && C > 0 && Co > 0 && R > 0 && S > 0 && pad >= 0, "conv_dgrad_s2_tf32: bad sizes");
+  MMFN_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && Ho == (H + 2 * pad - R) / 2 + 1 && Wo == (W + 2 * pad - S) / 2 + 1,
+                 "conv_dgrad_s2_tf32: H, W must be even and consistent with Ho, Wo");
+  MMFN_CHECK_ARG(Co % 32 == 0 && C % 4 == 0, "conv_dgrad_s2_tf32: Co % 32 == 0, C % 4 == 0");
+  MMFN_CHECK_ARG((((uintptr_t)dy | (uintptr_t)wt) & 15) == 0, "conv_dgrad_s2_tf32: operands must be 16-byte aligned");
+  const int Hs = H / 2, Ws = W / 2;                    // one parity class of dx
+  MMFN_CHECK_ARG(Hs >= 8 && Ws >= 8, "conv_dgrad_s2_tf32: dx must be at least 16x16");
+  ConvGeomTc g{N, H, W, C, Co, R, S, 2, pad, Ho, Wo};
+  g.BW = Ws >= 16 ? 16 : 8;
+  g.BH = 8;
+  g.BI = tc::TBM / (g.BW * g.BH);
+  g.tiles_w = (Ws + g.BW - 1) / g.BW; g.tiles_h = (Hs + g.BH - 1) / g.BH; g.tiles_n = (N + g.BI - 1) / g.BI;
+  CUtensorMap ta, tb;
+  if (int rc = make_act_tmap(&ta, dy, N, Ho, Wo, Co, g.BW, g.BH, g.BI, 1, false)) return rc;
+  const int ptiles = g.tiles_w * g.tiles_h * g.tiles_n;
+  MMFN_CHECK_ARG(ptiles <= 65535, "conv_dgrad_s2_tf32: too many pixel tiles");
+  const int tbn = (C <= 64 || ptiles * 4 * ((C + 127) / 128) < 148) ? 64 : 128;
+  if (int rc = make_krsc_b_tmap(&tb, wt, Co, R, S, C)) return rc;
+  tc::Epilogue e{dx, nullptr, res, nullptr, 1.f, 0, 0, 0.f, 0, mmfn_tc_trace_ptr()};
+  if (tbn == 64) {
+    ConvDgradS2Op<64> op{g, 0};
+    return tc::launch<ConvDgradS2Op<64>, 64, 4>(ta, tb, op, e, dim3((C + 63) / 64, ptiles, 4), stream, "conv_dgrad_s2_tf32");
+  }
+  ConvDgradS2Op<128> op{g, 0};
+  return tc::launch<ConvDgradS2Op<128>, 128, 3>(ta, tb, op, e, dim3((C + 127) / 128, ptiles, 4), stream, "conv_dgrad_s2_tf32");
+}
+
+MMFN_API int mmfn_conv2d_dgrad_tf32(const float* dy, const float* w, float* dx, const float* res,
+                                    int N, int H, int W, int C, int Co, int R, int S, int stride, int pad,
+                                    int Ho, int Wo, cudaStream_t stream) {
+  MMFN_CHECK_ARG(dy && w && dx, "conv_dgrad_tf32: null pointer");
+  MMFN_CHECK_ARG(stride == 1 || stride == 2, "conv_dgrad_tf32: stride must be 1 or 2");
+  if (stride == 2) return conv2d_dgrad_s2(dy, w, dx, res, N, H, W, C, Co, R, S, pad, Ho, Wo, stream);
+  // stride 1: a forward convolution of dy (N,Ho,Wo,Co) -> dx (N,H,W,C) with mirrored taps and padding R-1-pad
+  MMFN_CHECK_ARG(pad < R && pad < S && Ho == H + 2 * pad - R + 1 && Wo == W + 2 * pad - S + 1, "conv_dgrad_tf32: inconsistent sizes");
+  MMFN_CHECK_ARG(Co % 32 == 0 && C % 4 == 0, "conv_dgrad_tf32: Co % 32 == 0, C % 4 == 0");
+  MMFN_CHECK_ARG((((uintptr_t)dy | (uintptr_t)w) & 15) == 0, "conv_dgrad_tf32: operands must be 16-byte aligned");
+  MMFN_CHECK_ARG(W >= 8 && H >= 8, "conv_dgrad_tf32: dx must be at least 8x8");
+  ConvGeomTc g{N, Ho, Wo, Co, C, R, S, 1, R - 1 - pad, H, W};       // roles as a forward conv: in = dy, out = dx
+  g.BW = W >= 16 ? 16 : 8;
+  g.BH = 8;
+  g.BI = tc::TBM / (g.BW * g.BH);
+  g.tiles_w = (W + g.BW - 1) / g.BW; g.tiles_h = (H + g.BH - 1) / g.BH; g.tiles_n = (N + g.BI - 1) / g.BI;
+  CUtensorMap ta, tb;
+  if (int rc = make_act_tmap(&ta, dy, N, Ho, Wo, Co, g.BW, g.BH, g.BI, 1, false)) return rc;
+  const int tbn = (C <= 64 || g.tiles_w * g.tiles_h * g.tiles_n * ((C + 127) / 128) < 148) ? 64 : 128;
+  if (int rc = make_krsc_b_tmap(&tb, w, Co, R, S, C)) return rc;
+  int ptiles = g.tiles_w * g.tiles_h * g.tiles_n;
+  MMFN_CHECK_ARG(ptiles <= 65535, "conv_dgrad_tf32: too many pixel tiles");
+  const int nkb = R * S * (Co / 32);
+  const int ctas = ptiles * ((C + tbn - 1) / tbn);
+  int splitk = 1;
+  if (ctas < 148) splitk = max(1, min(nkb / 8, (2 * 148) / ctas));
+  int kb_per = (nkb + splitk - 1) / splitk;
+  splitk = (nkb + kb_per - 1) / kb_per;
+  if (splitk > 1) {
+    cudaError_t ce = cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)N * H * W * C, stream);
+    if (ce != cudaSuccess) { mmfn_set_error("conv_dgrad_tf32: memset: %s", cudaGetErrorString(ce)); return (int)ce; }
+  }
+  tc::Epilogue e{dx, nullptr, res, nullptr, 1.f, 0, splitk > 1 ? 2 : 0, 0.f, 0, mmfn_tc_trace_ptr()};
+  if (tbn == 64) {
+    ConvFwdOp<64, true> op{g, kb_per};
+    return tc::launch<ConvFwdOp<64, true>, 64, 4>(ta, tb, op, e, dim3((C + 63) / 64, ptiles, splitk), stream, "conv_dgrad_tf32");
+  }
+  ConvFwdOp<128, true> op{g, kb_per};
+  return tc::launch<ConvFwdOp<128, true>, 128, 3>(ta, tb, op, e, dim3((C + 127) / 128, ptiles, splitk), stream, "conv_dgrad_tf32");
 }
 
 // dw(Co,R,S,C) += dy^T * im2col(x), atomically; TF32 multiply, FP32 accumulate.  C % 32 == 0, Co % 4 == 0.

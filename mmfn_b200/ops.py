@@ -175,31 +175,32 @@ def filter_crsk(w_krsc, flip=False):
 
 
 def dgrad_uses_flipped_filter(w_krsc, x_shape, stride):
-    """True when conv2d_dgrad runs as a forward convolution with the mirrored CRSK filters (tensor-core path)."""
-    N, H, W, C = x_shape
-    Co = w_krsc.shape[0]
-    return stride in (1, 2) and _tc_conv_ok(Co, C, H, W) and (stride == 1 or (H % 2 == 0 and W % 2 == 0))
+    """Kept for callers that pre-computed mirrored CRSK filters: the tensor-core data gradient now reads the KRSC
+    filters directly (MN-major B operand), so no transformed copy is needed any more."""
+    return False
+
+
+def _tc_dgrad_ok(C, Co, H, W, stride, Ho, Wo):
+    if not (TF32 and C % 32 == 0 and Co % 32 == 0):
+        return False
+    if stride == 1:
+        return H >= 8 and W >= 8
+    return stride == 2 and H == 2 * Ho and W == 2 * Wo and H >= 16 and W >= 16
 
 
 def conv2d_dgrad(dy, w_krsc, x_shape, stride, pad, res=None, wt_flipped=None):
-    """wt_flipped: optional pre-computed filter_crsk(w_krsc, flip=True) (see dgrad_uses_flipped_filter)."""
+    """Data gradient of conv2d_fwd.  Tensor-core path: stride 1 = forward convolution of dy with mirrored taps;
+    stride 2 = four parity classes of dx, each a small stride-1 implicit GEMM over dy with only the taps that can
+    reach it (no zero insertion, exact MAC count).  Both read the KRSC filters as they are."""
     N, H, W, C = x_shape
     Co, R, S, _ = w_krsc.shape
     _, Ho, Wo, _ = dy.shape
-    if stride == 1 and _tc_conv_ok(Co, C, H, W):
-        # stride-1 data gradient == forward convolution of dy with the mirrored, channel-swapped filters
-        wt = wt_flipped if wt_flipped is not None else filter_crsk(w_krsc, flip=True)
-        return conv2d_fwd(dy, wt, 1, R - 1 - pad, res=res)
-    if stride == 2 and _tc_conv_ok(Co, C, H, W) and H == 2 * Ho and W == 2 * Wo:
-        # stride-2: the same, on dy with zeros inserted between pixels (75 % of the MMA work multiplies
-        # zeros, but it runs on the tensor cores instead of the SIMT gather kernel)
-        up = torch.empty((N, H, W, Co), device=dy.device, dtype=torch.float32)
-        lib().zero_upsample2_f32(_p(dy), _p(up), N, Ho, Wo, Co, _st())
-        wt = wt_flipped if wt_flipped is not None else filter_crsk(w_krsc, flip=True)
-        return conv2d_fwd(up, wt, 1, R - 1 - pad, res=res)
-    wt = filter_crsk(w_krsc)
     dx = torch.empty(x_shape, device=dy.device, dtype=torch.float32)
     lib().next_work = _conv_work(N, H, W, C, Co, R, S, Ho, Wo)
+    if _tc_dgrad_ok(C, Co, H, W, stride, Ho, Wo):
+        lib().conv2d_dgrad_tf32(_p(dy), _p(w_krsc), _p(dx), _p(res), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, _st())
+        return dx
+    wt = filter_crsk(w_krsc)
     lib().conv2d_dgrad_f32(_p(dy), _p(wt), _p(dx), _p(res), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, _st())
     return dx
 
