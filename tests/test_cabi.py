@@ -76,3 +76,29 @@ def test_param_spec_matches_reference_state_dict():
     root.load_state_dict(synthetic.fill_golden_weights(sd, 1))
     k = "encoder.transformer4.blocks.7.mlp.2.bias"
     assert torch.equal(st.p(k), synthetic.fill_golden_weights({k: sd[k]}, 1)[k])
+
+
+def test_flat_layout_buckets_are_contiguous():
+    """[late | early | never-used]: the early gradient bucket (head, transformer4, radar GAT, layer4 of every trunk)
+    is ONE contiguous 16-byte-aligned range, fused q/k/v stay adjacent, never-used parameters sit behind n_active."""
+    from mmfn_b200.config import GlobalConfig
+    from mmfn_b200.params import ParamStore, is_early_bucket, is_unused
+    for variant in ("rad", "vec", "img", "transfuser"):
+        st = ParamStore(GlobalConfig(), "cpu", variant)
+        assert 0 < st.n_late < st.n_active <= st.n_total and st.n_late % 4 == 0 and st.n_active % 4 == 0
+        n_early = 0
+        for k, off in st.offsets.items():
+            n = 1
+            for d in st.shapes[k]:
+                n *= d
+            assert off % 4 == 0, k
+            if is_unused(k, variant):
+                assert off >= st.n_active, k
+            elif is_early_bucket(k):
+                assert st.n_late <= off and off + n <= st.n_active, k
+                n_early += n
+            else:
+                assert off + n <= st.n_late, k
+        assert n_early > 0.4 * st.n_active            # the overlap-able bucket carries > 40 % of the gradient bytes
+        qkv = st.fused([f"encoder.transformer1.blocks.0.attn.{n}.weight" for n in ("key", "query", "value")])
+        assert tuple(qkv.shape) == (192, 64)
