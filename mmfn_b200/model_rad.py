@@ -330,20 +330,26 @@ class Block:
         da = self.fc2.bwd(dz, dx_mask=a)                              # ReLU mask fused into the dgrad GEMM
         dh2 = self.fc1.bwd(da, masked=True)
         dx1, dzp = self.ln2.bwd(dh2, dres=dx2, drop=(self.rp, self.seed + 1))
+        y_att = self.proj.x                                        # attention output saved by the projection
         dy = self.proj.bwd(dzp)
         qkv = self.qkv_out
         k, q, v = (self._heads(qkv, B, T, i * C) for i in range(3))
         dqkv = torch.empty_like(qkv)
         dk, dq, dv = (self._heads(dqkv, B, T, i * C) for i in range(3))
         dyh = dy.view(B, T, nh, hs).permute(0, 2, 1, 3)
-        dPd = torch.empty((B, nh, T, T), device=dy.device, dtype=torch.float32)
-        # critical chain: dPd -> dS -> dQ; dV and dK are leaves until the qkv backward: side stream
-        ops.gemm(dyh, v, dPd)
         Pd = self.Pd
+        # critical chain: dPd -> dS -> dQ; dV and dK are leaves until the qkv backward: fork streams
         ev_v = _Aux.fork(lambda: ops.gemm(Pd.transpose(-1, -2), dyh.transpose(-1, -2), dv), Pd, dy, dqkv)
-        dS = ops.softmax_bwd(self.P, dPd, 1.0 / math.sqrt(hs), self.ap, self.seed)
-        ev_k = _Aux.fork(lambda: ops.gemm(dS.transpose(-1, -2), q.transpose(-1, -2), dk), dS, qkv, dqkv)
-        ops.gemm(dS, k.transpose(-1, -2), dq)
+        if ops.attention_fwd_ok(T, C, nh) and ops.FUSED_ATTN_BWD:
+            # ONE tcgen05 kernel: dPd stays in TMEM, dS tiles feed the dQ MMA and are stored for the dK GEMM
+            dS = ops.attention_bwd_dq(qkv, dy, y_att, self.P, dqkv, B, T, C, nh, self.ap, self.seed)
+            ev_k = _Aux.fork(lambda: ops.gemm(dS.transpose(-1, -2), q.transpose(-1, -2), dk), dS, qkv, dqkv)
+        else:
+            dPd = torch.empty((B, nh, T, T), device=dy.device, dtype=torch.float32)
+            ops.gemm(dyh, v, dPd)
+            dS = ops.softmax_bwd(self.P, dPd, 1.0 / math.sqrt(hs), self.ap, self.seed)
+            ev_k = _Aux.fork(lambda: ops.gemm(dS.transpose(-1, -2), q.transpose(-1, -2), dk), dS, qkv, dqkv)
+            ops.gemm(dS, k.transpose(-1, -2), dq)
         _Aux.wait(ev_v, ev_k)
         dh1 = self.qkv.bwd(dqkv)
         self.P = self.Pd = self.qkv_out = None

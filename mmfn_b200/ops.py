@@ -22,6 +22,13 @@ def _chk(t, name="tensor"):
 
 
 TF32 = True   # large aligned GEMMs/convs run on the tcgen05 TF32 path; False = exact fp32 SIMT everywhere
+# Attention backward dP -> dS -> dQ in one tcgen05 kernel (attention_bwd_dq) instead of GEMM + softmax_bwd + GEMM.
+# Off by default: (1) measured on B200 at B=16 it shortens the step by < 0.1 ms, because the dK GEMM still has to wait
+# for its dS (9.9 us + 9 us vs 9.1 + 4.5 + 9.0 us with dQ || dK); (2) it takes the softmax row term from the
+# FlashAttention identity delta_i = sum_d dY_id Y_id, which under TF32 rounding of Y differs from sum_j dP_ij P_ij by
+# ~1e-3 relative -- enough to dominate the (second-order small) query/key gradients of a freshly initialised model and
+# to fail the per-tensor gradient-norm check of tests/test_gpu_parity.py.  The kernel itself is covered op-level.
+FUSED_ATTN_BWD = False
 
 
 def _major(t):
@@ -400,6 +407,18 @@ def attention_fwd(qkv, B, T, C, nh, drop_p=0.0, seed=0):
     lib().next_work = (4.0 * B * nh * T * T * hs, 4.0 * (B * T * 4 * C + B * nh * T * T), B, T, C, nh)
     lib().attention_fwd_tf32(_p(qkv), _p(y), _p(P), _p(Pd), B, T, C, nh, float(drop_p), int(seed), _st())
     return y, P, (Pd if Pd is not None else P)
+
+
+def attention_bwd_dq(qkv, dy, y, P, dqkv, B, T, C, nh, drop_p=0.0, seed=0):
+    """Fused critical half of the attention backward: dPd = dY V^T (TMEM only), dS = softmax'(P, dPd o mask),
+    dQ = dS K written into the query slice of dqkv.  Returns dS (B,nh,T,T) for the dK GEMM."""
+    assert qkv.is_contiguous() and dy.is_contiguous() and y.is_contiguous() and P.is_contiguous() and dqkv.is_contiguous()
+    assert dy.shape == (B * T, C) and y.shape == (B * T, C) and dqkv.shape == qkv.shape
+    dS = torch.empty_like(P)
+    hs = C // nh
+    lib().next_work = (4.0 * B * nh * T * T * hs, 4.0 * (B * T * 5 * C + 2 * B * nh * T * T), B, T, C, nh)
+    lib().attention_bwd_dq_tf32(_p(qkv), _p(dy), _p(y), _p(P), _p(dS), _p(dqkv), B, T, C, nh, float(drop_p), int(seed), _st())
+    return dS
 
 
 def attention_fwd_ok(T, C, nh):

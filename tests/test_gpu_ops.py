@@ -152,6 +152,49 @@ def test_attention_products_on_strided_heads(C, T):
     close(ops.softmax_bwd(p, g_dS, hs ** -0.5), Sr.grad, 1e-4)
 
 
+@pytest.mark.parametrize("C,T", [(64, 192), (128, 192), (256, 192), (512, 256)])
+def test_fused_attention_backward_dq_ds(C, T):
+    """attention_bwd_dq (dP in TMEM -> dS -> dQ in one kernel) against torch autograd, without dropout, and against the
+    unfused kernel sequence (batched GEMM + softmax_bwd + batched GEMM) with the SAME dropout masks (p = 0.1)."""
+    import math
+    from mmfn_b200 import ops
+    B, nh = 3, 4
+    hs = C // nh
+    qkv = (torch.randn(B * T, 3 * C) * 0.5)
+    dy = torch.randn(B * T, C)
+    heads = lambda t2d, i: t2d[:, i * C:(i + 1) * C].view(B, T, nh, hs).permute(0, 2, 1, 3)
+    qkv_r = qkv.clone().requires_grad_(True)
+    k, q, v = (heads(qkv_r, i) for i in range(3))
+    P = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hs), -1)
+    y = (P @ v).permute(0, 2, 1, 3).reshape(B * T, C)
+    (dS_ref,) = torch.autograd.grad(y, P, dy, retain_graph=True)          # = dP; dS below
+    y.backward(dy)
+    g_qkv, g_dy, g_P, g_y = qkv.to(DEV), dy.to(DEV), P.detach().contiguous().to(DEV), y.detach().to(DEV)
+    dqkv = torch.zeros_like(g_qkv)
+    dS = ops.attention_bwd_dq(g_qkv, g_dy, g_y, g_P, dqkv, B, T, C, nh)
+    dP = dS_ref
+    ds_ref = P.detach() * (dP - (dP * P.detach()).sum(-1, keepdim=True)) / math.sqrt(hs)
+    close(dS, ds_ref, 3e-3)
+    close(heads(dqkv, 1), heads(qkv_r.grad, 1), 3e-3)                      # query gradient
+    assert torch.count_nonzero(heads(dqkv, 0)).item() == 0               # key / value slices untouched
+    # with dropout: same hash as the stand-alone kernels
+    p_drop, seed = 0.1, 11
+    gk, gq, gv = (heads(g_qkv, i) for i in range(3))
+    g_dyh = g_dy.view(B, T, nh, hs).permute(0, 2, 1, 3)
+    Pd = ops.dropout(g_P, p_drop, seed)
+    yd = torch.empty(B * T, C, device=DEV)
+    ops.gemm(Pd, gv.transpose(-1, -2), yd.view(B, T, nh, hs).permute(0, 2, 1, 3))
+    dPd = torch.empty(B, nh, T, T, device=DEV)
+    ops.gemm(g_dyh, gv, dPd)
+    dS_u = ops.softmax_bwd(g_P, dPd, 1.0 / math.sqrt(hs), p_drop, seed)
+    dq_u = torch.zeros_like(g_qkv)
+    ops.gemm(dS_u, gk.transpose(-1, -2), heads(dq_u, 1))
+    dq_f = torch.zeros_like(g_qkv)
+    dS_f = ops.attention_bwd_dq(g_qkv, g_dy, yd, g_P, dq_f, B, T, C, nh, p_drop, seed)
+    close(dS_f, dS_u, 3e-3)
+    close(dq_f, dq_u, 5e-3)
+
+
 def test_batchnorm_train_forward_backward():
     from mmfn_b200 import ops
     # M = N*H*H <= 4096 rows: single-launch kernel; larger: two launches whose scratch must come back zeroed (the
