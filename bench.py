@@ -54,7 +54,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append((float(f[0]), float(f[1]), f[2:]))
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         if not self.samples:
