@@ -81,6 +81,12 @@ def gemm(A, B, C, *, bias=None, res=None, mask=None, alpha=1.0, act=0, accum=0,
         if am is not None and bm is not None and C.stride(-1) == 1 and bs_ok and nbt * max(1, splitk) <= 4096:
             if accum == 1:          # plain += is a single-writer RMW; tensor-core path accumulates atomically
                 accum = 2
+            linear = act == 0 and mask is None and drop_p == 0
+            if accum == 0 and linear and splitk == 1 and K >= 4096 and ((M + 127) // 128) * ((N + 63) // 64) * nbt < 64:
+                # few output tiles, long reduction (VectorNet generator dgrad at B >= 64: 64x64 <- K = 262144):
+                # zero C and let the library split K over the SMs with atomic accumulation
+                C.zero_()
+                accum = 2
             lib().gemm_tf32(_p(A), am[1], am[0], a_b[0], a_b[1], _p(B), bm[1], bm[0], b_b[0], b_b[1],
                             _p(C), C.stride(-2), c_b[0], c_b[1], M, N, K, nb[0], nb[1],
                             _p(bias), _p(res), _p(mask), float(alpha), int(act), int(accum), float(drop_p),

@@ -114,6 +114,17 @@ def test_linear_gemms_and_epilogues_tf32(C, T):
     assert x is not None
 
 
+def test_skinny_gemm_with_long_reduction_splits_k():
+    """64 x 64 outputs over K = 32768 (the VectorNet generator data gradient at B >= 64): the tensor-core path must
+    split K over CTAs (zeroed output + atomic accumulation) and still add the bias exactly once."""
+    from mmfn_b200 import ops
+    M, N, K = 64, 64, 32768
+    a, w, bias = torch.randn(M, K) * 0.1, torch.randn(N, K) * 0.1, torch.randn(N)
+    out = torch.full((M, N), 7.0, device=DEV)                  # stale contents must be overwritten, not accumulated
+    ops.gemm(a.to(DEV), w.to(DEV), out, bias=bias.to(DEV))
+    close(out, a @ w.t() + bias, 3e-3)
+
+
 @pytest.mark.parametrize("C,T", [(64, 192), (128, 192), (256, 192), (512, 256)])
 def test_attention_products_on_strided_heads(C, T):
     from mmfn_b200 import ops
