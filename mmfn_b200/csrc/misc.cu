@@ -92,30 +92,42 @@ __global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ c
 // Fast path for the stems (compile-time S, C): one warp per output pixel, lane l writes columns l, l+32, ... of the
 // pixel's row (fully coalesced 128-byte stores); a filter row is a contiguous run of S*C input floats, so the loads of
 // neighbouring lanes are contiguous too, and the only divisions are by compile-time constants.
-template <int S, int C>
+template <int S, int C, int KP>
 __global__ void __launch_bounds__(256)
 im2col_rows_kernel(const float* __restrict__ x, float* __restrict__ col, int N, int H, int W, int R,
-                   int stride, int pad, int Ho, int Wo, int Kp) {
+                   int stride, int pad, int Ho, int Wo) {
   constexpr int SC = S * C;
+  constexpr int NK = KP / 32;                // columns per lane
   const int K = R * SC;
   const int lane = threadIdx.x & 31;
   const int npix = N * Ho * Wo;
   const int wpg = (gridDim.x * blockDim.x) >> 5;
+  // per-lane column decomposition is the same for every pixel: hoisted out of the pixel loop
+  int rr[NK], rem[NK], dw[NK];
+  bool kin[NK];
+#pragma unroll
+  for (int j = 0; j < NK; ++j) {
+    const int k = lane + 32 * j;
+    kin[j] = k < K;
+    rr[j] = k / SC;
+    rem[j] = k - rr[j] * SC;
+    dw[j] = rem[j] / C;
+  }
   for (int pix = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pix < npix; pix += wpg) {
     const int wo = pix % Wo, t = pix / Wo;
     const int ho = t % Ho, n = t / Ho;
     const int h0 = ho * stride - pad, w0 = wo * stride - pad;
-    const float* xn = x + (int64_t)n * H * W * C;
-    float* dst = col + (int64_t)pix * Kp;
-    for (int k = lane; k < Kp; k += 32) {
-      float v = 0.f;
-      if (k < K) {
-        const int r = k / SC, rem = k - r * SC;
-        const int h = h0 + r, w = w0 + rem / C;
-        if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(xn + ((int64_t)h * W + w0) * C + rem);
-      }
-      dst[k] = v;
+    const float* xn = x + ((int64_t)n * H * W + w0) * C;
+    float v[NK];
+#pragma unroll
+    for (int j = 0; j < NK; ++j) {             // all loads of the pixel row in flight before the first store
+      const int h = h0 + rr[j], w = w0 + dw[j];
+      v[j] = 0.f;
+      if (kin[j] && h >= 0 && h < H && w >= 0 && w < W) v[j] = __ldg(xn + (int64_t)h * W * C + rem[j]);
     }
+    float* dst = col + (int64_t)pix * KP + lane;
+#pragma unroll
+    for (int j = 0; j < NK; ++j) dst[32 * j] = v[j];
   }
 }
 
@@ -330,10 +342,10 @@ MMFN_API int mmfn_im2col_nhwc(const float* x, float* col, int N, int H, int W, i
   MMFN_CHECK_ARG(Kp % 4 == 0 && Kp >= R * S * C && (((uintptr_t)col) & 15) == 0, "im2col: Kp must be a multiple of 4, >= R*S*C; col 16-byte aligned");
   const int64_t n4 = (int64_t)N * Ho * Wo * (Kp / 4);
   const int64_t npix = (int64_t)N * Ho * Wo;
-  if (S == 7 && (C == 3 || C == 2) && npix < (1ll << 31)) {
+  if (S == 7 && R == 7 && ((C == 3 && Kp == 160) || (C == 2 && Kp == 128)) && npix < (1ll << 31)) {
     const int grid = grid_1d(npix * 32, 256);
-    if (C == 3) im2col_rows_kernel<7, 3><<<grid, 256, 0, stream>>>(x, col, N, H, W, R, stride, pad, Ho, Wo, Kp);
-    else im2col_rows_kernel<7, 2><<<grid, 256, 0, stream>>>(x, col, N, H, W, R, stride, pad, Ho, Wo, Kp);
+    if (C == 3) im2col_rows_kernel<7, 3, 160><<<grid, 256, 0, stream>>>(x, col, N, H, W, R, stride, pad, Ho, Wo);
+    else im2col_rows_kernel<7, 2, 128><<<grid, 256, 0, stream>>>(x, col, N, H, W, R, stride, pad, Ho, Wo);
     return mmfn_launch_status("im2col_nhwc");
   }
   im2col_kernel<<<grid_1d(n4, 256), 256, 0, stream>>>(x, col, N, H, W, C, R, S, stride, pad, Ho, Wo, R * S * C, Kp);
