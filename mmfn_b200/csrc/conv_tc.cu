@@ -10,6 +10,7 @@
 //   weight-gradient         : M = Co tile, N = Ci tile, K loops over 32-pixel patches; both operands
 //                             MN-major (pixels are the slow dimension of dY and x); one CTA per
 //                             (tap, split) accumulates atomically into dW.
+#include <type_traits>
 #include "tc_kernel.cuh"
 
 namespace {
@@ -179,6 +180,196 @@ int make_krsc_b_tmap(CUtensorMap* m, const float* w, int Co, int R, int S, int C
   return mmfn_make_tmap_f32(m, w, 2, dims, strides, box, nullptr, true);
 }
 
+// ---------------------------------------------------------------- 3x3 stride-1 convolutions with input-halo reuse
+// The implicit GEMM above re-fetches every input pixel once per filter tap (9 x for 3x3), and with fp32 operands these
+// kernels run at the L2 -> SM bandwidth cap.  Here ONE (16+2) x (8+2) pixel patch of a 32-channel slice is loaded per
+// slice (one 4-D TMA box, zero padding = OOB fill) and all nine taps issue their MMAs from it: the A descriptor of tap
+// (r, s) simply starts (r * 10 + s) rows into the patch with a group stride SBO = 10 rows.  (A K-major SWIZZLE_128B
+// operand may start at any 128-byte row of a TMA-written tile and use any 128-byte-multiple group stride: the swizzle
+// is a function of the absolute shared-memory address -- tools/exp/desc_shift_probe.cu.)  Output tile = 16 rows x
+// 8 cols, so a UMMA row group (8 consecutive M rows) is 8 consecutive pixels of one image row.
+//   A ring: 2 x 23 KB patches (warp 2 lane 0 produces, then joins the epilogue); B ring: 64 KB of [TBN co x 32 ch] filter
+//   tiles, one per (slice, tap) (warp 0).  A traffic drops 9 x 16 KB -> 23 KB per slice.
+constexpr int PT_BH = 16, PT_BW = 8, PT_PH = PT_BH + 2, PT_PW = PT_BW + 2;
+constexpr int PT_A_BYTES = PT_PH * PT_PW * 128;            // 23 040
+constexpr int PT_A_STAGE = 23 * 1024;
+
+// DEEP = false: 3 patches + 32 KB of filter tiles = 101 KB, two CTAs per SM (grids of more than one CTA per SM).
+// DEEP = true : 5 patches + 64 KB of filter tiles = 179 KB, one CTA per SM: a patch is consumed in ~0.6 us (9 taps) but
+//               takes > 1 us to arrive (180 scattered 128-byte rows), so single-wave grids need more patches in flight.
+template <int TBN, bool DEEP>
+struct PatchSmem {
+  static constexpr int B_BYTES = TBN * 128;
+  static constexpr int A_STAGES = DEEP ? 5 : 3;
+  static constexpr int B_STAGES = (DEEP ? 65536 : 32768) / B_BYTES;
+  static constexpr int B_OFF = A_STAGES * PT_A_STAGE;
+  static constexpr int BAR_OFF = B_OFF + B_STAGES * B_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static_assert(PT_A_STAGE >= PT_A_BYTES && 8 * 32 * 36 * 4 + 128 * 8 <= BAR_OFF, "patch conv smem layout");
+};
+
+template <int TBN, bool DGRAD>
+struct ConvPatchOp {
+  static constexpr bool A_MN = false, B_MN = DGRAD;
+  ConvGeomTc g;              // forward roles (for DGRAD: in = dy, out = dx, g.C = dy channels, g.Co = dx channels)
+  int w0, h0, img, co0;
+  __device__ void setup() {
+    int t = blockIdx.y;
+    int tw = t % g.tiles_w; t /= g.tiles_w;
+    int th = t % g.tiles_h;
+    img = t / g.tiles_h;
+    w0 = tw * PT_BW; h0 = th * PT_BH;
+    co0 = blockIdx.x * TBN;
+  }
+  __device__ bool out_row(int r, int64_t& off) const {
+    int h = h0 + (r >> 3), w = w0 + (r & 7);
+    off = (((int64_t)img * g.Ho + h) * g.Wo + w) * g.Co;
+    return h < g.Ho && w < g.Wo;
+  }
+  __device__ int n_cols() const { return g.Co; }
+  __device__ int col0() const { return co0; }
+  __device__ bool first_split() const { return true; }
+};
+
+template <int TBN, bool DGRAD, bool DEEP>
+__global__ void __launch_bounds__(tc::TC_THREADS, DEEP ? 1 : 2)
+conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     ConvPatchOp<TBN, DGRAD> op, tc::Epilogue e) {
+  using L = PatchSmem<TBN, DEEP>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* a_empty = a_full + L::A_STAGES;
+  uint64_t* b_full = a_empty + L::A_STAGES;
+  uint64_t* b_empty = b_full + L::B_STAGES;
+  uint64_t* tmem_full = b_empty + L::B_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  op.setup();
+  const int nsl = op.g.C / 32;                             // 32-channel slices of the reduction
+
+  if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmA); tc::prefetch_tmap(&tmB); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < L::A_STAGES; ++i) { tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < L::B_STAGES; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
+    tc::mbar_init(tmem_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc(tmem_slot, TBN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (tc::elect_one()) {                                 // ===== filter-tile producer =====
+      int st = 0; uint32_t ph = 0;
+      for (int sl = 0; sl < nsl; ++sl)
+        for (int tap = 0; tap < 9; ++tap) {
+          tc::mbar_wait(&b_empty[st], ph ^ 1);
+          uint8_t* sb = smem + L::B_OFF + st * L::B_BYTES;
+          tc::mbar_expect_tx(&b_full[st], L::B_BYTES);
+          if constexpr (!DGRAD) tc::tma_load_2d(sb, &tmB, &b_full[st], tap * op.g.C + sl * 32, op.co0);
+          else {
+            const int ftap = 8 - tap;                      // mirrored tap of the original filter
+#pragma unroll
+            for (int j = 0; j < TBN / 32; ++j)
+              tc::tma_load_2d(sb + j * tc::BOX_BYTES, &tmB, &b_full[st], ftap * op.g.Co + op.co0 + 32 * j, sl * 32);
+          }
+          if (++st == L::B_STAGES) { st = 0; ph ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {                                 // ===== MMA issuer =====
+      const uint32_t idesc = tc::idesc_tf32(tc::TBM, TBN, false, DGRAD);
+      int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+      for (int sl = 0; sl < nsl; ++sl) {
+        tc::mbar_wait(&a_full[sa], pa);
+        tc::tc_fence_after();
+        const uint32_t patch = tc::smem_u32(smem + sa * PT_A_STAGE);
+        for (int tap = 0; tap < 9; ++tap) {
+          tc::mbar_wait(&b_full[sb], pb);
+          tc::tc_fence_after();
+          const int r = tap / 3, s = tap - 3 * r;
+          const uint32_t a0 = patch + (uint32_t)(r * PT_PW + s) * 128u;
+          const uint32_t b0 = tc::smem_u32(smem + L::B_OFF + sb * L::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < tc::TBK / tc::UMMA_K; ++k) {
+            const uint64_t ad = tc::smem_desc(a0 + k * 32, 16, PT_PW * 128, 2);
+            const uint64_t bd = DGRAD ? tc::smem_desc_mnmajor(b0 + k * 1024, tc::BOX_BYTES) : tc::smem_desc_kmajor(b0 + k * 32);
+            tc::mma_tf32(tmem_base, ad, bd, idesc, (sl | tap | k) ? 1u : 0u);
+          }
+          tc::mma_commit(&b_empty[sb]);
+          if (++sb == L::B_STAGES) { sb = 0; pb ^= 1; }
+        }
+        tc::mma_commit(&a_empty[sa]);
+        if (++sa == L::A_STAGES) { sa = 0; pa ^= 1; }
+      }
+      tc::mma_commit(tmem_full);
+    }
+  } else {
+    if (warp == 2) {
+      if (tc::elect_one()) {                               // ===== patch producer (then an epilogue warp like the rest) =====
+        int st = 0; uint32_t ph = 0;
+        for (int sl = 0; sl < nsl; ++sl) {
+          tc::mbar_wait(&a_empty[st], ph ^ 1);
+          tc::mbar_expect_tx(&a_full[st], PT_A_BYTES);
+          tc::tma_load_4d(smem + st * PT_A_STAGE, &tmA, &a_full[st], sl * 32, op.w0 - 1, op.h0 - 1, op.img);
+          if (++st == L::A_STAGES) { st = 0; ph ^= 1; }
+        }
+      }
+      __syncwarp();
+    }
+    tc::tc_epilogue<ConvPatchOp<TBN, DGRAD>, TBN, false>(op, e, smem, tmem_full, tmem_base, 0, nsl);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tc::tmem_dealloc(tmem_base, TBN);
+}
+
+// x: conv input (fwd) or dy (dgrad), NHWC with Cin channels; out NHWC with Cout channels, same H x W (3x3, stride 1, pad 1)
+template <bool DGRAD>
+int launch_conv3x3_patch(const float* x, const float* w, float* out, const float* res, int N, int H, int W, int Cin, int Cout,
+                         cudaStream_t stream, const char* what) {
+  ConvGeomTc g{N, H, W, Cin, Cout, 3, 3, 1, 1, H, W};
+  g.BW = PT_BW; g.BH = PT_BH; g.BI = 1;
+  g.tiles_w = (W + PT_BW - 1) / PT_BW; g.tiles_h = (H + PT_BH - 1) / PT_BH; g.tiles_n = N;
+  const int ptiles = g.tiles_w * g.tiles_h * g.tiles_n;
+  MMFN_CHECK_ARG(ptiles <= 65535, "%s: too many pixel tiles", what);
+  CUtensorMap ta, tb;
+  if (int rc = make_act_tmap(&ta, x, N, H, W, Cin, PT_PW, PT_PH, 1, 1, false)) return rc;
+  const int tbn = (Cout <= 64 || ptiles * ((Cout + 127) / 128) < 148) ? 64 : 128;
+  if (DGRAD) {
+    if (int rc = make_krsc_b_tmap(&tb, w, Cin, 3, 3, Cout)) return rc;          // w is (Co_conv = Cin here, 3, 3, C_conv = Cout)
+  } else {
+    uint64_t dims[2] = {(uint64_t)9 * Cin, (uint64_t)Cout}, strides[2] = {1, (uint64_t)9 * Cin};
+    uint32_t box[2] = {32, (uint32_t)tbn};
+    if (int rc = mmfn_make_tmap_f32(&tb, w, 2, dims, strides, box, nullptr, false)) return rc;
+  }
+  tc::Epilogue e{out, nullptr, res, nullptr, 1.f, 0, 0, 0.f, 0, nullptr};
+  auto go = [&](auto tbn_tag, auto deep_tag) -> int {
+    constexpr int TBN = decltype(tbn_tag)::value;
+    constexpr bool DEEP = decltype(deep_tag)::value;
+    using L = PatchSmem<TBN, DEEP>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t ce = cudaFuncSetAttribute(conv3x3_patch_kernel<TBN, DGRAD, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+      if (ce != cudaSuccess) { mmfn_set_error("%s: smem attribute: %s", what, cudaGetErrorString(ce)); return (int)ce; }
+      attr_set = true;
+    }
+    ConvPatchOp<TBN, DGRAD> op{g};
+    conv3x3_patch_kernel<TBN, DGRAD, DEEP><<<dim3((Cout + TBN - 1) / TBN, ptiles, 1), tc::TC_THREADS, L::TOTAL, stream>>>(ta, tb, op, e);
+    return mmfn_launch_status(what);
+  };
+  const bool deep = ptiles * ((Cout + tbn - 1) / tbn) <= 148 && Cin > 96;      // single wave and more than 3 slices
+  if (tbn == 64) return deep ? go(std::integral_constant<int, 64>{}, std::true_type{}) : go(std::integral_constant<int, 64>{}, std::false_type{});
+  return deep ? go(std::integral_constant<int, 128>{}, std::true_type{}) : go(std::integral_constant<int, 128>{}, std::false_type{});
+}
+
+static inline bool patch_conv_ok(int R, int S, int stride, int pad, int H, int W) {
+  return R == 3 && S == 3 && stride == 1 && pad == 1 && H >= 16 && W >= 8;
+}
+
 __global__ void krsc_to_crsk_kernel(const float* __restrict__ w, float* __restrict__ wt, int Co, int R, int S, int C, int flip) {
   int64_t n = (int64_t)Co * R * S * C;
   int RS = R * S;
@@ -237,6 +428,7 @@ MMFN_API int mmfn_conv2d_fwd_tf32(const float* x, const float* w, float* y, cons
   if (int rc = check_tc_geom(g, "conv_fwd_tf32")) return rc;
   MMFN_CHECK_ARG((((uintptr_t)x | (uintptr_t)w) & 15) == 0, "conv_fwd_tf32: operands must be 16-byte aligned");
   MMFN_CHECK_ARG(Wo >= 8 && Ho >= 8, "conv_fwd_tf32: output must be at least 8x8");
+  if (patch_conv_ok(R, S, stride, pad, H, W)) return launch_conv3x3_patch<false>(x, w, y, res, N, H, W, C, Co, stream, "conv_fwd_tf32");
   // 128-pixel tile: 8 rows x 16 cols of one image, or two whole 8x8 maps
   g.BW = Wo >= 16 ? 16 : 8;
   g.BH = 8;
@@ -321,6 +513,7 @@ MMFN_API int mmfn_conv2d_dgrad_tf32(const float* dy, const float* w, float* dx, 
   MMFN_CHECK_ARG(Co % 32 == 0 && C % 4 == 0, "conv_dgrad_tf32: Co % 32 == 0, C % 4 == 0");
   MMFN_CHECK_ARG((((uintptr_t)dy | (uintptr_t)w) & 15) == 0, "conv_dgrad_tf32: operands must be 16-byte aligned");
   MMFN_CHECK_ARG(W >= 8 && H >= 8, "conv_dgrad_tf32: dx must be at least 8x8");
+  if (patch_conv_ok(R, S, 1, pad, H, W)) return launch_conv3x3_patch<true>(dy, w, dx, res, N, H, W, Co, C, stream, "conv_dgrad_tf32");
   ConvGeomTc g{N, Ho, Wo, Co, C, R, S, 1, R - 1 - pad, H, W};       // roles as a forward conv: in = dy, out = dx
   g.BW = W >= 16 ? 16 : 8;
   g.BH = 8;

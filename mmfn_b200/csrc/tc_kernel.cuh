@@ -51,83 +51,12 @@ struct Smem {
   static_assert(8 * 32 * 36 * 4 + 128 * 8 <= STAGES * STAGE_BYTES, "epilogue staging does not fit");
 };
 
-// Op contract (all __device__):
-//   static constexpr bool A_MN, B_MN;
-//   void setup();                                 per-CTA decode of blockIdx (called by every thread)
-//   int kb_begin(), kb_end();                     this CTA's k-block range
-//   void load(kb, sa, sb, bar, &tmA, &tmB);       issue the TMA boxes of k-block kb (one thread)
-//   bool out_row(r, int64_t& off);                element offset of tile row r, column 0 of the OUTPUT row
-//   int n_cols();  int col0();                    valid output columns, first column of this tile
-//   bool first_split();                           bias / residual are added by the first split only
-// FULL = false compiles the epilogue down to alpha*acc + bias + residual (most launches); the
-// ReLU / mask / dropout variant is a separate instantiation so its hash arithmetic is never if-converted in.
-template <class Op, int TBN, int STAGES, bool FULL>
-__global__ void __launch_bounds__(TC_THREADS, 2)
-tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Op op, Epilogue e) {
-  using L = Smem<TBN, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-
+// Epilogue shared by every tcgen05 kernel of the library (called by warps 2..9 = 8 epilogue warps; `smem` is the
+// 1024-byte aligned dynamic shared memory whose first 8*32*36*4 + 128*8 bytes are idle once tmem_full has fired).
+template <class Op, int TBN, bool FULL>
+__device__ __forceinline__ void tc_epilogue(const Op& op, const Epilogue& e, uint8_t* smem, uint64_t* tmem_full,
+                                            uint32_t tmem_base, int kb0, int kb1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  op.setup();
-  const int kb0 = op.kb_begin(), kb1 = op.kb_end();
-  if (threadIdx.x == 0) TC_STAMP(0);                      // kernel entry
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmB);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, TBN);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) TC_STAMP(1);                      // barriers + TMEM ready
-
-  if (warp == 0) {
-    if (elect_one()) {                                   // ===== TMA producer =====
-      int stage = 0; uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * L::STAGE_BYTES;
-        mbar_expect_tx(&full[stage], L::STAGE_BYTES);
-        op.load(kb, sa, sa + L::A_BYTES, &full[stage], &tmA, &tmB);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (elect_one()) {                                   // ===== MMA issuer =====
-      const uint32_t idesc = idesc_tf32(TBM, TBN, Op::A_MN, Op::B_MN);
-      int stage = 0; uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        if (kb == kb0) TC_STAMP(2);                      // first operands landed
-        const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-        const uint32_t sb = sa + L::A_BYTES;
-#pragma unroll
-        for (int k = 0; k < TBK / UMMA_K; ++k) {
-          // K-major: 8 tf32 = 32 bytes along the swizzled row; MN-major: the next 8 k-rows = 1024 bytes
-          uint64_t ad = Op::A_MN ? smem_desc_mnmajor(sa + k * 1024, BOX_BYTES) : smem_desc_kmajor(sa + k * 32);
-          uint64_t bd = Op::B_MN ? smem_desc_mnmajor(sb + k * 1024, BOX_BYTES) : smem_desc_kmajor(sb + k * 32);
-          mma_tf32(tmem_base, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-        }
-        mma_commit(&empty[stage]);                       // frees the smem slot once these MMAs retire
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
-      }
-      mma_commit(tmem_full);                             // accumulator complete
-      TC_STAMP(3);                                       // all MMAs issued
-    }
-  } else {
     // ===== epilogue: 8 warps; warp w owns TMEM lane quarter (w % 4) and every other 32-column chunk =====
     // tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns).  The rows are
     // re-tiled through shared memory (the idle pipeline stages, 36-float pitch: conflict-free for
@@ -252,6 +181,86 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
       if (threadIdx.x == 64 && c == 0) TC_STAMP(9);         // first chunk's stores issued
     }
+}
+
+// Op contract (all __device__):
+//   static constexpr bool A_MN, B_MN;
+//   void setup();                                 per-CTA decode of blockIdx (called by every thread)
+//   int kb_begin(), kb_end();                     this CTA's k-block range
+//   void load(kb, sa, sb, bar, &tmA, &tmB);       issue the TMA boxes of k-block kb (one thread)
+//   bool out_row(r, int64_t& off);                element offset of tile row r, column 0 of the OUTPUT row
+//   int n_cols();  int col0();                    valid output columns, first column of this tile
+//   bool first_split();                           bias / residual are added by the first split only
+// FULL = false compiles the epilogue down to alpha*acc + bias + residual (most launches); the
+// ReLU / mask / dropout variant is a separate instantiation so its hash arithmetic is never if-converted in.
+template <class Op, int TBN, int STAGES, bool FULL>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Op op, Epilogue e) {
+  using L = Smem<TBN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  op.setup();
+  const int kb0 = op.kb_begin(), kb1 = op.kb_end();
+  if (threadIdx.x == 0) TC_STAMP(0);                      // kernel entry
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TBN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TC_STAMP(1);                      // barriers + TMEM ready
+
+  if (warp == 0) {
+    if (elect_one()) {                                   // ===== TMA producer =====
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * L::STAGE_BYTES;
+        mbar_expect_tx(&full[stage], L::STAGE_BYTES);
+        op.load(kb, sa, sa + L::A_BYTES, &full[stage], &tmA, &tmB);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {                                   // ===== MMA issuer =====
+      const uint32_t idesc = idesc_tf32(TBM, TBN, Op::A_MN, Op::B_MN);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (kb == kb0) TC_STAMP(2);                      // first operands landed
+        const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+        const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TBK / UMMA_K; ++k) {
+          // K-major: 8 tf32 = 32 bytes along the swizzled row; MN-major: the next 8 k-rows = 1024 bytes
+          uint64_t ad = Op::A_MN ? smem_desc_mnmajor(sa + k * 1024, BOX_BYTES) : smem_desc_kmajor(sa + k * 32);
+          uint64_t bd = Op::B_MN ? smem_desc_mnmajor(sb + k * 1024, BOX_BYTES) : smem_desc_kmajor(sb + k * 32);
+          mma_tf32(tmem_base, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        mma_commit(&empty[stage]);                       // frees the smem slot once these MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      mma_commit(tmem_full);                             // accumulator complete
+      TC_STAMP(3);                                       // all MMAs issued
+    }
+  } else {
+    tc_epilogue<Op, TBN, FULL>(op, e, smem, tmem_full, tmem_base, kb0, kb1);
   }
   if (threadIdx.x == 64) TC_STAMP(5);                    // epilogue stores issued
   tc_fence_before();
