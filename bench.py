@@ -116,8 +116,8 @@ def run_reference(args):
 
 # ncu --set full captures of the headline shapes (tools/ncu_targets.py -> profiles/r01_ncu_full_kernels.json)
 NCU_KERNEL_OF = {
-    ("conv2d_fwd_tf32", 16, 16, 256, 256, 3, 16): ("tc_kernel<ConvFwdOp<64>, 64, 4, 0>", "(4, 32, 2)"),
-    ("conv2d_fwd_tf32", 16, 64, 64, 64, 3, 64): ("tc_kernel<ConvFwdOp<64>, 64, 4, 0>", "(1, 512, 1)"),
+    ("conv2d_fwd_tf32", 16, 16, 256, 256, 3, 16): ("conv3x3_patch_kernel<64, 0, 1>", "(4, 32, 1)"),
+    ("conv2d_fwd_tf32", 16, 64, 64, 64, 3, 64): ("conv3x3_patch_kernel<64, 0, 0>", "(1, 512, 1)"),
     ("gemm_tf32", 4096, 2048, 512, 1): ("tc_kernel<GemmOp<0, 0, 128>, 128, 3, 1>", "(16, 32, 1)"),
 }
 
