@@ -338,7 +338,9 @@ int launch_conv3x3_patch(const float* x, const float* w, float* out, const float
   MMFN_CHECK_ARG(ptiles <= 65535, "%s: too many pixel tiles", what);
   CUtensorMap ta, tb;
   if (int rc = make_act_tmap(&ta, x, N, H, W, Cin, PT_PW, PT_PH, 1, 1, false)) return rc;
-  const int tbn = (Cout <= 64 || ptiles * ((Cout + 127) / 128) < 148) ? 64 : 128;
+  // 128-wide filter tiles as soon as they still give ~100 CTAs: a TF32 MMA re-reads its 4 KB A operand from shared
+  // memory for every 128 x N x 8 step, so N = 64 is bound by operand bandwidth (6 KB per 33 clk of math), N = 128 much less
+  const int tbn = (Cout % 128 == 0 && ptiles * (Cout / 128) >= 100) ? 128 : (Cout <= 64 || ptiles * ((Cout + 127) / 128) < 148) ? 64 : 128;
   if (DGRAD) {
     if (int rc = make_krsc_b_tmap(&tb, w, Cin, 3, 3, Cout)) return rc;          // w is (Co_conv = Cin here, 3, 3, C_conv = Cout)
   } else {
