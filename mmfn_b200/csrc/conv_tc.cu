@@ -385,31 +385,7 @@ __global__ void krsc_to_crsk_kernel(const float* __restrict__ w, float* __restri
   }
 }
 
-// y[n, 2h, 2w, :] = x[n, h, w, :], zeros elsewhere (y is (N, 2H, 2W, C)); float4 over channels
-__global__ void zero_upsample2_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N, int H, int W, int C4) {
-  int64_t n = (int64_t)N * 2 * H * 2 * W * C4;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C4);
-    int64_t t = i / C4;
-    int w = (int)(t % (2 * W)); t /= 2 * W;
-    int h = (int)(t % (2 * H));
-    int b = (int)(t / (2 * H));
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!(h & 1) && !(w & 1)) v = __ldg(x + (((int64_t)b * H + (h >> 1)) * W + (w >> 1)) * C4 + c);
-    y[i] = v;
-  }
-}
-
 }  // namespace
-
-// y(N,2H,2W,C) = x(N,H,W,C) with zeros inserted between pixels: turns the data-gradient of a stride-2
-// convolution into a stride-1 forward convolution (of the up-sampled dy with the mirrored filters).
-MMFN_API int mmfn_zero_upsample2_f32(const float* x, float* y, int N, int H, int W, int C, cudaStream_t stream) {
-  MMFN_CHECK_ARG(x && y && N > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "zero_upsample2: bad args (C % 4 == 0)");
-  int64_t n = (int64_t)N * 4 * H * W * (C / 4);
-  zero_upsample2_kernel<<<grid_1d(n, 256), 256, 0, stream>>>((const float4*)x, (float4*)y, N, H, W, C / 4);
-  return mmfn_launch_status("zero_upsample2");
-}
 
 // wt[c][r][s][co] = w[co][r][s][c]; with flip != 0 the taps are mirrored (r,s -> R-1-r, S-1-s), which
 // turns a stride-1 data-gradient into a plain forward convolution of dy with wt.

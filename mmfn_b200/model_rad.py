@@ -127,7 +127,7 @@ class ConvBN:
     """conv (bias-free) -> BatchNorm2d [-> + residual] [-> ReLU]; torchvision BasicBlock pieces."""
 
     def __init__(self, st, conv_key, bn_key, stride, pad, dgrad=True):
-        self.dgrad, self.wt, self.wt_ev = dgrad, None, None
+        self.dgrad = dgrad
         self.w, self.dw = st.p(conv_key), st.g(conv_key)
         self.gam, self.dgam = st.p(bn_key + ".weight"), st.g(bn_key + ".weight")
         self.bet, self.dbet = st.p(bn_key + ".bias"), st.g(bn_key + ".bias")
@@ -142,12 +142,6 @@ class ConvBN:
             self.z, self.col, self.w_pad = ops.conv2d_fwd_im2col(x, self.w, self.stride, self.pad, getattr(self, "w_pad", None))
         else:
             self.z = ops.conv2d_fwd(x, self.w, self.stride, self.pad)
-        if train and self.dgrad and ops.dgrad_uses_flipped_filter(self.w, x.shape, self.stride):
-            # the data-gradient conv reads the mirrored CRSK filters: a pure function of the weights, so
-            # the transform is issued here on the side stream instead of on the backward critical path
-            def flip():
-                self.wt = ops.filter_crsk(self.w, flip=True)
-            self.wt_ev = _Aux.fork(flip)
         if train:
             self.y, self.mean, self.rstd = ops.bn_train_fwd(self.z, self.gam, self.bet, self.rm, self.rv, res=res, relu=relu)
         else:
@@ -164,11 +158,8 @@ class ConvBN:
             _Aux.run(lambda: ops.conv2d_wgrad_(dz, x, self.dw, self.stride, self.pad), dz, x)
         dx = None
         if need_dx:
-            _Aux.wait(self.wt_ev)
-            dx = ops.conv2d_dgrad(dz, self.w, self.x.shape, self.stride, self.pad, res=dx_res, wt_flipped=self.wt)
-            if self.wt is not None:
-                _Aux.keep.append(self.wt)                # allocated on the side stream: hold until join_all()
-        self.x = self.z = self.y = self.wt = self.wt_ev = self.col = None
+            dx = ops.conv2d_dgrad(dz, self.w, self.x.shape, self.stride, self.pad, res=dx_res)
+        self.x = self.z = self.y = self.col = None
         return dx, dres
 
 

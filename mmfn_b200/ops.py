@@ -187,12 +187,6 @@ def filter_crsk(w_krsc, flip=False):
     return wt
 
 
-def dgrad_uses_flipped_filter(w_krsc, x_shape, stride):
-    """Kept for callers that pre-computed mirrored CRSK filters: the tensor-core data gradient now reads the KRSC
-    filters directly (MN-major B operand), so no transformed copy is needed any more."""
-    return False
-
-
 def _tc_dgrad_ok(C, Co, H, W, stride, Ho, Wo):
     if not (TF32 and C % 32 == 0 and Co % 32 == 0):
         return False
@@ -201,7 +195,7 @@ def _tc_dgrad_ok(C, Co, H, W, stride, Ho, Wo):
     return stride == 2 and H == 2 * Ho and W == 2 * Wo and H >= 16 and W >= 16
 
 
-def conv2d_dgrad(dy, w_krsc, x_shape, stride, pad, res=None, wt_flipped=None):
+def conv2d_dgrad(dy, w_krsc, x_shape, stride, pad, res=None):
     """Data gradient of conv2d_fwd.  Tensor-core path: stride 1 = forward convolution of dy with mirrored taps;
     stride 2 = four parity classes of dx, each a small stride-1 implicit GEMM over dy with only the taps that can
     reach it (no zero insertion, exact MAC count).  Both read the KRSC filters as they are."""
