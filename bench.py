@@ -137,8 +137,17 @@ def ncu_traffic(dom):
 def dominant_kernel_chain(ops, L, dev, prof_steps):
     """Pick the tensor-core launch shape with the largest eager total and time it as a graph chain."""
     import torch
-    cand = [r for r in L.last_shapes if r[0][0] in ("conv2d_fwd_tf32", "gemm_tf32") and (r[0][0] != "gemm_tf32" or r[0][4] == 1)]
-    key, n, _, flops = cand[0]
+    # the stride-1 3x3 data gradient runs the SAME kernel as the forward convolution (mirrored taps): count them together
+    merged = {}
+    for key, n, ms, flops in L.last_shapes:
+        if key[0] == "conv2d_dgrad_tf32" and key[3] == key[4] and key[2] == key[6]:
+            key = ("conv2d_fwd_tf32",) + tuple(key[1:])
+        if key[0] not in ("conv2d_fwd_tf32", "gemm_tf32") or (key[0] == "gemm_tf32" and key[4] != 1):
+            continue
+        m = merged.setdefault(tuple(key), [0, 0.0, flops])
+        m[0] += n
+        m[1] += ms
+    key, (n, _, flops) = max(merged.items(), key=lambda kv: kv[1][1])
     if key[0] == "conv2d_fwd_tf32":
         _, N, H, C, Co, R, Ho = key
         stride = H // Ho
