@@ -145,8 +145,10 @@ gemm_simt_kernel(AL A, BL B, int M, int N, int K, Epilogue e, int nb1, int split
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   const int ty = tid >> 4, tx = tid & 15;
-  for (int k0 = kbeg; k0 < kend; k0 += BK) {
-    float av[4], bv[4];
+  // global -> register fetch of one BK-deep tile pair (issued one tile AHEAD of the math: the loads of tile k0 + BK
+  // fly while tile k0 is multiplied out of shared memory, so the K loop no longer pays a full memory round trip per step)
+  float av[4], bv[4];
+  auto fetch = [&](int k0) {
     if (akf) {
       typename AL::Kc kc = A.kc(k0 + (tid & 15));
       kc.ok = kc.ok && (k0 + (tid & 15) < kend);
@@ -175,13 +177,17 @@ gemm_simt_kernel(AL A, BL B, int M, int N, int K, Epilogue e, int nb1, int split
         bv[i] = B.load(bbase, brow[0], kc);
       }
     }
-    __syncthreads();
+  };
+  if (kbeg < kend) fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    __syncthreads();                                   // previous tile fully consumed
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       if (akf) As[tid & 15][(tid >> 4) + 16 * i] = av[i]; else As[(tid >> 6) + 4 * i][tid & 63] = av[i];
       if (bkf) Bs[tid & 15][(tid >> 4) + 16 * i] = bv[i]; else Bs[(tid >> 6) + 4 * i][tid & 63] = bv[i];
     }
     __syncthreads();
+    if (k0 + BK < kend) fetch(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
