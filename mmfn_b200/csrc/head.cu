@@ -9,121 +9,153 @@ constexpr int HID = 64;
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// block per sample, 64 threads.  saved: (B, steps, 5, 64) = h_prev, r, z, n, gh_n ; xin: (B, steps, 2)
-__global__ void gru_head_fwd_kernel(const float* __restrict__ z0, const float* __restrict__ target,
-                                    const float* __restrict__ w_ih, const float* __restrict__ w_hh,
-                                    const float* __restrict__ b_ih, const float* __restrict__ b_hh,
-                                    const float* __restrict__ w_out, const float* __restrict__ b_out,
-                                    int steps, float* __restrict__ pred, float* __restrict__ saved,
-                                    float* __restrict__ xin_saved, float* __restrict__ hlast) {
-  __shared__ float h[HID], hn[HID];
+// Block per sample, 192 threads = one per gate row of W_hh, whose 64 weights stay in registers for the whole roll-out
+// (the 4 steps are strictly sequential, so the kernel is pure latency: no global weight reads inside the time loop).
+// saved: (B, steps, 5, 64) = h_prev, r, z, n, gh_n ; xin: (B, steps, 2)
+constexpr int GRU_THREADS = 3 * HID;
+
+__global__ void __launch_bounds__(GRU_THREADS)
+gru_head_fwd_kernel(const float* __restrict__ z0, const float* __restrict__ target,
+                    const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                    const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                    const float* __restrict__ w_out, const float* __restrict__ b_out,
+                    int steps, float* __restrict__ pred, float* __restrict__ saved,
+                    float* __restrict__ xin_saved, float* __restrict__ hlast) {
+  __shared__ float h[HID], hn[HID], gi_s[3 * HID], gh_s[3 * HID];
   __shared__ float x[2], xin[2];
-  int b = blockIdx.x, j = threadIdx.x;
-  h[j] = z0[b * HID + j];
-  if (j < 2) x[j] = 0.f;
+  const int b = blockIdx.x, row = threadIdx.x;
+  float w[HID];
+  if ((reinterpret_cast<uintptr_t>(w_hh) & 15) == 0) {
+#pragma unroll
+    for (int q = 0; q < HID / 4; ++q) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(w_hh + row * HID) + q);
+      w[4 * q] = t4.x; w[4 * q + 1] = t4.y; w[4 * q + 2] = t4.z; w[4 * q + 3] = t4.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < HID; ++k) w[k] = __ldg(w_hh + row * HID + k);
+  }
+  const float wi0 = w_ih[row * 2], wi1 = w_ih[row * 2 + 1], bi = b_ih[row], bh = b_hh[row];
+  if (row < HID) h[row] = z0[b * HID + row];
+  if (row < 2) x[row] = 0.f;
   __syncthreads();
   for (int t = 0; t < steps; ++t) {
-    if (j < 2) { xin[j] = x[j] + target[b * 2 + j]; xin_saved[(b * steps + t) * 2 + j] = xin[j]; }
+    if (row < 2) { xin[row] = x[row] + target[b * 2 + row]; xin_saved[(b * steps + t) * 2 + row] = xin[row]; }
     __syncthreads();
-    float gi[3], gh[3];
+    float a = bh;
 #pragma unroll
-    for (int g = 0; g < 3; ++g) {
-      int row = g * HID + j;
-      gi[g] = w_ih[row * 2] * xin[0] + w_ih[row * 2 + 1] * xin[1] + b_ih[row];
-      float a = b_hh[row];
-      const float* wr = w_hh + row * HID;
-      for (int k = 0; k < HID; ++k) a += wr[k] * h[k];
-      gh[g] = a;
-    }
-    float r = sigmoidf_(gi[0] + gh[0]);
-    float zg = sigmoidf_(gi[1] + gh[1]);
-    float n = tanhf(gi[2] + r * gh[2]);
-    float hnew = (1.f - zg) * n + zg * h[j];
-    float* sv = saved + ((int64_t)(b * steps + t) * 5) * HID;
-    sv[j] = h[j]; sv[HID + j] = r; sv[2 * HID + j] = zg; sv[3 * HID + j] = n; sv[4 * HID + j] = gh[2];
-    hn[j] = hnew;
+    for (int k = 0; k < HID; ++k) a += w[k] * h[k];
+    gi_s[row] = wi0 * xin[0] + wi1 * xin[1] + bi;
+    gh_s[row] = a;
     __syncthreads();
-    h[j] = hnew;
-    if (j < 2) {
-      float d = b_out[j];
-      for (int k = 0; k < HID; ++k) d += w_out[j * HID + k] * hn[k];
-      x[j] += d;
-      pred[(b * steps + t) * 2 + j] = x[j];
+    if (row < HID) {
+      const int j = row;
+      const float r = sigmoidf_(gi_s[j] + gh_s[j]);
+      const float zg = sigmoidf_(gi_s[HID + j] + gh_s[HID + j]);
+      const float n = tanhf(gi_s[2 * HID + j] + r * gh_s[2 * HID + j]);
+      const float hnew = (1.f - zg) * n + zg * h[j];
+      float* sv = saved + ((int64_t)(b * steps + t) * 5) * HID;
+      sv[j] = h[j]; sv[HID + j] = r; sv[2 * HID + j] = zg; sv[3 * HID + j] = n; sv[4 * HID + j] = gh_s[2 * HID + j];
+      hn[j] = hnew;
+    }
+    __syncthreads();
+    if (row < HID) h[row] = hn[row];
+    if (row >= HID && row < HID + 2) {                     // output layer: two threads of the second warp pair
+      const int c = row - HID;
+      float d = b_out[c];
+      for (int k = 0; k < HID; ++k) d += w_out[c * HID + k] * hn[k];
+      x[c] += d;
+      pred[(b * steps + t) * 2 + c] = x[c];
     }
     __syncthreads();
   }
-  hlast[b * HID + j] = h[j];
+  if (row < HID) hlast[b * HID + row] = h[row];
 }
 
-__global__ void gru_head_bwd_kernel(const float* __restrict__ dpred, const float* __restrict__ saved,
-                                    const float* __restrict__ xin_saved, const float* __restrict__ hlast,
-                                    const float* __restrict__ w_ih, const float* __restrict__ w_hh,
-                                    const float* __restrict__ w_out, int steps,
-                                    float* __restrict__ dz0, float* __restrict__ dw_ih, float* __restrict__ dw_hh,
-                                    float* __restrict__ db_ih, float* __restrict__ db_hh,
-                                    float* __restrict__ dw_out, float* __restrict__ db_out) {
-  __shared__ float dgi[3 * HID], dgh[3 * HID], hprev[HID];
-  __shared__ float gx[2], dxin[2], dxc[2];
-  __shared__ float red[2][HID];
-  int b = blockIdx.x, j = threadIdx.x;
-  float dh = 0.f;
-  if (j < 2) dxc[j] = 0.f;
+// Backward through the roll-out.  Thread = gate row: its row of dW_hh (64 values) and its dW_ih / bias gradients are
+// accumulated in registers over the time steps and leave with ONE atomic pass at the end; the W_hh^T dgh product is
+// split over the three gates (thread (g, j) sums gate g's 64 rows of column j, coalesced reads).
+__global__ void __launch_bounds__(GRU_THREADS)
+gru_head_bwd_kernel(const float* __restrict__ dpred, const float* __restrict__ saved,
+                    const float* __restrict__ xin_saved, const float* __restrict__ hlast,
+                    const float* __restrict__ w_ih, const float* __restrict__ w_hh,
+                    const float* __restrict__ w_out, int steps,
+                    float* __restrict__ dz0, float* __restrict__ dw_ih, float* __restrict__ dw_hh,
+                    float* __restrict__ db_ih, float* __restrict__ db_hh,
+                    float* __restrict__ dw_out, float* __restrict__ db_out) {
+  __shared__ float dgi[3 * HID], dgh[3 * HID], hprev[HID], part[3][HID];
+  __shared__ float gx[2], dxc[2], px[2][GRU_THREADS / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, j = tid & (HID - 1), g = tid / HID;
+  const int lane = tid & 31, warp = tid >> 5;
+  const float wi0 = w_ih[tid * 2], wi1 = w_ih[tid * 2 + 1];
+  float dwhh[HID];
+#pragma unroll
+  for (int k = 0; k < HID; ++k) dwhh[k] = 0.f;
+  float dwih0 = 0.f, dwih1 = 0.f, dbih = 0.f, dbhh = 0.f, dwo0 = 0.f, dwo1 = 0.f, dbo = 0.f;
+  float dh = 0.f, dhp = 0.f;
+  if (tid < 2) dxc[tid] = 0.f;
   __syncthreads();
   for (int t = steps - 1; t >= 0; --t) {
     const float* sv = saved + ((int64_t)(b * steps + t) * 5) * HID;
-    float hp = sv[j], r = sv[HID + j], zg = sv[2 * HID + j], n = sv[3 * HID + j], ghn = sv[4 * HID + j];
-    // h' of this step = h_prev of next step (or hlast)
-    float hnew = (t == steps - 1) ? hlast[b * HID + j] : saved[((int64_t)(b * steps + t + 1) * 5) * HID + j];
-    if (j < 2) gx[j] = dpred[(b * steps + t) * 2 + j] + dxc[j];
-    hprev[j] = hp;
+    float hp = 0.f, r = 0.f, zg = 0.f, n = 0.f, ghn = 0.f, hnew = 0.f;
+    if (tid < HID) {
+      hp = sv[j]; r = sv[HID + j]; zg = sv[2 * HID + j]; n = sv[3 * HID + j]; ghn = sv[4 * HID + j];
+      // h' of this step = h_prev of the next step (or hlast)
+      hnew = (t == steps - 1) ? hlast[b * HID + j] : saved[((int64_t)(b * steps + t + 1) * 5) * HID + j];
+      hprev[j] = hp;
+    }
+    if (tid < 2) gx[tid] = dpred[(b * steps + t) * 2 + tid] + dxc[tid];
     __syncthreads();
-    // output layer
-    atomicAdd(dw_out + j, gx[0] * hnew);
-    atomicAdd(dw_out + HID + j, gx[1] * hnew);
-    if (j < 2) atomicAdd(db_out + j, gx[j]);
-    float dhn = dh + w_out[j] * gx[0] + w_out[HID + j] * gx[1];
-    float dn = dhn * (1.f - zg), dzg = dhn * (hp - n);
-    float dhp = dhn * zg;
-    float dan = dn * (1.f - n * n);
-    float dr = dan * ghn;
-    float daz = dzg * zg * (1.f - zg);
-    float dar = dr * r * (1.f - r);
-    dgi[j] = dar; dgi[HID + j] = daz; dgi[2 * HID + j] = dan;
-    dgh[j] = dar; dgh[HID + j] = daz; dgh[2 * HID + j] = dan * r;
+    if (tid < HID) {
+      dwo0 += gx[0] * hnew;
+      dwo1 += gx[1] * hnew;
+      const float dhn = dh + w_out[j] * gx[0] + w_out[HID + j] * gx[1];
+      const float dn = dhn * (1.f - zg), dzg = dhn * (hp - n);
+      dhp = dhn * zg;
+      const float dan = dn * (1.f - n * n);
+      const float dr = dan * ghn;
+      const float daz = dzg * zg * (1.f - zg);
+      const float dar = dr * r * (1.f - r);
+      dgi[j] = dar; dgi[HID + j] = daz; dgi[2 * HID + j] = dan;
+      dgh[j] = dar; dgh[HID + j] = daz; dgh[2 * HID + j] = dan * r;
+    }
+    if (tid < 2) dbo += gx[tid];
+    __syncthreads();
+    // parameter gradients of row `tid`
     const float xi0 = xin_saved[(b * steps + t) * 2], xi1 = xin_saved[(b * steps + t) * 2 + 1];
-    __syncthreads();
-    // parameter gradients
+    const float gi = dgi[tid], gh = dgh[tid];
+    dwih0 += gi * xi0; dwih1 += gi * xi1; dbih += gi; dbhh += gh;
 #pragma unroll
-    for (int g = 0; g < 3; ++g) {
-      int row = g * HID + j;
-      atomicAdd(dw_ih + row * 2, dgi[row] * xi0);
-      atomicAdd(dw_ih + row * 2 + 1, dgi[row] * xi1);
-      atomicAdd(db_ih + row, dgi[row]);
-      atomicAdd(db_hh + row, dgh[row]);
-    }
-    for (int row = 0; row < 3 * HID; ++row) atomicAdd(dw_hh + row * HID + j, dgh[row] * hprev[j]);
-    // dh_prev += W_hh^T dgh ; dx_in = W_ih^T dgi
-    float acc = dhp;
-    for (int row = 0; row < 3 * HID; ++row) acc += w_hh[row * HID + j] * dgh[row];
-    float p0 = 0.f, p1 = 0.f;
-#pragma unroll
-    for (int g = 0; g < 3; ++g) {
-      int row = g * HID + j;
-      p0 += w_ih[row * 2] * dgi[row];
-      p1 += w_ih[row * 2 + 1] * dgi[row];
-    }
-    red[0][j] = p0; red[1][j] = p1;
+    for (int k = 0; k < HID; ++k) dwhh[k] += gh * hprev[k];
+    // dh_prev += W_hh^T dgh: gate g's share of column j
+    float acc = 0.f;
+#pragma unroll 8
+    for (int rr = 0; rr < HID; ++rr) acc += __ldg(w_hh + (g * HID + rr) * HID + j) * dgh[g * HID + rr];
+    part[g][j] = acc;
+    // dx_in = W_ih^T dgi: block reduction over the 192 rows
+    float p0 = warp_sum(wi0 * gi), p1 = warp_sum(wi1 * gi);
+    if (lane == 0) { px[0][warp] = p0; px[1][warp] = p1; }
     __syncthreads();
-    if (j < 2) {
-      float s = 0.f;
-      for (int k = 0; k < HID; ++k) s += red[j][k];
-      dxin[j] = s;
-      dxc[j] = gx[j] + s;
+    if (tid < HID) dh = dhp + part[0][j] + part[1][j] + part[2][j];
+    if (tid < 2) {
+      float sacc = 0.f;
+      for (int wv = 0; wv < GRU_THREADS / 32; ++wv) sacc += px[tid][wv];
+      dxc[tid] = gx[tid] + sacc;
     }
-    dh = acc;
     __syncthreads();
   }
-  dz0[b * HID + j] = dh;
+  if (tid < HID) {
+    dz0[b * HID + j] = dh;
+    atomicAdd(dw_out + j, dwo0);
+    atomicAdd(dw_out + HID + j, dwo1);
+  }
+  if (tid < 2) atomicAdd(db_out + tid, dbo);
+  atomicAdd(dw_ih + tid * 2, dwih0);
+  atomicAdd(dw_ih + tid * 2 + 1, dwih1);
+  atomicAdd(db_ih + tid, dbih);
+  atomicAdd(db_hh + tid, dbhh);
+#pragma unroll
+  for (int k = 0; k < HID; ++k) atomicAdd(dw_hh + tid * HID + k, dwhh[k]);
 }
 
 // loss = mean |pred - gt| ; dpred = sign(pred - gt) * gscale / n
@@ -178,7 +210,7 @@ MMFN_API int mmfn_gru_head_fwd(const float* z0, const float* target, const float
   MMFN_CHECK_ARG(z0 && target && w_ih && w_hh && b_ih && b_hh && w_out && b_out && pred && saved && xin_saved && hlast,
                  "gru_head_fwd: null pointer");
   MMFN_CHECK_ARG(B > 0 && steps > 0, "gru_head_fwd: bad sizes");
-  gru_head_fwd_kernel<<<B, HID, 0, stream>>>(z0, target, w_ih, w_hh, b_ih, b_hh, w_out, b_out, steps, pred, saved, xin_saved, hlast);
+  gru_head_fwd_kernel<<<B, GRU_THREADS, 0, stream>>>(z0, target, w_ih, w_hh, b_ih, b_hh, w_out, b_out, steps, pred, saved, xin_saved, hlast);
   return mmfn_launch_status("gru_head_fwd");
 }
 
@@ -190,7 +222,7 @@ MMFN_API int mmfn_gru_head_bwd(const float* dpred, const float* saved, const flo
   MMFN_CHECK_ARG(dpred && saved && xin_saved && hlast && w_ih && w_hh && w_out && dz0 && dw_ih && dw_hh && db_ih && db_hh &&
                  dw_out && db_out, "gru_head_bwd: null pointer");
   MMFN_CHECK_ARG(B > 0 && steps > 0, "gru_head_bwd: bad sizes");
-  gru_head_bwd_kernel<<<B, HID, 0, stream>>>(dpred, saved, xin_saved, hlast, w_ih, w_hh, w_out, steps, dz0, dw_ih, dw_hh,
+  gru_head_bwd_kernel<<<B, GRU_THREADS, 0, stream>>>(dpred, saved, xin_saved, hlast, w_ih, w_hh, w_out, steps, dz0, dw_ih, dw_hh,
                                              db_ih, db_hh, dw_out, db_out);
   return mmfn_launch_status("gru_head_bwd");
 }
