@@ -106,25 +106,49 @@ struct FeatPtrs { const float* p[4]; };
 struct FeatPtrsW { float* p[4]; };
 
 // tokens[b, m*64 + ph*8 + pw, c] = drop(mean_{k x k} feat_m + pos_emb + vel_w*v[b] + vel_b)
-__global__ void tokens_fwd_kernel(FeatPtrs f, int nmod, int B, int H, int W, int C,
-                                  const float* __restrict__ pos, const float* __restrict__ vel_w,
-                                  const float* __restrict__ vel_b, const float* __restrict__ vel,
-                                  float* __restrict__ tok, float drop_p, uint64_t seed) {
-  int T = nmod * 64, kh = H / 8, kw = W / 8;
-  float inv = 1.0f / (float)(kh * kw);
-  int64_t n = (int64_t)B * T * C;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(i % C);
-    int64_t t2 = i / C;
-    int t = (int)(t2 % T);
-    int b = (int)(t2 / T);
-    int m = t >> 6, ph = (t >> 3) & 7, pw = t & 7;
-    const float* src = f.p[m] + (((int64_t)b * H + ph * kh) * W + pw * kw) * C + c;
-    float s = 0.f;
-    for (int r = 0; r < kh; ++r)
-      for (int q = 0; q < kw; ++q) s += __ldg(src + ((int64_t)r * W + q) * C);
-    float v = s * inv + pos[(int64_t)t * C + c] + vel_w[c] * vel[b] + vel_b[c];
-    tok[i] = v * mmfn_dropout_scale(drop_p, seed, (uint64_t)i);
+// One CTA per (sample, token): the kh x kw window is spread over 256 / (C/4) pixel lanes, 4 channels per thread
+// (float4 loads), reduced through shared memory; C % 4 == 0.
+__global__ void __launch_bounds__(256)
+tokens_fwd_kernel(FeatPtrs f, int nmod, int B, int H, int W, int C,
+                  const float* __restrict__ pos, const float* __restrict__ vel_w,
+                  const float* __restrict__ vel_b, const float* __restrict__ vel,
+                  float* __restrict__ tok, float drop_p, uint64_t seed) {
+  extern __shared__ float4 red4[];                           // [lanes][C4]
+  const int T = nmod * 64, kh = H / 8, kw = W / 8, C4 = C >> 2;
+  const int b = blockIdx.x / T, t = blockIdx.x - b * T;
+  const int m = t >> 6, ph = (t >> 3) & 7, pw = t & 7;
+  const int lanes = blockDim.x / C4;                         // host guarantees >= 1
+  const int cq = threadIdx.x % C4, lane = threadIdx.x / C4;
+  const float* src = f.p[m] + (((int64_t)b * H + ph * kh) * W + pw * kw) * C;
+  const int npx = kh * kw;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane < lanes) {
+    for (int i = lane; i < npx; i += lanes) {
+      const int r = i / kw, q = i - r * kw;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((int64_t)r * W + q) * C) + cq);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    red4[lane * C4 + cq] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < C4) {
+    for (int l = 1; l < lanes; ++l) {
+      const float4 u = red4[l * C4 + cq];
+      acc.x += u.x; acc.y += u.y; acc.z += u.z; acc.w += u.w;
+    }
+    const float inv = 1.0f / (float)npx, vb = vel[b];
+    const int c = cq * 4;
+    const float4 pe = __ldg(reinterpret_cast<const float4*>(pos + (int64_t)t * C + c));
+    const float4 vw = __ldg(reinterpret_cast<const float4*>(vel_w + c)), vbias = __ldg(reinterpret_cast<const float4*>(vel_b + c));
+    const int64_t i0 = ((int64_t)b * T + t) * C + c;
+    float ds[4];
+    mmfn_dropout_scale4(drop_p, seed, (uint64_t)i0, ds);     // i0 % 4 == 0
+    float4 o;
+    o.x = (acc.x * inv + pe.x + vw.x * vb + vbias.x) * ds[0];
+    o.y = (acc.y * inv + pe.y + vw.y * vb + vbias.y) * ds[1];
+    o.z = (acc.z * inv + pe.z + vw.z * vb + vbias.z) * ds[2];
+    o.w = (acc.w * inv + pe.w + vw.w * vb + vbias.w) * ds[3];
+    *reinterpret_cast<float4*>(tok + i0) = o;
   }
 }
 
@@ -368,8 +392,11 @@ MMFN_API int mmfn_tokens_fwd(const float* f0, const float* f1, const float* f2, 
                  "tokens_fwd: bad modality pointers");
   MMFN_CHECK_ARG(pos_emb && vel_w && vel_b && velocity && tokens, "tokens_fwd: null pointer");
   MMFN_CHECK_ARG(B > 0 && C > 0 && H >= 8 && W >= 8 && H % 8 == 0 && W % 8 == 0, "tokens_fwd: H,W must be multiples of 8");
+  MMFN_CHECK_ARG(C % 4 == 0 && C <= 1024 && (((uintptr_t)f0 | (uintptr_t)f1 | (uintptr_t)f2 | (uintptr_t)f3 | (uintptr_t)pos_emb |
+                                               (uintptr_t)vel_w | (uintptr_t)vel_b | (uintptr_t)tokens) & 15) == 0,
+                 "tokens_fwd: C % 4 == 0, C <= 1024, 16-byte aligned buffers");
   FeatPtrs f{{f0, f1, f2, f3}};
-  tokens_fwd_kernel<<<grid_1d((int64_t)B * nmod * 64 * C, 256), 256, 0, stream>>>(f, nmod, B, H, W, C, pos_emb, vel_w, vel_b,
+  tokens_fwd_kernel<<<B * nmod * 64, 256, 256 * sizeof(float4), stream>>>(f, nmod, B, H, W, C, pos_emb, vel_w, vel_b,
                                                                           velocity, tokens, drop_p, seed);
   return mmfn_launch_status("tokens_fwd");
 }
