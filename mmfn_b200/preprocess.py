@@ -1,0 +1,106 @@
+"""Host-side frame preprocessing of the training data path: what
+CARLA_Data.__getitem__ (team_code/mmfn_utils/datasets/dataloader.py:183-268) does to one raw frame before it is
+pickled by phase1_preprocess_data.py and later read back by PRE_Data.
+
+  transform_points_2d     dataloader.py:311-334 -- ego-frame change of an (N, 3) point set, float64
+  radar_to_size           dataloader.py:336-346 -- pad / prune the radar returns to (81, 5)
+  crop_image_chw          dataloader.py:296-308 -- centre crop to channels-first (scale = 1 path)
+  local_waypoints         dataloader.py:241-248 -- future ego positions in the current ego frame
+  local_command_point     dataloader.py:250-261 -- navigation target in the current ego frame
+  frame_to_sample         dataloader.py:201-268 -- the sample dict; the LiDAR histogram comes from a caller-supplied
+                          builder: `mmfn_b200.ops.bev_scatter` on the GPU (bit-exact with the reference function for
+                          identical points) or the CPU oracle in tests
+
+The rigid transform is evaluated in closed form (one rotation by r1 - r2 and one translation) instead of the
+reference's two 3x3 matrix products and a matrix inverse: mathematically identical, numerically equal to ~1e-13
+relative (tests/test_preprocess_cpu.py pins it against outputs of the reference function).  No torch autograd,
+no GPU work here: it is loader-side code.
+"""
+import numpy as np
+import torch
+
+
+def transform_points_2d(xyz, r1, t1_x, t1_y, r2, t2_x, t2_y):
+    """Points given in frame 1 (pose: heading r1, offset (t1_x, t1_y)) expressed in frame 2; z is carried over.
+
+    The reference maps p -> M1 p to the world frame, with M1 = [[c1, s1, t1_x], [-s1, c1, t1_y], [0, 0, 1]], and then
+    applies inverse(M2).  With R(a) = [[cos a, sin a], [-sin a, cos a]] this is
+        out_xy = R(r2)^T (R(r1) p_xy + t1 - t2).
+    """
+    xyz = np.asarray(xyz, dtype=np.float64)
+    c1, s1 = np.cos(r1), np.sin(r1)
+    c2, s2 = np.cos(r2), np.sin(r2)
+    wx = c1 * xyz[:, 0] + s1 * xyz[:, 1] + (t1_x - t2_x)
+    wy = -s1 * xyz[:, 0] + c1 * xyz[:, 1] + (t1_y - t2_y)
+    out = np.empty_like(xyz)
+    out[:, 0] = c2 * wx - s2 * wy
+    out[:, 1] = s2 * wx + c2 * wy
+    out[:, 2] = xyz[:, 2]
+    return out
+
+
+def radar_to_size(data, target_size=(81, 5)):
+    """Fewer returns than rows: zero padding at the end.  More: drop the returns with the LARGEST |depth / velocity|
+    (time to collision; NaN / inf from zero velocity sort last under argsort of the negated value, exactly as in the
+    reference) until `target_size[0]` remain, keeping the original order of the survivors."""
+    data = np.asarray(data)
+    rows = target_size[0]
+    if data.shape[0] >= rows:
+        n = data.shape[0] - rows
+        with np.errstate(divide="ignore", invalid="ignore"):
+            drop = (-np.abs(data[:, 0] / data[:, 3])).argsort()[:n]
+        return np.delete(data, drop, 0)
+    out = np.zeros(target_size)
+    out[: data.shape[0], :] = data
+    return out
+
+
+def crop_image_chw(image_hwc, crop=256):
+    """Centre crop of an (H, W, 3) uint8 frame, channels first (scale_and_crop_image with scale = 1)."""
+    image_hwc = np.asarray(image_hwc)
+    h, w = image_hwc.shape[:2]
+    y0, x0 = h // 2 - crop // 2, w // 2 - crop // 2
+    return np.ascontiguousarray(np.transpose(image_hwc[y0:y0 + crop, x0:x0 + crop], (2, 0, 1)))
+
+
+def local_waypoints(xs, ys, thetas, ego_index):
+    """Ego positions of the frames in `xs, ys, thetas` (world) expressed in the frame of `ego_index`: the reference
+    transforms the ORIGIN of every frame i into the ego frame (dataloader.py:241-247)."""
+    ex, ey, et = xs[ego_index], ys[ego_index], thetas[ego_index]
+    wps = []
+    for x, y, th in zip(xs, ys, thetas):
+        p = transform_points_2d(np.zeros((1, 3)), np.pi / 2 - th, -x, -y, np.pi / 2 - et, -ex, -ey)
+        wps.append((p[0, 0], p[0, 1]))
+    return wps
+
+
+def local_command_point(x_command, y_command, ego_x, ego_y, ego_theta):
+    """Navigation target in the ego frame: R(pi/2 + theta)^T (target - ego) (dataloader.py:250-261)."""
+    a = np.pi / 2 + ego_theta
+    c, s = np.cos(a), np.sin(a)
+    dx, dy = x_command - ego_x, y_command - ego_y
+    return (c * dx + s * dy, -s * dx + c * dy)
+
+
+def frame_to_sample(rgb_hwc, points_xyzi, lanes, radar_raw, map_hwc, xs, ys, thetas, x_command, y_command,
+                    bev_fn, seq_len=1, steer=0.0, throttle=0.0, brake=False, command=4, velocity=0.0, crop=256):
+    """One training sample in the layout the phase-1 pickles hold (seq_len = 1, the MMFN configuration).
+    xs / ys / thetas: ego poses of the current frame followed by the `pred_len` future frames.
+    bev_fn(points (N, 3) float32) -> (2, 256, 256) float32 histogram."""
+    assert seq_len == 1, "MMFN is trained with seq_len = 1 (config.py:6)"
+    thetas = [0.0 if np.isnan(t) else float(t) for t in thetas]              # dataloader.py:222-224
+    i = seq_len - 1
+    pts = np.array(np.asarray(points_xyzi)[..., :3], dtype=np.float64)
+    pts[:, 1] *= -1                                                          # dataloader.py:232
+    pts = transform_points_2d(pts, np.pi / 2 - thetas[i], -xs[i], -ys[i], np.pi / 2 - thetas[i], -xs[i], -ys[i])
+    lidar = np.asarray(bev_fn(pts.astype(np.float32)), dtype=np.float32)
+    return {
+        "fronts": [torch.from_numpy(crop_image_chw(rgb_hwc, crop))],
+        "lidars": [lidar],
+        "vectormaps": [torch.from_numpy(np.asarray(lanes))],
+        "radar": [radar_to_size(radar_raw, (81, 5))],
+        "maps": [torch.from_numpy(np.ascontiguousarray(np.transpose(np.asarray(map_hwc), (2, 0, 1))))],
+        "waypoints": local_waypoints(xs, ys, thetas, i),
+        "target_point": local_command_point(x_command, y_command, xs[i], ys[i], thetas[i]),
+        "steer": steer, "throttle": throttle, "brake": brake, "command": command, "velocity": velocity,
+    }
