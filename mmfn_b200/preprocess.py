@@ -104,3 +104,56 @@ def frame_to_sample(rgb_hwc, points_xyzi, lanes, radar_raw, map_hwc, xs, ys, the
         "target_point": local_command_point(x_command, y_command, xs[i], ys[i], thetas[i]),
         "steer": steer, "throttle": throttle, "brake": brake, "command": command, "velocity": velocity,
     }
+
+
+# --------------------------------------------------------------------------- recorded route -> pickles (phase 1)
+def route_sequences(route_dir, seq_len=1, pred_len=4):
+    """Frame numbers of the usable samples of one recorded route, as CARLA_Data.__init__ enumerates them
+    (dataloader.py:69-80): the first frame and the last pred_len + 1 frames are not used as `current` frames."""
+    import os
+    n = len(os.listdir(os.path.join(route_dir, "rgb_front")))
+    num_seq = (n - pred_len - 2) // seq_len
+    return [seq * seq_len + 1 for seq in range(num_seq)]
+
+
+def load_route_sample(route_dir, frame, bev_fn, pred_len=4, crop=256):
+    """Read one recorded frame (+ the poses of its pred_len successors) from the CARLA recording layout
+    rgb_front/ maps/ vectormap/ lidar/ radar/ measurements/ (dataloader.py:83-118) and preprocess it."""
+    import json
+    import os
+    from PIL import Image
+
+    def name(f, ext):
+        return f"{str(f).zfill(4)}.{ext}"
+
+    meas = []
+    for f in range(frame, frame + 1 + pred_len):
+        with open(os.path.join(route_dir, "measurements", name(f, "json"))) as fd:
+            meas.append(json.load(fd))
+    cur = meas[0]
+    vm = os.path.join(route_dir, "vectormap", name(frame, "npy"))
+    if not os.path.exists(vm):
+        raise FileNotFoundError(f"{vm}: the reference falls back to a neighbouring sample's lanes here "
+                                "(dataloader.py:206-214); this loader reports the missing file instead")
+    return frame_to_sample(
+        np.asarray(Image.open(os.path.join(route_dir, "rgb_front", name(frame, "png")))),
+        np.load(os.path.join(route_dir, "lidar", name(frame, "npy"))),
+        np.load(vm),
+        np.load(os.path.join(route_dir, "radar", name(frame, "npy"))),
+        np.asarray(Image.open(os.path.join(route_dir, "maps", name(frame, "png")))),
+        [m["x"] for m in meas], [m["y"] for m in meas], [m["theta"] for m in meas],
+        cur["x_command"], cur["y_command"], bev_fn,
+        steer=cur["steer"], throttle=cur["throttle"], brake=cur["brake"], command=cur["command"],
+        velocity=cur["speed"], crop=crop)
+
+
+def write_pickles(samples, out_dir):
+    """phase1_preprocess_data.py:41-43: one `<index>.pkl` per sample, the files PRE_Data (data.py) reads back."""
+    import os
+    import pickle
+    os.makedirs(out_dir, exist_ok=True)
+    n = 0
+    for n, s in enumerate(samples, start=1):
+        with open(os.path.join(out_dir, f"{n - 1}.pkl"), "wb") as fd:
+            pickle.dump(s, fd)
+    return n

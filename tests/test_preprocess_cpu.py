@@ -63,3 +63,43 @@ def test_radar_to_size_matches_reference_function(gold):
         assert out.shape == (81, 5)
         assert np.array_equal(out, gold[f"radar_out_{name}"])
     assert np.array_equal(pp.radar_to_size(np.zeros((0, 5)), (81, 5)), np.zeros((81, 5)))
+
+
+def test_recorded_route_to_pickles_to_engine_batch(gold, tmp_path):
+    """raw recording on disk -> preprocess -> <i>.pkl -> PRE_Data -> collate -> engine batch: the whole loader side."""
+    import json
+    import torch
+    from PIL import Image
+    from mmfn_b200 import data as mdata
+    from mmfn_b200.config import GlobalConfig
+    route = tmp_path / "town" / "route_00"
+    for sub in ("rgb_front", "maps", "vectormap", "lidar", "radar", "measurements"):
+        (route / sub).mkdir(parents=True)
+    for f in range(1, fx.N_FRAMES + 1):
+        fr = fx.raw_frame(f)
+        name = str(f).zfill(4)
+        Image.fromarray(fr["rgb"]).save(route / "rgb_front" / (name + ".png"))
+        Image.fromarray(fr["map"]).save(route / "maps" / (name + ".png"))
+        np.save(route / "vectormap" / (name + ".npy"), fr["lanes"])
+        np.save(route / "lidar" / (name + ".npy"), fr["points"])
+        np.save(route / "radar" / (name + ".npy"), fr["radar"])
+        json.dump(fr["meas"], open(route / "measurements" / (name + ".json"), "w"))
+    frames = pp.route_sequences(str(route))
+    assert frames == [1, 2]
+    out = tmp_path / "pro_train"
+    n = pp.write_pickles((pp.load_route_sample(str(route), f, bev_oracle.lidar_to_histogram_features) for f in frames), str(out))
+    assert n == 2 and sorted(p.name for p in out.iterdir()) == ["0.pkl", "1.pkl"]
+    ds = mdata.PRE_Data(str(out), GlobalConfig())
+    assert len(ds) == 2
+    samples = sorted((ds[i] for i in range(2)), key=lambda s: s["steer"])
+    for i, s in enumerate(samples):
+        assert np.array_equal(np.round(np.asarray(s["lidars"][0]) * 5).astype(np.uint8), gold[f"s{i}_lidar_x5"])
+        assert np.array_equal(s["radar"][0], gold[f"s{i}_radar"])
+        assert s["radar_adj"].shape == (81, 81)
+        assert np.allclose(np.asarray(s["waypoints"]), gold[f"s{i}_waypoints"], atol=1e-9)
+    batch = mdata.collate_single_cpu(samples)
+    lanes, lane_num, lmax = batch["vectormaps"][0]
+    assert lanes.shape[0] == 2 and lanes.shape[1] == int(lane_num.max()) == lmax
+    eb = mdata.to_engine_batch(batch)
+    assert eb["rgb_u8"].shape == (2, 3, 256, 256) and eb["rgb_u8"].dtype == torch.uint8
+    assert eb["gt_waypoints"].shape == (2, 4, 2) and eb["radar"].shape == (2, 81, 5)
