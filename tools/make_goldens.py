@@ -194,7 +194,23 @@ def transfuser(B=2):
     print("transfuser loss", loss.item())
 
 
+def control():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from control_fixture import control_inputs
+    # MMFN.control_pid (model_rad.py:697-739) driven over a sequence: the two PID controllers carry state.
+    net = model_rad.MMFN(GlobalConfig(), "cpu")
+    rows = []
+    for wp, v in control_inputs():
+        steer, throttle, brake, meta = net.control_pid(torch.from_numpy(wp.copy()), torch.from_numpy(v.copy()))
+        rows.append([float(steer), float(throttle), float(brake), meta["desired_speed"], meta["angle"], meta["delta"],
+                     meta["aim"][0], meta["aim"][1], meta["speed"]])
+    np.savez_compressed(os.path.join(GOLD, "control_pid_golden.npz"), rows=np.asarray(rows, dtype=np.float64))
+
+
 if __name__ == "__main__":
+    if "--control-only" in sys.argv:
+        control()
+        sys.exit(0)
     if "--transfuser-only" in sys.argv:
         transfuser(2)
         sys.exit(0)
@@ -206,3 +222,4 @@ if __name__ == "__main__":
     model(2)
     transfuser(2)
     variants(2)
+    control()
