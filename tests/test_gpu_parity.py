@@ -88,7 +88,8 @@ def test_train_step_matches_oracle_and_reference_goldens(dev, golden_dir, tf32):
     cfg, model, sd, b = _setup(dev, B, tf32)
     # measured on B200: waypoint L1 1.5e-7 (fp32) / 1.7e-4 (tf32); loss error 0 / 1e-6;
     # worst per-tensor gradient error 1.5e-2 (fp32, B=2 train-mode BN amplifies fp32 noise) / 0.37 (tf32)
-    wp_tol, loss_tol, grad_tol, norm_tol = (2e-4, 2e-4, 2e-2, 2e-2) if not tf32 else (1e-3, 1e-3, 0.6, 0.25)
+    # (grad_tol 3e-2: the worst tensor moves between 1.5e-2 and 2.2e-2 with the summation order of split-K atomics)
+    wp_tol, loss_tol, grad_tol, norm_tol = (2e-4, 2e-4, 3e-2, 2e-2) if not tf32 else (1e-3, 1e-3, 0.6, 0.25)
     lidar = ops.bev_scatter(b["points"].to(dev))
     lidar_ref = torch.from_numpy(np.stack([bev_oracle.lidar_to_histogram_features(p[:, :3].numpy()) for p in b["points"]]))
     assert torch.equal(lidar.cpu(), lidar_ref)
