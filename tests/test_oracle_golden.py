@@ -150,3 +150,17 @@ def test_vec_and_img_variant_oracles_match_reference_goldens(golden_dir):
             ref, got = gold["grad/" + k], probe(g, 6)
             worst = max(worst, np.abs(np.delete(got - ref, 1)).max() / max(abs(ref[0]), 1e-6))
         assert worst < 5e-3, (variant, worst)
+
+
+def test_model_oracle_inference_path_matches_reference_golden(golden_dir):
+    """eval() mode (BatchNorm running statistics, dropout inactive whatever the config says): the path the e2e agents
+    run (e2e_agent/mmfn_radar.py:296-306).  The golden running statistics are deliberately far from the batch
+    statistics, so the outputs are O(1e3): compared relative to their magnitude."""
+    gold = np.load(os.path.join(golden_dir, "mmfn_eval_golden_b1.npz"))["pred_wp"]
+    sd, _, batch = _oracle_step(1)
+    cfg = GlobalConfig()                                     # reference default: dropout 0.1 -- must be a no-op in eval
+    with torch.no_grad():
+        pred = mmfn_oracle.forward(sd, cfg, *batch["inputs"], train=False)
+    assert pred.shape == gold.shape == (1, 4, 2)
+    rel = np.abs(pred.numpy() - gold).mean() / np.abs(gold).mean()
+    assert rel < 1e-5, rel

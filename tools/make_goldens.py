@@ -194,6 +194,23 @@ def transfuser(B=2):
     print("transfuser loss", loss.item())
 
 
+def eval_mode(B=1):
+    """Inference path of the reference (what the e2e agents run, e2e_agent/mmfn_radar.py:296-306): eval() mode --
+    BatchNorm running statistics, dropout off -- with the reference DEFAULT dropout config."""
+    torch.manual_seed(0)
+    cfg = GlobalConfig()
+    net = model_rad.MMFN(cfg, "cpu")
+    net.load_state_dict(synthetic.fill_golden_weights(net.state_dict(), 42))
+    net.eval()
+    b = synthetic.synth_batch(B)
+    lidar = torch.from_numpy(np.stack([lidar_to_histogram_features(p[:, :3].numpy()) for p in b["points"]]))
+    vectormaps = [[b["lane"]], [b["lane_num"].float()], b["lane"].shape[1]]
+    with torch.no_grad():
+        pred = net([b["rgb_u8"].float()], [lidar], None, vectormaps, [b["radar"]], [b["radar_adj"]], b["target_point"], b["velocity"])
+    np.savez_compressed(os.path.join(GOLD, f"mmfn_eval_golden_b{B}.npz"), pred_wp=pred.numpy())
+    print("eval pred", pred.abs().mean().item())
+
+
 def control():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from control_fixture import control_inputs
@@ -211,6 +228,9 @@ if __name__ == "__main__":
     if "--control-only" in sys.argv:
         control()
         sys.exit(0)
+    if "--eval-only" in sys.argv:
+        eval_mode(1)
+        sys.exit(0)
     if "--transfuser-only" in sys.argv:
         transfuser(2)
         sys.exit(0)
@@ -223,3 +243,4 @@ if __name__ == "__main__":
     transfuser(2)
     variants(2)
     control()
+    eval_mode(1)
