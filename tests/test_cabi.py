@@ -36,6 +36,23 @@ def test_argument_validation_without_gpu():
         lib().bev_scatter(16, 1, 10, 2, 16, 0, None)
     with pytest.raises(MmfnError, match="null"):
         lib().gemm_f32(0, 1, 1, 0, 0, 0, 1, 1, 0, 0, 0, 1, 0, 0, 4, 4, 4, 1, 1, 0, 0, 0, 1.0, 0, 0, 0.0, 0, 1, None)
+    # entry points added for the tensor-core data gradients, the stems, the fused attention backward and the bucketed
+    # optimizer: shape / alignment violations are reported before any launch (fake 16-byte aligned pointers)
+    P = 4096
+    with pytest.raises(MmfnError, match="stride must be 1 or 2"):
+        lib().conv2d_dgrad_tf32(P, P, P, 0, 2, 32, 32, 64, 64, 3, 3, 3, 1, 11, 11, None)
+    with pytest.raises(MmfnError, match="H, W must be even"):
+        lib().conv2d_dgrad_tf32(P, P, P, 0, 2, 31, 31, 64, 64, 3, 3, 2, 1, 16, 16, None)
+    with pytest.raises(MmfnError, match="Kp must be a multiple of 4"):
+        lib().im2col_nhwc(P, P, 1, 8, 8, 3, 7, 7, 2, 3, 4, 4, 150, None)
+    with pytest.raises(MmfnError, match="multiple of 32, <= 256"):
+        lib().attention_bwd_dq_tf32(P, P, P, P, P, P, 1, 100, 64, 4, 0.0, 0, None)
+    with pytest.raises(MmfnError, match="head size"):
+        lib().attention_bwd_dq_tf32(P, P, P, P, P, P, 1, 192, 96, 4, 0.0, 0, None)
+    with pytest.raises(MmfnError, match="multiple of 4"):
+        lib().adamw_apply(P, P, P, P, 10, 1e-4, 0.9, 0.999, 1e-8, 0.01, P, 1.0, None)
+    with pytest.raises(MmfnError, match="bad args"):
+        lib().copy2d_f32(P, 4, P, 8, 2, 6, 0, None)
 
 
 def test_product_never_imports_oracle():
