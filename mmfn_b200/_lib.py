@@ -54,6 +54,23 @@ class _Lib:
                 setattr(self, name[len("mmfn_"):], self._wrap(name, fn))
         self.version = self._dll.mmfn_version()
 
+    # ---- process-wide dropout offset -------------------------------------------------------------
+    # mmfn_rng_bind stores a DEVICE ADDRESS in constant memory: it must outlive every engine and must not be rebound
+    # by a second engine, so the library owns ONE int64 cell per device that is never freed.
+    _rng = {}
+
+    def rng_tensor(self, device, rank=0):
+        import torch
+        device = torch.device(device)
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        t = self._rng.get(key)
+        if t is None:
+            # ranks start from different offsets: data-parallel replicas must not draw identical masks
+            t = self._rng[key] = torch.full((1,), int(rank) * 7919 * 1000003, device=device, dtype=torch.int64)
+            with torch.cuda.device(device):
+                self.rng_bind(t.data_ptr())
+        return t
+
     def last_error(self):
         buf = ctypes.create_string_buffer(512)
         self._dll.mmfn_last_error(buf, 512)
@@ -89,14 +106,30 @@ class _Lib:
     profile = None        # list of (fn, (flops, bytes) | None, start_event, end_event) while enabled
     next_work = None      # set by ops wrappers right before a call: algorithmic (flops, bytes)
 
+    @staticmethod
+    def kernel_class(fn, work):
+        """conv | linear | attention (tensor-pipe bound) | hbm (everything else: normalisation, pooling, scatter,
+        optimizer ...).  Batched GEMMs are the attention products (QK^T, PV and their gradients)."""
+        if fn.startswith("conv2d_"):
+            return "conv"
+        if fn.startswith("attention_"):
+            return "attention"
+        if fn.startswith("gemm_"):
+            return "attention" if (work and len(work) >= 6 and work[5] > 1) else "linear"
+        return "hbm"
+
     def start_profile(self):
         self.profile = []
 
     def stop_profile(self):
         """-> {fn: dict(calls, ms, flops, bytes)}; caller must have synchronised the device."""
-        out, shapes = {}, {}
+        out, shapes, classes = {}, {}, {}
         for fn, work, e0, e1 in self.profile or []:
             ms = e0.elapsed_time(e1)
+            c = classes.setdefault(self.kernel_class(fn, work), dict(calls=0, ms=0.0, flops=0.0))
+            c["calls"] += 1
+            c["ms"] += ms
+            c["flops"] += work[0] if work else 0.0
             d = out.setdefault(fn, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
             d["calls"] += 1
             d["ms"] += ms
@@ -107,6 +140,7 @@ class _Lib:
                 s[0] += 1
                 s[1] += ms
         self.profile = None
+        self.last_classes = classes
         self.last_shapes = sorted(([k, v[0], v[1], v[2]] for k, v in shapes.items()), key=lambda r: -r[2])
         return out
 

@@ -26,6 +26,32 @@ MMFN_API int mmfn_last_error(char* buf, int64_t len) {
 
 using namespace mmfn;
 
+// Scratch / saved-tensor sizes a caller must allocate (the library owns no device memory).  `op` is one of the
+// MMFN_WS_* codes of the header, `dtype` one of MMFN_F32 / MMFN_TF32 / MMFN_BF16 (element size of the tensors the op
+// stores: 4 / 4 / 2 bytes); a, b, c, d are the op's sizes:
+//   MMFN_WS_BN            a = channels C                     fp64 partial-sum slots + ticket + published coefficients of
+//                                                            mmfn_bn_train_fwd / _bwd (zero once; every call leaves it zero)
+//   MMFN_WS_STEM_IM2COL   a = N, b = Ho*Wo, c = R*S*C        column matrix (N*Ho*Wo, Kp) of the 7x7/2 stems, Kp = c rounded
+//                                                            up to the k-block (32 elements fp32/tf32, 64 bf16)
+//   MMFN_WS_STEM_FILTER   a = Co, c = R*S*C                  zero-padded (Co, Kp) filter matrix of the same GEMM
+//   MMFN_WS_ATTN_PROB     a = B, b = heads, c = T, d = 1|2   saved attention probabilities (B, heads, T, T); d = 2 with
+//                                                            dropout (P and P after dropout)
+//   MMFN_WS_GRU_SAVED     a = B, b = steps                   gate activations kept by mmfn_gru_head_fwd for BPTT
+// Replaces nothing in the reference (PyTorch's caching allocator does this implicitly); SURVEY.md section 8(b).
+MMFN_API int mmfn_workspace_bytes(int op, int dtype, int64_t a, int64_t b, int64_t c, int64_t d, int64_t* bytes) {
+  MMFN_CHECK_ARG(bytes, "workspace_bytes: null output");
+  MMFN_CHECK_ARG(dtype >= 0 && dtype <= 2, "workspace_bytes: unknown dtype %d", dtype);
+  const int64_t es = dtype == 2 ? 2 : 4, kblock = dtype == 2 ? 64 : 32;
+  switch (op) {
+    case 0: MMFN_CHECK_ARG(a > 0, "workspace_bytes: C"); *bytes = (34 * a + 8) * 8; return 0;
+    case 1: MMFN_CHECK_ARG(a > 0 && b > 0 && c > 0, "workspace_bytes: sizes"); *bytes = a * b * ((c + kblock - 1) / kblock * kblock) * es; return 0;
+    case 2: MMFN_CHECK_ARG(a > 0 && c > 0, "workspace_bytes: sizes"); *bytes = a * ((c + kblock - 1) / kblock * kblock) * es; return 0;
+    case 3: MMFN_CHECK_ARG(a > 0 && b > 0 && c > 0 && (d == 1 || d == 2), "workspace_bytes: sizes"); *bytes = a * b * c * c * es * d; return 0;
+    case 4: MMFN_CHECK_ARG(a > 0 && b > 0, "workspace_bytes: sizes"); *bytes = a * b * 5 * 64 * 4; return 0;
+    default: mmfn_set_error("workspace_bytes: unknown op %d", op); return MMFN_BAD_ARG;
+  }
+}
+
 // C[b0,b1](M,N) (+)= alpha * A(M,K) * B(N,K)^T with fused epilogue; all operands strided.
 MMFN_API int mmfn_gemm_f32(const float* A, int64_t a_sr, int64_t a_sk, int64_t a_sb0, int64_t a_sb1,
                            const float* B, int64_t b_sr, int64_t b_sk, int64_t b_sb0, int64_t b_sb1,
@@ -110,6 +136,7 @@ int mmfn_bind_rng_conv_tc(const unsigned long long*);
 int mmfn_bind_rng_misc(const unsigned long long*);
 int mmfn_bind_rng_pool(const unsigned long long*);
 int mmfn_bind_rng_attn_tc(const unsigned long long*);
+int mmfn_bind_rng_norm(const unsigned long long*);
 
 // Bind (or with null: unbind) a device-resident 64-bit offset that every dropout site adds to its
 // seed at run time.  The training engine bumps it on the device once per step, so the dropout masks
@@ -122,6 +149,7 @@ MMFN_API int mmfn_rng_bind(const unsigned long long* dev_offset) {
   if (!rc) rc = mmfn_bind_rng_misc(dev_offset);
   if (!rc) rc = mmfn_bind_rng_pool(dev_offset);
   if (!rc) rc = mmfn_bind_rng_attn_tc(dev_offset);
+  if (!rc) rc = mmfn_bind_rng_norm(dev_offset);     // LayerNorm backward regenerates the residual-branch masks
   if (rc) mmfn_set_error("rng_bind: cudaMemcpyToSymbol failed (%d)", rc);
   return rc;
 }

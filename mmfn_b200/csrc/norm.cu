@@ -587,3 +587,5 @@ MMFN_API int mmfn_layernorm_bwd(const float* dy, const float* x, const float* ga
   }
   return mmfn_launch_status("layernorm_bwd");
 }
+
+MMFN_DEFINE_RNG_BINDER(norm)

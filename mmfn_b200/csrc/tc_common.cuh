@@ -2,6 +2,7 @@
 // tcgen05 (alloc / mma / commit / ld) and UMMA descriptor construction.  Inline PTX only.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace tc {
@@ -105,6 +106,13 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// D[tmem] (+)= A[smem] * B[smem], BF16 inputs (kind::f16), FP32 accumulate; issued by ONE thread.  K = 16 per instruction.
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // mbarrier arrives once all MMAs issued so far by this thread have completed.
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -145,6 +153,16 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t saddr) { return smem_desc(saddr, 16, 1024, 2); }
 // MN-major tile built from TMA boxes of [k rows][32 fp32]: 4-row atoms 512 B apart along K, boxes `box_bytes` apart along MN.
 __device__ __forceinline__ uint64_t smem_desc_mnmajor(uint32_t saddr, uint32_t box_bytes) { return smem_desc(saddr, box_bytes, 512, 1); }
+// MN-major 16-bit tile built from TMA boxes of [64 k rows][64 bf16] (SWIZZLE_128B on both sides): canonical layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units (cute mma_traits_sm100.hpp) -- 8-row atoms 1024 B apart along K,
+// 64-element blocks `box_bytes` apart along MN.  One kind::f16 MMA (K = 16) spans two atoms.
+__device__ __forceinline__ uint64_t smem_desc_mnmajor16(uint32_t saddr, uint32_t box_bytes) { return smem_desc(saddr, box_bytes, 1024, 2); }
+// Instruction descriptor for kind::f16 with BF16 operands, fp32 accumulate (a_format = b_format = 1).
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10)
+         | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16)
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // Instruction descriptor for kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor bit layout).
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn_major, bool b_mn_major) {
   return (1u << 4)            // c_format  = F32
@@ -169,3 +187,23 @@ unsigned long long* mmfn_tc_trace_ptr();
 int mmfn_make_tmap_f32(CUtensorMap* out, const float* base, int rank, const uint64_t* dims,
                        const uint64_t* strides_elems, const uint32_t* box, const uint32_t* elem_strides,
                        bool swizzle32, bool as_tf32 = true);   // as_tf32 = false: plain FLOAT32 map (TMA stores)
+// bf16 tensor (rank <= 4), SWIZZLE_128B (K-major and MN-major 16-bit tiles use the same TMA pattern), OOB -> 0.
+// strides in ELEMENTS (multiples of 8 = 16 bytes).
+int mmfn_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_elems, const uint32_t* box, const uint32_t* elem_strides);
+
+// ---------------------------------------------------------------- element traits of a tensor-core pipeline
+// EB = elements per 128-byte k-block row: 32 (fp32 storage read as TF32) or 64 (bf16).  A k-block is always four MMAs.
+template <int EB_> struct ElemTraits;
+template <> struct ElemTraits<32> {
+  static constexpr int EB = 32, BOX_BYTES = 32 * 128, MN_STEP = 1024;   // MN-major: [32 k][32 fp32] boxes, 8 k rows per MMA
+  __device__ static __forceinline__ uint64_t mn_desc(uint32_t saddr) { return tc::smem_desc_mnmajor(saddr, BOX_BYTES); }
+  __host__ __device__ static constexpr uint32_t idesc(int M, int N, bool amn, bool bmn) { return tc::idesc_tf32(M, N, amn, bmn); }
+  __device__ static __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t i, uint32_t acc) { tc::mma_tf32(d, a, b, i, acc); }
+};
+template <> struct ElemTraits<64> {
+  static constexpr int EB = 64, BOX_BYTES = 64 * 128, MN_STEP = 2048;   // MN-major: [64 k][64 bf16] boxes, 16 k rows per MMA
+  __device__ static __forceinline__ uint64_t mn_desc(uint32_t saddr) { return tc::smem_desc_mnmajor16(saddr, BOX_BYTES); }
+  __host__ __device__ static constexpr uint32_t idesc(int M, int N, bool amn, bool bmn) { return tc::idesc_bf16(M, N, amn, bmn); }
+  __device__ static __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t i, uint32_t acc) { tc::mma_bf16(d, a, b, i, acc); }
+};

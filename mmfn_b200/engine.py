@@ -99,9 +99,11 @@ class TrainEngine:
         self.p_active = self.st.flat[:n]
         self.g_active = self.st.flat_grad[:n]
         self.last_pred = None
-        # device-resident dropout offset, bumped once per step inside the (captured) schedule
-        self.rng = torch.zeros(1, device=dev, dtype=torch.int64)
-        lib().rng_bind(self.rng.data_ptr())
+        # device-resident dropout offset, bumped once per step inside the (captured) schedule.  ONE cell per
+        # device, owned by the library binding (never freed, never rebound by a second engine); the data-parallel
+        # rank is folded into its initial value so replicas draw different masks.
+        rank = dist.get_rank(process_group) if self.world > 1 else 0
+        self.rng = lib().rng_tensor(dev, rank)
         self._graph = None
 
     def broadcast_parameters(self, src=0):
@@ -147,8 +149,14 @@ class TrainEngine:
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            for _ in range(warmup):                      # sets kernel attributes, warms the allocator
-                self.step(static_batch)
+            # sets kernel attributes, warms the allocator.  forward+backward only: the optimizer kernels are not part
+            # of the captured graphs, and a warm-up must not move weights, m / v or the step count.  BatchNorm running
+            # statistics / num_batches_tracked are training state too: restored after the warm-up.
+            buf0, nbt0 = self.st.flat_buf.clone(), self.st.flat_nbt.clone()
+            for _ in range(warmup):
+                self.forward_backward(static_batch)
+            self.st.flat_buf.copy_(buf0)
+            self.st.flat_nbt.copy_(nbt0)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()

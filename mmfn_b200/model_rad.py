@@ -720,6 +720,7 @@ class MMFN(nn.Module):
         self.net = self.NET(self.store, config)
         self.seed = 0
         self.reset_parameters()
+        self._maybe_load_pretrained()
 
     # ---- initialisation following the reference constructors ---------------------------------
     @torch.no_grad()
@@ -756,6 +757,47 @@ class MMFN(nn.Module):
                 b.fill_(1.0)
             else:
                 b.zero_()
+
+    # ---- ImageNet initialisation of the two ResNet-34 trunks --------------------------------
+    PRETRAINED_FILE = "resnet34-b627a593.pth"           # what models.resnet34(pretrained=True) downloads
+
+    @torch.no_grad()
+    def load_torchvision_resnet34(self, weights, trunks=("image_encoder", "img_map_encoder")):
+        """The reference builds both ResNet-34 trunks as `models.resnet34(pretrained=True)` with `fc` removed
+        (ImageCNN, model_rad.py:22-23; image_encoder / img_map_encoder :427-428).  `weights`: a torchvision resnet34
+        state_dict or the path of its checkpoint file.  Copies every tensor but `fc.*` into
+        encoder.{image_encoder,img_map_encoder}.features.* (the RGB+LiDAR variant has only image_encoder)."""
+        if isinstance(weights, (str, bytes)) or hasattr(weights, "__fspath__"):
+            weights = torch.load(weights, map_location="cpu")
+        own = self.state_dict()
+        part = {}
+        for trunk in trunks:
+            prefix = f"encoder.{trunk}.features."
+            if not any(k.startswith(prefix) for k in own):
+                continue
+            for k, v in weights.items():
+                if k.startswith("fc."):
+                    continue
+                if prefix + k not in own or tuple(own[prefix + k].shape) != tuple(v.shape):
+                    raise ops.MmfnError(f"load_torchvision_resnet34: {k} does not fit {prefix}{k}")
+                part[prefix + k] = v
+        if not part:
+            raise ops.MmfnError("load_torchvision_resnet34: no ResNet-34 trunk in this model")
+        self.load_state_dict(part, strict=False)
+        return sorted(part)
+
+    def _maybe_load_pretrained(self):
+        """Reference behaviour when the ImageNet checkpoint is available locally (torch hub cache or
+        $MMFN_RESNET34_WEIGHTS); otherwise the trunks keep the seeded kaiming init -- there is no network here."""
+        import os
+        cands = [os.environ.get("MMFN_RESNET34_WEIGHTS"),
+                 os.path.join(torch.hub.get_dir(), "checkpoints", self.PRETRAINED_FILE)]
+        for c in cands:
+            if c and os.path.isfile(c):
+                self.load_torchvision_resnet34(c)
+                self.pretrained_from = c
+                return
+        self.pretrained_from = None
 
     def _fan_in_of_bias(self, k):
         w = k[: -len("bias")] + "weight"

@@ -29,6 +29,19 @@ TF32 = True   # large aligned GEMMs/convs run on the tcgen05 TF32 path; False = 
 # ~1e-3 relative -- enough to dominate the (second-order small) query/key gradients of a freshly initialised model and
 # to fail the per-tensor gradient-norm check of tests/test_gpu_parity.py.  The kernel itself is covered op-level.
 FUSED_ATTN_BWD = False
+# bf16 tensor-core operands (BASELINE configs[2]): activations that feed MMAs and a bf16 shadow of the weights are
+# stored in bf16 (tcgen05 kind::f16, fp32 accumulate); residual stream, statistics, gradients of parameters, master
+# weights and optimizer stay fp32.  Implies TF32 for everything the bf16 kernels do not cover (stems, VectorNet, GAT, head).
+BF16 = False
+
+
+def set_precision(mode):
+    """"fp32": exact-fp32 SIMT kernels everywhere (tests);  "tf32": production configs[1];  "bf16": configs[2]."""
+    global TF32, BF16
+    if mode not in ("fp32", "tf32", "bf16"):
+        raise MmfnError(f"unknown precision {mode!r}")
+    TF32 = mode != "fp32"
+    BF16 = mode == "bf16"
 
 
 def _major(t):
@@ -231,12 +244,24 @@ BN_WS_MAX_C = 2048
 BN_SMALL_ROWS = 2048     # norm.cu: feature maps with at most this many rows take the single-launch kernel
 
 
+F32, TF32_T, BF16_T = 0, 1, 2                     # MMFN_F32 / MMFN_TF32 / MMFN_BF16 of the header
+WS_BN, WS_STEM_IM2COL, WS_STEM_FILTER, WS_ATTN_PROB, WS_GRU_SAVED = range(5)
+
+
+def workspace_bytes(op, dtype=F32, a=0, b=0, c=0, d=0):
+    """mmfn_workspace_bytes: the library states the scratch size, the caller (torch) allocates it."""
+    out = torch.zeros(1, dtype=torch.int64)
+    lib().workspace_bytes(op, dtype, a, b, c, d, out.data_ptr())
+    lib().launches -= 1                           # host-only query, not a kernel
+    return int(out.item())
+
+
 def _bn_ws(dev):
     """fp64 scratch for the BatchNorm partial sums: one per stream, since trunks run concurrently.  Zeroed ONCE here;
-    the reduction kernel's last CTA leaves it zero again (34*C + 8 doubles, C <= BN_WS_MAX_C)."""
+    the reduction kernel's last CTA leaves it zero again (size from mmfn_workspace_bytes, C <= BN_WS_MAX_C)."""
     key = (dev, torch.cuda.current_stream().cuda_stream)
     if key not in _ws:
-        _ws[key] = torch.zeros(34 * BN_WS_MAX_C + 8, device=dev, dtype=torch.float64)
+        _ws[key] = torch.zeros(workspace_bytes(WS_BN, F32, BN_WS_MAX_C) // 8, device=dev, dtype=torch.float64)
     return _ws[key]
 
 

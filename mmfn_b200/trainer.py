@@ -110,8 +110,13 @@ class Trainer:
         self.cur_epoch, self.cur_iter = t["epoch"], t.get("iter", 0)
         self.bestval, self.train_loss, self.val_loss = t["bestval"], t["train_loss"], t["val_loss"]
         self.bestval_epoch = t.get("bestval_epoch", 0)
-        load_optimizer_state_dict(self.engine, torch.load(os.path.join(logdir, "best_optim.pth"), map_location="cpu"))
-        self.model.load_state_dict(torch.load(os.path.join(logdir, "best_model.pth"), map_location="cpu"))
+        # the reference reloads best_* (phase2_train_net.py:288-302); a run saved before its first validation has only
+        # model.pth / recent_optim.pth -- fall back to those instead of raising
+        def pick(best, recent):
+            p = os.path.join(logdir, best)
+            return p if os.path.isfile(p) else os.path.join(logdir, recent)
+        load_optimizer_state_dict(self.engine, torch.load(pick("best_optim.pth", "recent_optim.pth"), map_location="cpu"))
+        self.model.load_state_dict(torch.load(pick("best_model.pth", "model.pth"), map_location="cpu"))
         return True
 
 

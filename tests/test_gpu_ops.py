@@ -163,6 +163,41 @@ def test_attention_products_on_strided_heads(C, T):
     close(ops.softmax_bwd(p, g_dS, hs ** -0.5), Sr.grad, 1e-4)
 
 
+@pytest.mark.parametrize("C,T,B", [(64, 192, 3), (128, 192, 3), (256, 192, 2), (512, 256, 2), (512, 256, 16)])
+def test_attention_fwd_fused(C, T, B):
+    """mmfn_attention_fwd_tf32 (S = QK^T in TMEM -> softmax -> dropout -> PV, one tcgen05 kernel; SelfAttention.forward,
+    model_rad.py:96-105) against plain fp32 torch for the four transformer geometries (+ the benchmarked B=16 grid of
+    transformer4), without and with dropout: P == softmax, Pd == P * mask / (1 - p) with the library's own mask,
+    y == Pd V."""
+    from mmfn_b200 import ops
+    nh = 4
+    hs = C // nh
+    qkv = torch.randn(B * T, 3 * C)
+    heads = lambda t2d, i: t2d[:, i * C:(i + 1) * C].view(B, T, nh, hs).permute(0, 2, 1, 3)
+    k, q, v = (heads(qkv, i) for i in range(3))
+    Pr = torch.softmax(q @ k.transpose(-1, -2) / hs ** 0.5, -1)
+    yr = (Pr @ v).permute(0, 2, 1, 3).reshape(B * T, C)
+    g_qkv = qkv.to(DEV)
+    assert ops.attention_fwd_ok(T, C, nh)
+    y, P, Pd = ops.attention_fwd(g_qkv, B, T, C, nh)
+    assert Pd is P                                                  # no dropout: one probability tensor
+    close(P, Pr, 2e-3)
+    close(y, yr, 3e-3)
+    close(P.sum(-1), torch.ones(B, nh, T), 1e-5)                    # rows are normalised in fp32 whatever the TF32 scores
+    p_drop, seed = 0.1, 1234
+    y2, P2, Pd2 = ops.attention_fwd(g_qkv, B, T, C, nh, p_drop, seed)
+    mask = ops.dropout(torch.ones_like(P2), p_drop, seed)           # same (seed, index) hash as the kernel
+    close(P2, Pr, 2e-3)
+    assert torch.equal(Pd2, P2 * mask)
+    assert abs((mask == 0).float().mean().item() - p_drop) < 0.01
+    close(y2, ((Pr * mask.cpu()) @ v).permute(0, 2, 1, 3).reshape(B * T, C), 3e-3)
+    # the saved tensors are exactly what the (unfused) backward consumes: dV = Pd^T dY through the batched GEMM
+    dy = torch.randn(B * T, C, device=DEV)
+    dv = torch.empty(B, nh, T, hs, device=DEV)
+    ops.gemm(Pd2.transpose(-1, -2), dy.view(B, T, nh, hs).permute(0, 2, 1, 3).transpose(-1, -2), dv)
+    close(dv, (Pr * mask.cpu()).transpose(-1, -2) @ dy.cpu().view(B, T, nh, hs).permute(0, 2, 1, 3), 3e-3)
+
+
 @pytest.mark.parametrize("C,T", [(64, 192), (128, 192), (256, 192), (512, 256)])
 def test_fused_attention_backward_dq_ds(C, T):
     """attention_bwd_dq (dP in TMEM -> dS -> dQ in one kernel) against torch autograd, without dropout, and against the
@@ -403,3 +438,92 @@ def test_dropout_masks_are_consistent_between_kernels_and_passes():
     assert torch.equal(c1 == 0, mask == 0) and torch.equal(c2 == 0, mask == 0)
     assert abs((mask == 0).float().mean().item() - 0.1) < 0.01
     assert torch.allclose(mask[mask != 0], torch.tensor(1 / 0.9, device=DEV))
+
+
+def test_dropout_masks_follow_the_bound_rng_offset_in_every_translation_unit():
+    """Round-1 advisor finding: norm.cu never bound the device-resident rng offset, so with an engine alive the
+    LayerNorm-backward residual-dropout mask differed from the forward GEMM-epilogue mask.  Bump the process-wide
+    offset to a non-zero value and check every dropout site against the stand-alone kernel (misc.cu)."""
+    from mmfn_b200 import ops
+    from mmfn_b200._lib import lib
+    rng = lib().rng_tensor(torch.device(DEV))
+    old = rng.clone()
+    try:
+        rng.add_(1000003 * 17)
+        p, seed = 0.1, 77
+        M, C = 384, 256
+        ones = torch.ones(M, C, device=DEV)
+        mask = ops.dropout(ones, p, seed)                             # misc.cu
+        assert abs((mask == 0).float().mean().item() - p) < 0.02
+        rng.add_(-1000003 * 17)
+        mask0 = ops.dropout(ones, p, seed)
+        rng.add_(1000003 * 17)
+        assert not torch.equal(mask0, mask)                           # the offset really changes the masks
+        # GEMM epilogues (tcgen05 and SIMT)
+        A, W = torch.randn(M, 128, device=DEV), torch.randn(C, 128, device=DEV)
+        for tf32 in (True, False):
+            ops.TF32 = tf32
+            c = torch.empty(M, C, device=DEV)
+            ops.gemm(A, W, c, drop_p=p, seed=seed)
+            assert torch.equal(c == 0, mask == 0), tf32
+        ops.TF32 = True
+        # LayerNorm backward's fused dropout copy (norm.cu)
+        x, dy = torch.randn(M, C, device=DEV), torch.randn(M, C, device=DEV)
+        g, b = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV)
+        _, mean, rstd = ops.layernorm_fwd(x, g, b)
+        dx, dxd = ops.layernorm_bwd(dy, x, g, b, mean, rstd, None, None, parts=1, drop=(p, seed))
+        assert torch.equal(dxd, dx * mask)
+        # fused attention probabilities (attn_tc.cu) and the softmax kernels (attn.cu)
+        B, T, Cc, nh = 2, 192, 128, 4
+        qkv = torch.randn(B * T, 3 * Cc, device=DEV)
+        _, P, Pd = ops.attention_fwd(qkv, B, T, Cc, nh, p, seed)
+        pm = ops.dropout(torch.ones_like(P), p, seed)
+        assert torch.equal(Pd, P * pm)
+        S = torch.randn(B, nh, T, T, device=DEV)
+        p2, pd2 = ops.softmax_fwd(S, 1.0, p, seed)
+        assert torch.equal(pd2, p2 * pm)
+    finally:
+        rng.copy_(old)
+
+
+def test_block_gradients_with_residual_dropout_and_bound_rng():
+    """One transformer Block forward + backward with resid_pdrop = attn_pdrop = 0.1 and a non-zero rng offset bound:
+    the hand-written backward must be the exact adjoint of the forward WITH ITS MASKS.  Checked by a directional
+    finite difference of the (mask-frozen, hence piecewise-linear-in-dropout) forward in exact-fp32 mode."""
+    from mmfn_b200 import ops
+    from mmfn_b200._lib import lib
+    from mmfn_b200.config import GlobalConfig
+    from mmfn_b200.model_rad import Block, _Aux
+    from mmfn_b200.params import ParamStore
+    ops.TF32 = False
+    rng = lib().rng_tensor(torch.device(DEV))
+    old = rng.clone()
+    try:
+        rng.add_(1000003 * 5)
+        cfg = GlobalConfig()
+        st = ParamStore(cfg, DEV)
+        torch.manual_seed(1)
+        st.flat.copy_(torch.randn_like(st.flat) * 0.05)
+        pre = "encoder.transformer2.blocks.0"
+        for ln in ("ln1", "ln2"):
+            st.p(f"{pre}.{ln}.weight").fill_(1.0)
+        C, B, T = 128, 2, 192
+        blk = Block(st, pre, C, 4, 0.1, 0.1)
+        x = torch.randn(B * T, C, device=DEV)
+        d = torch.randn(B * T, C, device=DEV)                     # perturbation direction
+        w = torch.randn(B * T, C, device=DEV)                     # loss = <w, block(x)>
+        seed = 4242
+
+        def f(xx):
+            return (blk.fwd(xx, B, T, seed, True).double() * w.double()).sum().item()
+        eps = 1e-2
+        fd = (f(x + eps * d) - f(x - eps * d)) / (2 * eps)        # masks depend on (seed, index) only: frozen
+        blk.fwd(x, B, T, seed, True)
+        st.flat_grad.zero_()
+        dz = ops.dropout(w, 0.1, seed + 2)                        # gradient entering the fc2 residual-branch dropout
+        dx, _ = blk.bwd(w, dz, (0.0, 0))
+        _Aux.join_all()
+        an = (dx.double() * d.double()).sum().item()
+        assert abs(an - fd) <= 2e-3 * max(1.0, abs(fd)), (an, fd)
+    finally:
+        rng.copy_(old)

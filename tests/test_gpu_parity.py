@@ -242,6 +242,134 @@ def test_config2_full_size_properties(dev):
     assert cos.item() > 0.999, cos.item()
 
 
+def _report(name, payload):
+    """Measured parity figures are also dropped under gpurun_out/ (scratch) so a GPU session can copy them to profiles/."""
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, name), "w") as f:
+            json.dump(payload, f, indent=1)
+    except OSError:
+        pass
+
+
+def _grad_stats(model, ograds):
+    """whole-model cosine + per-tensor relative errors of store.flat_grad against the oracle gradients"""
+    dot = n1 = n2 = 0.0
+    rel = {}
+    for k, g in ograds.items():
+        if g is None:
+            continue
+        got = model.store.torch_view(k, grad=True).detach().cpu().double()
+        gd = g.double()
+        assert torch.isfinite(got).all(), k
+        dot += (got * gd).sum().item(); n1 += got.pow(2).sum().item(); n2 += gd.pow(2).sum().item()
+        rel[k] = ((got - gd).norm() / gd.norm().clamp_min(1e-12)).item()
+    return dot / (n1 ** 0.5 * n2 ** 0.5), rel
+
+
+def test_config2_b16_matches_oracle(dev):
+    """BASELINE configs[1] at the BENCHMARKED size (B=16, production TF32 tensor-core path, dropout off, train-mode
+    BatchNorm) against the CPU oracle on the same seeded frames: waypoints (north_star bar 1e-3 L1), loss, every
+    parameter gradient.  Measured on B200 (profiles/r02_parity_b16.json): see the asserted bounds."""
+    from mmfn_b200.engine import TrainEngine
+    B = 16
+    cfg, model, sd, b = _setup(dev, B, tf32=True)
+    eng = TrainEngine(model, lr=1e-4)
+    db = {k: v.to(dev) for k, v in b.items()}
+    loss = eng.forward_backward(db).item()
+    torch.cuda.synchronize()
+    lidar_ref = torch.from_numpy(np.stack([bev_oracle.lidar_to_histogram_features(p[:, :3].numpy()) for p in b["points"]]))
+    inputs = (b["rgb_u8"].float(), lidar_ref, b["lane"], b["lane_num"], b["radar"], b["radar_adj"],
+              b["target_point"], b["velocity"])
+    oloss, opred, ograds = mmfn_oracle.train_step({k: v.clone() for k, v in sd.items()}, cfg,
+                                                  dict(inputs=inputs, gt_waypoints=b["gt_waypoints"]))
+    wp_l1 = (eng.last_pred.cpu() - opred).abs().mean().item()
+    wp_max = (eng.last_pred.cpu() - opred).abs().max().item()
+    cosine, rel = _grad_stats(model, ograds)
+    rels = sorted(rel.values())
+    worst_key = max(rel, key=rel.get)
+    _report("parity_b16_tf32.json", dict(B=B, path="tf32", waypoint_l1=wp_l1, waypoint_max=wp_max, loss=loss,
+                                         oracle_loss=oloss.item(), grad_cosine=cosine, grad_rel_median=rels[len(rels) // 2],
+                                         grad_rel_p90=rels[int(0.9 * len(rels))], grad_rel_worst=rels[-1], worst_key=worst_key))
+    assert wp_l1 < 1e-3, wp_l1                                   # north_star bar
+    assert abs(loss - oloss.item()) < 1e-3
+    assert cosine > 0.985, cosine
+    assert rels[len(rels) // 2] < 0.25 and rels[-1] < 0.6, (rels[len(rels) // 2], rels[-1], worst_key)
+
+
+def test_loss_trajectory_tracks_oracle_over_20_steps(dev):
+    """20 optimisation steps (BEV scatter + forward + backward + fused AdamW) of the production TF32 path against the
+    oracle's AdamW on two alternating fixed batches (B=4, dropout off).  AdamW's sign-like early steps amplify tiny
+    gradient differences element-wise, so the weights drift apart slowly; the LOSS trajectories must stay together."""
+    from mmfn_b200.engine import TrainEngine
+    B, steps = 4, 20
+    cfg, model, sd, _ = _setup(dev, B, tf32=True)
+    batches = [synthetic.synth_batch(B, first_index=i * B) for i in range(2)]
+    eng = TrainEngine(model, lr=1e-4)
+    osd = {k: v.clone() for k, v in sd.items()}
+    opt = {"t": 0, "m": {}, "v": {}}
+    dbs, oins = [], []
+    for b in batches:
+        dbs.append({k: v.to(dev) for k, v in b.items()})
+        lidar_ref = torch.from_numpy(np.stack([bev_oracle.lidar_to_histogram_features(p[:, :3].numpy()) for p in b["points"]]))
+        oins.append(dict(inputs=(b["rgb_u8"].float(), lidar_ref, b["lane"], b["lane_num"], b["radar"], b["radar_adj"],
+                                 b["target_point"], b["velocity"]), gt_waypoints=b["gt_waypoints"]))
+    mine, orac = [], []
+    for i in range(steps):
+        mine.append(eng.step(dbs[i % 2]).item())
+        orac.append(mmfn_oracle.train_step(osd, cfg, oins[i % 2], opt_state=opt)[0].item())
+    dev_rel = [abs(a - o) / max(abs(o), 1e-6) for a, o in zip(mine, orac)]
+    _report("trajectory_tf32.json", dict(B=B, steps=steps, loss_gpu=mine, loss_oracle=orac, rel_dev=dev_rel))
+    assert dev_rel[0] < 1e-3, dev_rel[0]
+    assert max(dev_rel) < 0.05, (max(dev_rel), mine, orac)
+    # both optimisers make the same progress on the two batches they keep seeing
+    assert sum(mine[-2:]) < sum(mine[:2]) and sum(orac[-2:]) < sum(orac[:2])
+    assert abs(sum(mine[-2:]) - sum(orac[-2:])) < 0.05 * sum(orac[-2:])
+
+
+def test_torchvision_resnet34_weights_load_into_both_trunks(dev):
+    """ImageCNN = models.resnet34(pretrained=True) minus fc (model_rad.py:22-23): a torchvision state_dict must land in
+    encoder.image_encoder.features.* and encoder.img_map_encoder.features.* (KRSC storage behind the (K,C,R,S) view)."""
+    import torchvision
+    from mmfn_b200.model_rad import MMFN
+    tv = torchvision.models.resnet34(weights=None)
+    tsd = {k: torch.randn_like(v) if v.dtype.is_floating_point else v + 3 for k, v in tv.state_dict().items()}
+    model = MMFN(GlobalConfig(), dev)
+    before = model.state_dict()["encoder.lidar_encoder._model.layer1.0.conv1.weight"].clone()
+    loaded = model.load_torchvision_resnet34(tsd)
+    assert len(loaded) == 2 * (len(tsd) - 2)
+    msd = model.state_dict()
+    for trunk in ("image_encoder", "img_map_encoder"):
+        for k in ("conv1.weight", "layer2.0.downsample.0.weight", "layer4.2.bn2.running_var", "layer3.5.conv2.weight",
+                  "bn1.num_batches_tracked"):
+            assert torch.equal(msd[f"encoder.{trunk}.features.{k}"].cpu(), tsd[k]), (trunk, k)
+    w = model.store.p("encoder.image_encoder.features.layer1.0.conv1.weight")          # KRSC as the kernels read it
+    assert torch.equal(w.cpu(), tsd["layer1.0.conv1.weight"].permute(0, 2, 3, 1))
+    assert torch.equal(msd["encoder.lidar_encoder._model.layer1.0.conv1.weight"], before)   # other trunks untouched
+    bad = dict(tsd)
+    bad["conv1.weight"] = torch.zeros(64, 3, 3, 3)
+    with pytest.raises(Exception):
+        model.load_torchvision_resnet34(bad)
+
+
+def test_two_gpu_data_parallel_step_matches_hand_summed_gradients(dev):
+    """On-hardware check of the DDP contract (phase2_train_net.py:263-269) over NCCL, world size 2: the all-reduced
+    gradient equals the hand-summed per-rank gradients (and their mean the oracle's replica average), parameters
+    are bit-identical on both ranks after eager and CUDA-graph steps.  Needs 2 GPUs (skipped otherwise)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    worker = os.path.join(root, "tests", "dp_gpu_worker.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", worker],
+                       capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "DP_GPU_OK" in r.stdout, r.stdout[-2000:]
+
+
 def test_state_dict_interchange(dev):
     from mmfn_b200.model_rad import MMFN
     keys = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "state_dict_keys.json")))
