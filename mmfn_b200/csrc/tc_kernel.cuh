@@ -15,10 +15,10 @@
 namespace tc {
 
 constexpr int TBM = 128;          // tile rows (UMMA M)
-constexpr int TBK = 32;           // fp32 elements per k-block = one 128-byte swizzle span
-constexpr int UMMA_K = 8;         // tf32
+constexpr int TBK = 32;           // fp32 elements per k-block = one 128-byte swizzle span (bf16 pipelines: Op::EB = 64)
+constexpr int UMMA_K = 8;         // tf32 (bf16: 16); either way a k-block is FOUR MMAs, 32 bytes apart in a K-major row
 constexpr int TC_THREADS = 320;        // TMA warp + MMA warp + 8 epilogue warps
-constexpr int BOX_BYTES = 32 * 128;   // one MN-major box: 32 k-rows x 128 B
+constexpr int BOX_BYTES = 32 * 128;   // one MN-major fp32 box: 32 k-rows x 128 B (bf16: ElemTraits<64>::BOX_BYTES)
 
 struct Epilogue {
   float* C;
@@ -31,6 +31,8 @@ struct Epilogue {
   float drop_p;
   uint64_t drop_seed;
   unsigned long long* trace;   // optional: 8 x %globaltimer stamps of CTA 0 (mmfn_tc_set_trace), else null
+  __nv_bfloat16* C16;                // OUT16 instantiations: the result is written here as bf16 (same indexing as C)
+  const __nv_bfloat16* mask16;       // like mask, for a bf16 tensor
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -53,7 +55,7 @@ struct Smem {
 
 // Epilogue shared by every tcgen05 kernel of the library (called by warps 2..9 = 8 epilogue warps; `smem` is the
 // 1024-byte aligned dynamic shared memory whose first 8*32*36*4 + 128*8 bytes are idle once tmem_full has fired).
-template <class Op, int TBN, bool FULL>
+template <class Op, int TBN, bool FULL, bool OUT16 = false>
 __device__ __forceinline__ void tc_epilogue(const Op& op, const Epilogue& e, uint8_t* smem, uint64_t* tmem_full,
                                             uint32_t tmem_base, int kb0, int kb1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -73,8 +75,8 @@ __device__ __forceinline__ void tc_epilogue(const Op& op, const Epilogue& e, uin
     const float* bias = op.first_split() ? e.bias : nullptr;    // bias / residual are added by the first K split only
     const float* res = op.first_split() ? e.res : nullptr;
     // 16-byte path: every row of this warp's quarter starts on a float4 boundary and the tile is full in N
-    const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0) && (n0 + TBN <= N) &&
-                     __all_sync(0xffffffffu, !my_ok || (my_off & 3) == 0);
+    const bool vec = (N % 4 == 0) && (OUT16 ? (reinterpret_cast<uintptr_t>(e.C16) & 7) == 0 : (reinterpret_cast<uintptr_t>(e.C) & 15) == 0) &&
+                     (n0 + TBN <= N) && __all_sync(0xffffffffu, !my_ok || (my_off & 3) == 0);
     mbar_wait(tmem_full, 0);                              // all MMAs retired: TMEM valid, smem stages idle
     tc_fence_after();
     if (ew < 4) sts64(row_off + (q * 32 + lane) * 8, my_ok ? my_off : (int64_t)-1);
@@ -122,6 +124,17 @@ __device__ __forceinline__ void tc_epilogue(const Op& op, const Epilogue& e, uin
 #pragma unroll
               for (int rr = 0; rr < 4; ++rr)
                 m4v[rr] = offs[rr] >= 0 ? __ldg(reinterpret_cast<const float4*>(e.mask + offs[rr] + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else if (e.mask16) {
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr) {
+                m4v[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (offs[rr] >= 0) {
+                  const uint2 raw = __ldg(reinterpret_cast<const uint2*>(e.mask16 + offs[rr] + col));
+                  const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+                  const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+                  m4v[rr] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                }
+              }
             }
           }
 #pragma unroll
@@ -138,7 +151,7 @@ __device__ __forceinline__ void tc_epilogue(const Op& op, const Epilogue& e, uin
 #pragma unroll
                 for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.f);
               }
-              if (e.mask) {
+              if (e.mask || e.mask16) {
                 const float mk[4] = {m4v[rr].x, m4v[rr].y, m4v[rr].z, m4v[rr].w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) x[j] = mk[j] > 0.f ? x[j] : 0.f;
@@ -151,7 +164,13 @@ __device__ __forceinline__ void tc_epilogue(const Op& op, const Epilogue& e, uin
               }
             }
             if (res) { x[0] += r4[rr].x; x[1] += r4[rr].y; x[2] += r4[rr].z; x[3] += r4[rr].w; }
-            if (e.accum == 0) *reinterpret_cast<float4*>(e.C + idx) = make_float4(x[0], x[1], x[2], x[3]);
+            if constexpr (OUT16) {          // bf16 result (tensors that only feed further MMAs): one 8-byte store
+              const __nv_bfloat162 lo = __floats2bfloat162_rn(x[0], x[1]), hi = __floats2bfloat162_rn(x[2], x[3]);
+              uint2 pk;
+              pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(e.C16 + idx) = pk;
+            } else if (e.accum == 0) *reinterpret_cast<float4*>(e.C + idx) = make_float4(x[0], x[1], x[2], x[3]);
             else  // split-K / weight-gradient accumulation: one 16-byte vector reduction instead of four scalar atomics
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(e.C + idx), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
           }
@@ -171,10 +190,12 @@ __device__ __forceinline__ void tc_epilogue(const Op& op, const Epilogue& e, uin
             if constexpr (FULL) {
               if (e.act == 1) t = fmaxf(t, 0.f);
               if (e.mask) t = __ldg(e.mask + idx) > 0.f ? t : 0.f;
+              else if (e.mask16) t = __bfloat162float(e.mask16[idx]) > 0.f ? t : 0.f;
               if (e.drop_p > 0.f) t *= mmfn_dropout_scale(e.drop_p, e.drop_seed, (uint64_t)idx);
             }
             if (res) t += __ldg(res + idx);
-            if (e.accum == 0) e.C[idx] = t;
+            if constexpr (OUT16) e.C16[idx] = __float2bfloat16_rn(t);
+            else if (e.accum == 0) e.C[idx] = t;
             else atomicAdd(e.C + idx, t);
           }
         }
@@ -193,10 +214,11 @@ __device__ __forceinline__ void tc_epilogue(const Op& op, const Epilogue& e, uin
 //   bool first_split();                           bias / residual are added by the first split only
 // FULL = false compiles the epilogue down to alpha*acc + bias + residual (most launches); the
 // ReLU / mask / dropout variant is a separate instantiation so its hash arithmetic is never if-converted in.
-template <class Op, int TBN, int STAGES, bool FULL>
+template <class Op, int TBN, int STAGES, bool FULL, bool OUT16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Op op, Epilogue e) {
   using L = Smem<TBN, STAGES>;
+  using ET = ElemTraits<Op::EB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -238,7 +260,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   } else if (warp == 1) {
     if (elect_one()) {                                   // ===== MMA issuer =====
-      const uint32_t idesc = idesc_tf32(TBM, TBN, Op::A_MN, Op::B_MN);
+      const uint32_t idesc = ET::idesc(TBM, TBN, Op::A_MN, Op::B_MN);
       int stage = 0; uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full[stage], phase);
@@ -248,10 +270,10 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
         for (int k = 0; k < TBK / UMMA_K; ++k) {
-          // K-major: 8 tf32 = 32 bytes along the swizzled row; MN-major: the next 8 k-rows = 1024 bytes
-          uint64_t ad = Op::A_MN ? smem_desc_mnmajor(sa + k * 1024, BOX_BYTES) : smem_desc_kmajor(sa + k * 32);
-          uint64_t bd = Op::B_MN ? smem_desc_mnmajor(sb + k * 1024, BOX_BYTES) : smem_desc_kmajor(sb + k * 32);
-          mma_tf32(tmem_base, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          // K-major: 8 tf32 / 16 bf16 = 32 bytes along the swizzled row; MN-major: the next 8 / 16 k-rows = 1024 / 2048 bytes
+          uint64_t ad = Op::A_MN ? ET::mn_desc(sa + k * ET::MN_STEP) : smem_desc_kmajor(sa + k * 32);
+          uint64_t bd = Op::B_MN ? ET::mn_desc(sb + k * ET::MN_STEP) : smem_desc_kmajor(sb + k * 32);
+          ET::mma(tmem_base, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
         mma_commit(&empty[stage]);                       // frees the smem slot once these MMAs retire
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -260,7 +282,7 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       TC_STAMP(3);                                       // all MMAs issued
     }
   } else {
-    tc_epilogue<Op, TBN, FULL>(op, e, smem, tmem_full, tmem_base, kb0, kb1);
+    tc_epilogue<Op, TBN, FULL, OUT16>(op, e, smem, tmem_full, tmem_base, kb0, kb1);
   }
   if (threadIdx.x == 64) TC_STAMP(5);                    // epilogue stores issued
   tc_fence_before();
@@ -269,25 +291,36 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (threadIdx.x == 64) TC_STAMP(6);                    // TMEM released
 }
 
-template <class Op, int TBN, int STAGES, bool FULL>
+template <class Op, int TBN, int STAGES, bool FULL, bool OUT16 = false>
 static int launch_impl(const CUtensorMap& ta, const CUtensorMap& tb, const Op& op, const Epilogue& e, dim3 grid,
                        cudaStream_t stream, const char* what) {
   using L = Smem<TBN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(tc_kernel<Op, TBN, STAGES, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    cudaError_t ce = cudaFuncSetAttribute(tc_kernel<Op, TBN, STAGES, FULL, OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (ce != cudaSuccess) { mmfn_set_error("%s: smem attribute: %s", what, cudaGetErrorString(ce)); return (int)ce; }
     attr_set = true;
   }
-  tc_kernel<Op, TBN, STAGES, FULL><<<grid, TC_THREADS, L::TOTAL, stream>>>(ta, tb, op, e);
+  tc_kernel<Op, TBN, STAGES, FULL, OUT16><<<grid, TC_THREADS, L::TOTAL, stream>>>(ta, tb, op, e);
   return mmfn_launch_status(what);
 }
 
-template <class Op, int TBN, int STAGES>
+// ALLOW16: instantiate the bf16-output epilogues for this Op (GEMMs; the convolutions always write fp32)
+template <class Op, int TBN, int STAGES, bool ALLOW16 = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Op& op, const Epilogue& e, dim3 grid,
                   cudaStream_t stream, const char* what) {
-  if (e.act != 0 || e.mask != nullptr || e.drop_p > 0.f)
-    return launch_impl<Op, TBN, STAGES, true>(ta, tb, op, e, grid, stream, what);
+  const bool full = e.act != 0 || e.mask != nullptr || e.mask16 != nullptr || e.drop_p > 0.f;
+  if (e.C16 != nullptr) {
+    if constexpr (ALLOW16) {
+      if (e.accum != 0) { mmfn_set_error("%s: a bf16 result cannot be accumulated atomically", what); return MMFN_BAD_ARG; }
+      if (full) return launch_impl<Op, TBN, STAGES, true, true>(ta, tb, op, e, grid, stream, what);
+      return launch_impl<Op, TBN, STAGES, false, true>(ta, tb, op, e, grid, stream, what);
+    } else {
+      mmfn_set_error("%s: bf16 output is not available for this kernel", what);
+      return MMFN_BAD_ARG;
+    }
+  }
+  if (full) return launch_impl<Op, TBN, STAGES, true>(ta, tb, op, e, grid, stream, what);
   return launch_impl<Op, TBN, STAGES, false>(ta, tb, op, e, grid, stream, what);
 }
 

@@ -487,9 +487,11 @@ def test_dropout_masks_follow_the_bound_rng_offset_in_every_translation_unit():
 
 
 def test_block_gradients_with_residual_dropout_and_bound_rng():
-    """One transformer Block forward + backward with resid_pdrop = attn_pdrop = 0.1 and a non-zero rng offset bound:
-    the hand-written backward must be the exact adjoint of the forward WITH ITS MASKS.  Checked by a directional
-    finite difference of the (mask-frozen, hence piecewise-linear-in-dropout) forward in exact-fp32 mode."""
+    """One transformer Block (model_rad.py:112-133) forward + backward with resid_pdrop = attn_pdrop = 0.1 and a
+    non-zero rng offset bound, exact-fp32 kernels, against torch autograd on the SAME block with the library's own
+    masks (ops.dropout of ones): the hand-written backward must regenerate exactly the forward's masks in every
+    translation unit (GEMM epilogues, softmax, LayerNorm backward)."""
+    import math
     from mmfn_b200 import ops
     from mmfn_b200._lib import lib
     from mmfn_b200.config import GlobalConfig
@@ -505,25 +507,43 @@ def test_block_gradients_with_residual_dropout_and_bound_rng():
         torch.manual_seed(1)
         st.flat.copy_(torch.randn_like(st.flat) * 0.05)
         pre = "encoder.transformer2.blocks.0"
-        for ln in ("ln1", "ln2"):
-            st.p(f"{pre}.{ln}.weight").fill_(1.0)
-        C, B, T = 128, 2, 192
-        blk = Block(st, pre, C, 4, 0.1, 0.1)
+        C, B, T, nh, p = 128, 2, 192, 4, 0.1
+        hs = C // nh
+        blk = Block(st, pre, C, nh, p, p)
+        blk.ln1.g.add_(1.0); blk.ln2.g.add_(1.0)
         x = torch.randn(B * T, C, device=DEV)
-        d = torch.randn(B * T, C, device=DEV)                     # perturbation direction
         w = torch.randn(B * T, C, device=DEV)                     # loss = <w, block(x)>
         seed = 4242
-
-        def f(xx):
-            return (blk.fwd(xx, B, T, seed, True).double() * w.double()).sum().item()
-        eps = 1e-2
-        fd = (f(x + eps * d) - f(x - eps * d)) / (2 * eps)        # masks depend on (seed, index) only: frozen
-        blk.fwd(x, B, T, seed, True)
+        out = blk.fwd(x, B, T, seed, True)
         st.flat_grad.zero_()
-        dz = ops.dropout(w, 0.1, seed + 2)                        # gradient entering the fc2 residual-branch dropout
+        dz = ops.dropout(w, p, seed + 2)                          # gradient entering the fc2 residual-branch dropout
         dx, _ = blk.bwd(w, dz, (0.0, 0))
         _Aux.join_all()
-        an = (dx.double() * d.double()).sum().item()
-        assert abs(an - fd) <= 2e-3 * max(1.0, abs(fd)), (an, fd)
+        torch.cuda.synchronize()
+        # ---- torch autograd replica with the library's masks
+        m_att = ops.dropout(torch.ones(B, nh, T, T, device=DEV), p, seed)
+        m_proj = ops.dropout(torch.ones(B * T, C, device=DEV), p, seed + 1)
+        m_fc2 = ops.dropout(torch.ones(B * T, C, device=DEV), p, seed + 2)
+        leaves = {n: t.detach().clone().requires_grad_(True) for n, t in
+                  dict(x=x, wqkv=blk.qkv.w, bqkv=blk.qkv.b, wp=blk.proj.w, bp=blk.proj.b, w1=blk.fc1.w, b1=blk.fc1.b,
+                       w2=blk.fc2.w, b2=blk.fc2.b, g1=blk.ln1.g, c1=blk.ln1.b, g2=blk.ln2.g, c2=blk.ln2.b).items()}
+        L = leaves
+        h1 = F.layer_norm(L["x"], (C,), L["g1"], L["c1"])
+        qkv = h1 @ L["wqkv"].t() + L["bqkv"]
+        heads = lambda i: qkv[:, i * C:(i + 1) * C].view(B, T, nh, hs).permute(0, 2, 1, 3)
+        k, q, v = heads(0), heads(1), heads(2)
+        att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(hs), -1) * m_att
+        y = (att @ v).permute(0, 2, 1, 3).reshape(B * T, C)
+        x1 = L["x"] + (y @ L["wp"].t() + L["bp"]) * m_proj
+        h2 = F.layer_norm(x1, (C,), L["g2"], L["c2"])
+        x2 = x1 + (torch.relu(h2 @ L["w1"].t() + L["b1"]) @ L["w2"].t() + L["b2"]) * m_fc2
+        close(out, x2, 1e-4)
+        (x2 * w).sum().backward()
+        close(dx, L["x"].grad, 2e-4)
+        for name, got in dict(wqkv=blk.qkv.dw, bqkv=blk.qkv.db, wp=blk.proj.dw, bp=blk.proj.db, w1=blk.fc1.dw, b1=blk.fc1.db,
+                              w2=blk.fc2.dw, b2=blk.fc2.db, g1=blk.ln1.dg, c1=blk.ln1.db, g2=blk.ln2.dg, c2=blk.ln2.db).items():
+            ref = L[name].grad
+            err = (got - ref).norm().item() / max(ref.norm().item(), 1e-9)
+            assert err < 1e-3, (name, err)
     finally:
         rng.copy_(old)
