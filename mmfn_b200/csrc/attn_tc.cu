@@ -41,7 +41,8 @@ __device__ __forceinline__ void sts_swizzled_row(uint8_t* tile, int row, const f
 __global__ void __launch_bounds__(AT_THREADS)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmP,
-                const __grid_constant__ CUtensorMap tmPd, const __grid_constant__ CUtensorMap tmY, AttnParams p) {
+                const __grid_constant__ CUtensorMap tmPd, const __grid_constant__ CUtensorMap tmY, AttnParams p,
+                __nv_bfloat16* __restrict__ y16, int C) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);
@@ -193,18 +194,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc::tc_fence_after();
     if (threadIdx.x == 64) tc::tma_store_wait_read<0>();
     asm volatile("bar.sync 1, 128;" ::: "memory");
-    for (int d = 0; d < nkc; ++d) {
-      float v[32];
-      tc::tmem_ld32(tmem_o + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * 32), v);
-      sts_swizzled_row(smem + d * 16384, row, v);
+    if (y16) {
+      // bf16 attention output (it only feeds the projection GEMM): each thread owns one row -- 32 columns = 64
+      // contiguous bytes = two full 32-byte sectors per chunk, written straight from registers
+      for (int d = 0; d < nkc; ++d) {
+        float v[32];
+        tc::tmem_ld32(tmem_o + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * 32), v);
+        if (m0 + row < T) {
+          __nv_bfloat16* dst = y16 + ((int64_t)b * T + m0 + row) * C + h * hs + d * 32;
+          const int nv = min(32, hs - d * 32);
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            if (j < nv) {
+              const uint2 lo = mmfn_pack_bf16x4(v[j], v[j + 1], v[j + 2], v[j + 3]), hi = mmfn_pack_bf16x4(v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(dst + j) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            }
+        }
+      }
+    } else {
+      for (int d = 0; d < nkc; ++d) {
+        float v[32];
+        tc::tmem_ld32(tmem_o + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * 32), v);
+        sts_swizzled_row(smem + d * 16384, row, v);
+      }
+      tc::fence_async_smem();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        for (int d = 0; d < nkc; ++d) tc::tma_store_4d(smem + d * 16384, &tmY, d * 32, h, m0, b);
+        tc::tma_store_commit();
+        tc::tma_store_wait_read<0>();
+      }
     }
-    tc::fence_async_smem();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (threadIdx.x == 64) {
-      for (int d = 0; d < nkc; ++d) tc::tma_store_4d(smem + d * 16384, &tmY, d * 32, h, m0, b);
-      tc::tma_store_commit();
-      tc::tma_store_wait_read<0>();
-    }
+    if (threadIdx.x == 64) tc::tma_store_wait_read<0>();      // outstanding P tile stores must have read their smem
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -401,7 +422,8 @@ int head_tmap(CUtensorMap* m, const float* base, int B, int T, int nh, int hs, i
 // qkv: (B*T, 3C) fused projections, columns [key | query | value] (model_rad.py:96-98); y: (B*T, C);
 // prob: (B, nh, T, T) softmax probabilities saved for backward; prob_drop: same after dropout (required iff
 // drop_p > 0, else may be null).  T in {64, 128, 192, 256}, head size C/nh in {16, 32, 64, 128}.
-MMFN_API int mmfn_attention_fwd_tf32(const float* qkv, float* y, float* prob, float* prob_drop,
+// y_bf16 != 0: y is a BF16 tensor (BASELINE configs[2]: the attention output only feeds the bf16 projection GEMM).
+MMFN_API int mmfn_attention_fwd_tf32(const float* qkv, void* y, int y_bf16, float* prob, float* prob_drop,
                                      int B, int T, int C, int nh, float drop_p, uint64_t seed, cudaStream_t stream) {
   MMFN_CHECK_ARG(qkv && y && prob, "attention_fwd: null pointer");
   MMFN_CHECK_ARG(drop_p <= 0.f || prob_drop, "attention_fwd: prob_drop is required with dropout");
@@ -414,7 +436,7 @@ MMFN_API int mmfn_attention_fwd_tf32(const float* qkv, float* y, float* prob, fl
   if (int rc = head_tmap(&tk, qkv, B, T, nh, hs, 3 * C, T, false, true)) return rc;
   if (int rc = head_tmap(&tq, qkv + C, B, T, nh, hs, 3 * C, 128, false, true)) return rc;
   if (int rc = head_tmap(&tv, qkv + 2 * C, B, T, nh, hs, 3 * C, 32, true, true)) return rc;
-  if (int rc = head_tmap(&ty, y, B, T, nh, hs, C, 128, false, false)) return rc;
+  if (int rc = head_tmap(&ty, y_bf16 ? qkv : static_cast<const float*>(y), B, T, nh, hs, y_bf16 ? 3 * C : C, 128, false, false)) return rc;   // unused when y_bf16
   {
     uint64_t dims[4] = {(uint64_t)T, (uint64_t)T, (uint64_t)nh, (uint64_t)B};
     uint64_t strides[4] = {1, (uint64_t)T, (uint64_t)T * T, (uint64_t)T * T * nh};
@@ -436,7 +458,7 @@ MMFN_API int mmfn_attention_fwd_tf32(const float* qkv, float* y, float* prob, fl
     attr_set = true;
   }
   dim3 grid((T + 127) / 128, nh, B);
-  attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(tq, tk, tv, tp, tpd, ty, p);
+  attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM, stream>>>(tq, tk, tv, tp, tpd, ty, p, y_bf16 ? static_cast<__nv_bfloat16*>(y) : nullptr, C);
   return mmfn_launch_status("attention_fwd");
 }
 

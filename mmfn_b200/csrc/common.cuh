@@ -1,6 +1,7 @@
 // Shared device/host helpers for libmmfn_b200.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <math.h>
 
@@ -82,6 +83,20 @@ __host__ __device__ __forceinline__ void mmfn_dropout_scale4(float p, uint64_t s
   s[1] = ((lo >> 16) >= thr) ? keep : 0.f;
   s[2] = ((hi & 0xFFFFu) >= thr) ? keep : 0.f;
   s[3] = ((hi >> 16) >= thr) ? keep : 0.f;
+}
+
+// four fp32 values -> four bf16 (round to nearest even), packed for one 8-byte store; and back
+__device__ __forceinline__ uint2 mmfn_pack_bf16x4(float a, float b, float c, float d) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 r;
+  r.x = *reinterpret_cast<const uint32_t*>(&lo);
+  r.y = *reinterpret_cast<const uint32_t*>(&hi);
+  return r;
+}
+__device__ __forceinline__ float4 mmfn_unpack_bf16x4(uint2 r) {
+  const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+  const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -182,7 +182,7 @@ __global__ void adamw_advance_kernel(float* state, float beta1, float beta2) {
 
 __global__ void adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
                              float4* __restrict__ v, int64_t n4, float lr, float beta1, float beta2, float eps,
-                             float wd, const float* __restrict__ state, float gscale) {
+                             float wd, const float* __restrict__ state, float gscale, uint2* __restrict__ p16) {
   float bc1 = state[1], bc2 = state[2];
   float step_size = lr / bc1, rbc2 = 1.0f / sqrtf(bc2), decay = 1.0f - lr * wd;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -198,6 +198,7 @@ __global__ void adamw_kernel(float4* __restrict__ p, const float4* __restrict__ 
       pa[k] = pk - step_size * (ma[k] / denom);
     }
     p[i] = pp; m[i] = mm; v[i] = vv;
+    if (p16) p16[i] = mmfn_pack_bf16x4(pp.x, pp.y, pp.z, pp.w);      // bf16 shadow read by the tensor-core kernels
   }
 }
 
@@ -236,15 +237,16 @@ MMFN_API int mmfn_l1_loss(const float* pred, const float* gt, int n, float* loss
 }
 
 // state: 3 device floats {t, 1-beta1^t, 1-beta2^t}; advanced on device so a captured graph replays correctly.
+// p_bf16 (nullable): bf16 shadow of p refreshed in the same pass (BASELINE configs[2]).
 MMFN_API int mmfn_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                              float beta2, float eps, float weight_decay, float* state, float grad_scale,
-                             cudaStream_t stream) {
+                             void* p_bf16, cudaStream_t stream) {
   MMFN_CHECK_ARG(p && g && m && v && state && n >= 0 && n % 4 == 0, "adamw: n must be a multiple of 4");
   MMFN_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adamw: buffers must be 16B aligned");
   adamw_advance_kernel<<<1, 1, 0, stream>>>(state, beta1, beta2);
   if (n > 0)
     adamw_kernel<<<grid_1d(n / 4, 256), 256, 0, stream>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v, n / 4, lr,
-                                                           beta1, beta2, eps, weight_decay, state, grad_scale);
+                                                           beta1, beta2, eps, weight_decay, state, grad_scale, (uint2*)p_bf16);
   return mmfn_launch_status("adamw");
 }
 
@@ -258,11 +260,11 @@ MMFN_API int mmfn_adamw_advance(float* state, float beta1, float beta2, cudaStre
 
 MMFN_API int mmfn_adamw_apply(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                               float beta2, float eps, float weight_decay, const float* state, float grad_scale,
-                              cudaStream_t stream) {
+                              void* p_bf16, cudaStream_t stream) {
   MMFN_CHECK_ARG(p && g && m && v && state && n >= 0 && n % 4 == 0, "adamw_apply: n must be a multiple of 4");
   MMFN_CHECK_ARG((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adamw_apply: buffers must be 16B aligned");
   if (n > 0)
     adamw_kernel<<<grid_1d(n / 4, 256), 256, 0, stream>>>((float4*)p, (const float4*)g, (float4*)m, (float4*)v, n / 4, lr,
-                                                           beta1, beta2, eps, weight_decay, state, grad_scale);
+                                                           beta1, beta2, eps, weight_decay, state, grad_scale, (uint2*)p_bf16);
   return mmfn_launch_status("adamw_apply");
 }

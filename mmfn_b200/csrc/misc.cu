@@ -25,6 +25,34 @@ __global__ void colsum_kernel(const float* __restrict__ x, int64_t ld, int64_t M
   }
 }
 
+// bf16 input variant (gradients written in bf16 by the LayerNorm backward / GEMM epilogues of the bf16 configuration)
+__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, int64_t M, int N, float* __restrict__ out) {
+  __shared__ float s[8][33];
+  int n = blockIdx.x * 32 + threadIdx.x;
+  int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
+  int64_t r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float a = 0.f;
+  if (n < N) {
+#pragma unroll 8
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) a += __bfloat162float(x[r * ld + n]);
+  }
+  s[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) a += s[i][threadIdx.x];
+    atomicAdd(out + n, a);
+  }
+}
+
+// y = bf16(x), 4 elements per thread
+__global__ void f32_to_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ y, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x + i);
+    y[i] = mmfn_pack_bf16x4(v.x, v.y, v.z, v.w);
+  }
+}
+
 __global__ void elu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float v = x[i];
@@ -258,6 +286,29 @@ MMFN_API int mmfn_colsum_f32(const float* x, int64_t ld, int64_t M, int N, float
   dim3 grid((unsigned)colgroups, (unsigned)slabs);
   colsum_kernel<<<grid, dim3(32, 8), 0, stream>>>(x, ld, M, N, out);
   return mmfn_launch_status("colsum");
+}
+
+// out[n] += sum_m x[m*ld + n] for a BF16 matrix (bias gradients of the bf16 configuration)
+MMFN_API int mmfn_colsum_bf16(const void* x, int64_t ld, int64_t M, int N, float* out, cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && out && M >= 0 && N > 0 && ld >= N, "colsum_bf16: bad args");
+  if (M == 0) return 0;
+  const int64_t colgroups = (N + 31) / 32;
+  int64_t slabs = ceil_div64(M, 64);
+  const int64_t cap = ceil_div64(148 * 8, colgroups);
+  if (slabs > cap) slabs = cap;
+  if (slabs > 65535) slabs = 65535;
+  colsum_bf16_kernel<<<dim3((unsigned)colgroups, (unsigned)slabs), dim3(32, 8), 0, stream>>>((const __nv_bfloat16*)x, ld, M, N, out);
+  return mmfn_launch_status("colsum_bf16");
+}
+
+// y (bf16) = x (fp32), n % 4 == 0, 16 / 8-byte aligned: the bf16 shadow of the master weights after a checkpoint load,
+// and tensors produced by fp32-only kernels that feed a bf16 GEMM.
+MMFN_API int mmfn_f32_to_bf16(const float* x, void* y, int64_t n, cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && y && n >= 0 && n % 4 == 0, "f32_to_bf16: n must be a multiple of 4");
+  MMFN_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 7) == 0, "f32_to_bf16: alignment");
+  if (n == 0) return 0;
+  f32_to_bf16_kernel<<<grid_1d(n / 4, 256), 256, 0, stream>>>((const float4*)x, (uint2*)y, n / 4);
+  return mmfn_launch_status("f32_to_bf16");
 }
 
 MMFN_API int mmfn_elu_fwd(const float* x, float* y, int64_t n, cudaStream_t stream) {

@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256)
 bn_apply_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n4, int C4,
                 const float* __restrict__ mean, const float* __restrict__ rstd,
                 const float4* __restrict__ gamma, const float4* __restrict__ beta,
-                const float4* __restrict__ res, int relu) {
+                const float4* __restrict__ res, int relu, uint2* __restrict__ y16) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const bool fixed = stride % C4 == 0;
@@ -168,6 +168,7 @@ bn_apply_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n4
     if (res) { const float4 q = __ldg(res + i); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     y[i] = o;
+    if (y16) y16[i] = mmfn_pack_bf16x4(o.x, o.y, o.z, o.w);       // bf16 twin: the operand of the next convolution
   }
 }
 
@@ -178,7 +179,7 @@ bn_bwd_dx_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
                  const float4* __restrict__ yout, const float* __restrict__ mean,
                  const float* __restrict__ rstd, const float* __restrict__ gamma,
                  const float* __restrict__ fin, int64_t M, int C4,
-                 float4* __restrict__ dx, float4* __restrict__ dres) {
+                 float4* __restrict__ dx, float4* __restrict__ dres, uint2* __restrict__ dx16) {
   const int C = C4 * 4;
   const int64_t n4 = M * C4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -212,7 +213,8 @@ bn_bwd_dx_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
     o.y = k.y * (g.y - a.y - (xv.y - m.y) * r.y * b.y);
     o.z = k.z * (g.z - a.z - (xv.z - m.z) * r.z * b.z);
     o.w = k.w * (g.w - a.w - (xv.w - m.w) * r.w * b.w);
-    dx[i] = o;
+    if (dx16) dx16[i] = mmfn_pack_bf16x4(o.x, o.y, o.z, o.w);     // dz only feeds the wgrad / dgrad MMAs
+    else dx[i] = o;
     if (dres) dres[i] = g;
   }
 }
@@ -226,7 +228,8 @@ bn_small_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, con
                 const float4* __restrict__ res, float4* __restrict__ out, float4* __restrict__ dres,
                 float* __restrict__ mean, float* __restrict__ rstd, const float4* __restrict__ gamma,
                 const float4* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
-                float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int C4, float eps, float momentum, int relu) {
+                float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int C4, float eps, float momentum, int relu,
+                uint2* __restrict__ out16) {
   __shared__ double red[8][8];
   __shared__ float fin[8];
   const int cq = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -312,6 +315,7 @@ bn_small_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, con
         for (int k = 0; k < 4; ++k) o[k] = fmaxf(o[k], 0.f);
       }
       out[i] = make_float4(o[0], o[1], o[2], o[3]);
+      if (out16) out16[i] = mmfn_pack_bf16x4(o[0], o[1], o[2], o[3]);
     }
   } else {
     float kk[4];
@@ -334,7 +338,8 @@ bn_small_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, con
       float o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) o[k] = kk[k] * (gg[k] - fin[k] - (xa[k] - m4[k]) * r4[k] * fin[4 + k]);
-      out[i] = make_float4(o[0], o[1], o[2], o[3]);
+      if (out16) out16[i] = mmfn_pack_bf16x4(o[0], o[1], o[2], o[3]);
+      else out[i] = make_float4(o[0], o[1], o[2], o[3]);
       if (dres) dres[i] = make_float4(gg[0], gg[1], gg[2], gg[3]);
     }
   }
@@ -361,7 +366,7 @@ __device__ __forceinline__ float act_grad(float v, int act) {
 __global__ void ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                               const float* __restrict__ beta, float* __restrict__ y,
                               float* __restrict__ mean, float* __restrict__ rstd,
-                              int64_t M, int C, float eps, int act) {
+                              int64_t M, int C, float eps, int act, __nv_bfloat16* __restrict__ y16) {
   int lane = threadIdx.x & 31;
   int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -373,6 +378,11 @@ __global__ void ln_fwd_kernel(const float* __restrict__ x, const float* __restri
   for (int c = lane; c < C; c += 32) { float d = xr[c] - mu; v += d * d; }
   float rs = rsqrtf(warp_sum(v) / (float)C + eps);
   if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+  if (y16) {                                   // bf16 result: the LayerNorm output only feeds GEMMs
+    __nv_bfloat16* yr = y16 + row * C;
+    for (int c = lane; c < C; c += 32) yr[c] = __float2bfloat16_rn(act_fwd((xr[c] - mu) * rs * gamma[c] + beta[c], act));
+    return;
+  }
   float* yr = y + row * C;
   for (int c = lane; c < C; c += 32) yr[c] = act_fwd((xr[c] - mu) * rs * gamma[c] + beta[c], act);
 }
@@ -383,7 +393,8 @@ __global__ void ln_bwd_dx_kernel(const float* __restrict__ dy, const float* __re
                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                  const float* __restrict__ mean, const float* __restrict__ rstd,
                                  const float* __restrict__ dres, float* __restrict__ dx, int64_t M, int C, int act,
-                                 float* __restrict__ dx_drop, float drop_p, uint64_t drop_seed) {
+                                 float* __restrict__ dx_drop, float drop_p, uint64_t drop_seed,
+                                 __nv_bfloat16* __restrict__ dx_drop16) {
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -429,12 +440,13 @@ __global__ void ln_bwd_dx_kernel(const float* __restrict__ dy, const float* __re
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
       *reinterpret_cast<float4*>(dx + row * C + c) = o;
-      if (dx_drop) {        // gradient entering the next residual branch's dropout (same hash as the forward mask)
+      if (dx_drop || dx_drop16) {   // gradient entering the next residual branch's dropout (same hash as the forward mask)
         const uint64_t i0 = (uint64_t)(row * C + c);
         float ds[4];
-        mmfn_dropout_scale4(drop_p, drop_seed, i0, ds);          // i0 % 4 == 0 (C % 4 == 0)
+        mmfn_dropout_scale4(drop_p, drop_seed, i0, ds);          // i0 % 4 == 0 (C % 4 == 0); all ones when drop_p == 0
         o.x *= ds[0]; o.y *= ds[1]; o.z *= ds[2]; o.w *= ds[3];
-        *reinterpret_cast<float4*>(dx_drop + row * C + c) = o;
+        if (dx_drop16) *reinterpret_cast<uint2*>(dx_drop16 + row * C + c) = mmfn_pack_bf16x4(o.x, o.y, o.z, o.w);
+        else *reinterpret_cast<float4*>(dx_drop + row * C + c) = o;
       }
     }
   }
@@ -475,6 +487,7 @@ __global__ void ln_bwd_param_kernel(const float* __restrict__ dy, const float* _
 
 }  // namespace
 
+// y_bf16 (nullable): a bf16 twin of y written in the same pass -- the operand of the next bf16 convolution.
 // x,y: (M,C) NHWC rows.  ws: per-stream scratch of at least 34*C + 8 doubles that is ZERO on entry (zero it once
 // after allocation; every call leaves it zero again).  Writes mean/rstd (C each) and, when running_* are non-null,
 // the momentum update with the unbiased variance.
@@ -482,14 +495,16 @@ MMFN_API int mmfn_bn_train_fwd(const float* x, float* y, int64_t M, int C,
                                const float* gamma, const float* beta,
                                float* running_mean, float* running_var, float momentum, float eps,
                                float* mean, float* rstd, const float* res, int relu,
-                               double* ws, cudaStream_t stream) {
+                               double* ws, void* y_bf16, cudaStream_t stream) {
   MMFN_CHECK_ARG(x && y && gamma && beta && mean && rstd && ws, "bn_fwd: null pointer");
+  MMFN_CHECK_ARG(((uintptr_t)y_bf16 & 7) == 0, "bn_fwd: y_bf16 must be 8-byte aligned");
   MMFN_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "bn_fwd: C must be a positive multiple of 4");
   MMFN_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)mean | (uintptr_t)rstd) & 15) == 0,
                  "bn_fwd: 16-byte alignment");
   if (M <= BN_SMALL_ROWS) {
     bn_small_kernel<false><<<C / 4, 256, 0, stream>>>((const float4*)x, nullptr, nullptr, (const float4*)res, (float4*)y, nullptr,
-        mean, rstd, (const float4*)gamma, (const float4*)beta, running_mean, running_var, nullptr, nullptr, (int)M, C / 4, eps, momentum, relu);
+        mean, rstd, (const float4*)gamma, (const float4*)beta, running_mean, running_var, nullptr, nullptr, (int)M, C / 4, eps, momentum, relu,
+        (uint2*)y_bf16);
     return mmfn_launch_status("bn_train_fwd");
   }
   int qpr; dim3 grid; int64_t rpb;
@@ -498,15 +513,16 @@ MMFN_API int mmfn_bn_train_fwd(const float* x, float* y, int64_t M, int C,
   bn_colsum_kernel<false><<<grid, BN_THREADS, 0, stream>>>((const float4*)x, nullptr, nullptr, nullptr, nullptr, M, C / 4, qpr, rpb, ws, fz);
   int64_t n4 = M * C / 4;
   bn_apply_kernel<<<grid_1d(n4, 256), 256, 0, stream>>>((const float4*)x, (float4*)y, n4, C / 4,
-      mean, rstd, (const float4*)gamma, (const float4*)beta, (const float4*)res, relu);
+      mean, rstd, (const float4*)gamma, (const float4*)beta, (const float4*)res, relu, (uint2*)y_bf16);
   return mmfn_launch_status("bn_train_fwd");
 }
 
+// dx_bf16 != 0: dx is a BF16 tensor (the gradient of the convolution output only feeds the wgrad / dgrad MMAs).
 // yout: post-ReLU output of the forward (null when no ReLU followed). dres (nullable)
 // receives the ReLU-masked dy for the residual branch.  dgamma/dbeta are accumulated.  ws: as in mmfn_bn_train_fwd.
 MMFN_API int mmfn_bn_train_bwd(const float* dy, const float* x, const float* yout,
                                const float* mean, const float* rstd, const float* gamma,
-                               int64_t M, int C, float* dx, float* dres, float* dgamma, float* dbeta,
+                               int64_t M, int C, void* dx, int dx_bf16, float* dres, float* dgamma, float* dbeta,
                                double* ws, cudaStream_t stream) {
   MMFN_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && ws, "bn_bwd: null pointer");
   MMFN_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "bn_bwd: C must be a positive multiple of 4");
@@ -514,7 +530,8 @@ MMFN_API int mmfn_bn_train_bwd(const float* dy, const float* x, const float* you
                  "bn_bwd: 16-byte alignment");
   if (M <= BN_SMALL_ROWS) {
     bn_small_kernel<true><<<C / 4, 256, 0, stream>>>((const float4*)x, (const float4*)dy, (const float4*)yout, nullptr, (float4*)dx, (float4*)dres,
-        const_cast<float*>(mean), const_cast<float*>(rstd), (const float4*)gamma, nullptr, nullptr, nullptr, dgamma, dbeta, (int)M, C / 4, 0.f, 0.f, 0);
+        const_cast<float*>(mean), const_cast<float*>(rstd), (const float4*)gamma, nullptr, nullptr, nullptr, dgamma, dbeta, (int)M, C / 4, 0.f, 0.f, 0,
+        dx_bf16 ? (uint2*)dx : nullptr);
     return mmfn_launch_status("bn_train_bwd");
   }
   int qpr; dim3 grid; int64_t rpb;
@@ -523,7 +540,8 @@ MMFN_API int mmfn_bn_train_bwd(const float* dy, const float* x, const float* you
   BnFinal fz = {nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, fin, dgamma, dbeta};
   bn_colsum_kernel<true><<<grid, BN_THREADS, 0, stream>>>((const float4*)x, (const float4*)dy, (const float4*)yout, mean, rstd, M, C / 4, qpr, rpb, ws, fz);
   bn_bwd_dx_kernel<<<grid_1d(M * C / 4, 256), 256, 0, stream>>>(
-      (const float4*)dy, (const float4*)x, (const float4*)yout, mean, rstd, gamma, fin, M, C / 4, (float4*)dx, (float4*)dres);
+      (const float4*)dy, (const float4*)x, (const float4*)yout, mean, rstd, gamma, fin, M, C / 4, (float4*)dx, (float4*)dres,
+      dx_bf16 ? (uint2*)dx : nullptr);
   return mmfn_launch_status("bn_train_bwd");
 }
 
@@ -537,34 +555,37 @@ __global__ void bn_eval_stats_kernel(const float* rm, const float* rv, float eps
 // Inference-mode BN: y = (x - running_mean) / sqrt(running_var + eps) * gamma + beta (+res, relu).
 MMFN_API int mmfn_bn_eval_fwd(const float* x, float* y, int64_t M, int C, const float* gamma, const float* beta,
                               const float* running_mean, const float* running_var, float eps,
-                              float* mean, float* rstd, const float* res, int relu, cudaStream_t stream) {
+                              float* mean, float* rstd, const float* res, int relu, void* y_bf16, cudaStream_t stream) {
   MMFN_CHECK_ARG(x && y && gamma && beta && running_mean && running_var && mean && rstd, "bn_eval: null pointer");
   MMFN_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "bn_eval: C must be a positive multiple of 4");
   bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, stream>>>(running_mean, running_var, eps, mean, rstd, C);
   int64_t n4 = M * C / 4;
   bn_apply_kernel<<<grid_1d(n4, 256), 256, 0, stream>>>((const float4*)x, (float4*)y, n4, C / 4,
-      mean, rstd, (const float4*)gamma, (const float4*)beta, (const float4*)res, relu);
+      mean, rstd, (const float4*)gamma, (const float4*)beta, (const float4*)res, relu, (uint2*)y_bf16);
   return mmfn_launch_status("bn_eval_fwd");
 }
 
 // act: 0 none, 1 ReLU, 2 exact GELU applied to the LayerNorm output.
-MMFN_API int mmfn_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y,
+// y_bf16 != 0: y is a BF16 tensor (LayerNorm outputs that only feed bf16 GEMMs).
+MMFN_API int mmfn_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y, int y_bf16,
                                 float* mean, float* rstd, int64_t M, int C, float eps, int act,
                                 cudaStream_t stream) {
   MMFN_CHECK_ARG(x && gamma && beta && y && mean && rstd, "ln_fwd: null pointer");
   MMFN_CHECK_ARG(M >= 0 && C > 0, "ln_fwd: bad sizes");
   if (M == 0) return 0;
-  ln_fwd_kernel<<<(unsigned)ceil_div64(M, 8), 256, 0, stream>>>(x, gamma, beta, y, mean, rstd, M, C, eps, act);
+  ln_fwd_kernel<<<(unsigned)ceil_div64(M, 8), 256, 0, stream>>>(x, gamma, beta, y_bf16 ? nullptr : (float*)y, mean, rstd, M, C, eps, act,
+                                                               y_bf16 ? (__nv_bfloat16*)y : nullptr);
   return mmfn_launch_status("layernorm_fwd");
 }
 
+// drop_bf16 != 0: dx_drop is a BF16 tensor and is written even when drop_p == 0 (it feeds the bf16 GEMMs of the branch).
 // parts: bit 0 = data gradient dx (+ dres; optionally also dx_drop = dx * dropout_mask(drop_p, drop_seed), the
 // gradient entering the dropout of the next residual branch), bit 1 = parameter gradients (accumulated).  The two
 // halves are independent kernels so that a caller can put the parameter reduction on a side stream.
 MMFN_API int mmfn_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* beta,
                                 const float* mean, const float* rstd, const float* dres, float* dx,
                                 float* dgamma, float* dbeta, int64_t M, int C, int act, int parts,
-                                float* dx_drop, float drop_p, uint64_t drop_seed, cudaStream_t stream) {
+                                void* dx_drop, int drop_bf16, float drop_p, uint64_t drop_seed, cudaStream_t stream) {
   MMFN_CHECK_ARG(dy && x && gamma && beta && mean && rstd, "ln_bwd: null pointer");
   MMFN_CHECK_ARG((parts & 3) != 0 && (!(parts & 1) || dx) && (!(parts & 2) || (dgamma && dbeta)), "ln_bwd: missing output for the requested parts");
   MMFN_CHECK_ARG(M >= 0 && C > 0 && C <= 512 && C % 4 == 0, "ln_bwd: C must be a multiple of 4 in (0, 512]");
@@ -573,10 +594,12 @@ MMFN_API int mmfn_layernorm_bwd(const float* dy, const float* x, const float* ga
   if (M == 0) return 0;
   if (parts & 1) {
     unsigned blocks = (unsigned)ceil_div64(M, 8);
-    if (drop_p <= 0.f) dx_drop = nullptr;
-    if (C <= 128) ln_bwd_dx_kernel<1><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act, dx_drop, drop_p, drop_seed);
-    else if (C <= 256) ln_bwd_dx_kernel<2><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act, dx_drop, drop_p, drop_seed);
-    else ln_bwd_dx_kernel<4><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act, dx_drop, drop_p, drop_seed);
+    // fp32 copy: only needed when a mask applies (the caller reuses dx otherwise); bf16 copy: always (it is a conversion too)
+    float* dd = (!drop_bf16 && drop_p > 0.f) ? (float*)dx_drop : nullptr;
+    __nv_bfloat16* dd16 = drop_bf16 ? (__nv_bfloat16*)dx_drop : nullptr;
+    if (C <= 128) ln_bwd_dx_kernel<1><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act, dd, drop_p, drop_seed, dd16);
+    else if (C <= 256) ln_bwd_dx_kernel<2><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act, dd, drop_p, drop_seed, dd16);
+    else ln_bwd_dx_kernel<4><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act, dd, drop_p, drop_seed, dd16);
   }
   if (parts & 2) {
     // 32 rows (4 row iterations per thread, all loads in flight) per CTA unless that exceeds ~8 waves of CTAs

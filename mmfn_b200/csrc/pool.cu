@@ -40,7 +40,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 
 // 4 channels per thread (C % 4 == 0): float4 loads, the four argmax taps packed into one 32-bit store
 __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ idx,
-                                   int B, int H, int W, int C, int Ho, int Wo) {
+                                   int B, int H, int W, int C, int Ho, int Wo, uint2* __restrict__ y16) {
   const int C4 = C >> 2;
   const int64_t n = (int64_t)B * Ho * Wo * C4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -66,6 +66,7 @@ __global__ void maxpool_fwd_kernel(const float* __restrict__ x, float* __restric
       }
     }
     *reinterpret_cast<float4*>(y + (i << 2)) = make_float4(best[0], best[1], best[2], best[3]);
+    if (y16) y16[i] = mmfn_pack_bf16x4(best[0], best[1], best[2], best[3]);
     *reinterpret_cast<uint32_t*>(idx + (i << 2)) = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
   }
 }
@@ -219,7 +220,8 @@ __device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, 
 
 // out = feat + bilinear_up(tok[:, m*64:(m+1)*64, :] as 8x8xC -> HxW); 4 channels per thread
 __global__ void upsample_add_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ tok,
-                                        float* __restrict__ out, int m, int T, int B, int H, int W, int C, int align) {
+                                        float* __restrict__ out, int m, int T, int B, int H, int W, int C, int align,
+                                        uint2* __restrict__ out16) {
   float sh = bilinear_scale(8, H, align), sw = bilinear_scale(8, W, align);
   const int C4 = C >> 2;
   int64_t n = (int64_t)B * H * W * C4;
@@ -243,6 +245,7 @@ __global__ void upsample_add_fwd_kernel(const float* __restrict__ feat, const fl
     f.z += a0 * (b0 * t00.z + b1 * t01.z) + a1 * (b0 * t10.z + b1 * t11.z);
     f.w += a0 * (b0 * t00.w + b1 * t01.w) + a1 * (b0 * t10.w + b1 * t11.w);
     *reinterpret_cast<float4*>(out + (i << 2)) = f;
+    if (out16) out16[i] = mmfn_pack_bf16x4(f.x, f.y, f.z, f.w);
   }
 }
 
@@ -365,12 +368,13 @@ MMFN_API int mmfn_transpose_f32(const float* in, float* out, int nb, int R, int 
   return mmfn_launch_status("transpose");
 }
 
+// y_bf16 (nullable): bf16 twin of y (operand of the first layer-1 convolution in the bf16 configuration).
 MMFN_API int mmfn_maxpool3x3s2_fwd(const float* x, float* y, uint8_t* idx, int B, int H, int W, int C,
-                                   cudaStream_t stream) {
+                                   void* y_bf16, cudaStream_t stream) {
   MMFN_CHECK_ARG(x && y && idx && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "maxpool_fwd: bad args (C % 4 == 0)");
   MMFN_CHECK_ARG((((uintptr_t)x | (uintptr_t)y) & 15) == 0 && ((uintptr_t)idx & 3) == 0, "maxpool_fwd: alignment");
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  maxpool_fwd_kernel<<<grid_1d((int64_t)B * Ho * Wo * (C / 4), 256), 256, 0, stream>>>(x, y, idx, B, H, W, C, Ho, Wo);
+  maxpool_fwd_kernel<<<grid_1d((int64_t)B * Ho * Wo * (C / 4), 256), 256, 0, stream>>>(x, y, idx, B, H, W, C, Ho, Wo, (uint2*)y_bf16);
   return mmfn_launch_status("maxpool_fwd");
 }
 
@@ -421,11 +425,13 @@ MMFN_API int mmfn_tokens_bwd(const float* dtokens, float* df0, float* df1, float
   return mmfn_launch_status("tokens_bwd");
 }
 
+// out_bf16 (nullable): bf16 twin of out (operand of the next layer's first convolution in the bf16 configuration).
 MMFN_API int mmfn_upsample_add_fwd(const float* feat, const float* tokens, float* out, int m, int T,
-                                   int B, int H, int W, int C, int align_corners, cudaStream_t stream) {
+                                   int B, int H, int W, int C, int align_corners, void* out_bf16, cudaStream_t stream) {
   MMFN_CHECK_ARG(feat && tokens && out && B > 0 && H >= 8 && W >= 8 && C > 0 && m >= 0 && (m + 1) * 64 <= T, "upsample_add_fwd: bad args");
   MMFN_CHECK_ARG(C % 4 == 0 && (((uintptr_t)feat | (uintptr_t)tokens | (uintptr_t)out) & 15) == 0, "upsample_add_fwd: C % 4 == 0, 16-byte aligned");
-  upsample_add_fwd_kernel<<<grid_1d((int64_t)B * H * W * (C / 4), 256), 256, 0, stream>>>(feat, tokens, out, m, T, B, H, W, C, align_corners);
+  upsample_add_fwd_kernel<<<grid_1d((int64_t)B * H * W * (C / 4), 256), 256, 0, stream>>>(feat, tokens, out, m, T, B, H, W, C, align_corners,
+                                                                                     (uint2*)out_bf16);
   return mmfn_launch_status("upsample_add_fwd");
 }
 

@@ -98,6 +98,8 @@ class TrainEngine:
         self.state = torch.zeros(3, device=dev, dtype=torch.float32)
         self.p_active = self.st.flat[:n]
         self.g_active = self.st.flat_grad[:n]
+        self.p16_active = self.st.flat16[:n]         # bf16 weight shadow, refreshed by the AdamW kernel (bf16 configuration)
+        self.st.sync_shadow()
         self.last_pred = None
         # device-resident dropout offset, bumped once per step inside the (captured) schedule.  ONE cell per
         # device, owned by the library binding (never freed, never rebound by a second engine); the data-parallel
@@ -115,6 +117,8 @@ class TrainEngine:
         """b: device batch. Returns the loss (0-d device tensor); gradients land in store.flat_grad."""
         model = self.model
         model.train()
+        if ops.BF16 and not torch.cuda.is_current_stream_capturing():
+            self.st.sync_shadow()                      # eager callers may have touched the fp32 masters; replays rely on AdamW
         self.st.flat_grad.zero_()
         self.rng.add_(1000003)
         self.st.flat_nbt.add_(model._nbt_step())
@@ -133,7 +137,8 @@ class TrainEngine:
         if collective:
             parallel.allreduce_sum_(self.g_active, self.pg)                       # ONE collective per step
         ops.adamw_step_(self.p_active, self.g_active, self.m, self.v, self.state, self.lr, self.betas[0],
-                        self.betas[1], self.eps, self.wd, grad_scale=1.0 / self.world)
+                        self.betas[1], self.eps, self.wd, grad_scale=1.0 / self.world,
+                        p16=self.p16_active if ops.BF16 else None)
 
     def step(self, device_batch):
         loss = self.forward_backward(device_batch)
@@ -191,7 +196,8 @@ class TrainEngine:
         g = self.g_active[lo:hi]
         parallel.allreduce_sum_(g, self.pg)
         ops.adamw_apply_(self.p_active[lo:hi], g, self.m[lo:hi], self.v[lo:hi], self.state, self.lr, self.betas[0],
-                         self.betas[1], self.eps, self.wd, grad_scale=1.0 / self.world)
+                         self.betas[1], self.eps, self.wd, grad_scale=1.0 / self.world,
+                         p16=self.p16_active[lo:hi] if ops.BF16 else None)
 
     def step_graph(self):
         """Replay the captured step.  Order on the device: graph A (zero grads, BEV, forward, backward down to the

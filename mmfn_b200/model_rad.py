@@ -129,36 +129,45 @@ class ConvBN:
     def __init__(self, st, conv_key, bn_key, stride, pad, dgrad=True):
         self.dgrad = dgrad
         self.w, self.dw = st.p(conv_key), st.g(conv_key)
+        self.w16 = st.p16(conv_key)                 # bf16 shadow of the filters (bf16 configuration)
         self.gam, self.dgam = st.p(bn_key + ".weight"), st.g(bn_key + ".weight")
         self.bet, self.dbet = st.p(bn_key + ".bias"), st.g(bn_key + ".bias")
         self.rm, self.rv = st.buf(bn_key + ".running_mean"), st.buf(bn_key + ".running_var")
         self.stride, self.pad = stride, pad
 
-    def fwd(self, x, res=None, relu=True, train=True):
+    def fwd(self, x, res=None, relu=True, train=True, no_twin=False):
         self.x, self.relu = x, relu
         self.col = None
-        if ops.stem_uses_im2col(x, self.w):
+        # bf16 configuration: the convolution reads the bf16 twin its producer wrote (x.h) and the bf16 filter shadow;
+        # its fp32 output z feeds the batch statistics; BatchNorm-apply writes y in fp32 AND its bf16 twin
+        Ho, Wo = ops.conv_out_hw(x.shape[1], x.shape[2], self.w.shape[1], self.w.shape[2], self.stride, self.pad)
+        self.bf = ops.twin(x) is not None and ops.bf16_conv_ok(x.shape[3], self.w.shape[0], Ho, Wo)
+        if self.bf:
+            self.z = ops.conv2d_fwd(x.h, self.w16, self.stride, self.pad)
+        elif ops.stem_uses_im2col(x, self.w):
             # stems: im2col + one dense tensor-core GEMM; the column matrix is kept for the weight gradient
             self.z, self.col, self.w_pad = ops.conv2d_fwd_im2col(x, self.w, self.stride, self.pad, getattr(self, "w_pad", None))
         else:
             self.z = ops.conv2d_fwd(x, self.w, self.stride, self.pad)
-        if train:
-            self.y, self.mean, self.rstd = ops.bn_train_fwd(self.z, self.gam, self.bet, self.rm, self.rv, res=res, relu=relu)
-        else:
-            self.y, self.mean, self.rstd = ops.bn_eval_fwd(self.z, self.gam, self.bet, self.rm, self.rv, res=res, relu=relu)
+        bn = ops.bn_train_fwd if train else ops.bn_eval_fwd
+        self.y, self.mean, self.rstd = bn(self.z, self.gam, self.bet, self.rm, self.rv, res=res, relu=relu,
+                                          want16=ops.BF16 and not no_twin)
         return self.y
 
     def bwd(self, dy, need_dx=True, want_dres=False, dx_res=None):
         dz, dres = ops.bn_train_bwd(dy, self.z, self.y if self.relu else None, self.mean, self.rstd, self.gam,
-                                    self.dgam, self.dbet, want_dres)
+                                    self.dgam, self.dbet, want_dres, out_bf16=self.bf)
         x, col = self.x, self.col
-        if col is not None:
+        if self.bf:
+            x16 = x.h
+            _Aux.run(lambda: ops.conv2d_wgrad_(dz, x16, self.dw, self.stride, self.pad), dz, x16)
+        elif col is not None:
             _Aux.run(lambda: ops.conv2d_wgrad_im2col_(dz, col, self.dw), dz, col)
         else:
             _Aux.run(lambda: ops.conv2d_wgrad_(dz, x, self.dw, self.stride, self.pad), dz, x)
         dx = None
         if need_dx:
-            dx = ops.conv2d_dgrad(dz, self.w, self.x.shape, self.stride, self.pad, res=dx_res)
+            dx = ops.conv2d_dgrad(dz, self.w16 if self.bf else self.w, self.x.shape, self.stride, self.pad, res=dx_res)
         self.x = self.z = self.y = self.col = None
         return dx, dres
 
@@ -171,7 +180,7 @@ class BasicBlock:
 
     def fwd(self, x, train):
         a = self.c1.fwd(x, relu=True, train=train)
-        idn = self.ds.fwd(x, relu=False, train=train) if self.ds else x
+        idn = self.ds.fwd(x, relu=False, train=train, no_twin=True) if self.ds else x     # residual only: fp32 suffices
         return self.c2.fwd(a, res=idn, relu=True, train=train)
 
     def bwd(self, dout):
@@ -205,9 +214,9 @@ class Stem:
         self.cb = ConvBN(st, prefix + ".conv1.weight", prefix + ".bn1", 2, 3, dgrad=False)
 
     def fwd(self, x, train):
-        y = self.cb.fwd(x, relu=True, train=train)
+        y = self.cb.fwd(x, relu=True, train=train, no_twin=True)
         self.in_shape = y.shape
-        out, self.idx = ops.maxpool_fwd(y)
+        out, self.idx = ops.maxpool_fwd(y, want16=ops.BF16)
         return out
 
     def bwd(self, d):
@@ -221,22 +230,31 @@ class Linear:
         if keys is None:
             self.w, self.dw = st.p(prefix + ".weight"), st.g(prefix + ".weight")
             self.b, self.db = (st.p(prefix + ".bias"), st.g(prefix + ".bias")) if bias else (None, None)
+            self.w16 = st.p16(prefix + ".weight")
         else:       # several adjacent reference Linears fused into one GEMM
             self.w, self.dw = st.fused([k + ".weight" for k in keys]), st.fused([k + ".weight" for k in keys], True)
             self.b, self.db = st.fused([k + ".bias" for k in keys]), st.fused([k + ".bias" for k in keys], True)
+            self.w16 = st.fused16([k + ".weight" for k in keys])
 
-    def fwd(self, x, out=None, act=0, res=None, drop_p=0.0, seed=0):
-        """x (M,K) -> (M,N) = drop(act(x W^T + b)) + res"""
+    def _w(self, like):
+        """the weight copy matching an operand's element type: bf16 shadow for bf16 activations, fp32 master otherwise"""
+        return self.w16 if like.dtype == torch.bfloat16 else self.w
+
+    def fwd(self, x, out=None, act=0, res=None, drop_p=0.0, seed=0, out_bf16=False):
+        """x (M,K) -> (M,N) = drop(act(x W^T + b)) + res.  A bf16 x multiplies the bf16 weight shadow; out_bf16 writes
+        the result as bf16 (tensors that only feed further GEMMs)."""
         self.x, self.act = x, act
-        y = out if out is not None else torch.empty((x.shape[0], self.w.shape[0]), device=x.device, dtype=torch.float32)
-        ops.gemm(x, self.w, y, bias=self.b, res=res, act=act, drop_p=drop_p, seed=seed)
+        y = out if out is not None else torch.empty((x.shape[0], self.w.shape[0]), device=x.device,
+                                                    dtype=torch.bfloat16 if out_bf16 else torch.float32)
+        ops.gemm(x, self._w(x), y, bias=self.b, res=res, act=act, drop_p=drop_p, seed=seed)
         self.y = y if act else None
         return y
 
-    def bwd(self, dy, need_dx=True, dx_mask=None, masked=False):
+    def bwd(self, dy, need_dx=True, dx_mask=None, masked=False, dx_bf16=False):
         """dy: gradient of this layer's output (dropout mask already applied by the caller).  The
         ReLU derivative is applied here from the saved output unless `masked`.  dx_mask fuses the
-        ReLU mask of the PRODUCER of x into the dgrad GEMM epilogue."""
+        ReLU mask of the PRODUCER of x into the dgrad GEMM epilogue.  bf16 dy (bf16 configuration): the weight
+        gradient multiplies dy^T by the saved bf16 x, the data gradient dy by the bf16 weight shadow."""
         if self.act == 1 and not masked:
             dy = ops.relu_bwd(dy, self.y)
         x = self.x
@@ -248,8 +266,8 @@ class Linear:
         _Aux.run(wgrad, dy, x)
         dx = None
         if need_dx:
-            dx = torch.empty((dy.shape[0], self.w.shape[1]), device=dy.device, dtype=torch.float32)
-            ops.gemm(dy, self.w.t(), dx, mask=dx_mask)
+            dx = torch.empty((dy.shape[0], self.w.shape[1]), device=dy.device, dtype=torch.bfloat16 if dx_bf16 else torch.float32)
+            ops.gemm(dy, self._w(dy).t(), dx, mask=dx_mask)
         self.x = self.y = None
         return dx
 
@@ -260,18 +278,19 @@ class LayerNorm:
         self.b, self.db = st.p(prefix + ".bias"), st.g(prefix + ".bias")
         self.act = act
 
-    def fwd(self, x, out=None):
+    def fwd(self, x, out=None, out_bf16=False):
         self.x = x
-        y, self.mean, self.rstd = ops.layernorm_fwd(x, self.g, self.b, act=self.act, out=out)
+        y, self.mean, self.rstd = ops.layernorm_fwd(x, self.g, self.b, act=self.act, out=out, out_bf16=out_bf16)
         return y
 
-    def bwd(self, dy, dres=None, drop=None):
-        """dx (and, with drop=(p, seed), also dx * dropout mask).  The parameter-gradient reduction is a
-        leaf of the backward graph: it runs on the auxiliary stream."""
+    def bwd(self, dy, dres=None, drop=None, drop_bf16=False):
+        """dx (and, with drop=(p, seed), also dx * dropout mask; drop_bf16: that copy in bf16).  The parameter-gradient
+        reduction is a leaf of the backward graph: it runs on the auxiliary stream."""
         x, mean, rstd = self.x, self.mean, self.rstd
         _Aux.run(lambda: ops.layernorm_bwd(dy, x, self.g, self.b, mean, rstd, self.dg, self.db, act=self.act, parts=2),
                  dy, x, mean, rstd)
-        out = ops.layernorm_bwd(dy, x, self.g, self.b, mean, rstd, None, None, act=self.act, dres=dres, parts=1, drop=drop)
+        out = ops.layernorm_bwd(dy, x, self.g, self.b, mean, rstd, None, None, act=self.act, dres=dres, parts=1, drop=drop,
+                                drop_bf16=drop_bf16)
         self.x = None
         return out
 
@@ -295,11 +314,15 @@ class Block:
         C, nh, hs = self.C, self.nh, self.hs
         ap, rp = (self.attn_p, self.resid_p) if train else (0.0, 0.0)
         self.B, self.T, self.seed, self.ap, self.rp = B, T, seed, ap, rp
-        h1 = self.ln1.fwd(x)
-        qkv = self.qkv.fwd(h1)                                       # columns [key | query | value]
+        # bf16 configuration: tensors that only feed the linears (LayerNorm outputs, attention output, MLP hidden) are
+        # bf16 and multiply the bf16 weight shadow; the residual stream x, the qkv buffer and the attention core
+        # (TF32 tcgen05 kernel, fp32 softmax) stay fp32
+        bf = self.bf = ops.BF16 and C % 64 == 0
+        h1 = self.ln1.fwd(x, out_bf16=bf)
+        qkv = self.qkv.fwd(h1)                                       # columns [key | query | value], fp32
         if ops.attention_fwd_ok(T, C, nh):
             # S = QK^T -> softmax -> dropout -> PV in ONE tcgen05 kernel; only P (and Pd) reach HBM
-            y, self.P, self.Pd = ops.attention_fwd(qkv, B, T, C, nh, ap, seed)
+            y, self.P, self.Pd = ops.attention_fwd(qkv, B, T, C, nh, ap, seed, y_bf16=bf)
         else:
             k, q, v = (self._heads(qkv, B, T, i * C) for i in range(3))
             S = torch.empty((B, nh, T, T), device=x.device, dtype=torch.float32)
@@ -307,31 +330,35 @@ class Block:
             self.P, self.Pd = ops.softmax_fwd(S, 1.0 / math.sqrt(hs), ap, seed)
             y = torch.empty((B * T, C), device=x.device, dtype=torch.float32)
             ops.gemm(self.Pd, v.transpose(-1, -2), y.view(B, T, nh, hs).permute(0, 2, 1, 3))
+            if bf:
+                y = ops.to_bf16(y)
         self.qkv_out = qkv
         x1 = self.proj.fwd(y, res=x, drop_p=rp, seed=seed + 1)
-        h2 = self.ln2.fwd(x1)
-        a = self.fc1.fwd(h2, act=1)
+        h2 = self.ln2.fwd(x1, out_bf16=bf)
+        a = self.fc1.fwd(h2, act=1, out_bf16=bf)
         return self.fc2.fwd(a, res=x1, drop_p=rp, seed=seed + 2)
 
     def bwd(self, dx2, dz, drop_prev=None):
         """dx2: gradient of the block output; dz = dx2 * dropout mask of the fc2 branch (produced by the
-        LayerNorm backward that made dx2).  drop_prev=(p, seed) asks for the same pair for the block below."""
+        LayerNorm backward that made dx2; bf16 in the bf16 configuration).  drop_prev=(p, seed) asks for the same pair
+        for the block below."""
         B, T, C, nh, hs = self.B, self.T, self.C, self.nh, self.hs
+        bf = self.bf
         a = self.fc1.y
-        da = self.fc2.bwd(dz, dx_mask=a)                              # ReLU mask fused into the dgrad GEMM
+        da = self.fc2.bwd(dz, dx_mask=a, dx_bf16=bf)                  # ReLU mask fused into the dgrad GEMM
         dh2 = self.fc1.bwd(da, masked=True)
-        dx1, dzp = self.ln2.bwd(dh2, dres=dx2, drop=(self.rp, self.seed + 1))
+        dx1, dzp = self.ln2.bwd(dh2, dres=dx2, drop=(self.rp, self.seed + 1), drop_bf16=bf)
         y_att = self.proj.x                                        # attention output saved by the projection
-        dy = self.proj.bwd(dzp)
+        dy = self.proj.bwd(dzp)                                    # fp32: operand of the TF32 attention-gradient products
         qkv = self.qkv_out
         k, q, v = (self._heads(qkv, B, T, i * C) for i in range(3))
-        dqkv = torch.empty_like(qkv)
+        dqkv = torch.empty(qkv.shape, device=qkv.device, dtype=torch.bfloat16 if bf else torch.float32)
         dk, dq, dv = (self._heads(dqkv, B, T, i * C) for i in range(3))
         dyh = dy.view(B, T, nh, hs).permute(0, 2, 1, 3)
         Pd = self.Pd
         # critical chain: dPd -> dS -> dQ; dV and dK are leaves until the qkv backward: fork streams
         ev_v = _Aux.fork(lambda: ops.gemm(Pd.transpose(-1, -2), dyh.transpose(-1, -2), dv), Pd, dy, dqkv)
-        if ops.attention_fwd_ok(T, C, nh) and ops.FUSED_ATTN_BWD:
+        if ops.attention_fwd_ok(T, C, nh) and ops.FUSED_ATTN_BWD and not bf:
             # ONE tcgen05 kernel: dPd stays in TMEM, dS tiles feed the dQ MMA and are stored for the dK GEMM
             dS = ops.attention_bwd_dq(qkv, dy, y_att, self.P, dqkv, B, T, C, nh, self.ap, self.seed)
             ev_k = _Aux.fork(lambda: ops.gemm(dS.transpose(-1, -2), q.transpose(-1, -2), dk), dS, qkv, dqkv)
@@ -344,7 +371,8 @@ class Block:
         _Aux.wait(ev_v, ev_k)
         dh1 = self.qkv.bwd(dqkv)
         self.P = self.Pd = self.qkv_out = None
-        return self.ln1.bwd(dh1, dres=dx1, drop=drop_prev if drop_prev is not None else (0.0, 0))
+        return self.ln1.bwd(dh1, dres=dx1, drop=drop_prev if drop_prev is not None else (0.0, 0),
+                            drop_bf16=bf and drop_prev is not None)
 
 
 class FusionGPT:
@@ -374,7 +402,7 @@ class FusionGPT:
     def bwd(self, dtok_out, dfeats):
         """dtok_out (B,T,C); dfeats: per-modality feature gradients, accumulated in place."""
         blocks = self.blocks
-        d, dz = self.ln_f.bwd(dtok_out.view(-1, self.C), drop=(blocks[-1].rp, blocks[-1].seed + 2))
+        d, dz = self.ln_f.bwd(dtok_out.view(-1, self.C), drop=(blocks[-1].rp, blocks[-1].seed + 2), drop_bf16=blocks[-1].bf)
         for i in range(len(blocks) - 1, -1, -1):
             below = (blocks[i - 1].rp, blocks[i - 1].seed + 2) if i > 0 else None
             d, dz = blocks[i].bwd(d, dz, below)
@@ -799,6 +827,12 @@ class MMFN(nn.Module):
                 return
         self.pretrained_from = None
 
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """nn.Module.load_state_dict + refresh of the bf16 weight shadow the bf16 tensor-core kernels read."""
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self.store.sync_shadow()
+        return out
+
     def _fan_in_of_bias(self, k):
         w = k[: -len("bias")] + "weight"
         return self.store.shapes[w][1] if w in self.store.shapes else 64
@@ -832,6 +866,8 @@ class MMFN(nn.Module):
         if self.training:
             self.seed += 1000
             self.store.flat_nbt.add_(self._nbt_step())     # BatchNorm.num_batches_tracked
+        if ops.BF16:                                       # a caller-side optimizer (torch.optim) moves only the fp32 masters
+            self.store.sync_shadow()
         return self.net.forward(image, lidar, lane, lane_num, radar, radar_adj, target_point, velocity,
                                 self.seed, self.training)
 

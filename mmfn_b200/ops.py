@@ -16,9 +16,33 @@ def _st():
     return torch.cuda.current_stream().cuda_stream
 
 
-def _chk(t, name="tensor"):
-    if t is not None and not (t.is_cuda and t.dtype == torch.float32):
-        raise MmfnError(f"{name}: expected a CUDA float32 tensor, got {t.device}/{t.dtype}")
+def _chk(t, name="tensor", bf16_ok=False):
+    if t is not None and not (t.is_cuda and (t.dtype == torch.float32 or (bf16_ok and t.dtype == torch.bfloat16))):
+        raise MmfnError(f"{name}: expected a CUDA float32{'/bfloat16' if bf16_ok else ''} tensor, got {t.device}/{t.dtype}")
+
+
+BF = torch.bfloat16
+
+
+def twin(t):
+    """The bf16 twin a producer kernel wrote next to an fp32 activation (attribute `.h`), or None.  In the bf16
+    configuration trunk activations exist twice: fp32 for the element-wise consumers (residual adds, BatchNorm backward,
+    pooling), bf16 for the convolution that reads them through TMA."""
+    return getattr(t, "h", None)
+
+
+def _with_twin(t, h):
+    if h is not None:
+        t.h = h
+    return t
+
+
+def to_bf16(x):
+    """fp32 -> bf16 copy (n % 4 == 0)."""
+    assert x.is_contiguous() and x.dtype == torch.float32 and x.numel() % 4 == 0
+    y = torch.empty(x.shape, device=x.device, dtype=BF)
+    lib().f32_to_bf16(_p(x), _p(y), x.numel(), _st())
+    return y
 
 
 TF32 = True   # large aligned GEMMs/convs run on the tcgen05 TF32 path; False = exact fp32 SIMT everywhere
@@ -45,14 +69,16 @@ def set_precision(mode):
 
 
 def _major(t):
-    """-> (is_mn_major, pitch) when `t` (.., rows, red) is TMA-addressable as a 2-D fp32 matrix, else None."""
+    """-> (is_mn_major, pitch) when `t` (.., rows, red) is TMA-addressable as a 2-D matrix (pitches are multiples of
+    16 bytes: 4 fp32 / 8 bf16 elements), else None."""
     rows, red = t.shape[-2], t.shape[-1]
     sr, sc = t.stride(-2), t.stride(-1)
+    al = 8 if t.dtype == BF else 4
     if t.data_ptr() % 16:
         return None
-    if sc == 1 and sr % 4 == 0 and sr >= red:
+    if sc == 1 and sr % al == 0 and sr >= red:
         return (0, sr)
-    if sr == 1 and sc % 4 == 0 and sc >= rows:
+    if sr == 1 and sc % al == 0 and sc >= rows:
         return (1, sc)
     return None
 
@@ -63,8 +89,15 @@ def gemm(A, B, C, *, bias=None, res=None, mask=None, alpha=1.0, act=0, accum=0,
 
     A and B may be arbitrary strided views; C needs unit column stride.  res/mask index like C.
     """
-    for t in (A, B, C, bias, res, mask):
+    for t in (A, B, C, mask):
+        _chk(t, bf16_ok=True)
+    for t in (bias, res):
         _chk(t)
+    bf_in = A.dtype == BF
+    if bf_in != (B.dtype == BF):
+        raise MmfnError("gemm: A and B must have the same element type")
+    if mask is not None and (mask.dtype == BF) != bf_in:
+        raise MmfnError("gemm: the mask tensor must have the operands' element type")
     nbd = C.dim() - 2
     assert A.dim() == C.dim() and B.dim() == C.dim() and 0 <= nbd <= 2
     M, K = A.shape[-2], A.shape[-1]
@@ -85,7 +118,36 @@ def gemm(A, B, C, *, bias=None, res=None, mask=None, alpha=1.0, act=0, accum=0,
         if t is not None:
             assert t.shape == C.shape and t.stride() == C.stride()
     nbt = nb[0] * nb[1]
-    lib().next_work = (2.0 * M * N * K * nbt, 4.0 * nbt * (M * K + N * K + M * N), M, N, K, nbt)
+    es = 2.0 if bf_in else 4.0
+    lib().next_work = (2.0 * M * N * K * nbt, nbt * (es * (M * K + N * K) + C.element_size() * M * N), M, N, K, nbt)
+    if bf_in:
+        # bf16 operands: tcgen05 kind::f16 only -- there is no other path for 2-byte tensors
+        am, bm = _major(A), _major(B)
+        ok = (am is not None and bm is not None and C.stride(-1) == 1 and all(x % 8 == 0 for x in a_b + b_b)
+              and all(x > 0 for i, x in enumerate(a_b + b_b) if ([nb[0], nb[1]] * 2)[i] > 1))
+        if not ok:
+            raise MmfnError(f"gemm(bf16): operands are not TMA-addressable (shapes {tuple(A.shape)} x {tuple(B.shape)}, "
+                            f"strides {A.stride()} / {B.stride()})")
+        if accum == 1:
+            accum = 2
+        linear = act == 0 and mask is None and drop_p == 0
+        if accum == 0 and linear and splitk == 1 and K >= 4096 and C.dtype != BF and ((M + 127) // 128) * ((N + 63) // 64) * nbt < 64:
+            C.zero_()
+            accum = 2
+        lib().gemm_bf16(_p(A), am[1], am[0], a_b[0], a_b[1], _p(B), bm[1], bm[0], b_b[0], b_b[1],
+                        _p(C), int(C.dtype == BF), C.stride(-2), c_b[0], c_b[1], M, N, K, nb[0], nb[1],
+                        _p(bias), _p(res), _p(mask), float(alpha), int(act), int(accum), float(drop_p),
+                        int(seed), int(splitk) if splitk > 1 else 0, _st())
+        return C
+    if C.dtype == BF:
+        # fp32 operands (TF32 multiply), bf16 result: attention-gradient products feeding a bf16 GEMM
+        am, bm = _major(A), _major(B)
+        if not (TF32 and am is not None and bm is not None and act == 0 and mask is None and drop_p == 0 and accum == 0
+                and bias is None and res is None and all(x % 4 == 0 for x in a_b + b_b)):
+            raise MmfnError("gemm: a bf16 result from fp32 operands needs the plain TF32 tensor-core path")
+        lib().gemm_tf32_out(_p(A), am[1], am[0], a_b[0], a_b[1], _p(B), bm[1], bm[0], b_b[0], b_b[1],
+                            _p(C), 1, C.stride(-2), c_b[0], c_b[1], M, N, K, nb[0], nb[1], float(alpha), _st())
+        return C
     if TF32 and M >= 64 and K >= 16 and M * N * K * nbt >= (1 << 18):
         am, bm = _major(A), _major(B)
         bs_ok = all(x % 4 == 0 for x in a_b + b_b)
@@ -125,9 +187,10 @@ def gemm(A, B, C, *, bias=None, res=None, mask=None, alpha=1.0, act=0, accum=0,
 
 
 def colsum_(x2d, out):
-    """out[n] += sum_m x2d[m, n]"""
+    """out[n] += sum_m x2d[m, n]  (x2d fp32 or bf16)"""
     assert x2d.stride(1) == 1
-    lib().colsum_f32(_p(x2d), x2d.stride(0), x2d.shape[0], x2d.shape[1], _p(out), _st())
+    fn = lib().colsum_bf16 if x2d.dtype == BF else lib().colsum_f32
+    fn(_p(x2d), x2d.stride(0), x2d.shape[0], x2d.shape[1], _p(out), _st())
 
 
 # ------------------------------------------------------------------ convolution (NHWC / KRSC)
@@ -145,6 +208,11 @@ def _tc_conv_ok(C, Co, Ho, Wo):
     return TF32 and C % 32 == 0 and Co % 32 == 0 and Ho >= 8 and Wo >= 8
 
 
+def bf16_conv_ok(C, Co, Ho, Wo):
+    """geometries the bf16 implicit-GEMM kernels take (every BasicBlock convolution of the three trunks)"""
+    return BF16 and C % 64 == 0 and Co % 64 == 0 and Ho >= 8 and Wo >= 8
+
+
 def conv2d_fwd(x, w_krsc, stride, pad, res=None):
     N, H, W, C = x.shape
     Co, R, S, C2 = w_krsc.shape
@@ -152,6 +220,10 @@ def conv2d_fwd(x, w_krsc, stride, pad, res=None):
     Ho, Wo = conv_out_hw(H, W, R, S, stride, pad)
     y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
     lib().next_work = _conv_work(N, H, W, C, Co, R, S, Ho, Wo)
+    if x.dtype == BF:
+        assert w_krsc.dtype == BF and C % 64 == 0 and Ho >= 8 and Wo >= 8, "bf16 convolution: unsupported geometry"
+        lib().conv2d_fwd_bf16(_p(x), _p(w_krsc), _p(y), _p(res), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, _st())
+        return y
     if _tc_conv_ok(C, Co, Ho, Wo):
         lib().conv2d_fwd_tf32(_p(x), _p(w_krsc), _p(y), _p(res), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, _st())
     else:
@@ -217,6 +289,10 @@ def conv2d_dgrad(dy, w_krsc, x_shape, stride, pad, res=None):
     _, Ho, Wo, _ = dy.shape
     dx = torch.empty(x_shape, device=dy.device, dtype=torch.float32)
     lib().next_work = _conv_work(N, H, W, C, Co, R, S, Ho, Wo)
+    if dy.dtype == BF:
+        assert w_krsc.dtype == BF and Co % 64 == 0, "bf16 data gradient: unsupported geometry"
+        lib().conv2d_dgrad_bf16(_p(dy), _p(w_krsc), _p(dx), _p(res), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, _st())
+        return dx
     if _tc_dgrad_ok(C, Co, H, W, stride, Ho, Wo):
         lib().conv2d_dgrad_tf32(_p(dy), _p(w_krsc), _p(dx), _p(res), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, _st())
         return dx
@@ -232,6 +308,10 @@ def conv2d_wgrad_(dy, x, dw_krsc, stride, pad):
     _, Ho, Wo, _ = dy.shape
     assert dw_krsc.is_contiguous() and dy.is_contiguous() and x.is_contiguous()
     lib().next_work = _conv_work(N, H, W, C, Co, R, S, Ho, Wo)
+    if dy.dtype == BF:
+        assert x.dtype == BF and dw_krsc.dtype == torch.float32
+        lib().conv2d_wgrad_bf16(_p(dy), _p(x), _p(dw_krsc), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, 0, _st())
+        return
     if _tc_conv_ok(C, Co, Ho, Wo):
         lib().conv2d_wgrad_tf32(_p(dy), _p(x), _p(dw_krsc), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, 0, _st())
     else:
@@ -265,65 +345,73 @@ def _bn_ws(dev):
     return _ws[key]
 
 
-def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5, res=None, relu=False):
+def bn_train_fwd(x, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5, res=None, relu=False, want16=False):
+    """want16: also write the bf16 twin of y (y.h) in the same pass."""
     C = x.shape[-1]
     assert C <= BN_WS_MAX_C
     M = x.numel() // C
     y = torch.empty_like(x)
+    y16 = torch.empty(x.shape, device=x.device, dtype=BF) if want16 else None
     mean = torch.empty(C, device=x.device, dtype=torch.float32)
     rstd = torch.empty(C, device=x.device, dtype=torch.float32)
     lib().bn_train_fwd(_p(x), _p(y), M, C, _p(gamma), _p(beta), _p(running_mean), _p(running_var),
-                       momentum, eps, _p(mean), _p(rstd), _p(res), int(relu), _p(_bn_ws(x.device)), _st())
+                       momentum, eps, _p(mean), _p(rstd), _p(res), int(relu), _p(_bn_ws(x.device)), _p(y16), _st())
     if M <= BN_SMALL_ROWS:
         lib().launches -= 1
-    return y, mean, rstd
+    return _with_twin(y, y16), mean, rstd
 
 
-def bn_eval_fwd(x, gamma, beta, running_mean, running_var, eps=1e-5, res=None, relu=False):
+def bn_eval_fwd(x, gamma, beta, running_mean, running_var, eps=1e-5, res=None, relu=False, want16=False):
     C = x.shape[-1]
     M = x.numel() // C
     y = torch.empty_like(x)
+    y16 = torch.empty(x.shape, device=x.device, dtype=BF) if want16 else None
     mean = torch.empty(C, device=x.device, dtype=torch.float32)
     rstd = torch.empty(C, device=x.device, dtype=torch.float32)
     lib().bn_eval_fwd(_p(x), _p(y), M, C, _p(gamma), _p(beta), _p(running_mean), _p(running_var), eps,
-                      _p(mean), _p(rstd), _p(res), int(relu), _st())
-    return y, mean, rstd
+                      _p(mean), _p(rstd), _p(res), int(relu), _p(y16), _st())
+    return _with_twin(y, y16), mean, rstd
 
 
-def bn_train_bwd(dy, x, yout, mean, rstd, gamma, dgamma, dbeta, want_dres=False):
+def bn_train_bwd(dy, x, yout, mean, rstd, gamma, dgamma, dbeta, want_dres=False, out_bf16=False):
+    """out_bf16: dx (the gradient of the convolution output) is written as bf16 -- it only feeds wgrad / dgrad MMAs."""
     C = x.shape[-1]
     assert C <= BN_WS_MAX_C
     M = x.numel() // C
-    dx = torch.empty_like(x)
+    dx = torch.empty(x.shape, device=x.device, dtype=BF if out_bf16 else torch.float32)
     dres = torch.empty_like(x) if want_dres else None
-    lib().bn_train_bwd(_p(dy), _p(x), _p(yout), _p(mean), _p(rstd), _p(gamma), M, C, _p(dx), _p(dres),
+    lib().bn_train_bwd(_p(dy), _p(x), _p(yout), _p(mean), _p(rstd), _p(gamma), M, C, _p(dx), int(out_bf16), _p(dres),
                        _p(dgamma), _p(dbeta), _p(_bn_ws(x.device)), _st())
     if M <= BN_SMALL_ROWS:
         lib().launches -= 1
     return dx, dres
 
 
-def layernorm_fwd(x2d, gamma, beta, act=0, eps=1e-5, out=None):
+def layernorm_fwd(x2d, gamma, beta, act=0, eps=1e-5, out=None, out_bf16=False):
     M, C = x2d.shape
     assert x2d.is_contiguous()
-    y = torch.empty_like(x2d) if out is None else out
+    if out is None:
+        out = torch.empty(x2d.shape, device=x2d.device, dtype=BF if out_bf16 else torch.float32)
+    y = out
     mean = torch.empty(M, device=x2d.device, dtype=torch.float32)
     rstd = torch.empty(M, device=x2d.device, dtype=torch.float32)
-    lib().layernorm_fwd(_p(x2d), _p(gamma), _p(beta), _p(y), _p(mean), _p(rstd), M, C, eps, act, _st())
+    lib().layernorm_fwd(_p(x2d), _p(gamma), _p(beta), _p(y), int(y.dtype == BF), _p(mean), _p(rstd), M, C, eps, act, _st())
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x2d, gamma, beta, mean, rstd, dgamma, dbeta, act=0, dres=None, parts=3, drop=None):
+def layernorm_bwd(dy, x2d, gamma, beta, mean, rstd, dgamma, dbeta, act=0, dres=None, parts=3, drop=None, drop_bf16=False):
     """parts bit 0: dx (returned), bit 1: dgamma/dbeta accumulation.  drop=(p, seed): also return
-    dx * dropout_mask(p, seed) -- the gradient entering the dropout of the next residual branch."""
+    dx * dropout_mask(p, seed) -- the gradient entering the dropout of the next residual branch (drop_bf16: as a bf16
+    tensor, written even for p == 0 because it is the operand of that branch's bf16 GEMMs)."""
     M, C = x2d.shape
     assert dy.is_contiguous() and x2d.is_contiguous()
     dx = torch.empty_like(x2d) if parts & 1 else None
     dxd, p, seed = None, 0.0, 0
-    if drop is not None and drop[0] > 0 and parts & 1:
-        dxd, p, seed = torch.empty_like(x2d), drop[0], drop[1]
+    if drop is not None and parts & 1 and (drop[0] > 0 or drop_bf16):
+        dxd = torch.empty(x2d.shape, device=x2d.device, dtype=BF if drop_bf16 else torch.float32)
+        p, seed = drop[0], drop[1]
     lib().layernorm_bwd(_p(dy), _p(x2d), _p(gamma), _p(beta), _p(mean), _p(rstd), _p(dres), _p(dx),
-                        _p(dgamma), _p(dbeta), M, C, act, parts, _p(dxd), float(p), int(seed), _st())
+                        _p(dgamma), _p(dbeta), M, C, act, parts, _p(dxd), int(drop_bf16 and dxd is not None), float(p), int(seed), _st())
     if drop is not None:
         return dx, (dxd if dxd is not None else dx)
     return dx
@@ -351,13 +439,14 @@ def transpose(x3d):
     return y
 
 
-def maxpool_fwd(x):
+def maxpool_fwd(x, want16=False):
     B, H, W, C = x.shape
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     y = torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.float32)
+    y16 = torch.empty((B, Ho, Wo, C), device=x.device, dtype=BF) if want16 else None
     idx = torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.uint8)
-    lib().maxpool3x3s2_fwd(_p(x), _p(y), idx.data_ptr(), B, H, W, C, _st())
-    return y, idx
+    lib().maxpool3x3s2_fwd(_p(x), _p(y), idx.data_ptr(), B, H, W, C, _p(y16), _st())
+    return _with_twin(y, y16), idx
 
 
 def maxpool_bwd(dy, idx, x_shape):
@@ -390,12 +479,14 @@ def tokens_bwd_(dtok, dfeats, shape, velocity, dpos, dvel_w, dvel_b, drop_p=0.0,
                      _p(dpos), _p(dvel_w), _p(dvel_b), drop_p, seed, _st())
 
 
-def upsample_add_fwd(feat, tok, m, align_corners=True):
-    """feat + bilinear upsample of tokens [m*64, (m+1)*64) viewed as an 8x8 map (F.interpolate semantics)."""
+def upsample_add_fwd(feat, tok, m, align_corners=True, want16=None):
+    """feat + bilinear upsample of tokens [m*64, (m+1)*64) viewed as an 8x8 map (F.interpolate semantics).
+    want16 (default: the bf16 configuration): also write the bf16 twin the next layer's first convolution reads."""
     B, H, W, C = feat.shape
     out = torch.empty_like(feat)
-    lib().upsample_add_fwd(_p(feat), _p(tok), _p(out), m, tok.shape[1], B, H, W, C, int(align_corners), _st())
-    return out
+    out16 = torch.empty(feat.shape, device=feat.device, dtype=BF) if (BF16 if want16 is None else want16) else None
+    lib().upsample_add_fwd(_p(feat), _p(tok), _p(out), m, tok.shape[1], B, H, W, C, int(align_corners), _p(out16), _st())
+    return _with_twin(out, out16)
 
 
 def upsample_add_bwd_(dA, dtok, m, align_corners=True):
@@ -421,16 +512,16 @@ def pool_sum_bwd(dfused, nmod):
 
 
 # ------------------------------------------------------------------ softmax family
-def attention_fwd(qkv, B, T, C, nh, drop_p=0.0, seed=0):
+def attention_fwd(qkv, B, T, C, nh, drop_p=0.0, seed=0, y_bf16=False):
     """Fused tcgen05 attention forward on the (B*T, 3C) [key|query|value] buffer.
-    -> y (B*T, C), P (B,nh,T,T) softmax probabilities, Pd (= P after dropout; P itself when drop_p == 0)."""
+    -> y (B*T, C) (bf16 when y_bf16), P (B,nh,T,T) softmax probabilities, Pd (= P after dropout; P itself when drop_p == 0)."""
     assert qkv.is_contiguous() and qkv.shape == (B * T, 3 * C)
-    y = torch.empty((B * T, C), device=qkv.device, dtype=torch.float32)
+    y = torch.empty((B * T, C), device=qkv.device, dtype=BF if y_bf16 else torch.float32)
     P = torch.empty((B, nh, T, T), device=qkv.device, dtype=torch.float32)
     Pd = torch.empty_like(P) if drop_p > 0 else None
     hs = C // nh
     lib().next_work = (4.0 * B * nh * T * T * hs, 4.0 * (B * T * 4 * C + B * nh * T * T), B, T, C, nh)
-    lib().attention_fwd_tf32(_p(qkv), _p(y), _p(P), _p(Pd), B, T, C, nh, float(drop_p), int(seed), _st())
+    lib().attention_fwd_tf32(_p(qkv), _p(y), int(y_bf16), _p(P), _p(Pd), B, T, C, nh, float(drop_p), int(seed), _st())
     return y, P, (Pd if Pd is not None else P)
 
 
@@ -626,16 +717,17 @@ def l1_loss(pred, gt, gscale=1.0, want_grad=True):
     return loss, dpred
 
 
-def adamw_step_(p, g, m, v, state, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, grad_scale=1.0):
+def adamw_step_(p, g, m, v, state, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, grad_scale=1.0, p16=None):
+    """p16: bf16 shadow of p, refreshed in the same pass (bf16 configuration)."""
     lib().adamw_step(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay,
-                     _p(state), grad_scale, _st())
+                     _p(state), grad_scale, _p(p16), _st())
 
 
 def adamw_advance_(state, beta1=0.9, beta2=0.999):
     lib().adamw_advance(_p(state), beta1, beta2, _st())
 
 
-def adamw_apply_(p, g, m, v, state, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, grad_scale=1.0):
+def adamw_apply_(p, g, m, v, state, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, grad_scale=1.0, p16=None):
     """AdamW on one parameter range; the step count in `state` must already be advanced (adamw_advance_)."""
     lib().adamw_apply(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay,
-                      _p(state), grad_scale, _st())
+                      _p(state), grad_scale, _p(p16), _st())

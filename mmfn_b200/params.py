@@ -176,6 +176,9 @@ class ParamStore:
         self.kinds = {k: kind for k, _, kind in self.spec}
         self.flat = torch.zeros(self.n_total, device=self.device, dtype=torch.float32)
         self.flat_grad = torch.zeros(self.n_total, device=self.device, dtype=torch.float32)
+        # bf16 shadow of the master weights (same offsets): the B operand of every bf16 tensor-core kernel
+        # (BASELINE configs[2]).  Refreshed by the AdamW kernel (engine) or sync_shadow() (after a state_dict load).
+        self.flat16 = torch.zeros(self.n_total, device=self.device, dtype=torch.bfloat16) if self.device.type == "cuda" else None
         bufs = [(k, s) for k, s, kind in self.spec if kind == "buf"]
         self.buf_offsets, boff = {}, 0
         for k, s in bufs:
@@ -217,6 +220,23 @@ class ParamStore:
 
     def g(self, key):
         return self._native(self.flat_grad, key)
+
+    def p16(self, key):
+        """bf16 shadow of p(key) (None on CPU stores)"""
+        return None if self.flat16 is None else self._native(self.flat16, key)
+
+    def fused16(self, keys):
+        if self.flat16 is None:
+            return None
+        off = self.offsets[keys[0]]
+        n = sum(_numel(self.shapes[k]) for k in keys)
+        sh = self.shapes[keys[0]]
+        return self.flat16[off: off + n].view(len(keys) * sh[0], *sh[1:])
+
+    def sync_shadow(self):
+        """flat16 <- bf16(flat): after load_state_dict / reset_parameters, or before an eager bf16 forward."""
+        from ._lib import lib
+        lib().f32_to_bf16(self.flat.data_ptr(), self.flat16.data_ptr(), self.n_total, torch.cuda.current_stream().cuda_stream)
 
     def fused(self, keys, grad=False):
         """One 2-D/1-D view over parameters that are adjacent in the flat buffer (e.g. key|query|value)."""

@@ -90,4 +90,6 @@ class TransFuser(MMFN):
         if self.training:
             self.seed += 1000
             self.store.flat_nbt.add_(self._nbt_step())
+        if ops.BF16:
+            self.store.sync_shadow()
         return self.net.forward(image, lidar, None, None, None, None, target_point, velocity, self.seed, self.training)

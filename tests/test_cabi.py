@@ -50,7 +50,20 @@ def test_argument_validation_without_gpu():
     with pytest.raises(MmfnError, match="head size"):
         lib().attention_bwd_dq_tf32(P, P, P, P, P, P, 1, 192, 96, 4, 0.0, 0, None)
     with pytest.raises(MmfnError, match="multiple of 4"):
-        lib().adamw_apply(P, P, P, P, 10, 1e-4, 0.9, 0.999, 1e-8, 0.01, P, 1.0, None)
+        lib().adamw_apply(P, P, P, P, 10, 1e-4, 0.9, 0.999, 1e-8, 0.01, P, 1.0, 0, None)
+    # bf16 tensor-core entry points (BASELINE configs[2]) and the size query
+    with pytest.raises(MmfnError, match="multiples of 16 bytes"):
+        lib().gemm_bf16(P, 12, 0, 0, 0, P, 64, 0, 0, 0, P, 0, 64, 0, 0, 128, 64, 64, 1, 1, 0, 0, 0, 1.0, 0, 0, 0.0, 0, 1, None)
+    with pytest.raises(MmfnError, match="cannot be accumulated"):
+        lib().gemm_bf16(P, 64, 0, 0, 0, P, 64, 0, 0, 0, P, 1, 64, 0, 0, 128, 64, 64, 1, 1, 0, 0, 0, 1.0, 0, 2, 0.0, 0, 1, None)
+    with pytest.raises(MmfnError, match="multiple of 64"):
+        lib().conv2d_fwd_bf16(P, P, P, 0, 2, 32, 32, 32, 64, 3, 3, 1, 1, 32, 32, None)
+    with pytest.raises(MmfnError, match="Co % 64"):
+        lib().conv2d_dgrad_bf16(P, P, P, 0, 2, 32, 32, 64, 96, 3, 3, 1, 1, 32, 32, None)
+    with pytest.raises(MmfnError, match="unknown op"):
+        lib().workspace_bytes(99, 0, 1, 1, 1, 1, P, )
+    with pytest.raises(MmfnError, match="multiple of 4"):
+        lib().f32_to_bf16(P, P, 6, None)
     with pytest.raises(MmfnError, match="bad args"):
         lib().copy2d_f32(P, 4, P, 8, 2, 6, 0, None)
 

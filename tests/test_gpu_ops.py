@@ -547,3 +547,161 @@ def test_block_gradients_with_residual_dropout_and_bound_rng():
             assert err < 1e-3, (name, err)
     finally:
         rng.copy_(old)
+
+
+# ------------------------------------------------------------------------------------------------ bf16 (BASELINE configs[2])
+# Tolerances: operands are rounded to bf16 (8-bit mantissa, relative step 2^-8 = 3.9e-3), products accumulate in fp32.
+# Against an fp32 torch reference evaluated ON THE SAME bf16-ROUNDED OPERANDS the only differences are accumulation order
+# and the rounding of a bf16 result: 2e-3 (fp32 result) / 8e-3 (bf16 result) relative to the tensor's max.
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K", [(384, 64, 64), (4096, 2048, 512), (768, 192, 64), (8192, 512, 2048), (200, 72, 40)])
+def test_gemm_bf16_all_majors_and_epilogues(M, N, K):
+    """mmfn_gemm_bf16: K-major / MN-major operands (forward, data-gradient and weight-gradient forms of nn.Linear),
+    fp32 and bf16 results, bias / ReLU / bf16 mask / dropout / residual epilogues, split-K accumulation."""
+    from mmfn_b200 import ops
+    A, Bm = torch.randn(M, K), torch.randn(N, K) * 0.1
+    A16, B16 = _bf(A).to(DEV), _bf(Bm).to(DEV)
+    Ar, Br = A16.float().cpu(), B16.float().cpu()
+    ref = Ar @ Br.t()
+    c = torch.empty(M, N, device=DEV)
+    ops.gemm(A16, B16, c)
+    close(c, ref, 2e-3)
+    c16 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A16, B16, c16)
+    close(c16, ref, 8e-3)
+    # MN-major operands: A stored (K, M), B stored (K, N)
+    At, Bt = A16.t().contiguous(), B16.t().contiguous()
+    for a_op, b_op in ((At.t(), B16), (A16, Bt.t()), (At.t(), Bt.t())):
+        c.zero_()
+        ops.gemm(a_op, b_op, c)
+        close(c, ref, 2e-3)
+    if N % 8 == 0:
+        bias, res = torch.randn(N), torch.randn(M, N)
+        mask = _bf(torch.randn(M, N)).to(DEV)
+        ops.gemm(A16, B16, c, bias=bias.to(DEV), res=res.to(DEV), act=1)
+        close(c, torch.relu(ref + bias) + res, 2e-3)
+        ops.gemm(A16, B16, c16, mask=mask)
+        close(c16, ref * (mask.float().cpu() > 0), 8e-3)
+        ops.gemm(A16, B16, c, bias=bias.to(DEV), drop_p=0.1, seed=9, res=res.to(DEV))
+        dm = ops.dropout(torch.ones(M, N, device=DEV), 0.1, 9).cpu()
+        close(c, (ref + bias) * dm + res, 2e-3)
+    # weight-gradient form: dW (N, K) += dY^T X with the reduction over M rows, both operands MN-major, atomics
+    dw = torch.zeros(N, K, device=DEV)
+    dy16 = _bf(torch.randn(M, N)).to(DEV)
+    ops.gemm(dy16.t(), A16.t(), dw, accum=1)
+    close(dw, dy16.float().cpu().t() @ Ar, 2e-3)
+
+
+@pytest.mark.parametrize("C,T", [(64, 192), (128, 192), (256, 192), (512, 256)])
+def test_bf16_result_from_tf32_attention_products(C, T):
+    """dV / dK / dQ written as bf16 head slices of dqkv by the TF32 batched GEMMs (mmfn_gemm_tf32_out)."""
+    from mmfn_b200 import ops
+    B, nh = 2, 4
+    hs = C // nh
+    qkv, dy, dS = torch.randn(B * T, 3 * C), torch.randn(B * T, C), torch.randn(B, nh, T, T)
+    heads = lambda t2d, i: t2d[:, i * C:(i + 1) * C].view(B, T, nh, hs).permute(0, 2, 1, 3)
+    k, q, v = (heads(qkv, i) for i in range(3))
+    P = torch.softmax(q @ k.transpose(-1, -2) / hs ** 0.5, -1)
+    dyh = dy.view(B, T, nh, hs).permute(0, 2, 1, 3)
+    g_qkv, g_dy, g_dS, g_P = qkv.to(DEV), dy.to(DEV), dS.to(DEV), P.to(DEV)
+    gk, gq, gv = (heads(g_qkv, i) for i in range(3))
+    dqkv = torch.zeros(B * T, 3 * C, device=DEV, dtype=torch.bfloat16)
+    dk, dq, dv = (heads(dqkv, i) for i in range(3))
+    ops.gemm(g_P.transpose(-1, -2), g_dy.view(B, T, nh, hs).permute(0, 2, 1, 3).transpose(-1, -2), dv)
+    ops.gemm(g_dS, gk.transpose(-1, -2), dq)
+    ops.gemm(g_dS.transpose(-1, -2), gq.transpose(-1, -2), dk)
+    close(dv, P.transpose(-1, -2) @ dyh, 8e-3)
+    close(dq, dS @ k, 8e-3)
+    close(dk, dS.transpose(-1, -2) @ q, 8e-3)
+
+
+BF_CONVS = [g for g in CONVS if g[2] % 64 == 0] + [(16, 16, 256, 256, 3, 1, 1), (3, 64, 64, 64, 3, 1, 1), (5, 8, 512, 512, 3, 1, 1)]
+
+
+@pytest.mark.parametrize("geom", BF_CONVS, ids=lambda g: f"N{g[0]}H{g[1]}C{g[2]}-{g[3]}R{g[4]}s{g[5]}")
+def test_conv_bf16_fwd_dgrad_wgrad(geom):
+    """mmfn_conv2d_{fwd,dgrad,wgrad}_bf16 on every BasicBlock geometry of the trunks against torch fp32 on the same
+    bf16-rounded operands."""
+    from mmfn_b200 import ops
+    N, H, C, Co, R, stride, pad = geom
+    x = _bf(torch.randn(N, C, H, H))
+    w = _bf(torch.randn(Co, C, R, R) * (2.0 / (C * R * R)) ** 0.5)
+    xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+    yr = F.conv2d(xr, wr, stride=stride, padding=pad)
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    wk = w.permute(0, 2, 3, 1).contiguous().to(DEV)
+    ops.BF16 = True
+    try:
+        y = ops.conv2d_fwd(xn, wk, stride, pad)
+        close(y.permute(0, 3, 1, 2), yr, 2e-3)
+        dy = _bf(torch.randn_like(yr))
+        yr.backward(dy.float())
+        dyn = dy.permute(0, 2, 3, 1).contiguous().to(DEV)
+        res = torch.randn(N, H, H, C, device=DEV)
+        dx = ops.conv2d_dgrad(dyn, wk, xn.shape, stride, pad, res=res)
+        close(dx.permute(0, 3, 1, 2), xr.grad + res.cpu().permute(0, 3, 1, 2), 2e-3)
+        dw = torch.zeros(Co, R, R, C, device=DEV)
+        ops.conv2d_wgrad_(dyn, xn, dw, stride, pad)
+        close(dw.permute(0, 3, 1, 2), wr.grad, 2e-3)
+    finally:
+        ops.BF16 = False
+
+
+def test_bf16_twins_and_typed_elementwise_outputs():
+    """Producers of MMA operands write bf16 next to / instead of fp32 in the same pass: BatchNorm apply (twin),
+    BatchNorm backward (bf16 dz), LayerNorm forward (bf16 out) and backward (bf16 dropout copy), max-pool and
+    upsample-add twins, bf16 column sums, the AdamW weight shadow and the fused attention's bf16 output."""
+    from mmfn_b200 import ops
+    rnd = lambda t: t.to(torch.bfloat16).float()
+    M, C = 4096, 128
+    x = torch.randn(M, C, device=DEV)
+    g, b = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    for rows in (M, 512):                                        # two-kernel and single-launch BatchNorm variants
+        xx = x[:rows].contiguous().view(rows // 64, 8, 8, C)
+        res = torch.randn_like(xx)
+        y, mean, rstd = ops.bn_train_fwd(xx, g, b, rm.clone(), rv.clone(), res=res, relu=True, want16=True)
+        y0, _, _ = ops.bn_train_fwd(xx, g, b, rm.clone(), rv.clone(), res=res, relu=True)
+        assert torch.equal(y, y0) and torch.equal(ops.twin(y).float(), rnd(y)) and ops.twin(y0) is None
+        dy = torch.randn_like(xx)
+        dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        dz, dres = ops.bn_train_bwd(dy, xx, y, mean, rstd, g, dg, db, want_dres=True)
+        dz16, dres16 = ops.bn_train_bwd(dy, xx, y, mean, rstd, g, dg.clone(), db.clone(), want_dres=True, out_bf16=True)
+        assert dz16.dtype == torch.bfloat16 and torch.equal(dz16.float(), rnd(dz)) and torch.equal(dres, dres16)
+    h, mean, rstd = ops.layernorm_fwd(x, g, b)
+    h16, _, _ = ops.layernorm_fwd(x, g, b, out_bf16=True)
+    assert torch.equal(h16.float(), rnd(h))
+    dy = torch.randn(M, C, device=DEV)
+    for p in (0.0, 0.1):
+        dx, dxd = ops.layernorm_bwd(dy, x, g, b, mean, rstd, None, None, parts=1, drop=(p, 3))
+        dx2, dxd16 = ops.layernorm_bwd(dy, x, g, b, mean, rstd, None, None, parts=1, drop=(p, 3), drop_bf16=True)
+        assert torch.equal(dx, dx2) and dxd16.dtype == torch.bfloat16 and torch.equal(dxd16.float(), rnd(dxd))
+    out = torch.zeros(C, device=DEV)
+    ops.colsum_(h16, out)
+    close(out, h16.float().sum(0), 1e-4)
+    img = torch.randn(2, 32, 32, 64, device=DEV)
+    mp, idx = ops.maxpool_fwd(img, want16=True)
+    assert torch.equal(ops.twin(mp).float(), rnd(mp))
+    tok = torch.randn(2, 192, 64, device=DEV)
+    up = ops.upsample_add_fwd(img, tok, 1, want16=True)
+    up0 = ops.upsample_add_fwd(img, tok, 1, want16=False)
+    assert torch.equal(up, up0) and torch.equal(ops.twin(up).float(), rnd(up))
+    n = 4096
+    p0, gr = torch.randn(n, device=DEV), torch.randn(n, device=DEV)
+    pa, pb = p0.clone(), p0.clone()
+    sh = torch.zeros(n, device=DEV, dtype=torch.bfloat16)
+    for _ in range(2):
+        ma, va, sa = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), torch.zeros(3, device=DEV)
+        ops.adamw_step_(pa, gr, ma, va, sa, 1e-2)
+        mb, vb, sb = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV), torch.zeros(3, device=DEV)
+        ops.adamw_step_(pb, gr, mb, vb, sb, 1e-2, p16=sh)
+    assert torch.equal(pa, pb) and torch.equal(sh.float(), rnd(pb))
+    assert torch.equal(ops.to_bf16(p0).float(), rnd(p0))
+    B, T, Cc, nh = 2, 192, 128, 4
+    qkv = torch.randn(B * T, 3 * Cc, device=DEV)
+    y, P, _ = ops.attention_fwd(qkv, B, T, Cc, nh)
+    y16, P2, _ = ops.attention_fwd(qkv, B, T, Cc, nh, y_bf16=True)
+    assert torch.equal(P, P2) and torch.equal(y16.float(), rnd(y))

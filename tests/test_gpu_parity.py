@@ -328,6 +328,73 @@ def test_loss_trajectory_tracks_oracle_over_20_steps(dev):
     assert abs(sum(mine[-2:]) - sum(orac[-2:])) < 0.05 * sum(orac[-2:])
 
 
+@pytest.mark.parametrize("B", [2, 32])
+def test_bf16_step_matches_oracle(dev, B):
+    """BASELINE configs[2] numerics (bf16 tensor-core operands for the BasicBlock convolutions and the transformer
+    linears, fp32 accumulate / statistics / residual stream / master weights) against the fp32 CPU oracle, at B=2 and
+    at the configuration's per-GPU batch 32.  The reference itself under torch.autocast(bfloat16) drifts from its fp32
+    output by 1.6e-3 mean / 4.9e-3 max waypoint L1: the bound asserted here is 5e-3, the
+    measured figures are written to gpurun_out/parity_bf16_b*.json (committed under profiles/)."""
+    from mmfn_b200 import ops
+    from mmfn_b200.engine import TrainEngine
+    try:
+        cfg, model, sd, b = _setup(dev, B, tf32=True)
+        ops.set_precision("bf16")
+        eng = TrainEngine(model, lr=1e-4)
+        db = {k: v.to(dev) for k, v in b.items()}
+        loss = eng.forward_backward(db).item()
+        torch.cuda.synchronize()
+        lidar_ref = torch.from_numpy(np.stack([bev_oracle.lidar_to_histogram_features(p[:, :3].numpy()) for p in b["points"]]))
+        inputs = (b["rgb_u8"].float(), lidar_ref, b["lane"], b["lane_num"], b["radar"], b["radar_adj"],
+                  b["target_point"], b["velocity"])
+        oloss, opred, ograds = mmfn_oracle.train_step({k: v.clone() for k, v in sd.items()}, cfg,
+                                                      dict(inputs=inputs, gt_waypoints=b["gt_waypoints"]))
+        wp_l1 = (eng.last_pred.cpu() - opred).abs().mean().item()
+        wp_max = (eng.last_pred.cpu() - opred).abs().max().item()
+        cosine, rel = _grad_stats(model, ograds)
+        rels = sorted(rel.values())
+        _report(f"parity_bf16_b{B}.json", dict(B=B, path="bf16", waypoint_l1=wp_l1, waypoint_max=wp_max, loss=loss,
+                                              oracle_loss=oloss.item(), grad_cosine=cosine, grad_rel_median=rels[len(rels) // 2],
+                                              grad_rel_p90=rels[int(0.9 * len(rels))], grad_rel_worst=rels[-1],
+                                              worst_key=max(rel, key=rel.get)))
+        assert np.isfinite(loss) and torch.isfinite(eng.last_pred).all()
+        assert wp_l1 < 5e-3, wp_l1
+        assert abs(loss - oloss.item()) < 5e-3, (loss, oloss.item())
+        assert cosine > 0.9, cosine
+    finally:
+        ops.set_precision("tf32")
+
+
+def test_bf16_graph_steps_keep_shadow_in_sync_and_train(dev):
+    """The captured bf16 step: AdamW refreshes the bf16 weight shadow in the same pass (no convert kernel in the graph),
+    load_state_dict refreshes it too, and the loss trajectory follows the TF32 path's on the same batch."""
+    from mmfn_b200 import ops
+    from mmfn_b200.engine import BatchStager, TrainEngine
+    B = 4
+    traj = {}
+    try:
+        for mode in ("tf32", "bf16"):
+            cfg, model, sd, b = _setup(dev, B, tf32=True)
+            ops.set_precision(mode)
+            eng = TrainEngine(model, lr=1e-4)
+            stager = BatchStager(b, dev)
+            db = stager.stage(b)
+            torch.cuda.synchronize()
+            eng.capture(db, warmup=1)
+            model.load_state_dict(sd)
+            traj[mode] = [eng.step_graph().item() for _ in range(6)]
+            torch.cuda.synchronize()
+            if mode == "bf16":
+                st = model.store
+                assert torch.equal(st.flat16[: st.n_active].float(), st.flat[: st.n_active].to(torch.bfloat16).float())
+        _report("trajectory_bf16_vs_tf32.json", traj)
+        for a, c in zip(traj["tf32"], traj["bf16"]):
+            assert abs(a - c) < 0.03 * max(1.0, abs(a)), traj
+        assert traj["bf16"][-1] < traj["bf16"][0]
+    finally:
+        ops.set_precision("tf32")
+
+
 def test_torchvision_resnet34_weights_load_into_both_trunks(dev):
     """ImageCNN = models.resnet34(pretrained=True) minus fc (model_rad.py:22-23): a torchvision state_dict must land in
     encoder.image_encoder.features.* and encoder.img_map_encoder.features.* (KRSC storage behind the (K,C,R,S) view)."""
