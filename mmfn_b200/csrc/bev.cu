@@ -1,12 +1,12 @@
 // LiDAR point cloud -> 2-channel BEV pillar histogram (reference:
 // team_code/mmfn_utils/datasets/dataloader.py:271-293 lidar_to_histogram_features).
 //
-// One CTA owns one (frame, channel, x-strip) slab of the 256x256 grid and keeps its
-// counters in shared memory as packed u16 fields; every CTA streams the frame's
-// points (L2-resident after the first CTA touches them), bins them with integer
-// arithmetic only, and finally writes its slab once, coalesced, already clamped
-// and scaled.  DRAM traffic is therefore the algorithmic N*stride*4 + 2*256*256*4
-// bytes per frame; there are no global atomics and no separate memset/finalize.
+// One CTA owns one (frame, x-strip) slab of the 256x256 grid -- BOTH height channels -- and keeps its
+// counters in shared memory as packed u16 fields; every CTA streams the frame's points ONCE (L2-resident
+// after the first CTA touches them; one pass serves both channels), bins them with integer arithmetic only,
+// and finally writes its two channel slabs once, coalesced, already clamped and scaled.  DRAM traffic is
+// therefore the algorithmic N*stride*4 + 2*256*256*4 bytes per frame; there are no global atomics and no
+// separate memset/finalize.  L2 read amplification = number of strips (chosen so that ~256 CTAs exist).
 #include "common.cuh"
 
 namespace {
@@ -18,18 +18,18 @@ __global__ void __launch_bounds__(1024)
 bev_scatter_kernel(const float* __restrict__ pts, int n_pts, int pt_stride,
                    float* __restrict__ out) {
   constexpr int ROWS = GRID / STRIPS;              // x-bins owned by this CTA
-  extern __shared__ uint32_t cnt[];                // ROWS*GRID/2 words: two u16 counters per word
+  constexpr int WORDS = ROWS * GRID / 2;           // words per channel: two u16 counters per word
+  extern __shared__ uint32_t cnt[];                // [2 channels][WORDS]
   const int strip = blockIdx.x % STRIPS;
-  const int chan = (blockIdx.x / STRIPS) & 1;
-  const int frame = blockIdx.x / (2 * STRIPS);
-  for (int i = threadIdx.x; i < ROWS * GRID / 2; i += blockDim.x) cnt[i] = 0u;
+  const int frame = blockIdx.x / STRIPS;
+  for (int i = threadIdx.x; i < 2 * WORDS; i += blockDim.x) cnt[i] = 0u;
   __syncthreads();
 
   const float* p = pts + (int64_t)frame * n_pts * pt_stride;
   const int x_lo = strip * ROWS;
-  // four points per thread are requested before the first is binned: the loop is latency-bound otherwise
+  // eight points per thread are requested before the first is binned: the loop is latency-bound otherwise
   // (one dependent L2 round trip per point and thread)
-  constexpr int U = 4;
+  constexpr int U = 8;
   for (int i0 = threadIdx.x; i0 < n_pts; i0 += U * blockDim.x) {
     float px[U], py[U], pz[U];
 #pragma unroll
@@ -49,33 +49,39 @@ bev_scatter_kernel(const float* __restrict__ pts, int n_pts, int pt_stride,
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const float x = px[u], y = py[u], z = pz[u];
-      // channel 0: z <= -2, channel 1: z > -2; NaN z matches neither.
-      bool in_chan = chan == 0 ? (z <= -2.0f) : (z > -2.0f);
       // closed range test also rejects NaN; x*8 / y*8 are exact in fp32.
-      if (!in_chan || !(x >= -16.0f && x <= 16.0f && y >= -24.0f && y <= 8.0f)) continue;
+      if (!(x >= -16.0f && x <= 16.0f && y >= -24.0f && y <= 8.0f)) continue;
+      // channel 0: z <= -2, channel 1: z > -2; NaN z matches neither.
+      const bool lo = z <= -2.0f, hi = z > -2.0f;
+      if (!(lo || hi)) continue;
       int ix = (int)floorf(x * 8.0f) + 128;
       int iy = (int)floorf(y * 8.0f) + 192;
       ix = min(ix, GRID - 1);                        // right-most edge is inclusive
       iy = min(iy, GRID - 1);
       ix -= x_lo;
       if (ix < 0 || ix >= ROWS) continue;
-      int bin = ix * GRID + iy;
-      uint32_t shift = (bin & 1) * 16;
+      const int bin = ix * GRID + iy;
+      uint32_t* word = cnt + (hi ? WORDS : 0) + (bin >> 1);
+      const uint32_t shift = (bin & 1) * 16;
       // counts are clamped at 5 downstream: stop incrementing once a field reached 5 so
       // a u16 field can never carry into its neighbour (<= 4 + blockDim.x increments).
-      if (((((volatile uint32_t*)cnt)[bin >> 1] >> shift) & 0xffffu) >= 5u) continue;
-      atomicAdd(&cnt[bin >> 1], 1u << shift);
+      if (((*(volatile uint32_t*)word >> shift) & 0xffffu) >= 5u) continue;
+      atomicAdd(word, 1u << shift);
     }
   }
   __syncthreads();
 
   // float32(k / 5.0) for k = 0..5
   const float lut[6] = {0.0f, 0.2f, 0.4f, 0.6f, 0.8f, 1.0f};
-  float* o = out + (((int64_t)frame * 2 + chan) * GRID + x_lo) * GRID;
-  for (int i = threadIdx.x; i < ROWS * GRID / 2; i += blockDim.x) {
-    uint32_t w = cnt[i];
-    uint32_t a = min(w & 0xffffu, 5u), b = min(w >> 16, 5u);
-    reinterpret_cast<float2*>(o)[i] = make_float2(lut[a], lut[b]);
+#pragma unroll
+  for (int chan = 0; chan < 2; ++chan) {
+    float* o = out + (((int64_t)frame * 2 + chan) * GRID + x_lo) * GRID;
+    const uint32_t* c = cnt + chan * WORDS;
+    for (int i = threadIdx.x; i < WORDS / 2; i += blockDim.x) {       // 4 bins = one 16-byte store per thread
+      const uint2 w = reinterpret_cast<const uint2*>(c)[i];
+      reinterpret_cast<float4*>(o)[i] = make_float4(lut[min(w.x & 0xffffu, 5u)], lut[min(w.x >> 16, 5u)],
+                                                    lut[min(w.y & 0xffffu, 5u)], lut[min(w.y >> 16, 5u)]);
+    }
   }
 }
 
@@ -89,11 +95,12 @@ MMFN_API int mmfn_bev_scatter(const float* pts, int frames, int n_pts, int pt_st
   MMFN_CHECK_ARG(pt_stride >= 3, "bev_scatter: pt_stride must be >= 3 (x,y,z,...)");
   MMFN_CHECK_ARG(pt_stride != 4 || ((uintptr_t)pts & 15) == 0, "bev_scatter: xyzi rows must be 16B aligned");
   if (frames == 0) return 0;
-  if (strips <= 0) {                                // enough CTAs to cover the SMs
-    strips = frames >= 74 ? 1 : frames >= 37 ? 2 : frames >= 16 ? 4 : frames >= 8 ? 8 : 16;
+  if (strips <= 0) {                                // ~256 CTAs (two 1024-thread CTAs per SM): 148 SMs covered, one wave
+    strips = frames >= 64 ? 4 : frames >= 24 ? 8 : 16;
   }
-  dim3 grid(frames * 2 * strips);
-  size_t smem = (size_t)(GRID / strips) * GRID / 2 * sizeof(uint32_t);
+  MMFN_CHECK_ARG(((uintptr_t)out & 15) == 0, "bev_scatter: out must be 16-byte aligned");
+  dim3 grid(frames * strips);
+  size_t smem = (size_t)2 * (GRID / strips) * GRID / 2 * sizeof(uint32_t);      // both channels of the strip
 #define MMFN_BEV_CASE(S)                                                                         \
   case S: {                                                                                      \
     cudaError_t ce = cudaFuncSetAttribute(bev_scatter_kernel<S>,                                 \
@@ -102,8 +109,9 @@ MMFN_API int mmfn_bev_scatter(const float* pts, int frames, int n_pts, int pt_st
     bev_scatter_kernel<S><<<grid, 1024, smem, stream>>>(pts, n_pts, pt_stride, out);             \
   } break;
   switch (strips) {
-    MMFN_BEV_CASE(1) MMFN_BEV_CASE(2) MMFN_BEV_CASE(4) MMFN_BEV_CASE(8) MMFN_BEV_CASE(16)
-    default: mmfn_set_error("bev_scatter: strips must be 1, 2, 4, 8 or 16"); return MMFN_BAD_ARG;
+    MMFN_BEV_CASE(2) MMFN_BEV_CASE(4) MMFN_BEV_CASE(8) MMFN_BEV_CASE(16)
+    case 1: mmfn_set_error("bev_scatter: strips = 1 needs 256 KB of shared memory (both channels of a frame); use 2, 4, 8 or 16"); return MMFN_BAD_ARG;
+    default: mmfn_set_error("bev_scatter: strips must be 2, 4, 8 or 16"); return MMFN_BAD_ARG;
   }
 #undef MMFN_BEV_CASE
   return mmfn_launch_status("bev_scatter");

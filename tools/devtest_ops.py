@@ -324,7 +324,7 @@ def t_bev():
     for n, s in [(32768, 4), (1000, 3), (0, 4)]:
         pts = np.stack([synth_points(1234 + i, n)[:, :s] for i in range(3)])
         ref = np.stack([lidar_to_histogram_features(p[:, :3]) for p in pts])
-        for strips in (0, 1, 2, 4, 8, 16):
+        for strips in (0, 2, 4, 8, 16):
             out = ops.bev_scatter(torch.from_numpy(np.ascontiguousarray(pts)).to(dev), strips)
             ok = bool((out.cpu().numpy() == ref).all())
             results.append((f"bev n{n} s{s} strips{strips}", ok, 0 if ok else 1, 1))
