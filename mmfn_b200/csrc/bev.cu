@@ -27,6 +27,11 @@ bev_scatter_kernel(const float* __restrict__ pts, int n_pts, int pt_stride,
 
   const float* p = pts + (int64_t)frame * n_pts * pt_stride;
   const int x_lo = strip * ROWS;
+  // Every CTA of a frame scans all of its points, so the common case -- a point outside this strip -- must cost two
+  // compares: ix = floor(x*8) + 128 lies in [x_lo, x_lo + ROWS) iff x lies in [(x_lo-128)/8, (x_lo+ROWS-128)/8) (x*8
+  // and the bounds are exact in fp32); the inclusive right edge x == 16 belongs to the last strip.  NaN fails both.
+  const float xs_lo = (float)(x_lo - 128) * 0.125f, xs_hi = (float)(x_lo + ROWS - 128) * 0.125f;
+  const bool last_strip = strip == STRIPS - 1;
   // eight points per thread are requested before the first is binned: the loop is latency-bound otherwise
   // (one dependent L2 round trip per point and thread)
   constexpr int U = 8;
@@ -49,8 +54,9 @@ bev_scatter_kernel(const float* __restrict__ pts, int n_pts, int pt_stride,
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const float x = px[u], y = py[u], z = pz[u];
+      if (!(x >= xs_lo && (x < xs_hi || (last_strip && x <= 16.0f)))) continue;
       // closed range test also rejects NaN; x*8 / y*8 are exact in fp32.
-      if (!(x >= -16.0f && x <= 16.0f && y >= -24.0f && y <= 8.0f)) continue;
+      if (!(y >= -24.0f && y <= 8.0f)) continue;
       // channel 0: z <= -2, channel 1: z > -2; NaN z matches neither.
       const bool lo = z <= -2.0f, hi = z > -2.0f;
       if (!(lo || hi)) continue;

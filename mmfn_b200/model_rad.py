@@ -318,9 +318,13 @@ class Block:
         # bf16 and multiply the bf16 weight shadow; the residual stream x, the qkv buffer and the attention core
         # (TF32 tcgen05 kernel, fp32 softmax) stay fp32
         bf = self.bf = ops.BF16 and C % 64 == 0
+        self.bfa = bf and ops.attention_bf16_ok(T, C, nh) and ops.BF16_ATTN    # attention core in bf16 too (attn_bf16.cu)
         h1 = self.ln1.fwd(x, out_bf16=bf)
-        qkv = self.qkv.fwd(h1)                                       # columns [key | query | value], fp32
-        if ops.attention_fwd_ok(T, C, nh):
+        qkv = self.qkv.fwd(h1, out_bf16=self.bfa)                    # columns [key | query | value]
+        if self.bfa:
+            # bf16 operands, K / V resident in shared memory, single-exp softmax; P / Pd saved as bf16
+            y, self.P, self.Pd, _ = ops.attention_fwd_bf16(qkv, B, T, C, nh, ap, seed)
+        elif ops.attention_fwd_ok(T, C, nh):
             # S = QK^T -> softmax -> dropout -> PV in ONE tcgen05 kernel; only P (and Pd) reach HBM
             y, self.P, self.Pd = ops.attention_fwd(qkv, B, T, C, nh, ap, seed, y_bf16=bf)
         else:
@@ -349,7 +353,7 @@ class Block:
         dh2 = self.fc1.bwd(da, masked=True)
         dx1, dzp = self.ln2.bwd(dh2, dres=dx2, drop=(self.rp, self.seed + 1), drop_bf16=bf)
         y_att = self.proj.x                                        # attention output saved by the projection
-        dy = self.proj.bwd(dzp)                                    # fp32: operand of the TF32 attention-gradient products
+        dy = self.proj.bwd(dzp, dx_bf16=self.bfa)                  # operand of the attention-gradient products (bf16 / TF32)
         qkv = self.qkv_out
         k, q, v = (self._heads(qkv, B, T, i * C) for i in range(3))
         dqkv = torch.empty(qkv.shape, device=qkv.device, dtype=torch.bfloat16 if bf else torch.float32)

@@ -57,6 +57,7 @@ FUSED_ATTN_BWD = False
 # stored in bf16 (tcgen05 kind::f16, fp32 accumulate); residual stream, statistics, gradients of parameters, master
 # weights and optimizer stay fp32.  Implies TF32 for everything the bf16 kernels do not cover (stems, VectorNet, GAT, head).
 BF16 = False
+BF16_ATTN = True      # bf16 configuration: attention core on the bf16 kernel (False: TF32 kernel on an fp32 qkv buffer)
 
 
 def set_precision(mode):
@@ -525,6 +526,25 @@ def attention_fwd(qkv, B, T, C, nh, drop_p=0.0, seed=0, y_bf16=False):
     return y, P, (Pd if Pd is not None else P)
 
 
+def attention_fwd_bf16(qkv, B, T, C, nh, drop_p=0.0, seed=0, save_probs=True):
+    """Fused bf16 attention forward (mmfn_attention_fwd_bf16) on the bf16 (B*T, 3C) [key|query|value] buffer.
+    -> y (B*T, C) bf16, P / Pd (B,nh,T,T) bf16 (None when save_probs is False), stats (B,nh,T,2) fp32 row max / sum."""
+    assert qkv.is_contiguous() and qkv.shape == (B * T, 3 * C) and qkv.dtype == BF
+    y = torch.empty((B * T, C), device=qkv.device, dtype=BF)
+    P = torch.empty((B, nh, T, T), device=qkv.device, dtype=BF) if save_probs else None
+    Pd = torch.empty_like(P) if (save_probs and drop_p > 0) else None
+    stats = torch.empty((B, nh, T, 2), device=qkv.device, dtype=torch.float32)
+    hs = C // nh
+    lib().next_work = (4.0 * B * nh * T * T * hs, 2.0 * (B * T * 4 * C) + (2.0 * B * nh * T * T * (2 if Pd is not None else 1) if save_probs else 0.0),
+                       B, T, C, nh)
+    lib().attention_fwd_bf16(_p(qkv), _p(y), _p(P), _p(Pd), _p(stats), B, T, C, nh, float(drop_p), int(seed), _st())
+    return y, P, (Pd if Pd is not None else P), stats
+
+
+def attention_bf16_ok(T, C, nh):
+    return BF16 and C % nh == 0 and (C // nh) in (16, 32, 64, 128) and T in (128, 192, 256)
+
+
 def attention_bwd_dq(qkv, dy, y, P, dqkv, B, T, C, nh, drop_p=0.0, seed=0):
     """Fused critical half of the attention backward: dPd = dY V^T (TMEM only), dS = softmax'(P, dPd o mask),
     dQ = dS K written into the query slice of dqkv.  Returns dS (B,nh,T,T) for the dK GEMM."""
@@ -551,10 +571,14 @@ def softmax_fwd(s, scale, drop_p=0.0, seed=0):
 
 
 def softmax_bwd(p, dpd, scale, drop_p=0.0, seed=0):
+    """p bf16 (saved by attention_fwd_bf16): dS is written as bf16 too (operand of the dQ / dK GEMMs)"""
     cols = p.shape[-1]
     rows = p.numel() // cols
     ds = torch.empty_like(p)
-    lib().softmax_bwd(_p(p), _p(dpd), _p(ds), rows, cols, scale, drop_p, seed, _st())
+    if p.dtype == BF:
+        lib().softmax_bwd_bf16(_p(p), _p(dpd), _p(ds), rows, cols, scale, drop_p, seed, _st())
+    else:
+        lib().softmax_bwd(_p(p), _p(dpd), _p(ds), rows, cols, scale, drop_p, seed, _st())
     return ds
 
 

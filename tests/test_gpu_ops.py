@@ -705,3 +705,42 @@ def test_bf16_twins_and_typed_elementwise_outputs():
     y, P, _ = ops.attention_fwd(qkv, B, T, Cc, nh)
     y16, P2, _ = ops.attention_fwd(qkv, B, T, Cc, nh, y_bf16=True)
     assert torch.equal(P, P2) and torch.equal(y16.float(), rnd(y))
+
+
+@pytest.mark.parametrize("C,T,B", [(64, 192, 3), (128, 192, 3), (256, 192, 2), (512, 256, 2), (512, 256, 32), (256, 128, 2)])
+def test_attention_fwd_bf16(C, T, B):
+    """mmfn_attention_fwd_bf16 (K / V resident, two softmax threads per row, one exp2 per score, packed-bf16 registers)
+    against fp32 torch on the same bf16-rounded q, k, v: probabilities, dropout consistency with the library's mask,
+    y == Pd V on the STORED bf16 probabilities, saved row statistics, and the stats-only mode (no P store)."""
+    from mmfn_b200 import ops
+    nh = 4
+    hs = C // nh
+    qkv16 = _bf(torch.randn(B * T, 3 * C)).to(DEV)
+    qkv = qkv16.float().cpu()
+    heads = lambda t2d, i: t2d[:, i * C:(i + 1) * C].view(B, T, nh, hs).permute(0, 2, 1, 3)
+    k, q, v = (heads(qkv, i) for i in range(3))
+    S = q @ k.transpose(-1, -2) / hs ** 0.5
+    Pr = torch.softmax(S, -1)
+    y, P, Pd, stats = ops.attention_fwd_bf16(qkv16, B, T, C, nh)
+    assert Pd is P and P.dtype == torch.bfloat16 and y.dtype == torch.bfloat16
+    close(P, Pr, 5e-3)
+    close(P.float().sum(-1), torch.ones(B, nh, T), 5e-3)
+    close(y, (Pr @ v).permute(0, 2, 1, 3).reshape(B * T, C), 1e-2)
+    close(y, (P.float().cpu() @ v).permute(0, 2, 1, 3).reshape(B * T, C), 5e-3)      # exactly what the MMA consumed
+    l2 = S * 1.4426950408889634
+    close(stats[..., 0], l2.max(-1)[0], 1e-4)
+    close(stats[..., 1], torch.exp2(l2 - l2.max(-1, keepdim=True)[0]).sum(-1), 2e-3)
+    p_drop, seed = 0.1, 4321
+    y2, P2, Pd2, _ = ops.attention_fwd_bf16(qkv16, B, T, C, nh, p_drop, seed)
+    mask = ops.dropout(torch.ones(B, nh, T, T, device=DEV), p_drop, seed)
+    assert torch.equal(P2, P)
+    assert torch.equal(Pd2, (P2.float() * mask).to(torch.bfloat16))
+    close(y2, (Pd2.float().cpu() @ v).permute(0, 2, 1, 3).reshape(B * T, C), 5e-3)
+    y3, P3, _, stats3 = ops.attention_fwd_bf16(qkv16, B, T, C, nh, p_drop, seed, save_probs=False)
+    assert P3 is None and torch.equal(y3, y2) and torch.equal(stats3, stats)
+    # backward pieces on the saved bf16 tensors: softmax backward -> bf16 dS
+    dP = torch.randn(B, nh, T, T, device=DEV)
+    dS = ops.softmax_bwd(P2, dP, hs ** -0.5, p_drop, seed)
+    g = dP.cpu() * mask.cpu()
+    Pf = P2.float().cpu()
+    close(dS, hs ** -0.5 * Pf * (g - (g * Pf).sum(-1, keepdim=True)), 8e-3)

@@ -335,8 +335,8 @@ def test_loss_trajectory_tracks_oracle_over_20_steps(dev):
     assert abs(sum(mine[-2:]) - sum(orac[-2:])) < 0.05 * sum(orac[-2:])
 
 
-@pytest.mark.parametrize("B", [2, 32])
-def test_bf16_step_matches_oracle(dev, B):
+@pytest.mark.parametrize("B,attn", [(2, "bf16"), (2, "tf32"), (32, "bf16")])
+def test_bf16_step_matches_oracle(dev, B, attn):
     """BASELINE configs[2] numerics (bf16 tensor-core operands for the BasicBlock convolutions and the transformer
     linears, fp32 accumulate / statistics / residual stream / master weights) against the fp32 CPU oracle, at B=2 and
     at the configuration's per-GPU batch 32.  The reference itself under torch.autocast(bfloat16) drifts from its fp32
@@ -347,6 +347,7 @@ def test_bf16_step_matches_oracle(dev, B):
     try:
         cfg, model, sd, b = _setup(dev, B, tf32=True)
         ops.set_precision("bf16")
+        ops.BF16_ATTN = attn == "bf16"             # attention core on the bf16 kernel, or the TF32 kernel on fp32 qkv
         eng = TrainEngine(model, lr=1e-4)
         db = {k: v.to(dev) for k, v in b.items()}
         loss = eng.forward_backward(db).item()
@@ -360,7 +361,7 @@ def test_bf16_step_matches_oracle(dev, B):
         wp_max = (eng.last_pred.cpu() - opred).abs().max().item()
         cosine, rel = _grad_stats(model, ograds)
         rels = sorted(rel.values())
-        _report(f"parity_bf16_b{B}.json", dict(B=B, path="bf16", waypoint_l1=wp_l1, waypoint_max=wp_max, loss=loss,
+        _report(f"parity_bf16_b{B}_attn{attn}.json", dict(B=B, path="bf16", attention_core=attn, waypoint_l1=wp_l1, waypoint_max=wp_max, loss=loss,
                                               oracle_loss=oloss.item(), grad_cosine=cosine, grad_rel_median=rels[len(rels) // 2],
                                               grad_rel_p90=rels[int(0.9 * len(rels))], grad_rel_worst=rels[-1],
                                               worst_key=max(rel, key=rel.get)))
@@ -370,6 +371,7 @@ def test_bf16_step_matches_oracle(dev, B):
         assert cosine > 0.9, cosine
     finally:
         ops.set_precision("tf32")
+        ops.BF16_ATTN = True
 
 
 def test_bf16_graph_steps_keep_shadow_in_sync_and_train(dev):
