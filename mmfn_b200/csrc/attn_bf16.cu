@@ -7,10 +7,12 @@
 //   * Q tile, ALL keys and ALL values of the (batch, head) are requested by TMA at kernel start and stay resident in
 //     shared memory (bf16: 32 + 64 + 64 KB at T = 256, hs = 128) -- the TF32 kernel streamed 32-key V boxes through a
 //     two-stage ring and exposed one L2 round trip per stage on its serial chain;
-//   * the softmax runs on 8 warps, TWO threads per query row (interleaved 32-key chunks), so every SM sub-partition
-//     holds two softmax warps and MUFU / TMEM-load latencies overlap;
-//   * exp2 is evaluated ONCE per score: the unnormalised probabilities are kept in registers as packed bf16 until the
-//     row sum is known, then normalised, written as the swizzled K-major A operand of the PV MMA (one 64-key tile per
+//   * the softmax runs on 16 warps, FOUR threads per query row (interleaved 32-key chunks), so every SM sub-partition
+//     holds four softmax warps and MUFU / TMEM-load / integer-hash latencies overlap (two threads per row measured
+//     21 us at B = 32: 34 % issue utilisation, stalled on latency -- profiles/r02_attn_ncu_v2.txt);
+//   * the scores are read from TMEM ONCE and exp2 is evaluated ONCE per score (chunk-local maxima, rescaled when the
+//     row maximum is known): the unnormalised probabilities wait in registers as packed bf16 until the row sum is
+//     known, then are normalised, written as the swizzled K-major A operand of the PV MMA (one 64-key tile per
 //     mbarrier, so the MMA of tile j overlaps the normalisation of tile j + 1) and -- only when the caller wants them
 //     for the unfused backward -- stored to HBM as bf16 straight from registers (64 contiguous bytes per thread);
 //   * the row statistics (max, sum) are saved so that a backward pass can recompute P instead of loading it.
@@ -19,7 +21,7 @@
 
 namespace {
 
-constexpr int AB_THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2-9 softmax / epilogue
+constexpr int AB_THREADS = 576;                 // warp 0 TMA, warp 1 MMA, warps 2-17 softmax / epilogue (4 threads per row)
 
 struct AttnBf16Params {
   int T, nh, C;
@@ -31,6 +33,7 @@ struct AttnBf16Params {
   __nv_bfloat16* P;                             // (B, nh, T, T) softmax probabilities, or null
   __nv_bfloat16* Pd;                            // after dropout (null when drop_p == 0 or P is null)
   float2* stats;                                // (B, nh, T) {row max of scale_log2 * s, row sum of exp2}, or null
+  unsigned long long* trace;                    // developer aid: %globaltimer stamps of CTA 0, or null
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -43,13 +46,26 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) {
 __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ float ex2(float x) {               // MUFU.EX2, flush-to-zero: one instruction
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+#define AT_STAMP(i) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.trace[i] = tc::gtimer(); } while (0)
 
+// Thread (row, part), part = 0..3, owns the 32-key chunks c = part, part + 4 of its query row (NCH = chunks per thread).
+// One pass over TMEM: per chunk a LOCAL maximum m_c, e = exp2(s - m_c) packed to bf16, local sum; the four threads of
+// a row exchange (max, sum) once through shared memory; chunk c is then rescaled by exp2(m_c - M) / total while it is
+// written out -- the scores are read from TMEM once (TMEM reads run at 64 B/clk per SM: a second pass over the
+// 128 x 256 fp32 tile costs 2048 cycles, as much as both MMAs of the tile).
 template <int HS, int NJB>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, AttnBf16Params p) {
   constexpr int NKB = (HS + 63) / 64;           // 64-element (128-byte) blocks of the head dimension
   constexpr int T = NJB * 64;
+  constexpr int NC = T / 32;                    // 32-key chunks of a row
+  constexpr int NCH = (NC + 3) / 4;             // chunks per thread
   constexpr int Q_BYTES = NKB * 16384, K_BYTES = NKB * T * 128, V_BYTES = NJB * NKB * 8192, P_BYTES = NJB * 16384;
   constexpr int NO = HS < 16 ? 16 : HS;         // N of the PV MMA
   extern __shared__ uint8_t smem_raw[];
@@ -68,11 +84,12 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  if (threadIdx.x == 0) AT_STAMP(0);
 
   if (warp == 0 && lane == 0) { tc::prefetch_tmap(&tmQ); tc::prefetch_tmap(&tmK); tc::prefetch_tmap(&tmV); }
   if (warp == 1 && lane == 0) {
     tc::mbar_init(qk_full, 1); tc::mbar_init(v_full, 1); tc::mbar_init(s_full, 1); tc::mbar_init(o_full, 1);
-    for (int j = 0; j < NJB; ++j) tc::mbar_init(&p_full[j], 256);
+    for (int j = 0; j < NJB; ++j) tc::mbar_init(&p_full[j], 256);     // two 32-key chunks x 128 rows per 64-key tile
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc(tmem_slot, p.tmem_cols);
@@ -81,6 +98,7 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   tc::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_o = tmem + (uint32_t)p.o_col;
+  if (threadIdx.x == 0) AT_STAMP(1);
 
   if (warp == 0) {
     if (tc::elect_one()) {                       // ===== TMA producer: everything up front =====
@@ -101,6 +119,7 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (tc::elect_one()) {                       // ===== MMA issuer =====
       tc::mbar_wait(qk_full, 0);
       tc::tc_fence_after();
+      AT_STAMP(2);
       const uint32_t idesc_s = tc::idesc_bf16(128, T, false, false);
       const uint32_t q0 = tc::smem_u32(sQ), k0 = tc::smem_u32(sK);
 #pragma unroll
@@ -118,102 +137,123 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       for (int jb = 0; jb < NJB; ++jb) {
         tc::mbar_wait(&p_full[jb], 0);
         tc::tc_fence_after();
+        if (jb == 0) AT_STAMP(6);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           tc::mma_bf16(tmem_o, tc::smem_desc_kmajor(p0 + jb * 16384 + k * 32),
                        tc::smem_desc_mnmajor16(v0 + jb * NKB * 8192 + k * 2048, 8192), idesc_o, (jb | k) ? 1u : 0u);
       }
       tc::mma_commit(o_full);
+      AT_STAMP(7);
     }
   } else {
-    // ===== softmax: two threads per query row; thread (row, half) owns the 32-key chunks 2*jb + half =====
+    // ===== softmax: four threads per query row =====
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;                       // warps 2-5: 0, warps 6-9: 1
+    const int part = (warp - 2) >> 2;                       // 0..3
     const int row = q * 32 + lane;                          // row inside the tile == TMEM lane
     const bool row_ok = m0 + row < T;
     const uint32_t t_row = tmem + ((uint32_t)(q * 32) << 16);
-    float* xmax = reinterpret_cast<float*>(sQ);             // [2][128]  (Q is dead once s_full fired)
-    float* xsum = xmax + 256;                               // [2][128]
+    float2* xch = reinterpret_cast<float2*>(sQ);            // [4][128] {max, sum}  (Q is dead once s_full fired)
     tc::mbar_wait(s_full, 0);
     tc::tc_fence_after();
-    // pass 1: row maximum
-    float mx = -INFINITY;
+    if (threadIdx.x == 64) AT_STAMP(3);
+    uint32_t e[NCH][16];
+    float mc[NCH];
+    float mt = -INFINITY, st = 0.f;                         // this thread's running (max, sum)
 #pragma unroll
-    for (int jb = 0; jb < NJB; ++jb) {
-      float v[32];
-      tc::tmem_ld32(t_row + (uint32_t)((2 * jb + half) * 32), v);
+    for (int i = 0; i < NCH; ++i) {
+      const int c = part + 4 * i;
+      mc[i] = -INFINITY;
+      if (c < NC) {                                         // warp-uniform
+        float v[32];
+        tc::tmem_ld32(t_row + (uint32_t)(c * 32), v);
+        float m = v[0];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, v[j]);
-    }
-    xmax[half * 128 + row] = mx;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    mx = fmaxf(mx, xmax[(half ^ 1) * 128 + row]) * p.scale_log2;
-    // pass 2: exp2 once per score, kept as packed bf16; row sum in fp32
-    uint32_t e[NJB][16];
-    float sum = 0.f;
+        for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+        m *= p.scale_log2;
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int jb = 0; jb < NJB; ++jb) {
-      float v[32];
-      tc::tmem_ld32(t_row + (uint32_t)((2 * jb + half) * 32), v);
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const float a = exp2f(v[j] * p.scale_log2 - mx), c = exp2f(v[j + 1] * p.scale_log2 - mx);
-        sum += a + c;
-        e[jb][j >> 1] = pack2(a, c);
+        for (int j = 0; j < 32; j += 2) {
+          const float a = ex2(fmaf(v[j], p.scale_log2, -m)), d = ex2(fmaf(v[j + 1], p.scale_log2, -m));
+          s0 += a; s1 += d;
+          e[i][j >> 1] = pack2(a, d);
+        }
+        mc[i] = m;
+        const float nm = fmaxf(mt, m);
+        st = st * ex2(mt - nm) + (s0 + s1) * ex2(m - nm);
+        mt = nm;
       }
     }
-    xsum[half * 128 + row] = sum;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    sum += xsum[(half ^ 1) * 128 + row];
-    const float inv = 1.0f / sum;
-    if (p.stats && half == 0 && row_ok) p.stats[((int64_t)b * p.nh + h) * T + m0 + row] = make_float2(mx, sum);
-    // pass 3: normalise, (store), dropout, A-operand tiles of the PV MMA
+    xch[part * 128 + row] = make_float2(mt, st);
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    float M = mt;
+#pragma unroll
+    for (int o = 1; o < 4; ++o) M = fmaxf(M, xch[((part + o) & 3) * 128 + row].x);
+    float total = 0.f;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const float2 t = xch[o * 128 + row];
+      total += t.y * ex2(t.x - M);
+    }
+    const float inv = 1.0f / total;
+    if (p.stats && part == 0 && row_ok) p.stats[((int64_t)b * p.nh + h) * T + m0 + row] = make_float2(M, total);
+    if (threadIdx.x == 64) AT_STAMP(4);
+    // normalise, (store), dropout, A-operand tiles of the PV MMA
     const int64_t prow = (((int64_t)b * p.nh + h) * T + (m0 + row)) * T;   // linear index of P[b,h,i,0] (dropout hash key)
     const bool drop = p.drop_p > 0.f;
+    const uint32_t thr = mmfn_drop_threshold(p.drop_p);
+    const float keep = 1.0f / (1.0f - p.drop_p);
+    const uint64_t dseed = mmfn_drop_seed(p.seed);
     const uint32_t tile_row = tc::smem_u32(sP) + row * 128;
 #pragma unroll
-    for (int jb = 0; jb < NJB; ++jb) {
-      const int col0 = (2 * jb + half) * 32;
-      uint32_t w[16];
+    for (int i = 0; i < NCH; ++i) {
+      const int c = part + 4 * i;
+      if (c < NC) {
+        const int col0 = c * 32, jb = c >> 1, hf = c & 1;
+        const float f = ex2(mc[i] - M) * inv;               // chunk-local maximum -> row maximum, and 1 / sum
+        uint32_t w[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float2 f = unpack2(e[jb][j]);
-        w[j] = pack2(f.x * inv, f.y * inv);
-      }
-      if (p.P && row_ok) {
-        uint4* dst = reinterpret_cast<uint4*>(p.P + prow + col0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-      }
-      if (drop) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {                   // one hash per four keys (prow % 4 == 0, col0 % 32 == 0)
-          float ds[4];
-          mmfn_dropout_scale4(p.drop_p, p.seed, (uint64_t)(prow + col0 + 2 * j), ds);
-          const float2 f0 = unpack2(w[j]), f1 = unpack2(w[j + 1]);
-          w[j] = pack2(f0.x * ds[0], f0.y * ds[1]);
-          w[j + 1] = pack2(f1.x * ds[2], f1.y * ds[3]);
+        for (int j = 0; j < 16; ++j) {
+          const float2 t = unpack2(e[i][j]);
+          w[j] = pack2(t.x * f, t.y * f);
         }
-        if (p.Pd && row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(p.Pd + prow + col0);
+        if (p.P && row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(p.P + prow + col0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) dst[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
         }
+        if (drop) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {                 // one hash per four keys (prow % 4 == 0, col0 % 32 == 0)
+            const uint64_t hsh = mmfn_hash64(dseed, (uint64_t)(prow + col0 + 2 * j) >> 2);
+            const uint32_t lo = (uint32_t)hsh, hi = (uint32_t)(hsh >> 32);
+            const float2 f0 = unpack2(w[j]), f1 = unpack2(w[j + 1]);
+            w[j] = pack2((lo & 0xFFFFu) >= thr ? f0.x * keep : 0.f, (lo >> 16) >= thr ? f0.y * keep : 0.f);
+            w[j + 1] = pack2((hi & 0xFFFFu) >= thr ? f1.x * keep : 0.f, (hi >> 16) >= thr ? f1.y * keep : 0.f);
+          }
+          if (p.Pd && row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(p.Pd + prow + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          }
+        }
+        // K-major SWIZZLE_128B tile: row r at r*128 bytes, 16-byte chunk k stored at position k ^ (r & 7);
+        // this thread owns chunks hf*4 .. hf*4 + 3 (its 32 keys) of the 64-key tile jb
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          sts128u(tile_row + jb * 16384 + ((((hf << 2) + k) ^ (row & 7)) << 4), w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+        tc::fence_async_smem();                             // generic-proxy writes -> visible to the UMMA
+        tc::mbar_arrive(&p_full[jb]);
       }
-      // K-major SWIZZLE_128B tile: row r at r*128 bytes, 16-byte chunk c stored at position c ^ (r & 7);
-      // this thread owns chunks half*4 .. half*4 + 3 (its 32 keys) of tile jb
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        sts128u(tile_row + jb * 16384 + ((((half << 2) + c) ^ (row & 7)) << 4), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-      tc::fence_async_smem();                               // generic-proxy writes -> visible to the UMMA
-      tc::mbar_arrive(&p_full[jb]);
     }
-    // O: TMEM -> bf16 -> HBM straight from registers (each thread owns one row: 32 columns = 64 contiguous bytes)
-    if (half == 0) {
-      tc::mbar_wait(o_full, 0);
-      tc::tc_fence_after();
+    if (threadIdx.x == 64) AT_STAMP(5);
+    // O: TMEM -> bf16 -> HBM straight from registers: the four threads of a row take the 32-column chunks d = part, ...
+    tc::mbar_wait(o_full, 0);
+    tc::tc_fence_after();
+    if (threadIdx.x == 64) AT_STAMP(8);
 #pragma unroll
-      for (int d = 0; d < (HS + 31) / 32; ++d) {
+    for (int d = 0; d < (HS + 31) / 32; ++d) {
+      if ((d & 3) == part) {                                // warp-uniform
         float v[32];
         tc::tmem_ld32(tmem_o + ((uint32_t)(q * 32) << 16) + (uint32_t)(d * 32), v);
         if (row_ok) {
@@ -226,6 +266,7 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         }
       }
     }
+    if (threadIdx.x == 64) AT_STAMP(9);
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -329,6 +370,7 @@ MMFN_API int mmfn_attention_fwd_bf16(const void* qkv, void* y, void* prob, void*
   p.P = static_cast<__nv_bfloat16*>(prob);
   p.Pd = (prob && drop_p > 0.f) ? static_cast<__nv_bfloat16*>(prob_drop) : nullptr;
   p.stats = reinterpret_cast<float2*>(stats);
+  p.trace = mmfn_tc_trace_ptr();
 #define MMFN_ATTN_CASE(HS_)                                                                     \
   case HS_:                                                                                     \
     if (T == 128) return launch_attn<HS_, 2>(tq, tk, tv, p, B, stream);                         \

@@ -91,7 +91,93 @@ bev_scatter_kernel(const float* __restrict__ pts, int n_pts, int pt_stride,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// One-visit variant.  The strip kernel above re-reads every point once per strip: with ~256 CTAs that is 8-16 passes
+// over the sweep through L2 (134 MB at 16 or 64 frames) and the kernel runs at the L2 read rate, ~25 us whatever the
+// frame count (profiles/r02_bev_bench_v2a.json).  Here every point is read ONCE: a CTA owns a chunk of one frame's
+// points and counts them with packed-u16 atomics (red.global) into a per-frame counter grid that lives in L2
+// (2 x 256 x 256 u16 = 256 KB per frame); the LAST CTA of a frame (arrival ticket) converts the counters to the
+// clamped / scaled fp32 grid, and re-zeroes counters and ticket, so the scratch is zero again for the next call
+// (no memset, one launch).  A u16 field cannot overflow: a frame has fewer than 65536 points per launch (checked).
+// ws layout: [frames][65536] u32 counters (two bins per word), then [frames] u32 tickets.
+constexpr int CHUNK_THREADS = 256, CHUNK_PTS = 4;       // 1024 points per CTA, all loads in flight
+
+__global__ void __launch_bounds__(CHUNK_THREADS)
+bev_scatter_onevisit_kernel(const float* __restrict__ pts, int n_pts, int pt_stride, int chunks,
+                            float* __restrict__ out, uint32_t* __restrict__ ws, int frames) {
+  __shared__ bool last_cta;
+  const int frame = blockIdx.x / chunks, chunk = blockIdx.x - frame * chunks;
+  uint32_t* cnt = ws + (int64_t)frame * (GRID * GRID);                 // [2 channels][65536 bins / 2]
+  uint32_t* ticket = ws + (int64_t)frames * (GRID * GRID) + frame;
+  const float* p = pts + (int64_t)frame * n_pts * pt_stride;
+  const int base = chunk * (CHUNK_THREADS * CHUNK_PTS);
+  float px[CHUNK_PTS], py[CHUNK_PTS], pz[CHUNK_PTS];
+#pragma unroll
+  for (int u = 0; u < CHUNK_PTS; ++u) {
+    const int i = base + u * CHUNK_THREADS + threadIdx.x;
+    px[u] = py[u] = pz[u] = __int_as_float(0x7fc00000);               // NaN: rejected below
+    if (i < n_pts) {
+      if (pt_stride == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+        px[u] = v.x; py[u] = v.y; pz[u] = v.z;
+      } else {
+        const float* q = p + (int64_t)i * pt_stride;
+        px[u] = __ldg(q); py[u] = __ldg(q + 1); pz[u] = __ldg(q + 2);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < CHUNK_PTS; ++u) {
+    const float x = px[u], y = py[u], z = pz[u];
+    // closed range test also rejects NaN; x*8 / y*8 are exact in fp32.
+    if (!(x >= -16.0f && x <= 16.0f && y >= -24.0f && y <= 8.0f)) continue;
+    const bool lo = z <= -2.0f, hi = z > -2.0f;                        // channel 0 / 1; NaN z matches neither
+    if (!(lo || hi)) continue;
+    int ix = (int)floorf(x * 8.0f) + 128;
+    int iy = (int)floorf(y * 8.0f) + 192;
+    ix = min(ix, GRID - 1);                                            // right-most edge is inclusive
+    iy = min(iy, GRID - 1);
+    const int bin = (hi ? GRID * GRID : 0) + ix * GRID + iy;
+    atomicAdd(cnt + (bin >> 1), 1u << ((bin & 1) * 16));               // result unused: compiles to red.global.add
+  }
+  // ---- last CTA of this frame: counters -> clamped, scaled fp32 grid; scratch back to zero
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last_cta = atomicAdd(ticket, 1u) == (uint32_t)chunks - 1;
+  __syncthreads();
+  if (!last_cta) return;
+  __threadfence();
+  const float lut[6] = {0.0f, 0.2f, 0.4f, 0.6f, 0.8f, 1.0f};           // float32(k / 5.0)
+  float4* o = reinterpret_cast<float4*>(out + (int64_t)frame * 2 * GRID * GRID);
+  uint4* c4 = reinterpret_cast<uint4*>(cnt);
+  for (int i = threadIdx.x; i < GRID * GRID / 4; i += CHUNK_THREADS) {  // 4 words = 8 bins = two 16-byte stores
+    const uint4 w = __ldcg(c4 + i);
+    c4[i] = make_uint4(0u, 0u, 0u, 0u);
+    o[2 * i] = make_float4(lut[min(w.x & 0xffffu, 5u)], lut[min(w.x >> 16, 5u)], lut[min(w.y & 0xffffu, 5u)], lut[min(w.y >> 16, 5u)]);
+    o[2 * i + 1] = make_float4(lut[min(w.z & 0xffffu, 5u)], lut[min(w.z >> 16, 5u)], lut[min(w.w & 0xffffu, 5u)], lut[min(w.w >> 16, 5u)]);
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
 }  // namespace
+
+// One-visit BEV scatter (see bev_scatter_onevisit_kernel).  ws: (frames * 65536 + frames) u32 of scratch that is
+// ZERO on entry (zero it once after allocation; every call leaves it zero again) -- mmfn_workspace_bytes(MMFN_WS_BEV).
+MMFN_API int mmfn_bev_scatter_ws(const float* pts, int frames, int n_pts, int pt_stride,
+                                 float* out, void* ws, cudaStream_t stream) {
+  MMFN_CHECK_ARG(out && ws && (pts || n_pts == 0 || frames == 0), "bev_scatter_ws: null pointer");
+  MMFN_CHECK_ARG(frames >= 0 && n_pts >= 0 && n_pts < 65536, "bev_scatter_ws: 0 <= n_pts < 65536 (u16 pillar counters)");
+  MMFN_CHECK_ARG(pt_stride >= 3, "bev_scatter_ws: pt_stride must be >= 3 (x,y,z,...)");
+  MMFN_CHECK_ARG(pt_stride != 4 || ((uintptr_t)pts & 15) == 0, "bev_scatter_ws: xyzi rows must be 16B aligned");
+  MMFN_CHECK_ARG((((uintptr_t)out | (uintptr_t)ws) & 15) == 0, "bev_scatter_ws: out / ws must be 16-byte aligned");
+  if (frames == 0) return 0;
+  const int per = CHUNK_THREADS * CHUNK_PTS;
+  const int chunks = n_pts > 0 ? (n_pts + per - 1) / per : 1;
+  MMFN_CHECK_ARG((int64_t)frames * chunks <= 0x7fffffff, "bev_scatter_ws: too many CTAs");
+  bev_scatter_onevisit_kernel<<<frames * chunks, CHUNK_THREADS, 0, stream>>>(pts, n_pts, pt_stride, chunks, out,
+                                                                             static_cast<uint32_t*>(ws), frames);
+  return mmfn_launch_status("bev_scatter_ws");
+}
 
 // pts: (frames, n_pts, pt_stride) f32 device; out: (frames, 2, 256, 256) f32 device.
 MMFN_API int mmfn_bev_scatter(const float* pts, int frames, int n_pts, int pt_stride,

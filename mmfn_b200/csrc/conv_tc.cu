@@ -13,6 +13,10 @@
 #include <type_traits>
 #include "tc_kernel.cuh"
 
+// norm.cu: stand-alone batch-statistics pass (used when a split-K launch cannot accumulate them in its epilogue)
+int mmfn_bn_stats_launch(const float* x, int64_t M, int C, float* mean, float* rstd, float* running_mean, float* running_var,
+                         float momentum, float eps, double* ws, cudaStream_t stream);
+
 namespace {
 
 struct ConvGeomTc {
@@ -158,6 +162,15 @@ struct ConvWgradOp {
   __device__ int col0() const { return ci0; }
   __device__ bool first_split() const { return true; }
 };
+
+// Train-mode BatchNorm statistics of the convolution output, accumulated by the epilogue (tc_kernel.cuh) when the
+// launch is not split over K; otherwise by a separate reduction pass (norm.cu).
+struct BnStatsArgs { double* ws; float* mean; float* rstd; float* rmean; float* rvar; float momentum, eps; };
+static inline void set_bn(tc::Epilogue& e, const BnStatsArgs* bn, long long rows) {
+  if (!bn) return;
+  e.bn_ws = bn->ws; e.bn_mean = bn->mean; e.bn_rstd = bn->rstd; e.bn_rmean = bn->rmean; e.bn_rvar = bn->rvar;
+  e.bn_eps = bn->eps; e.bn_momentum = bn->momentum; e.bn_rows = rows;
+}
 
 int check_tc_geom(const ConvGeomTc& g, const char* what, int EB = 32) {
   MMFN_CHECK_ARG(g.N > 0 && g.H > 0 && g.W > 0 && g.C > 0 && g.Co > 0 && g.R > 0 && g.S > 0 && g.stride > 0 && g.pad >= 0,
@@ -342,12 +355,14 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 2) tc::tmem_dealloc(tmem_base, TBN);
+  __shared__ bool bn_last;
+  tc::tc_bn_finalize(e, op.g.Co, &bn_last);
 }
 
 // x: conv input (fwd) or dy (dgrad), NHWC with Cin channels; out NHWC with Cout channels, same H x W (3x3, stride 1, pad 1)
 template <bool DGRAD, int EB = 32>
 int launch_conv3x3_patch(const void* x, const void* w, float* out, const float* res, int N, int H, int W, int Cin, int Cout,
-                         cudaStream_t stream, const char* what) {
+                         cudaStream_t stream, const char* what, const BnStatsArgs* bn = nullptr) {
   ConvGeomTc g{N, H, W, Cin, Cout, 3, 3, 1, 1, H, W};
   g.BW = PT_BW; g.BH = PT_BH; g.BI = 1;
   g.tiles_w = (W + PT_BW - 1) / PT_BW; g.tiles_h = (H + PT_BH - 1) / PT_BH; g.tiles_n = N;
@@ -364,6 +379,7 @@ int launch_conv3x3_patch(const void* x, const void* w, float* out, const float* 
     if (int rc = make_krsc_fwd_tmap(&tb, w, Cout, 3, 3, Cin, tbn, EB)) return rc;
   }
   tc::Epilogue e{out, nullptr, res, nullptr, 1.f, 0, 0, 0.f, 0, nullptr};
+  set_bn(e, bn, (long long)N * H * W);
   auto go = [&](auto tbn_tag, auto deep_tag) -> int {
     constexpr int TBN = decltype(tbn_tag)::value;
     constexpr bool DEEP = decltype(deep_tag)::value;
@@ -415,14 +431,15 @@ MMFN_API int mmfn_filter_krsc_to_crsk(const float* w, float* wt, int Co, int R, 
 template <int EB>
 static int conv_fwd_impl(const void* x, const void* w, float* y, const float* res,
                          int N, int H, int W, int C, int Co, int R, int S, int stride, int pad,
-                         int Ho, int Wo, cudaStream_t stream) {
+                         int Ho, int Wo, cudaStream_t stream, const BnStatsArgs* bn = nullptr) {
   const char* what = EB == 64 ? "conv_fwd_bf16" : "conv_fwd_tf32";
+  MMFN_CHECK_ARG(!bn || (bn->ws && bn->mean && bn->rstd && !res && Co % 64 == 0), "%s: batch statistics need ws / mean / rstd, no residual, Co %% 64 == 0", what);
   MMFN_CHECK_ARG(x && w && y, "%s: null pointer", what);
   ConvGeomTc g{N, H, W, C, Co, R, S, stride, pad, Ho, Wo};
   if (int rc = check_tc_geom(g, what, EB)) return rc;
   MMFN_CHECK_ARG((((uintptr_t)x | (uintptr_t)w) & 15) == 0, "%s: operands must be 16-byte aligned", what);
   MMFN_CHECK_ARG(Wo >= 8 && Ho >= 8, "%s: output must be at least 8x8", what);
-  if (patch_conv_ok(R, S, stride, pad, H, W)) return launch_conv3x3_patch<false, EB>(x, w, y, res, N, H, W, C, Co, stream, what);
+  if (patch_conv_ok(R, S, stride, pad, H, W)) return launch_conv3x3_patch<false, EB>(x, w, y, res, N, H, W, C, Co, stream, what, bn);
   // 128-pixel tile: 8 rows x 16 cols of one image, or two whole 8x8 maps
   g.BW = Wo >= 16 ? 16 : 8;
   g.BH = 8;
@@ -450,12 +467,18 @@ static int conv_fwd_impl(const void* x, const void* w, float* y, const float* re
     if (ce != cudaSuccess) { mmfn_set_error("%s: memset: %s", what, cudaGetErrorString(ce)); return (int)ce; }
   }
   tc::Epilogue e{y, nullptr, res, nullptr, 1.f, 0, splitk > 1 ? 2 : 0, 0.f, 0, mmfn_tc_trace_ptr()};
+  if (splitk == 1) set_bn(e, bn, (long long)N * Ho * Wo);       // partial sums of a K split are not the output: separate pass below
+  int rc;
   if (tbn == 64) {
     ConvFwdOp<64, false, EB> op{g, kb_per};
-    return tc::launch<ConvFwdOp<64, false, EB>, 64, 4>(ta, tb, op, e, dim3((Co + 63) / 64, ptiles, splitk), stream, what);
+    rc = tc::launch<ConvFwdOp<64, false, EB>, 64, 4>(ta, tb, op, e, dim3((Co + 63) / 64, ptiles, splitk), stream, what);
+  } else {
+    ConvFwdOp<128, false, EB> op{g, kb_per};
+    rc = tc::launch<ConvFwdOp<128, false, EB>, 128, 3>(ta, tb, op, e, dim3((Co + 127) / 128, ptiles, splitk), stream, what);
   }
-  ConvFwdOp<128, false, EB> op{g, kb_per};
-  return tc::launch<ConvFwdOp<128, false, EB>, 128, 3>(ta, tb, op, e, dim3((Co + 127) / 128, ptiles, splitk), stream, what);
+  if (rc == 0 && bn && splitk > 1)
+    rc = mmfn_bn_stats_launch(y, (int64_t)N * Ho * Wo, Co, bn->mean, bn->rstd, bn->rmean, bn->rvar, bn->momentum, bn->eps, bn->ws, stream);
+  return rc;
 }
 
 // Data gradient on the tensor cores straight from the KRSC filters w(Co,R,S,C) (no transposed / mirrored filter copy):
@@ -577,6 +600,27 @@ MMFN_API int mmfn_conv2d_fwd_tf32(const float* x, const float* w, float* y, cons
                                   int N, int H, int W, int C, int Co, int R, int S, int stride, int pad,
                                   int Ho, int Wo, cudaStream_t stream) {
   return conv_fwd_impl<32>(x, w, y, res, N, H, W, C, Co, R, S, stride, pad, Ho, Wo, stream);
+}
+
+// mmfn_conv2d_fwd_tf32 + the train-mode BatchNorm statistics of its output (conv -> BatchNorm2d of a torchvision
+// BasicBlock): per-channel mean / rstd (biased variance, eps) and the momentum update of running_mean / running_var
+// (unbiased variance; nullable) are produced by the convolution's own epilogue + last-CTA finalize -- no separate pass
+// over y.  ws: the BatchNorm scratch of mmfn_bn_train_fwd (zero on entry, left zero).  Follow with mmfn_bn_apply.
+MMFN_API int mmfn_conv2d_fwd_bn_tf32(const float* x, const float* w, float* y,
+                                     int N, int H, int W, int C, int Co, int R, int S, int stride, int pad, int Ho, int Wo,
+                                     double* ws, float* mean, float* rstd, float* running_mean, float* running_var,
+                                     float momentum, float eps, cudaStream_t stream) {
+  BnStatsArgs bn{ws, mean, rstd, running_mean, running_var, momentum, eps};
+  return conv_fwd_impl<32>(x, w, y, nullptr, N, H, W, C, Co, R, S, stride, pad, Ho, Wo, stream, &bn);
+}
+
+// bf16-operand variant of mmfn_conv2d_fwd_bn_tf32 (x and w BF16, y fp32).
+MMFN_API int mmfn_conv2d_fwd_bn_bf16(const void* x, const void* w, float* y,
+                                     int N, int H, int W, int C, int Co, int R, int S, int stride, int pad, int Ho, int Wo,
+                                     double* ws, float* mean, float* rstd, float* running_mean, float* running_var,
+                                     float momentum, float eps, cudaStream_t stream) {
+  BnStatsArgs bn{ws, mean, rstd, running_mean, running_var, momentum, eps};
+  return conv_fwd_impl<64>(x, w, y, nullptr, N, H, W, C, Co, R, S, stride, pad, Ho, Wo, stream, &bn);
 }
 
 // Data gradient of mmfn_conv2d_fwd_tf32 straight from the KRSC filters (see conv_dgrad_impl): stride 1 or 2.

@@ -518,6 +518,32 @@ MMFN_API int mmfn_bn_train_fwd(const float* x, float* y, int64_t M, int C,
 }
 
 // dx_bf16 != 0: dx is a BF16 tensor (the gradient of the convolution output only feeds the wgrad / dgrad MMAs).
+// Batch statistics only (internal: called by the convolution entry points when their epilogue could not accumulate
+// them, i.e. for split-K launches): fills mean / rstd, updates the running statistics, leaves ws zero.
+int mmfn_bn_stats_launch(const float* x, int64_t M, int C, float* mean, float* rstd, float* running_mean, float* running_var,
+                         float momentum, float eps, double* ws, cudaStream_t stream) {
+  int qpr; dim3 grid; int64_t rpb;
+  bn_colsum_grid(M, C, qpr, grid, rpb);
+  BnFinal fz = {mean, rstd, running_mean, running_var, eps, momentum, nullptr, nullptr, nullptr};
+  bn_colsum_kernel<false><<<grid, BN_THREADS, 0, stream>>>((const float4*)x, nullptr, nullptr, nullptr, nullptr, M, C / 4, qpr, rpb, ws, fz);
+  return mmfn_launch_status("bn_stats");
+}
+
+// y = (x - mean) * rstd * gamma + beta (+ res, ReLU) from statistics that already exist (published by the epilogue of
+// mmfn_conv2d_fwd_bn_*): the apply half of mmfn_bn_train_fwd.  y_bf16 (nullable): bf16 twin of y.
+MMFN_API int mmfn_bn_apply(const float* x, float* y, int64_t M, int C, const float* gamma, const float* beta,
+                           const float* mean, const float* rstd, const float* res, int relu, void* y_bf16,
+                           cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && y && gamma && beta && mean && rstd, "bn_apply: null pointer");
+  MMFN_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "bn_apply: C must be a positive multiple of 4");
+  MMFN_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)mean | (uintptr_t)rstd) & 15) == 0 &&
+                 ((uintptr_t)y_bf16 & 7) == 0, "bn_apply: alignment");
+  const int64_t n4 = M * C / 4;
+  bn_apply_kernel<<<grid_1d(n4, 256), 256, 0, stream>>>((const float4*)x, (float4*)y, n4, C / 4,
+      mean, rstd, (const float4*)gamma, (const float4*)beta, (const float4*)res, relu, (uint2*)y_bf16);
+  return mmfn_launch_status("bn_apply");
+}
+
 // yout: post-ReLU output of the forward (null when no ReLU followed). dres (nullable)
 // receives the ReLU-masked dy for the residual branch.  dgamma/dbeta are accumulated.  ws: as in mmfn_bn_train_fwd.
 MMFN_API int mmfn_bn_train_bwd(const float* dy, const float* x, const float* yout,

@@ -33,7 +33,16 @@ struct Epilogue {
   unsigned long long* trace;   // optional: 8 x %globaltimer stamps of CTA 0 (mmfn_tc_set_trace), else null
   __nv_bfloat16* C16;                // OUT16 instantiations: the result is written here as bf16 (same indexing as C)
   const __nv_bfloat16* mask16;       // like mask, for a bf16 tensor
+  // BatchNorm batch statistics of the OUTPUT (train-mode BN after a convolution), accumulated by the epilogue instead
+  // of a separate pass over the tensor: per-channel sum / sum of squares into the fp64 slot scratch of norm.cu; the
+  // last CTA folds the slots and publishes mean / rstd (+ running statistics).  Null ws = off.
+  double* bn_ws;
+  float* bn_mean; float* bn_rstd; float* bn_rmean; float* bn_rvar;
+  float bn_eps, bn_momentum;
+  long long bn_rows;                 // rows of the (rows, C) output = BatchNorm sample count per channel
 };
+
+constexpr int BN_SLOTS = 16;         // must match norm.cu
 
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
@@ -105,6 +114,7 @@ __device__ __forceinline__ void tc_epilogue(const Op& op, const Epilogue& e, uin
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
         const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+        float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};     // BatchNorm partials of this thread's 8 rows
         // per half (4 rows): the rows' offsets, then all residual / mask vectors, are requested before the first use --
         // four independent 16-byte loads in flight per operand instead of one per (dependent) loop iteration.
         // (All eight at once pushes the FULL variant past 102 registers = one CTA per SM.)
@@ -164,6 +174,12 @@ __device__ __forceinline__ void tc_epilogue(const Op& op, const Epilogue& e, uin
               }
             }
             if (res) { x[0] += r4[rr].x; x[1] += r4[rr].y; x[2] += r4[rr].z; x[3] += r4[rr].w; }
+            if constexpr (!FULL && !OUT16) {
+              if (e.bn_ws) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { st1[j] += x[j]; st2[j] += x[j] * x[j]; }
+              }
+            }
             if constexpr (OUT16) {          // bf16 result (tensors that only feed further MMAs): one 8-byte store
               const __nv_bfloat162 lo = __floats2bfloat162_rn(x[0], x[1]), hi = __floats2bfloat162_rn(x[2], x[3]);
               uint2 pk;
@@ -173,6 +189,22 @@ __device__ __forceinline__ void tc_epilogue(const Op& op, const Epilogue& e, uin
             } else if (e.accum == 0) *reinterpret_cast<float4*>(e.C + idx) = make_float4(x[0], x[1], x[2], x[3]);
             else  // split-K / weight-gradient accumulation: one 16-byte vector reduction instead of four scalar atomics
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(e.C + idx), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
+          }
+        }
+        if constexpr (!FULL && !OUT16) {
+          if (e.bn_ws) {
+            // the four row sub-groups of the warp (lanes l, l+8, l+16, l+24) hold the same 4 columns: fold them, then
+            // lanes 0-7 add this warp's 32 rows x 32 columns into the slot of this CTA (fp64 atomics, <= gridDim/16 per address)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              st1[j] += __shfl_xor_sync(0xffffffffu, st1[j], 8);  st2[j] += __shfl_xor_sync(0xffffffffu, st2[j], 8);
+              st1[j] += __shfl_xor_sync(0xffffffffu, st1[j], 16); st2[j] += __shfl_xor_sync(0xffffffffu, st2[j], 16);
+            }
+            if (lane < 8) {
+              double* slot = e.bn_ws + (int64_t)((blockIdx.x + blockIdx.y) % BN_SLOTS) * 2 * N;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { atomicAdd(slot + col + j, (double)st1[j]); atomicAdd(slot + N + col + j, (double)st2[j]); }
+            }
           }
         }
       } else {
@@ -202,6 +234,43 @@ __device__ __forceinline__ void tc_epilogue(const Op& op, const Epilogue& e, uin
       }
       if (threadIdx.x == 64 && c == 0) TC_STAMP(9);         // first chunk's stores issued
     }
+}
+
+// Last-CTA finalize of the epilogue-accumulated BatchNorm statistics (called by EVERY thread of the CTA after the
+// epilogue's stores were issued).  Same arithmetic as bn_colsum_kernel<false> of norm.cu: fp64 fold of the slots, biased
+// variance for the normalisation, unbiased for the running estimate; the scratch is left zero for the next call.
+__device__ __forceinline__ void tc_bn_finalize(const Epilogue& e, int C, bool* last_flag) {
+  if (!e.bn_ws) return;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(e.bn_ws + (int64_t)BN_SLOTS * 2 * C);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) *last_flag = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y * gridDim.z - 1;
+  __syncthreads();
+  if (!*last_flag) return;
+  __threadfence();
+  const double M = (double)e.bn_rows, invM = 1.0 / M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < BN_SLOTS; ++sl) {
+      double* slot = e.bn_ws + (int64_t)sl * 2 * C;
+      s1 += __ldcg(slot + c);
+      s2 += __ldcg(slot + C + c);
+      slot[c] = 0.0;
+      slot[C + c] = 0.0;
+    }
+    const double md = s1 * invM;
+    double var = s2 * invM - md * md;
+    if (var < 0.0) var = 0.0;
+    e.bn_mean[c] = (float)md;
+    e.bn_rstd[c] = (float)(1.0 / sqrt(var + (double)e.bn_eps));
+    if (e.bn_rmean) {
+      const double unbiased = e.bn_rows > 1 ? var * M / (M - 1.0) : var;
+      e.bn_rmean[c] = (float)((1.0 - e.bn_momentum) * e.bn_rmean[c] + e.bn_momentum * md);
+      e.bn_rvar[c] = (float)((1.0 - e.bn_momentum) * e.bn_rvar[c] + e.bn_momentum * unbiased);
+    }
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
 }
 
 // Op contract (all __device__):
@@ -289,6 +358,10 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, TBN);
   if (threadIdx.x == 64) TC_STAMP(6);                    // TMEM released
+  if constexpr (!FULL && !OUT16) {
+    __shared__ bool bn_last;
+    tc_bn_finalize(e, op.n_cols(), &bn_last);
+  }
 }
 
 template <class Op, int TBN, int STAGES, bool FULL, bool OUT16 = false>

@@ -142,6 +142,13 @@ class ConvBN:
         # its fp32 output z feeds the batch statistics; BatchNorm-apply writes y in fp32 AND its bf16 twin
         Ho, Wo = ops.conv_out_hw(x.shape[1], x.shape[2], self.w.shape[1], self.w.shape[2], self.stride, self.pad)
         self.bf = ops.twin(x) is not None and ops.bf16_conv_ok(x.shape[3], self.w.shape[0], Ho, Wo)
+        xin, win = (x.h, self.w16) if self.bf else (x, self.w)
+        if train and ops.conv_bn_fusable(xin, win, self.stride, self.pad):
+            # batch statistics from the convolution's own epilogue (+ last-CTA finalize): no reduction pass over z
+            self.z, self.mean, self.rstd = ops.conv2d_fwd_bn(xin, win, self.stride, self.pad, self.rm, self.rv)
+            self.y = ops.bn_apply(self.z, self.gam, self.bet, self.mean, self.rstd, res=res, relu=relu,
+                                  want16=ops.BF16 and not no_twin)
+            return self.y
         if self.bf:
             self.z = ops.conv2d_fwd(x.h, self.w16, self.stride, self.pad)
         elif ops.stem_uses_im2col(x, self.w):

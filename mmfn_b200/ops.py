@@ -233,6 +233,45 @@ def conv2d_fwd(x, w_krsc, stride, pad, res=None):
     return y
 
 
+FUSE_BN_STATS = True    # train-mode BatchNorm statistics from the convolution epilogue (no separate reduction pass over z)
+
+
+def conv_bn_fusable(x, w_krsc, stride, pad):
+    """conv -> train-mode BatchNorm pairs whose batch statistics the tensor-core convolution accumulates itself: feature
+    maps above the single-launch BatchNorm threshold on the TF32 / bf16 implicit-GEMM path."""
+    N, H, W, C = x.shape
+    Co, R, S, _ = w_krsc.shape
+    Ho, Wo = conv_out_hw(H, W, R, S, stride, pad)
+    tc_ok = (x.dtype == BF and C % 64 == 0) or (x.dtype == torch.float32 and _tc_conv_ok(C, Co, Ho, Wo))
+    return FUSE_BN_STATS and tc_ok and Co % 64 == 0 and Co <= BN_WS_MAX_C and Ho >= 8 and Wo >= 8 and N * Ho * Wo > BN_SMALL_ROWS
+
+
+def conv2d_fwd_bn(x, w_krsc, stride, pad, running_mean, running_var, momentum=0.1, eps=1e-5):
+    """z = conv(x, w) plus the batch statistics of z (mean, rstd; running statistics updated) from the same launch.
+    -> (z, mean, rstd); follow with bn_apply."""
+    N, H, W, C = x.shape
+    Co, R, S, C2 = w_krsc.shape
+    assert C2 == C and x.is_contiguous() and w_krsc.is_contiguous() and x.dtype == w_krsc.dtype
+    Ho, Wo = conv_out_hw(H, W, R, S, stride, pad)
+    z = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
+    mean = torch.empty(Co, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(Co, device=x.device, dtype=torch.float32)
+    lib().next_work = _conv_work(N, H, W, C, Co, R, S, Ho, Wo)
+    fn = lib().conv2d_fwd_bn_bf16 if x.dtype == BF else lib().conv2d_fwd_bn_tf32
+    fn(_p(x), _p(w_krsc), _p(z), N, H, W, C, Co, R, S, stride, pad, Ho, Wo, _p(_bn_ws(x.device)), _p(mean), _p(rstd),
+       _p(running_mean), _p(running_var), momentum, eps, _st())
+    return z, mean, rstd
+
+
+def bn_apply(x, gamma, beta, mean, rstd, res=None, relu=False, want16=False):
+    C = x.shape[-1]
+    M = x.numel() // C
+    y = torch.empty_like(x)
+    y16 = torch.empty(x.shape, device=x.device, dtype=BF) if want16 else None
+    lib().bn_apply(_p(x), _p(y), M, C, _p(gamma), _p(beta), _p(mean), _p(rstd), _p(res), int(relu), _p(y16), _st())
+    return _with_twin(y, y16)
+
+
 def stem_uses_im2col(x, w_krsc):
     """The two stems (7x7/2 on 3 / 2 channels) cannot use the implicit-GEMM tensor-core path (channels % 32); with
     TF32 enabled they run as im2col + ONE dense tensor-core GEMM instead of the SIMT gather-GEMM."""
@@ -326,7 +365,7 @@ BN_SMALL_ROWS = 2048     # norm.cu: feature maps with at most this many rows tak
 
 
 F32, TF32_T, BF16_T = 0, 1, 2                     # MMFN_F32 / MMFN_TF32 / MMFN_BF16 of the header
-WS_BN, WS_STEM_IM2COL, WS_STEM_FILTER, WS_ATTN_PROB, WS_GRU_SAVED = range(5)
+WS_BN, WS_STEM_IM2COL, WS_STEM_FILTER, WS_ATTN_PROB, WS_GRU_SAVED, WS_BEV = range(6)
 
 
 def workspace_bytes(op, dtype=F32, a=0, b=0, c=0, d=0):
@@ -702,12 +741,25 @@ def radar_logsoftmax_bwd(dy, y):
     return dv
 
 
+_bev_ws = {}
+
+
 def bev_scatter(points, strips=0):
-    """points (frames, n, 3|4) f32 -> (frames, 2, 256, 256) f32, reference layout [c, xbin, ybin]."""
+    """points (frames, n, 3|4) f32 -> (frames, 2, 256, 256) f32, reference layout [c, xbin, ybin].
+    strips == 0 (default): the one-visit kernel (every point read once, packed-u16 counters in an L2-resident scratch
+    that the kernel leaves zero; one scratch per (stream, frame count)).  strips in (2, 4, 8, 16): the shared-memory
+    strip kernel (no scratch, every CTA scans the whole frame)."""
     _chk(points, "points")
     assert points.dim() == 3 and points.is_contiguous()
     F, n, s = points.shape
     out = torch.empty((F, 2, 256, 256), device=points.device, dtype=torch.float32)
+    if strips == 0 and n < 65536 and F > 0:
+        key = (points.device, torch.cuda.current_stream().cuda_stream, F)
+        ws = _bev_ws.get(key)
+        if ws is None:
+            ws = _bev_ws[key] = torch.zeros(workspace_bytes(WS_BEV, F32, F) // 4, device=points.device, dtype=torch.int32)
+        lib().bev_scatter_ws(_p(points), F, n, s, _p(out), _p(ws), _st())
+        return out
     lib().bev_scatter(_p(points), F, n, s, _p(out), strips, _st())
     return out
 

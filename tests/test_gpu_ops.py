@@ -744,3 +744,40 @@ def test_attention_fwd_bf16(C, T, B):
     g = dP.cpu() * mask.cpu()
     Pf = P2.float().cpu()
     close(dS, hs ** -0.5 * Pf * (g - (g * Pf).sum(-1, keepdim=True)), 8e-3)
+
+
+@pytest.mark.parametrize("bf16", [False, True], ids=["tf32", "bf16"])
+@pytest.mark.parametrize("geom", [(4, 64, 64, 64, 3, 1, 1), (4, 64, 64, 128, 3, 2, 1), (4, 64, 64, 128, 1, 2, 0), (8, 32, 128, 128, 3, 1, 1),
+                                  (16, 32, 128, 256, 3, 2, 1), (16, 16, 256, 256, 3, 1, 1), (32, 16, 256, 512, 3, 2, 1)],
+                         ids=lambda g: f"N{g[0]}H{g[1]}C{g[2]}-{g[3]}R{g[4]}s{g[5]}")
+def test_conv_epilogue_batchnorm_statistics(geom, bf16):
+    """mmfn_conv2d_fwd_bn_*: per-channel mean / rstd / running statistics accumulated by the convolution epilogue
+    (halo-reuse 3x3 kernel, generic implicit GEMM, and the split-K fallback to a separate pass) equal those of the
+    stand-alone reduction over the same convolution output; bn_apply == the apply half of bn_train_fwd."""
+    from mmfn_b200 import ops
+    N, H, C, Co, R, stride, pad = geom
+    x = torch.randn(N, H, H, C, device=DEV) * 2 + 0.5
+    w = torch.randn(Co, R, R, C, device=DEV) * (2.0 / (C * R * R)) ** 0.5
+    if bf16:
+        x, w = x.to(torch.bfloat16), w.to(torch.bfloat16)
+    g, b = torch.rand(Co, device=DEV) + 0.5, torch.randn(Co, device=DEV)
+    rm0, rv0 = torch.randn(Co, device=DEV), torch.rand(Co, device=DEV) + 0.5
+    ops.BF16 = bf16
+    try:
+        assert ops.conv_bn_fusable(x, w, stride, pad)
+        z0 = ops.conv2d_fwd(x, w, stride, pad)
+        rm_a, rv_a = rm0.clone(), rv0.clone()
+        res = torch.randn_like(z0)
+        y0, mean0, rstd0 = ops.bn_train_fwd(z0, g, b, rm_a, rv_a, res=res, relu=True, want16=bf16)
+        rm_b, rv_b = rm0.clone(), rv0.clone()
+        z1, mean1, rstd1 = ops.conv2d_fwd_bn(x, w, stride, pad, rm_b, rv_b)
+        y1 = ops.bn_apply(z1, g, b, mean1, rstd1, res=res, relu=True, want16=bf16)
+        z2, mean2, rstd2 = ops.conv2d_fwd_bn(x, w, stride, pad, rm_b.clone(), rv_b.clone())       # scratch left zero: repeatable
+        for got, ref in ((mean1, mean0), (rstd1, rstd0), (rm_b, rm_a), (rv_b, rv_a), (mean2, mean0), (rstd2, rstd0)):
+            assert torch.allclose(got, ref, rtol=2e-5, atol=2e-6), (got - ref).abs().max().item()
+        close(z1, z0, 1e-6 if z1.shape[1] * z1.shape[2] * N > 0 else 0)     # same kernel, atomics order only for split-K
+        close(y1, y0, 2e-5)
+        if bf16:
+            assert ops.twin(y1).dtype == torch.bfloat16 and torch.equal(ops.twin(y1).float(), y1.to(torch.bfloat16).float())
+    finally:
+        ops.BF16 = False

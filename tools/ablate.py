@@ -18,6 +18,7 @@ from mmfn_b200.engine import BatchStager, TrainEngine     # noqa: E402
 from mmfn_b200.model_rad import MMFN, _Aux                # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+ops.set_precision(sys.argv[2] if len(sys.argv) > 2 else "tf32")      # "tf32" (configs[1]) or "bf16" (configs[2])
 dev = torch.device("cuda:0")
 model = MMFN(GlobalConfig(), dev)
 eng = TrainEngine(model)

@@ -29,6 +29,25 @@ def main():
             ops.attention_fwd(qkv.float(), B, T, C, nh, 0.1, 7)
         torch.cuda.synchronize()
         return
+    if "--trace" in sys.argv:
+        # %globaltimer stamps of CTA 0 (ns): 0 entry, 1 setup done, 2 Q/K landed, 3 S visible to the softmax, 4 row statistics
+        # exchanged, 5 all P tiles written, 6 first PV MMA issued, 7 all MMAs issued, 8 O visible, 9 y stored
+        from mmfn_b200._lib import lib
+        res = {}
+        for B, T, C in ((16, 256, 512), (32, 256, 512), (32, 192, 256), (32, 192, 64)):
+            qkv = torch.randn(B * T, 3 * C, device=dev).to(torch.bfloat16)
+            buf = torch.zeros(16, dtype=torch.int64, device=dev)
+            for _ in range(3):
+                ops.attention_fwd_bf16(qkv, B, T, C, 4, 0.1, 7, save_probs=False)
+            torch.cuda.synchronize()
+            lib().tc_set_trace(buf.data_ptr())
+            ops.attention_fwd_bf16(qkv, B, T, C, 4, 0.1, 7, save_probs=False)
+            torch.cuda.synchronize()
+            lib().tc_set_trace(0)
+            t = buf.cpu().tolist()
+            res[f"B{B}_T{T}_C{C}"] = [x - t[0] for x in t[:10]]
+        print(json.dumps(res))
+        return
     peaks = measured_peaks()
     tf32_peak = measure_matmul_peak(dev, True)[1]
     out = {"bf16_peak_tflops": peaks["tf_sust"], "tf32_peak_tflops": tf32_peak, "rows": []}
