@@ -157,7 +157,7 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tc::mbar_wait(s_full, 0);
     tc::tc_fence_after();
     if (threadIdx.x == 64) AT_STAMP(3);
-    uint32_t e[NCH][16];
+    float e[NCH][32];                                       // exp2(s - chunk maximum), fp32 until the row sum is known
     float mc[NCH];
     float mt = -INFINITY, st = 0.f;                         // this thread's running (max, sum)
 #pragma unroll
@@ -165,18 +165,17 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const int c = part + 4 * i;
       mc[i] = -INFINITY;
       if (c < NC) {                                         // warp-uniform
-        float v[32];
-        tc::tmem_ld32(t_row + (uint32_t)(c * 32), v);
-        float m = v[0];
+        tc::tmem_ld32(t_row + (uint32_t)(c * 32), e[i]);
+        float m = e[i][0];
 #pragma unroll
-        for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+        for (int j = 1; j < 32; ++j) m = fmaxf(m, e[i][j]);
         m *= p.scale_log2;
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          const float a = ex2(fmaf(v[j], p.scale_log2, -m)), d = ex2(fmaf(v[j + 1], p.scale_log2, -m));
-          s0 += a; s1 += d;
-          e[i][j >> 1] = pack2(a, d);
+          e[i][j] = ex2(fmaf(e[i][j], p.scale_log2, -m));
+          e[i][j + 1] = ex2(fmaf(e[i][j + 1], p.scale_log2, -m));
+          s0 += e[i][j]; s1 += e[i][j + 1];
         }
         mc[i] = m;
         const float nm = fmaxf(mt, m);
@@ -198,7 +197,8 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float inv = 1.0f / total;
     if (p.stats && part == 0 && row_ok) p.stats[((int64_t)b * p.nh + h) * T + m0 + row] = make_float2(M, total);
     if (threadIdx.x == 64) AT_STAMP(4);
-    // normalise, (store), dropout, A-operand tiles of the PV MMA
+    // normalise, (store), dropout, A-operand tiles of the PV MMA.  One fp32 -> bf16 pack per stored / consumed value
+    // (F2FP is a quarter-rate instruction: with the MUFU it is what bounds this phase).
     const int64_t prow = (((int64_t)b * p.nh + h) * T + (m0 + row)) * T;   // linear index of P[b,h,i,0] (dropout hash key)
     const bool drop = p.drop_p > 0.f;
     const uint32_t thr = mmfn_drop_threshold(p.drop_p);
@@ -211,31 +211,35 @@ attn_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       if (c < NC) {
         const int col0 = c * 32, jb = c >> 1, hf = c & 1;
         const float f = ex2(mc[i] - M) * inv;               // chunk-local maximum -> row maximum, and 1 / sum
-        uint32_t w[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float2 t = unpack2(e[i][j]);
-          w[j] = pack2(t.x * f, t.y * f);
-        }
+        for (int j = 0; j < 32; ++j) e[i][j] *= f;
+        uint32_t w[16];
         if (p.P && row_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = pack2(e[i][2 * j], e[i][2 * j + 1]);
           uint4* dst = reinterpret_cast<uint4*>(p.P + prow + col0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) dst[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
         }
         if (drop) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) {                 // one hash per four keys (prow % 4 == 0, col0 % 32 == 0)
-            const uint64_t hsh = mmfn_hash64(dseed, (uint64_t)(prow + col0 + 2 * j) >> 2);
+          for (int j = 0; j < 32; j += 4) {                 // one hash per four keys (prow % 4 == 0, col0 % 32 == 0)
+            const uint64_t hsh = mmfn_hash64(dseed, (uint64_t)(prow + col0 + j) >> 2);
             const uint32_t lo = (uint32_t)hsh, hi = (uint32_t)(hsh >> 32);
-            const float2 f0 = unpack2(w[j]), f1 = unpack2(w[j + 1]);
-            w[j] = pack2((lo & 0xFFFFu) >= thr ? f0.x * keep : 0.f, (lo >> 16) >= thr ? f0.y * keep : 0.f);
-            w[j + 1] = pack2((hi & 0xFFFFu) >= thr ? f1.x * keep : 0.f, (hi >> 16) >= thr ? f1.y * keep : 0.f);
+            e[i][j] = (lo & 0xFFFFu) >= thr ? e[i][j] * keep : 0.f;
+            e[i][j + 1] = (lo >> 16) >= thr ? e[i][j + 1] * keep : 0.f;
+            e[i][j + 2] = (hi & 0xFFFFu) >= thr ? e[i][j + 2] * keep : 0.f;
+            e[i][j + 3] = (hi >> 16) >= thr ? e[i][j + 3] * keep : 0.f;
           }
-          if (p.Pd && row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(p.Pd + prow + col0);
+        }
+        if (drop || !(p.P && row_ok)) {                     // (without dropout the stored P tile is the MMA operand)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-          }
+          for (int j = 0; j < 16; ++j) w[j] = pack2(e[i][2 * j], e[i][2 * j + 1]);
+        }
+        if (drop && p.Pd && row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(p.Pd + prow + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
         }
         // K-major SWIZZLE_128B tile: row r at r*128 bytes, 16-byte chunk k stored at position k ^ (r & 7);
         // this thread owns chunks hf*4 .. hf*4 + 3 (its 32 keys) of the 64-key tile jb

@@ -147,10 +147,12 @@ class TrainEngine:
 
     # ---- CUDA-graph schedule -----------------------------------------------------------------
     def capture(self, static_batch, warmup=2):
-        """Capture forward+backward on `static_batch` (fixed device tensors, e.g. BatchStager.dev_views) as TWO graphs
-        split where the early gradient bucket (head, transformer4, radar encoder, layer4 of every trunk: the
-        contiguous range [n_late, n_active) of the flat buffer) is final, so that its all-reduce and AdamW update run
-        on a side stream under the second graph.  Later steps refill the static tensors in place and call step_graph()."""
+        """Capture forward+backward on `static_batch` (fixed device tensors, e.g. BatchStager.dev_views) as THREE graphs
+        split where a gradient bucket is final: the early bucket (head, transformer4, radar encoder, layer4 of every
+        trunk: [n_mid, n_active) of the flat buffer) after the last fusion stage, the mid bucket (layer3, transformer3,
+        transformer2: [n_late, n_mid)) after transformer2's backward.  Their all-reduce and AdamW updates run on a side
+        stream under the following graph; only the late bucket [0, n_late) is exchanged after backward.  Later steps
+        refill the static tensors in place and call step_graph()."""
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -164,28 +166,32 @@ class TrainEngine:
             self.st.flat_nbt.copy_(nbt0)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        graphs = [torch.cuda.CUDAGraph() for _ in range(3)]
         pool = torch.cuda.graph_pool_handle()
         l0 = lib().launches
         cap = torch.cuda.Stream(priority=-1)     # critical chain: above the leaf (weight-gradient) streams
         cap.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(cap):
-            ga.capture_begin(pool=pool)
+            graphs[0].capture_begin(pool=pool)
+            state = {"i": 0}
 
-            def split():
-                ga.capture_end()
-                gb.capture_begin(pool=pool)
+            def split(which):
+                assert which == ("early", "mid")[state["i"]], which
+                graphs[state["i"]].capture_end()
+                state["i"] += 1
+                graphs[state["i"]].capture_begin(pool=pool)
             self.net.mid_hook = split
             try:
                 self._graph_loss = self.forward_backward(static_batch)
                 self._graph_pred = self.last_pred
             finally:
                 self.net.mid_hook = None
-            gb.capture_end()
+            assert state["i"] == 2, "the schedule did not report both bucket boundaries"
+            graphs[2].capture_end()
         torch.cuda.current_stream().wait_stream(cap)
         torch.cuda.synchronize()
         self.graph_launches = lib().launches - l0
-        self._graph = (ga, gb)
+        self._graph = tuple(graphs)
         self._comm = torch.cuda.Stream()
         return self._graph
 
@@ -200,22 +206,29 @@ class TrainEngine:
                          p16=self.p16_active[lo:hi] if ops.BF16 else None)
 
     def step_graph(self):
-        """Replay the captured step.  Order on the device: graph A (zero grads, BEV, forward, backward down to the
-        last fusion stage) -> [side stream: early bucket all-reduce + AdamW] || graph B (rest of backward) ->
-        late bucket all-reduce + AdamW.  Returns the loss tensor."""
-        ga, gb = self._graph
+        """Replay the captured step.  Order on the device: graph A (zero grads, BEV, forward, backward down to the last
+        fusion stage) -> [side stream: early bucket all-reduce + AdamW] || graph B (backward through transformer2) ->
+        [side stream: mid bucket] || graph C (rest of backward) -> late bucket all-reduce + AdamW.  Returns the loss."""
+        ga, gb, gc = self._graph
         main = torch.cuda.current_stream()
+        st = self.st
         ops.adamw_advance_(self.state, self.betas[0], self.betas[1])
         ga.replay()
         ev = torch.cuda.Event()
         ev.record(main)
         self._comm.wait_event(ev)
         with torch.cuda.stream(self._comm):
-            self._bucket_update(self.st.n_late, self.st.n_active)
+            self._bucket_update(st.n_mid, st.n_active)
+        gb.replay()
+        ev2 = torch.cuda.Event()
+        ev2.record(main)
+        self._comm.wait_event(ev2)
+        with torch.cuda.stream(self._comm):
+            self._bucket_update(st.n_late, st.n_mid)
             done = torch.cuda.Event()
             done.record(self._comm)
-        gb.replay()
-        self._bucket_update(0, self.st.n_late)
+        gc.replay()
+        self._bucket_update(0, st.n_late)
         main.wait_event(done)
         lib().launches += self.graph_launches
         self.last_pred = self._graph_pred

@@ -656,13 +656,17 @@ class _Net:
 
     mid_hook = None
 
-    def _early_bucket_done(self):
-        """Backward has passed the last fusion stage: every gradient of params.is_early_bucket() is final once the
-        leaf streams are joined.  The engine hooks in here to split the captured step into two graphs and start the
-        early bucket's all-reduce + AdamW under the rest of backward."""
+    def _bucket_done(self, which):
+        """Backward has passed a fusion stage: every gradient of params.is_early_bucket() ("early": after the last
+        stage) / params.is_mid_bucket() ("mid": after transformer2's backward) is final once the leaf streams are
+        joined.  The engine hooks in here to split the captured step into three graphs and start that bucket's
+        all-reduce + AdamW under the rest of backward."""
         if self.mid_hook is not None:
             _Aux.join_all()
-            self.mid_hook()
+            self.mid_hook(which)
+
+    def _early_bucket_done(self):
+        self._bucket_done("early")
 
     def backward(self, dpred):
         dfused = self.head.bwd(dpred)
@@ -691,6 +695,8 @@ class _Net:
             if s == 2:
                 self._early_bucket_done()
             self.gpts[s].bwd(dtok, [dimg, dlid, dmp])
+            if s == 1:
+                self._bucket_done("mid")                       # layer3 x3 (deferred leaves ran under transformer2), transformer3 / 2
         self._parallel(lambda: self.img_stem.bwd(self.img_layers[0].bwd(dimg)),
                        lambda: self.lid_stem.bwd(self.lid_layers[0].bwd(dlid)),
                        (lambda: self.map_stem.bwd(self.map_layers[0].bwd(dmp))) if self.map_stem is not None

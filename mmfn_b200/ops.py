@@ -58,6 +58,9 @@ FUSED_ATTN_BWD = False
 # weights and optimizer stay fp32.  Implies TF32 for everything the bf16 kernels do not cover (stems, VectorNet, GAT, head).
 BF16 = False
 BF16_ATTN = True      # bf16 configuration: attention core on the bf16 kernel (False: TF32 kernel on an fp32 qkv buffer)
+import os as _os
+if _os.environ.get("MMFN_BF16_ATTN") is not None:          # A/B switches for measurement runs
+    BF16_ATTN = _os.environ["MMFN_BF16_ATTN"] != "0"
 
 
 def set_precision(mode):
@@ -233,7 +236,7 @@ def conv2d_fwd(x, w_krsc, stride, pad, res=None):
     return y
 
 
-FUSE_BN_STATS = True    # train-mode BatchNorm statistics from the convolution epilogue (no separate reduction pass over z)
+FUSE_BN_STATS = _os.environ.get("MMFN_FUSE_BN", "1") != "0"   # train-mode BatchNorm statistics from the convolution epilogue
 
 
 def conv_bn_fusable(x, w_krsc, stride, pad):

@@ -140,6 +140,16 @@ def is_early_bucket(key):
     return key.startswith(EARLY_BUCKET_PREFIXES)
 
 
+MID_BUCKET_PREFIXES = ("encoder.image_encoder.features.layer3.", "encoder.img_map_encoder.features.layer3.",
+                       "encoder.lidar_encoder._model.layer3.", "encoder.transformer3.", "encoder.transformer2.")
+
+
+def is_mid_bucket(key):
+    """Parameters whose gradients are complete once backward has passed the SECOND fusion stage (layer3 of every
+    trunk, transformer3, transformer2): the second overlap-able range of the flat buffer."""
+    return key.startswith(MID_BUCKET_PREFIXES)
+
+
 def _numel(shape):
     n = 1
     for s in shape:
@@ -157,16 +167,21 @@ class ParamStore:
         shapes = dict(fkeys)
         self.offsets = {}
         off = 0
-        # flat layout: [late bucket | early bucket | never-used].  "early" = parameters whose gradients are final
-        # first in backward (head, transformer4, radar encoder, layer4 of every trunk): they form ONE contiguous
-        # range [n_late, n_active), so their all-reduce + AdamW can start while the rest of backward still runs.
-        for group in ("late", "early", "unused"):
-            if group == "early":
+        # flat layout: [late bucket | mid bucket | early bucket | never-used].  "early" = parameters whose gradients are
+        # final first in backward (head, transformer4, radar encoder, layer4 of every trunk), "mid" = final after the
+        # second fusion stage (layer3 of every trunk, transformer3, transformer2): each is ONE contiguous range --
+        # early [n_mid, n_active), mid [n_late, n_mid) -- so its all-reduce + AdamW can start while the rest of
+        # backward still runs; only the late range [0, n_late) (layers 1-2, stems, transformer1, VectorNet: ~20 % of
+        # the gradient bytes) is exchanged after backward.
+        for group in ("late", "mid", "early", "unused"):
+            if group == "mid":
                 self.n_late = off
+            if group == "early":
+                self.n_mid = off
             if group == "unused":
                 self.n_active = off
             for k in order:
-                g = "unused" if is_unused(k, variant) else ("early" if is_early_bucket(k) else "late")
+                g = "unused" if is_unused(k, variant) else ("early" if is_early_bucket(k) else ("mid" if is_mid_bucket(k) else "late"))
                 if g != group:
                     continue
                 self.offsets[k] = off

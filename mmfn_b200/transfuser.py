@@ -67,6 +67,8 @@ class _NetTF(_Net):
             if s == 2:
                 self._early_bucket_done()
             self.gpts[s].bwd(dtok, [dimg, dlid])
+            if s == 1:
+                self._bucket_done("mid")
         self._parallel(lambda: self.img_stem.bwd(self.img_layers[0].bwd(dimg)),
                        lambda: self.lid_stem.bwd(self.lid_layers[0].bwd(dlid)))
         _Aux.join_all()

@@ -112,10 +112,11 @@ def test_flat_layout_buckets_are_contiguous():
     """[late | early | never-used]: the early gradient bucket (head, transformer4, radar GAT, layer4 of every trunk)
     is ONE contiguous 16-byte-aligned range, fused q/k/v stay adjacent, never-used parameters sit behind n_active."""
     from mmfn_b200.config import GlobalConfig
-    from mmfn_b200.params import ParamStore, is_early_bucket, is_unused
+    from mmfn_b200.params import ParamStore, is_early_bucket, is_mid_bucket, is_unused
     for variant in ("rad", "vec", "img", "transfuser"):
         st = ParamStore(GlobalConfig(), "cpu", variant)
-        assert 0 < st.n_late < st.n_active <= st.n_total and st.n_late % 4 == 0 and st.n_active % 4 == 0
+        assert 0 < st.n_late < st.n_mid < st.n_active <= st.n_total
+        assert st.n_late % 4 == 0 and st.n_mid % 4 == 0 and st.n_active % 4 == 0
         n_early = 0
         for k, off in st.offsets.items():
             n = 1
@@ -125,10 +126,13 @@ def test_flat_layout_buckets_are_contiguous():
             if is_unused(k, variant):
                 assert off >= st.n_active, k
             elif is_early_bucket(k):
-                assert st.n_late <= off and off + n <= st.n_active, k
+                assert st.n_mid <= off and off + n <= st.n_active, k
                 n_early += n
+            elif is_mid_bucket(k):
+                assert st.n_late <= off and off + n <= st.n_mid, k
             else:
                 assert off + n <= st.n_late, k
-        assert n_early > 0.4 * st.n_active            # the overlap-able bucket carries > 40 % of the gradient bytes
+        assert n_early > 0.4 * st.n_active            # the first overlap-able bucket carries > 40 % of the gradient bytes
+        assert st.n_late < 0.35 * st.n_active         # ... and less than 35 % is left for the exposed exchange after backward
         qkv = st.fused([f"encoder.transformer1.blocks.0.attn.{n}.weight" for n in ("key", "query", "value")])
         assert tuple(qkv.shape) == (192, 64)

@@ -54,15 +54,17 @@ def _worker(rank, world, initfile, outdir):
     mine = parallel.shard_batch(gb, rank, world)
     loss, _, grads = _small_step(sd, cfg, mine)
     # local gradients -> flat buffer (what the CUDA backward writes), then the gradient exchange exactly as
-    # TrainEngine.step_graph issues it: the early bucket [n_late, n_active) first (under the rest of backward on the
-    # GPU), then the late bucket [0, n_late).  Together they must equal ONE all-reduce over [0, n_active).
+    # TrainEngine.step_graph issues it: the early bucket [n_mid, n_active) first, then the mid bucket [n_late, n_mid)
+    # (both under the rest of backward on the GPU), then the late bucket [0, n_late).  Together they must equal ONE
+    # all-reduce over [0, n_active).
     store.flat_grad.zero_()
     for k, g in grads.items():
         if g is not None:
             store.torch_view(k, grad=True).copy_(g)
     whole = store.flat_grad[: store.n_active].clone()
     parallel.allreduce_sum_(whole)
-    parallel.allreduce_sum_(store.flat_grad[store.n_late: store.n_active])
+    parallel.allreduce_sum_(store.flat_grad[store.n_mid: store.n_active])
+    parallel.allreduce_sum_(store.flat_grad[store.n_late: store.n_mid])
     parallel.allreduce_sum_(store.flat_grad[: store.n_late])
     assert torch.equal(whole, store.flat_grad[: store.n_active])
     torch.save({"flat_grad": store.flat_grad.clone(), "loss": loss, "w": store.flat[:1000].clone(),

@@ -734,7 +734,8 @@ def test_attention_fwd_bf16(C, T, B):
     y2, P2, Pd2, _ = ops.attention_fwd_bf16(qkv16, B, T, C, nh, p_drop, seed)
     mask = ops.dropout(torch.ones(B, nh, T, T, device=DEV), p_drop, seed)
     assert torch.equal(P2, P)
-    assert torch.equal(Pd2, (P2.float() * mask).to(torch.bfloat16))
+    assert torch.count_nonzero(Pd2[mask == 0]).item() == 0             # exactly the library's mask ...
+    close(Pd2, P2.float() * mask, 4e-3)                                # ... on the fp32 probabilities (one rounding each)
     close(y2, (Pd2.float().cpu() @ v).permute(0, 2, 1, 3).reshape(B * T, C), 5e-3)
     y3, P3, _, stats3 = ops.attention_fwd_bf16(qkv16, B, T, C, nh, p_drop, seed, save_probs=False)
     assert P3 is None and torch.equal(y3, y2) and torch.equal(stats3, stats)
@@ -748,7 +749,7 @@ def test_attention_fwd_bf16(C, T, B):
 
 @pytest.mark.parametrize("bf16", [False, True], ids=["tf32", "bf16"])
 @pytest.mark.parametrize("geom", [(4, 64, 64, 64, 3, 1, 1), (4, 64, 64, 128, 3, 2, 1), (4, 64, 64, 128, 1, 2, 0), (8, 32, 128, 128, 3, 1, 1),
-                                  (16, 32, 128, 256, 3, 2, 1), (16, 16, 256, 256, 3, 1, 1), (32, 16, 256, 512, 3, 2, 1)],
+                                  (16, 32, 128, 256, 3, 2, 1), (16, 16, 256, 256, 3, 1, 1), (40, 16, 256, 512, 3, 2, 1)],
                          ids=lambda g: f"N{g[0]}H{g[1]}C{g[2]}-{g[3]}R{g[4]}s{g[5]}")
 def test_conv_epilogue_batchnorm_statistics(geom, bf16):
     """mmfn_conv2d_fwd_bn_*: per-channel mean / rstd / running statistics accumulated by the convolution epilogue
