@@ -129,16 +129,22 @@ bev_scatter_onevisit_kernel(const float* __restrict__ pts, int n_pts, int pt_str
 #pragma unroll
   for (int u = 0; u < CHUNK_PTS; ++u) {
     const float x = px[u], y = py[u], z = pz[u];
-    // closed range test also rejects NaN; x*8 / y*8 are exact in fp32.
-    if (!(x >= -16.0f && x <= 16.0f && y >= -24.0f && y <= 8.0f)) continue;
-    const bool lo = z <= -2.0f, hi = z > -2.0f;                        // channel 0 / 1; NaN z matches neither
-    if (!(lo || hi)) continue;
-    int ix = (int)floorf(x * 8.0f) + 128;
-    int iy = (int)floorf(y * 8.0f) + 192;
-    ix = min(ix, GRID - 1);                                            // right-most edge is inclusive
-    iy = min(iy, GRID - 1);
-    const int bin = (hi ? GRID * GRID : 0) + ix * GRID + iy;
-    atomicAdd(cnt + (bin >> 1), 1u << ((bin & 1) * 16));               // result unused: compiles to red.global.add
+    // closed range test also rejects NaN; x*8 / y*8 are exact in fp32.  channel 0: z <= -2, channel 1: z > -2 (NaN: neither)
+    const bool lo = z <= -2.0f, hi = z > -2.0f;
+    int bin = -1;
+    if (x >= -16.0f && x <= 16.0f && y >= -24.0f && y <= 8.0f && (lo || hi)) {
+      int ix = (int)floorf(x * 8.0f) + 128;
+      int iy = (int)floorf(y * 8.0f) + 192;
+      ix = min(ix, GRID - 1);                                          // right-most edge is inclusive
+      iy = min(iy, GRID - 1);
+      bin = (hi ? GRID * GRID : 0) + ix * GRID + iy;
+    }
+    // Dense pillars (hundreds of returns in one bin) would serialise hundreds of same-address L2 atomics: the lanes of
+    // a warp that hit the same bin elect ONE leader, which adds min(count, 5) (the grid is clamped at 5 anyway; a u16
+    // field receives at most 5 per warp instruction, so < 65536 / 5 warp instructions per frame cannot overflow it).
+    const unsigned peers = __match_any_sync(0xffffffffu, bin);
+    if (bin >= 0 && (threadIdx.x & 31) == (__ffs(peers) - 1))
+      atomicAdd(cnt + (bin >> 1), (uint32_t)min(__popc(peers), 5) << ((bin & 1) * 16));
   }
   // ---- last CTA of this frame: counters -> clamped, scaled fp32 grid; scratch back to zero
   __threadfence();
@@ -176,7 +182,7 @@ bev_scatter_onevisit_kernel(const float* __restrict__ pts, int n_pts, int pt_str
 MMFN_API int mmfn_bev_scatter_ws(const float* pts, int frames, int n_pts, int pt_stride,
                                  float* out, void* ws, cudaStream_t stream) {
   MMFN_CHECK_ARG(out && ws && (pts || n_pts == 0 || frames == 0), "bev_scatter_ws: null pointer");
-  MMFN_CHECK_ARG(frames >= 0 && n_pts >= 0 && n_pts < 65536, "bev_scatter_ws: 0 <= n_pts < 65536 (u16 pillar counters)");
+  MMFN_CHECK_ARG(frames >= 0 && n_pts >= 0 && n_pts <= 262144, "bev_scatter_ws: 0 <= n_pts <= 262144 (u16 pillar counters: <= 5 per warp instruction)");
   MMFN_CHECK_ARG(pt_stride >= 3, "bev_scatter_ws: pt_stride must be >= 3 (x,y,z,...)");
   MMFN_CHECK_ARG(pt_stride != 4 || ((uintptr_t)pts & 15) == 0, "bev_scatter_ws: xyzi rows must be 16B aligned");
   MMFN_CHECK_ARG((((uintptr_t)out | (uintptr_t)ws) & 15) == 0, "bev_scatter_ws: out / ws must be 16-byte aligned");

@@ -756,7 +756,7 @@ def bev_scatter(points, strips=0):
     assert points.dim() == 3 and points.is_contiguous()
     F, n, s = points.shape
     out = torch.empty((F, 2, 256, 256), device=points.device, dtype=torch.float32)
-    if strips == 0 and n < 65536 and F > 0:
+    if strips == 0 and n <= 262144 and F > 0:
         key = (points.device, torch.cuda.current_stream().cuda_stream, F)
         ws = _bev_ws.get(key)
         if ws is None:

@@ -61,4 +61,34 @@ n = 104708260
 p = torch.randn(n, device=dev); g = torch.randn(n, device=dev); m = torch.zeros(n, device=dev); v = torch.zeros(n, device=dev)
 st = torch.zeros(3, device=dev)
 run(lambda: ops.adamw_step_(p, g, m, v, st, 1e-4))
+# ---------------------------------------------------------------- bf16 configuration (BASELINE configs[2], B = 32)
+if len(sys.argv) > 2 and sys.argv[2] == "bf16":
+    ops.set_precision("bf16")
+    B = 32
+    bf = torch.bfloat16
+    # 7. fc1 of transformer4 in bf16: (8192 x 512) @ (2048 x 512)^T, bias + ReLU, bf16 result; its data / weight gradients
+    A = torch.randn(B * 256, 512, device=dev).to(bf); W = (torch.randn(2048, 512, device=dev) * 0.02).to(bf)
+    C16 = torch.empty(B * 256, 2048, device=dev, dtype=bf)
+    run(lambda: ops.gemm(A, W, C16, bias=bias, act=1))
+    dY = torch.randn(B * 256, 2048, device=dev).to(bf); dW = torch.zeros(2048, 512, device=dev); dX = torch.empty(B * 256, 512, device=dev)
+    run(lambda: ops.gemm(dY, W.t(), dX))
+    run(lambda: ops.gemm(dY.t(), A.t(), dW, accum=2))
+    # 8. layer-3 / layer-1 3x3 convolutions in bf16: forward with BatchNorm statistics in the epilogue, dgrad, wgrad
+    for (H, Cc) in [(16, 256), (64, 64)]:
+        x = torch.randn(B, H, H, Cc, device=dev).to(bf); w = (torch.randn(Cc, 3, 3, Cc, device=dev) * 0.05).to(bf)
+        dy = torch.randn(B, H, H, Cc, device=dev).to(bf); dw = torch.zeros(Cc, 3, 3, Cc, device=dev)
+        rmc, rvc = torch.zeros(Cc, device=dev), torch.ones(Cc, device=dev)
+        run(lambda: ops.conv2d_fwd(x, w, 1, 1))
+        run(lambda: ops.conv2d_fwd_bn(x, w, 1, 1, rmc, rvc))
+        run(lambda: ops.conv2d_dgrad(dy, w, (B, H, H, Cc), 1, 1))
+        run(lambda: ops.conv2d_wgrad_(dy, x, dw, 1, 1))
+    # 9. fused bf16 attention, every transformer scale: with P / Pd stored (training) and stats-only
+    for (T, Cc) in [(192, 64), (192, 128), (192, 256), (256, 512)]:
+        q16 = torch.randn(B * T, 3 * Cc, device=dev).to(bf)
+        run(lambda: ops.attention_fwd_bf16(q16, B, T, Cc, 4, 0.1, 7))
+        run(lambda: ops.attention_fwd_bf16(q16, B, T, Cc, 4, 0.1, 7, save_probs=False))
+    # 10. BEV scatter at 64 frames (both kernels)
+    pts64 = torch.from_numpy(np.stack([synthetic.synth_points(1234 + i) for i in range(64)])).to(dev)
+    run(lambda: ops.bev_scatter(pts64))
+    run(lambda: ops.bev_scatter(pts64, 4))
 print("done")
