@@ -152,7 +152,9 @@ def gemm(A, B, C, *, bias=None, res=None, mask=None, alpha=1.0, act=0, accum=0,
         lib().gemm_tf32_out(_p(A), am[1], am[0], a_b[0], a_b[1], _p(B), bm[1], bm[0], b_b[0], b_b[1],
                             _p(C), 1, C.stride(-2), c_b[0], c_b[1], M, N, K, nb[0], nb[1], float(alpha), _st())
         return C
-    if TF32 and M >= 64 and K >= 16 and M * N * K * nbt >= (1 << 18):
+    # (M >= 16: the per-sample matrices of the waypoint head / VectorNet tail (M = batch) also take the tensor-core kernel --
+    #  TMA zero-fills the rest of the 128-row tile; the SIMT kernel needs ~18 us for these latency-bound shapes)
+    if TF32 and M >= 16 and K >= 16 and M * N * K * nbt >= (1 << 18):
         am, bm = _major(A), _major(B)
         bs_ok = all(x % 4 == 0 for x in a_b + b_b)
         if nbt > 1:      # TMA cannot express broadcast (stride-0) batches
