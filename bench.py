@@ -353,9 +353,14 @@ def run_torch_eager(args):
 # ncu --set full captures of the headline shapes (tools/ncu_targets.py -> profiles/*_ncu_full_kernels.json)
 NCU_FILES = ("r02_ncu_full_kernels.json", "r01_ncu_full_kernels.json")
 NCU_KERNEL_OF = {
-    ("conv2d_fwd_tf32", 16, 16, 256, 256, 3, 16): ("conv3x3_patch_kernel<64, 0, 1>", "(4, 32, 1)"),
-    ("conv2d_fwd_tf32", 16, 64, 64, 64, 3, 64): ("conv3x3_patch_kernel<64, 0, 0>", "(1, 512, 1)"),
-    ("gemm_tf32", 4096, 2048, 512, 1): ("tc_kernel<GemmOp<0, 0, 128>, 128, 3, 1>", "(16, 32, 1)"),
+    ("conv2d_fwd_tf32", 16, 16, 256, 256, 3, 16): ("conv3x3_patch_kernel<64, 0, 1, 32>", "(4, 32, 1)"),
+    ("conv2d_fwd_tf32", 16, 64, 64, 64, 3, 64): ("conv3x3_patch_kernel<64, 0, 0, 32>", "(1, 512, 1)"),
+    ("gemm_tf32", 4096, 2048, 512, 1): ("tc_kernel<GemmOp<0, 0, 128, 32>, 128, 3, 1, 0>", "(16, 32, 1)"),
+    ("conv2d_fwd_bf16", 32, 16, 256, 256, 3, 16): ("conv3x3_patch_kernel<128, 0, 1, 64>", "(2, 64, 1)"),
+    ("conv2d_fwd_bf16", 32, 64, 64, 64, 3, 64): ("conv3x3_patch_kernel<64, 0, 0, 64>", "(1, 1024, 1)"),
+    ("gemm_bf16", 8192, 2048, 512, 1): ("tc_kernel<GemmOp<0, 0, 128, 64>, 128, 3, 1, 1>", "(16, 64, 1)"),
+    # round-1 names (profiles/r01_ncu_full_kernels.json)
+    ("r01", "conv2d_fwd_tf32", 16, 16, 256, 256, 3, 16): ("conv3x3_patch_kernel<64, 0, 1>", "(4, 32, 1)"),
 }
 
 

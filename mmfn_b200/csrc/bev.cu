@@ -7,6 +7,7 @@
 // and finally writes its two channel slabs once, coalesced, already clamped and scaled.  DRAM traffic is
 // therefore the algorithmic N*stride*4 + 2*256*256*4 bytes per frame; there are no global atomics and no
 // separate memset/finalize.  L2 read amplification = number of strips (chosen so that ~256 CTAs exist).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -107,7 +108,7 @@ constexpr int CHUNK_THREADS = 512, CHUNK_PTS = 4;       // 2048 points per CTA, 
 
 __global__ void __launch_bounds__(CHUNK_THREADS)
 bev_scatter_onevisit_kernel(const float* __restrict__ pts, int n_pts, int pt_stride, int chunks,
-                            float* __restrict__ out, uint32_t* __restrict__ ws, int frames) {
+                            float* __restrict__ out, uint32_t* __restrict__ ws, int frames, int dbg) {
   __shared__ bool last_cta;
   const int frame = blockIdx.x / chunks, chunk = blockIdx.x - frame * chunks;
   uint32_t* cnt = ws + (int64_t)frame * (GRID * GRID);                 // [2 channels][65536 bins / 2]
@@ -145,8 +146,12 @@ bev_scatter_onevisit_kernel(const float* __restrict__ pts, int n_pts, int pt_str
     // Dense pillars (hundreds of returns in one bin) would serialise hundreds of same-address L2 atomics: the lanes of
     // a warp that hit the same bin elect ONE leader, which adds min(count, 5) (the grid is clamped at 5 anyway; a u16
     // field receives at most 5 per warp instruction, so < 65536 / 5 warp instructions per frame cannot overflow it).
+    if (dbg & 4) {                                                      // developer variant: no warp-level dedupe
+      if (bin >= 0 && !(dbg & 1)) atomicAdd(cnt + (bin >> 1), 1u << ((bin & 1) * 16));
+      continue;
+    }
     const unsigned peers = __match_any_sync(0xffffffffu, bin);
-    if (bin >= 0 && (threadIdx.x & 31) == (__ffs(peers) - 1))
+    if (bin >= 0 && (threadIdx.x & 31) == (__ffs(peers) - 1) && !(dbg & 1))
       atomicAdd(cnt + (bin >> 1), (uint32_t)min(__popc(peers), 5) << ((bin & 1) * 16));
   }
   // ---- last CTA of this frame: counters -> clamped, scaled fp32 grid; scratch back to zero
@@ -156,6 +161,7 @@ bev_scatter_onevisit_kernel(const float* __restrict__ pts, int n_pts, int pt_str
   __syncthreads();
   if (!last_cta) return;
   __threadfence();
+  if (dbg & 2) { if (threadIdx.x == 0) *ticket = 0u; return; }          // developer variant: no conversion tail
   float4* o = reinterpret_cast<float4*>(out + (int64_t)frame * 2 * GRID * GRID);
   uint4* c4 = reinterpret_cast<uint4*>(cnt);
   // 16384 x 16 bytes of counters: 32 per thread, EIGHT loads in flight per step (a one-load-per-iteration loop runs at
@@ -192,8 +198,9 @@ MMFN_API int mmfn_bev_scatter_ws(const float* pts, int frames, int n_pts, int pt
   const int per = CHUNK_THREADS * CHUNK_PTS;
   const int chunks = n_pts > 0 ? (n_pts + per - 1) / per : 1;
   MMFN_CHECK_ARG((int64_t)frames * chunks <= 0x7fffffff, "bev_scatter_ws: too many CTAs");
+  const char* dv = getenv("MMFN_BEV_DEBUG");                            // developer timing variants (results are then WRONG)
   bev_scatter_onevisit_kernel<<<frames * chunks, CHUNK_THREADS, 0, stream>>>(pts, n_pts, pt_stride, chunks, out,
-                                                                             static_cast<uint32_t*>(ws), frames);
+                                                                             static_cast<uint32_t*>(ws), frames, dv ? atoi(dv) : 0);
   return mmfn_launch_status("bev_scatter_ws");
 }
 

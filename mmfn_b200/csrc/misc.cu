@@ -120,9 +120,12 @@ __global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ c
 // Fast path for the stems (compile-time S, C): one warp per output pixel, lane l writes columns l, l+32, ... of the
 // pixel's row (fully coalesced 128-byte stores); a filter row is a contiguous run of S*C input floats, so the loads of
 // neighbouring lanes are contiguous too, and the only divisions are by compile-time constants.
-template <int S, int C, int KP>
+__device__ __forceinline__ void im2col_store(float* p, float v) { *p = v; }
+__device__ __forceinline__ void im2col_store(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <int S, int C, int KP, typename TOUT = float>
 __global__ void __launch_bounds__(256)
-im2col_rows_kernel(const float* __restrict__ x, float* __restrict__ col, int N, int H, int W, int R,
+im2col_rows_kernel(const float* __restrict__ x, TOUT* __restrict__ col, int N, int H, int W, int R,
                    int stride, int pad, int Ho, int Wo) {
   constexpr int SC = S * C;
   constexpr int NK = KP / 32;                // columns per lane
@@ -153,9 +156,9 @@ im2col_rows_kernel(const float* __restrict__ x, float* __restrict__ col, int N, 
       v[j] = 0.f;
       if (kin[j] && h >= 0 && h < H && w >= 0 && w < W) v[j] = __ldg(xn + (int64_t)h * W * C + rem[j]);
     }
-    float* dst = col + (int64_t)pix * KP + lane;
+    TOUT* dst = col + (int64_t)pix * KP + lane;
 #pragma unroll
-    for (int j = 0; j < NK; ++j) dst[32 * j] = v[j];
+    for (int j = 0; j < NK; ++j) im2col_store(dst + 32 * j, v[j]);
   }
 }
 
@@ -401,6 +404,19 @@ MMFN_API int mmfn_im2col_nhwc(const float* x, float* col, int N, int H, int W, i
   }
   im2col_kernel<<<grid_1d(n4, 256), 256, 0, stream>>>(x, col, N, H, W, C, R, S, stride, pad, Ho, Wo, R * S * C, Kp);
   return mmfn_launch_status("im2col_nhwc");
+}
+
+// im2col of the two stems with a BF16 column matrix (bf16 configuration: halves the 168 MB-per-16-frames matrix the
+// stem GEMMs stream): 7x7 filters on 3 / 2 channels only, Kp = 192 / 128 (multiples of the 64-element bf16 k-block).
+MMFN_API int mmfn_im2col_stem_bf16(const float* x, void* col, int N, int H, int W, int C, int stride, int pad,
+                                   int Ho, int Wo, int Kp, cudaStream_t stream) {
+  MMFN_CHECK_ARG(x && col && N > 0 && H > 0 && W > 0 && stride > 0, "im2col_stem_bf16: bad args");
+  MMFN_CHECK_ARG((C == 3 && Kp == 192) || (C == 2 && Kp == 128), "im2col_stem_bf16: C = 3 (Kp 192) or C = 2 (Kp 128) only");
+  MMFN_CHECK_ARG((((uintptr_t)col) & 15) == 0, "im2col_stem_bf16: col must be 16-byte aligned");
+  const int grid = grid_1d((int64_t)N * Ho * Wo * 32, 256);
+  if (C == 3) im2col_rows_kernel<7, 3, 192, __nv_bfloat16><<<grid, 256, 0, stream>>>(x, (__nv_bfloat16*)col, N, H, W, 7, stride, pad, Ho, Wo);
+  else im2col_rows_kernel<7, 2, 128, __nv_bfloat16><<<grid, 256, 0, stream>>>(x, (__nv_bfloat16*)col, N, H, W, 7, stride, pad, Ho, Wo);
+  return mmfn_launch_status("im2col_stem_bf16");
 }
 
 // dst[r*ldd + c] (+)= src[r*lds + c], r < rows, c < cols

@@ -153,7 +153,8 @@ class ConvBN:
             self.z = ops.conv2d_fwd(x.h, self.w16, self.stride, self.pad)
         elif ops.stem_uses_im2col(x, self.w):
             # stems: im2col + one dense tensor-core GEMM; the column matrix is kept for the weight gradient
-            self.z, self.col, self.w_pad = ops.conv2d_fwd_im2col(x, self.w, self.stride, self.pad, getattr(self, "w_pad", None))
+            self.z, self.col, self.w_pad = ops.conv2d_fwd_im2col(x, self.w, self.stride, self.pad, getattr(self, "w_pad", None),
+                                                                 bf16=ops.BF16)
         else:
             self.z = ops.conv2d_fwd(x, self.w, self.stride, self.pad)
         bn = ops.bn_train_fwd if train else ops.bn_eval_fwd
@@ -163,7 +164,8 @@ class ConvBN:
 
     def bwd(self, dy, need_dx=True, want_dres=False, dx_res=None):
         dz, dres = ops.bn_train_bwd(dy, self.z, self.y if self.relu else None, self.mean, self.rstd, self.gam,
-                                    self.dgam, self.dbet, want_dres, out_bf16=self.bf)
+                                    self.dgam, self.dbet, want_dres,
+                                    out_bf16=self.bf or (self.col is not None and self.col.dtype == torch.bfloat16))
         x, col = self.x, self.col
         if self.bf:
             x16 = x.h

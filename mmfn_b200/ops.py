@@ -239,6 +239,7 @@ def conv2d_fwd(x, w_krsc, stride, pad, res=None):
 
 
 FUSE_BN_STATS = _os.environ.get("MMFN_FUSE_BN", "1") != "0"   # train-mode BatchNorm statistics from the convolution epilogue
+BN_FUSE_MAX_CTAS = int(_os.environ.get("MMFN_FUSE_BN_MAX_CTAS", "512"))
 
 
 def conv_bn_fusable(x, w_krsc, stride, pad):
@@ -248,7 +249,11 @@ def conv_bn_fusable(x, w_krsc, stride, pad):
     Co, R, S, _ = w_krsc.shape
     Ho, Wo = conv_out_hw(H, W, R, S, stride, pad)
     tc_ok = (x.dtype == BF and C % 64 == 0) or (x.dtype == torch.float32 and _tc_conv_ok(C, Co, Ho, Wo))
-    return FUSE_BN_STATS and tc_ok and Co % 64 == 0 and Co <= BN_WS_MAX_C and Ho >= 8 and Wo >= 8 and N * Ho * Wo > BN_SMALL_ROWS
+    # every epilogue warp adds its column sums with fp64 atomics: measured +5.7 us on a 128-CTA layer-3 convolution (the
+    # separate reduction pass costs ~13 us) but +16.8 us on a 1024-CTA layer-1 convolution (profiles/r02_ncu_full_kernels.json)
+    ctas = ((N * Ho * Wo + 127) // 128) * ((Co + 127) // 128)
+    return (FUSE_BN_STATS and tc_ok and Co % 64 == 0 and Co <= BN_WS_MAX_C and Ho >= 8 and Wo >= 8
+            and N * Ho * Wo > BN_SMALL_ROWS and ctas <= BN_FUSE_MAX_CTAS)
 
 
 def conv2d_fwd_bn(x, w_krsc, stride, pad, running_mean, running_var, momentum=0.1, eps=1e-5):
@@ -283,21 +288,29 @@ def stem_uses_im2col(x, w_krsc):
     return TF32 and x.shape[-1] < 32 and w_krsc.shape[0] % 4 == 0
 
 
-def conv2d_fwd_im2col(x, w_krsc, stride, pad, w_pad=None):
+def conv2d_fwd_im2col(x, w_krsc, stride, pad, w_pad=None, bf16=False):
     """-> (y, col, w_pad): col (N*Ho*Wo, Kp) is kept for the weight gradient; w_pad (Co, Kp) is the zero-padded filter
-    matrix (allocate once by passing None, then pass it back in)."""
+    matrix (allocate once by passing None, then pass it back in).  bf16 (bf16 configuration, 7x7 stems only): the column
+    matrix and the padded filters are bf16 (Kp = a multiple of the 64-element k-block), the GEMM runs on kind::f16."""
     N, H, W, C = x.shape
     Co, R, S, _ = w_krsc.shape
     Ho, Wo = conv_out_hw(H, W, R, S, stride, pad)
     K = R * S * C
-    Kp = (K + 31) // 32 * 32
-    if w_pad is None:
+    blk = 64 if bf16 else 32
+    Kp = (K + blk - 1) // blk * blk
+    if w_pad is None or w_pad.shape[1] != Kp:
         w_pad = torch.zeros((Co, Kp), device=x.device, dtype=torch.float32)
     lib().copy2d_f32(_p(w_krsc), K, _p(w_pad), Kp, Co, K, 0, _st())
-    col = torch.empty((N * Ho * Wo, Kp), device=x.device, dtype=torch.float32)
-    lib().im2col_nhwc(_p(x), _p(col), N, H, W, C, R, S, stride, pad, Ho, Wo, Kp, _st())
     y = torch.empty((N, Ho, Wo, Co), device=x.device, dtype=torch.float32)
-    gemm(col, w_pad, y.view(N * Ho * Wo, Co))
+    if bf16:
+        assert R == 7 and S == 7 and C in (2, 3)
+        col = torch.empty((N * Ho * Wo, Kp), device=x.device, dtype=BF)
+        lib().im2col_stem_bf16(_p(x), _p(col), N, H, W, C, stride, pad, Ho, Wo, Kp, _st())
+        gemm(col, to_bf16(w_pad), y.view(N * Ho * Wo, Co))
+    else:
+        col = torch.empty((N * Ho * Wo, Kp), device=x.device, dtype=torch.float32)
+        lib().im2col_nhwc(_p(x), _p(col), N, H, W, C, R, S, stride, pad, Ho, Wo, Kp, _st())
+        gemm(col, w_pad, y.view(N * Ho * Wo, Co))
     lib().next_work = None
     return y, col, w_pad
 

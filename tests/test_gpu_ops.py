@@ -764,6 +764,7 @@ def test_conv_epilogue_batchnorm_statistics(geom, bf16):
     g, b = torch.rand(Co, device=DEV) + 0.5, torch.randn(Co, device=DEV)
     rm0, rv0 = torch.randn(Co, device=DEV), torch.rand(Co, device=DEV) + 0.5
     ops.BF16 = bf16
+    old_cap, ops.BN_FUSE_MAX_CTAS = ops.BN_FUSE_MAX_CTAS, 1 << 20          # exercise the epilogue path on every geometry
     try:
         assert ops.conv_bn_fusable(x, w, stride, pad)
         z0 = ops.conv2d_fwd(x, w, stride, pad)
@@ -782,3 +783,27 @@ def test_conv_epilogue_batchnorm_statistics(geom, bf16):
             assert ops.twin(y1).dtype == torch.bfloat16 and torch.equal(ops.twin(y1).float(), y1.to(torch.bfloat16).float())
     finally:
         ops.BF16 = False
+        ops.BN_FUSE_MAX_CTAS = old_cap
+
+
+
+@pytest.mark.parametrize("C", [3, 2])
+def test_stem_conv_bf16_column_matrix(C):
+    """bf16 configuration of the 7x7/2 stems: bf16 im2col matrix + kind::f16 GEMMs (forward, weight gradient) against
+    torch fp32 on bf16-rounded operands."""
+    from mmfn_b200 import ops
+    N, H, Co = 2, 256, 64
+    x = _bf(torch.randn(N, C, H, H))
+    w = _bf(torch.randn(Co, C, 7, 7) * 0.1)
+    xr, wr = x.float(), w.float().requires_grad_(True)
+    yr = F.conv2d(xr, wr, stride=2, padding=3)
+    xn = x.float().permute(0, 2, 3, 1).contiguous().to(DEV)
+    wk = w.float().permute(0, 2, 3, 1).contiguous().to(DEV)
+    y, col, w_pad = ops.conv2d_fwd_im2col(xn, wk, 2, 3, None, bf16=True)
+    assert col.dtype == torch.bfloat16 and col.shape[1] % 64 == 0
+    close(y.permute(0, 3, 1, 2), yr, 3e-3)
+    dy = _bf(torch.randn_like(yr))
+    yr.backward(dy.float())
+    dw = torch.zeros(Co, 7, 7, C, device=DEV)
+    ops.conv2d_wgrad_im2col_(dy.permute(0, 2, 3, 1).contiguous().to(DEV), col, dw)
+    close(dw.permute(0, 3, 1, 2), wr.grad, 3e-3)

@@ -405,6 +405,44 @@ def test_bf16_graph_steps_keep_shadow_in_sync_and_train(dev):
         ops.set_precision("tf32")
 
 
+def test_loader_to_engine_path_matches_oracle(dev, tmp_path):
+    """SURVEY 8(f) rank 1, end to end on the GPU: phase-1 pickles on disk -> PRE_Data (adds the radar adjacency) ->
+    torch DataLoader with collate_single_cpu (ragged lane sets padded) -> to_engine_batch -> BatchStager (ONE packed H2D
+    copy) -> TrainEngine step, against the oracle fed with the same collated tensors the way Engine.train builds them
+    (phase2_train_net.py:66-103).  Exact-fp32 kernels."""
+    import pickle
+    from mmfn_b200 import data as mdata, ops
+    from mmfn_b200.engine import BatchStager, TrainEngine
+    B = 3
+    cfg, model, sd, _ = _setup(dev, B, tf32=False)
+    lanes = (70, 128, 93)
+    for i in range(B):
+        smp = synthetic.synth_sample(40 + i, bev_oracle.lidar_to_histogram_features, n_lanes=128)
+        smp["vectormaps"] = [smp["vectormaps"][0][: lanes[i]]]
+        with open(tmp_path / f"{i}.pkl", "wb") as f:
+            pickle.dump(smp, f)
+    ds = mdata.PRE_Data(str(tmp_path), cfg)
+    loader = torch.utils.data.DataLoader(ds, batch_size=B, shuffle=False, num_workers=0, collate_fn=mdata.collate_single_cpu)
+    data = next(iter(loader))
+    eb = mdata.to_engine_batch(data, seq_len=cfg.seq_len, pad_lanes_to=128)
+    assert eb["lane"].shape == (B, 128, 10, 5) and len(set(eb["lane_num"].tolist())) > 1 and "lidar" in eb   # ragged lane sets
+    stager = BatchStager(eb, dev)
+    db = stager.stage(eb)
+    eng = TrainEngine(model, lr=1e-4)
+    loss = eng.forward_backward(db).item()
+    # the reference's own tensors (Engine.train): fronts / lidars lists, vectormaps = [[lane], [lane_num], Lmax]
+    lane, lane_num, _ = data["vectormaps"][0]
+    lane_p = torch.nn.functional.pad(lane.float(), (0, 0, 0, 0, 0, 128 - lane.shape[1]))
+    inputs = (data["fronts"][0].float(), data["lidars"][0].float(), lane_p, lane_num, data["radar"][0].float(),
+              data["radar_adj"].float(), torch.stack(data["target_point"], 1).float(), data["velocity"].float())
+    gt = torch.stack([torch.stack(data["waypoints"][i], 1) for i in range(cfg.seq_len, len(data["waypoints"]))], 1).float()
+    oloss, opred, ograds = mmfn_oracle.train_step({k: v.clone() for k, v in sd.items()}, cfg, dict(inputs=inputs, gt_waypoints=gt))
+    assert (eng.last_pred.cpu() - opred).abs().mean().item() < 2e-4
+    assert abs(loss - oloss.item()) < 2e-4
+    cosine, _ = _grad_stats(model, ograds)
+    assert cosine > 0.9995, cosine
+
+
 def test_torchvision_resnet34_weights_load_into_both_trunks(dev):
     """ImageCNN = models.resnet34(pretrained=True) minus fc (model_rad.py:22-23): a torchvision state_dict must land in
     encoder.image_encoder.features.* and encoder.img_map_encoder.features.* (KRSC storage behind the (K,C,R,S) view)."""
