@@ -7,7 +7,6 @@
 // and finally writes its two channel slabs once, coalesced, already clamped and scaled.  DRAM traffic is
 // therefore the algorithmic N*stride*4 + 2*256*256*4 bytes per frame; there are no global atomics and no
 // separate memset/finalize.  L2 read amplification = number of strips (chosen so that ~256 CTAs exist).
-#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -96,23 +95,24 @@ bev_scatter_kernel(const float* __restrict__ pts, int n_pts, int pt_stride,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One-visit variant.  The strip kernel above re-reads every point once per strip: with ~256 CTAs that is 8-16 passes
-// over the sweep through L2 (134 MB at 16 or 64 frames) and the kernel runs at the L2 read rate, ~25 us whatever the
-// frame count (profiles/r02_bev_bench_v2a.json).  Here every point is read ONCE: a CTA owns a chunk of one frame's
-// points and counts them with packed-u16 atomics (red.global) into a per-frame counter grid that lives in L2
-// (2 x 256 x 256 u16 = 256 KB per frame); the LAST CTA of a frame (arrival ticket) converts the counters to the
-// clamped / scaled fp32 grid, and re-zeroes counters and ticket, so the scratch is zero again for the next call
-// (no memset, one launch).  A u16 field cannot overflow: a frame has fewer than 65536 points per launch (checked).
-// ws layout: [frames][65536] u32 counters (two bins per word), then [frames] u32 tickets.
+// One-visit variant (two launches).  The strip kernel above re-reads every point once per strip: with ~256 CTAs that is
+// 8-16 passes over the sweep through L2 (134 MB at 16 or 64 frames) and the kernel runs at the L2 read rate, ~25 us
+// whatever the frame count (profiles/r02_bev_bench_strip_v2b.json).  Here every point is read ONCE:
+//   1. bev_count_kernel: a CTA owns a chunk of one frame's points and counts them with packed-u16 `red.global` atomics
+//      into a per-frame counter grid that lives in L2 (2 x 256 x 256 u16 = 256 KB per frame);
+//   2. bev_convert_kernel: one thread per 8 bins turns the counters into the clamped / scaled fp32 grid and re-zeroes
+//      them, so the scratch is zero again for the next call (no memset).
+// (A single launch whose last CTA per frame converted the frame measured 38 us at 16 frames, 31 us of it in that
+// one-SM-per-frame tail; counting alone takes 6.7 us -- profiles/r02_bev_variants.txt.)
+// A u16 field cannot overflow: at most 5 are added per warp instruction with the warp-level dedupe, 1 per point without.
+// ws layout: [frames][65536] u32 counters (two bins per word).
 constexpr int CHUNK_THREADS = 512, CHUNK_PTS = 4;       // 2048 points per CTA, all loads in flight
 
+template <bool DEDUPE>
 __global__ void __launch_bounds__(CHUNK_THREADS)
-bev_scatter_onevisit_kernel(const float* __restrict__ pts, int n_pts, int pt_stride, int chunks,
-                            float* __restrict__ out, uint32_t* __restrict__ ws, int frames, int dbg) {
-  __shared__ bool last_cta;
+bev_count_kernel(const float* __restrict__ pts, int n_pts, int pt_stride, int chunks, uint32_t* __restrict__ ws) {
   const int frame = blockIdx.x / chunks, chunk = blockIdx.x - frame * chunks;
   uint32_t* cnt = ws + (int64_t)frame * (GRID * GRID);                 // [2 channels][65536 bins / 2]
-  uint32_t* ticket = ws + (int64_t)frames * (GRID * GRID) + frame;
   const float* p = pts + (int64_t)frame * n_pts * pt_stride;
   const int base = chunk * (CHUNK_THREADS * CHUNK_PTS);
   float px[CHUNK_PTS], py[CHUNK_PTS], pz[CHUNK_PTS];
@@ -143,64 +143,48 @@ bev_scatter_onevisit_kernel(const float* __restrict__ pts, int n_pts, int pt_str
       iy = min(iy, GRID - 1);
       bin = (hi ? GRID * GRID : 0) + ix * GRID + iy;
     }
-    // Dense pillars (hundreds of returns in one bin) would serialise hundreds of same-address L2 atomics: the lanes of
-    // a warp that hit the same bin elect ONE leader, which adds min(count, 5) (the grid is clamped at 5 anyway; a u16
-    // field receives at most 5 per warp instruction, so < 65536 / 5 warp instructions per frame cannot overflow it).
-    if (dbg & 4) {                                                      // developer variant: no warp-level dedupe
-      if (bin >= 0 && !(dbg & 1)) atomicAdd(cnt + (bin >> 1), 1u << ((bin & 1) * 16));
-      continue;
-    }
-    const unsigned peers = __match_any_sync(0xffffffffu, bin);
-    if (bin >= 0 && (threadIdx.x & 31) == (__ffs(peers) - 1) && !(dbg & 1))
-      atomicAdd(cnt + (bin >> 1), (uint32_t)min(__popc(peers), 5) << ((bin & 1) * 16));
-  }
-  // ---- last CTA of this frame: counters -> clamped, scaled fp32 grid; scratch back to zero
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) last_cta = atomicAdd(ticket, 1u) == (uint32_t)chunks - 1;
-  __syncthreads();
-  if (!last_cta) return;
-  __threadfence();
-  if (dbg & 2) { if (threadIdx.x == 0) *ticket = 0u; return; }          // developer variant: no conversion tail
-  float4* o = reinterpret_cast<float4*>(out + (int64_t)frame * 2 * GRID * GRID);
-  uint4* c4 = reinterpret_cast<uint4*>(cnt);
-  // 16384 x 16 bytes of counters: 32 per thread, EIGHT loads in flight per step (a one-load-per-iteration loop runs at
-  // one L2 round trip per 16 bytes and thread: 64 us measured for this tail alone)
-  constexpr int UN = 8;
-  static_assert((GRID * GRID / 4) % (CHUNK_THREADS * UN) == 0, "conversion tail tiling");
-  for (int i0 = threadIdx.x; i0 < GRID * GRID / 4; i0 += CHUNK_THREADS * UN) {
-    uint4 w[UN];
-#pragma unroll
-    for (int u = 0; u < UN; ++u) w[u] = __ldcg(c4 + i0 + u * CHUNK_THREADS);
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int i = i0 + u * CHUNK_THREADS;
-      c4[i] = make_uint4(0u, 0u, 0u, 0u);
-      o[2 * i] = make_float4(fifth(w[u].x & 0xffffu), fifth(w[u].x >> 16), fifth(w[u].y & 0xffffu), fifth(w[u].y >> 16));
-      o[2 * i + 1] = make_float4(fifth(w[u].z & 0xffffu), fifth(w[u].z >> 16), fifth(w[u].w & 0xffffu), fifth(w[u].w >> 16));
+    if constexpr (DEDUPE) {
+      // dense pillars: the lanes of a warp that hit the same bin elect ONE leader, which adds min(count, 5)
+      const unsigned peers = __match_any_sync(0xffffffffu, bin);
+      if (bin >= 0 && (threadIdx.x & 31) == (__ffs(peers) - 1))
+        atomicAdd(cnt + (bin >> 1), (uint32_t)min(__popc(peers), 5) << ((bin & 1) * 16));
+    } else {
+      if (bin >= 0) atomicAdd(cnt + (bin >> 1), 1u << ((bin & 1) * 16));   // result unused: red.global.add
     }
   }
-  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// counters -> clamp(count, 5) / 5 as fp32, counters re-zeroed: one thread per 4 words (8 bins, two 16-byte stores)
+__global__ void __launch_bounds__(256)
+bev_convert_kernel(uint4* __restrict__ cnt, float4* __restrict__ out, int64_t n4) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const uint4 w = __ldcg(cnt + i);
+  cnt[i] = make_uint4(0u, 0u, 0u, 0u);
+  out[2 * i] = make_float4(fifth(w.x & 0xffffu), fifth(w.x >> 16), fifth(w.y & 0xffffu), fifth(w.y >> 16));
+  out[2 * i + 1] = make_float4(fifth(w.z & 0xffffu), fifth(w.z >> 16), fifth(w.w & 0xffffu), fifth(w.w >> 16));
 }
 
 }  // namespace
 
-// One-visit BEV scatter (see bev_scatter_onevisit_kernel).  ws: (frames * 65536 + frames) u32 of scratch that is
-// ZERO on entry (zero it once after allocation; every call leaves it zero again) -- mmfn_workspace_bytes(MMFN_WS_BEV).
+// One-visit BEV scatter (see bev_count_kernel / bev_convert_kernel).  ws: frames * 65536 u32 of scratch that is ZERO on
+// entry (zero it once after allocation; every call leaves it zero again) -- mmfn_workspace_bytes(MMFN_WS_BEV).
 MMFN_API int mmfn_bev_scatter_ws(const float* pts, int frames, int n_pts, int pt_stride,
                                  float* out, void* ws, cudaStream_t stream) {
   MMFN_CHECK_ARG(out && ws && (pts || n_pts == 0 || frames == 0), "bev_scatter_ws: null pointer");
-  MMFN_CHECK_ARG(frames >= 0 && n_pts >= 0 && n_pts <= 262144, "bev_scatter_ws: 0 <= n_pts <= 262144 (u16 pillar counters: <= 5 per warp instruction)");
+  MMFN_CHECK_ARG(frames >= 0 && n_pts >= 0 && n_pts < 65536, "bev_scatter_ws: 0 <= n_pts < 65536 (u16 pillar counters)");
   MMFN_CHECK_ARG(pt_stride >= 3, "bev_scatter_ws: pt_stride must be >= 3 (x,y,z,...)");
   MMFN_CHECK_ARG(pt_stride != 4 || ((uintptr_t)pts & 15) == 0, "bev_scatter_ws: xyzi rows must be 16B aligned");
   MMFN_CHECK_ARG((((uintptr_t)out | (uintptr_t)ws) & 15) == 0, "bev_scatter_ws: out / ws must be 16-byte aligned");
   if (frames == 0) return 0;
   const int per = CHUNK_THREADS * CHUNK_PTS;
-  const int chunks = n_pts > 0 ? (n_pts + per - 1) / per : 1;
+  const int chunks = n_pts > 0 ? (n_pts + per - 1) / per : 0;
   MMFN_CHECK_ARG((int64_t)frames * chunks <= 0x7fffffff, "bev_scatter_ws: too many CTAs");
-  const char* dv = getenv("MMFN_BEV_DEBUG");                            // developer timing variants (results are then WRONG)
-  bev_scatter_onevisit_kernel<<<frames * chunks, CHUNK_THREADS, 0, stream>>>(pts, n_pts, pt_stride, chunks, out,
-                                                                             static_cast<uint32_t*>(ws), frames, dv ? atoi(dv) : 0);
+  // (the warp-level dedupe variant <true> measured 12.4 vs 11.9 us at 16 frames: __match_any_sync costs what it saves)
+  if (chunks > 0)
+    bev_count_kernel<false><<<frames * chunks, CHUNK_THREADS, 0, stream>>>(pts, n_pts, pt_stride, chunks, static_cast<uint32_t*>(ws));
+  const int64_t n4 = (int64_t)frames * (GRID * GRID / 4);
+  bev_convert_kernel<<<(unsigned)ceil_div64(n4, 256), 256, 0, stream>>>(static_cast<uint4*>(ws), reinterpret_cast<float4*>(out), n4);
   return mmfn_launch_status("bev_scatter_ws");
 }
 

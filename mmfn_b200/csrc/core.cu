@@ -37,7 +37,7 @@ using namespace mmfn;
 //   MMFN_WS_ATTN_PROB     a = B, b = heads, c = T, d = 1|2   saved attention probabilities (B, heads, T, T); d = 2 with
 //                                                            dropout (P and P after dropout)
 //   MMFN_WS_GRU_SAVED     a = B, b = steps                   gate activations kept by mmfn_gru_head_fwd for BPTT
-//   MMFN_WS_BEV           a = frames                         packed-u16 pillar counters + tickets of mmfn_bev_scatter_ws
+//   MMFN_WS_BEV           a = frames                         packed-u16 pillar counters of mmfn_bev_scatter_ws
 //                                                            (zero once; every call leaves it zero)
 // Replaces nothing in the reference (PyTorch's caching allocator does this implicitly); SURVEY.md section 8(b).
 MMFN_API int mmfn_workspace_bytes(int op, int dtype, int64_t a, int64_t b, int64_t c, int64_t d, int64_t* bytes) {
@@ -50,7 +50,7 @@ MMFN_API int mmfn_workspace_bytes(int op, int dtype, int64_t a, int64_t b, int64
     case 2: MMFN_CHECK_ARG(a > 0 && c > 0, "workspace_bytes: sizes"); *bytes = a * ((c + kblock - 1) / kblock * kblock) * es; return 0;
     case 3: MMFN_CHECK_ARG(a > 0 && b > 0 && c > 0 && (d == 1 || d == 2), "workspace_bytes: sizes"); *bytes = a * b * c * c * es * d; return 0;
     case 4: MMFN_CHECK_ARG(a > 0 && b > 0, "workspace_bytes: sizes"); *bytes = a * b * 5 * 64 * 4; return 0;
-    case 5: MMFN_CHECK_ARG(a > 0, "workspace_bytes: frames"); *bytes = ((a * 65536 + a + 3) / 4 * 4) * 4; return 0;
+    case 5: MMFN_CHECK_ARG(a > 0, "workspace_bytes: frames"); *bytes = a * 65536 * 4; return 0;
     default: mmfn_set_error("workspace_bytes: unknown op %d", op); return MMFN_BAD_ARG;
   }
 }

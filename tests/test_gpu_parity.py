@@ -33,7 +33,7 @@ def test_bev_scatter_bit_exact_vs_oracle_and_goldens(dev, golden_dir):
         ref = (gold[key].astype(np.float64) / 5).astype(np.float32)
         for stride in (4, 3):
             p = torch.from_numpy(np.ascontiguousarray(pts[None, :, :stride])).to(dev)
-            for strips in (0, 2, 4, 8, 16):
+            for strips in (0, -1, 2, 4, 8, 16):
                 out = ops.bev_scatter(p, strips).cpu().numpy()[0]
                 assert np.array_equal(out, ref), (key, stride, strips)
     # a ragged multi-frame batch against the oracle
@@ -48,6 +48,7 @@ def test_bev_scatter_full_size_properties(dev):
     from mmfn_b200 import ops
     pts = torch.from_numpy(np.stack([synthetic.synth_points(9000 + i) for i in range(64)])).to(dev)
     out = ops.bev_scatter(pts)
+    assert torch.equal(ops.bev_scatter(pts, -1), out)          # strip kernel (64 frames) == one-visit kernels
     vals = torch.unique(out).cpu().numpy()
     assert set(np.round(vals * 5).astype(int)) <= {0, 1, 2, 3, 4, 5}
     # permutation invariance and frame independence

@@ -56,7 +56,7 @@ out = []
 for frames in (16, 32, 64, 128):
     pts = torch.from_numpy(np.stack([synthetic.synth_points(9000 + i) for i in range(frames)])).cuda()
     # MMFN_BEV_STRIPS=1: the shared-memory strip kernel with its automatic strip count instead of the one-visit kernel
-    strips = (4 if frames >= 64 else 8 if frames >= 24 else 16) if os.environ.get("MMFN_BEV_STRIPS") else 0
+    strips = (4 if frames >= 64 else 8 if frames >= 24 else 16) if os.environ.get("MMFN_BEV_STRIPS") else -1
     fn = lambda: ops.bev_scatter(pts, strips)
     warm, cold = chain_us(fn), cold_us(fn)
     byts = frames * 1048576.0
