@@ -439,12 +439,20 @@ class VectorNet:
         B, L, P, _ = lane.shape
         G, V = B * L, P - 1
         self.G, self.V, self.B, self.L, self.lane_num = G, V, B, L, lane_num
-        x = ops.lane_to_vector(lane)
-        self.args = []
-        for lin, ln in self.sub:
-            x, arg = ops.subgraph_pool_fwd(ln.fwd(lin.fwd(x)), G, V)
-            self.args.append(arg)
-        tok, self.argf = ops.segmax_fwd(x, G, V)
+        if ops.FUSE_SUBGRAPH and V in ops.SUBGRAPH_FUSED_V:
+            # one launch for the whole polyline sub-graph; it leaves behind exactly what the per-layer backward reads
+            o = ops.subgraph_fused_fwd(lane, [(lin.w, lin.b, ln.g, ln.b) for lin, ln in self.sub])
+            for i, (lin, ln) in enumerate(self.sub):
+                lin.x, lin.act, lin.y = (o["vec"], o["x1"], o["x2"])[i], 0, None
+                ln.x, ln.mean, ln.rstd = o["y"][i], o["mean"][i], o["rstd"][i]
+            self.args, self.argf, tok = o["arg"], o["argf"], o["tok"]
+        else:
+            x = ops.lane_to_vector(lane)
+            self.args = []
+            for lin, ln in self.sub:
+                x, arg = ops.subgraph_pool_fwd(ln.fwd(lin.fwd(x)), G, V)
+                self.args.append(arg)
+            tok, self.argf = ops.segmax_fwd(x, G, V)
         self.qkv_out = self.qkv.fwd(tok).view(B, L, 384)
         self.prob, att0 = ops.l2l_row0_fwd(self.qkv_out, lane_num, 2, None)
         cat = torch.empty((B, 192), device=lane.device, dtype=torch.float32)

@@ -66,6 +66,11 @@ def test_argument_validation_without_gpu():
         lib().f32_to_bf16(P, P, 6, None)
     with pytest.raises(MmfnError, match="bad args"):
         lib().copy2d_f32(P, 4, P, 8, 2, 6, 0, None)
+    # one-launch polyline sub-graph: instantiated for 9 / 19 vectors per polyline only
+    with pytest.raises(MmfnError, match="V must be 9 or 19"):
+        lib().subgraph_fused_fwd(P, 4, 12, *([P] * 12), *([P] * 17), 1e-5, None)
+    with pytest.raises(MmfnError, match="null output"):
+        lib().subgraph_fused_fwd(P, 4, 9, *([P] * 12), 0, *([P] * 16), 1e-5, None)
 
 
 def test_product_never_imports_oracle():

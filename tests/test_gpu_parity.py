@@ -592,6 +592,45 @@ def test_config5_vectornet_only_matches_oracle(dev, tf32):
         assert rel < (1e-3 if not tf32 else 3e-2), (k, rel)     # measured 2.7e-4 (fp32: split-K atomics over 20k vectors)
 
 
+@pytest.mark.parametrize("L,P", [(128, 10), (256, 20), (7, 10), (5, 20)], ids=["ref-10-node", "bench-20-node", "ragged-10", "ragged-20"])
+def test_fused_subgraph_forward_matches_unfused_kernels(dev, L, P):
+    """csrc/vectornet.cu (one launch: vectorise + 3 x [Linear, LayerNorm, ReLU, max-pool, concat] + final max) against the
+    per-layer kernels it replaces, exact-fp32 GEMMs on both sides: every tensor the backward consumes, the arg-max
+    routing tables, and the parameter gradients of a full VectorNet forward+backward.  Polyline counts that
+    are not a multiple of the polylines-per-warp packing (3 at 9 vectors, 1 at 19) exercise the ragged tail."""
+    from mmfn_b200 import ops
+    from mmfn_b200.model_rad import _Aux
+    B = 3
+    model, sd, b = _vectornet_setup(dev, B, L, P, False)
+    vn = model.net.vectornet
+    lane, num = b["lane"].to(dev), b["lane_num"].to(dev)
+    dmap = torch.randn(B, 64, 64, 64, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+    res = {}
+    try:
+        for fused in (False, True):
+            ops.FUSE_SUBGRAPH = fused
+            model.store.flat_grad.zero_()
+            out = vn.fwd(lane, num).clone()
+            saved = dict(x=[lin.x.clone() for lin, _ in vn.sub], y=[ln.x.clone() for _, ln in vn.sub],
+                         mean=[ln.mean.clone() for _, ln in vn.sub], rstd=[ln.rstd.clone() for _, ln in vn.sub],
+                         arg=[a.clone() for a in vn.args], argf=vn.argf.clone())
+            vn.bwd(dmap)
+            _Aux.join_all()
+            torch.cuda.synchronize()
+            res[fused] = (out, saved, model.store.flat_grad.clone())
+    finally:
+        ops.FUSE_SUBGRAPH = True
+    (o0, s0, g0), (o1, s1, g1) = res[False], res[True]
+    for i in range(3):
+        # identical routing except where two nodes tie to within the fp32 summation-order noise of the two GEMM orders
+        assert (s0["arg"][i] != s1["arg"][i]).float().mean().item() < 1e-3, i
+        for k in ("x", "y", "mean", "rstd"):
+            assert torch.allclose(s0[k][i], s1[k][i], rtol=2e-5, atol=2e-5), (k, i, (s0[k][i] - s1[k][i]).abs().max().item())
+    assert (s0["argf"] != s1["argf"]).float().mean().item() < 1e-3
+    assert torch.allclose(o0, o1, rtol=1e-4, atol=1e-5)
+    assert (g0 - g1).norm().item() <= 1e-4 * g0.norm().item()
+
+
 def test_config5_vectornet_full_size_properties(dev):
     """Size-independent checks at BASELINE's size (B=128, 256 polylines x 19 nodes): samples are independent,
     padded lanes do not influence the result, gradients are finite."""
