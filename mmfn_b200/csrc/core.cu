@@ -141,6 +141,7 @@ int mmfn_bind_rng_pool(const unsigned long long*);
 int mmfn_bind_rng_attn_tc(const unsigned long long*);
 int mmfn_bind_rng_norm(const unsigned long long*);
 int mmfn_bind_rng_attn_bf16(const unsigned long long*);
+int mmfn_bind_rng_gpt_small(const unsigned long long*);
 
 // Bind (or with null: unbind) a device-resident 64-bit offset that every dropout site adds to its
 // seed at run time.  The training engine bumps it on the device once per step, so the dropout masks
@@ -154,6 +155,7 @@ MMFN_API int mmfn_rng_bind(const unsigned long long* dev_offset) {
   if (!rc) rc = mmfn_bind_rng_pool(dev_offset);
   if (!rc) rc = mmfn_bind_rng_attn_tc(dev_offset);
   if (!rc) rc = mmfn_bind_rng_attn_bf16(dev_offset);
+  if (!rc) rc = mmfn_bind_rng_gpt_small(dev_offset);
   if (!rc) rc = mmfn_bind_rng_norm(dev_offset);     // LayerNorm backward regenerates the residual-branch masks
   if (rc) mmfn_set_error("rng_bind: cudaMemcpyToSymbol failed (%d)", rc);
   return rc;

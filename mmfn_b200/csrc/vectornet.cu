@@ -54,10 +54,14 @@ subgraph_fused_fwd_kernel(SubgraphParams p) {
   float* mst = par + 9 * HID;                   // [warps][PPW][64]  pooled maxima of the current layer (per polyline)
   float* hst = mst + (SG_THREADS / 32) * PPW * HID;   // [64][threads]  this thread's activations, k-major (bank = thread)
   for (int i = threadIdx.x; i < 7 * HID; i += SG_THREADS) { const int k = i / HID, c = i - k * HID; w0t[i] = p.w[0][c * 7 + k]; }
-  for (int i = threadIdx.x; i < 128 * HID; i += SG_THREADS) {
-    const int k = i / HID, c = i - k * HID;
-    w1t[i] = p.w[1][c * 128 + k];
-    w2t[i] = p.w[2][c * 128 + k];
+  // (64,128) row-major weights -> k-major copies: coalesced global reads into a padded staging tile (the activation
+  // buffer, not yet in use), transposed on the way out of it (stride 129: conflict-free both ways)
+  for (int m = 1; m <= 2; ++m) {
+    float* dst = m == 1 ? w1t : w2t;
+    for (int i = threadIdx.x; i < 128 * HID; i += SG_THREADS) { const int c = i >> 7, k = i & 127; hst[c * 129 + k] = p.w[m][i]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 128 * HID; i += SG_THREADS) { const int k = i / HID, c = i - k * HID; dst[i] = hst[c * 129 + k]; }
+    __syncthreads();
   }
   for (int i = threadIdx.x; i < 3 * HID; i += SG_THREADS) {
     const int l = i / HID, c = i - l * HID;

@@ -351,6 +351,24 @@ class Block:
         a = self.fc1.fwd(h2, act=1, out_bf16=bf)
         return self.fc2.fwd(a, res=x1, drop_p=rp, seed=seed + 2)
 
+    def params12(self, bf):
+        """operand-typed weights, fp32 biases and LayerNorm parameters in the order mmfn_gpt_small_fwd's table wants"""
+        w = (lambda lin: lin.w16 if bf else lin.w)
+        return (w(self.qkv), w(self.proj), w(self.fc1), w(self.fc2), self.qkv.b, self.proj.b, self.fc1.b, self.fc2.b,
+                self.ln1.g, self.ln1.b, self.ln2.g, self.ln2.b)
+
+    def adopt(self, o, l, x_in, B, T, seed, ap, rp, bf):
+        """take over block l's saved tensors from the whole-GPT forward kernel: exactly the state fwd() leaves behind"""
+        self.B, self.T, self.seed, self.ap, self.rp = B, T, seed, ap, rp
+        self.bf = self.bfa = bf
+        self.ln1.x, self.ln1.mean, self.ln1.rstd = x_in, o["mean1"][l], o["rstd1"][l]
+        self.qkv.x, self.qkv.act, self.qkv.y = o["h1"][l], 0, None
+        self.qkv_out, self.P, self.Pd = o["qkv"][l], o["P"][l], o["Pd"][l]
+        self.proj.x, self.proj.act, self.proj.y = o["y"][l], 0, None
+        self.ln2.x, self.ln2.mean, self.ln2.rstd = o["x1"][l], o["mean2"][l], o["rstd2"][l]
+        self.fc1.x, self.fc1.act, self.fc1.y = o["h2"][l], 1, o["a"][l]
+        self.fc2.x, self.fc2.act, self.fc2.y = o["a"][l], 0, None
+
     def bwd(self, dx2, dz, drop_prev=None):
         """dx2: gradient of the block output; dz = dx2 * dropout mask of the fc2 branch (produced by the
         LayerNorm backward that made dx2; bf16 in the bf16 configuration).  drop_prev=(p, seed) asks for the same pair
@@ -408,8 +426,18 @@ class FusionGPT:
         self.ep = self.embd_p if train else 0.0
         self.seed = seed + self.site * 100
         x = ops.tokens_fwd(feats, self.pos, self.vw, self.vb, velocity, self.ep, self.seed).view(B * self.T, self.C)
-        for i, blk in enumerate(self.blocks):
-            x = blk.fwd(x, B, self.T, self.seed + 3 * i + 1, train)
+        blocks = self.blocks
+        if ops.gpt_small_ok(self.C, self.T, blocks[0].nh, len(blocks)):
+            # all blocks in ONE launch (csrc/gpt_small.cu); each block adopts the tensors its backward reads
+            bf = ops.BF16
+            ap, rp = (blocks[0].attn_p, blocks[0].resid_p) if train else (0.0, 0.0)
+            o = ops.gpt_small_fwd(x, B, self.T, self.C, blocks[0].nh, [blk.params12(bf) for blk in blocks], ap, rp, self.seed)
+            for i, blk in enumerate(blocks):
+                blk.adopt(o, i, x if i == 0 else o["xout"][i - 1], B, self.T, self.seed + 3 * i + 1, ap, rp, bf)
+            x = o["xout"][len(blocks) - 1]
+        else:
+            for i, blk in enumerate(blocks):
+                x = blk.fwd(x, B, self.T, self.seed + 3 * i + 1, train)
         return self.ln_f.fwd(x).view(B, self.T, self.C)
 
     def bwd(self, dtok_out, dfeats):

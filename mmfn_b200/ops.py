@@ -746,6 +746,45 @@ def segmax_bwd(dout, arg, G, V):
     return dx
 
 
+FUSE_GPT = _os.environ.get("MMFN_FUSE_GPT", "0") != "0"    # off until it beats the per-op chain in the step
+
+
+def gpt_small_ok(C, T, nh, n_layer):
+    """whole-GPT forward kernel (csrc/gpt_small.cu): the two narrow fusion transformers, tensor-core precisions only"""
+    return FUSE_GPT and (BF16 or TF32) and C in (64, 128) and T in (128, 192) and nh == 4 and 1 <= n_layer <= 12
+
+
+def gpt_small_fwd(x0, B, T, C, nh, layers, attn_p, resid_p, seed, eps=1e-5):
+    """All transformer blocks of one fusion GPT in one launch.  x0 (B*T, C) fp32; layers: per block a 12-tuple of tensors
+    (Wqkv, Wproj, Wfc1, Wfc2 in the operand type, their fp32 biases, ln1 gamma / beta, ln2 gamma / beta).
+    -> dict of tensors stacked over the blocks: xout, x1 (fp32); h1, qkv, y, h2, a, P, Pd (operand type); mean1, rstd1,
+    mean2, rstd2."""
+    import ctypes
+    Lr, M = len(layers), B * T
+    bf = layers[0][0].dtype == BF
+    dt = BF if bf else torch.float32
+    dev = x0.device
+    assert x0.is_contiguous() and x0.shape == (M, C) and x0.dtype == torch.float32
+    f = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+    e = lambda *shape: torch.empty(shape, device=dev, dtype=dt)
+    o = dict(xout=f(Lr, M, C), x1=f(Lr, M, C), h1=e(Lr, M, C), qkv=e(Lr, M, 3 * C), y=e(Lr, M, C), h2=e(Lr, M, C), a=e(Lr, M, 4 * C),
+             P=e(Lr, B, nh, T, T), mean1=f(Lr, M), rstd1=f(Lr, M), mean2=f(Lr, M), rstd2=f(Lr, M))
+    o["Pd"] = e(Lr, B, nh, T, T) if attn_p > 0 else None
+    tab = (ctypes.c_void_p * (12 * Lr))()
+    for l, tensors in enumerate(layers):
+        assert len(tensors) == 12 and all(t.is_contiguous() for t in tensors) and all(t.dtype == dt for t in tensors[:4])
+        for i, t in enumerate(tensors):
+            tab[l * 12 + i] = t.data_ptr()
+    hs = C // nh
+    lib().next_work = (Lr * (2.0 * M * 12 * C * C + 4.0 * B * nh * T * T * hs), 0.0, B, T, C, nh)
+    lib().gpt_small_fwd(_p(x0), B, T, C, nh, Lr, 2 if bf else 1, ctypes.addressof(tab), _p(o["xout"]), _p(o["x1"]), _p(o["h1"]),
+                        _p(o["qkv"]), _p(o["y"]), _p(o["h2"]), _p(o["a"]), _p(o["P"]), _p(o["Pd"]), _p(o["mean1"]), _p(o["rstd1"]),
+                        _p(o["mean2"]), _p(o["rstd2"]), float(attn_p), float(resid_p), int(seed), eps, _st())
+    if o["Pd"] is None:
+        o["Pd"] = o["P"]
+    return o
+
+
 FUSE_SUBGRAPH = _os.environ.get("MMFN_FUSE_SUBGRAPH", "1") != "0"
 SUBGRAPH_FUSED_V = (9, 19)       # vectors per polyline the one-launch Subgraph forward is instantiated for
 

@@ -807,3 +807,66 @@ def test_trainer_validate_save_resume_roundtrip(dev, tmp_path):
     assert torch.equal(tr2.engine.m, tr.engine.m) and torch.equal(tr2.engine.v, tr.engine.v)
     assert torch.equal(tr2.engine.state, tr.engine.state)
     assert torch.equal(model2.store.flat_buf, model.store.flat_buf)
+
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32"])
+@pytest.mark.parametrize("site,nmod", [(0, 3), (1, 3), (0, 2), (1, 2)], ids=["C64-T192", "C128-T192", "C64-T128", "C128-T128"])
+@pytest.mark.parametrize("drop", [0.0, 0.1], ids=["nodrop", "drop"])
+def test_whole_gpt_forward_kernel_matches_per_op_path(dev, prec, site, nmod, drop):
+    """csrc/gpt_small.cu (all 8 blocks of a narrow fusion transformer in one cluster launch) against the per-op chain
+    (LayerNorm, tcgen05 GEMMs, fused attention, ... = 7 launches per block) in the same precision: block outputs, every
+    tensor saved for the backward, identical dropout masks (same counter-hash streams), and -- because the backward is the
+    per-op one in both cases -- the parameter gradients of a full forward + backward."""
+    from mmfn_b200 import ops
+    from mmfn_b200.config import GlobalConfig
+    from mmfn_b200.model_rad import MMFN, _Aux
+    from mmfn_b200.transfuser import TransFuser
+    ops.set_precision(prec)
+    try:
+        cfg = GlobalConfig(embd_pdrop=drop, attn_pdrop=drop, resid_pdrop=drop)
+        model = (MMFN if nmod == 3 else TransFuser)(cfg, dev)
+        sd = synthetic.fill_golden_weights(model.state_dict(), 42)
+        model.load_state_dict(sd)
+        if prec == "bf16":
+            model.store.sync_shadow()
+        gpt = model.net.gpts[site]
+        B, C, T = 3, gpt.C, gpt.T
+        gen = torch.Generator(device=dev).manual_seed(11)
+        feats = [torch.randn(B, 16, 16, C, device=dev, generator=gen) for _ in range(nmod)]
+        vel = torch.randn(B, 1, device=dev, generator=gen)
+        dtok = torch.randn(B, T, C, device=dev, generator=gen)
+        res = {}
+        for fused in (False, True):
+            ops.FUSE_GPT = fused
+            model.store.flat_grad.zero_()
+            out = gpt.fwd(feats, vel, 1234, True).clone()
+            saved = []
+            for blk in gpt.blocks:
+                saved.append(dict(x=blk.ln1.x.float().clone(), mean1=blk.ln1.mean.clone(), rstd1=blk.ln1.rstd.clone(),
+                                  h1=blk.qkv.x.float().clone(), qkv=blk.qkv_out.float().clone(), P=blk.P.float().clone(),
+                                  Pd=blk.Pd.float().clone(), y=blk.proj.x.float().clone(), x1=blk.ln2.x.float().clone(),
+                                  h2=blk.fc1.x.float().clone(), a=blk.fc1.y.float().clone()))
+            dfeats = [torch.zeros_like(f) for f in feats]
+            gpt.bwd(dtok.clone(), dfeats)
+            _Aux.join_all()
+            torch.cuda.synchronize()
+            res[fused] = (out, saved, model.store.flat_grad.clone(), [d.clone() for d in dfeats])
+    finally:
+        ops.FUSE_GPT = True
+        ops.set_precision("tf32")
+    (o0, s0, g0, d0), (o1, s1, g1, d1) = res[False], res[True]
+    tol = 3e-2 if prec == "bf16" else 4e-3          # relative to each tensor's scale; bf16 rounding compounds over 8 blocks
+    for l, (a, b) in enumerate(zip(s0, s1)):
+        for k in a:
+            scale = a[k].abs().max().item() + 1e-6
+            if k in ("P", "Pd"):
+                # same dropout mask: an element is zero in one exactly where it is zero in the other (up to values that
+                # round to zero), and the kept values agree
+                assert ((a[k] == 0) != (b[k] == 0)).float().mean().item() < 1e-3, (l, k)
+            err = (a[k] - b[k]).abs().max().item() / scale
+            assert err < tol * (1 + l), (l, k, err)
+    assert (o0 - o1).abs().max().item() / o0.abs().max().item() < tol * 8
+    rel = (g0 - g1).norm().item() / g0.norm().item()
+    assert rel < (0.1 if prec == "bf16" else 0.02), rel
+    for a, b in zip(d0, d1):
+        assert (a - b).norm().item() / a.norm().item() < (0.1 if prec == "bf16" else 0.02)
