@@ -63,6 +63,29 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+// Distributed shared memory: address of the same variable in CTA `rank` of the cluster, and loads through the SHARED
+// pipe.  (Generic loads of cluster.map_shared_rank() pointers go through the local/global queue instead: 19 % of this
+// kernel's stall samples were lg_throttle on exactly those loads, profiles/r02_ncu_gpt_small_v1.txt.)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r; asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank)); return r;
+}
+__device__ __forceinline__ uint2 ldsc2(uint32_t addr) {
+  uint2 v; asm volatile("ld.shared::cluster.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory"); return v;
+}
+__device__ __forceinline__ uint4 ldsc4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared::cluster.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// n words (2 or 4) of a peer CTA's shared memory in one instruction
+template <int N>
+__device__ __forceinline__ void ldsc_words(uint32_t addr, uint32_t* out) {
+  if constexpr (N == 2) { const uint2 v = ldsc2(addr); out[0] = v.x; out[1] = v.y; }
+  else { const uint4 v = ldsc4(addr); out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w; }
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -79,11 +102,25 @@ struct PrecBF {
   __device__ static __forceinline__ void st_smem(uint32_t* base, int ld, int row, int col, float v0, float v1) {
     base[row * ld + (col >> 1)] = pack_bf16(v0, v1);
   }
-  __device__ static __forceinline__ void st_smem_t(uint32_t* base, int ld, int row, int col, float v) {   // transposed element
-    reinterpret_cast<__nv_bfloat16*>(base + row * ld)[col] = __float2bfloat16_rn(v);
+  // K, elements col / col + 1 of a key row, words of a head permuted (see the attention phase): word w of the head
+  // (HW words) is stored at (w & 3) * (HW / 4) + (w >> 2)
+  template <int HS>
+  __device__ static __forceinline__ void st_k(uint32_t* base, int ld, int row, int col, float v0, float v1) {
+    constexpr int HW = HS / 2;
+    const int w = (col % HS) >> 1;
+    base[row * ld + (col / HS) * HW + (w & 3) * (HW / 4) + (w >> 2)] = pack_bf16(v0, v1);
+  }
+  // V^T element (dim `row`, key `key` of the slab): key word w = key / 2 is stored at (w & 3) * 8 + (w >> 2)
+  __device__ static __forceinline__ void st_vt(uint32_t* base, int ld, int row, int key, float v) {
+    const int w = key >> 1;
+    reinterpret_cast<__nv_bfloat16*>(base + row * ld + (w & 3) * 8 + (w >> 2))[key & 1] = __float2bfloat16_rn(v);
   }
   __device__ static __forceinline__ void st_global(void* base, long long idx, float v0, float v1) {
     *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(base) + idx) = pack_bf16(v0, v1);
+  }
+  // staging tile (16 rows x 32 words, 16-byte chunks XOR-swizzled by the row): elements col, col + 1 (col even, < 64)
+  __device__ static __forceinline__ void st_stage(uint32_t* stg, int r, int col, float v0, float v1) {
+    stg[r * 32 + ((((col >> 3) ^ (r & 7)) << 2) | ((col >> 1) & 3))] = pack_bf16(v0, v1);
   }
 };
 struct PrecTF {
@@ -96,13 +133,44 @@ struct PrecTF {
   __device__ static __forceinline__ void st_smem(uint32_t* base, int ld, int row, int col, float v0, float v1) {
     *reinterpret_cast<float2*>(base + row * ld + col) = make_float2(v0, v1);
   }
-  __device__ static __forceinline__ void st_smem_t(uint32_t* base, int ld, int row, int col, float v) {
-    base[row * ld + col] = __float_as_uint(v);
+  template <int HS>
+  __device__ static __forceinline__ void st_k(uint32_t* base, int ld, int row, int col, float v0, float v1) {
+    constexpr int HW = HS;
+    const int w = col % HS;                              // even: w and w + 1 share w >> 2
+    uint32_t* r = base + row * ld + (col / HS) * HW + (w >> 2);
+    r[(w & 3) * (HW / 4)] = __float_as_uint(v0);
+    r[((w + 1) & 3) * (HW / 4)] = __float_as_uint(v1);
+  }
+  // V^T element (dim `row`, key): the PV product pairs MMA k index t with key 8 k8 + 2t and t + 4 with 8 k8 + 2t + 1;
+  // key is stored at ((key & 7) >> 1) * 16 + (key >> 3) * 2 + (key & 1): a thread's 16 words of the slab are contiguous
+  __device__ static __forceinline__ void st_vt(uint32_t* base, int ld, int row, int key, float v) {
+    base[row * ld + ((key & 7) >> 1) * 16 + (key >> 3) * 2 + (key & 1)] = __float_as_uint(v);
   }
   __device__ static __forceinline__ void st_global(void* base, long long idx, float v0, float v1) {
     *reinterpret_cast<float2*>(reinterpret_cast<float*>(base) + idx) = make_float2(v0, v1);
   }
+  __device__ static __forceinline__ void st_stage(uint32_t* stg, int r, int col, float v0, float v1) {   // col even, < 32
+    *reinterpret_cast<float2*>(stg + r * 32 + ((((col >> 2) ^ (r & 7)) << 2) | (col & 3))) = make_float2(v0, v1);
+  }
 };
+
+// Coalesced write-out of a warp's 16-row tile that sits in shared memory (NW words per row, row stride ldw words;
+// SWZ: the XOR-swizzled staging tile): 16-byte chunks, a row's chunks on consecutive lanes -> full 128-byte lines.
+// (Storing the MMA fragments directly costs one 4/8-byte store per thread = 8 partial lines per instruction: those
+// stores were ~half of the first version's attention phase.)
+template <int NW, bool SWZ>
+__device__ __forceinline__ void flush_rows(const uint32_t* src, int ldw, void* dst, long long ld_bytes) {
+  constexpr int CH = NW / 4, RPI = 32 / CH;              // chunks per row, rows per instruction
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 16 / RPI; ++i) {
+    const int r = i * RPI + lane / CH, c = lane % CH;
+    const uint4 v = *reinterpret_cast<const uint4*>(src + r * ldw + ((SWZ ? (c ^ (r & 7)) : c) << 2));
+    *reinterpret_cast<uint4*>(reinterpret_cast<char*>(dst) + r * ld_bytes + c * 16) = v;
+  }
+  __syncwarp();
+}
 
 template <int C, class Pr>
 struct Lay {
@@ -119,7 +187,9 @@ struct Lay {
   static constexpr int QS = HS + GS_ROWS * A_LD;
   static constexpr int KS = QS + GS_ROWS * A_LD;
   static constexpr int VT = KS + GS_ROWS * A_LD;
-  static constexpr int WS = VT + C * V_LD;
+  static constexpr int PR = VT + C * V_LD;              // 2 x 13C floats: biases and LayerNorm parameters of this / the next block
+  static constexpr int SG = PR + 2 * 13 * C;            // per-warp staging tiles (16 x 32 words) for coalesced write-out
+  static constexpr int WS = SG + (GS_THREADS / 32) * 512;
   // weight-tile ring: the stream is latency-bound (one tile = 8-18 KB, L2 round trip ~1.5 us), so as many tiles as
   // shared memory allows are kept in flight
   static constexpr int STAGES = (C == 64) ? 8 : (EPW == 2 ? 5 : 3);
@@ -147,25 +217,26 @@ __device__ __forceinline__ void load_tile(const GptFwdParams& p, uint32_t* wbuf,
   }
 }
 
-// acc[NT][4] += A[64 x C] (shared, operand-typed) . Wblk[C x C]^T for this warp's 16 rows x C/2 columns.
-// `ti` is the stream index of the block's first tile; tiles ti .. ti + STAGES - 2 are already in flight.
-template <int C, class Pr>
-__device__ __forceinline__ void gemm_block(const GptFwdParams& p, uint32_t* smem, const uint32_t* A, float (*acc)[4], int& ti) {
+// acc[NT][4] += A[64 x C] (shared, operand-typed, row stride lda words) . Wblk[C x C]^T for this warp's 16 rows x C/2
+// columns.  `ti` is the stream index of the block's first tile; tiles ti .. ti + STAGES - 2 are already in flight;
+// load(wbuf, i) issues the cp.async copies of stream tile i, `total` is the length of the stream.
+template <int C, class Pr, class Loader>
+__device__ __forceinline__ void gemm_block(const Loader& load, int total, uint32_t* smem_w, const uint32_t* A, int lda,
+                                           float (*acc)[4], int& ti) {
   using L = Lay<C, Pr>;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int rb = warp & 3, chalf = warp >> 2;
-  const int total = p.L * 12 * L::TILES;
   for (int kt = 0; kt < L::TILES; ++kt, ++ti) {
     cp_async_wait<L::STAGES - 2>();                      // this thread's part of tile ti has landed
     __syncthreads();                                     // ... everyone's; and everyone is done with tile ti - 1's slot
-    if (ti + L::STAGES - 1 < total) load_tile<C, Pr>(p, smem + L::WS + ((ti + L::STAGES - 1) % L::STAGES) * L::WTILE, ti + L::STAGES - 1);
+    if (ti + L::STAGES - 1 < total) load(smem_w + ((ti + L::STAGES - 1) % L::STAGES) * L::WTILE, ti + L::STAGES - 1);
     cp_async_commit();                                   // (an empty group keeps the group count uniform)
-    const uint32_t* Wt = smem + L::WS + (ti % L::STAGES) * L::WTILE + (chalf * (C / 2) + g) * L::W_LD + t;
-    const uint32_t* Ar = A + (rb * 16 + g) * L::A_LD + kt * 32 + t;
+    const uint32_t* Wt = smem_w + (ti % L::STAGES) * L::WTILE + (chalf * (C / 2) + g) * L::W_LD + t;
+    const uint32_t* Ar = A + (rb * 16 + g) * lda + kt * 32 + t;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       uint32_t a[4];
-      a[0] = Ar[ks * 8]; a[1] = Ar[8 * L::A_LD + ks * 8]; a[2] = Ar[ks * 8 + 4]; a[3] = Ar[8 * L::A_LD + ks * 8 + 4];
+      a[0] = Ar[ks * 8]; a[1] = Ar[8 * lda + ks * 8]; a[2] = Ar[ks * 8 + 4]; a[3] = Ar[8 * lda + ks * 8 + 4];
 #pragma unroll
       for (int j = 0; j < L::NT; ++j) {
         const uint32_t b0 = Wt[j * 8 * L::W_LD + ks * 8], b1 = Wt[j * 8 * L::W_LD + ks * 8 + 4];
@@ -186,30 +257,59 @@ __device__ __forceinline__ void layernorm_slab(const float* xs, uint32_t* hs, co
   float gm[CPL], bt[CPL];
 #pragma unroll
   for (int i = 0; i < CPL; ++i) { gm[i] = gamma[lane * CPL + i]; bt[i] = beta[lane * CPL + i]; }
-#pragma unroll 2
-  for (int rr = 0; rr < 8; ++rr) {
-    const int row = warp * 8 + rr;
-    float v[CPL];
-    float s = 0.f;
+#pragma unroll 1
+  for (int r4 = 0; r4 < 8; r4 += 4) {                   // four rows in flight: the shuffle chains overlap
+    float v[4][CPL], s[4], q[4];
 #pragma unroll
-    for (int i = 0; i < CPL; ++i) { v[i] = xs[row * L::XS_LD + lane * CPL + i]; s += v[i]; }
+    for (int u = 0; u < 4; ++u) {
+      s[u] = 0.f;
 #pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mu = s / (float)C;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < CPL; ++i) { v[i] -= mu; q = fmaf(v[i], v[i], q); }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rs = rsqrtf(q / (float)C + eps);
-#pragma unroll
-    for (int i = 0; i < CPL; ++i) v[i] = fmaf(v[i] * rs, gm[i], bt[i]);
-#pragma unroll
-    for (int i = 0; i < CPL; i += 2) {
-      Pr::st_smem(hs, L::A_LD, row, lane * CPL + i, v[i], v[i + 1]);
-      Pr::st_global(hout, (row0 + row) * C + lane * CPL + i, v[i], v[i + 1]);
+      for (int i = 0; i < CPL; ++i) { v[u][i] = xs[(warp * 8 + r4 + u) * L::XS_LD + lane * CPL + i]; s[u] += v[u][i]; }
     }
-    if (lane == 0) { mean[row0 + row] = mu; rstd[row0 + row] = rs; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s[u] = s[u] / (float)C;
+      q[u] = 0.f;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) { v[u][i] -= s[u]; q[u] = fmaf(v[u][i], v[u][i], q[u]); }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) q[u] += __shfl_xor_sync(0xffffffffu, q[u], o);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int row = warp * 8 + r4 + u;
+      const float rs = rsqrtf(q[u] / (float)C + eps);
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) v[u][i] = fmaf(v[u][i] * rs, gm[i], bt[i]);
+#pragma unroll
+      for (int i = 0; i < CPL; i += 2) {
+        Pr::st_smem(hs, L::A_LD, row, lane * CPL + i, v[u][i], v[u][i + 1]);
+        Pr::st_global(hout, (row0 + row) * C + lane * CPL + i, v[u][i], v[u][i + 1]);
+      }
+      if (lane == 0) { mean[row0 + row] = s[u]; rstd[row0 + row] = rs; }
+    }
+  }
+}
+
+// biases and LayerNorm parameters of one block -> shared: [bqkv 3C | bproj C | b1 4C | b2 C | ln1 g, b | ln2 g, b]
+template <int C>
+__device__ __forceinline__ void load_params(const GptFwdParams& p, float* dst, int layer) {
+  for (int i = threadIdx.x; i < 13 * C; i += GS_THREADS) {
+    const float* src;
+    if (i < 3 * C) src = p.bias[layer][0] + i;
+    else if (i < 4 * C) src = p.bias[layer][1] + (i - 3 * C);
+    else if (i < 8 * C) src = p.bias[layer][2] + (i - 4 * C);
+    else if (i < 9 * C) src = p.bias[layer][3] + (i - 8 * C);
+    else src = p.ln[layer][(i - 9 * C) / C] + (i - 9 * C) % C;
+    cp_async4(dst + i, src);
   }
 }
 
@@ -220,6 +320,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_fwd_kernel(const __gr
   constexpr int HW = HS / EPW;                          // words per head row
   constexpr int QK_STEPS = HW / 8;                      // MMA k-steps of one score
   constexpr int NT = L::NT;
+  constexpr int NWE = (C / 2) / EPW;                    // words per row of a warp's operand-typed output tile (16 or 32)
   extern __shared__ __align__(16) uint32_t smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int slab = (int)cluster.block_rank();           // == blockIdx.x
@@ -234,25 +335,31 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_fwd_kernel(const __gr
   uint32_t* qs = smem + L::QS;
   uint32_t* ks = smem + L::KS;
   uint32_t* vt = smem + L::VT;
-  const uint32_t* ks_of[NS];
-  const uint32_t* vt_of[NS];
+  uint32_t ks_of[NS], vt_of[NS];                        // shared::cluster byte addresses of every slab's K and V^T
 #pragma unroll
-  for (int s = 0; s < NS; ++s) { ks_of[s] = cluster.map_shared_rank(ks, s); vt_of[s] = cluster.map_shared_rank(vt, s); }
+  for (int s = 0; s < NS; ++s) {
+    ks_of[s] = mapa_u32((uint32_t)__cvta_generic_to_shared(ks), s);
+    vt_of[s] = mapa_u32((uint32_t)__cvta_generic_to_shared(vt), s);
+  }
+  float* prm = reinterpret_cast<float*>(smem + L::PR);
+  uint32_t* stg = smem + L::SG + warp * 512;            // this warp's staging tile
 
   int ti = 0;                                            // weight-tile stream position
-  {
-    const int total = p.L * 12 * L::TILES;
+  const int total_tiles = p.L * 12 * L::TILES;
+  const auto loader = [&p](uint32_t* wbuf, int i) { load_tile<C, Pr>(p, wbuf, i); };
+  load_params<C>(p, prm, 0);
+  cp_async_commit();
 #pragma unroll 1
-    for (int s = 0; s < L::STAGES - 1; ++s) {
-      if (s < total) load_tile<C, Pr>(p, smem + L::WS + s * L::WTILE, s);
-      cp_async_commit();
-    }
+  for (int s = 0; s < L::STAGES - 1; ++s) {
+    if (s < total_tiles) loader(smem + L::WS + s * L::WTILE, s);
+    cp_async_commit();
   }
   // residual stream of the slab
   for (int i = threadIdx.x; i < GS_ROWS * (C / 4); i += GS_THREADS) {
     const int r = i / (C / 4), c4 = i - r * (C / 4);
     *reinterpret_cast<float4*>(xs + r * L::XS_LD + c4 * 4) = *reinterpret_cast<const float4*>(p.x0 + (row0 + r) * C + c4 * 4);
   }
+  cp_async_wait<L::STAGES - 1>();                        // the oldest group = block 0's parameters
   __syncthreads();
 
   const float keep_r = 1.0f / (1.0f - p.resid_p), keep_a = 1.0f / (1.0f - p.attn_p);
@@ -265,8 +372,10 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_fwd_kernel(const __gr
     const uint64_t seed_a = mmfn_drop_seed(p.seed + 3 * layer + 1), seed_p = mmfn_drop_seed(p.seed + 3 * layer + 2),
                    seed_m = mmfn_drop_seed(p.seed + 3 * layer + 3);
     gs_stamp(p.trace, layer * 10 + 0);
+    const float* pl = prm + (layer & 1) * 13 * C;         // this block's biases / LayerNorm parameters (shared)
+    if (layer + 1 < p.L) load_params<C>(p, prm + ((layer + 1) & 1) * 13 * C, layer + 1);   // rides in the next tile's group
     // ---- ln1
-    layernorm_slab<C, Pr>(xs, hs, p.ln[layer][0], p.ln[layer][1], reinterpret_cast<typename Pr::elem*>(p.h1) + lM * C,
+    layernorm_slab<C, Pr>(xs, hs, pl + 9 * C, pl + 10 * C, reinterpret_cast<typename Pr::elem*>(p.h1) + lM * C,
                           p.mean1 + lM, p.rstd1 + lM, row0, p.eps);
     gs_stamp(p.trace, layer * 10 + 1);
     // ---- key / query / value
@@ -276,23 +385,32 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_fwd_kernel(const __gr
       float acc[NT][4];
 #pragma unroll
       for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-      gemm_block<C, Pr>(p, smem, hs, acc, ti);
-      const float* bias = p.bias[layer][0] + part * C;
+      gemm_block<C, Pr>(loader, total_tiles, smem + L::WS, hs, L::A_LD, acc, ti);
+      const float* bias = pl + part * C;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         const int col = chalf * (C / 2) + j * 8 + 2 * t;
         const float b0 = bias[col], b1 = bias[col + 1];
         const float v00 = acc[j][0] + b0, v01 = acc[j][1] + b1, v10 = acc[j][2] + b0, v11 = acc[j][3] + b1;
-        Pr::st_global(qkv_g, (row0 + r0) * 3 * C + part * C + col, v00, v01);
-        Pr::st_global(qkv_g, (row0 + r0 + 8) * 3 * C + part * C + col, v10, v11);
-        if (part < 2) {
-          uint32_t* dst = part == 0 ? ks : qs;
-          Pr::st_smem(dst, L::A_LD, r0, col, v00, v01);
-          Pr::st_smem(dst, L::A_LD, r0 + 8, col, v10, v11);
-        } else {                                          // V^T: [dim][key of the slab]
-          Pr::st_smem_t(vt, L::V_LD, col, r0, v00); Pr::st_smem_t(vt, L::V_LD, col + 1, r0, v01);
-          Pr::st_smem_t(vt, L::V_LD, col, r0 + 8, v10); Pr::st_smem_t(vt, L::V_LD, col + 1, r0 + 8, v11);
+        if (part == 1) {
+          Pr::st_smem(qs, L::A_LD, r0, col, v00, v01);
+          Pr::st_smem(qs, L::A_LD, r0 + 8, col, v10, v11);
+        } else {
+          if (part == 0) {                                // K: head words permuted for wide DSMEM loads
+            Pr::template st_k<HS>(ks, L::A_LD, r0, col, v00, v01);
+            Pr::template st_k<HS>(ks, L::A_LD, r0 + 8, col, v10, v11);
+          } else {                                        // V^T: [dim][key of the slab], key words permuted
+            Pr::st_vt(vt, L::V_LD, col, r0, v00); Pr::st_vt(vt, L::V_LD, col + 1, r0, v01);
+            Pr::st_vt(vt, L::V_LD, col, r0 + 8, v10); Pr::st_vt(vt, L::V_LD, col + 1, r0 + 8, v11);
+          }
+          Pr::st_stage(stg, g, j * 8 + 2 * t, v00, v01);  // row-major copy for the write-out
+          Pr::st_stage(stg, g + 8, j * 8 + 2 * t, v10, v11);
         }
+      }
+      {
+        char* dst = reinterpret_cast<char*>(qkv_g + (row0 + rb * 16) * 3 * C + part * C + chalf * (C / 2));
+        if (part == 1) flush_rows<NWE, false>(qs + rb * 16 * L::A_LD + chalf * NWE, L::A_LD, dst, 3LL * C * sizeof(typename Pr::elem));
+        else flush_rows<NWE, true>(stg, 32, dst, 3LL * C * sizeof(typename Pr::elem));
       }
     }
     gs_stamp(p.trace, layer * 10 + 2);
@@ -314,13 +432,16 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_fwd_kernel(const __gr
 #pragma unroll
       for (int j = 0; j < NS * 8; ++j) sa[j][0] = sa[j][1] = sa[j][2] = sa[j][3] = 0.f;
 #pragma unroll
-      for (int s = 0; s < NS; ++s) {
-        const uint32_t* kr = ks_of[s] + g * L::A_LD + h * HW + t;
+      for (int s = 0; s < NS; ++s) {                      // one slab of 64 keys: all its K fragments in flight, then the MMAs
+        // a thread's words of a key's head row (MMA words st * 8 + t and st * 8 + t + 4) are contiguous: one load per key
+        const uint32_t kr = ks_of[s] + (uint32_t)(g * L::A_LD + h * HW + t * (HW / 4)) * 4u;
+        uint32_t kb[8][HW / 4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ldsc_words<HW / 4>(kr + (uint32_t)(j * 8 * L::A_LD) * 4u, kb[j]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
 #pragma unroll
-          for (int st = 0; st < QK_STEPS; ++st)
-            Pr::mma(sa[s * 8 + j], qf[st], kr[j * 8 * L::A_LD + st * 8], kr[j * 8 * L::A_LD + st * 8 + 4]);
+          for (int st = 0; st < QK_STEPS; ++st) Pr::mma(sa[s * 8 + j], qf[st], kb[j][2 * st], kb[j][2 * st + 1]);
         }
       }
       float m0 = -3.0e38f, m1 = -3.0e38f;
@@ -340,25 +461,42 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_fwd_kernel(const __gr
       s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
       const float i0 = 1.0f / s0, i1 = 1.0f / s1;
       // P[b, h, i, :] (and dropout(P)) to HBM for the backward; index = dropout hash key, as attn_bf16.cu
-      const long long pl = (long long)layer * p.B * NH * T * T;
-      const long long prow0 = pl + (((long long)b * NH + h) * T + slab * GS_ROWS + r0) * T, prow1 = prow0 + 8LL * T;
+      const long long pofs = (long long)layer * p.B * NH * T * T;
+      const long long prow0 = (((long long)b * NH + h) * T + slab * GS_ROWS + r0) * T, prow1 = prow0 + 8LL * T;   // hash keys
+      const long long ptile = pofs + (((long long)b * NH + h) * T + slab * GS_ROWS + rb * 16) * T;   // P[b, h, first row of the warp, 0]
       const bool drop = p.attn_p > 0.f;
+      constexpr int TPS = 4 * EPW;                        // score tiles per staging pass (64 keys bf16, 32 keys fp32)
 #pragma unroll
-      for (int j = 0; j < NS * 8; ++j) {
-        const int col = j * 8 + 2 * t;
-        sa[j][0] *= i0; sa[j][1] *= i0; sa[j][2] *= i1; sa[j][3] *= i1;
-        Pr::st_global(p.P, prow0 + col, sa[j][0], sa[j][1]);
-        Pr::st_global(p.P, prow1 + col, sa[j][2], sa[j][3]);
-        if (drop) {
+      for (int j = 0; j < NS * 8; ++j) { sa[j][0] *= i0; sa[j][1] *= i0; sa[j][2] *= i1; sa[j][3] *= i1; }
+#pragma unroll
+      for (int ps = 0; ps < NS * 8 / TPS; ++ps) {
+#pragma unroll
+        for (int jj = 0; jj < TPS; ++jj) {
+          Pr::st_stage(stg, g, jj * 8 + 2 * t, sa[ps * TPS + jj][0], sa[ps * TPS + jj][1]);
+          Pr::st_stage(stg, g + 8, jj * 8 + 2 * t, sa[ps * TPS + jj][2], sa[ps * TPS + jj][3]);
+        }
+        flush_rows<32, true>(stg, 32, reinterpret_cast<typename Pr::elem*>(p.P) + ptile + ps * TPS * 8, (long long)T * sizeof(typename Pr::elem));
+      }
+      if (drop) {
+#pragma unroll
+        for (int j = 0; j < NS * 8; ++j) {
+          const int col = j * 8 + 2 * t;
           const int sh = (col & 2) * 16;                  // 16-bit field of element col in its group of four
-          const uint64_t h0 = mmfn_hash64(seed_a, (uint64_t)((prow0 - pl) + col) >> 2) >> sh;
-          const uint64_t h1 = mmfn_hash64(seed_a, (uint64_t)((prow1 - pl) + col) >> 2) >> sh;
+          const uint64_t h0 = mmfn_hash64(seed_a, (uint64_t)(prow0 + col) >> 2) >> sh;
+          const uint64_t h1 = mmfn_hash64(seed_a, (uint64_t)(prow1 + col) >> 2) >> sh;
           sa[j][0] = ((uint32_t)h0 & 0xFFFFu) >= thr_a ? sa[j][0] * keep_a : 0.f;
           sa[j][1] = ((uint32_t)(h0 >> 16) & 0xFFFFu) >= thr_a ? sa[j][1] * keep_a : 0.f;
           sa[j][2] = ((uint32_t)h1 & 0xFFFFu) >= thr_a ? sa[j][2] * keep_a : 0.f;
           sa[j][3] = ((uint32_t)(h1 >> 16) & 0xFFFFu) >= thr_a ? sa[j][3] * keep_a : 0.f;
-          Pr::st_global(p.Pd, prow0 + col, sa[j][0], sa[j][1]);
-          Pr::st_global(p.Pd, prow1 + col, sa[j][2], sa[j][3]);
+        }
+#pragma unroll
+        for (int ps = 0; ps < NS * 8 / TPS; ++ps) {
+#pragma unroll
+          for (int jj = 0; jj < TPS; ++jj) {
+            Pr::st_stage(stg, g, jj * 8 + 2 * t, sa[ps * TPS + jj][0], sa[ps * TPS + jj][1]);
+            Pr::st_stage(stg, g + 8, jj * 8 + 2 * t, sa[ps * TPS + jj][2], sa[ps * TPS + jj][3]);
+          }
+          flush_rows<32, true>(stg, 32, reinterpret_cast<typename Pr::elem*>(p.Pd) + ptile + ps * TPS * 8, (long long)T * sizeof(typename Pr::elem));
         }
       }
       // y = dropout(P) V: the score fragments ARE the A operand
@@ -367,38 +505,56 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_fwd_kernel(const __gr
       for (int j = 0; j < HS / 8; ++j) oa[j][0] = oa[j][1] = oa[j][2] = oa[j][3] = 0.f;
       if constexpr (EPW == 2) {
 #pragma unroll
-        for (int kk = 0; kk < NS * 4; ++kk) {             // 16 keys per step = two score tiles
-          uint32_t a[4];
-          a[0] = pack_bf16(sa[2 * kk][0], sa[2 * kk][1]); a[1] = pack_bf16(sa[2 * kk][2], sa[2 * kk][3]);
-          a[2] = pack_bf16(sa[2 * kk + 1][0], sa[2 * kk + 1][1]); a[3] = pack_bf16(sa[2 * kk + 1][2], sa[2 * kk + 1][3]);
-          const uint32_t* vr = vt_of[kk >> 2] + (h * HS + g) * L::V_LD + (kk & 3) * 8 + t;
+        for (int s = 0; s < NS; ++s) {                    // one slab of 64 keys = four 16-key steps: loads first, then MMAs
+          const uint32_t vr = vt_of[s] + (uint32_t)((h * HS + g) * L::V_LD + 8 * t) * 4u;
+          uint32_t vb[HS / 8][8];                         // [2 k4 + b]: the thread's b0 / b1 words of step k4
 #pragma unroll
-          for (int jn = 0; jn < HS / 8; ++jn) Pr::mma(oa[jn], a, vr[jn * 8 * L::V_LD], vr[jn * 8 * L::V_LD + 4]);
+          for (int jn = 0; jn < HS / 8; ++jn) {
+            ldsc_words<4>(vr + (uint32_t)(jn * 8 * L::V_LD) * 4u, vb[jn]);
+            ldsc_words<4>(vr + (uint32_t)(jn * 8 * L::V_LD + 4) * 4u, vb[jn] + 4);
+          }
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int kk = s * 4 + k4;                    // 16 keys per step = two score tiles
+            uint32_t a[4];
+            a[0] = pack_bf16(sa[2 * kk][0], sa[2 * kk][1]); a[1] = pack_bf16(sa[2 * kk][2], sa[2 * kk][3]);
+            a[2] = pack_bf16(sa[2 * kk + 1][0], sa[2 * kk + 1][1]); a[3] = pack_bf16(sa[2 * kk + 1][2], sa[2 * kk + 1][3]);
+#pragma unroll
+            for (int jn = 0; jn < HS / 8; ++jn) Pr::mma(oa[jn], a, vb[jn][2 * k4], vb[jn][2 * k4 + 1]);
+          }
         }
       } else {
 #pragma unroll
-        for (int kk = 0; kk < NS * 8; ++kk) {             // 8 keys per step; MMA k index t <-> key 2t, t + 4 <-> key 2t + 1
-          uint32_t a[4];
-          a[0] = __float_as_uint(sa[kk][0]); a[1] = __float_as_uint(sa[kk][2]);
-          a[2] = __float_as_uint(sa[kk][1]); a[3] = __float_as_uint(sa[kk][3]);
-          const uint32_t* vr = vt_of[kk >> 3] + (h * HS + g) * L::V_LD + (kk & 7) * 8 + 2 * t;
+        for (int s = 0; s < NS; ++s) {                    // one slab = eight 8-key steps
+          const uint32_t vr = vt_of[s] + (uint32_t)((h * HS + g) * L::V_LD + 16 * t) * 4u;
+          uint32_t vb[HS / 8][16];                        // [2 k8 + b]
 #pragma unroll
           for (int jn = 0; jn < HS / 8; ++jn) {
-            const uint2 bb = *reinterpret_cast<const uint2*>(vr + jn * 8 * L::V_LD);
-            Pr::mma(oa[jn], a, bb.x, bb.y);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) ldsc_words<4>(vr + (uint32_t)(jn * 8 * L::V_LD + 4 * q4) * 4u, vb[jn] + 4 * q4);
+          }
+#pragma unroll
+          for (int k8 = 0; k8 < 8; ++k8) {
+            const int kk = s * 8 + k8;                    // MMA k index t <-> key 2t, t + 4 <-> key 2t + 1
+            uint32_t a[4];
+            a[0] = __float_as_uint(sa[kk][0]); a[1] = __float_as_uint(sa[kk][2]);
+            a[2] = __float_as_uint(sa[kk][1]); a[3] = __float_as_uint(sa[kk][3]);
+#pragma unroll
+            for (int jn = 0; jn < HS / 8; ++jn) Pr::mma(oa[jn], a, vb[jn][2 * k8], vb[jn][2 * k8 + 1]);
           }
         }
       }
-      typename Pr::elem* y_g = reinterpret_cast<typename Pr::elem*>(p.y) + lM * C;
 #pragma unroll
       for (int jn = 0; jn < HS / 8; ++jn) {
         const int col = h * HS + jn * 8 + 2 * t;
         Pr::st_smem(hs, L::A_LD, r0, col, oa[jn][0], oa[jn][1]);
         Pr::st_smem(hs, L::A_LD, r0 + 8, col, oa[jn][2], oa[jn][3]);
-        Pr::st_global(y_g, (row0 + r0) * C + col, oa[jn][0], oa[jn][1]);
-        Pr::st_global(y_g, (row0 + r0 + 8) * C + col, oa[jn][2], oa[jn][3]);
       }
     }
+    // the warp's two heads are its column half of y: write it out from the operand buffer
+    flush_rows<NWE, false>(hs + rb * 16 * L::A_LD + chalf * NWE, L::A_LD,
+                           reinterpret_cast<typename Pr::elem*>(p.y) + lM * C + (row0 + rb * 16) * C + chalf * (C / 2),
+                           (long long)C * sizeof(typename Pr::elem));
     gs_stamp(p.trace, layer * 10 + 4);
     cluster.sync();                                       // peers are done with this slab's K / V^T
     gs_stamp(p.trace, layer * 10 + 5);
@@ -407,8 +563,8 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_fwd_kernel(const __gr
       float acc[NT][4];
 #pragma unroll
       for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-      gemm_block<C, Pr>(p, smem, hs, acc, ti);
-      const float* bias = p.bias[layer][1];
+      gemm_block<C, Pr>(loader, total_tiles, smem + L::WS, hs, L::A_LD, acc, ti);
+      const float* bias = pl + 3 * C;
       float* x1_g = p.x1 + lM * C;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
@@ -429,14 +585,14 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_fwd_kernel(const __gr
         float2 ua = *xa, ub = *xb;
         ua.x += v[0]; ua.y += v[1]; ub.x += v[2]; ub.y += v[3];
         *xa = ua; *xb = ub;
-        *reinterpret_cast<float2*>(x1_g + (row0 + r0) * C + col) = ua;
-        *reinterpret_cast<float2*>(x1_g + (row0 + r0 + 8) * C + col) = ub;
       }
+      flush_rows<C / 2, false>(reinterpret_cast<const uint32_t*>(xs) + rb * 16 * L::XS_LD + chalf * (C / 2), L::XS_LD,
+                               x1_g + (row0 + rb * 16) * C + chalf * (C / 2), (long long)C * 4);
     }
     __syncthreads();
     gs_stamp(p.trace, layer * 10 + 6);
     // ---- ln2
-    layernorm_slab<C, Pr>(xs, hs, p.ln[layer][2], p.ln[layer][3], reinterpret_cast<typename Pr::elem*>(p.h2) + lM * C,
+    layernorm_slab<C, Pr>(xs, hs, pl + 11 * C, pl + 12 * C, reinterpret_cast<typename Pr::elem*>(p.h2) + lM * C,
                           p.mean2 + lM, p.rstd2 + lM, row0, p.eps);
     gs_stamp(p.trace, layer * 10 + 7);
     // ---- MLP: hidden chunk c = ReLU(h2 W1[c]^T + b1[c]) -> shared (Q's buffer) -> acc2 += chunk . W2[:, c]^T
@@ -450,8 +606,8 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_fwd_kernel(const __gr
         float acc[NT][4];
 #pragma unroll
         for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-        gemm_block<C, Pr>(p, smem, hs, acc, ti);
-        const float* bias = p.bias[layer][2] + c * C;
+        gemm_block<C, Pr>(loader, total_tiles, smem + L::WS, hs, L::A_LD, acc, ti);
+        const float* bias = pl + 4 * C + c * C;
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
           const int col = chalf * (C / 2) + j * 8 + 2 * t;
@@ -460,12 +616,12 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_fwd_kernel(const __gr
           const float v10 = fmaxf(acc[j][2] + b0, 0.f), v11 = fmaxf(acc[j][3] + b1, 0.f);
           Pr::st_smem(qs, L::A_LD, r0, col, v00, v01);
           Pr::st_smem(qs, L::A_LD, r0 + 8, col, v10, v11);
-          Pr::st_global(a_g, (row0 + r0) * 4 * C + c * C + col, v00, v01);
-          Pr::st_global(a_g, (row0 + r0 + 8) * 4 * C + c * C + col, v10, v11);
         }
-        gemm_block<C, Pr>(p, smem, qs, acc2, ti);   // (its first __syncthreads publishes the chunk)
+        flush_rows<NWE, false>(qs + rb * 16 * L::A_LD + chalf * NWE, L::A_LD, a_g + (row0 + rb * 16) * 4 * C + c * C + chalf * (C / 2),
+                               4LL * C * sizeof(typename Pr::elem));
+        gemm_block<C, Pr>(loader, total_tiles, smem + L::WS, qs, L::A_LD, acc2, ti);   // (its first __syncthreads publishes the chunk)
       }
-      const float* bias = p.bias[layer][3];
+      const float* bias = pl + 8 * C;
       float* xo_g = p.xout + lM * C;
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
@@ -486,9 +642,9 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_fwd_kernel(const __gr
         float2 ua = *xa, ub = *xb;
         ua.x += v[0]; ua.y += v[1]; ub.x += v[2]; ub.y += v[3];
         *xa = ua; *xb = ub;
-        *reinterpret_cast<float2*>(xo_g + (row0 + r0) * C + col) = ua;
-        *reinterpret_cast<float2*>(xo_g + (row0 + r0 + 8) * C + col) = ub;
       }
+      flush_rows<C / 2, false>(reinterpret_cast<const uint32_t*>(xs) + rb * 16 * L::XS_LD + chalf * (C / 2), L::XS_LD,
+                               xo_g + (row0 + rb * 16) * C + chalf * (C / 2), (long long)C * 4);
     }
     __syncthreads();
     gs_stamp(p.trace, layer * 10 + 8);
@@ -521,6 +677,303 @@ int launch_gpt_fwd(const GptFwdParams& p, cudaStream_t stream) {
   return mmfn_launch_status("gpt_small_fwd");
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Backward, row-local part.  Between two attention backwards everything is row-local (no token mixes with another):
+//   part A (block `hi`):  dh1 = dqkv . Wqkv ;  dx = dx1 + LayerNorm1'(dh1)                                   [3 blocks]
+//   part B (block `lo` = hi - 1):  dz = dx o mask_mlp ;  da = (dz . W2) o [a > 0] ;  dh2 = da . W1 ;
+//                                  dx1 = dx + LayerNorm2'(dh2) ;  dzp = dx1 o mask_proj ;  dy = dzp . Wproj  [9 blocks]
+// = 6 dependent launches of the per-op chain (4 dgrad GEMMs + 2 LayerNorm backward) in ONE, any 64 rows per CTA, no
+// cluster.  The products are written out for the weight-gradient GEMMs / LayerNorm parameter reductions, which are leaves
+// of the backward graph and stay on the side streams (dz, da, dzp, dqkv are their `dy` operands; dh1, dh2 the LayerNorm
+// ones); dy feeds the attention backward.  Same GEMM primitive as the forward; B operands come from TRANSPOSED weight
+// copies (mmfn_gpt_small_transpose) so that the contraction index is contiguous, as in the forward.
+struct GptBwdParams {
+  int has_a, has_b;
+  // part A
+  const void* dqkv;                            // (M, 3C) operand-typed
+  const float *dx1_in, *xa, *mean_a, *rstd_a, *gamma_a;
+  const void* wqkvT;                           // (C, 3C)
+  float *dh1, *dx_out;                         // dx_out: written when there is no part B (gradient leaving the GPT)
+  // part B
+  const float* dx2_in;                         // read when there is no part A (gradient entering the GPT's last block)
+  const void* a;                               // (M, 4C) saved MLP hidden (ReLU mask)
+  const float *x1, *mean_b, *rstd_b, *gamma_b;
+  const void *w2T, *w1T, *wpT;                 // (4C, C), (C, 4C), (C, C)
+  void *dz, *da, *dzp, *dy;                    // operand-typed (M,C), (M,4C), (M,C), (M,C)
+  float *dh2, *dx1_out;
+  float resid_p;
+  unsigned long long seed_m, seed_p;
+};
+
+template <int C, class Pr>
+struct BLay {
+  using L = Lay<C, Pr>;
+  static constexpr int EPW = Pr::EPW;
+  static constexpr int AQ_LD = 3 * C / EPW + 4;
+  static constexpr int DXS = 0;                          // fp32 [64][C + 8] gradient of the residual stream
+  static constexpr int FB = DXS + GS_ROWS * L::XS_LD;    // fp32 [64][C + 8] GEMM result entering a LayerNorm backward
+  static constexpr int AQ = FB + GS_ROWS * L::XS_LD;     // dqkv slab [64][3C]; part B: two [64][C] operand buffers
+  static constexpr int GM = AQ + GS_ROWS * AQ_LD;        // gamma of the two LayerNorms
+  static constexpr int WS = GM + 2 * C;
+  static constexpr int WORDS = WS + L::STAGES * L::WTILE;
+};
+
+// dx = dres + LayerNorm'(dh) for the slab: dh in fb (shared fp32), x / mean / rstd from global, gamma shared.
+// dres_g != null: residual gradient from global, else from dxs (in place).  Result -> dxs and (out_g != null) global.
+template <int C, class Pr>
+__device__ __forceinline__ void ln_bwd_slab(const float* fb, float* dxs, const float* x_g, const float* mean, const float* rstd,
+                                            const float* gamma, const float* dres_g, float* out_g, long long row0) {
+  using L = Lay<C, Pr>;
+  constexpr int CPL = C / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float gm[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) gm[i] = gamma[lane * CPL + i];
+#pragma unroll 1
+  for (int r4 = 0; r4 < 8; r4 += 4) {
+    float gv[4][CPL], xh[4][CPL], s1[4], s2[4], rs[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int row = warp * 8 + r4 + u;
+      const float mu = mean[row0 + row];
+      rs[u] = rstd[row0 + row];
+      s1[u] = s2[u] = 0.f;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        const float xv = x_g[(row0 + row) * C + lane * CPL + i];
+        xh[u][i] = (xv - mu) * rs[u];
+        gv[u][i] = fb[row * L::XS_LD + lane * CPL + i] * gm[i];
+        s1[u] += gv[u][i];
+        s2[u] = fmaf(gv[u][i], xh[u][i], s2[u]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s1[u] += __shfl_xor_sync(0xffffffffu, s1[u], o); s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], o); }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int row = warp * 8 + r4 + u;
+      const float m1 = s1[u] / (float)C, m2 = s2[u] / (float)C;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) {
+        const int col = lane * CPL + i;
+        float o = rs[u] * (gv[u][i] - m1 - xh[u][i] * m2);
+        o += dres_g ? dres_g[(row0 + row) * C + col] : dxs[row * L::XS_LD + col];
+        dxs[row * L::XS_LD + col] = o;
+        if (out_g) out_g[(row0 + row) * C + col] = o;
+      }
+    }
+  }
+}
+
+// abuf (operand-typed [64][C]) and out_g = dxs o dropout mask (seed, index row * C + col): the gradient entering a
+// residual branch's dropout
+template <int C, class Pr>
+__device__ __forceinline__ void masked_copy_slab(const float* dxs, uint32_t* abuf, void* out_g, long long row0, float p, uint64_t seed) {
+  using L = Lay<C, Pr>;
+  const uint32_t thr = mmfn_drop_threshold(p);
+  const float keep = 1.0f / (1.0f - p);
+  for (int i = threadIdx.x; i < GS_ROWS * (C / 4); i += GS_THREADS) {
+    const int r = i / (C / 4), c = (i - r * (C / 4)) * 4;
+    float4 v = *reinterpret_cast<const float4*>(dxs + r * L::XS_LD + c);
+    if (p > 0.f) {
+      const uint64_t h = mmfn_hash64(seed, (uint64_t)((row0 + r) * C + c) >> 2);
+      const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
+      v.x = (lo & 0xFFFFu) >= thr ? v.x * keep : 0.f;
+      v.y = (lo >> 16) >= thr ? v.y * keep : 0.f;
+      v.z = (hi & 0xFFFFu) >= thr ? v.z * keep : 0.f;
+      v.w = (hi >> 16) >= thr ? v.w * keep : 0.f;
+    }
+    Pr::st_smem(abuf, L::A_LD, r, c, v.x, v.y);
+    Pr::st_smem(abuf, L::A_LD, r, c + 2, v.z, v.w);
+    Pr::st_global(out_g, (row0 + r) * C + c, v.x, v.y);
+    Pr::st_global(out_g, (row0 + r) * C + c + 2, v.z, v.w);
+  }
+}
+
+__device__ __forceinline__ float2 ld_pair(const __nv_bfloat16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
+__device__ __forceinline__ float2 ld_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
+
+template <int C, class Pr>
+__global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_bwd_rows_kernel(const __grid_constant__ GptBwdParams p) {
+  using L = Lay<C, Pr>;
+  using BL = BLay<C, Pr>;
+  using E = typename Pr::elem;
+  constexpr int NT = L::NT;
+  constexpr int NWE = (C / 2) / L::EPW;
+  extern __shared__ __align__(16) uint32_t smem[];
+  __shared__ const E* tab_ptr[12];
+  __shared__ int tab_ld[12];
+  const long long row0 = (long long)blockIdx.x * GS_ROWS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int rb = warp & 3, chalf = warp >> 2;
+  const int r0 = rb * 16 + g;
+  float* dxs = reinterpret_cast<float*>(smem + BL::DXS);
+  float* fb = reinterpret_cast<float*>(smem + BL::FB);
+  uint32_t* aq = smem + BL::AQ;
+  uint32_t* abuf0 = aq;
+  uint32_t* abuf1 = aq + GS_ROWS * L::A_LD;
+  float* gam = reinterpret_cast<float*>(smem + BL::GM);
+  if (threadIdx.x == 0) {
+    int n = 0;
+    if (p.has_a) for (int j = 0; j < 3; ++j) { tab_ptr[n] = (const E*)p.wqkvT + j * C; tab_ld[n++] = 3 * C; }
+    if (p.has_b) {
+      for (int c = 0; c < 4; ++c) {
+        tab_ptr[n] = (const E*)p.w2T + (long long)c * C * C; tab_ld[n++] = C;
+        tab_ptr[n] = (const E*)p.w1T + c * C; tab_ld[n++] = 4 * C;
+      }
+      tab_ptr[n] = (const E*)p.wpT; tab_ld[n++] = C;
+    }
+  }
+  for (int i = threadIdx.x; i < 2 * C; i += GS_THREADS)
+    gam[i] = i < C ? (p.has_a ? p.gamma_a[i] : 0.f) : (p.has_b ? p.gamma_b[i - C] : 0.f);
+  __syncthreads();
+  const int total_tiles = (3 * p.has_a + 9 * p.has_b) * L::TILES;
+  const auto loader = [&](uint32_t* wbuf, int ti) {
+    const int blk = ti / L::TILES, kt = ti - blk * L::TILES;
+    const E* src = tab_ptr[blk] + kt * L::KT;
+    const int ldw = tab_ld[blk];
+    for (int i = threadIdx.x; i < C * 8; i += GS_THREADS) {
+      const int n = i >> 3, ch = i & 7;
+      cp_async16(wbuf + n * L::W_LD + ch * 4, reinterpret_cast<const char*>(src + (long long)n * ldw) + ch * 16);
+    }
+  };
+  int ti = 0;
+#pragma unroll 1
+  for (int s = 0; s < L::STAGES - 1; ++s) {
+    if (s < total_tiles) loader(smem + BL::WS + s * L::WTILE, s);
+    cp_async_commit();
+  }
+
+  if (p.has_a) {
+    // ---- dqkv slab -> shared (rows of 3C operand-typed elements = 3C / EPW words)
+    constexpr int RW = 3 * C / L::EPW;
+    for (int i = threadIdx.x; i < GS_ROWS * (RW / 4); i += GS_THREADS) {
+      const int r = i / (RW / 4), c4 = i - r * (RW / 4);
+      *reinterpret_cast<uint4*>(aq + r * BL::AQ_LD + c4 * 4) =
+          *reinterpret_cast<const uint4*>(reinterpret_cast<const uint32_t*>(p.dqkv) + (row0 + r) * RW + c4 * 4);
+    }
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < 3; ++j)                          // (the first tile's __syncthreads publishes the slab)
+      gemm_block<C, Pr>(loader, total_tiles, smem + BL::WS, aq + j * (C / L::EPW), BL::AQ_LD, acc, ti);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int col = chalf * (C / 2) + j * 8 + 2 * t;
+      *reinterpret_cast<float2*>(fb + r0 * L::XS_LD + col) = make_float2(acc[j][0], acc[j][1]);
+      *reinterpret_cast<float2*>(fb + (r0 + 8) * L::XS_LD + col) = make_float2(acc[j][2], acc[j][3]);
+    }
+    flush_rows<C / 2, false>(reinterpret_cast<const uint32_t*>(fb) + rb * 16 * L::XS_LD + chalf * (C / 2), L::XS_LD,
+                             p.dh1 + (row0 + rb * 16) * C + chalf * (C / 2), (long long)C * 4);
+    __syncthreads();
+    ln_bwd_slab<C, Pr>(fb, dxs, p.xa, p.mean_a, p.rstd_a, gam, p.dx1_in, p.has_b ? nullptr : p.dx_out, row0);
+    __syncthreads();
+  } else {
+    for (int i = threadIdx.x; i < GS_ROWS * (C / 4); i += GS_THREADS) {
+      const int r = i / (C / 4), c4 = i - r * (C / 4);
+      *reinterpret_cast<float4*>(dxs + r * L::XS_LD + c4 * 4) = *reinterpret_cast<const float4*>(p.dx2_in + (row0 + r) * C + c4 * 4);
+    }
+    __syncthreads();
+  }
+  if (p.has_b) {
+    // ---- dz = dx o mask of the MLP branch's dropout
+    masked_copy_slab<C, Pr>(dxs, abuf0, p.dz, row0, p.resid_p, mmfn_drop_seed(p.seed_m));
+    float acc2[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc2[j][0] = acc2[j][1] = acc2[j][2] = acc2[j][3] = 0.f;
+    const E* a_g = reinterpret_cast<const E*>(p.a);
+    E* da_g = reinterpret_cast<E*>(p.da);
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      float acc[NT][4];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+      // the ReLU mask of this thread's fragment: issue the loads before the GEMM so they are back when it ends
+      float2 m0[NT], m1[NT];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int col = c * C + chalf * (C / 2) + j * 8 + 2 * t;
+        m0[j] = ld_pair(a_g + (row0 + r0) * 4 * C + col);
+        m1[j] = ld_pair(a_g + (row0 + r0 + 8) * 4 * C + col);
+      }
+      gemm_block<C, Pr>(loader, total_tiles, smem + BL::WS, abuf0, L::A_LD, acc, ti);     // dz . W2[:, chunk c]
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        const int col = chalf * (C / 2) + j * 8 + 2 * t;
+        const float v00 = m0[j].x > 0.f ? acc[j][0] : 0.f, v01 = m0[j].y > 0.f ? acc[j][1] : 0.f;
+        const float v10 = m1[j].x > 0.f ? acc[j][2] : 0.f, v11 = m1[j].y > 0.f ? acc[j][3] : 0.f;
+        Pr::st_smem(abuf1, L::A_LD, r0, col, v00, v01);
+        Pr::st_smem(abuf1, L::A_LD, r0 + 8, col, v10, v11);
+      }
+      flush_rows<NWE, false>(abuf1 + rb * 16 * L::A_LD + chalf * NWE, L::A_LD, da_g + (row0 + rb * 16) * 4 * C + c * C + chalf * (C / 2),
+                             4LL * C * sizeof(E));
+      gemm_block<C, Pr>(loader, total_tiles, smem + BL::WS, abuf1, L::A_LD, acc2, ti);    // += da_c . W1[chunk c, :]
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int col = chalf * (C / 2) + j * 8 + 2 * t;
+      *reinterpret_cast<float2*>(fb + r0 * L::XS_LD + col) = make_float2(acc2[j][0], acc2[j][1]);
+      *reinterpret_cast<float2*>(fb + (r0 + 8) * L::XS_LD + col) = make_float2(acc2[j][2], acc2[j][3]);
+    }
+    flush_rows<C / 2, false>(reinterpret_cast<const uint32_t*>(fb) + rb * 16 * L::XS_LD + chalf * (C / 2), L::XS_LD,
+                             p.dh2 + (row0 + rb * 16) * C + chalf * (C / 2), (long long)C * 4);
+    __syncthreads();
+    ln_bwd_slab<C, Pr>(fb, dxs, p.x1, p.mean_b, p.rstd_b, gam + C, nullptr, p.dx1_out, row0);
+    __syncthreads();
+    // ---- dzp = dx1 o mask of the projection's dropout; dy = dzp . Wproj
+    masked_copy_slab<C, Pr>(dxs, abuf0, p.dzp, row0, p.resid_p, mmfn_drop_seed(p.seed_p));
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    gemm_block<C, Pr>(loader, total_tiles, smem + BL::WS, abuf0, L::A_LD, acc, ti);
+    E* dy_g = reinterpret_cast<E*>(p.dy);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int col = chalf * (C / 2) + j * 8 + 2 * t;
+      Pr::st_smem(abuf1, L::A_LD, r0, col, acc[j][0], acc[j][1]);      // (the da buffer is free: staging for the write-out)
+      Pr::st_smem(abuf1, L::A_LD, r0 + 8, col, acc[j][2], acc[j][3]);
+    }
+    flush_rows<NWE, false>(abuf1 + rb * 16 * L::A_LD + chalf * NWE, L::A_LD, dy_g + (row0 + rb * 16) * C + chalf * (C / 2), (long long)C * sizeof(E));
+  }
+  cp_async_wait_all();
+}
+
+template <int C, class Pr>
+int launch_gpt_bwd_rows(const GptBwdParams& p, long long M, cudaStream_t stream) {
+  const int smem = BLay<C, Pr>::WORDS * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(gpt_small_bwd_rows_kernel<C, Pr>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (ce != cudaSuccess) { mmfn_set_error("gpt_small_bwd_rows: shared memory attribute (%d B): %s", smem, cudaGetErrorString(ce)); return (int)ce; }
+    attr_set = true;
+  }
+  gpt_small_bwd_rows_kernel<C, Pr><<<(unsigned)(M / GS_ROWS), GS_THREADS, smem, stream>>>(p);
+  return mmfn_launch_status("gpt_small_bwd_rows");
+}
+
+// (R, Cc) row-major -> (Cc, R), batched over blockIdx.z = (block, matrix); 32 x 32 tiles through shared memory
+template <class E>
+__global__ void gpt_transpose_kernel(const void* const* __restrict__ tab, E* __restrict__ out, int C) {
+  __shared__ E tile[32][33];
+  const int layer = blockIdx.z >> 2, m = blockIdx.z & 3;
+  const int R = m == 0 ? 3 * C : (m == 2 ? 4 * C : C), Cc = m == 3 ? 4 * C : C;
+  const long long off = (long long)layer * 12 * C * C + (m == 0 ? 0 : m == 1 ? 3 : m == 2 ? 4 : 8) * (long long)C * C;
+  const int tiles_c = Cc / 32, ntiles = (R / 32) * tiles_c;
+  const E* src = reinterpret_cast<const E*>(tab[layer * 12 + m]);
+  for (int tl = blockIdx.x; tl < ntiles; tl += gridDim.x) {
+    const int tr = tl / tiles_c, tc = tl - tr * tiles_c;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) tile[i][threadIdx.x] = src[(long long)(tr * 32 + i) * Cc + tc * 32 + threadIdx.x];
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) out[off + (long long)(tc * 32 + i) * R + tr * 32 + threadIdx.x] = tile[threadIdx.x][i];
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 MMFN_DEFINE_RNG_BINDER(gpt_small)
@@ -531,7 +984,7 @@ static unsigned long long* g_gpt_trace = nullptr;
 MMFN_API int mmfn_gpt_small_trace(void* buf) { g_gpt_trace = (unsigned long long*)buf; return 0; }
 
 // All n_layer pre-LN transformer blocks of one fusion GPT (model_rad.py:112-133 x n_layer, called from :236) in one
-// launch, for n_embd C in {64, 128}, 4 heads, T in {128, 192} tokens.  dtype MMFN_BF16: bf16 operands (weights = the
+// launch, for n_embd C in {64, 128} (128: bf16 only), 4 heads, T in {128, 192} tokens.  dtype MMFN_BF16: bf16 operands (weights = the
 // bf16 shadow, saved operand tensors bf16); MMFN_TF32: fp32 storage multiplied as TF32.  x0 (B*T, C) fp32 tokens.
 // tab: HOST array of n_layer x 12 device pointers per block: weights qkv (3C,C) rows [key|query|value], proj (C,C),
 // fc1 (4C,C), fc2 (C,4C) in the operand type; their fp32 biases; ln1 gamma, beta, ln2 gamma, beta.
@@ -562,8 +1015,58 @@ MMFN_API int mmfn_gpt_small_fwd(const float* x0, int B, int T, int C, int nh, in
   }
   p.B = B; p.T = T; p.L = n_layer; p.attn_p = attn_p; p.resid_p = resid_p; p.eps = eps; p.seed = seed; p.trace = g_gpt_trace;
   const bool bf = dtype == 2;
+  // n_embd 128 as TF32 does not fit: fp32 operands double every operand buffer and leave room for only two weight tiles
+  // in flight (measured 2.3x SLOWER than the per-op chain, profiles/r02_gpt_bench_v1.json)
+  MMFN_CHECK_ARG(bf || C == 64, "gpt_small_fwd: n_embd 128 needs dtype MMFN_BF16");
   if (C == 64 && T == 128) return bf ? launch_gpt_fwd<64, 2, PrecBF>(p, stream) : launch_gpt_fwd<64, 2, PrecTF>(p, stream);
   if (C == 64 && T == 192) return bf ? launch_gpt_fwd<64, 3, PrecBF>(p, stream) : launch_gpt_fwd<64, 3, PrecTF>(p, stream);
-  if (C == 128 && T == 128) return bf ? launch_gpt_fwd<128, 2, PrecBF>(p, stream) : launch_gpt_fwd<128, 2, PrecTF>(p, stream);
-  return bf ? launch_gpt_fwd<128, 3, PrecBF>(p, stream) : launch_gpt_fwd<128, 3, PrecTF>(p, stream);
+  if (T == 128) return launch_gpt_fwd<128, 2, PrecBF>(p, stream);
+  return launch_gpt_fwd<128, 3, PrecBF>(p, stream);
+}
+
+// Transposed operand-typed copies of one fusion GPT's linear weights for mmfn_gpt_small_bwd_rows: per block
+// [Wqkv^T (C,3C) | Wproj^T (C,C) | Wfc1^T (C,4C) | Wfc2^T (4C,C)] = 12 C^2 elements, blocks back to back in `out`.
+// tab: DEVICE array of n_layer x 12 pointers laid out as mmfn_gpt_small_fwd's table (only the four weights are read).
+MMFN_API int mmfn_gpt_small_transpose(const void* const* tab_dev, int n_layer, int C, int dtype, void* out, cudaStream_t stream) {
+  MMFN_CHECK_ARG(tab_dev && out && n_layer >= 1 && n_layer <= GS_MAXL && (C == 64 || C == 128) && (dtype == 1 || dtype == 2),
+                 "gpt_small_transpose: bad arguments");
+  const dim3 grid(16, 1, n_layer * 4), block(32, 8);
+  if (dtype == 2) gpt_transpose_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(tab_dev, (__nv_bfloat16*)out, C);
+  else gpt_transpose_kernel<float><<<grid, block, 0, stream>>>(tab_dev, (float*)out, C);
+  return mmfn_launch_status("gpt_small_transpose");
+}
+
+// Row-local backward between two attention backwards of a narrow fusion GPT (see the kernel comment): part A finishes
+// block `hi` (dqkv -> dh1 -> dx through LayerNorm1), part B starts block `lo` = hi - 1 (MLP and LayerNorm2 backward,
+// projection data gradient).  has_a = 0: the chain starts at the GPT's last block from dx2_in; has_b = 0: it ends at
+// block 0 and writes dx_out.  wT_hi / wT_lo: that block's slice of mmfn_gpt_small_transpose's output.  M = B*T rows
+// (multiple of 64).  Outputs (caller-allocated): dh1 (M,C) fp32, dz / dzp / dy (M,C) and da (M,4C) operand-typed,
+// dh2 / dx1_out (M,C) fp32, dx_out (M,C) fp32.  seed_mlp / seed_proj: block lo's dropout streams (attention seed + 2, + 1).
+MMFN_API int mmfn_gpt_small_bwd_rows(int64_t M, int C, int dtype, int has_a, int has_b,
+                                     const void* dqkv, const float* dx1_in, const float* x_hi, const float* mean1, const float* rstd1,
+                                     const float* gamma1, const void* wT_hi, float* dh1, float* dx_out,
+                                     const float* dx2_in, const void* a, const float* x1, const float* mean2, const float* rstd2,
+                                     const float* gamma2, const void* wT_lo, void* dz, void* da, float* dh2, float* dx1_out,
+                                     void* dzp, void* dy, float resid_p, uint64_t seed_mlp, uint64_t seed_proj, cudaStream_t stream) {
+  MMFN_CHECK_ARG((C == 64 || C == 128) && (dtype == 2 || (dtype == 1 && C == 64)) && M > 0 && M % GS_ROWS == 0,
+                 "gpt_small_bwd_rows: needs C in {64,128} (128: bf16 only), M a positive multiple of 64");
+  MMFN_CHECK_ARG(has_a || has_b, "gpt_small_bwd_rows: nothing to do");
+  MMFN_CHECK_ARG(!has_a || (dqkv && dx1_in && x_hi && mean1 && rstd1 && gamma1 && wT_hi && dh1 && (has_b || dx_out)), "gpt_small_bwd_rows: null pointer (part A)");
+  MMFN_CHECK_ARG(!has_b || ((has_a || dx2_in) && a && x1 && mean2 && rstd2 && gamma2 && wT_lo && dz && da && dh2 && dx1_out && dzp && dy),
+                 "gpt_small_bwd_rows: null pointer (part B)");
+  MMFN_CHECK_ARG(resid_p >= 0.f && resid_p < 1.f, "gpt_small_bwd_rows: bad dropout probability");
+  const size_t es = dtype == 2 ? 2 : 4;
+  GptBwdParams p = {};
+  p.has_a = has_a; p.has_b = has_b;
+  p.dqkv = dqkv; p.dx1_in = dx1_in; p.xa = x_hi; p.mean_a = mean1; p.rstd_a = rstd1; p.gamma_a = gamma1; p.dh1 = dh1; p.dx_out = dx_out;
+  p.wqkvT = wT_hi;
+  p.dx2_in = dx2_in; p.a = a; p.x1 = x1; p.mean_b = mean2; p.rstd_b = rstd2; p.gamma_b = gamma2;
+  if (has_b) {
+    const char* w = (const char*)wT_lo;
+    p.wpT = w + (size_t)3 * C * C * es; p.w1T = w + (size_t)4 * C * C * es; p.w2T = w + (size_t)8 * C * C * es;
+  }
+  p.dz = dz; p.da = da; p.dzp = dzp; p.dy = dy; p.dh2 = dh2; p.dx1_out = dx1_out;
+  p.resid_p = resid_p; p.seed_m = seed_mlp; p.seed_p = seed_proj;
+  if (C == 64) return dtype == 2 ? launch_gpt_bwd_rows<64, PrecBF>(p, M, stream) : launch_gpt_bwd_rows<64, PrecTF>(p, M, stream);
+  return launch_gpt_bwd_rows<128, PrecBF>(p, M, stream);
 }

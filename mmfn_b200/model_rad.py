@@ -373,14 +373,23 @@ class Block:
         """dx2: gradient of the block output; dz = dx2 * dropout mask of the fc2 branch (produced by the
         LayerNorm backward that made dx2; bf16 in the bf16 configuration).  drop_prev=(p, seed) asks for the same pair
         for the block below."""
-        B, T, C, nh, hs = self.B, self.T, self.C, self.nh, self.hs
         bf = self.bf
         a = self.fc1.y
         da = self.fc2.bwd(dz, dx_mask=a, dx_bf16=bf)                  # ReLU mask fused into the dgrad GEMM
         dh2 = self.fc1.bwd(da, masked=True)
         dx1, dzp = self.ln2.bwd(dh2, dres=dx2, drop=(self.rp, self.seed + 1), drop_bf16=bf)
-        y_att = self.proj.x                                        # attention output saved by the projection
         dy = self.proj.bwd(dzp, dx_bf16=self.bfa)                  # operand of the attention-gradient products (bf16 / TF32)
+        dqkv = self.attn_bwd(dy)
+        dh1 = self.qkv.bwd(dqkv)
+        self.P = self.Pd = self.qkv_out = None
+        return self.ln1.bwd(dh1, dres=dx1, drop=drop_prev if drop_prev is not None else (0.0, 0),
+                            drop_bf16=bf and drop_prev is not None)
+
+    def attn_bwd(self, dy):
+        """dy: gradient of the attention output (B*T, C) -> dqkv (B*T, 3C) [key | query | value]"""
+        B, T, C, nh, hs = self.B, self.T, self.C, self.nh, self.hs
+        bf = self.bf
+        y_att = self.proj.x                                        # attention output saved by the projection
         qkv = self.qkv_out
         k, q, v = (self._heads(qkv, B, T, i * C) for i in range(3))
         dqkv = torch.empty(qkv.shape, device=qkv.device, dtype=torch.bfloat16 if bf else torch.float32)
@@ -400,10 +409,26 @@ class Block:
             ev_k = _Aux.fork(lambda: ops.gemm(dS.transpose(-1, -2), q.transpose(-1, -2), dk), dS, qkv, dqkv)
             ops.gemm(dS, k.transpose(-1, -2), dq)
         _Aux.wait(ev_v, ev_k)
-        dh1 = self.qkv.bwd(dqkv)
+        return dqkv
+
+    def leaves_rows_b(self, o):
+        """parameter gradients of the MLP, LayerNorm2 and the projection from the row kernel's products (side streams)"""
+        self.fc2.bwd(o["dz"], need_dx=False)
+        self.fc1.bwd(o["da"], need_dx=False, masked=True)
+        ln = self.ln2
+        _Aux.run(lambda dy=o["dh2"], x=ln.x, m=ln.mean, r=ln.rstd: ops.layernorm_bwd(dy, x, ln.g, ln.b, m, r, ln.dg, ln.db, act=0, parts=2),
+                 o["dh2"], ln.x, ln.mean, ln.rstd)
+        ln.x = None
+        self.proj.bwd(o["dzp"], need_dx=False)
+
+    def leaves_rows_a(self, dqkv, dh1):
+        """parameter gradients of the qkv linear and LayerNorm1"""
+        self.qkv.bwd(dqkv, need_dx=False)
+        ln = self.ln1
+        _Aux.run(lambda dy=dh1, x=ln.x, m=ln.mean, r=ln.rstd: ops.layernorm_bwd(dy, x, ln.g, ln.b, m, r, ln.dg, ln.db, act=0, parts=2),
+                 dh1, ln.x, ln.mean, ln.rstd)
+        ln.x = None
         self.P = self.Pd = self.qkv_out = None
-        return self.ln1.bwd(dh1, dres=dx1, drop=drop_prev if drop_prev is not None else (0.0, 0),
-                            drop_bf16=bf and drop_prev is not None)
 
 
 class FusionGPT:
@@ -419,6 +444,7 @@ class FusionGPT:
                        for i in range(cfg.n_layer)]
         self.ln_f = LayerNorm(st, prefix + ".ln_f")
         self.embd_p, self.site = cfg.embd_pdrop, site
+        self.fused, self.wT, self.tab_dev = False, None, None
 
     def fwd(self, feats, velocity, seed, train):
         B = feats[0].shape[0]
@@ -427,7 +453,8 @@ class FusionGPT:
         self.seed = seed + self.site * 100
         x = ops.tokens_fwd(feats, self.pos, self.vw, self.vb, velocity, self.ep, self.seed).view(B * self.T, self.C)
         blocks = self.blocks
-        if ops.gpt_small_ok(self.C, self.T, blocks[0].nh, len(blocks)):
+        self.fused = ops.gpt_small_ok(self.C, self.T, blocks[0].nh, len(blocks))
+        if self.fused:
             # all blocks in ONE launch (csrc/gpt_small.cu); each block adopts the tensors its backward reads
             bf = ops.BF16
             ap, rp = (blocks[0].attn_p, blocks[0].resid_p) if train else (0.0, 0.0)
@@ -443,11 +470,42 @@ class FusionGPT:
     def bwd(self, dtok_out, dfeats):
         """dtok_out (B,T,C); dfeats: per-modality feature gradients, accumulated in place."""
         blocks = self.blocks
+        if self.fused and ops.FUSE_GPT_BWD:
+            return self._bwd_fused_rows(dtok_out, dfeats)
         d, dz = self.ln_f.bwd(dtok_out.view(-1, self.C), drop=(blocks[-1].rp, blocks[-1].seed + 2), drop_bf16=blocks[-1].bf)
         for i in range(len(blocks) - 1, -1, -1):
             below = (blocks[i - 1].rp, blocks[i - 1].seed + 2) if i > 0 else None
             d, dz = blocks[i].bwd(d, dz, below)
         ops.tokens_bwd_(d, dfeats, self.shape, self.vel, self.dpos, self.dvw, self.dvb, self.ep, self.seed)
+
+
+    def _bwd_fused_rows(self, dtok_out, dfeats):
+        """Backward of a GPT whose forward ran in the whole-GPT kernel: between two attention backwards everything is
+        row-local and runs in ONE launch (mmfn_gpt_small_bwd_rows: finish block i + 1, start block i); parameter
+        gradients are leaves on the side streams, fed with the row kernel's products."""
+        blocks, C = self.blocks, self.C
+        n, M, bf = len(blocks), dtok_out.shape[0] * self.T, blocks[0].bf
+        dt = torch.bfloat16 if bf else torch.float32
+        if self.wT is None or self.wT.dtype != dt:
+            self.wT = torch.empty((n, 12 * C * C), device=dtok_out.device, dtype=dt)
+            self.tab_dev = torch.tensor([[t.data_ptr() for t in blk.params12(bf)] for blk in blocks], dtype=torch.int64, device=dtok_out.device)
+        ev = _Aux.fork(lambda: ops.gpt_small_transpose(self.tab_dev, n, C, bf, self.wT), self.wT)
+        d = self.ln_f.bwd(dtok_out.view(-1, C))
+        _Aux.wait(ev)
+        part_a = None
+        for i in range(n - 1, -1, -1):
+            blk = blocks[i]
+            part_b = dict(dx2=d if part_a is None else None, a=blk.fc1.y, x1=blk.ln2.x, mean=blk.ln2.mean, rstd=blk.ln2.rstd,
+                          gamma=blk.ln2.g, wT=self.wT[i], p=blk.rp, seed_mlp=blk.seed + 2, seed_proj=blk.seed + 1)
+            o = ops.gpt_small_bwd_rows(M, C, bf, part_a, part_b)
+            if part_a is not None:
+                blocks[i + 1].leaves_rows_a(part_a["dqkv"], o["dh1"])
+            blk.leaves_rows_b(o)
+            dqkv = blk.attn_bwd(o["dy"])
+            part_a = dict(dqkv=dqkv, dx1=o["dx1"], x=blk.ln1.x, mean=blk.ln1.mean, rstd=blk.ln1.rstd, gamma=blk.ln1.g, wT=self.wT[i])
+        o = ops.gpt_small_bwd_rows(M, C, bf, part_a, None)
+        blocks[0].leaves_rows_a(part_a["dqkv"], o["dh1"])
+        ops.tokens_bwd_(o["dx"], dfeats, self.shape, self.vel, self.dpos, self.dvw, self.dvb, self.ep, self.seed)
 
 
 class VectorNet:

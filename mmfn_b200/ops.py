@@ -751,7 +751,7 @@ FUSE_GPT = _os.environ.get("MMFN_FUSE_GPT", "0") != "0"    # off until it beats 
 
 def gpt_small_ok(C, T, nh, n_layer):
     """whole-GPT forward kernel (csrc/gpt_small.cu): the two narrow fusion transformers, tensor-core precisions only"""
-    return FUSE_GPT and (BF16 or TF32) and C in (64, 128) and T in (128, 192) and nh == 4 and 1 <= n_layer <= 12
+    return FUSE_GPT and (BF16 or (TF32 and C == 64)) and C in (64, 128) and T in (128, 192) and nh == 4 and 1 <= n_layer <= 12
 
 
 def gpt_small_fwd(x0, B, T, C, nh, layers, attn_p, resid_p, seed, eps=1e-5):
@@ -782,6 +782,41 @@ def gpt_small_fwd(x0, B, T, C, nh, layers, attn_p, resid_p, seed, eps=1e-5):
                         _p(o["mean2"]), _p(o["rstd2"]), float(attn_p), float(resid_p), int(seed), eps, _st())
     if o["Pd"] is None:
         o["Pd"] = o["P"]
+    return o
+
+
+FUSE_GPT_BWD = _os.environ.get("MMFN_FUSE_GPT_BWD", "1") != "0"
+
+
+def gpt_small_transpose(tab_dev, n_layer, C, bf, out):
+    """transposed operand-typed weight copies for gpt_small_bwd_rows; tab_dev: int64 device tensor (n_layer, 12) of pointers"""
+    lib().gpt_small_transpose(tab_dev.data_ptr(), n_layer, C, 2 if bf else 1, _p(out), _st())
+
+
+def gpt_small_bwd_rows(M, C, bf, a=None, b=None):
+    """Row-local backward between two attention backwards (csrc/gpt_small.cu).  a = dict(dqkv, dx1, x, mean, rstd, gamma,
+    wT) finishes a block; b = dict(dx2 (None when a is given), a, x1, mean, rstd, gamma, wT, p, seed_mlp, seed_proj)
+    starts the block below.  -> dict of new tensors: dh1, dx (only without b) | dz, da, dh2, dx1, dzp, dy."""
+    dev = (a or b)["wT"].device
+    dt = BF if bf else torch.float32
+    f = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+    e = lambda *shape: torch.empty(shape, device=dev, dtype=dt)
+    o = {}
+    if a is not None:
+        o["dh1"] = f(M, C)
+        if b is None:
+            o["dx"] = f(M, C)
+    if b is not None:
+        o.update(dz=e(M, C), da=e(M, 4 * C), dh2=f(M, C), dx1=f(M, C), dzp=e(M, C), dy=e(M, C))
+    A = a or {}
+    Bk = b or {}
+    g = lambda d, k: _p(d.get(k))
+    lib().gpt_small_bwd_rows(M, C, 2 if bf else 1, int(a is not None), int(b is not None),
+                             g(A, "dqkv"), g(A, "dx1"), g(A, "x"), g(A, "mean"), g(A, "rstd"), g(A, "gamma"), g(A, "wT"),
+                             _p(o.get("dh1")), _p(o.get("dx")),
+                             g(Bk, "dx2"), g(Bk, "a"), g(Bk, "x1"), g(Bk, "mean"), g(Bk, "rstd"), g(Bk, "gamma"), g(Bk, "wT"),
+                             _p(o.get("dz")), _p(o.get("da")), _p(o.get("dh2")), _p(o.get("dx1")), _p(o.get("dzp")), _p(o.get("dy")),
+                             float(Bk.get("p", 0.0)), int(Bk.get("seed_mlp", 0)), int(Bk.get("seed_proj", 0)), _st())
     return o
 
 

@@ -821,6 +821,8 @@ def test_whole_gpt_forward_kernel_matches_per_op_path(dev, prec, site, nmod, dro
     from mmfn_b200.config import GlobalConfig
     from mmfn_b200.model_rad import MMFN, _Aux
     from mmfn_b200.transfuser import TransFuser
+    if prec == "tf32" and site == 1:
+        pytest.skip("n_embd 128 is fused in the bf16 configuration only (fp32 operand buffers do not fit)")
     ops.set_precision(prec)
     try:
         cfg = GlobalConfig(embd_pdrop=drop, attn_pdrop=drop, resid_pdrop=drop)
