@@ -86,6 +86,10 @@ __device__ __forceinline__ void ldsc_words(uint32_t addr, uint32_t* out) {
   if constexpr (N == 2) { const uint2 v = ldsc2(addr); out[0] = v.x; out[1] = v.y; }
   else { const uint4 v = ldsc4(addr); out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w; }
 }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t saddr, uint32_t* r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -224,23 +228,30 @@ template <int C, class Pr, class Loader>
 __device__ __forceinline__ void gemm_block(const Loader& load, int total, uint32_t* smem_w, const uint32_t* A, int lda,
                                            float (*acc)[4], int& ti) {
   using L = Lay<C, Pr>;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rb = warp & 3, chalf = warp >> 2;
   for (int kt = 0; kt < L::TILES; ++kt, ++ti) {
     cp_async_wait<L::STAGES - 2>();                      // this thread's part of tile ti has landed
     __syncthreads();                                     // ... everyone's; and everyone is done with tile ti - 1's slot
     if (ti + L::STAGES - 1 < total) load(smem_w + ((ti + L::STAGES - 1) % L::STAGES) * L::WTILE, ti + L::STAGES - 1);
     cp_async_commit();                                   // (an empty group keeps the group count uniform)
-    const uint32_t* Wt = smem_w + (ti % L::STAGES) * L::WTILE + (chalf * (C / 2) + g) * L::W_LD + t;
-    const uint32_t* Ar = A + (rb * 16 + g) * lda + kt * 32 + t;
+    // fragments by ldmatrix: in 32-bit words an 8 x 8 b16 matrix is 8 rows x 4 words and thread (g, t) receives word t of
+    // row g -- the A / B fragment pieces of both operand types.  A: rows 0-7 / 8-15 x words 0-3 / 4-7 of the k-step;
+    // B: two column tiles x words 0-3 / 4-7.  (One instruction instead of four / four 32-bit loads.)
+    const uint32_t wt_s = (uint32_t)__cvta_generic_to_shared(smem_w + (ti % L::STAGES) * L::WTILE) +
+                          (uint32_t)((chalf * (C / 2) + (lane >> 4) * 8 + (lane & 7)) * L::W_LD + ((lane >> 3) & 1) * 4) * 4u;
+    const uint32_t a_s = (uint32_t)__cvta_generic_to_shared(A) +
+                         (uint32_t)((rb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * lda + kt * 32 + (lane >> 4) * 4) * 4u;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       uint32_t a[4];
-      a[0] = Ar[ks * 8]; a[1] = Ar[8 * lda + ks * 8]; a[2] = Ar[ks * 8 + 4]; a[3] = Ar[8 * lda + ks * 8 + 4];
+      ldmatrix_x4(a_s + ks * 32, a);
 #pragma unroll
-      for (int j = 0; j < L::NT; ++j) {
-        const uint32_t b0 = Wt[j * 8 * L::W_LD + ks * 8], b1 = Wt[j * 8 * L::W_LD + ks * 8 + 4];
-        Pr::mma(acc[j], a, b0, b1);
+      for (int j = 0; j < L::NT; j += 2) {
+        uint32_t bb[4];
+        ldmatrix_x4(wt_s + (uint32_t)(j * 8 * L::W_LD + ks * 8) * 4u, bb);
+        Pr::mma(acc[j], a, bb[0], bb[1]);
+        Pr::mma(acc[j + 1], a, bb[2], bb[3]);
       }
     }
   }
@@ -335,12 +346,6 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_fwd_kernel(const __gr
   uint32_t* qs = smem + L::QS;
   uint32_t* ks = smem + L::KS;
   uint32_t* vt = smem + L::VT;
-  uint32_t ks_of[NS], vt_of[NS];                        // shared::cluster byte addresses of every slab's K and V^T
-#pragma unroll
-  for (int s = 0; s < NS; ++s) {
-    ks_of[s] = mapa_u32((uint32_t)__cvta_generic_to_shared(ks), s);
-    vt_of[s] = mapa_u32((uint32_t)__cvta_generic_to_shared(vt), s);
-  }
   float* prm = reinterpret_cast<float*>(smem + L::PR);
   uint32_t* stg = smem + L::SG + warp * 512;            // this warp's staging tile
 
@@ -416,10 +421,39 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_fwd_kernel(const __gr
     gs_stamp(p.trace, layer * 10 + 2);
     cluster.sync();                                       // K, V^T of every slab of the sample are in place
     gs_stamp(p.trace, layer * 10 + 3);
-    // ---- attention: warp = (16 query rows, 2 heads); scores, softmax and P V in registers
+    // ---- attention: warp = (16 query rows, 2 heads); scores, softmax and P V in registers.
+    // Slabs are visited in rotated order -- the CTA's own first, peers after -- and a peer's K / V^T fragments are
+    // requested one slab ahead of their MMAs: a DSMEM round trip is ~1 us, six exposed ones per head were most of
+    // this phase in the first version.
+    int rk[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) rk[i] = slab + i >= NS ? slab + i - NS : slab + i;
+    constexpr int VPT = 64 / EPW / 4;                     // V^T words per thread, dim row and slab: 8 (bf16) / 16 (fp32)
+    uint32_t kb[2][8][HW / 4];
+    // a thread's words of a key's head row (MMA words st * 8 + t and st * 8 + t + 4) are contiguous: one load per key
+    auto load_k = [&](uint32_t (*dst)[HW / 4], int i, int h) {
+      const uint32_t base = mapa_u32((uint32_t)__cvta_generic_to_shared(ks), rk[i]) + (uint32_t)(g * L::A_LD + h * HW + t * (HW / 4)) * 4u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ldsc_words<HW / 4>(base + (uint32_t)(j * 8 * L::A_LD) * 4u, dst[j]);
+    };
+    // 16-dim heads (8 registers per slab): the next head's first K slabs are requested during this head's P V phase;
+    // the 32-dim variants have no registers to carry them across the softmax
+    constexpr bool K_EARLY = HW / 4 == 2;
+    if constexpr (K_EARLY) { load_k(kb[0], 0, chalf * 2); load_k(kb[1], 1, chalf * 2); }
 #pragma unroll 1
     for (int u = 0; u < 2; ++u) {
       const int h = chalf * 2 + u;
+      if constexpr (!K_EARLY) { load_k(kb[0], 0, h); load_k(kb[1], 1, h); }
+      const uint32_t voff = (uint32_t)((h * HS + g) * L::V_LD + VPT * t) * 4u;
+      uint32_t vb[2][HS / 8][VPT];
+      auto load_v = [&](uint32_t (*dst)[VPT], int i) {
+        const uint32_t base = mapa_u32((uint32_t)__cvta_generic_to_shared(vt), rk[i]) + voff;
+#pragma unroll
+        for (int jn = 0; jn < HS / 8; ++jn) {
+#pragma unroll
+          for (int q4 = 0; q4 < VPT / 4; ++q4) ldsc_words<4>(base + (uint32_t)(jn * 8 * L::V_LD + 4 * q4) * 4u, dst[jn] + 4 * q4);
+        }
+      };
       uint32_t qf[QK_STEPS][4];
       {
         const uint32_t* qr = qs + r0 * L::A_LD + h * HW + t;
@@ -428,22 +462,22 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_fwd_kernel(const __gr
           qf[s][0] = qr[s * 8]; qf[s][1] = qr[8 * L::A_LD + s * 8]; qf[s][2] = qr[s * 8 + 4]; qf[s][3] = qr[8 * L::A_LD + s * 8 + 4];
         }
       }
-      float sa[NS * 8][4];
+      float sa[NS * 8][4];                                // sa[8 i + j]: keys 64 rk[i] + 8 j .. + 7
 #pragma unroll
       for (int j = 0; j < NS * 8; ++j) sa[j][0] = sa[j][1] = sa[j][2] = sa[j][3] = 0.f;
-#pragma unroll
-      for (int s = 0; s < NS; ++s) {                      // one slab of 64 keys: all its K fragments in flight, then the MMAs
-        // a thread's words of a key's head row (MMA words st * 8 + t and st * 8 + t + 4) are contiguous: one load per key
-        const uint32_t kr = ks_of[s] + (uint32_t)(g * L::A_LD + h * HW + t * (HW / 4)) * 4u;
-        uint32_t kb[8][HW / 4];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ldsc_words<HW / 4>(kr + (uint32_t)(j * 8 * L::A_LD) * 4u, kb[j]);
+      auto mma_k = [&](int i, uint32_t (*src)[HW / 4]) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
 #pragma unroll
-          for (int st = 0; st < QK_STEPS; ++st) Pr::mma(sa[s * 8 + j], qf[st], kb[j][2 * st], kb[j][2 * st + 1]);
+          for (int st = 0; st < QK_STEPS; ++st) Pr::mma(sa[i * 8 + j], qf[st], src[j][2 * st], src[j][2 * st + 1]);
         }
-      }
+      };
+      mma_k(0, kb[0]);                                    // (this head's first two slabs were requested a phase ago)
+      if constexpr (NS > 2) load_k(kb[0], 2, h);
+      mma_k(1, kb[1]);
+      if constexpr (NS > 2) mma_k(2, kb[0]);
+      load_v(vb[0], 0);                                   // in flight during the softmax
+      load_v(vb[1], 1);
       float m0 = -3.0e38f, m1 = -3.0e38f;
 #pragma unroll
       for (int j = 0; j < NS * 8; ++j) { m0 = fmaxf(m0, fmaxf(sa[j][0], sa[j][1])); m1 = fmaxf(m1, fmaxf(sa[j][2], sa[j][3])); }
@@ -468,27 +502,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_fwd_kernel(const __gr
       constexpr int TPS = 4 * EPW;                        // score tiles per staging pass (64 keys bf16, 32 keys fp32)
 #pragma unroll
       for (int j = 0; j < NS * 8; ++j) { sa[j][0] *= i0; sa[j][1] *= i0; sa[j][2] *= i1; sa[j][3] *= i1; }
-#pragma unroll
-      for (int ps = 0; ps < NS * 8 / TPS; ++ps) {
-#pragma unroll
-        for (int jj = 0; jj < TPS; ++jj) {
-          Pr::st_stage(stg, g, jj * 8 + 2 * t, sa[ps * TPS + jj][0], sa[ps * TPS + jj][1]);
-          Pr::st_stage(stg, g + 8, jj * 8 + 2 * t, sa[ps * TPS + jj][2], sa[ps * TPS + jj][3]);
-        }
-        flush_rows<32, true>(stg, 32, reinterpret_cast<typename Pr::elem*>(p.P) + ptile + ps * TPS * 8, (long long)T * sizeof(typename Pr::elem));
-      }
-      if (drop) {
-#pragma unroll
-        for (int j = 0; j < NS * 8; ++j) {
-          const int col = j * 8 + 2 * t;
-          const int sh = (col & 2) * 16;                  // 16-bit field of element col in its group of four
-          const uint64_t h0 = mmfn_hash64(seed_a, (uint64_t)(prow0 + col) >> 2) >> sh;
-          const uint64_t h1 = mmfn_hash64(seed_a, (uint64_t)(prow1 + col) >> 2) >> sh;
-          sa[j][0] = ((uint32_t)h0 & 0xFFFFu) >= thr_a ? sa[j][0] * keep_a : 0.f;
-          sa[j][1] = ((uint32_t)(h0 >> 16) & 0xFFFFu) >= thr_a ? sa[j][1] * keep_a : 0.f;
-          sa[j][2] = ((uint32_t)h1 & 0xFFFFu) >= thr_a ? sa[j][2] * keep_a : 0.f;
-          sa[j][3] = ((uint32_t)(h1 >> 16) & 0xFFFFu) >= thr_a ? sa[j][3] * keep_a : 0.f;
-        }
+      auto store_probs = [&](void* dstp) {
 #pragma unroll
         for (int ps = 0; ps < NS * 8 / TPS; ++ps) {
 #pragma unroll
@@ -496,54 +510,64 @@ __global__ void __launch_bounds__(GS_THREADS, 1) gpt_small_fwd_kernel(const __gr
             Pr::st_stage(stg, g, jj * 8 + 2 * t, sa[ps * TPS + jj][0], sa[ps * TPS + jj][1]);
             Pr::st_stage(stg, g + 8, jj * 8 + 2 * t, sa[ps * TPS + jj][2], sa[ps * TPS + jj][3]);
           }
-          flush_rows<32, true>(stg, 32, reinterpret_cast<typename Pr::elem*>(p.Pd) + ptile + ps * TPS * 8, (long long)T * sizeof(typename Pr::elem));
+          const int key0 = rk[ps * TPS / 8] * 64 + (ps * TPS % 8) * 8;      // first key of this pass
+          flush_rows<32, true>(stg, 32, reinterpret_cast<typename Pr::elem*>(dstp) + ptile + key0, (long long)T * sizeof(typename Pr::elem));
+        }
+      };
+      store_probs(p.P);
+      if (drop) {
+        // one 64-bit hash covers four consecutive keys of a row = this thread's pair and its quad neighbour's: the even
+        // thread hashes row g, the odd one row g + 8, and they swap the halves the other needs
+        const long long prow_mine = (t & 1) ? prow1 : prow0;
+#pragma unroll
+        for (int j = 0; j < NS * 8; ++j) {
+          const int col = rk[j / 8] * 64 + (j % 8) * 8 + 2 * t;
+          const uint64_t hh = mmfn_hash64(seed_a, (uint64_t)(prow_mine + col) >> 2);
+          const uint32_t mine = (t & 1) ? (uint32_t)(hh >> 32) : (uint32_t)hh;      // this thread's columns, the row it hashed
+          const uint32_t give = (t & 1) ? (uint32_t)hh : (uint32_t)(hh >> 32);      // the neighbour's columns of that row
+          const uint32_t got = __shfl_xor_sync(0xffffffffu, give, 1);               // this thread's columns, the other row
+          const uint32_t f0 = (t & 1) ? got : mine, f1 = (t & 1) ? mine : got;      // rows g, g + 8
+          sa[j][0] = (f0 & 0xFFFFu) >= thr_a ? sa[j][0] * keep_a : 0.f;
+          sa[j][1] = (f0 >> 16) >= thr_a ? sa[j][1] * keep_a : 0.f;
+          sa[j][2] = (f1 & 0xFFFFu) >= thr_a ? sa[j][2] * keep_a : 0.f;
+          sa[j][3] = (f1 >> 16) >= thr_a ? sa[j][3] * keep_a : 0.f;
         }
       }
       // y = dropout(P) V: the score fragments ARE the A operand
       float oa[HS / 8][4];
 #pragma unroll
       for (int j = 0; j < HS / 8; ++j) oa[j][0] = oa[j][1] = oa[j][2] = oa[j][3] = 0.f;
-      if constexpr (EPW == 2) {
+      auto mma_v = [&](int i, uint32_t (*src)[VPT]) {
+        if constexpr (EPW == 2) {
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {                    // one slab of 64 keys = four 16-key steps: loads first, then MMAs
-          const uint32_t vr = vt_of[s] + (uint32_t)((h * HS + g) * L::V_LD + 8 * t) * 4u;
-          uint32_t vb[HS / 8][8];                         // [2 k4 + b]: the thread's b0 / b1 words of step k4
-#pragma unroll
-          for (int jn = 0; jn < HS / 8; ++jn) {
-            ldsc_words<4>(vr + (uint32_t)(jn * 8 * L::V_LD) * 4u, vb[jn]);
-            ldsc_words<4>(vr + (uint32_t)(jn * 8 * L::V_LD + 4) * 4u, vb[jn] + 4);
-          }
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            const int kk = s * 4 + k4;                    // 16 keys per step = two score tiles
+          for (int k4 = 0; k4 < 4; ++k4) {                // 16 keys per step = two score tiles; src[.][2 k4 + b] = the step's b0 / b1
+            const int kk = i * 4 + k4;
             uint32_t a[4];
             a[0] = pack_bf16(sa[2 * kk][0], sa[2 * kk][1]); a[1] = pack_bf16(sa[2 * kk][2], sa[2 * kk][3]);
             a[2] = pack_bf16(sa[2 * kk + 1][0], sa[2 * kk + 1][1]); a[3] = pack_bf16(sa[2 * kk + 1][2], sa[2 * kk + 1][3]);
 #pragma unroll
-            for (int jn = 0; jn < HS / 8; ++jn) Pr::mma(oa[jn], a, vb[jn][2 * k4], vb[jn][2 * k4 + 1]);
+            for (int jn = 0; jn < HS / 8; ++jn) Pr::mma(oa[jn], a, src[jn][2 * k4], src[jn][2 * k4 + 1]);
           }
-        }
-      } else {
+        } else {
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {                    // one slab = eight 8-key steps
-          const uint32_t vr = vt_of[s] + (uint32_t)((h * HS + g) * L::V_LD + 16 * t) * 4u;
-          uint32_t vb[HS / 8][16];                        // [2 k8 + b]
-#pragma unroll
-          for (int jn = 0; jn < HS / 8; ++jn) {
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) ldsc_words<4>(vr + (uint32_t)(jn * 8 * L::V_LD + 4 * q4) * 4u, vb[jn] + 4 * q4);
-          }
-#pragma unroll
-          for (int k8 = 0; k8 < 8; ++k8) {
-            const int kk = s * 8 + k8;                    // MMA k index t <-> key 2t, t + 4 <-> key 2t + 1
+          for (int k8 = 0; k8 < 8; ++k8) {                // 8 keys per step; MMA k index t <-> key 2t, t + 4 <-> key 2t + 1
+            const int kk = i * 8 + k8;
             uint32_t a[4];
             a[0] = __float_as_uint(sa[kk][0]); a[1] = __float_as_uint(sa[kk][2]);
             a[2] = __float_as_uint(sa[kk][1]); a[3] = __float_as_uint(sa[kk][3]);
 #pragma unroll
-            for (int jn = 0; jn < HS / 8; ++jn) Pr::mma(oa[jn], a, vb[jn][2 * k8], vb[jn][2 * k8 + 1]);
+            for (int jn = 0; jn < HS / 8; ++jn) Pr::mma(oa[jn], a, src[jn][2 * k8], src[jn][2 * k8 + 1]);
           }
         }
+      };
+      mma_v(0, vb[0]);
+      if constexpr (NS > 2) load_v(vb[0], 2);             // the last slab's V^T and the next head's first K slabs travel
+      if constexpr (K_EARLY) {                            // while dropout(P) is written out
+        if (u == 0) { load_k(kb[0], 0, h + 1); load_k(kb[1], 1, h + 1); }
       }
+      if (drop) store_probs(p.Pd);
+      mma_v(1, vb[1]);
+      if constexpr (NS > 2) mma_v(2, vb[0]);
 #pragma unroll
       for (int jn = 0; jn < HS / 8; ++jn) {
         const int col = h * HS + jn * 8 + 2 * t;

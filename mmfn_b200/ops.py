@@ -746,12 +746,17 @@ def segmax_bwd(dout, arg, G, V):
     return dx
 
 
-FUSE_GPT = _os.environ.get("MMFN_FUSE_GPT", "0") != "0"    # off until it beats the per-op chain in the step
+# whole-GPT kernels (csrc/gpt_small.cu): "1" = where they beat the per-op chain on B200 (n_embd 64: 1225 -> 908 us fwd+bwd
+# at B=32 bf16, 1037 -> 965 us at B=16 TF32), "2" = also n_embd 128 in bf16 (a wash: 1379 -> 1357 us at B=32, slower at
+# B=16; profiles/r02_gpt_bench_final.json), "0" = off
+FUSE_GPT = int(_os.environ.get("MMFN_FUSE_GPT", "1"))
 
 
 def gpt_small_ok(C, T, nh, n_layer):
-    """whole-GPT forward kernel (csrc/gpt_small.cu): the two narrow fusion transformers, tensor-core precisions only"""
-    return FUSE_GPT and (BF16 or (TF32 and C == 64)) and C in (64, 128) and T in (128, 192) and nh == 4 and 1 <= n_layer <= 12
+    """whole-GPT forward kernel + row-local backward kernel: the narrow fusion transformers, tensor-core precisions only"""
+    if not FUSE_GPT or not (BF16 or TF32) or nh != 4 or T not in (128, 192) or not 1 <= n_layer <= 12:
+        return False
+    return C == 64 or (C == 128 and BF16 and int(FUSE_GPT) >= 2)
 
 
 def gpt_small_fwd(x0, B, T, C, nh, layers, attn_p, resid_p, seed, eps=1e-5):

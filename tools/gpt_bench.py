@@ -63,7 +63,7 @@ def main():
                 dfeats = [torch.zeros_like(f) for f in feats]
                 r = dict(prec=prec, B=B, C=C, T=T)
                 for fused in (0, 1):
-                    ops.FUSE_GPT = bool(fused)
+                    ops.FUSE_GPT = 2 * fused
 
                     def fwd():
                         gpt.fwd(feats, vel, 7, True)
@@ -75,7 +75,7 @@ def main():
                     r[f"fwd_us_fused{fused}"], r[f"fwd_launches_fused{fused}"] = timed_graph(fwd)
                     r[f"fwdbwd_us_fused{fused}"], r[f"fwdbwd_launches_fused{fused}"] = timed_graph(fwd_bwd)
                 # phase timeline of the first CTA (one eager launch): ns per phase, averaged over blocks 1..7
-                ops.FUSE_GPT = True
+                ops.FUSE_GPT = 2
                 tr = torch.zeros(10 * 8, dtype=torch.int64, device=dev)
                 lib().gpt_small_trace(tr.data_ptr())
                 gpt.fwd(feats, vel, 7, True)
@@ -88,7 +88,7 @@ def main():
                 out.append(r)
                 print(json.dumps(r), flush=True)
         del model
-    ops.FUSE_GPT = True
+    ops.FUSE_GPT = 1
     ops.set_precision("tf32")
     print(json.dumps(out))
 

@@ -16,7 +16,7 @@ site = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 32
 dev = torch.device("cuda:0")
 ops.set_precision(prec)
-ops.FUSE_GPT = True
+ops.FUSE_GPT = 2
 model = MMFN(GlobalConfig(), dev)
 if prec == "bf16":
     model.store.sync_shadow()
