@@ -108,12 +108,14 @@ class _Lib:
 
     @staticmethod
     def kernel_class(fn, work):
-        """conv | linear | attention (tensor-pipe bound) | hbm (everything else: normalisation, pooling, scatter,
+        """conv | linear | attention | fused_gpt (tensor-pipe bound) | hbm (everything else: normalisation, pooling, scatter,
         optimizer ...).  Batched GEMMs are the attention products (QK^T, PV and their gradients)."""
         if fn.startswith("conv2d_"):
             return "conv"
         if fn.startswith("attention_"):
             return "attention"
+        if fn.startswith("gpt_small_") and fn != "gpt_small_transpose":
+            return "fused_gpt"          # whole-GPT forward / row-local backward (linears + attention of the narrow transformers)
         if fn.startswith("gemm_"):
             return "attention" if (work and len(work) >= 6 and work[5] > 1) else "linear"
         return "hbm"

@@ -816,6 +816,7 @@ def gpt_small_bwd_rows(M, C, bf, a=None, b=None):
     A = a or {}
     Bk = b or {}
     g = lambda d, k: _p(d.get(k))
+    lib().next_work = (2.0 * M * C * C * (3 * (a is not None) + 9 * (b is not None)), 0.0, M, C)
     lib().gpt_small_bwd_rows(M, C, 2 if bf else 1, int(a is not None), int(b is not None),
                              g(A, "dqkv"), g(A, "dx1"), g(A, "x"), g(A, "mean"), g(A, "rstd"), g(A, "gamma"), g(A, "wT"),
                              _p(o.get("dh1")), _p(o.get("dx")),
