@@ -34,6 +34,9 @@ for (H, Cc) in [(16, 256), (64, 64)]:
     dy = torch.randn(B, H, H, Cc, device=dev); dw = torch.zeros_like(w)
     run(lambda: ops.conv2d_fwd(x, w, 1, 1))
     run(lambda: ops.conv2d_wgrad_(dy, x, dw, 1, 1))
+# 3b. layer-4 3x3 convolution 512->512 @8x8 (M = 1024 rows: the generic implicit-GEMM kernel, BatchNorm statistics not fused)
+x4 = torch.randn(B, 8, 8, 512, device=dev); w4 = torch.randn(512, 3, 3, 512, device=dev) * 0.02
+run(lambda: ops.conv2d_fwd(x4, w4, 1, 1))
 # 4. fused attention, transformer4 geometry
 qkv = torch.randn(B * 256, 3 * 512, device=dev)
 run(lambda: ops.attention_fwd(qkv, B, 256, 512, 4, 0.1, 7))
