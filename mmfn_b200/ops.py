@@ -826,6 +826,24 @@ def gpt_small_bwd_rows(M, C, bf, a=None, b=None):
     return o
 
 
+FUSE_ATTN_BWD_SMALL = _os.environ.get("MMFN_FUSE_ATTN_BWD_SMALL", "1") != "0"
+
+
+def attention_bwd_small_ok(T, C, nh, p):
+    """one-launch attention backward (csrc/attn_bwd_small.cu): bf16, heads of 16 / 32 dims, T in {128, 192}"""
+    return FUSE_ATTN_BWD_SMALL and p.dtype == BF and C % nh == 0 and (C // nh) in (16, 32) and T in (128, 192)
+
+
+def attention_bwd_small(qkv, dy, P, Pd, B, T, C, nh):
+    """qkv (B*T, 3C), dy (B*T, C), P / Pd (B, nh, T, T), all bf16 -> dqkv (B*T, 3C) bf16"""
+    assert qkv.is_contiguous() and dy.is_contiguous() and P.is_contiguous() and Pd.is_contiguous()
+    assert qkv.dtype == BF and dy.dtype == BF and P.dtype == BF and Pd.dtype == BF and P.shape == (B, nh, T, T)
+    dqkv = torch.empty_like(qkv)
+    lib().next_work = (8.0 * B * nh * T * T * (C // nh), 2.0 * (B * T * 7 * C + 2 * B * nh * T * T), B, T, C, nh)
+    lib().attention_bwd_small_bf16(_p(qkv), _p(dy), _p(P), _p(Pd), _p(dqkv), B, T, C, nh, _st())
+    return dqkv
+
+
 FUSE_SUBGRAPH = _os.environ.get("MMFN_FUSE_SUBGRAPH", "1") != "0"
 SUBGRAPH_FUSED_V = (9, 19)       # vectors per polyline the one-launch Subgraph forward is instantiated for
 
