@@ -1,4 +1,4 @@
-// Attention backward of the narrow fusion transformers (heads of 16 / 32 dims, T = 128 / 192 tokens) in ONE launch,
+// Attention backward of fusion transformers 1-3 (heads of 16 / 32 / 64 dims, T = 128 / 192 tokens) in ONE launch,
 // bf16 configuration (reference: autograd through SelfAttention.forward, model_rad.py:96-105).
 //
 // The per-op chain is five launches per block -- dPd = dY V^T, softmax backward, dQ = dS K on the critical path, dV =
@@ -42,12 +42,15 @@ __global__ void __launch_bounds__(NQ * 32, 1)
 attn_bwd_small_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ P,
                       const __nv_bfloat16* __restrict__ Pd, __nv_bfloat16* __restrict__ dqkv, int C, int nh, float scale) {
   constexpr int T = NQ * 16, LH = HS + 8, LT = T + 8, NTH = NQ * 32;
+  // 64-dim heads: q, k, v do not fit next to the two T x T tiles -- they take turns in ONE buffer (v for dPd, then k for
+  // dQ, then q for dK), two extra L2 round trips per CTA
+  constexpr bool STAGED = HS > 32;
   extern __shared__ __align__(16) __nv_bfloat16 sm[];
-  __nv_bfloat16* qs = sm;
-  __nv_bfloat16* ks = qs + T * LH;
-  __nv_bfloat16* vs = ks + T * LH;
-  __nv_bfloat16* ds = vs + T * LH;
-  __nv_bfloat16* SB = ds + T * LH;
+  __nv_bfloat16* ds = sm;
+  __nv_bfloat16* vs = ds + T * LH;
+  __nv_bfloat16* ks = STAGED ? vs : vs + T * LH;
+  __nv_bfloat16* qs = STAGED ? vs : ks + T * LH;
+  __nv_bfloat16* SB = (STAGED ? vs : qs) + T * LH;
   __nv_bfloat16* PB = SB + T * LT;
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -58,8 +61,10 @@ attn_bwd_small_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
     for (int i = threadIdx.x; i < T * CH; i += NTH) {
       const int r = i / CH, c = i - r * CH;
       const __nv_bfloat16* src = qkv + (row0 + r) * 3 * C + h * HS + c * 8;
-      cp_async16(ks + r * LH + c * 8, src);
-      cp_async16(qs + r * LH + c * 8, src + C);
+      if constexpr (!STAGED) {
+        cp_async16(ks + r * LH + c * 8, src);
+        cp_async16(qs + r * LH + c * 8, src + C);
+      }
       cp_async16(vs + r * LH + c * 8, src + 2 * C);
       cp_async16(ds + r * LH + c * 8, dy + (row0 + r) * C + h * HS + c * 8);
     }
@@ -122,6 +127,16 @@ attn_bwd_small_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
       SBo[w0 + j * 4] = dsp[j][0];
       SBo[w1 + j * 4] = dsp[j][1];
     }
+    if constexpr (STAGED) {                               // v is done: k takes its place
+      __syncthreads();
+      for (int i = threadIdx.x; i < T * (HS / 8); i += NTH) {
+        const int r = i / (HS / 8), c = i - r * (HS / 8);
+        cp_async16(ks + r * LH + c * 8, qkv + (row0 + r) * 3 * C + h * HS + c * 8);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+    }
     // dq[q, dim] = sum_key dS[q, key] k[key, dim]: A from the registers, B = k read transposed
     float dq[HS / 8][4];
 #pragma unroll
@@ -145,6 +160,15 @@ attn_bwd_small_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
     }
   }
   __syncthreads();
+  if constexpr (STAGED) {                                 // k is done: q takes its place
+    for (int i = threadIdx.x; i < T * (HS / 8); i += NTH) {
+      const int r = i / (HS / 8), c = i - r * (HS / 8);
+      cp_async16(qs + r * LH + c * 8, qkv + (row0 + r) * 3 * C + C + h * HS + c * 8);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
   // ================= phase 2: this warp's 16 keys =================
   {
     const int k0 = warp * 16;
@@ -185,7 +209,7 @@ attn_bwd_small_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16
 template <int HS, int NQ>
 int launch_attn_bwd_small(const void* qkv, const void* dy, const void* P, const void* Pd, void* dqkv, int B, int C, int nh, cudaStream_t stream) {
   constexpr int T = NQ * 16;
-  const int smem = (4 * T * (HS + 8) + 2 * T * (T + 8)) * 2;
+  const int smem = ((HS > 32 ? 2 : 4) * T * (HS + 8) + 2 * T * (T + 8)) * 2;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t ce = cudaFuncSetAttribute(attn_bwd_small_kernel<HS, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -202,16 +226,18 @@ int launch_attn_bwd_small(const void* qkv, const void* dy, const void* P, const 
 
 // Whole attention backward of one transformer block for small heads, bf16: qkv (B*T, 3C) [key | query | value], dy (B*T, C)
 // gradient of the attention output, P / Pd (B, nh, T, T) saved probabilities before / after dropout (the same tensor when
-// there was no dropout) -> dqkv (B*T, 3C), every element written.  Head size C / nh in {16, 32}, T in {128, 192}.
+// there was no dropout) -> dqkv (B*T, 3C), every element written.  Head size C / nh in {16, 32, 64}, T in {128, 192}.
 MMFN_API int mmfn_attention_bwd_small_bf16(const void* qkv, const void* dy, const void* P, const void* Pd, void* dqkv,
                                            int B, int T, int C, int nh, cudaStream_t stream) {
   MMFN_CHECK_ARG(qkv && dy && P && Pd && dqkv, "attention_bwd_small: null pointer");
-  MMFN_CHECK_ARG(B >= 1 && B <= 65535 && nh >= 1 && C % nh == 0 && (C / nh == 16 || C / nh == 32) && (T == 128 || T == 192),
-                 "attention_bwd_small: needs head size 16 or 32 and T in {128, 192}");
+  MMFN_CHECK_ARG(B >= 1 && B <= 65535 && nh >= 1 && C % nh == 0 && (C / nh == 16 || C / nh == 32 || C / nh == 64) && (T == 128 || T == 192),
+                 "attention_bwd_small: needs head size 16, 32 or 64 and T in {128, 192}");
   MMFN_CHECK_ARG((((uintptr_t)qkv | (uintptr_t)dy | (uintptr_t)P | (uintptr_t)Pd | (uintptr_t)dqkv) & 15) == 0, "attention_bwd_small: 16-byte alignment");
   const int hs = C / nh;
   if (hs == 16) return T == 192 ? launch_attn_bwd_small<16, 12>(qkv, dy, P, Pd, dqkv, B, C, nh, stream)
                                 : launch_attn_bwd_small<16, 8>(qkv, dy, P, Pd, dqkv, B, C, nh, stream);
-  return T == 192 ? launch_attn_bwd_small<32, 12>(qkv, dy, P, Pd, dqkv, B, C, nh, stream)
-                  : launch_attn_bwd_small<32, 8>(qkv, dy, P, Pd, dqkv, B, C, nh, stream);
+  if (hs == 32) return T == 192 ? launch_attn_bwd_small<32, 12>(qkv, dy, P, Pd, dqkv, B, C, nh, stream)
+                                : launch_attn_bwd_small<32, 8>(qkv, dy, P, Pd, dqkv, B, C, nh, stream);
+  return T == 192 ? launch_attn_bwd_small<64, 12>(qkv, dy, P, Pd, dqkv, B, C, nh, stream)
+                  : launch_attn_bwd_small<64, 8>(qkv, dy, P, Pd, dqkv, B, C, nh, stream);
 }

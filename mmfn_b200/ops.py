@@ -830,8 +830,8 @@ FUSE_ATTN_BWD_SMALL = _os.environ.get("MMFN_FUSE_ATTN_BWD_SMALL", "1") != "0"
 
 
 def attention_bwd_small_ok(T, C, nh, p):
-    """one-launch attention backward (csrc/attn_bwd_small.cu): bf16, heads of 16 / 32 dims, T in {128, 192}"""
-    return FUSE_ATTN_BWD_SMALL and p.dtype == BF and C % nh == 0 and (C // nh) in (16, 32) and T in (128, 192)
+    """one-launch attention backward (csrc/attn_bwd_small.cu): bf16, heads of 16 / 32 / 64 dims, T in {128, 192}"""
+    return FUSE_ATTN_BWD_SMALL and p.dtype == BF and C % nh == 0 and (C // nh) in (16, 32, 64) and T in (128, 192)
 
 
 def attention_bwd_small(qkv, dy, P, Pd, B, T, C, nh):

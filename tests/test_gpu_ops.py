@@ -809,7 +809,7 @@ def test_stem_conv_bf16_column_matrix(C):
     close(dw.permute(0, 3, 1, 2), wr.grad, 3e-3)
 
 
-@pytest.mark.parametrize("T,C", [(192, 64), (192, 128), (128, 64), (128, 128)])
+@pytest.mark.parametrize("T,C", [(192, 64), (192, 128), (128, 64), (128, 128), (192, 256), (128, 256)])
 @pytest.mark.parametrize("drop", [0.0, 0.1])
 def test_attention_bwd_small_bf16_matches_the_formulas(T, C, drop):
     """csrc/attn_bwd_small.cu (dPd, softmax backward, dQ, dK, dV of one block in one launch) against the same formulas in
