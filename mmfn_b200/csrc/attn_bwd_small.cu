@@ -11,6 +11,7 @@
 //   phase 2, warp = 16 keys:     dk = dS^T q and dv = Pd^T dy, the transposed operands fetched with ldmatrix.trans.
 // No atomics, no cross-CTA traffic, deterministic.  TF32 (fp32 P: 2 x 147 KB) does not fit and keeps the per-op chain.
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace {
 
@@ -222,6 +223,206 @@ int launch_attn_bwd_small(const void* qkv, const void* dy, const void* P, const 
   return mmfn_launch_status("attention_bwd_small");
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// TF32 configuration (fp32 tensors, tf32 m16n8k8 MMAs): two fp32 T x T tiles do not fit in one CTA, so a CLUSTER OF TWO
+// CTAs owns a (sample, head): CTA r holds P / Pd of queries [r T/2, (r+1) T/2), computes their dS and dQ, then the
+// partial dK / dV of ALL keys over its queries; the halves are exchanged through distributed shared memory (each CTA
+// finishes the keys of its own half).  q, k, v take turns in one buffer.  Operand fragments that need a transposed view
+// are fetched with 32-bit shared loads (ldmatrix.trans works on 16-bit elements only); strides keep them conflict-free.
+__device__ __forceinline__ void mma_tf32(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// NW warps per CTA, TQ = 16 NW queries per CTA, T = 2 TQ tokens.  Shared memory (fp32): dy [T][HS + 4], staged q / k / v
+// [T][HS + 4], SB (P -> dS) and PB (Pd) [TQ][T + 8].
+template <int HS, int NW>
+__global__ void __launch_bounds__(NW * 32, 1)
+attn_bwd_small_tf32_kernel(const float* __restrict__ qkv, const float* __restrict__ dy, const float* __restrict__ P,
+                           const float* __restrict__ Pd, float* __restrict__ dqkv, int C, int nh, float scale) {
+  constexpr int TQ = NW * 16, T = 2 * TQ, LH = HS + 4, LT = T + 8, NTH = NW * 32;
+  extern __shared__ __align__(16) float smf[];
+  float* ds = smf;
+  float* xb = ds + T * LH;
+  float* SB = xb + T * LH;
+  float* PB = SB + TQ * LT;
+  namespace cgx = cooperative_groups;
+  cgx::cluster_group cluster = cgx::this_cluster();
+  const int r = (int)cluster.block_rank();                // which half of the queries
+  const int h = blockIdx.x >> 1, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int l7 = lane & 7, l3 = (lane >> 3) & 1, l4 = lane >> 4;
+  const long long row0 = (long long)b * T;
+  auto load_head = [&](float* dst, const float* src, long long ld) {     // [T][HS] slice of a (rows, ld) matrix
+    for (int i = threadIdx.x; i < T * (HS / 4); i += NTH) {
+      const int rr = i / (HS / 4), c = i - rr * (HS / 4);
+      cp_async16(dst + rr * LH + c * 4, src + (row0 + rr) * ld + c * 4);
+    }
+  };
+  load_head(ds, dy + h * HS, C);
+  load_head(xb, qkv + 2 * C + h * HS, 3LL * C);           // v
+  {
+    const long long pbase = (((long long)b * nh + h) * T + r * TQ) * T;
+    for (int i = threadIdx.x; i < TQ * (T / 4); i += NTH) {
+      const int rr = i / (T / 4), c = i - rr * (T / 4);
+      cp_async16(SB + rr * LT + c * 4, P + pbase + (long long)rr * T + c * 4);
+      cp_async16(PB + rr * LT + c * 4, Pd + pbase + (long long)rr * T + c * 4);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const uint32_t ds_s = (uint32_t)__cvta_generic_to_shared(ds), xb_s = (uint32_t)__cvta_generic_to_shared(xb);
+  const uint32_t* xbw = reinterpret_cast<const uint32_t*>(xb);
+  const uint32_t* dsw = reinterpret_cast<const uint32_t*>(ds);
+
+  // ================= phase 1: this warp's 16 queries =================
+  const int lq = warp * 16, gq = r * TQ + lq;             // local / in-sample query row
+  float dsv[T / 8][4];                                    // dPd, then dS (C-fragment layout)
+  {
+    uint32_t ady[HS / 8][4];
+#pragma unroll
+    for (int s = 0; s < HS / 8; ++s)
+      ldm_x4(ds_s + (uint32_t)((gq + l7 + l3 * 8) * LH + s * 8 + l4 * 4) * 4u, ady[s]);
+#pragma unroll
+    for (int j = 0; j < T / 8; ++j) dsv[j][0] = dsv[j][1] = dsv[j][2] = dsv[j][3] = 0.f;
+#pragma unroll
+    for (int j = 0; j < T / 8; j += 2) {
+#pragma unroll
+      for (int s = 0; s < HS / 8; ++s) {
+        uint32_t bb[4];
+        ldm_x4(xb_s + (uint32_t)((j * 8 + l4 * 8 + l7) * LH + s * 8 + l3 * 4) * 4u, bb);
+        mma_tf32(dsv[j], ady[s], bb[0], bb[1]);
+        mma_tf32(dsv[j + 1], ady[s], bb[2], bb[3]);
+      }
+    }
+    float r0 = 0.f, r1 = 0.f;
+    float* sb0 = SB + (lq + g) * LT + 2 * t;
+    const float* pb0 = PB + (lq + g) * LT + 2 * t;
+#pragma unroll
+    for (int j = 0; j < T / 8; ++j) {
+      const float2 pd0 = *reinterpret_cast<const float2*>(pb0 + j * 8), pd1 = *reinterpret_cast<const float2*>(pb0 + 8 * LT + j * 8);
+      dsv[j][0] *= pd0.x; dsv[j][1] *= pd0.y; dsv[j][2] *= pd1.x; dsv[j][3] *= pd1.y;
+      r0 += dsv[j][0] + dsv[j][1]; r1 += dsv[j][2] + dsv[j][3];
+    }
+    r0 += __shfl_xor_sync(0xffffffffu, r0, 1); r0 += __shfl_xor_sync(0xffffffffu, r0, 2);
+    r1 += __shfl_xor_sync(0xffffffffu, r1, 1); r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+#pragma unroll
+    for (int j = 0; j < T / 8; ++j) {
+      const float2 p0 = *reinterpret_cast<const float2*>(sb0 + j * 8), p1 = *reinterpret_cast<const float2*>(sb0 + 8 * LT + j * 8);
+      dsv[j][0] = scale * (dsv[j][0] - p0.x * r0); dsv[j][1] = scale * (dsv[j][1] - p0.y * r0);
+      dsv[j][2] = scale * (dsv[j][2] - p1.x * r1); dsv[j][3] = scale * (dsv[j][3] - p1.y * r1);
+      *reinterpret_cast<float2*>(sb0 + j * 8) = make_float2(dsv[j][0], dsv[j][1]);
+      *reinterpret_cast<float2*>(sb0 + 8 * LT + j * 8) = make_float2(dsv[j][2], dsv[j][3]);
+    }
+  }
+  __syncthreads();                                        // v is done: k takes its place
+  load_head(xb, qkv + h * HS, 3LL * C);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  {
+    // dq = dS k: A = the score fragments (MMA k index t <-> key 8j + 2t, t + 4 <-> key 8j + 2t + 1), B = k rows 8j + 2t (+1)
+    float dq[HS / 8][4];
+#pragma unroll
+    for (int j = 0; j < HS / 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f;
+#pragma unroll
+    for (int j = 0; j < T / 8; ++j) {
+      const uint32_t a[4] = {__float_as_uint(dsv[j][0]), __float_as_uint(dsv[j][2]), __float_as_uint(dsv[j][1]), __float_as_uint(dsv[j][3])};
+      const uint32_t* kr = xbw + (j * 8 + 2 * t) * LH + g;
+#pragma unroll
+      for (int jn = 0; jn < HS / 8; ++jn) mma_tf32(dq[jn], a, kr[jn * 8], kr[LH + jn * 8]);
+    }
+#pragma unroll
+    for (int j = 0; j < HS / 8; ++j) {
+      float* o = dqkv + (row0 + gq + g) * 3 * C + C + h * HS + j * 8 + 2 * t;
+      *reinterpret_cast<float2*>(o) = make_float2(dq[j][0], dq[j][1]);
+      *reinterpret_cast<float2*>(o + 8LL * 3 * C) = make_float2(dq[j][2], dq[j][3]);
+    }
+  }
+  __syncthreads();                                        // k is done: q takes its place; every warp's dS is in SB
+  load_head(xb, qkv + C + h * HS, 3LL * C);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // ================= phase 2: partial dK / dV of two 16-key blocks over this CTA's queries =================
+  float acc[2][2][HS / 8][4];                             // [mine / theirs][dk / dv]
+#pragma unroll
+  for (int w2 = 0; w2 < 2; ++w2) {
+    const int k0 = ((w2 == 0 ? r : 1 - r) * NW + warp) * 16;
+#pragma unroll
+    for (int jn = 0; jn < HS / 8; ++jn) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[w2][0][jn][i] = acc[w2][1][jn][i] = 0.f;
+    }
+    const uint32_t* sbw = reinterpret_cast<const uint32_t*>(SB) + k0 + g;
+    const uint32_t* pbw = reinterpret_cast<const uint32_t*>(PB) + k0 + g;
+#pragma unroll 2
+    for (int qs = 0; qs < TQ / 8; ++qs) {
+      // A[m = key][k = query] = X[query][key]: a0 (key g, query t), a1 (key g + 8, t), a2 (g, t + 4), a3 (g + 8, t + 4)
+      const int o0 = (qs * 8 + t) * LT, o1 = o0 + 4 * LT;
+      const uint32_t as[4] = {sbw[o0], sbw[o0 + 8], sbw[o1], sbw[o1 + 8]};
+      const uint32_t ap[4] = {pbw[o0], pbw[o0 + 8], pbw[o1], pbw[o1 + 8]};
+      const int qrow = (r * TQ + qs * 8 + t) * LH + g;    // B[k = query][n = dim]: rows t, t + 4 of the step
+#pragma unroll
+      for (int jn = 0; jn < HS / 8; ++jn) {
+        mma_tf32(acc[w2][0][jn], as, xbw[qrow + jn * 8], xbw[qrow + 4 * LH + jn * 8]);
+        mma_tf32(acc[w2][1][jn], ap, dsw[qrow + jn * 8], dsw[qrow + 4 * LH + jn * 8]);
+      }
+    }
+  }
+  // ---- exchange: the other CTA finishes "theirs"; its partial for "mine" comes back the same way
+  __syncthreads();                                        // SB is free: it carries the exported fragments [warp][dk/dv][tile][lane][4]
+  float4* xp = reinterpret_cast<float4*>(SB);
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {
+#pragma unroll
+    for (int jn = 0; jn < HS / 8; ++jn)
+      xp[((warp * 2 + w) * (HS / 8) + jn) * 32 + lane] = make_float4(acc[1][w][jn][0], acc[1][w][jn][1], acc[1][w][jn][2], acc[1][w][jn][3]);
+  }
+  cluster.sync();
+  const float4* xpeer = cluster.map_shared_rank(xp, 1 - r);
+  const int k0 = (r * NW + warp) * 16;
+#pragma unroll
+  for (int w = 0; w < 2; ++w) {
+#pragma unroll
+    for (int jn = 0; jn < HS / 8; ++jn) {
+      const float4 o = xpeer[((warp * 2 + w) * (HS / 8) + jn) * 32 + lane];
+      float* dst = dqkv + (row0 + k0 + g) * 3 * C + (w == 0 ? 0 : 2 * C) + h * HS + jn * 8 + 2 * t;
+      *reinterpret_cast<float2*>(dst) = make_float2(acc[0][w][jn][0] + o.x, acc[0][w][jn][1] + o.y);
+      *reinterpret_cast<float2*>(dst + 8LL * 3 * C) = make_float2(acc[0][w][jn][2] + o.z, acc[0][w][jn][3] + o.w);
+    }
+  }
+  cluster.sync();                                         // the peer may still be reading this CTA's shared memory
+}
+
+template <int HS, int NW>
+int launch_attn_bwd_small_tf32(const void* qkv, const void* dy, const void* P, const void* Pd, void* dqkv, int B, int C, int nh, cudaStream_t stream) {
+  constexpr int TQ = NW * 16, T = 2 * TQ;
+  const int smem = (2 * T * (HS + 4) + 2 * TQ * (T + 8)) * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t ce = cudaFuncSetAttribute(attn_bwd_small_tf32_kernel<HS, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (ce != cudaSuccess) { mmfn_set_error("attention_bwd_small_tf32: shared memory attribute (%d B): %s", smem, cudaGetErrorString(ce)); return (int)ce; }
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * nh, B, 1);
+  cfg.blockDim = dim3(NW * 32, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t ce = cudaLaunchKernelEx(&cfg, attn_bwd_small_tf32_kernel<HS, NW>, (const float*)qkv, (const float*)dy, (const float*)P,
+                                      (const float*)Pd, (float*)dqkv, C, nh, rsqrtf((float)HS));
+  if (ce != cudaSuccess) { mmfn_set_error("attention_bwd_small_tf32: launch: %s", cudaGetErrorString(ce)); return (int)ce; }
+  return mmfn_launch_status("attention_bwd_small_tf32");
+}
+
 }  // namespace
 
 // Whole attention backward of one transformer block for small heads, bf16: qkv (B*T, 3C) [key | query | value], dy (B*T, C)
@@ -240,4 +441,18 @@ MMFN_API int mmfn_attention_bwd_small_bf16(const void* qkv, const void* dy, cons
                                 : launch_attn_bwd_small<32, 8>(qkv, dy, P, Pd, dqkv, B, C, nh, stream);
   return T == 192 ? launch_attn_bwd_small<64, 12>(qkv, dy, P, Pd, dqkv, B, C, nh, stream)
                   : launch_attn_bwd_small<64, 8>(qkv, dy, P, Pd, dqkv, B, C, nh, stream);
+}
+
+// The same for the TF32 configuration: fp32 tensors, tf32 tensor-core products; head size 16 or 32, T in {128, 192}.
+// Launches 2 * nh * B CTAs in clusters of two (see the kernel comment).
+MMFN_API int mmfn_attention_bwd_small_tf32(const float* qkv, const float* dy, const float* P, const float* Pd, float* dqkv,
+                                           int B, int T, int C, int nh, cudaStream_t stream) {
+  MMFN_CHECK_ARG(qkv && dy && P && Pd && dqkv, "attention_bwd_small_tf32: null pointer");
+  MMFN_CHECK_ARG(B >= 1 && B <= 65535 && nh >= 1 && C % nh == 0 && (C / nh == 16 || C / nh == 32) && (T == 128 || T == 192),
+                 "attention_bwd_small_tf32: needs head size 16 or 32 and T in {128, 192}");
+  MMFN_CHECK_ARG((((uintptr_t)qkv | (uintptr_t)dy | (uintptr_t)P | (uintptr_t)Pd | (uintptr_t)dqkv) & 15) == 0, "attention_bwd_small_tf32: 16-byte alignment");
+  if (C / nh == 16) return T == 192 ? launch_attn_bwd_small_tf32<16, 6>(qkv, dy, P, Pd, dqkv, B, C, nh, stream)
+                                    : launch_attn_bwd_small_tf32<16, 4>(qkv, dy, P, Pd, dqkv, B, C, nh, stream);
+  return T == 192 ? launch_attn_bwd_small_tf32<32, 6>(qkv, dy, P, Pd, dqkv, B, C, nh, stream)
+                  : launch_attn_bwd_small_tf32<32, 4>(qkv, dy, P, Pd, dqkv, B, C, nh, stream);
 }
