@@ -391,7 +391,8 @@ class Block:
         bf = self.bf
         y_att = self.proj.x                                        # attention output saved by the projection
         qkv = self.qkv_out
-        if bf and dy.dtype == torch.bfloat16 and ops.attention_bwd_small_ok(T, C, nh, self.P):
+        want = torch.bfloat16 if bf else torch.float32              # operand type of the qkv linear's backward
+        if dy.dtype == self.P.dtype == qkv.dtype == want and ops.attention_bwd_small_ok(T, C, nh, self.P):
             # narrow heads: dPd, softmax backward, dQ, dK and dV in ONE launch per block (csrc/attn_bwd_small.cu)
             return ops.attention_bwd_small(qkv, dy, self.P, self.Pd, B, T, C, nh)
         k, q, v = (self._heads(qkv, B, T, i * C) for i in range(3))

@@ -830,17 +830,27 @@ FUSE_ATTN_BWD_SMALL = _os.environ.get("MMFN_FUSE_ATTN_BWD_SMALL", "1") != "0"
 
 
 def attention_bwd_small_ok(T, C, nh, p):
-    """one-launch attention backward (csrc/attn_bwd_small.cu): bf16, heads of 16 / 32 / 64 dims, T in {128, 192}"""
-    return FUSE_ATTN_BWD_SMALL and p.dtype == BF and C % nh == 0 and (C // nh) in (16, 32, 64) and T in (128, 192)
+    """one-launch attention backward (csrc/attn_bwd_small.cu): bf16 heads of 16 / 32 / 64 dims, TF32 heads of 16 / 32, T in {128, 192}"""
+    if not FUSE_ATTN_BWD_SMALL or C % nh or T not in (128, 192):
+        return False
+    if p.dtype == BF:
+        return (C // nh) in (16, 32, 64)
+    # TF32: a cluster of two CTAs per (sample, head); 64-dim heads do not fit
+    return p.dtype == torch.float32 and TF32 and (C // nh) in (16, 32)
 
 
 def attention_bwd_small(qkv, dy, P, Pd, B, T, C, nh):
-    """qkv (B*T, 3C), dy (B*T, C), P / Pd (B, nh, T, T), all bf16 -> dqkv (B*T, 3C) bf16"""
+    """qkv (B*T, 3C), dy (B*T, C), P / Pd (B, nh, T, T), all bf16 or all fp32 (TF32 products) -> dqkv (B*T, 3C)"""
     assert qkv.is_contiguous() and dy.is_contiguous() and P.is_contiguous() and Pd.is_contiguous()
-    assert qkv.dtype == BF and dy.dtype == BF and P.dtype == BF and Pd.dtype == BF and P.shape == (B, nh, T, T)
+    assert dy.dtype == qkv.dtype and P.dtype == qkv.dtype and Pd.dtype == qkv.dtype and P.shape == (B, nh, T, T)
     dqkv = torch.empty_like(qkv)
-    lib().next_work = (8.0 * B * nh * T * T * (C // nh), 2.0 * (B * T * 7 * C + 2 * B * nh * T * T), B, T, C, nh)
-    lib().attention_bwd_small_bf16(_p(qkv), _p(dy), _p(P), _p(Pd), _p(dqkv), B, T, C, nh, _st())
+    es = qkv.element_size()
+    lib().next_work = (8.0 * B * nh * T * T * (C // nh), es * (B * T * 7 * C + 2 * B * nh * T * T), B, T, C, nh)
+    if qkv.dtype == BF:
+        lib().attention_bwd_small_bf16(_p(qkv), _p(dy), _p(P), _p(Pd), _p(dqkv), B, T, C, nh, _st())
+    else:
+        assert qkv.dtype == torch.float32
+        lib().attention_bwd_small_tf32(_p(qkv), _p(dy), _p(P), _p(Pd), _p(dqkv), B, T, C, nh, _st())
     return dqkv
 
 

@@ -78,6 +78,8 @@ def test_argument_validation_without_gpu():
         lib().gpt_small_bwd_rows(100, 64, 2, 1, 1, *([P] * 9), *([P] * 13), 0.0, 0, 0, None)
     with pytest.raises(MmfnError, match="head size 16, 32 or 64"):
         lib().attention_bwd_small_bf16(P, P, P, P, P, 2, 192, 512, 4, None)
+    with pytest.raises(MmfnError, match="head size 16 or 32"):
+        lib().attention_bwd_small_tf32(P, P, P, P, P, 2, 192, 256, 4, None)
 
 
 def test_product_never_imports_oracle():
