@@ -86,12 +86,19 @@ __device__ __forceinline__ void tc_epilogue(const Op& op, const Epilogue& e, uin
     // 16-byte path: every row of this warp's quarter starts on a float4 boundary and the tile is full in N
     const bool vec = (N % 4 == 0) && (OUT16 ? (reinterpret_cast<uintptr_t>(e.C16) & 7) == 0 : (reinterpret_cast<uintptr_t>(e.C) & 15) == 0) &&
                      (n0 + TBN <= N) && __all_sync(0xffffffffu, !my_ok || (my_off & 3) == 0);
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+    // bias vectors of this warp's (up to two) column chunks: requested while the main loop still runs -- read inside the
+    // chunk loop, the L2 round trip (~0.7 us) sat in front of every chunk's stores (profiles/r02_tc_trace_gemm.txt)
+    float4 b_lo = make_float4(0.f, 0.f, 0.f, 0.f), b_hi = b_lo;
+    if (vec && bias) {
+      b_lo = __ldg(reinterpret_cast<const float4*>(bias + n0 + (ew >> 2) * 32 + c4));
+      if constexpr (TBN / 32 > 2) b_hi = __ldg(reinterpret_cast<const float4*>(bias + n0 + ((ew >> 2) + 2) * 32 + c4));
+    }
     mbar_wait(tmem_full, 0);                              // all MMAs retired: TMEM valid, smem stages idle
     tc_fence_after();
     if (ew < 4) sts64(row_off + (q * 32 + lane) * 8, my_ok ? my_off : (int64_t)-1);
     asm volatile("bar.sync 1, 256;" ::: "memory");        // row_off visible to the 8 epilogue warps
     if (threadIdx.x == 64) TC_STAMP(4);                   // accumulator visible to the epilogue
-    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll 1
     for (int c = ew >> 2; c < TBN / 32; c += 2) {
       const int col0 = n0 + c * 32;
@@ -111,8 +118,7 @@ __device__ __forceinline__ void tc_epilogue(const Op& op, const Epilogue& e, uin
       if (vec) {
         // ---- fast path: float4 everywhere; kept small on purpose (this code runs once per CTA, from a cold
         // instruction cache -- a fully unrolled, branchy epilogue costs more in fetch stalls than it saves)
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
+        const float4 b4 = c < 2 ? b_lo : b_hi;            // (chunks c, c + 2 of this warp)
         const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
         float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};     // BatchNorm partials of this thread's 8 rows
         // per half (4 rows): the rows' offsets, then all residual / mask vectors, are requested before the first use --
