@@ -457,7 +457,7 @@ class FusionGPT:
         self.seed = seed + self.site * 100
         x = ops.tokens_fwd(feats, self.pos, self.vw, self.vb, velocity, self.ep, self.seed).view(B * self.T, self.C)
         blocks = self.blocks
-        self.fused = ops.gpt_small_ok(self.C, self.T, blocks[0].nh, len(blocks))
+        self.fused = ops.gpt_small_ok(self.C, self.T, blocks[0].nh, len(blocks), B)
         if self.fused:
             # all blocks in ONE launch (csrc/gpt_small.cu); each block adopts the tensors its backward reads
             bf = ops.BF16
