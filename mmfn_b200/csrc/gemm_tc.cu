@@ -7,6 +7,7 @@
 // Either operand may be K-major (row = M/N index, reduction contiguous: activations, weights in
 // forward) or MN-major (reduction is the slow dimension: W in dgrad, dY/X in wgrad), so forward,
 // data-gradient and weight-gradient GEMMs all read the same row-major tensors with no transposes.
+#include <cstdlib>
 #include "tc_kernel.cuh"
 
 namespace {
@@ -34,6 +35,15 @@ struct GemmOp {
     kb0 = split * kb_per_split;
     kb1 = min(nkb, kb0 + kb_per_split);
   }
+  // persistent kernel: linear tile index (n fastest), whole K, single batch
+  __device__ void set_tile(int t) {
+    const int tn = (N + TBN - 1) / TBN;
+    const int tm = t / tn;
+    m0 = tm * tc::TBM;
+    n0 = (t - tm * tn) * TBN;
+    b0 = 0; b1 = 0; kb0 = 0; kb1 = (K + EB - 1) / EB;
+  }
+  __device__ int kb_total() const { return (K + EB - 1) / EB; }
   __device__ int kb_begin() const { return kb0; }
   __device__ int kb_end() const { return kb1; }
   __device__ static void issue(uint8_t* dst, const CUtensorMap* t, uint64_t* bar, const OperandPos& p, int inner, int row,
@@ -56,8 +66,21 @@ struct GemmOp {
   }
   __device__ int n_cols() const { return N; }
   __device__ int col0() const { return n0; }
-  __device__ bool first_split() const { return (blockIdx.z % splitk) == 0; }
+  __device__ bool first_split() const { return splitk == 1 || (blockIdx.z % splitk) == 0; }
 };
+
+// Large plain GEMMs go to the persistent kernel (tc_kernel.cuh): >= 2 tiles per SM, no split-K, no batch.  MMFN_GEMM_PERSIST=0
+// switches it off (A/B runs).
+static int g_persist_mode = -1;
+static int persist_mode() {
+  if (g_persist_mode < 0) { const char* v = getenv("MMFN_GEMM_PERSIST"); g_persist_mode = (v && v[0] == '0') ? 0 : 1; }
+  return g_persist_mode;
+}
+static int sm_count() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
+}
 
 struct GemmArgs {
   int M, N, K, nb0, nb1, splitk, tbn;
@@ -77,6 +100,11 @@ int run_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, co
     return tc::launch<GemmOp<AMN, BMN, 64, EB>, 64, 4, true>(ta, tb, op, e, dim3((g.N + 63) / 64, (g.M + tc::TBM - 1) / tc::TBM, gz), stream, what);
   }
   GemmOp<AMN, BMN, 128, EB> op{g.M, g.N, g.K, kb_per, splitk, g.nb1, g.ldc, g.c_sb0, g.c_sb1, g.pa, g.pb};
+  {
+    const int ntiles = ((g.N + 127) / 128) * ((g.M + tc::TBM - 1) / tc::TBM);
+    if (splitk == 1 && gz == 1 && ntiles >= 2 * sm_count() && e.bn_ws == nullptr && e.trace == nullptr && persist_mode())
+      return tc::launch_persist<GemmOp<AMN, BMN, 128, EB>>(ta, tb, op, e, ntiles, sm_count(), stream, what);
+  }
   return tc::launch<GemmOp<AMN, BMN, 128, EB>, 128, 3, true>(ta, tb, op, e, dim3((g.N + 127) / 128, (g.M + tc::TBM - 1) / tc::TBM, gz), stream, what);
 }
 
@@ -124,6 +152,10 @@ unsigned long long* mmfn_tc_trace_ptr() { return g_trace; }
 
 // Developer aid: when buf (8 x uint64, device) is non-null every tensor-core kernel's CTA 0 writes
 // %globaltimer stamps of its pipeline phases there.  Pass null to switch it off (default).
+// Route large plain GEMMs (>= 2 output tiles per SM, no split-K, no batch) to the persistent kernel (1, default) or keep
+// every GEMM on the one-tile-per-CTA kernel (0).  Both produce bit-identical results; tests and A/B timing use this.
+MMFN_API int mmfn_set_gemm_persist(int on) { g_persist_mode = on ? 1 : 0; return 0; }
+
 MMFN_API int mmfn_tc_set_trace(unsigned long long* buf) {
   g_trace = buf;
   return 0;

@@ -847,3 +847,54 @@ def test_attention_bwd_small_matches_the_formulas(T, C, drop, prec):
         a, b = got[:, i * C:(i + 1) * C], ref[:, i * C:(i + 1) * C]
         err = (a - b).abs().max().item() / b.abs().max().item()
         assert err < (1.5e-2 if prec == "bf16" else 3e-3), (name, err)
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("variant", ["plain", "bias_relu", "res_drop", "dgrad_mask", "out16"])
+@pytest.mark.parametrize("M,N,K", [(8192, 2048, 512), (8192, 512, 2048), (4200, 1152, 320), (6144, 1024, 256)])
+def test_persistent_gemm_is_bit_identical_to_the_one_tile_kernel(M, N, K, variant, prec):
+    """Large plain GEMMs (>= 2 output tiles per SM) run on the persistent kernel (one CTA per SM, TMA ring across tiles,
+    two TMEM accumulators, two epilogue groups).  Same MMA order per tile and the same epilogue code, so the result must
+    equal the one-tile-per-CTA kernel's BIT FOR BIT -- bias / ReLU / residual / dropout / mask / bf16 output, K-major and
+    MN-major B operand, ragged last row tile -- and both must match torch within the operand precision."""
+    from mmfn_b200 import ops
+    from mmfn_b200._lib import lib
+    if prec == "tf32" and variant == "out16":
+        pytest.skip("bf16 results of TF32 products are covered by test_gemm_tf32_out")
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    dt = torch.bfloat16 if prec == "bf16" else torch.float32
+    ops.set_precision(prec)
+    try:
+        A = torch.randn(M, K, device=DEV, generator=gen).to(dt)
+        W = (torch.randn(N, K, device=DEV, generator=gen) * 0.05).to(dt)
+        bias = torch.randn(N, device=DEV, generator=gen)
+        res = torch.randn(M, N, device=DEV, generator=gen)
+        kw, Bop = {}, W
+        out_dt = torch.float32
+        if variant == "bias_relu":
+            kw = dict(bias=bias, act=1)
+        elif variant == "res_drop":
+            kw = dict(bias=bias, res=res, drop_p=0.1, seed=77)
+        elif variant == "dgrad_mask":                     # dx = dy W with the ReLU mask of the producer: B is a transposed view
+            Wt = (torch.randn(K, N, device=DEV, generator=gen) * 0.05).to(dt)
+            Bop = Wt.t()
+            kw = dict(mask=(torch.randn(M, N, device=DEV, generator=gen)).to(dt))
+        elif variant == "out16":
+            kw = dict(bias=bias, act=1)
+            out_dt = torch.bfloat16
+        outs = []
+        for persist in (0, 1):
+            lib().set_gemm_persist(persist)
+            C = torch.full((M, N), float("nan"), device=DEV, dtype=out_dt)
+            ops.gemm(A, Bop, C, **kw)
+            torch.cuda.synchronize()
+            outs.append(C)
+        assert torch.equal(outs[0], outs[1])
+        if variant in ("plain", "bias_relu", "out16"):
+            ref = A.float() @ (Bop.float().t() if variant != "dgrad_mask" else Bop.float().t())
+            if "bias" in kw:
+                ref = torch.relu(ref + bias)
+            close(outs[1], ref, 2e-2 if out_dt == torch.bfloat16 else (1e-2 if prec == "bf16" else 3e-3))
+    finally:
+        lib().set_gemm_persist(1)
+        ops.set_precision("tf32")
