@@ -76,6 +76,11 @@ static int persist_mode() {
   if (g_persist_mode < 0) { const char* v = getenv("MMFN_GEMM_PERSIST"); g_persist_mode = (v && v[0] == '0') ? 0 : 1; }
   return g_persist_mode;
 }
+static int persist_wide_tiles() {                        // MMFN_GEMM_PERSIST_256=1: 128 x 256 tiles where N % 256 == 0 (measured: no better than 128 x 128 on average)
+  static int mode = -1;
+  if (mode < 0) { const char* v = getenv("MMFN_GEMM_PERSIST_256"); mode = (v && v[0] == '1') ? 1 : 0; }
+  return mode;
+}
 static int sm_count() {
   static int n = 0;
   if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
@@ -99,11 +104,16 @@ int run_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, co
     GemmOp<AMN, BMN, 64, EB> op{g.M, g.N, g.K, kb_per, splitk, g.nb1, g.ldc, g.c_sb0, g.c_sb1, g.pa, g.pb};
     return tc::launch<GemmOp<AMN, BMN, 64, EB>, 64, 4, true>(ta, tb, op, e, dim3((g.N + 63) / 64, (g.M + tc::TBM - 1) / tc::TBM, gz), stream, what);
   }
+  if (g.tbn == 256) {                                    // (chosen by gemm_tc_impl only for the persistent kernel)
+    GemmOp<AMN, BMN, 256, EB> op{g.M, g.N, g.K, kb_per, splitk, g.nb1, g.ldc, g.c_sb0, g.c_sb1, g.pa, g.pb};
+    const int ntiles = (g.N / 256) * ((g.M + tc::TBM - 1) / tc::TBM);
+    return tc::launch_persist<GemmOp<AMN, BMN, 256, EB>, 256>(ta, tb, op, e, ntiles, sm_count(), stream, what);
+  }
   GemmOp<AMN, BMN, 128, EB> op{g.M, g.N, g.K, kb_per, splitk, g.nb1, g.ldc, g.c_sb0, g.c_sb1, g.pa, g.pb};
   {
     const int ntiles = ((g.N + 127) / 128) * ((g.M + tc::TBM - 1) / tc::TBM);
     if (splitk == 1 && gz == 1 && ntiles >= 2 * sm_count() && e.bn_ws == nullptr && e.trace == nullptr && persist_mode())
-      return tc::launch_persist<GemmOp<AMN, BMN, 128, EB>>(ta, tb, op, e, ntiles, sm_count(), stream, what);
+      return tc::launch_persist<GemmOp<AMN, BMN, 128, EB>, 128>(ta, tb, op, e, ntiles, sm_count(), stream, what);
   }
   return tc::launch<GemmOp<AMN, BMN, 128, EB>, 128, 3, true>(ta, tb, op, e, dim3((g.N + 127) / 128, (g.M + tc::TBM - 1) / tc::TBM, gz), stream, what);
 }
@@ -152,6 +162,12 @@ unsigned long long* mmfn_tc_trace_ptr() { return g_trace; }
 
 // Developer aid: when buf (8 x uint64, device) is non-null every tensor-core kernel's CTA 0 writes
 // %globaltimer stamps of its pipeline phases there.  Pass null to switch it off (default).
+// Developer aid: device buffer of 16 x 8 uint64 receiving the per-tile %globaltimer stamps of CTA 0 of the persistent GEMM
+// kernel (null = off); see tc_kernel.cuh.
+MMFN_API int mmfn_tc_set_persist_trace(unsigned long long* buf) {
+  return (int)cudaMemcpyToSymbol(tc::g_tcp_trace, &buf, sizeof(buf));
+}
+
 // Route large plain GEMMs (>= 2 output tiles per SM, no split-K, no batch) to the persistent kernel (1, default) or keep
 // every GEMM on the one-tile-per-CTA kernel (0).  Both produce bit-identical results; tests and A/B timing use this.
 MMFN_API int mmfn_set_gemm_persist(int on) { g_persist_mode = on ? 1 : 0; return 0; }
@@ -244,9 +260,14 @@ static int gemm_tc_impl(const void* A, int64_t lda, int a_mn, int64_t a_sb0, int
       splitk = max(1, min(nkb / 4, (2 * 148) / tiles));
     }
   }
+  // 128 x 256 tiles on the persistent kernel when the problem still gives every SM two of them
+  int tbn_final = tbn;
+  if (tbn == 128 && splitk == 1 && nb == 1 && N % 256 == 0 && (int64_t)mt * (N / 256) >= 2 * sm_count() && mmfn_tc_trace_ptr() == nullptr &&
+      persist_mode() && persist_wide_tiles())
+    tbn_final = 256;
   MMFN_CHECK_ARG(splitk == 1 || (accum == 2 && linear), "%s: split-K needs a linear atomic epilogue", what);
   MMFN_CHECK_ARG((int64_t)nb * splitk <= 65535, "%s: too many batches x splits", what);
-  GemmArgs g{M, N, K, nb0, nb1, splitk, tbn, ldc, c_sb0, c_sb1};
+  GemmArgs g{M, N, K, nb0, nb1, splitk, tbn_final, ldc, c_sb0, c_sb1};
   CUtensorMap ta, tb;
   if (int rc = make_operand_tmap(&ta, &g.pa, A, a_mn != 0, M, K, lda, nb0, nb1, a_sb0, a_sb1, tc::TBM, EB)) return rc;
   if (int rc = make_operand_tmap(&tb, &g.pb, B, b_mn != 0, N, K, ldb, nb0, nb1, b_sb0, b_sb1, g.tbn, EB)) return rc;

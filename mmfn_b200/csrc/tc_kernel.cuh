@@ -66,19 +66,23 @@ struct Smem {
 // 1024-byte aligned dynamic shared memory whose first 8*32*36*4 + 128*8 bytes are idle once tmem_full has fired).
 // Persistent kernels (tc_gemm_persist_kernel) run TWO epilogue groups of 8 warps: `ew_` = the warp's index inside its group,
 // `parity` = phase of the accumulator barrier for this tile, `bar_id` = the group's named barrier.
-template <class Op, int TBN, bool FULL, bool OUT16 = false>
+template <class Op, int TBN, bool FULL, bool OUT16 = false, bool WIDE = false>
 __device__ __forceinline__ void tc_epilogue(const Op& op, const Epilogue& e, uint8_t* smem, uint64_t* tmem_full,
                                             uint32_t tmem_base, int kb0, int kb1, int ew_ = -1, uint32_t parity = 0, int bar_id = 1) {
+  // WIDE: 16 epilogue warps (persistent kernel, TBN = 128): every warp owns ONE 32-column chunk of its lane quarter, so
+  // the per-tile read-out chain is half as long; staging = 16 x [32][36] floats
+  constexpr int NEW = WIDE ? 16 : 8;                    // epilogue warps
+  constexpr int CSTEP = NEW / 4;                        // column-chunk stride of a warp
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // ===== epilogue: 8 warps; warp w owns TMEM lane quarter (w % 4) and every other 32-column chunk =====
     // tcgen05.ld hands each thread one accumulator ROW (32 consecutive columns).  The rows are
     // re-tiled through shared memory (the idle pipeline stages, 36-float pitch: conflict-free for
     // 128-bit accesses) so that each warp instruction touches four fully coalesced 128-byte row
     // segments: result stores / atomics, residual and mask loads all run as 16-byte vectors.
-    const int ew = ew_ >= 0 ? ew_ : warp - 2;             // 0..7
+    const int ew = ew_ >= 0 ? ew_ : warp - 2;             // 0..NEW-1
     const int q = warp & 3;
     const uint32_t stg = smem_u32(smem) + ew * (32 * 36 * 4);                      // this warp's [32][36] staging tile
-    const uint32_t row_off = smem_u32(smem) + 8 * 32 * 36 * 4;                     // int64 [128]
+    const uint32_t row_off = smem_u32(smem) + NEW * 32 * 36 * 4;                   // int64 [128]
     int64_t my_off = 0;
     const bool my_ok = op.out_row(q * 32 + lane, my_off);
     const int N = op.n_cols(), n0 = op.col0();
@@ -94,16 +98,17 @@ __device__ __forceinline__ void tc_epilogue(const Op& op, const Epilogue& e, uin
     float4 b_lo = make_float4(0.f, 0.f, 0.f, 0.f), b_hi = b_lo;
     if (vec && bias) {
       b_lo = __ldg(reinterpret_cast<const float4*>(bias + n0 + (ew >> 2) * 32 + c4));
-      if constexpr (TBN / 32 > 2) b_hi = __ldg(reinterpret_cast<const float4*>(bias + n0 + ((ew >> 2) + 2) * 32 + c4));
+      if constexpr (TBN / 32 > CSTEP) b_hi = __ldg(reinterpret_cast<const float4*>(bias + n0 + ((ew >> 2) + CSTEP) * 32 + c4));
     }
     mbar_wait(tmem_full, parity);                         // all MMAs retired: TMEM valid, smem stages idle
     tc_fence_after();
     if (ew < 4) sts64(row_off + (q * 32 + lane) * 8, my_ok ? my_off : (int64_t)-1);
-    if (bar_id == 1) asm volatile("bar.sync 1, 256;" ::: "memory");       // row_off visible to the 8 epilogue warps
-    else asm volatile("bar.sync 2, 256;" ::: "memory");                   // (second epilogue group of the persistent kernel)
+    if constexpr (WIDE) asm volatile("bar.sync 1, 512;" ::: "memory");    // row_off visible to the epilogue warps
+    else if (bar_id == 1) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else asm volatile("bar.sync 2, 256;" ::: "memory");
     if (threadIdx.x == 64) TC_STAMP(4);                   // accumulator visible to the epilogue
 #pragma unroll 1
-    for (int c = ew >> 2; c < TBN / 32; c += 2) {
+    for (int c = ew >> 2; c < TBN / 32; c += CSTEP) {
       const int col0 = n0 + c * 32;
       if (col0 >= N) break;                               // warp-uniform
       {
@@ -121,7 +126,7 @@ __device__ __forceinline__ void tc_epilogue(const Op& op, const Epilogue& e, uin
       if (vec) {
         // ---- fast path: float4 everywhere; kept small on purpose (this code runs once per CTA, from a cold
         // instruction cache -- a fully unrolled, branchy epilogue costs more in fetch stalls than it saves)
-        const float4 b4 = c < 2 ? b_lo : b_hi;            // (chunks c, c + 2 of this warp)
+        const float4 b4 = c < CSTEP ? b_lo : b_hi;        // (chunks c, c + CSTEP of this warp)
         const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
         float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};     // BatchNorm partials of this thread's 8 rows
         // per half (4 rows): the rows' offsets, then all residual / mask vectors, are requested before the first use --
@@ -375,27 +380,43 @@ tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
 // ------------------------------------------------------------------------------------------------------------------
 // Persistent variant for large plain GEMMs (no split-K, no batch): ONE CTA per SM walks the output tiles; the TMA ring
-// runs ahead across tile boundaries, the accumulator is double-buffered in TMEM (2 x 128 columns) and TWO epilogue
-// groups of 8 warps alternate tiles, so operand streaming never stops for an epilogue.  Why: the one-tile-per-CTA
+// runs ahead across tile boundaries, the accumulator is double-buffered in TMEM (2 x 128 columns) and SIXTEEN epilogue
+// warps (one 32 x 32 chunk of the tile each) read one accumulator out while the MMA warp fills the other, so operand
+// streaming never stops for an epilogue.  Why: the one-tile-per-CTA
 // kernel keeps the SM's L2 ingest port busy about a third of the time on the K = 512 MLP GEMMs -- set-up, first-TMA
 // latency and a 3.5 us epilogue per tile, only partly hidden by the second resident CTA (profiles/r02_tc_trace_gemm.txt).
 // Op needs set_tile(int) (tile index -> m0 / n0, n fastest so that neighbouring CTAs share the A rows in L2).
 constexpr int TCP_THREADS = 64 + 2 * 256;            // TMA warp + MMA warp + two epilogue groups
-constexpr int TCP_STAGES = 4;
-constexpr int TCP_TBN = 128;
-constexpr int TCP_STG_BYTES = 8 * 32 * 36 * 4 + 128 * 8;      // per-group epilogue staging: [8 warps][32][36] floats + row offsets
+#ifndef MMFN_TCP_WIDE
+#define MMFN_TCP_WIDE 1
+#endif
+constexpr bool TCP_WIDE = MMFN_TCP_WIDE != 0;        // 16 warps on every tile | two groups of 8 alternating tiles
+constexpr int TCP_GRP_BYTES = (8 * 32 * 36 * 4 + 128 * 8 + 1023) / 1024 * 1024;
+constexpr int TCP_STG_BYTES = TCP_WIDE ? 16 * 32 * 36 * 4 + 128 * 8 : 2 * TCP_GRP_BYTES;     // epilogue staging + row offsets
 
+// TBN = 128: 4 stages x 32 KB; TBN = 256 (N % 256 == 0): 3 stages x 48 KB -- 1.33x the MMA work per operand byte, which is
+// what bounds these GEMMs (the bytes one CTA can keep in flight against the ~1.5 us L2 round trip under load)
+template <int TBN>
 struct SmemP {
-  static constexpr int STAGE_BYTES = TBM * 128 + TCP_TBN * 128;
-  static constexpr int STG_OFF = TCP_STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = STG_OFF + 2 * ((TCP_STG_BYTES + 1023) / 1024 * 1024);
+  static constexpr int STAGES = TBN == 256 ? 3 : 4;
+  static constexpr int STAGE_BYTES = TBM * 128 + TBN * 128;
+  static constexpr int STG_OFF = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFF = STG_OFF + (TCP_STG_BYTES + 1023) / 1024 * 1024;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
 };
 
-template <class Op, bool FULL, bool OUT16>
+// developer aid (tools/gemm_persist_bench.py --trace): %globaltimer stamps of CTA 0, 8 per tile --
+// 0 producer issues the tile's first k-block, 1 its last; 2 MMA warp has the accumulator, 3 first operands landed, 4 tile committed;
+// 5 epilogue sees the accumulator, 6 its stores are issued
+static __device__ unsigned long long* g_tcp_trace = nullptr;
+#define TCP_STAMP(it, i) do { if (g_tcp_trace && blockIdx.x == 0 && (it) < 16) g_tcp_trace[(it) * 8 + (i)] = gtimer(); } while (0)
+
+template <class Op, int TCP_TBN, bool FULL, bool OUT16>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Op op, Epilogue e, int ntiles) {
   using ET = ElemTraits<Op::EB>;
+  using SmemP = tc::SmemP<TCP_TBN>;
+  constexpr int TCP_STAGES = SmemP::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SmemP::BAR_OFF);
@@ -407,7 +428,7 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TCP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 8); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], TCP_WIDE ? 16 : 8); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 2 * TCP_TBN);
@@ -420,15 +441,18 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 0) {
     if (elect_one()) {                                   // ===== TMA producer: one ring across all of this CTA's tiles =====
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int pit = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++pit) {
         op.set_tile(tile);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
+          if (kb == 0) TCP_STAMP(pit, 0);
           uint8_t* sa = smem + stage * SmemP::STAGE_BYTES;
           mbar_expect_tx(&full[stage], SmemP::STAGE_BYTES);
           op.load(kb, sa, sa + TBM * 128, &full[stage], &tmA, &tmB);
           if (++stage == TCP_STAGES) { stage = 0; phase ^= 1; }
         }
+        TCP_STAMP(pit, 1);
       }
     }
   } else if (warp == 1) {
@@ -440,10 +464,12 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int b = it & 1;
         mbar_wait(&acc_empty[b], ((it >> 1) & 1) ^ 1);   // this accumulator's previous tile has been read out
         tc_fence_after();
+        TCP_STAMP(it, 2);
         const uint32_t acc = tmem_base + (uint32_t)(b * TCP_TBN);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
+          if (kb == 0) TCP_STAMP(it, 3);
           const uint32_t sa = smem_u32(smem + stage * SmemP::STAGE_BYTES);
           const uint32_t sb = sa + TBM * 128;
 #pragma unroll
@@ -456,21 +482,40 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (++stage == TCP_STAGES) { stage = 0; phase ^= 1; }
         }
         mma_commit(&acc_full[b]);
+        TCP_STAMP(it, 4);
       }
     }
   } else {
-    // ===== two epilogue groups: group g takes this CTA's tiles g, g + 2, ... (= accumulator g) =====
-    const int grp = (warp - 2) >> 3, ew = (warp - 2) & 7;
-    uint8_t* stg = smem + SmemP::STG_OFF + grp * ((TCP_STG_BYTES + 1023) / 1024 * 1024);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      if ((it & 1) != grp) continue;
-      op.set_tile(tile);
-      tc_epilogue<Op, TCP_TBN, FULL, OUT16>(op, e, stg, &acc_full[grp], tmem_base + (uint32_t)(grp * TCP_TBN), 0, nkb, ew,
-                                            (uint32_t)((it >> 1) & 1), 1 + grp);
-      tc_fence_before();                                 // this warp's tcgen05.ld of the tile are complete (wait::ld inside)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[grp]);
+    if constexpr (TCP_WIDE) {
+      // ===== 16 epilogue warps read out every tile (one 32 x 32 chunk each) while the MMA warp fills the other accumulator =====
+      const int ew = warp - 2;
+      uint8_t* stg = smem + SmemP::STG_OFF;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        op.set_tile(tile);
+        if (threadIdx.x == 64) { mbar_wait(&acc_full[b], (uint32_t)((it >> 1) & 1)); TCP_STAMP(it, 5); }
+        tc_epilogue<Op, TCP_TBN, FULL, OUT16, true>(op, e, stg, &acc_full[b], tmem_base + (uint32_t)(b * TCP_TBN), 0, nkb, ew,
+                                                    (uint32_t)((it >> 1) & 1), 1);
+        tc_fence_before();                               // this warp's tcgen05.ld of the tile are complete (wait::ld inside)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[b]);
+        if (threadIdx.x == 64) TCP_STAMP(it, 6);
+      }
+    } else {
+      // ===== two epilogue groups: group g takes this CTA's tiles g, g + 2, ... (= accumulator g) =====
+      const int grp = (warp - 2) >> 3, ew = (warp - 2) & 7;
+      uint8_t* stg = smem + SmemP::STG_OFF + grp * TCP_GRP_BYTES;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        if ((it & 1) != grp) continue;
+        op.set_tile(tile);
+        tc_epilogue<Op, TCP_TBN, FULL, OUT16, false>(op, e, stg, &acc_full[grp], tmem_base + (uint32_t)(grp * TCP_TBN), 0, nkb, ew,
+                                                     (uint32_t)((it >> 1) & 1), 1 + grp);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[grp]);
+      }
     }
   }
   tc_fence_before();
@@ -478,31 +523,31 @@ tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (warp == 2) tmem_dealloc(tmem_base, 2 * TCP_TBN);
 }
 
-template <class Op, bool FULL, bool OUT16>
+template <class Op, int TBN, bool FULL, bool OUT16>
 static int launch_persist_impl(const CUtensorMap& ta, const CUtensorMap& tb, const Op& op, const Epilogue& e, int ntiles, int nsm,
                                cudaStream_t stream, const char* what) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t ce = cudaFuncSetAttribute(tc_gemm_persist_kernel<Op, FULL, OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemP::TOTAL);
+    cudaError_t ce = cudaFuncSetAttribute(tc_gemm_persist_kernel<Op, TBN, FULL, OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemP<TBN>::TOTAL);
     if (ce != cudaSuccess) { mmfn_set_error("%s: smem attribute (persistent): %s", what, cudaGetErrorString(ce)); return (int)ce; }
     attr_set = true;
   }
   const int grid = ntiles < nsm ? ntiles : nsm;
-  tc_gemm_persist_kernel<Op, FULL, OUT16><<<grid, TCP_THREADS, SmemP::TOTAL, stream>>>(ta, tb, op, e, ntiles);
+  tc_gemm_persist_kernel<Op, TBN, FULL, OUT16><<<grid, TCP_THREADS, SmemP<TBN>::TOTAL, stream>>>(ta, tb, op, e, ntiles);
   return mmfn_launch_status(what);
 }
 
-template <class Op>
+template <class Op, int TBN>
 static int launch_persist(const CUtensorMap& ta, const CUtensorMap& tb, const Op& op, const Epilogue& e, int ntiles, int nsm,
                           cudaStream_t stream, const char* what) {
   const bool full = e.act != 0 || e.mask != nullptr || e.mask16 != nullptr || e.drop_p > 0.f;
   if (e.C16 != nullptr) {
     if (e.accum != 0) { mmfn_set_error("%s: a bf16 result cannot be accumulated atomically", what); return MMFN_BAD_ARG; }
-    if (full) return launch_persist_impl<Op, true, true>(ta, tb, op, e, ntiles, nsm, stream, what);
-    return launch_persist_impl<Op, false, true>(ta, tb, op, e, ntiles, nsm, stream, what);
+    if (full) return launch_persist_impl<Op, TBN, true, true>(ta, tb, op, e, ntiles, nsm, stream, what);
+    return launch_persist_impl<Op, TBN, false, true>(ta, tb, op, e, ntiles, nsm, stream, what);
   }
-  if (full) return launch_persist_impl<Op, true, false>(ta, tb, op, e, ntiles, nsm, stream, what);
-  return launch_persist_impl<Op, false, false>(ta, tb, op, e, ntiles, nsm, stream, what);
+  if (full) return launch_persist_impl<Op, TBN, true, false>(ta, tb, op, e, ntiles, nsm, stream, what);
+  return launch_persist_impl<Op, TBN, false, false>(ta, tb, op, e, ntiles, nsm, stream, what);
 }
 
 template <class Op, int TBN, int STAGES, bool FULL, bool OUT16 = false>
