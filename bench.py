@@ -355,11 +355,11 @@ NCU_FILES = ("r02_ncu_full_kernels.json", "r01_ncu_full_kernels.json")
 NCU_KERNEL_OF = {
     ("conv2d_fwd_tf32", 16, 16, 256, 256, 3, 16): ("conv3x3_patch_kernel<64, 0, 1, 32>", "(4, 32, 1)"),
     ("conv2d_fwd_tf32", 16, 64, 64, 64, 3, 64): ("conv3x3_patch_kernel<64, 0, 0, 32>", "(1, 512, 1)"),
-    ("gemm_tf32", 4096, 2048, 512, 1): ("tc_kernel<GemmOp<0, 0, 128, 32>, 128, 3, 1, 0>", "(16, 32, 1)"),
+    ("gemm_tf32", 4096, 2048, 512, 1): ("tc_gemm_persist_kernel<GemmOp<0, 0, 128, 32>, 128, 1, 0>", "(148, 1, 1)"),
     ("conv2d_fwd_tf32", 16, 8, 512, 512, 3, 8): ("tc_kernel<ConvFwdOp<64, 0, 32>, 64, 4, 0, 0>", "(8, 8, 4)"),
     ("conv2d_fwd_bf16", 32, 16, 256, 256, 3, 16): ("conv3x3_patch_kernel<128, 0, 1, 64>", "(2, 64, 1)"),
     ("conv2d_fwd_bf16", 32, 64, 64, 64, 3, 64): ("conv3x3_patch_kernel<64, 0, 0, 64>", "(1, 1024, 1)"),
-    ("gemm_bf16", 8192, 2048, 512, 1): ("tc_kernel<GemmOp<0, 0, 128, 64>, 128, 3, 1, 1>", "(16, 64, 1)"),
+    ("gemm_bf16", 8192, 2048, 512, 1): ("tc_gemm_persist_kernel<GemmOp<0, 0, 128, 64>, 128, 1, 1>", "(148, 1, 1)"),
     # round-1 names (profiles/r01_ncu_full_kernels.json)
     ("r01", "conv2d_fwd_tf32", 16, 16, 256, 256, 3, 16): ("conv3x3_patch_kernel<64, 0, 1>", "(4, 32, 1)"),
 }

@@ -85,11 +85,19 @@ if len(sys.argv) > 2 and sys.argv[2] == "bf16":
         run(lambda: ops.conv2d_fwd_bn(x, w, 1, 1, rmc, rvc))
         run(lambda: ops.conv2d_dgrad(dy, w, (B, H, H, Cc), 1, 1))
         run(lambda: ops.conv2d_wgrad_(dy, x, dw, 1, 1))
+    # 8b. layer-4 3x3 convolution 512->512 @8x8 in bf16 (generic implicit-GEMM kernel)
+    x4b = torch.randn(B, 8, 8, 512, device=dev).to(bf); w4b = (torch.randn(512, 3, 3, 512, device=dev) * 0.02).to(bf)
+    run(lambda: ops.conv2d_fwd(x4b, w4b, 1, 1))
     # 9. fused bf16 attention, every transformer scale: with P / Pd stored (training) and stats-only
     for (T, Cc) in [(192, 64), (192, 128), (192, 256), (256, 512)]:
         q16 = torch.randn(B * T, 3 * Cc, device=dev).to(bf)
         run(lambda: ops.attention_fwd_bf16(q16, B, T, Cc, 4, 0.1, 7))
         run(lambda: ops.attention_fwd_bf16(q16, B, T, Cc, 4, 0.1, 7, save_probs=False))
+    # 9b. one-launch attention backward (transformers 1-3 geometries)
+    for (T, Cc) in [(192, 64), (192, 128), (192, 256)]:
+        q16 = torch.randn(B * T, 3 * Cc, device=dev).to(bf); dy16 = torch.randn(B * T, Cc, device=dev).to(bf)
+        P16 = torch.softmax(torch.randn(B, 4, T, T, device=dev), -1).to(bf)
+        run(lambda: ops.attention_bwd_small(q16, dy16, P16, P16, B, T, Cc, 4))
     # 10. BEV scatter at 64 frames (both kernels)
     pts64 = torch.from_numpy(np.stack([synthetic.synth_points(1234 + i) for i in range(64)])).to(dev)
     run(lambda: ops.bev_scatter(pts64))
