@@ -78,7 +78,8 @@ class _Lib:
 
     # kernels launched per C-ABI call when it is not exactly one (for the bench's launch count)
     KERNELS_PER_CALL = {"mmfn_bn_train_fwd": 2, "mmfn_bn_eval_fwd": 2, "mmfn_bn_train_bwd": 2,
-                        "mmfn_adamw_step": 2, "mmfn_tokens_bwd": 2, "mmfn_bev_scatter_ws": 2}
+                        "mmfn_adamw_step": 2, "mmfn_tokens_bwd": 2, "mmfn_bev_scatter_ws": 2,
+                        "mmfn_stem_bn_relu_maxpool_fwd": 2, "mmfn_stem_bn_relu_maxpool_bwd": 2}
 
     def _wrap(self, name, fn):
         nk = self.KERNELS_PER_CALL.get(name, 1)

@@ -26,17 +26,78 @@ struct BnFinal {
   float* fin; float* dgamma; float* dbeta;                                                  // backward
 };
 
+// Block-level tail shared by the column-reduction kernels: fold the per-thread fp64 partials (thread = quad q of
+// `qpr`, row lane threadIdx.x / qpr) over the row lanes, add them into scratch slot `slot`, and let the LAST CTA of the
+// launch (`n_ctas` arrivals) fold the slots, publish and re-zero the scratch.
+template <bool BWD>
+__device__ __forceinline__ void bn_reduce_publish(const double (&acc)[8], int qpr, int quad0, int slot, unsigned n_ctas,
+                                                  int64_t M, int C4, double* __restrict__ ws, const BnFinal& fz) {
+  __shared__ double red[BN_THREADS][8];
+  __shared__ bool last_cta;
+  const int nrs = BN_THREADS / qpr;
+  const int C = C4 * 4;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.x][k] = acc[k];
+  __syncthreads();
+  // thread t < qpr * 8 reduces one (quad, component) over the row lanes
+  if (threadIdx.x < qpr * 8) {
+    const int qq = threadIdx.x >> 3, k = threadIdx.x & 7;
+    const int cqq = quad0 + qq;
+    if (cqq < C4) {
+      double t = 0.0;
+      for (int rs = 0; rs < nrs; ++rs) t += red[rs * qpr + qq][k];
+      double* sl = ws + (int64_t)slot * 2 * C;
+      atomicAdd(sl + (k < 4 ? 0 : C) + cqq * 4 + (k & 3), t);
+    }
+  }
+  // ---- last CTA: fold the slots, publish, re-zero
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(ws + (int64_t)BN_SLOTS * 2 * C);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last_cta = atomicAdd(ticket, 1u) == n_ctas - 1;
+  __syncthreads();
+  if (!last_cta) return;
+  __threadfence();
+  const double invM = 1.0 / (double)M;
+  for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < BN_SLOTS; ++sl) {
+      double* slotp = ws + (int64_t)sl * 2 * C;
+      s1 += __ldcg(slotp + c);
+      s2 += __ldcg(slotp + C + c);
+      slotp[c] = 0.0;
+      slotp[C + c] = 0.0;
+    }
+    if (!BWD) {
+      const double md = s1 * invM;
+      double var = s2 * invM - md * md;
+      if (var < 0.0) var = 0.0;
+      fz.mean[c] = (float)md;
+      fz.rstd[c] = (float)(1.0 / sqrt(var + (double)fz.eps));
+      if (fz.running_mean) {
+        const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        fz.running_mean[c] = (float)((1.0 - fz.momentum) * fz.running_mean[c] + fz.momentum * md);
+        fz.running_var[c] = (float)((1.0 - fz.momentum) * fz.running_var[c] + fz.momentum * unbiased);
+      }
+    } else {
+      fz.fin[c] = (float)(s1 * invM);
+      fz.fin[C + c] = (float)(s2 * invM);
+      fz.dbeta[c] += (float)s1;
+      fz.dgamma[c] += (float)s2;
+    }
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
 template <bool BWD>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_colsum_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float4* __restrict__ yout,
                  const float* __restrict__ mean, const float* __restrict__ rstd, int64_t M, int C4, int qpr,
                  int64_t rows_per_block, double* __restrict__ ws, BnFinal fz) {
-  __shared__ double red[BN_THREADS][8];
-  __shared__ bool last_cta;
   const int q = threadIdx.x % qpr, rsub = threadIdx.x / qpr, nrs = BN_THREADS / qpr;
   const int cq = blockIdx.x * qpr + q;                          // channel quad of this thread
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
-  const int C = C4 * 4;
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (cq < C4) {
     float m4[4] = {0.f, 0.f, 0.f, 0.f}, r4[4] = {1.f, 1.f, 1.f, 1.f};
@@ -67,58 +128,7 @@ bn_colsum_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, co
       }
     }
   }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) red[threadIdx.x][k] = acc[k];
-  __syncthreads();
-  // thread t < qpr * 8 reduces one (quad, component) over the row lanes
-  if (threadIdx.x < qpr * 8) {
-    const int qq = threadIdx.x >> 3, k = threadIdx.x & 7;
-    const int cqq = blockIdx.x * qpr + qq;
-    if (cqq < C4) {
-      double t = 0.0;
-      for (int rs = 0; rs < nrs; ++rs) t += red[rs * qpr + qq][k];
-      double* slot = ws + (int64_t)(blockIdx.y % BN_SLOTS) * 2 * C;
-      atomicAdd(slot + (k < 4 ? 0 : C) + cqq * 4 + (k & 3), t);
-    }
-  }
-  // ---- last CTA: fold the slots, publish, re-zero
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(ws + (int64_t)BN_SLOTS * 2 * C);
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) last_cta = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
-  __syncthreads();
-  if (!last_cta) return;
-  __threadfence();
-  const double invM = 1.0 / (double)M;
-  for (int c = threadIdx.x; c < C; c += BN_THREADS) {
-    double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-    for (int sl = 0; sl < BN_SLOTS; ++sl) {
-      double* slot = ws + (int64_t)sl * 2 * C;
-      s1 += __ldcg(slot + c);
-      s2 += __ldcg(slot + C + c);
-      slot[c] = 0.0;
-      slot[C + c] = 0.0;
-    }
-    if (!BWD) {
-      const double md = s1 * invM;
-      double var = s2 * invM - md * md;
-      if (var < 0.0) var = 0.0;
-      fz.mean[c] = (float)md;
-      fz.rstd[c] = (float)(1.0 / sqrt(var + (double)fz.eps));
-      if (fz.running_mean) {
-        const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
-        fz.running_mean[c] = (float)((1.0 - fz.momentum) * fz.running_mean[c] + fz.momentum * md);
-        fz.running_var[c] = (float)((1.0 - fz.momentum) * fz.running_var[c] + fz.momentum * unbiased);
-      }
-    } else {
-      fz.fin[c] = (float)(s1 * invM);
-      fz.fin[C + c] = (float)(s2 * invM);
-      fz.dbeta[c] += (float)s1;
-      fz.dgamma[c] += (float)s2;
-    }
-  }
-  if (threadIdx.x == 0) *ticket = 0u;
+  bn_reduce_publish<BWD>(acc, qpr, blockIdx.x * qpr, blockIdx.y % BN_SLOTS, gridDim.x * gridDim.y, M, C4, ws, fz);
 }
 
 static inline void bn_colsum_grid(int64_t M, int C, int& qpr, dim3& grid, int64_t& rows_per_block) {
@@ -346,6 +356,194 @@ bn_small_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, con
 }
 constexpr int BN_SMALL_ROWS = 2048;
 
+// ------------------------------------------------------------------ stem tail: BatchNorm -> ReLU -> MaxPool 3x3 / 2
+// The two ResNet stems end in bn1 -> relu -> maxpool (model_rad.py:512-521) on the largest activation of the network
+// (B x 128 x 128 x 64).  Unfused that is three passes forward (apply writes y, the pool reads it back) and three
+// backward (pool backward writes a 3/4-zero gradient map, the BatchNorm reduction and the dx pass each read it again).
+// Fused: the forward reads z once and writes only the pooled map; y is never materialised.  The arg-max byte carries
+// the ReLU mask (bit 7 set: the window maximum was not positive), so the backward needs neither y nor the pooled map.
+
+// one thread = one pooled pixel x 4 channels; all nine taps are independent loads
+__global__ void __launch_bounds__(256)
+bn_relu_maxpool_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ rstd,
+                           const float4* __restrict__ gamma, const float4* __restrict__ beta, float* __restrict__ out,
+                           uint2* __restrict__ out16, uint8_t* __restrict__ idx, int B, int H, int W, int C, int Ho, int Wo) {
+  const int C4 = C >> 2;
+  const int64_t n = (int64_t)B * Ho * Wo * C4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool fixed = stride % C4 == 0;
+  int cq = (int)(i0 % C4);
+  // (v - m) * r * g + b is evaluated in the order bn_apply_kernel uses: rstd and gamma stay separate factors
+  float m[4], k[4], gk[4], bt[4];
+  auto coef = [&](int c) {
+    const float4 mm = __ldg(reinterpret_cast<const float4*>(mean) + c), rr = __ldg(reinterpret_cast<const float4*>(rstd) + c);
+    const float4 g = __ldg(gamma + c), b = __ldg(beta + c);
+    m[0] = mm.x; m[1] = mm.y; m[2] = mm.z; m[3] = mm.w;
+    k[0] = rr.x; k[1] = rr.y; k[2] = rr.z; k[3] = rr.w;
+    gk[0] = g.x; gk[1] = g.y; gk[2] = g.z; gk[3] = g.w;
+    bt[0] = b.x; bt[1] = b.y; bt[2] = b.z; bt[3] = b.w;
+  };
+  coef(cq);
+  for (int64_t i = i0; i < n; i += stride) {
+    if (!fixed) { cq = (int)(i % C4); coef(cq); }
+    const int t = (int)(i / C4);                  // (b, ho, wo) flattened: < 2^31 pixels
+    const int wo = t % Wo, t2 = t / Wo;
+    const int ho = t2 % Ho, b = t2 / Ho;
+    float4 v[9];
+    bool ok[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int sx = 0; sx < 3; ++sx) {
+        const int h = ho * 2 - 1 + r, w = wo * 2 - 1 + sx;
+        ok[r * 3 + sx] = h >= 0 && h < H && w >= 0 && w < W;
+        const int hc = min(max(h, 0), H - 1), wc = min(max(w, 0), W - 1);
+        v[r * 3 + sx] = __ldg(reinterpret_cast<const float4*>(z + (((int64_t)b * H + hc) * W + wc) * C) + cq);
+      }
+    }
+    float best[4] = {0.f, 0.f, 0.f, 0.f};
+    int bi[4] = {-1, -1, -1, -1};
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+      if (!ok[tp]) continue;
+      const float a[4] = {v[tp].x, v[tp].y, v[tp].z, v[tp].w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float y = fmaxf((a[c] - m[c]) * k[c] * gk[c] + bt[c], 0.f);
+        if (bi[c] < 0 || y > best[c] || y != y) { best[c] = y; bi[c] = tp; }
+      }
+    }
+    *reinterpret_cast<float4*>(out + (i << 2)) = make_float4(best[0], best[1], best[2], best[3]);
+    if (out16) out16[i] = mmfn_pack_bf16x4(best[0], best[1], best[2], best[3]);
+    uint32_t code = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) code |= ((uint32_t)bi[c] | (best[c] > 0.f ? 0u : 0x80u)) << (8 * c);
+    *reinterpret_cast<uint32_t*>(idx + (i << 2)) = code;
+  }
+}
+
+// Reduction half of the backward.  The gradient of the BatchNorm output is non-zero only at the arg-max position of
+// each pooling window, so sum(dy') and sum(dy' * xhat) run over the POOLED pixels: rows = (b, ho, wo), the thread layout
+// of bn_colsum_kernel; z is gathered at the arg-max tap (each lane its own channel, 4-byte loads).
+__global__ void __launch_bounds__(BN_THREADS)
+stem_bwd_stats_kernel(const float4* __restrict__ dout, const uint8_t* __restrict__ idx, const float* __restrict__ z,
+                      const float* __restrict__ mean, const float* __restrict__ rstd, int H, int W, int C4, int Ho, int Wo,
+                      int64_t Mp, int64_t M, int qpr, int64_t rows_per_block, double* __restrict__ ws, BnFinal fz) {
+  const int q = threadIdx.x % qpr, rsub = threadIdx.x / qpr, nrs = BN_THREADS / qpr;
+  const int cq = blockIdx.x * qpr + q;
+  const int C = C4 * 4;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(Mp, r0 + rows_per_block);
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cq < C4) {
+    const float4 mm = __ldg(reinterpret_cast<const float4*>(mean) + cq), rr = __ldg(reinterpret_cast<const float4*>(rstd) + cq);
+    const float m4[4] = {mm.x, mm.y, mm.z, mm.w}, r4[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll 4
+    for (int64_t r = r0 + rsub; r < r1; r += nrs) {
+      const uint32_t code = __ldg(reinterpret_cast<const uint32_t*>(idx) + r * C4 + cq);
+      const float4 gv = __ldg(dout + r * C4 + cq);
+      const float ga[4] = {gv.x, gv.y, gv.z, gv.w};
+      const int t = (int)r;
+      const int wo = t % Wo, t2 = t / Wo;
+      const int ho = t2 % Ho, b = t2 / Ho;
+      const float* zb = z + (((int64_t)b * H + (ho * 2 - 1)) * W + (wo * 2 - 1)) * C + cq * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t byte = (code >> (8 * k)) & 0xffu;
+        if (byte & 0x80u) continue;                                 // ReLU mask: the maximum was not positive
+        const int dr = (int)byte / 3, dc = (int)byte - dr * 3;
+        const float xv = __ldg(zb + ((int64_t)dr * W + dc) * C + k);
+        acc[k] += ga[k];
+        acc[4 + k] += (double)ga[k] * ((xv - m4[k]) * r4[k]);
+      }
+    }
+  }
+  bn_reduce_publish<true>(acc, qpr, blockIdx.x * qpr, blockIdx.y % BN_SLOTS, gridDim.x * gridDim.y, M, C4, ws, fz);
+}
+
+// dx half: one thread owns a 2 x 2 patch of input positions x 4 channels.  The patch at (2hp, 2wp) is covered by the
+// four windows (hp + a, wp + c), a, c in {0, 1}: position (dh, dw) of the patch is tap (dh - 2a + 1, dw - 2c + 1) of
+// window (a, c) when both are in 0..2.  4 arg-max words + 4 gradient quads + 4 z quads, all independent loads.
+__global__ void __launch_bounds__(256)
+stem_bwd_dx_kernel(const float* __restrict__ dout, const uint8_t* __restrict__ idx, const float* __restrict__ z,
+                   const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                   const float* __restrict__ fin, int B, int H, int W, int C, int Ho, int Wo,
+                   float* __restrict__ dz, uint2* __restrict__ dz16) {
+  const int C4 = C >> 2;
+  const int Hp = (H + 1) >> 1, Wp = (W + 1) >> 1;
+  const int64_t n = (int64_t)B * Hp * Wp * C4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool fixed = stride % C4 == 0;
+  int cq = (int)(i0 % C4);
+  float m[4], r[4], kk[4], fa[4], fb[4];
+  auto coef = [&](int c) {
+    const float4 mm = __ldg(reinterpret_cast<const float4*>(mean) + c), rr = __ldg(reinterpret_cast<const float4*>(rstd) + c);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(fin) + c), b = __ldg(reinterpret_cast<const float4*>(fin + C) + c);
+    m[0] = mm.x; m[1] = mm.y; m[2] = mm.z; m[3] = mm.w;
+    r[0] = rr.x; r[1] = rr.y; r[2] = rr.z; r[3] = rr.w;
+    kk[0] = g.x * rr.x; kk[1] = g.y * rr.y; kk[2] = g.z * rr.z; kk[3] = g.w * rr.w;
+    fa[0] = a.x; fa[1] = a.y; fa[2] = a.z; fa[3] = a.w;
+    fb[0] = b.x; fb[1] = b.y; fb[2] = b.z; fb[3] = b.w;
+  };
+  coef(cq);
+  for (int64_t i = i0; i < n; i += stride) {
+    if (!fixed) { cq = (int)(i % C4); coef(cq); }
+    const int t = (int)(i / C4);
+    const int wp = t % Wp, t2 = t / Wp;
+    const int hp = t2 % Hp, b = t2 / Hp;
+    uint32_t code[4];
+    float4 g4[4], z4[4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int ho = hp + a, wo = wp + c;
+        const bool ok = ho < Ho && wo < Wo;
+        const int64_t o = (((int64_t)b * Ho + min(ho, Ho - 1)) * Wo + min(wo, Wo - 1)) * C4 + cq;
+        const uint32_t cd = __ldg(reinterpret_cast<const uint32_t*>(idx) + o);
+        code[a * 2 + c] = ok ? cd : 0xffffffffu;                       // 0xff never equals a tap
+        g4[a * 2 + c] = __ldg(reinterpret_cast<const float4*>(dout) + o);
+        const int h = min(2 * hp + a, H - 1), w = min(2 * wp + c, W - 1);
+        z4[a * 2 + c] = __ldg(reinterpret_cast<const float4*>(z + (((int64_t)b * H + h) * W + w) * C) + cq);
+      }
+    }
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh) {
+#pragma unroll
+      for (int dw = 0; dw < 2; ++dw) {
+        const int h = 2 * hp + dh, w = 2 * wp + dw;
+        if (h >= H || w >= W) continue;
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int tr = dh - 2 * a + 1, tc = dw - 2 * c + 1;
+            if (tr < 0 || tc < 0) continue;                          // compile-time: this window does not cover the position
+            const uint32_t tap = (uint32_t)(tr * 3 + tc);
+            const uint32_t cd = code[a * 2 + c];
+            const float4 d = g4[a * 2 + c];
+            if ((cd & 0xffu) == tap) g[0] += d.x;
+            if (((cd >> 8) & 0xffu) == tap) g[1] += d.y;
+            if (((cd >> 16) & 0xffu) == tap) g[2] += d.z;
+            if ((cd >> 24) == tap) g[3] += d.w;
+          }
+        }
+        const float4 zv = z4[dh * 2 + dw];
+        const float za[4] = {zv.x, zv.y, zv.z, zv.w};
+        float o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[c] = kk[c] * (g[c] - fa[c] - (za[c] - m[c]) * r[c] * fb[c]);
+        const int64_t e = (((int64_t)b * H + h) * W + w) * C4 + cq;
+        if (dz16) dz16[e] = mmfn_pack_bf16x4(o[0], o[1], o[2], o[3]);
+        else reinterpret_cast<float4*>(dz)[e] = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ LayerNorm
 __device__ __forceinline__ float act_fwd(float v, int act) {
   if (act == 1) return fmaxf(v, 0.f);
@@ -569,6 +767,54 @@ MMFN_API int mmfn_bn_train_bwd(const float* dy, const float* x, const float* you
       (const float4*)dy, (const float4*)x, (const float4*)yout, mean, rstd, gamma, fin, M, C / 4, (float4*)dx, (float4*)dres,
       dx_bf16 ? (uint2*)dx : nullptr);
   return mmfn_launch_status("bn_train_bwd");
+}
+
+// Stem tail forward: train-mode bn1 -> relu -> maxpool(3, 2, 1) of the two ResNet stems in two launches (batch
+// statistics, then ONE pass that normalises, rectifies and pools; model_rad.py:513-515 image, :519-521 LiDAR).
+// z (B, H, W, C) is the stem convolution's output; out (B, Ho, Wo, C) with Ho = (H - 1) / 2 + 1; out_bf16 (nullable): its
+// bf16 twin; idx (B, Ho, Wo, C) bytes: arg-max tap 0..8 of each window, bit 7 set when the maximum is not positive
+// (ReLU mask for mmfn_stem_bn_relu_maxpool_bwd -- NOT the plain tap mmfn_maxpool3x3s2_bwd expects).  mean / rstd (C)
+// are written; running statistics updated with `momentum`.  ws: as in mmfn_bn_train_fwd.
+MMFN_API int mmfn_stem_bn_relu_maxpool_fwd(const float* z, int B, int H, int W, int C, const float* gamma, const float* beta,
+                                           float* running_mean, float* running_var, float momentum, float eps,
+                                           float* mean, float* rstd, float* out, void* out_bf16, uint8_t* idx,
+                                           double* ws, cudaStream_t stream) {
+  MMFN_CHECK_ARG(z && gamma && beta && mean && rstd && out && idx && ws, "stem_fwd: null pointer");
+  MMFN_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "stem_fwd: bad shape (C % 4 == 0)");
+  MMFN_CHECK_ARG((((uintptr_t)z | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)out) & 15) == 0 &&
+                 ((uintptr_t)out_bf16 & 7) == 0 && ((uintptr_t)idx & 3) == 0, "stem_fwd: alignment");
+  const int64_t M = (int64_t)B * H * W;
+  MMFN_CHECK_ARG(M < (int64_t)1 << 31, "stem_fwd: too many pixels");
+  int rc = mmfn_bn_stats_launch(z, M, C, mean, rstd, running_mean, running_var, momentum, eps, ws, stream);
+  if (rc) return rc;
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  bn_relu_maxpool_fwd_kernel<<<grid_1d((int64_t)B * Ho * Wo * (C / 4), 256), 256, 0, stream>>>(
+      z, mean, rstd, (const float4*)gamma, (const float4*)beta, out, (uint2*)out_bf16, idx, B, H, W, C, Ho, Wo);
+  return mmfn_launch_status("stem_bn_relu_maxpool_fwd");
+}
+
+// Stem tail backward: dout (B, Ho, Wo, C) -> dz (B, H, W, C), the gradient of the stem convolution's output (bf16 when
+// dz_bf16: it only feeds the weight-gradient MMA), through maxpool, ReLU and train-mode BatchNorm; dgamma / dbeta are
+// accumulated.  Two launches: a reduction over the pooled pixels (the only non-zero gradients) and one pass over z.
+MMFN_API int mmfn_stem_bn_relu_maxpool_bwd(const float* dout, const uint8_t* idx, const float* z, const float* mean,
+                                           const float* rstd, const float* gamma, int B, int H, int W, int C, void* dz,
+                                           int dz_bf16, float* dgamma, float* dbeta, double* ws, cudaStream_t stream) {
+  MMFN_CHECK_ARG(dout && idx && z && mean && rstd && gamma && dz && dgamma && dbeta && ws, "stem_bwd: null pointer");
+  MMFN_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "stem_bwd: bad shape (C % 4 == 0)");
+  MMFN_CHECK_ARG((((uintptr_t)dout | (uintptr_t)z | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma | (uintptr_t)dz | (uintptr_t)ws) & 15) == 0 &&
+                 ((uintptr_t)idx & 3) == 0, "stem_bwd: alignment");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const int64_t M = (int64_t)B * H * W, Mp = (int64_t)B * Ho * Wo;
+  MMFN_CHECK_ARG(M < (int64_t)1 << 31, "stem_bwd: too many pixels");
+  int qpr; dim3 grid; int64_t rpb;
+  bn_colsum_grid(Mp, C, qpr, grid, rpb);
+  float* fin = bn_ws_fin(ws, C);
+  BnFinal fz = {nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, fin, dgamma, dbeta};
+  stem_bwd_stats_kernel<<<grid, BN_THREADS, 0, stream>>>((const float4*)dout, idx, z, mean, rstd, H, W, C / 4, Ho, Wo, Mp, M, qpr, rpb, ws, fz);
+  const int Hp = (H + 1) / 2, Wp = (W + 1) / 2;
+  stem_bwd_dx_kernel<<<grid_1d((int64_t)B * Hp * Wp * (C / 4), 256), 256, 0, stream>>>(
+      dout, idx, z, mean, rstd, gamma, fin, B, H, W, C, Ho, Wo, dz_bf16 ? nullptr : (float*)dz, dz_bf16 ? (uint2*)dz : nullptr);
+  return mmfn_launch_status("stem_bn_relu_maxpool_bwd");
 }
 
 namespace {

@@ -217,20 +217,44 @@ class ResLayer:
 
 
 class Stem:
-    """conv7x7/2 -> BN -> ReLU -> MaxPool3x3/2 on the (already NHWC) network input; no dgrad."""
+    """conv7x7/2 -> BN -> ReLU -> MaxPool3x3/2 on the (already NHWC) network input; no dgrad.  Training runs the tail
+    (BN -> ReLU -> pool) as fused kernels (ops.stem_bn_relu_maxpool_*): the pre-pool activation is never written."""
 
     def __init__(self, st, prefix):
         self.cb = ConvBN(st, prefix + ".conv1.weight", prefix + ".bn1", 2, 3, dgrad=False)
+        self.fused = False
 
     def fwd(self, x, train):
-        y = self.cb.fwd(x, relu=True, train=train, no_twin=True)
+        cb = self.cb
+        self.fused = train and ops.FUSE_STEM_TAIL
+        if self.fused:
+            cb.x, cb.relu, cb.bf, cb.col, cb.y = x, True, False, None, None
+            if ops.stem_uses_im2col(x, cb.w):
+                cb.z, cb.col, cb.w_pad = ops.conv2d_fwd_im2col(x, cb.w, cb.stride, cb.pad, getattr(cb, "w_pad", None), bf16=ops.BF16)
+            else:
+                cb.z = ops.conv2d_fwd(x, cb.w, cb.stride, cb.pad)
+            out, self.idx, cb.mean, cb.rstd = ops.stem_bn_relu_maxpool_fwd(cb.z, cb.gam, cb.bet, cb.rm, cb.rv, want16=ops.BF16)
+            return out
+        y = cb.fwd(x, relu=True, train=train, no_twin=True)
         self.in_shape = y.shape
         out, self.idx = ops.maxpool_fwd(y, want16=ops.BF16)
         return out
 
     def bwd(self, d):
+        cb = self.cb
+        if self.fused:
+            col = cb.col
+            dz = ops.stem_bn_relu_maxpool_bwd(d, self.idx, cb.z, cb.mean, cb.rstd, cb.gam, cb.dgam, cb.dbet,
+                                              out_bf16=col is not None and col.dtype == torch.bfloat16)
+            x = cb.x
+            if col is not None:
+                _Aux.run(lambda: ops.conv2d_wgrad_im2col_(dz, col, cb.dw), dz, col)
+            else:
+                _Aux.run(lambda: ops.conv2d_wgrad_(dz, x, cb.dw, cb.stride, cb.pad), dz, x)
+            cb.x = cb.z = cb.col = self.idx = None
+            return
         dy = ops.maxpool_bwd(d, self.idx, self.in_shape)
-        self.cb.bwd(dy, need_dx=False)
+        cb.bwd(dy, need_dx=False)
         self.idx = None
 
 

@@ -3,6 +3,8 @@
 torch supplies device memory and the current stream only; every arithmetic op below is a
 kernel of libmmfn_b200.so.  Tensors are fp32 CUDA tensors; activations are NHWC.
 """
+import os
+
 import torch
 
 from ._lib import lib, MmfnError  # noqa: F401
@@ -512,6 +514,36 @@ def maxpool_bwd(dy, idx, x_shape):
     dx = torch.empty(x_shape, device=dy.device, dtype=torch.float32)
     lib().maxpool3x3s2_bwd(_p(dy), idx.data_ptr(), _p(dx), B, H, W, C, _st())
     return dx
+
+
+# Stem tail (bn1 -> relu -> maxpool) as fused kernels: the pre-pool activation y is never written, the backward reduces
+# over the pooled pixels and makes one pass over z.  False = bn_train_fwd / maxpool_fwd / maxpool_bwd / bn_train_bwd.
+FUSE_STEM_TAIL = os.environ.get("MMFN_FUSE_STEM", "1") != "0"
+
+
+def stem_bn_relu_maxpool_fwd(z, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5, want16=False):
+    """-> (out (+ .h bf16 twin), idx, mean, rstd); idx carries the ReLU mask in bit 7 (see the C header)."""
+    B, H, W, C = z.shape
+    assert C <= BN_WS_MAX_C and z.is_contiguous()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty((B, Ho, Wo, C), device=z.device, dtype=torch.float32)
+    out16 = torch.empty((B, Ho, Wo, C), device=z.device, dtype=BF) if want16 else None
+    idx = torch.empty((B, Ho, Wo, C), device=z.device, dtype=torch.uint8)
+    mean = torch.empty(C, device=z.device, dtype=torch.float32)
+    rstd = torch.empty(C, device=z.device, dtype=torch.float32)
+    lib().stem_bn_relu_maxpool_fwd(_p(z), B, H, W, C, _p(gamma), _p(beta), _p(running_mean), _p(running_var), momentum, eps,
+                                   _p(mean), _p(rstd), _p(out), _p(out16), idx.data_ptr(), _p(_bn_ws(z.device)), _st())
+    return _with_twin(out, out16), idx, mean, rstd
+
+
+def stem_bn_relu_maxpool_bwd(dout, idx, z, mean, rstd, gamma, dgamma, dbeta, out_bf16=False):
+    """-> dz (B, H, W, C), fp32 or bf16; dgamma / dbeta accumulated."""
+    B, H, W, C = z.shape
+    assert dout.is_contiguous() and dout.dtype == torch.float32
+    dz = torch.empty(z.shape, device=z.device, dtype=BF if out_bf16 else torch.float32)
+    lib().stem_bn_relu_maxpool_bwd(_p(dout), idx.data_ptr(), _p(z), _p(mean), _p(rstd), _p(gamma), B, H, W, C, _p(dz),
+                                   int(out_bf16), _p(dgamma), _p(dbeta), _p(_bn_ws(z.device)), _st())
+    return dz
 
 
 def _four(ts):

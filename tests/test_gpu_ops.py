@@ -268,6 +268,47 @@ def test_batchnorm_train_forward_backward():
         close(dg, bn.weight.grad, 1e-4); close(db, bn.bias.grad, 1e-4)
 
 
+@pytest.mark.parametrize("geom", [(2, 64, 64, 64), (3, 31, 29, 8), (1, 8, 10, 128), (2, 33, 64, 96)], ids=lambda g: "N%dH%dW%dC%d" % g)
+def test_stem_tail_bn_relu_maxpool_fused(geom):
+    """ops.stem_bn_relu_maxpool_fwd / _bwd (BatchNorm -> ReLU -> MaxPool(3, 2, 1) of the ResNet stems, model_rad.py:513-521)
+    against torch autograd, and against the unfused kernels of the library (same values, same arg-max taps).  A negative
+    BatchNorm bias makes most windows tie at zero (first-tap rule + ReLU mask in bit 7 of the arg-max byte)."""
+    from mmfn_b200 import ops
+    N, H, W, C = geom
+    for bias_shift in (0.0, -1.5):
+        x = torch.randn(N, C, H, W) * 2 + 0.5
+        bn = torch.nn.BatchNorm2d(C).train()
+        with torch.no_grad():
+            bn.weight.uniform_(-1.5, 1.5); bn.bias.normal_().add_(bias_shift)        # negative gammas too
+        rm, rv = bn.running_mean.clone().to(DEV), bn.running_var.clone().to(DEV)
+        xr = x.clone().requires_grad_(True)
+        yr = F.max_pool2d(torch.relu(bn(xr)), 3, 2, 1)
+        dy = torch.randn_like(yr)
+        yr.backward(dy)
+        z = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+        g, b = bn.weight.data.to(DEV), bn.bias.data.to(DEV)
+        out, idx, mean, rstd = ops.stem_bn_relu_maxpool_fwd(z, g, b, rm, rv, want16=True)
+        close(out.permute(0, 3, 1, 2), yr, 1e-5)
+        close(rm, bn.running_mean, 1e-5); close(rv, bn.running_var, 1e-5)
+        assert torch.equal(out.h, out.to(torch.bfloat16))
+        # unfused library path: identical pooled values; identical taps; bit 7 <=> pooled value is not positive
+        y = ops.bn_apply(z, g, b, mean, rstd, relu=True)
+        out2, idx2 = ops.maxpool_fwd(y)
+        assert torch.equal(out, out2)
+        assert torch.equal(idx & 0x7F, idx2)
+        assert torch.equal((idx & 0x80) != 0, ~(out > 0))
+        dyn = dy.permute(0, 2, 3, 1).contiguous().to(DEV)
+        for bf in (False, True):
+            dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+            dz = ops.stem_bn_relu_maxpool_bwd(dyn, idx, z, mean, rstd, g, dg, db, out_bf16=bf)
+            close(dz.permute(0, 3, 1, 2), xr.grad, 1e-2 if bf else 1e-4)
+            close(dg, bn.weight.grad, 1e-4); close(db, bn.bias.grad, 1e-4)
+            # the unfused chain of the library computes the same gradient
+            dg2, db2 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+            dz2, _ = ops.bn_train_bwd(ops.maxpool_bwd(dyn, idx2, y.shape), z, y, mean, rstd, g, dg2, db2, out_bf16=bf)
+            close(dz, dz2, 1e-2 if bf else 1e-5); close(dg, dg2, 1e-5); close(db, db2, 1e-5)
+
+
 def test_layernorm_variants():
     from mmfn_b200 import ops
     for C, act in [(64, 0), (64, 1), (128, 2), (512, 0)]:
