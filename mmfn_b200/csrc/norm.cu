@@ -367,7 +367,8 @@ constexpr int BN_SMALL_ROWS = 2048;
 __global__ void __launch_bounds__(256)
 bn_relu_maxpool_fwd_kernel(const float* __restrict__ z, const float* __restrict__ mean, const float* __restrict__ rstd,
                            const float4* __restrict__ gamma, const float4* __restrict__ beta, float* __restrict__ out,
-                           uint2* __restrict__ out16, uint8_t* __restrict__ idx, int B, int H, int W, int C, int Ho, int Wo) {
+                           uint2* __restrict__ out16, uint8_t* __restrict__ idx, float4* __restrict__ zmax,
+                           int B, int H, int W, int C, int Ho, int Wo) {
   const int C4 = C >> 2;
   const int64_t n = (int64_t)B * Ho * Wo * C4;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -402,7 +403,7 @@ bn_relu_maxpool_fwd_kernel(const float* __restrict__ z, const float* __restrict_
         v[r * 3 + sx] = __ldg(reinterpret_cast<const float4*>(z + (((int64_t)b * H + hc) * W + wc) * C) + cq);
       }
     }
-    float best[4] = {0.f, 0.f, 0.f, 0.f};
+    float best[4] = {0.f, 0.f, 0.f, 0.f}, zb[4] = {0.f, 0.f, 0.f, 0.f};
     int bi[4] = {-1, -1, -1, -1};
 #pragma unroll
     for (int tp = 0; tp < 9; ++tp) {
@@ -411,10 +412,11 @@ bn_relu_maxpool_fwd_kernel(const float* __restrict__ z, const float* __restrict_
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const float y = fmaxf((a[c] - m[c]) * k[c] * gk[c] + bt[c], 0.f);
-        if (bi[c] < 0 || y > best[c] || y != y) { best[c] = y; bi[c] = tp; }
+        if (bi[c] < 0 || y > best[c] || y != y) { best[c] = y; bi[c] = tp; zb[c] = a[c]; }
       }
     }
     *reinterpret_cast<float4*>(out + (i << 2)) = make_float4(best[0], best[1], best[2], best[3]);
+    if (zmax) zmax[i] = make_float4(zb[0], zb[1], zb[2], zb[3]);
     if (out16) out16[i] = mmfn_pack_bf16x4(best[0], best[1], best[2], best[3]);
     uint32_t code = 0;
 #pragma unroll
@@ -425,14 +427,15 @@ bn_relu_maxpool_fwd_kernel(const float* __restrict__ z, const float* __restrict_
 
 // Reduction half of the backward.  The gradient of the BatchNorm output is non-zero only at the arg-max position of
 // each pooling window, so sum(dy') and sum(dy' * xhat) run over the POOLED pixels: rows = (b, ho, wo), the thread layout
-// of bn_colsum_kernel; z is gathered at the arg-max tap (each lane its own channel, 4-byte loads).
+// of bn_colsum_kernel.  The forward saved z at the arg-max (`zmax`), so this is a pure stream over three pooled-size
+// tensors (a gather of z at the arg-max tap measured 84 us at B = 32: 4-byte loads of 32-byte sectors, dependent on
+// the arg-max load).
 __global__ void __launch_bounds__(BN_THREADS)
-stem_bwd_stats_kernel(const float4* __restrict__ dout, const uint8_t* __restrict__ idx, const float* __restrict__ z,
-                      const float* __restrict__ mean, const float* __restrict__ rstd, int H, int W, int C4, int Ho, int Wo,
+stem_bwd_stats_kernel(const float4* __restrict__ dout, const uint8_t* __restrict__ idx, const float4* __restrict__ zmax,
+                      const float* __restrict__ mean, const float* __restrict__ rstd, int C4,
                       int64_t Mp, int64_t M, int qpr, int64_t rows_per_block, double* __restrict__ ws, BnFinal fz) {
   const int q = threadIdx.x % qpr, rsub = threadIdx.x / qpr, nrs = BN_THREADS / qpr;
   const int cq = blockIdx.x * qpr + q;
-  const int C = C4 * 4;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(Mp, r0 + rows_per_block);
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (cq < C4) {
@@ -442,19 +445,13 @@ stem_bwd_stats_kernel(const float4* __restrict__ dout, const uint8_t* __restrict
     for (int64_t r = r0 + rsub; r < r1; r += nrs) {
       const uint32_t code = __ldg(reinterpret_cast<const uint32_t*>(idx) + r * C4 + cq);
       const float4 gv = __ldg(dout + r * C4 + cq);
-      const float ga[4] = {gv.x, gv.y, gv.z, gv.w};
-      const int t = (int)r;
-      const int wo = t % Wo, t2 = t / Wo;
-      const int ho = t2 % Ho, b = t2 / Ho;
-      const float* zb = z + (((int64_t)b * H + (ho * 2 - 1)) * W + (wo * 2 - 1)) * C + cq * 4;
+      const float4 zv = __ldg(zmax + r * C4 + cq);
+      const float ga[4] = {gv.x, gv.y, gv.z, gv.w}, za[4] = {zv.x, zv.y, zv.z, zv.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const uint32_t byte = (code >> (8 * k)) & 0xffu;
-        if (byte & 0x80u) continue;                                 // ReLU mask: the maximum was not positive
-        const int dr = (int)byte / 3, dc = (int)byte - dr * 3;
-        const float xv = __ldg(zb + ((int64_t)dr * W + dc) * C + k);
+        if ((code >> (8 * k)) & 0x80u) continue;                    // ReLU mask: the maximum was not positive
         acc[k] += ga[k];
-        acc[4 + k] += (double)ga[k] * ((xv - m4[k]) * r4[k]);
+        acc[4 + k] += (double)ga[k] * ((za[k] - m4[k]) * r4[k]);
       }
     }
   }
@@ -769,39 +766,44 @@ MMFN_API int mmfn_bn_train_bwd(const float* dy, const float* x, const float* you
   return mmfn_launch_status("bn_train_bwd");
 }
 
+static inline int stem_grid(int64_t n) { const int64_t b = ceil_div64(n, 256); return (int)(b < 1 ? 1 : (b > 148 * 6 ? 148 * 6 : b)); }
+
 // Stem tail forward: train-mode bn1 -> relu -> maxpool(3, 2, 1) of the two ResNet stems in two launches (batch
 // statistics, then ONE pass that normalises, rectifies and pools; model_rad.py:513-515 image, :519-521 LiDAR).
 // z (B, H, W, C) is the stem convolution's output; out (B, Ho, Wo, C) with Ho = (H - 1) / 2 + 1; out_bf16 (nullable): its
 // bf16 twin; idx (B, Ho, Wo, C) bytes: arg-max tap 0..8 of each window, bit 7 set when the maximum is not positive
-// (ReLU mask for mmfn_stem_bn_relu_maxpool_bwd -- NOT the plain tap mmfn_maxpool3x3s2_bwd expects).  mean / rstd (C)
-// are written; running statistics updated with `momentum`.  ws: as in mmfn_bn_train_fwd.
+// (ReLU mask for mmfn_stem_bn_relu_maxpool_bwd -- NOT the plain tap mmfn_maxpool3x3s2_bwd expects); zmax (B, Ho, Wo, C):
+// z at the arg-max, saved for the backward reduction.  mean / rstd (C) are written; running statistics updated with
+// `momentum`.  ws: as in mmfn_bn_train_fwd.
 MMFN_API int mmfn_stem_bn_relu_maxpool_fwd(const float* z, int B, int H, int W, int C, const float* gamma, const float* beta,
                                            float* running_mean, float* running_var, float momentum, float eps,
-                                           float* mean, float* rstd, float* out, void* out_bf16, uint8_t* idx,
+                                           float* mean, float* rstd, float* out, void* out_bf16, uint8_t* idx, float* zmax,
                                            double* ws, cudaStream_t stream) {
-  MMFN_CHECK_ARG(z && gamma && beta && mean && rstd && out && idx && ws, "stem_fwd: null pointer");
+  MMFN_CHECK_ARG(z && gamma && beta && mean && rstd && out && idx && zmax && ws, "stem_fwd: null pointer");
   MMFN_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "stem_fwd: bad shape (C % 4 == 0)");
-  MMFN_CHECK_ARG((((uintptr_t)z | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)out) & 15) == 0 &&
+  MMFN_CHECK_ARG((((uintptr_t)z | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)out | (uintptr_t)zmax) & 15) == 0 &&
                  ((uintptr_t)out_bf16 & 7) == 0 && ((uintptr_t)idx & 3) == 0, "stem_fwd: alignment");
   const int64_t M = (int64_t)B * H * W;
   MMFN_CHECK_ARG(M < (int64_t)1 << 31, "stem_fwd: too many pixels");
   int rc = mmfn_bn_stats_launch(z, M, C, mean, rstd, running_mean, running_var, momentum, eps, ws, stream);
   if (rc) return rc;
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  bn_relu_maxpool_fwd_kernel<<<grid_1d((int64_t)B * Ho * Wo * (C / 4), 256), 256, 0, stream>>>(
-      z, mean, rstd, (const float4*)gamma, (const float4*)beta, out, (uint2*)out_bf16, idx, B, H, W, C, Ho, Wo);
+  // 72 / 80 registers: three CTAs per SM -> grids of two full waves (148 x 3 x 2), not grid_1d's eight CTAs per SM
+  bn_relu_maxpool_fwd_kernel<<<stem_grid((int64_t)B * Ho * Wo * (C / 4)), 256, 0, stream>>>(
+      z, mean, rstd, (const float4*)gamma, (const float4*)beta, out, (uint2*)out_bf16, idx, (float4*)zmax, B, H, W, C, Ho, Wo);
   return mmfn_launch_status("stem_bn_relu_maxpool_fwd");
 }
 
 // Stem tail backward: dout (B, Ho, Wo, C) -> dz (B, H, W, C), the gradient of the stem convolution's output (bf16 when
 // dz_bf16: it only feeds the weight-gradient MMA), through maxpool, ReLU and train-mode BatchNorm; dgamma / dbeta are
-// accumulated.  Two launches: a reduction over the pooled pixels (the only non-zero gradients) and one pass over z.
-MMFN_API int mmfn_stem_bn_relu_maxpool_bwd(const float* dout, const uint8_t* idx, const float* z, const float* mean,
+// accumulated.  idx / zmax: as written by the forward.  Two launches: a reduction over the pooled pixels (the only
+// non-zero gradients) and one pass over z.
+MMFN_API int mmfn_stem_bn_relu_maxpool_bwd(const float* dout, const uint8_t* idx, const float* z, const float* zmax, const float* mean,
                                            const float* rstd, const float* gamma, int B, int H, int W, int C, void* dz,
                                            int dz_bf16, float* dgamma, float* dbeta, double* ws, cudaStream_t stream) {
-  MMFN_CHECK_ARG(dout && idx && z && mean && rstd && gamma && dz && dgamma && dbeta && ws, "stem_bwd: null pointer");
+  MMFN_CHECK_ARG(dout && idx && z && zmax && mean && rstd && gamma && dz && dgamma && dbeta && ws, "stem_bwd: null pointer");
   MMFN_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "stem_bwd: bad shape (C % 4 == 0)");
-  MMFN_CHECK_ARG((((uintptr_t)dout | (uintptr_t)z | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma | (uintptr_t)dz | (uintptr_t)ws) & 15) == 0 &&
+  MMFN_CHECK_ARG((((uintptr_t)dout | (uintptr_t)z | (uintptr_t)zmax | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma | (uintptr_t)dz | (uintptr_t)ws) & 15) == 0 &&
                  ((uintptr_t)idx & 3) == 0, "stem_bwd: alignment");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const int64_t M = (int64_t)B * H * W, Mp = (int64_t)B * Ho * Wo;
@@ -810,9 +812,9 @@ MMFN_API int mmfn_stem_bn_relu_maxpool_bwd(const float* dout, const uint8_t* idx
   bn_colsum_grid(Mp, C, qpr, grid, rpb);
   float* fin = bn_ws_fin(ws, C);
   BnFinal fz = {nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, fin, dgamma, dbeta};
-  stem_bwd_stats_kernel<<<grid, BN_THREADS, 0, stream>>>((const float4*)dout, idx, z, mean, rstd, H, W, C / 4, Ho, Wo, Mp, M, qpr, rpb, ws, fz);
+  stem_bwd_stats_kernel<<<grid, BN_THREADS, 0, stream>>>((const float4*)dout, idx, (const float4*)zmax, mean, rstd, C / 4, Mp, M, qpr, rpb, ws, fz);
   const int Hp = (H + 1) / 2, Wp = (W + 1) / 2;
-  stem_bwd_dx_kernel<<<grid_1d((int64_t)B * Hp * Wp * (C / 4), 256), 256, 0, stream>>>(
+  stem_bwd_dx_kernel<<<stem_grid((int64_t)B * Hp * Wp * (C / 4)), 256, 0, stream>>>(
       dout, idx, z, mean, rstd, gamma, fin, B, H, W, C, Ho, Wo, dz_bf16 ? nullptr : (float*)dz, dz_bf16 ? (uint2*)dz : nullptr);
   return mmfn_launch_status("stem_bn_relu_maxpool_bwd");
 }

@@ -137,7 +137,7 @@ class ConvBN:
 
     def fwd(self, x, res=None, relu=True, train=True, no_twin=False):
         self.x, self.relu = x, relu
-        self.col = None
+        self.col, self.direct = None, False
         # bf16 configuration: the convolution reads the bf16 twin its producer wrote (x.h) and the bf16 filter shadow;
         # its fp32 output z feeds the batch statistics; BatchNorm-apply writes y in fp32 AND its bf16 twin
         Ho, Wo = ops.conv_out_hw(x.shape[1], x.shape[2], self.w.shape[1], self.w.shape[2], self.stride, self.pad)
@@ -151,6 +151,9 @@ class ConvBN:
             return self.y
         if self.bf:
             self.z = ops.conv2d_fwd(x.h, self.w16, self.stride, self.pad)
+        elif ops.stem_conv_direct_ok(x, self.w, self.stride, self.pad):
+            # stems: direct tensor-core kernel on a shared-memory input patch (no column matrix)
+            self.z, self.direct = ops.conv2d_stem7_fwd(x, self.w), True
         elif ops.stem_uses_im2col(x, self.w):
             # stems: im2col + one dense tensor-core GEMM; the column matrix is kept for the weight gradient
             self.z, self.col, self.w_pad = ops.conv2d_fwd_im2col(x, self.w, self.stride, self.pad, getattr(self, "w_pad", None),
@@ -165,11 +168,14 @@ class ConvBN:
     def bwd(self, dy, need_dx=True, want_dres=False, dx_res=None):
         dz, dres = ops.bn_train_bwd(dy, self.z, self.y if self.relu else None, self.mean, self.rstd, self.gam,
                                     self.dgam, self.dbet, want_dres,
-                                    out_bf16=self.bf or (self.col is not None and self.col.dtype == torch.bfloat16))
+                                    out_bf16=self.bf or (self.col is not None and self.col.dtype == torch.bfloat16)
+                                    or (self.direct and ops.BF16))
         x, col = self.x, self.col
         if self.bf:
             x16 = x.h
             _Aux.run(lambda: ops.conv2d_wgrad_(dz, x16, self.dw, self.stride, self.pad), dz, x16)
+        elif self.direct:
+            _Aux.run(lambda: ops.conv2d_stem7_wgrad_(dz, x, self.dw), dz, x)
         elif col is not None:
             _Aux.run(lambda: ops.conv2d_wgrad_im2col_(dz, col, self.dw), dz, col)
         else:
@@ -228,8 +234,10 @@ class Stem:
         cb = self.cb
         self.fused = train and ops.FUSE_STEM_TAIL
         if self.fused:
-            cb.x, cb.relu, cb.bf, cb.col, cb.y = x, True, False, None, None
-            if ops.stem_uses_im2col(x, cb.w):
+            cb.x, cb.relu, cb.bf, cb.col, cb.y, cb.direct = x, True, False, None, None, False
+            if ops.stem_conv_direct_ok(x, cb.w, cb.stride, cb.pad):
+                cb.z, cb.direct = ops.conv2d_stem7_fwd(x, cb.w), True
+            elif ops.stem_uses_im2col(x, cb.w):
                 cb.z, cb.col, cb.w_pad = ops.conv2d_fwd_im2col(x, cb.w, cb.stride, cb.pad, getattr(cb, "w_pad", None), bf16=ops.BF16)
             else:
                 cb.z = ops.conv2d_fwd(x, cb.w, cb.stride, cb.pad)
@@ -245,9 +253,11 @@ class Stem:
         if self.fused:
             col = cb.col
             dz = ops.stem_bn_relu_maxpool_bwd(d, self.idx, cb.z, cb.mean, cb.rstd, cb.gam, cb.dgam, cb.dbet,
-                                              out_bf16=col is not None and col.dtype == torch.bfloat16)
+                                              out_bf16=(col is not None and col.dtype == torch.bfloat16) or (cb.direct and ops.BF16))
             x = cb.x
-            if col is not None:
+            if cb.direct:
+                _Aux.run(lambda: ops.conv2d_stem7_wgrad_(dz, x, cb.dw), dz, x)
+            elif col is not None:
                 _Aux.run(lambda: ops.conv2d_wgrad_im2col_(dz, col, cb.dw), dz, col)
             else:
                 _Aux.run(lambda: ops.conv2d_wgrad_(dz, x, cb.dw, cb.stride, cb.pad), dz, x)

@@ -317,6 +317,35 @@ def conv2d_fwd_im2col(x, w_krsc, stride, pad, w_pad=None, bf16=False):
     return y, col, w_pad
 
 
+# Stem convolutions (7x7 / 2, 3 or 2 input channels) as a direct tensor-core kernel that gathers its operand from a
+# shared-memory input patch: no column matrix in HBM.  False = im2col + dense GEMM (conv2d_fwd_im2col).
+DIRECT_STEM_CONV = os.environ.get("MMFN_DIRECT_STEM", "1") != "0"
+
+
+def stem_conv_direct_ok(x, w_krsc, stride, pad):
+    return (TF32 and DIRECT_STEM_CONV and x.dtype == torch.float32 and x.shape[-1] in (2, 3) and stride == 2 and pad == 3
+            and tuple(w_krsc.shape[:3]) == (64, 7, 7))
+
+
+def conv2d_stem7_fwd(x, w_krsc):
+    N, H, W, C = x.shape
+    assert x.is_contiguous() and w_krsc.is_contiguous() and tuple(w_krsc.shape) == (64, 7, 7, C)
+    Ho, Wo = conv_out_hw(H, W, 7, 7, 2, 3)
+    z = torch.empty((N, Ho, Wo, 64), device=x.device, dtype=torch.float32)
+    lib().next_work = _conv_work(N, H, W, C, 64, 7, 7, Ho, Wo)
+    lib().conv2d_stem7_fwd(_p(x), _p(w_krsc), _p(z), N, H, W, C, _st())
+    return z
+
+
+def conv2d_stem7_wgrad_(dz, x, dw_krsc):
+    """dw_krsc (64, 7, 7, C) += weight gradient; dz (N, Ho, Wo, 64) fp32 or bf16."""
+    N, H, W, C = x.shape
+    Ho, Wo = conv_out_hw(H, W, 7, 7, 2, 3)
+    assert dz.is_contiguous() and x.is_contiguous() and dw_krsc.is_contiguous() and tuple(dz.shape) == (N, Ho, Wo, 64)
+    lib().next_work = _conv_work(N, H, W, C, 64, 7, 7, Ho, Wo)
+    lib().conv2d_stem7_wgrad(_p(dz), int(dz.dtype == BF), _p(x), _p(dw_krsc), N, H, W, C, _st())
+
+
 def conv2d_wgrad_im2col_(dy, col, dw_krsc):
     """dw_krsc (Co, R, S, C) += dy^T col  -- one split-K tensor-core GEMM over all output pixels."""
     Co = dw_krsc.shape[0]
@@ -522,18 +551,20 @@ FUSE_STEM_TAIL = os.environ.get("MMFN_FUSE_STEM", "1") != "0"
 
 
 def stem_bn_relu_maxpool_fwd(z, gamma, beta, running_mean, running_var, momentum=0.1, eps=1e-5, want16=False):
-    """-> (out (+ .h bf16 twin), idx, mean, rstd); idx carries the ReLU mask in bit 7 (see the C header)."""
+    """-> (out (+ .h bf16 twin), (idx, zmax), mean, rstd); idx carries the ReLU mask in bit 7, zmax is z at the arg-max
+    (see the C header): the pair is what stem_bn_relu_maxpool_bwd wants back."""
     B, H, W, C = z.shape
     assert C <= BN_WS_MAX_C and z.is_contiguous()
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     out = torch.empty((B, Ho, Wo, C), device=z.device, dtype=torch.float32)
     out16 = torch.empty((B, Ho, Wo, C), device=z.device, dtype=BF) if want16 else None
     idx = torch.empty((B, Ho, Wo, C), device=z.device, dtype=torch.uint8)
+    zmax = torch.empty((B, Ho, Wo, C), device=z.device, dtype=torch.float32)
     mean = torch.empty(C, device=z.device, dtype=torch.float32)
     rstd = torch.empty(C, device=z.device, dtype=torch.float32)
     lib().stem_bn_relu_maxpool_fwd(_p(z), B, H, W, C, _p(gamma), _p(beta), _p(running_mean), _p(running_var), momentum, eps,
-                                   _p(mean), _p(rstd), _p(out), _p(out16), idx.data_ptr(), _p(_bn_ws(z.device)), _st())
-    return _with_twin(out, out16), idx, mean, rstd
+                                   _p(mean), _p(rstd), _p(out), _p(out16), idx.data_ptr(), _p(zmax), _p(_bn_ws(z.device)), _st())
+    return _with_twin(out, out16), (idx, zmax), mean, rstd
 
 
 def stem_bn_relu_maxpool_bwd(dout, idx, z, mean, rstd, gamma, dgamma, dbeta, out_bf16=False):
@@ -541,7 +572,8 @@ def stem_bn_relu_maxpool_bwd(dout, idx, z, mean, rstd, gamma, dgamma, dbeta, out
     B, H, W, C = z.shape
     assert dout.is_contiguous() and dout.dtype == torch.float32
     dz = torch.empty(z.shape, device=z.device, dtype=BF if out_bf16 else torch.float32)
-    lib().stem_bn_relu_maxpool_bwd(_p(dout), idx.data_ptr(), _p(z), _p(mean), _p(rstd), _p(gamma), B, H, W, C, _p(dz),
+    idx, zmax = idx
+    lib().stem_bn_relu_maxpool_bwd(_p(dout), idx.data_ptr(), _p(z), _p(zmax), _p(mean), _p(rstd), _p(gamma), B, H, W, C, _p(dz),
                                    int(out_bf16), _p(dgamma), _p(dbeta), _p(_bn_ws(z.device)), _st())
     return dz
 

@@ -90,6 +90,36 @@ def test_stem_conv_as_im2col_tensor_core_gemm(C):
     close(y4.permute(0, 3, 1, 2), F.conv2d(x4, w4, stride=1, padding=1), 3e-3)
 
 
+@pytest.mark.parametrize("geom", [(2, 256, 256), (1, 37, 150), (3, 9, 13), (1, 130, 258)], ids=lambda g: "N%dH%dW%d" % g)
+@pytest.mark.parametrize("C", [3, 2])
+def test_stem_conv_direct_no_column_matrix(C, geom):
+    """ops.conv2d_stem7_fwd / conv2d_stem7_wgrad_ (csrc/stem_conv.cu: 7x7 / 2 / pad 3, C -> 64, operand gathered from a
+    shared-memory input patch, TF32 mma.sync) against torch fp32 conv2d: ragged tiles (output sizes that are not multiples
+    of the 2 x 64 tile), images smaller than one tile, fp32 and bf16 gradients, accumulation on top of an existing dw."""
+    from mmfn_b200 import ops
+    N, H, W = geom
+    x = torch.randn(N, C, H, W)
+    w = torch.randn(64, C, 7, 7) * (2.0 / (C * 49)) ** 0.5
+    xr, wr = x.clone(), w.clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, stride=2, padding=3)
+    dy = torch.randn_like(yr)
+    yr.backward(dy)
+    xn = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    wk = w.permute(0, 2, 3, 1).contiguous().to(DEV)
+    assert ops.stem_conv_direct_ok(xn, wk, 2, 3)
+    z = ops.conv2d_stem7_fwd(xn, wk)
+    assert z.shape == yr.permute(0, 2, 3, 1).shape
+    close(z.permute(0, 3, 1, 2), yr, 3e-3)
+    dyn = dy.permute(0, 2, 3, 1).contiguous().to(DEV)
+    dw = torch.ones_like(wk)
+    ops.conv2d_stem7_wgrad_(dyn, xn, dw)
+    close(dw.permute(0, 3, 1, 2) - 1.0, wr.grad, 3e-3)
+    dw16 = torch.zeros_like(wk)
+    ops.conv2d_stem7_wgrad_(dyn.to(torch.bfloat16), xn, dw16)
+    close(dw16.permute(0, 3, 1, 2), wr.grad, 1e-2)
+
+
+
 @pytest.mark.parametrize("C,T", [(64, 192), (128, 192), (256, 192), (512, 256)])
 def test_linear_gemms_and_epilogues_tf32(C, T):
     """qkv / proj / mlp GEMM shapes of one fusion-transformer block, forward and both backward products."""
@@ -287,7 +317,8 @@ def test_stem_tail_bn_relu_maxpool_fused(geom):
         yr.backward(dy)
         z = x.permute(0, 2, 3, 1).contiguous().to(DEV)
         g, b = bn.weight.data.to(DEV), bn.bias.data.to(DEV)
-        out, idx, mean, rstd = ops.stem_bn_relu_maxpool_fwd(z, g, b, rm, rv, want16=True)
+        out, saved, mean, rstd = ops.stem_bn_relu_maxpool_fwd(z, g, b, rm, rv, want16=True)
+        idx, zmax = saved
         close(out.permute(0, 3, 1, 2), yr, 1e-5)
         close(rm, bn.running_mean, 1e-5); close(rv, bn.running_var, 1e-5)
         assert torch.equal(out.h, out.to(torch.bfloat16))
@@ -297,10 +328,11 @@ def test_stem_tail_bn_relu_maxpool_fused(geom):
         assert torch.equal(out, out2)
         assert torch.equal(idx & 0x7F, idx2)
         assert torch.equal((idx & 0x80) != 0, ~(out > 0))
+        assert torch.equal(ops.bn_apply(zmax, g, b, mean, rstd, relu=True), out)       # zmax = z at the arg-max
         dyn = dy.permute(0, 2, 3, 1).contiguous().to(DEV)
         for bf in (False, True):
             dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
-            dz = ops.stem_bn_relu_maxpool_bwd(dyn, idx, z, mean, rstd, g, dg, db, out_bf16=bf)
+            dz = ops.stem_bn_relu_maxpool_bwd(dyn, saved, z, mean, rstd, g, dg, db, out_bf16=bf)
             close(dz.permute(0, 3, 1, 2), xr.grad, 1e-2 if bf else 1e-4)
             close(dg, bn.weight.grad, 1e-4); close(db, bn.bias.grad, 1e-4)
             # the unfused chain of the library computes the same gradient
