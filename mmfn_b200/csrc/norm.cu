@@ -26,6 +26,32 @@ struct BnFinal {
   float* fin; float* dgamma; float* dbeta;                                                  // backward
 };
 
+// ReLU mask of the BatchNorm backward: where the forward output was not positive the incoming gradient is dropped.
+// The mask comes from the saved output y (fp32, or its bf16 twin: half the bytes, same sign), or -- when nothing was
+// added between BatchNorm and ReLU -- is recomputed from z, which the backward reads anyway (no third stream at all);
+// the expression is bn_apply_kernel's, term for term.
+enum { BN_MASK_NONE = 0, BN_MASK_Y32 = 1, BN_MASK_Y16 = 2, BN_MASK_Z = 3 };
+__device__ __forceinline__ void bn_relu_mask4(float* ga, int mode, const void* __restrict__ yout, int64_t i, const float* xa,
+                                              const float* m4, const float* r4, const float* g4, const float* b4) {
+  if (mode == BN_MASK_Y32) {
+    const float4 yv = __ldg(reinterpret_cast<const float4*>(yout) + i);
+    if (!(yv.x > 0.f)) ga[0] = 0.f;
+    if (!(yv.y > 0.f)) ga[1] = 0.f;
+    if (!(yv.z > 0.f)) ga[2] = 0.f;
+    if (!(yv.w > 0.f)) ga[3] = 0.f;
+  } else if (mode == BN_MASK_Y16) {
+    const float4 yv = mmfn_unpack_bf16x4(__ldg(reinterpret_cast<const uint2*>(yout) + i));
+    if (!(yv.x > 0.f)) ga[0] = 0.f;
+    if (!(yv.y > 0.f)) ga[1] = 0.f;
+    if (!(yv.z > 0.f)) ga[2] = 0.f;
+    if (!(yv.w > 0.f)) ga[3] = 0.f;
+  } else if (mode == BN_MASK_Z) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (!((xa[k] - m4[k]) * r4[k] * g4[k] + b4[k] > 0.f)) ga[k] = 0.f;
+  }
+}
+
 // Block-level tail shared by the column-reduction kernels: fold the per-thread fp64 partials (thread = quad q of
 // `qpr`, row lane threadIdx.x / qpr) over the row lanes, add them into scratch slot `slot`, and let the LAST CTA of the
 // launch (`n_ctas` arrivals) fold the slots, publish and re-zero the scratch.
@@ -92,19 +118,25 @@ __device__ __forceinline__ void bn_reduce_publish(const double (&acc)[8], int qp
 
 template <bool BWD>
 __global__ void __launch_bounds__(BN_THREADS)
-bn_colsum_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float4* __restrict__ yout,
-                 const float* __restrict__ mean, const float* __restrict__ rstd, int64_t M, int C4, int qpr,
+bn_colsum_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const void* __restrict__ yout, int mask_mode,
+                 const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, int64_t M, int C4, int qpr,
                  int64_t rows_per_block, double* __restrict__ ws, BnFinal fz) {
   const int q = threadIdx.x % qpr, rsub = threadIdx.x / qpr, nrs = BN_THREADS / qpr;
   const int cq = blockIdx.x * qpr + q;                          // channel quad of this thread
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (cq < C4) {
-    float m4[4] = {0.f, 0.f, 0.f, 0.f}, r4[4] = {1.f, 1.f, 1.f, 1.f};
+    float m4[4] = {0.f, 0.f, 0.f, 0.f}, r4[4] = {1.f, 1.f, 1.f, 1.f}, g4[4] = {0.f, 0.f, 0.f, 0.f}, b4[4] = {0.f, 0.f, 0.f, 0.f};
     if (BWD) {
       const float4 mm = __ldg(reinterpret_cast<const float4*>(mean) + cq), rr = __ldg(reinterpret_cast<const float4*>(rstd) + cq);
       m4[0] = mm.x; m4[1] = mm.y; m4[2] = mm.z; m4[3] = mm.w;
       r4[0] = rr.x; r4[1] = rr.y; r4[2] = rr.z; r4[3] = rr.w;
+      if (mask_mode == BN_MASK_Z) {
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(gamma) + cq), bb = __ldg(reinterpret_cast<const float4*>(beta) + cq);
+        g4[0] = gg.x; g4[1] = gg.y; g4[2] = gg.z; g4[3] = gg.w;
+        b4[0] = bb.x; b4[1] = bb.y; b4[2] = bb.z; b4[3] = bb.w;
+      }
     }
 #pragma unroll 4
     for (int64_t r = r0 + rsub; r < r1; r += nrs) {
@@ -116,13 +148,7 @@ bn_colsum_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, co
       } else {
         const float4 gv = __ldg(dy + r * C4 + cq);
         float ga[4] = {gv.x, gv.y, gv.z, gv.w};
-        if (yout) {
-          const float4 yv = __ldg(yout + r * C4 + cq);
-          if (!(yv.x > 0.f)) ga[0] = 0.f;
-          if (!(yv.y > 0.f)) ga[1] = 0.f;
-          if (!(yv.z > 0.f)) ga[2] = 0.f;
-          if (!(yv.w > 0.f)) ga[3] = 0.f;
-        }
+        bn_relu_mask4(ga, mask_mode, yout, r * C4 + cq, xa, m4, r4, g4, b4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) { acc[k] += ga[k]; acc[4 + k] += (double)ga[k] * ((xa[k] - m4[k]) * r4[k]); }
       }
@@ -186,8 +212,8 @@ bn_apply_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n4
 // fin = [mean(dy') | mean(dy' xhat)] published by the reduction kernel.  Same fixed-channel-quad streaming loop.
 __global__ void __launch_bounds__(256)
 bn_bwd_dx_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
-                 const float4* __restrict__ yout, const float* __restrict__ mean,
-                 const float* __restrict__ rstd, const float* __restrict__ gamma,
+                 const void* __restrict__ yout, int mask_mode, const float* __restrict__ mean,
+                 const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                  const float* __restrict__ fin, int64_t M, int C4,
                  float4* __restrict__ dx, float4* __restrict__ dres, uint2* __restrict__ dx16) {
   const int C = C4 * 4;
@@ -197,6 +223,7 @@ bn_bwd_dx_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
   const bool fixed = stride % C4 == 0;
   int c = (int)(i0 % C4);
   float4 m, r, k, a, b;
+  float m4[4], r4[4], g4[4], b4[4];
   auto coef = [&](int cq) {
     m = __ldg(reinterpret_cast<const float4*>(mean) + cq);
     r = __ldg(reinterpret_cast<const float4*>(rstd) + cq);
@@ -204,20 +231,29 @@ bn_bwd_dx_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
     k = make_float4(g.x * r.x, g.y * r.y, g.z * r.z, g.w * r.w);
     a = __ldg(reinterpret_cast<const float4*>(fin) + cq);
     b = __ldg(reinterpret_cast<const float4*>(fin + C) + cq);
+    m4[0] = m.x; m4[1] = m.y; m4[2] = m.z; m4[3] = m.w;
+    r4[0] = r.x; r4[1] = r.y; r4[2] = r.z; r4[3] = r.w;
+    g4[0] = g.x; g4[1] = g.y; g4[2] = g.z; g4[3] = g.w;
+    if (mask_mode == BN_MASK_Z) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(beta) + cq);
+      b4[0] = bb.x; b4[1] = bb.y; b4[2] = bb.z; b4[3] = bb.w;
+    } else {
+      b4[0] = b4[1] = b4[2] = b4[3] = 0.f;
+    }
   };
   coef(c);
 #pragma unroll 4
   for (int64_t i = i0; i < n4; i += stride) {
     if (!fixed) { c = (int)(i % C4); coef(c); }
-    float4 g = __ldg(dy + i);
-    if (yout) {
-      const float4 yv = __ldg(yout + i);
-      if (!(yv.x > 0.f)) g.x = 0.f;
-      if (!(yv.y > 0.f)) g.y = 0.f;
-      if (!(yv.z > 0.f)) g.z = 0.f;
-      if (!(yv.w > 0.f)) g.w = 0.f;
-    }
+    const float4 gv = __ldg(dy + i);
     const float4 xv = __ldg(x + i);
+    float4 g;
+    {
+      float ga[4] = {gv.x, gv.y, gv.z, gv.w};
+      const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+      bn_relu_mask4(ga, mask_mode, yout, i, xa, m4, r4, g4, b4);
+      g = make_float4(ga[0], ga[1], ga[2], ga[3]);
+    }
     float4 o;
     o.x = k.x * (g.x - a.x - (xv.x - m.x) * r.x * b.x);
     o.y = k.y * (g.y - a.y - (xv.y - m.y) * r.y * b.y);
@@ -234,7 +270,7 @@ bn_bwd_dx_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
 // all rows, the CTA publishes the statistics, pass 2 re-reads the column (L2/L1 hits) and writes the result.
 template <bool BWD>
 __global__ void __launch_bounds__(256)
-bn_small_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float4* __restrict__ yout,
+bn_small_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const void* __restrict__ yout, int mask_mode,
                 const float4* __restrict__ res, float4* __restrict__ out, float4* __restrict__ dres,
                 float* __restrict__ mean, float* __restrict__ rstd, const float4* __restrict__ gamma,
                 const float4* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
@@ -243,11 +279,16 @@ bn_small_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, con
   __shared__ double red[8][8];
   __shared__ float fin[8];
   const int cq = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float m4[4] = {0.f, 0.f, 0.f, 0.f}, r4[4] = {1.f, 1.f, 1.f, 1.f};
+  float m4[4] = {0.f, 0.f, 0.f, 0.f}, r4[4] = {1.f, 1.f, 1.f, 1.f}, gz4[4] = {0.f, 0.f, 0.f, 0.f}, bz4[4] = {0.f, 0.f, 0.f, 0.f};
   if (BWD) {
     const float4 mm = __ldg(reinterpret_cast<const float4*>(mean) + cq), rr = __ldg(reinterpret_cast<const float4*>(rstd) + cq);
     m4[0] = mm.x; m4[1] = mm.y; m4[2] = mm.z; m4[3] = mm.w;
     r4[0] = rr.x; r4[1] = rr.y; r4[2] = rr.z; r4[3] = rr.w;
+    if (mask_mode == BN_MASK_Z) {
+      const float4 gg = __ldg(gamma + cq), bb = __ldg(beta + cq);
+      gz4[0] = gg.x; gz4[1] = gg.y; gz4[2] = gg.z; gz4[3] = gg.w;
+      bz4[0] = bb.x; bz4[1] = bb.y; bz4[2] = bb.z; bz4[3] = bb.w;
+    }
   }
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll 8
@@ -260,13 +301,7 @@ bn_small_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, con
     } else {
       const float4 gv = __ldg(dy + (int64_t)r * C4 + cq);
       float ga[4] = {gv.x, gv.y, gv.z, gv.w};
-      if (yout) {
-        const float4 yv = __ldg(yout + (int64_t)r * C4 + cq);
-        if (!(yv.x > 0.f)) ga[0] = 0.f;
-        if (!(yv.y > 0.f)) ga[1] = 0.f;
-        if (!(yv.z > 0.f)) ga[2] = 0.f;
-        if (!(yv.w > 0.f)) ga[3] = 0.f;
-      }
+      bn_relu_mask4(ga, mask_mode, yout, (int64_t)r * C4 + cq, xa, m4, r4, gz4, bz4);
 #pragma unroll
       for (int k = 0; k < 4; ++k) { acc[k] += ga[k]; acc[4 + k] += (double)ga[k] * ((xa[k] - m4[k]) * r4[k]); }
     }
@@ -336,15 +371,9 @@ bn_small_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, con
       const int64_t i = (int64_t)r * C4 + cq;
       const float4 gv = __ldg(dy + i);
       float gg[4] = {gv.x, gv.y, gv.z, gv.w};
-      if (yout) {
-        const float4 yv = __ldg(yout + i);
-        if (!(yv.x > 0.f)) gg[0] = 0.f;
-        if (!(yv.y > 0.f)) gg[1] = 0.f;
-        if (!(yv.z > 0.f)) gg[2] = 0.f;
-        if (!(yv.w > 0.f)) gg[3] = 0.f;
-      }
       const float4 xv = __ldg(x + i);
       const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+      bn_relu_mask4(gg, mask_mode, yout, i, xa, m4, r4, gz4, bz4);
       float o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) o[k] = kk[k] * (gg[k] - fin[k] - (xa[k] - m4[k]) * r4[k] * fin[4 + k]);
@@ -680,6 +709,47 @@ __global__ void ln_bwd_param_kernel(const float* __restrict__ dy, const float* _
   }
 }
 
+// C % 128 == 0 (the transformer widths 128 / 256 / 512): 4 columns per thread as 16-byte loads -- a warp reads 512
+// contiguous bytes of a row, 8 loads of 16 bytes in flight per thread (the scalar kernel above measured 19 us for the
+// 8192 x 512 rows of transformer 4: one 128-byte line per warp-load, latency-bound).  grid (C/128, row slabs).
+__global__ void __launch_bounds__(256)
+ln_bwd_param_vec_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
+                        const float4* __restrict__ gamma, const float4* __restrict__ beta,
+                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M, int C4, int act) {
+  __shared__ float4 s1[8][33], s2[8][33];
+  const int cq = blockIdx.x * 32 + threadIdx.x;
+  const int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  const float4 gm4 = __ldg(gamma + cq), bt4 = __ldg(beta + cq);
+  const float gm[4] = {gm4.x, gm4.y, gm4.z, gm4.w}, bt[4] = {bt4.x, bt4.y, bt4.z, bt4.w};
+#pragma unroll 4
+  for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+    const float4 xv = __ldg(x + r * C4 + cq), gv = __ldg(dy + r * C4 + cq);
+    const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+    const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+    float g[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xh = (xa[k] - mu) * rs;
+      if (act) g[k] *= act_grad(xh * gm[k] + bt[k], act);
+      a[k] += g[k] * xh;
+      b[k] += g[k];
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = make_float4(a[0], a[1], a[2], a[3]);
+  s2[threadIdx.y][threadIdx.x] = make_float4(b[0], b[1], b[2], b[3]);
+  __syncthreads();
+  // 256 threads fold the 8 row lanes of the CTA's 128 columns x {dgamma, dbeta}
+  const int t = threadIdx.y * 32 + threadIdx.x, col = t & 127, which = t >> 7;
+  const float4 (*src)[33] = which ? s2 : s1;
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc += reinterpret_cast<const float*>(&src[i][col >> 2])[col & 3];
+  atomicAdd((which ? dbeta : dgamma) + blockIdx.x * 128 + col, acc);
+}
+
 }  // namespace
 
 // y_bf16 (nullable): a bf16 twin of y written in the same pass -- the operand of the next bf16 convolution.
@@ -697,7 +767,7 @@ MMFN_API int mmfn_bn_train_fwd(const float* x, float* y, int64_t M, int C,
   MMFN_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)mean | (uintptr_t)rstd) & 15) == 0,
                  "bn_fwd: 16-byte alignment");
   if (M <= BN_SMALL_ROWS) {
-    bn_small_kernel<false><<<C / 4, 256, 0, stream>>>((const float4*)x, nullptr, nullptr, (const float4*)res, (float4*)y, nullptr,
+    bn_small_kernel<false><<<C / 4, 256, 0, stream>>>((const float4*)x, nullptr, nullptr, BN_MASK_NONE, (const float4*)res, (float4*)y, nullptr,
         mean, rstd, (const float4*)gamma, (const float4*)beta, running_mean, running_var, nullptr, nullptr, (int)M, C / 4, eps, momentum, relu,
         (uint2*)y_bf16);
     return mmfn_launch_status("bn_train_fwd");
@@ -705,7 +775,7 @@ MMFN_API int mmfn_bn_train_fwd(const float* x, float* y, int64_t M, int C,
   int qpr; dim3 grid; int64_t rpb;
   bn_colsum_grid(M, C, qpr, grid, rpb);
   BnFinal fz = {mean, rstd, running_mean, running_var, eps, momentum, nullptr, nullptr, nullptr};
-  bn_colsum_kernel<false><<<grid, BN_THREADS, 0, stream>>>((const float4*)x, nullptr, nullptr, nullptr, nullptr, M, C / 4, qpr, rpb, ws, fz);
+  bn_colsum_kernel<false><<<grid, BN_THREADS, 0, stream>>>((const float4*)x, nullptr, nullptr, BN_MASK_NONE, nullptr, nullptr, nullptr, nullptr, M, C / 4, qpr, rpb, ws, fz);
   int64_t n4 = M * C / 4;
   bn_apply_kernel<<<grid_1d(n4, 256), 256, 0, stream>>>((const float4*)x, (float4*)y, n4, C / 4,
       mean, rstd, (const float4*)gamma, (const float4*)beta, (const float4*)res, relu, (uint2*)y_bf16);
@@ -720,7 +790,7 @@ int mmfn_bn_stats_launch(const float* x, int64_t M, int C, float* mean, float* r
   int qpr; dim3 grid; int64_t rpb;
   bn_colsum_grid(M, C, qpr, grid, rpb);
   BnFinal fz = {mean, rstd, running_mean, running_var, eps, momentum, nullptr, nullptr, nullptr};
-  bn_colsum_kernel<false><<<grid, BN_THREADS, 0, stream>>>((const float4*)x, nullptr, nullptr, nullptr, nullptr, M, C / 4, qpr, rpb, ws, fz);
+  bn_colsum_kernel<false><<<grid, BN_THREADS, 0, stream>>>((const float4*)x, nullptr, nullptr, BN_MASK_NONE, nullptr, nullptr, nullptr, nullptr, M, C / 4, qpr, rpb, ws, fz);
   return mmfn_launch_status("bn_stats");
 }
 
@@ -739,19 +809,23 @@ MMFN_API int mmfn_bn_apply(const float* x, float* y, int64_t M, int C, const flo
   return mmfn_launch_status("bn_apply");
 }
 
-// yout: post-ReLU output of the forward (null when no ReLU followed). dres (nullable)
-// receives the ReLU-masked dy for the residual branch.  dgamma/dbeta are accumulated.  ws: as in mmfn_bn_train_fwd.
-MMFN_API int mmfn_bn_train_bwd(const float* dy, const float* x, const float* yout,
-                               const float* mean, const float* rstd, const float* gamma,
+// yout: post-ReLU output of the forward (null when no ReLU followed), fp32 or -- yout_bf16 -- its bf16 twin (only the
+// sign is used).  relu_from_z != 0 (with yout null and beta given): a ReLU followed the BatchNorm directly (nothing was
+// added in between), so its mask is recomputed from x instead of being read.  dres (nullable) receives the ReLU-masked
+// dy for the residual branch.  dgamma/dbeta are accumulated.  ws: as in mmfn_bn_train_fwd.
+MMFN_API int mmfn_bn_train_bwd(const float* dy, const float* x, const void* yout, int yout_bf16, int relu_from_z,
+                               const float* mean, const float* rstd, const float* gamma, const float* beta,
                                int64_t M, int C, void* dx, int dx_bf16, float* dres, float* dgamma, float* dbeta,
                                double* ws, cudaStream_t stream) {
   MMFN_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && ws, "bn_bwd: null pointer");
   MMFN_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "bn_bwd: C must be a positive multiple of 4");
-  MMFN_CHECK_ARG((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)yout | (uintptr_t)dx | (uintptr_t)dres | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma | (uintptr_t)ws) & 15) == 0,
-                 "bn_bwd: 16-byte alignment");
+  MMFN_CHECK_ARG(!relu_from_z || (beta && !yout), "bn_bwd: relu_from_z needs beta and no yout");
+  MMFN_CHECK_ARG((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)dx | (uintptr_t)dres | (uintptr_t)mean | (uintptr_t)rstd | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)ws) & 15) == 0 &&
+                 ((uintptr_t)yout & (yout_bf16 ? 7 : 15)) == 0, "bn_bwd: 16-byte alignment");
+  const int mode = relu_from_z ? BN_MASK_Z : !yout ? BN_MASK_NONE : yout_bf16 ? BN_MASK_Y16 : BN_MASK_Y32;
   if (M <= BN_SMALL_ROWS) {
-    bn_small_kernel<true><<<C / 4, 256, 0, stream>>>((const float4*)x, (const float4*)dy, (const float4*)yout, nullptr, (float4*)dx, (float4*)dres,
-        const_cast<float*>(mean), const_cast<float*>(rstd), (const float4*)gamma, nullptr, nullptr, nullptr, dgamma, dbeta, (int)M, C / 4, 0.f, 0.f, 0,
+    bn_small_kernel<true><<<C / 4, 256, 0, stream>>>((const float4*)x, (const float4*)dy, yout, mode, nullptr, (float4*)dx, (float4*)dres,
+        const_cast<float*>(mean), const_cast<float*>(rstd), (const float4*)gamma, (const float4*)beta, nullptr, nullptr, dgamma, dbeta, (int)M, C / 4, 0.f, 0.f, 0,
         dx_bf16 ? (uint2*)dx : nullptr);
     return mmfn_launch_status("bn_train_bwd");
   }
@@ -759,9 +833,9 @@ MMFN_API int mmfn_bn_train_bwd(const float* dy, const float* x, const float* you
   bn_colsum_grid(M, C, qpr, grid, rpb);
   float* fin = bn_ws_fin(ws, C);
   BnFinal fz = {nullptr, nullptr, nullptr, nullptr, 0.f, 0.f, fin, dgamma, dbeta};
-  bn_colsum_kernel<true><<<grid, BN_THREADS, 0, stream>>>((const float4*)x, (const float4*)dy, (const float4*)yout, mean, rstd, M, C / 4, qpr, rpb, ws, fz);
+  bn_colsum_kernel<true><<<grid, BN_THREADS, 0, stream>>>((const float4*)x, (const float4*)dy, yout, mode, mean, rstd, gamma, beta, M, C / 4, qpr, rpb, ws, fz);
   bn_bwd_dx_kernel<<<grid_1d(M * C / 4, 256), 256, 0, stream>>>(
-      (const float4*)dy, (const float4*)x, (const float4*)yout, mean, rstd, gamma, fin, M, C / 4, (float4*)dx, (float4*)dres,
+      (const float4*)dy, (const float4*)x, yout, mode, mean, rstd, gamma, beta, fin, M, C / 4, (float4*)dx, (float4*)dres,
       dx_bf16 ? (uint2*)dx : nullptr);
   return mmfn_launch_status("bn_train_bwd");
 }
@@ -878,6 +952,13 @@ MMFN_API int mmfn_layernorm_bwd(const float* dy, const float* x, const float* ga
   if (parts & 2) {
     // 32 rows (4 row iterations per thread, all loads in flight) per CTA unless that exceeds ~8 waves of CTAs
     int64_t slabs = ceil_div64(M, 32);
+    if (C % 128 == 0 && M >= 1024) {
+      const int64_t capv = ceil_div64(148 * 4, C / 128);
+      if (slabs > capv) slabs = capv;
+      ln_bwd_param_vec_kernel<<<dim3(C / 128, (unsigned)slabs), dim3(32, 8), 0, stream>>>(
+          (const float4*)dy, (const float4*)x, (const float4*)gamma, (const float4*)beta, mean, rstd, dgamma, dbeta, M, C / 4, act);
+      return mmfn_launch_status("layernorm_bwd");
+    }
     const int64_t cap = ceil_div64(148 * 8, (C + 31) / 32);
     if (slabs > cap) slabs = cap;
     ln_bwd_param_kernel<<<dim3((C + 31) / 32, (unsigned)slabs), dim3(32, 8), 0, stream>>>(dy, x, gamma, beta, mean, rstd, dgamma, dbeta, M, C, act);

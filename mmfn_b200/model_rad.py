@@ -138,6 +138,7 @@ class ConvBN:
     def fwd(self, x, res=None, relu=True, train=True, no_twin=False):
         self.x, self.relu = x, relu
         self.col, self.direct = None, False
+        self.has_res = res is not None
         # bf16 configuration: the convolution reads the bf16 twin its producer wrote (x.h) and the bf16 filter shadow;
         # its fp32 output z feeds the batch statistics; BatchNorm-apply writes y in fp32 AND its bf16 twin
         Ho, Wo = ops.conv_out_hw(x.shape[1], x.shape[2], self.w.shape[1], self.w.shape[2], self.stride, self.pad)
@@ -166,8 +167,11 @@ class ConvBN:
         return self.y
 
     def bwd(self, dy, need_dx=True, want_dres=False, dx_res=None):
-        dz, dres = ops.bn_train_bwd(dy, self.z, self.y if self.relu else None, self.mean, self.rstd, self.gam,
-                                    self.dgam, self.dbet, want_dres,
+        # ReLU mask: recomputed from z when the ReLU followed the BatchNorm directly, else read from y (bf16 twin if any)
+        from_z = self.relu and not self.has_res and ops.BN_MASK_FROM_Z
+        ymask = None if (from_z or not self.relu) else (ops.twin(self.y) if ops.twin(self.y) is not None and ops.BN_MASK_FROM_Z else self.y)
+        dz, dres = ops.bn_train_bwd(dy, self.z, ymask, self.mean, self.rstd, self.gam,
+                                    self.dgam, self.dbet, want_dres, relu_beta=self.bet if from_z else None,
                                     out_bf16=self.bf or (self.col is not None and self.col.dtype == torch.bfloat16)
                                     or (self.direct and ops.BF16))
         x, col = self.x, self.col

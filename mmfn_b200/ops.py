@@ -240,6 +240,8 @@ def conv2d_fwd(x, w_krsc, stride, pad, res=None):
     return y
 
 
+# BatchNorm backward: ReLU mask recomputed from z (conv -> BN -> ReLU without a residual) / read from the bf16 twin of y
+BN_MASK_FROM_Z = _os.environ.get("MMFN_BN_MASK_Z", "1") != "0"
 FUSE_BN_STATS = _os.environ.get("MMFN_FUSE_BN", "1") != "0"   # train-mode BatchNorm statistics from the convolution epilogue
 BN_FUSE_MAX_CTAS = int(_os.environ.get("MMFN_FUSE_BN_MAX_CTAS", "512"))
 
@@ -462,14 +464,18 @@ def bn_eval_fwd(x, gamma, beta, running_mean, running_var, eps=1e-5, res=None, r
     return _with_twin(y, y16), mean, rstd
 
 
-def bn_train_bwd(dy, x, yout, mean, rstd, gamma, dgamma, dbeta, want_dres=False, out_bf16=False):
-    """out_bf16: dx (the gradient of the convolution output) is written as bf16 -- it only feeds wgrad / dgrad MMAs."""
+def bn_train_bwd(dy, x, yout, mean, rstd, gamma, dgamma, dbeta, want_dres=False, out_bf16=False, relu_beta=None):
+    """out_bf16: dx (the gradient of the convolution output) is written as bf16 -- it only feeds wgrad / dgrad MMAs.
+    ReLU mask: from yout (the forward output, fp32 or its bf16 twin), or -- relu_beta given, yout None: the ReLU followed
+    the BatchNorm directly -- recomputed from x with the BatchNorm bias (no third tensor is read)."""
     C = x.shape[-1]
     assert C <= BN_WS_MAX_C
+    assert yout is None or relu_beta is None
     M = x.numel() // C
     dx = torch.empty(x.shape, device=x.device, dtype=BF if out_bf16 else torch.float32)
     dres = torch.empty_like(x) if want_dres else None
-    lib().bn_train_bwd(_p(dy), _p(x), _p(yout), _p(mean), _p(rstd), _p(gamma), M, C, _p(dx), int(out_bf16), _p(dres),
+    lib().bn_train_bwd(_p(dy), _p(x), _p(yout), int(yout is not None and yout.dtype == BF), int(relu_beta is not None),
+                       _p(mean), _p(rstd), _p(gamma), _p(relu_beta), M, C, _p(dx), int(out_bf16), _p(dres),
                        _p(dgamma), _p(dbeta), _p(_bn_ws(x.device)), _st())
     if M <= BN_SMALL_ROWS:
         lib().launches -= 1

@@ -296,6 +296,18 @@ def test_batchnorm_train_forward_backward():
         close(dx.permute(0, 3, 1, 2), xr.grad, 1e-4)
         close(dres.permute(0, 3, 1, 2), rr.grad, 1e-5)
         close(dg, bn.weight.grad, 1e-4); close(db, bn.bias.grad, 1e-4)
+        # the ReLU mask read from the bf16 twin of y instead of y: same signs, same result
+        dyn = dy.permute(0, 2, 3, 1).contiguous().to(DEV)
+        dg2, db2 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        dx2, dres2 = ops.bn_train_bwd(dyn, xn, y.to(torch.bfloat16), mean, rstd, g, dg2, db2, want_dres=True)
+        assert torch.equal(dres2, dres)
+        close(dx2, dx, 1e-6); close(dg2, dg, 1e-6); close(db2, db, 1e-6)
+        # conv -> BN -> ReLU without a residual: the mask recomputed from x (relu_beta) equals the mask read from y
+        y0, mean0, rstd0 = ops.bn_train_fwd(xn, g, b, rm.clone(), rv.clone(), relu=True)
+        dga, dba, dgb, dbb = (torch.zeros(C, device=DEV) for _ in range(4))
+        dxa, _ = ops.bn_train_bwd(dyn, xn, y0, mean0, rstd0, g, dga, dba)
+        dxb, _ = ops.bn_train_bwd(dyn, xn, None, mean0, rstd0, g, dgb, dbb, relu_beta=b)
+        close(dxa, dxb, 1e-6); close(dga, dgb, 1e-6); close(dba, dbb, 1e-6)
 
 
 @pytest.mark.parametrize("geom", [(2, 64, 64, 64), (3, 31, 29, 8), (1, 8, 10, 128), (2, 33, 64, 96)], ids=lambda g: "N%dH%dW%dC%d" % g)
@@ -343,8 +355,9 @@ def test_stem_tail_bn_relu_maxpool_fused(geom):
 
 def test_layernorm_variants():
     from mmfn_b200 import ops
-    for C, act in [(64, 0), (64, 1), (128, 2), (512, 0)]:
-        x = torch.randn(300, C) * 1.5 + 0.3
+    # rows >= 1024 with C % 128 == 0 take the 16-byte-load parameter-gradient kernel
+    for C, act, M in [(64, 0, 300), (64, 1, 300), (128, 2, 300), (512, 0, 300), (256, 1, 2050), (512, 0, 4100), (128, 2, 1030)]:
+        x = torch.randn(M, C) * 1.5 + 0.3
         ln = torch.nn.LayerNorm(C)
         with torch.no_grad():
             ln.weight.uniform_(0.5, 1.5); ln.bias.normal_()
