@@ -10,6 +10,11 @@
                          (run_steps/phase2_train_net.py:66-103), producing the packed-batch dict the
                          TrainEngine / BatchStager consume
 
+  PackedShard / PackedLoader   the packed alternative to the pickles (written by
+                         preprocess.write_packed): memory-mapped arrays -> engine batch with no unpickling, no collate and
+                         no per-sample Python; the histogram travels as uint8 counts and the radar adjacency is built on
+                         the GPU from the float64 azimuths (TrainEngine expands both)
+
 Samples are the dicts CARLA_Data.__getitem__ builds (dataloader.py:183-268): lists of per-timestep
 tensors for fronts / lidars / maps / vectormaps / radar, tuples for waypoints / target_point, floats.
 """
@@ -100,3 +105,121 @@ def to_engine_batch(data, seq_len=1, pad_lanes_to=None):
     else:
         out["lidar"] = data["lidars"][0].to(torch.float32)
     return out
+
+
+class PackedShard:
+    """Reader of one shard written by preprocess.write_packed.  engine_batch(indices) returns the dict to_engine_batch
+    builds from the same samples -- bit for bit -- except that `lidar` (float32 histogram) is `lidar_u8` (counts; the
+    engine multiplies by 0.2f on the GPU) and `radar_adj` is `radar_az64` (the engine forms az[j] - az[i] in float64)."""
+
+    def __init__(self, path):
+        import json
+        from .preprocess import PACK_ALIGN, PACK_MAGIC
+        with open(path, "rb") as fd:
+            if fd.read(len(PACK_MAGIC)) != PACK_MAGIC:
+                raise ValueError(f"{path}: not an MMFN packed shard")
+            hlen = int(np.frombuffer(fd.read(8), dtype=np.uint64)[0])
+            head = json.loads(fd.read(hlen).decode())
+        data0 = (len(PACK_MAGIC) + 8 + hlen + PACK_ALIGN - 1) // PACK_ALIGN * PACK_ALIGN
+        self.n = int(head["n"])
+        self.arrays = {name: np.memmap(path, mode="r", dtype=np.dtype(m["dtype"]), shape=tuple(m["shape"]), offset=data0 + m["offset"])
+                       for name, m in head["arrays"].items()}
+
+    def __len__(self):
+        return self.n
+
+    def engine_batch(self, indices, seq_len=1, pad_lanes_to=None):
+        a = self.arrays
+        idx = np.asarray(indices, dtype=np.int64)
+        order = np.argsort(idx, kind="stable")                     # memmap gathers in file order, then restored
+        inv = np.empty_like(order)
+        inv[order] = np.arange(len(order))
+
+        def take(name):
+            return torch.from_numpy(np.ascontiguousarray(a[name][idx[order]][inv]))
+        lane_num = take("lane_num")
+        lmax = int(lane_num.max())
+        L = lmax if pad_lanes_to is None else pad_lanes_to
+        if lmax > L:
+            raise ValueError(f"batch has {lmax} lanes, more than pad_lanes_to={pad_lanes_to}")
+        lane_all = take("lane")
+        lane = torch.zeros((len(idx), L) + tuple(lane_all.shape[2:]), dtype=torch.float32)
+        k = min(L, lane_all.shape[1])
+        lane[:, :k] = lane_all[:, :k]
+        wps = take("waypoints")
+        return {
+            "rgb_u8": take("fronts"),
+            "lidar_u8": take("lidar_u8"),
+            "lane": lane,
+            "lane_num": lane_num.to(torch.int32),
+            "radar": take("radar"),
+            "radar_az64": take("radar_az64"),
+            "velocity": take("velocity").to(torch.float32),
+            "target_point": take("target_point").to(torch.float32),
+            "gt_waypoints": wps[:, seq_len:].to(torch.float32).contiguous(),
+        }
+
+    def sample(self, i):
+        """Sample i back in the phase-1 pickle layout (what PRE_Data would unpickle) -- for interchange with the reference."""
+        a = self.arrays
+        n = int(a["lane_num"][i])
+        return {
+            "fronts": [torch.from_numpy(np.array(a["fronts"][i]))],
+            "lidars": [np.array(a["lidar_u8"][i], dtype=np.float32) * np.float32(0.2)],
+            "vectormaps": [torch.from_numpy(np.array(a["lane"][i, :n], dtype=np.float64))],
+            "radar": [np.array(a["radar"][i], dtype=np.float64)],
+            "maps": [torch.from_numpy(np.array(a["maps"][i]))],
+            "waypoints": [tuple(w) for w in np.array(a["waypoints"][i]).tolist()],
+            "target_point": tuple(np.array(a["target_point"][i]).tolist()),
+            "steer": float(a["steer"][i]), "throttle": float(a["throttle"][i]), "brake": bool(a["brake"][i]),
+            "command": int(a["command"][i]), "velocity": float(a["velocity"][i]),
+        }
+
+
+class PackedLoader:
+    """Batches of one or more shards for TrainEngine / BatchStager.  Index order follows torch's DistributedSampler
+    (phase2_train_net.py:265-267): a seeded permutation per epoch, padded to a multiple of the world size, rank r takes
+    every world-th index; incomplete last batches are dropped (fixed shapes keep one CUDA graph valid)."""
+
+    def __init__(self, shards, batch_size, shuffle=True, seed=0, rank=0, world=1, seq_len=1, pad_lanes_to=None):
+        self.shards = [s if isinstance(s, PackedShard) else PackedShard(s) for s in shards]
+        self.starts = np.cumsum([0] + [len(s) for s in self.shards])
+        self.batch_size, self.shuffle, self.seed, self.rank, self.world = batch_size, shuffle, seed, rank, world
+        self.seq_len, self.pad_lanes_to, self.epoch = seq_len, pad_lanes_to, 0
+
+    def set_epoch(self, epoch):
+        self.epoch = epoch
+
+    def indices(self):
+        n = int(self.starts[-1])
+        if self.shuffle:
+            g = torch.Generator()
+            g.manual_seed(self.seed + self.epoch)
+            idx = torch.randperm(n, generator=g).tolist()
+        else:
+            idx = list(range(n))
+        total = (n + self.world - 1) // self.world * self.world
+        idx += idx[: total - n]
+        return idx[self.rank: total: self.world]
+
+    def __len__(self):
+        return len(self.indices()) // self.batch_size
+
+    def __iter__(self):
+        idx = self.indices()
+        for b in range(len(idx) // self.batch_size):
+            chunk = np.asarray(idx[b * self.batch_size: (b + 1) * self.batch_size])
+            shard_of = np.searchsorted(self.starts, chunk, side="right") - 1
+            if len(set(shard_of.tolist())) == 1:
+                s = int(shard_of[0])
+                yield self.shards[s].engine_batch(chunk - self.starts[s], self.seq_len, self.pad_lanes_to)
+            else:                                                  # a batch that straddles shards: per-shard gathers, restored order
+                parts, pos = [], []
+                for s in sorted(set(shard_of.tolist())):
+                    m = np.nonzero(shard_of == s)[0]
+                    parts.append(self.shards[s].engine_batch(chunk[m] - self.starts[s], self.seq_len,
+                                                             self.pad_lanes_to if self.pad_lanes_to is not None else
+                                                             max(int(sh.arrays["lane"].shape[1]) for sh in self.shards)))
+                    pos.append(m)
+                order = np.argsort(np.concatenate(pos))
+                yield {k: torch.cat([p[k] for p in parts])[order] for k in parts[0]}

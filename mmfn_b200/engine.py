@@ -19,6 +19,9 @@ _FIELDS = (
     ("rgb_u8", torch.uint8), ("points", torch.float32), ("lane", torch.float32), ("lane_num", torch.int32),
     ("radar", torch.float32), ("radar_adj", torch.float32), ("velocity", torch.float32),
     ("target_point", torch.float32), ("gt_waypoints", torch.float32), ("lidar", torch.float32), ("map_u8", torch.uint8),
+    # packed loader format (data.PackedShard): histogram as uint8 counts, radar azimuths in float64 instead of the
+    # 81 x 81 adjacency -- both expanded on the GPU (ops.bev_unpack_u8 / ops.radar_adjacency)
+    ("lidar_u8", torch.uint8), ("radar_az64", torch.float64),
 )
 
 
@@ -122,11 +125,15 @@ class TrainEngine:
         self.st.flat_grad.zero_()
         self.rng.add_(1000003)
         self.st.flat_nbt.add_(model._nbt_step())
-        lidar = b["lidar"] if "lidar" in b else ops.bev_scatter(b["points"])
+        lidar = (b["lidar"] if "lidar" in b else ops.bev_unpack_u8(b["lidar_u8"]) if "lidar_u8" in b
+                 else ops.bev_scatter(b["points"]))
+        radar_adj = b.get("radar_adj")
+        if radar_adj is None and "radar_az64" in b:
+            radar_adj = ops.radar_adjacency(b["radar_az64"])
         image = b["rgb_u8"] if "rgb_u8" in b else b["image"]
         # the RGB+LiDAR-only variant (transfuser.TransFuser) has no lane / radar inputs
         lane = b["map_u8"] if model.VARIANT == "img" else b.get("lane")     # model_img: rasterised map image
-        pred = self.net.forward(image, lidar, lane, b.get("lane_num"), b.get("radar"), b.get("radar_adj"),
+        pred = self.net.forward(image, lidar, lane, b.get("lane_num"), b.get("radar"), radar_adj,
                                 b["target_point"], b["velocity"], model.seed, True)
         loss, dpred = ops.l1_loss(pred, b["gt_waypoints"])
         self.net.backward(dpred)

@@ -1030,3 +1030,40 @@ def adamw_apply_(p, g, m, v, state, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight
     """AdamW on one parameter range; the step count in `state` must already be advanced (adamw_advance_)."""
     lib().adamw_apply(_p(p), _p(g), _p(m), _p(v), p.numel(), lr, beta1, beta2, eps, weight_decay,
                       _p(state), grad_scale, _p(p16), _st())
+
+
+# ------------------------------------------------------------------ loader-side kernels (csrc/loader.cu)
+def lidar_ego_transform(points, pose):
+    """points (F, N, >= 3) fp32 raw sweeps, pose (F, 6) float64 [cos r1, sin r1, cos r2, sin r2, t1x - t2x, t1y - t2y]
+    -> (F, N, 3) fp32: y flip + frame change in float64 (dataloader.py:229-239), the input of bev_scatter."""
+    F_, N, S = points.shape
+    assert points.is_contiguous() and points.dtype == torch.float32 and pose.dtype == torch.float64 and tuple(pose.shape) == (F_, 6)
+    out = torch.empty((F_, N, 3), device=points.device, dtype=torch.float32)
+    lib().lidar_ego_transform_f64(_p(points), S, pose.contiguous().data_ptr(), _p(out), F_, N, _st())
+    return out
+
+
+def bev_pack_u8(hist):
+    """float32 histogram (values k / 5) -> uint8 counts k, same shape"""
+    assert hist.is_contiguous() and hist.dtype == torch.float32
+    out = torch.empty(hist.shape, device=hist.device, dtype=torch.uint8)
+    lib().bev_pack_u8(_p(hist), out.data_ptr(), hist.numel(), _st())
+    return out
+
+
+def bev_unpack_u8(counts, out=None):
+    """uint8 counts -> the float32 histogram the model consumes (bit-identical to bev_scatter's output)"""
+    assert counts.is_contiguous() and counts.dtype == torch.uint8
+    if out is None:
+        out = torch.empty(counts.shape, device=counts.device, dtype=torch.float32)
+    lib().bev_unpack_u8(counts.data_ptr(), _p(out), counts.numel(), _st())
+    return out
+
+
+def radar_adjacency(az64):
+    """az64 (B, R) float64 azimuths -> (B, R, R) fp32 with adj[b, i, j] = az[b, j] - az[b, i] (dataloader.py:379-384)"""
+    B, R = az64.shape
+    assert az64.is_contiguous() and az64.dtype == torch.float64
+    adj = torch.empty((B, R, R), device=az64.device, dtype=torch.float32)
+    lib().radar_adjacency_f64(az64.data_ptr(), _p(adj), B, R, _st())
+    return adj

@@ -11,6 +11,10 @@ pickled by phase1_preprocess_data.py and later read back by PRE_Data.
                           builder: `mmfn_b200.ops.bev_scatter` on the GPU (bit-exact with the reference function for
                           identical points) or the CPU oracle in tests
 
+  ego_pose_params / lidar_frames_to_bev_gpu / write_packed -- the same frame preprocessing with the per-point work on the
+                          GPU (csrc/loader.cu: float64 transform; csrc/bev.cu: histogram) and ONE packed shard file
+                          (data.PackedShard reads it back) instead of one pickle per frame
+
 The rigid transform is evaluated in closed form (one rotation by r1 - r2 and one translation) instead of the
 reference's two 3x3 matrix products and a matrix inverse: mathematically identical, numerically equal to ~1e-13
 relative (tests/test_preprocess_cpu.py pins it against outputs of the reference function).  No torch autograd,
@@ -157,3 +161,86 @@ def write_pickles(samples, out_dir):
         with open(os.path.join(out_dir, f"{n - 1}.pkl"), "wb") as fd:
             pickle.dump(s, fd)
     return n
+
+
+# --------------------------------------------------------------------------- GPU phase 1 + packed shard
+def ego_pose_params(r1, t1_x, t1_y, r2, t2_x, t2_y):
+    """The six float64 numbers mmfn_lidar_ego_transform_f64 takes per frame, evaluated with the numpy calls of
+    transform_points_2d so that the device result is bit-identical to it."""
+    return np.array([np.cos(r1), np.sin(r1), np.cos(r2), np.sin(r2), t1_x - t2_x, t1_y - t2_y], dtype=np.float64)
+
+
+def lidar_frames_to_bev_gpu(sweeps, xs, ys, thetas, device="cuda"):
+    """Raw sweeps (list of (N_i, >= 3) float32 arrays) + ego poses -> uint8 histogram counts (F, 2, 256, 256) on the
+    device: y flip and ego transform in float64 (dataloader.py:229-239), histogram (:271-293), all frames in three
+    launches.  Ragged sweeps are padded with points far outside the grid."""
+    from . import ops
+    F_ = len(sweeps)
+    n = max(int(s.shape[0]) for s in sweeps)
+    n = max(4, (n + 3) // 4 * 4)
+    pts = np.full((F_, n, 3), 1.0e6, dtype=np.float32)             # padding: lands outside every bin
+    pose = np.empty((F_, 6), dtype=np.float64)
+    for i, s in enumerate(sweeps):
+        pts[i, : s.shape[0]] = np.asarray(s)[:, :3]
+        th = 0.0 if np.isnan(thetas[i]) else float(thetas[i])
+        pose[i] = ego_pose_params(np.pi / 2 - th, -xs[i], -ys[i], np.pi / 2 - th, -xs[i], -ys[i])
+    ego = ops.lidar_ego_transform(torch.from_numpy(pts).to(device), torch.from_numpy(pose).to(device))
+    return ops.bev_pack_u8(ops.bev_scatter(ego))
+
+
+PACK_MAGIC = b"MMFNPK01"
+PACK_ALIGN = 4096
+
+
+def samples_to_arrays(samples, lidar_counts=None):
+    """Samples in the phase-1 pickle layout (frame_to_sample / synthetic.synth_sample) -> the arrays of a packed shard.
+    lidar_counts (F, 2, 256, 256) uint8: histogram counts from lidar_frames_to_bev_gpu; when None they are recovered from
+    the float32 histograms the samples hold (value * 5 is an integer 0..5)."""
+    F_ = len(samples)
+    lanes = [np.asarray(s["vectormaps"][0]) for s in samples]
+    lmax = max(l.shape[0] for l in lanes)
+    lane = np.zeros((F_, lmax) + lanes[0].shape[1:], dtype=np.float32)
+    for i, l in enumerate(lanes):
+        lane[i, : l.shape[0]] = l                                   # float64 -> float32: Engine.train's cast, done once
+    radar64 = np.stack([np.asarray(s["radar"][0], dtype=np.float64) for s in samples])
+    if lidar_counts is None:
+        lidar_counts = np.stack([np.rint(np.asarray(s["lidars"][0], dtype=np.float32) * 5.0).astype(np.uint8) for s in samples])
+    arrays = {
+        "fronts": np.stack([np.asarray(s["fronts"][0], dtype=np.uint8) for s in samples]),
+        "maps": np.stack([np.asarray(s["maps"][0], dtype=np.uint8) for s in samples]),
+        "lidar_u8": np.ascontiguousarray(np.asarray(lidar_counts, dtype=np.uint8)),
+        "lane": lane,
+        "lane_num": np.array([l.shape[0] for l in lanes], dtype=np.int32),
+        "radar": radar64.astype(np.float32),
+        "radar_az64": np.ascontiguousarray(radar64[:, :, 1]),
+        "waypoints": np.array([s["waypoints"] for s in samples], dtype=np.float64),
+        "target_point": np.array([s["target_point"] for s in samples], dtype=np.float64),
+        "velocity": np.array([s["velocity"] for s in samples], dtype=np.float64),
+        "steer": np.array([s["steer"] for s in samples], dtype=np.float64),
+        "throttle": np.array([s["throttle"] for s in samples], dtype=np.float64),
+        "brake": np.array([bool(s["brake"]) for s in samples], dtype=np.uint8),
+        "command": np.array([s["command"] for s in samples], dtype=np.int64),
+    }
+    return arrays
+
+
+def write_packed(samples, path, lidar_counts=None):
+    """ONE shard file instead of len(samples) pickles: magic, a JSON table {name: dtype, shape, offset}, then the raw
+    arrays at 4096-byte boundaries (memory-mappable, no unpickling on the training side).  Returns the sample count."""
+    import json
+    arrays = samples_to_arrays(samples, lidar_counts)
+    table, off = {}, 0
+    for name, a in arrays.items():
+        table[name] = {"dtype": a.dtype.str, "shape": list(a.shape), "offset": off}
+        off += (a.nbytes + PACK_ALIGN - 1) // PACK_ALIGN * PACK_ALIGN
+    head = json.dumps({"n": len(samples), "arrays": table}).encode()
+    data0 = (len(PACK_MAGIC) + 8 + len(head) + PACK_ALIGN - 1) // PACK_ALIGN * PACK_ALIGN
+    with open(path, "wb") as fd:
+        fd.write(PACK_MAGIC)
+        fd.write(np.uint64(len(head)).tobytes())
+        fd.write(head)
+        for name, a in arrays.items():
+            fd.seek(data0 + table[name]["offset"])
+            fd.write(np.ascontiguousarray(a).tobytes())
+        fd.truncate(data0 + off)
+    return len(samples)

@@ -444,6 +444,87 @@ def test_loader_to_engine_path_matches_oracle(dev, tmp_path):
     assert cosine > 0.9995, cosine
 
 
+def test_gpu_phase1_preprocessing_is_bit_exact(dev, golden_dir):
+    """SURVEY 8(f) rank 2 on the GPU (csrc/loader.cu + csrc/bev.cu): y flip + float64 ego transform of raw sweeps
+    (dataloader.py:229-239, :311-334), histogram (:271-293) and its uint8 packing, radar adjacency (:379-384) -- every
+    output bit-identical to the CPU mirror (mmfn_b200/preprocess.py, itself pinned to the reference by
+    tests/test_preprocess_cpu.py) on the seeded raw frames of tests/preprocess_fixture.py."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import preprocess_fixture as fx
+    from mmfn_b200 import ops, preprocess as pp
+    gold = np.load(os.path.join(golden_dir, "preprocess_golden.npz"))
+    # (1) general two-frame transforms (r1 != r2) from the reference-generated fixture
+    pts, poses = gold["tf_points"].astype(np.float32), gold["tf_poses"]
+    raw = np.concatenate([pts, np.zeros((pts.shape[0], 1), np.float32)], 1)               # x y z intensity
+    for p in poses:
+        flipped = np.array(pts, dtype=np.float64)
+        flipped[:, 1] *= -1
+        want = pp.transform_points_2d(flipped, *p).astype(np.float32)
+        got = ops.lidar_ego_transform(torch.from_numpy(raw[None]).to(dev), torch.from_numpy(pp.ego_pose_params(*p)[None]).to(dev))
+        assert np.array_equal(got[0].cpu().numpy(), want)
+    # (2) whole frames: ragged sweeps in one batch, NaN heading, histogram counts against the CPU mirror + oracle
+    frames = [fx.raw_frame(f) for f in range(1, fx.N_FRAMES + 1)]
+    for f, fr in enumerate(frames):
+        fr["points"] = fr["points"][: 4096 - 301 * f]                                    # different sweep lengths
+    xs, ys, th = ([fr["meas"][k] for fr in frames] for k in ("x", "y", "theta"))
+    counts = pp.lidar_frames_to_bev_gpu([fr["points"] for fr in frames], xs, ys, th, dev)
+    assert counts.dtype == torch.uint8 and tuple(counts.shape) == (len(frames), 2, 256, 256)
+    for f, fr in enumerate(frames):
+        t = 0.0 if np.isnan(th[f]) else th[f]
+        p64 = np.array(fr["points"][:, :3], dtype=np.float64)
+        p64[:, 1] *= -1
+        ego = pp.transform_points_2d(p64, np.pi / 2 - t, -xs[f], -ys[f], np.pi / 2 - t, -xs[f], -ys[f]).astype(np.float32)
+        hist = bev_oracle.lidar_to_histogram_features(ego)
+        assert np.array_equal(counts[f].cpu().numpy(), np.rint(hist * 5).astype(np.uint8)), f
+        assert np.array_equal(ops.bev_unpack_u8(counts[f: f + 1])[0].cpu().numpy(), hist), f
+    h = ops.bev_unpack_u8(counts)
+    assert torch.equal(ops.bev_pack_u8(h), counts)
+    # (3) radar "adjacency" from float64 azimuths
+    radar = np.stack([pp.radar_to_size(fr["radar"], (81, 5)) for fr in frames])
+    adj = ops.radar_adjacency(torch.from_numpy(np.ascontiguousarray(radar[:, :, 1])).to(dev))
+    assert np.array_equal(adj.cpu().numpy(), synthetic.radar_adjacency(radar).astype(np.float32))
+
+
+def test_packed_loader_to_engine_path_matches_pickle_loader(dev, tmp_path):
+    """packed shard -> PackedLoader -> BatchStager (ONE H2D copy of the packed batch: histogram as
+    uint8 counts, no adjacency matrix) -> TrainEngine, against pickles -> PRE_Data -> collate -> to_engine_batch ->
+    BatchStager -> TrainEngine on the same samples: the tensors the network receives are bit-identical, so are the
+    prediction and the loss; the packed batch moves 2.3x fewer bytes."""
+    import pickle
+    from mmfn_b200 import data as mdata, ops, preprocess as pp
+    from mmfn_b200.engine import BatchStager, TrainEngine
+    B = 3
+    cfg, model, sd, _ = _setup(dev, B, tf32=False)
+    lanes = (70, 128, 93)
+    smp = []
+    for i in range(B):
+        s = synthetic.synth_sample(40 + i, bev_oracle.lidar_to_histogram_features, n_lanes=128)
+        s["vectormaps"] = [s["vectormaps"][0][: lanes[i]]]
+        smp.append(s)
+        with open(tmp_path / f"{i}.pkl", "wb") as f:
+            pickle.dump(s, f)
+    ds = mdata.PRE_Data(str(tmp_path), cfg)
+    order = np.argsort([int(os.path.basename(p).split(".")[0]) for p in ds.preload_dict])
+    eb = mdata.to_engine_batch(mdata.collate_single_cpu([ds[int(j)] for j in order]), seq_len=cfg.seq_len, pad_lanes_to=128)
+    pp.write_packed(smp, str(tmp_path / "s.mmfnpack"))
+    loader = mdata.PackedLoader([str(tmp_path / "s.mmfnpack")], batch_size=B, shuffle=False, pad_lanes_to=128)
+    pb = next(iter(loader))
+    st_ref, st_pk = BatchStager(eb, dev), BatchStager(pb, dev)
+    assert st_pk.nbytes * 2 < st_ref.nbytes
+    db_ref, db_pk = st_ref.stage(eb), st_pk.stage(pb)
+    assert torch.equal(ops.bev_unpack_u8(db_pk["lidar_u8"]), db_ref["lidar"])
+    assert torch.equal(ops.radar_adjacency(db_pk["radar_az64"]), db_ref["radar_adj"])
+    for k in ("rgb_u8", "lane", "lane_num", "radar", "velocity", "target_point", "gt_waypoints"):
+        assert torch.equal(db_pk[k], db_ref[k]), k
+    eng = TrainEngine(model, lr=1e-4)
+    loss_ref = eng.forward_backward(db_ref).item()
+    pred_ref = eng.last_pred.clone()
+    loss_pk = eng.forward_backward(db_pk).item()
+    # same device tensors in, same kernels: equal up to the order of the fp64 BatchNorm-statistics atomics
+    assert (eng.last_pred - pred_ref).abs().max().item() <= 1e-6 and abs(loss_pk - loss_ref) <= 1e-6
+
+
 def test_torchvision_resnet34_weights_load_into_both_trunks(dev):
     """ImageCNN = models.resnet34(pretrained=True) minus fc (model_rad.py:22-23): a torchvision state_dict must land in
     encoder.image_encoder.features.* and encoder.img_map_encoder.features.* (KRSC storage behind the (K,C,R,S) view)."""
