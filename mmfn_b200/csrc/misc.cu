@@ -45,6 +45,57 @@ __global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t 
   }
 }
 
+// 16-byte loads: EPT = 4 fp32 / 8 bf16 columns per thread, a warp reads 512 contiguous bytes of a row (the scalar kernels
+// fetch 128 / 64 bytes per warp-load: latency-bound on the 8192 x 2048 gradients of transformer 4).  N % EPT == 0,
+// ld % EPT == 0, 16-byte aligned base.  blockDim (32, 8); grid (column groups of 32 EPT, row slabs).
+template <typename T, int EPT>
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const T* __restrict__ x, int64_t ld, int64_t M, int N, float* __restrict__ out) {
+  __shared__ float s[8][32 * EPT + 1];
+  const int n0 = (blockIdx.x * 32 + threadIdx.x) * EPT;
+  const int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float a[EPT];
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) a[k] = 0.f;
+  if (n0 < N) {
+#pragma unroll 4
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      const uint4 w = __ldg(reinterpret_cast<const uint4*>(x + r * ld + n0));
+      if (EPT == 4) {
+        a[0] += __uint_as_float(w.x); a[1] += __uint_as_float(w.y); a[2] += __uint_as_float(w.z); a[3] += __uint_as_float(w.w);
+      } else {
+        const float4 lo = mmfn_unpack_bf16x4(make_uint2(w.x, w.y)), hi = mmfn_unpack_bf16x4(make_uint2(w.z, w.w));
+        a[0] += lo.x; a[1] += lo.y; a[2] += lo.z; a[3] += lo.w;
+        a[4 % EPT] += hi.x; a[5 % EPT] += hi.y; a[6 % EPT] += hi.z; a[7 % EPT] += hi.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) s[threadIdx.y][threadIdx.x * EPT + k] = a[k];
+  __syncthreads();
+  for (int c = threadIdx.y * 32 + threadIdx.x; c < 32 * EPT; c += 256) {
+    const int n = blockIdx.x * 32 * EPT + c;
+    if (n < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += s[i][c];
+      atomicAdd(out + n, t);
+    }
+  }
+}
+
+template <typename T, int EPT>
+static bool colsum_vec_launch(const T* x, int64_t ld, int64_t M, int N, float* out, cudaStream_t stream) {
+  if (N % EPT != 0 || ld % EPT != 0 || ((uintptr_t)x & 15) != 0 || M < 512) return false;
+  const int64_t colgroups = (N + 32 * EPT - 1) / (32 * EPT);
+  int64_t slabs = ceil_div64(M, 32);
+  const int64_t cap = ceil_div64(148 * 4, colgroups);
+  if (slabs > cap) slabs = cap;
+  colsum_vec_kernel<T, EPT><<<dim3((unsigned)colgroups, (unsigned)slabs), dim3(32, 8), 0, stream>>>(x, ld, M, N, out);
+  return true;
+}
+
 // y = bf16(x), 4 elements per thread
 __global__ void f32_to_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ y, int64_t n4) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -280,6 +331,7 @@ __global__ void radar_logsoftmax_bwd_kernel(const float* __restrict__ dy, const 
 MMFN_API int mmfn_colsum_f32(const float* x, int64_t ld, int64_t M, int N, float* out, cudaStream_t stream) {
   MMFN_CHECK_ARG(x && out && M >= 0 && N > 0 && ld >= N, "colsum: bad args");
   if (M == 0) return 0;
+  if (colsum_vec_launch<float, 4>(x, ld, M, N, out, stream)) return mmfn_launch_status("colsum");
   // 64 rows (8 loads in flight per thread) per CTA unless that exceeds ~8 waves of CTAs
   const int64_t colgroups = (N + 31) / 32;
   int64_t slabs = ceil_div64(M, 64);
@@ -295,6 +347,7 @@ MMFN_API int mmfn_colsum_f32(const float* x, int64_t ld, int64_t M, int N, float
 MMFN_API int mmfn_colsum_bf16(const void* x, int64_t ld, int64_t M, int N, float* out, cudaStream_t stream) {
   MMFN_CHECK_ARG(x && out && M >= 0 && N > 0 && ld >= N, "colsum_bf16: bad args");
   if (M == 0) return 0;
+  if (colsum_vec_launch<__nv_bfloat16, 8>((const __nv_bfloat16*)x, ld, M, N, out, stream)) return mmfn_launch_status("colsum_bf16");
   const int64_t colgroups = (N + 31) / 32;
   int64_t slabs = ceil_div64(M, 64);
   const int64_t cap = ceil_div64(148 * 8, colgroups);

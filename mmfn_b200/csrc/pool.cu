@@ -270,17 +270,31 @@ upsample_add_bwd_kernel(const float* __restrict__ dA, float* __restrict__ dtok,
   const int nw = whi - wlo + 1, npx = (hhi - hlo + 1) * nw;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (lane < lanes) {
-    for (int i = lane; i < npx; i += lanes) {
-      const int h = hlo + i / nw, w = wlo + i % nw;
-      int h0, h1, w0, w1; float a0, a1, b0, b1;
-      bilinear_src(h, sh, 8, h0, h1, a0, a1, align);
-      bilinear_src(w, sw, 8, w0, w1, b0, b1, align);
-      const float wy = (h0 == py ? a0 : 0.f) + (h1 == py ? a1 : 0.f);
-      const float wx = (w0 == px ? b0 : 0.f) + (w1 == px ? b1 : 0.f);
-      const float wt = wy * wx;
-      if (wt == 0.f) continue;
-      const float4 g = __ldg(reinterpret_cast<const float4*>(dA + (((int64_t)b * H + h) * W + w) * C) + cq);
-      acc.x += wt * g.x; acc.y += wt * g.y; acc.z += wt * g.z; acc.w += wt * g.w;
+    // four pixels per trip: weights first, then the (predicated) loads of all four in flight together
+    for (int i0 = lane; i0 < npx; i0 += 4 * lanes) {
+      float wt[4];
+      const float4* src[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * lanes;
+        wt[u] = 0.f;
+        src[u] = nullptr;
+        if (i < npx) {
+          const int h = hlo + i / nw, w = wlo + i % nw;
+          int h0, h1, w0, w1; float a0, a1, b0, b1;
+          bilinear_src(h, sh, 8, h0, h1, a0, a1, align);
+          bilinear_src(w, sw, 8, w0, w1, b0, b1, align);
+          const float wy = (h0 == py ? a0 : 0.f) + (h1 == py ? a1 : 0.f);
+          const float wx = (w0 == px ? b0 : 0.f) + (w1 == px ? b1 : 0.f);
+          wt[u] = wy * wx;
+          src[u] = reinterpret_cast<const float4*>(dA + (((int64_t)b * H + h) * W + w) * C) + cq;
+        }
+      }
+      float4 g[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) g[u] = wt[u] != 0.f ? __ldg(src[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { acc.x += wt[u] * g[u].x; acc.y += wt[u] * g[u].y; acc.z += wt[u] * g[u].z; acc.w += wt[u] * g[u].w; }
     }
     red4[lane * C4 + cq] = acc;
   }

@@ -353,6 +353,26 @@ def test_stem_tail_bn_relu_maxpool_fused(geom):
             close(dz, dz2, 1e-2 if bf else 1e-5); close(dg, dg2, 1e-5); close(db, db2, 1e-5)
 
 
+
+def test_column_sums_scalar_and_16_byte_load_kernels():
+    """ops.colsum_ (bias gradients): fp32 / bf16, the 16-byte-load kernel (rows >= 512, widths and pitches that are
+    multiples of 4 / 8 elements) and the scalar kernel (everything else, e.g. an odd width or a column slice that starts at
+    an unaligned element), accumulation on top of `out`."""
+    from mmfn_b200 import ops
+    for M, N, dt in [(4100, 512, torch.float32), (8192, 2048, torch.bfloat16), (3072, 192, torch.bfloat16), (600, 68, torch.float32),
+                     (300, 512, torch.float32), (2000, 50, torch.bfloat16), (1024, 1536, torch.bfloat16)]:
+        x = torch.randn(M, N, device=DEV).to(dt)
+        out = torch.ones(N, device=DEV)
+        ops.colsum_(x, out)
+        close(out - 1.0, x.double().sum(0), 2e-5)
+    # strided views: a column slice of a wider matrix (aligned start -> vector kernel, unaligned start -> scalar kernel)
+    wide = torch.randn(2048, 3 * 256, device=DEV)
+    for c0 in (256, 258):
+        v = wide[:, c0: c0 + 256]
+        out = torch.zeros(256, device=DEV)
+        ops.colsum_(v, out)
+        close(out, v.double().sum(0), 2e-5)
+
 def test_layernorm_variants():
     from mmfn_b200 import ops
     # rows >= 1024 with C % 128 == 0 take the 16-byte-load parameter-gradient kernel

@@ -53,6 +53,15 @@ ys, col, wpad = ops.conv2d_fwd_im2col(xs, ws, 2, 3)
 dws = torch.zeros_like(ws)
 run(lambda: ops.conv2d_fwd_im2col(xs, ws, 2, 3, wpad))
 run(lambda: ops.conv2d_wgrad_im2col_(ys, col, dws))
+# 4c'. the production stem path: direct convolution (no column matrix), fused BatchNorm -> ReLU -> MaxPool tail, their backward
+zs = ops.conv2d_stem7_fwd(xs, ws)
+gs, bs_ = torch.rand(64, device=dev) + 0.5, torch.randn(64, device=dev)
+outs, saved_s, mean_s, rstd_s = ops.stem_bn_relu_maxpool_fwd(zs, gs, bs_, rm, rv)
+douts = torch.randn_like(outs)
+run(lambda: ops.conv2d_stem7_fwd(xs, ws))
+run(lambda: ops.stem_bn_relu_maxpool_fwd(zs, gs, bs_, rm, rv))
+run(lambda: ops.stem_bn_relu_maxpool_bwd(douts, saved_s, zs, mean_s, rstd_s, gs, dgm, dbt))
+run(lambda: ops.conv2d_stem7_wgrad_(ys, xs, dws))
 # 4d. attention backward pieces at transformer4 geometry: softmax backward (float4)
 P = torch.softmax(torch.randn(B, 4, 256, 256, device=dev), -1); dP = torch.randn_like(P)
 run(lambda: ops.softmax_bwd(P, dP, 0.088, 0.1, 5))
