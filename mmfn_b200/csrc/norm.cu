@@ -735,6 +735,111 @@ __global__ void ln_bwd_param_kernel(const float* __restrict__ dy, const float* _
   }
 }
 
+// ---- C == 64 (VectorNet sub-graph rows: 622 592 of them in BASELINE configs[4]).  The warp-per-row kernels above leave
+// half their lanes idle at 64 channels and keep two 256-byte loads in flight per warp; here a HALF-warp owns a row
+// (16 lanes x float4) and every thread works on RPT rows at once, so 2 RPT 16-byte loads are in flight per thread.
+// The half-warp butterfly (offsets 8, 4, 2, 1) adds in the order warp_sum does when lanes 16..31 hold zeros: results
+// are bit-identical to ln_bwd_dx_kernel<1>.
+template <int RPT>
+__global__ void __launch_bounds__(256)
+ln_bwd_dx_c64_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ dres, float* __restrict__ dx, int64_t M, int act) {
+  constexpr int C = 64;
+  const int q = threadIdx.x & 15;                            // channel quad
+  // the loop bound is WARP-uniform (both half-warps take every trip; rows past the end are clamped on load and not
+  // stored): the full-mask shuffles below need all 32 lanes
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int hsel = (threadIdx.x >> 4) & 1;
+  const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+  const float gma[4] = {gm.x, gm.y, gm.z, gm.w};
+  float ba[4] = {0.f, 0.f, 0.f, 0.f};
+  if (act) { const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + q); ba[0] = bt.x; ba[1] = bt.y; ba[2] = bt.z; ba[3] = bt.w; }
+  for (int64_t base = warp * 2 * RPT; base < M; base += nwarp * 2 * RPT) {
+    const int64_t r0 = base + hsel * RPT;
+    float4 xv[RPT], gy[RPT];
+    float mu[RPT], rs[RPT];
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const int64_t row = min(r0 + j, M - 1);
+      xv[j] = __ldg(reinterpret_cast<const float4*>(x + row * C) + q);
+      gy[j] = __ldg(reinterpret_cast<const float4*>(dy + row * C) + q);
+      mu[j] = __ldg(mean + row);
+      rs[j] = __ldg(rstd + row);
+    }
+#pragma unroll
+    for (int j = 0; j < RPT; ++j) {
+      const float xa[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w}, ga[4] = {gy[j].x, gy[j].y, gy[j].z, gy[j].w};
+      float gv[4], xh[4], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        xh[k] = (xa[k] - mu[j]) * rs[j];
+        float g = ga[k];
+        if (act) g *= act_grad(xh[k] * gma[k] + ba[k], act);
+        gv[k] = g * gma[k];
+        s1 += gv[k];
+        s2 += gv[k] * xh[k];
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+      s1 /= (float)C;
+      s2 /= (float)C;
+      if (r0 + j < M) {
+        float4 o4;
+        o4.x = rs[j] * (gv[0] - s1 - xh[0] * s2);
+        o4.y = rs[j] * (gv[1] - s1 - xh[1] * s2);
+        o4.z = rs[j] * (gv[2] - s1 - xh[2] * s2);
+        o4.w = rs[j] * (gv[3] - s1 - xh[3] * s2);
+        if (dres) {
+          const float4 r = __ldg(reinterpret_cast<const float4*>(dres + (r0 + j) * C) + q);
+          o4.x += r.x; o4.y += r.y; o4.z += r.z; o4.w += r.w;
+        }
+        reinterpret_cast<float4*>(dx + (r0 + j) * C)[q] = o4;
+      }
+    }
+  }
+}
+
+// dgamma / dbeta for C == 64: thread = (channel quad, one of 16 row lanes), 16-byte loads, four rows in flight.
+__global__ void __launch_bounds__(256)
+ln_bwd_param_c64_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const float4* __restrict__ gamma,
+                        const float4* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M, int act) {
+  __shared__ float s1[16][65], s2[16][65];
+  const int q = threadIdx.x & 15, rsub = threadIdx.x >> 4;
+  const int64_t rows_per = (M + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = blockIdx.x * rows_per, r1 = min(M, r0 + rows_per);
+  const float4 gm4 = __ldg(gamma + q), bt4 = __ldg(beta + q);
+  const float gm[4] = {gm4.x, gm4.y, gm4.z, gm4.w}, bt[4] = {bt4.x, bt4.y, bt4.z, bt4.w};
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int64_t r = r0 + rsub; r < r1; r += 16) {
+    const float4 xv = __ldg(x + r * 16 + q), gv = __ldg(dy + r * 16 + q);
+    const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+    const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+    float g[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xh = (xa[k] - mu) * rs;
+      if (act) g[k] *= act_grad(xh * gm[k] + bt[k], act);
+      a[k] += g[k] * xh;
+      b[k] += g[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { s1[rsub][q * 4 + k] = a[k]; s2[rsub][q * 4 + k] = b[k]; }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int c = threadIdx.x & 63;
+    const float (*src)[65] = threadIdx.x < 64 ? s1 : s2;
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += src[i][c];
+    atomicAdd((threadIdx.x < 64 ? dgamma : dbeta) + c, t);
+  }
+}
+
 // C % 128 == 0 (the transformer widths 128 / 256 / 512): 4 columns per thread as 16-byte loads -- a warp reads 512
 // contiguous bytes of a row, 8 loads of 16 bytes in flight per thread (the scalar kernel above measured 19 us for the
 // 8192 x 512 rows of transformer 4: one 128-byte line per warp-load, latency-bound).  grid (C/128, row slabs).
@@ -980,13 +1085,23 @@ MMFN_API int mmfn_layernorm_bwd(const float* dy, const float* x, const float* ga
     // fp32 copy: only needed when a mask applies (the caller reuses dx otherwise); bf16 copy: always (it is a conversion too)
     float* dd = (!drop_bf16 && drop_p > 0.f) ? (float*)dx_drop : nullptr;
     __nv_bfloat16* dd16 = drop_bf16 ? (__nv_bfloat16*)dx_drop : nullptr;
-    if (C <= 128) ln_bwd_dx_kernel<1><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act, dd, drop_p, drop_seed, dd16);
+    if (C == 64 && !dd && !dd16 && M >= 4096) {
+      constexpr int RPT = 4;
+      ln_bwd_dx_c64_kernel<RPT><<<grid_1d(ceil_div64(M, RPT) * 16, 256), 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, act);
+    } else if (C <= 128) ln_bwd_dx_kernel<1><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act, dd, drop_p, drop_seed, dd16);
     else if (C <= 256) ln_bwd_dx_kernel<2><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act, dd, drop_p, drop_seed, dd16);
     else ln_bwd_dx_kernel<4><<<blocks, 256, 0, stream>>>(dy, x, gamma, beta, mean, rstd, dres, dx, M, C, act, dd, drop_p, drop_seed, dd16);
   }
   if (parts & 2) {
     // 32 rows (4 row iterations per thread, all loads in flight) per CTA unless that exceeds ~8 waves of CTAs
     int64_t slabs = ceil_div64(M, 32);
+    if (C == 64 && M >= 4096) {
+      int64_t ctas = ceil_div64(M, 64);
+      if (ctas > 148 * 4) ctas = 148 * 4;
+      ln_bwd_param_c64_kernel<<<(unsigned)ctas, 256, 0, stream>>>((const float4*)dy, (const float4*)x, (const float4*)gamma, (const float4*)beta,
+                                                                  mean, rstd, dgamma, dbeta, M, act);
+      return mmfn_launch_status("layernorm_bwd");
+    }
     if (C % 128 == 0 && M >= 1024) {
       const int64_t capv = ceil_div64(148 * 4, C / 128);
       if (slabs > capv) slabs = capv;

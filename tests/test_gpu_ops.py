@@ -373,10 +373,27 @@ def test_column_sums_scalar_and_16_byte_load_kernels():
         ops.colsum_(v, out)
         close(out, v.double().sum(0), 2e-5)
 
+
+def test_segment_max_forward_backward_scalar_and_vector_kernels():
+    """ops.segmax_fwd / segmax_bwd (polyline max-pool of VectorNet, model_rad.py:281-283) against torch: C % 4 == 0 takes
+    the 16-byte-store backward, an odd width the scalar one."""
+    from mmfn_b200 import ops
+    for G, V, C in [(37, 9, 128), (6, 19, 128), (5, 19, 6), (300, 9, 64), (3, 7, 5)]:
+        x = torch.randn(G, V, C)
+        xr = x.clone().requires_grad_(True)
+        out_r = xr.max(dim=1).values
+        dout = torch.randn_like(out_r)
+        out_r.backward(dout)
+        out, arg = ops.segmax_fwd(x.view(G * V, C).to(DEV), G, V)
+        close(out, out_r, 1e-6)
+        dx = ops.segmax_bwd(dout.to(DEV), arg, G, V)
+        assert torch.equal(dx.view(G, V, C).cpu(), xr.grad)
+
 def test_layernorm_variants():
     from mmfn_b200 import ops
     # rows >= 1024 with C % 128 == 0 take the 16-byte-load parameter-gradient kernel
-    for C, act, M in [(64, 0, 300), (64, 1, 300), (128, 2, 300), (512, 0, 300), (256, 1, 2050), (512, 0, 4100), (128, 2, 1030)]:
+    for C, act, M in [(64, 0, 300), (64, 1, 300), (128, 2, 300), (512, 0, 300), (256, 1, 2050), (512, 0, 4100), (128, 2, 1030),
+                      (64, 1, 5003), (64, 0, 4099), (64, 2, 8192)]:       # C = 64, rows >= 4096: the half-warp-per-row kernels
         x = torch.randn(M, C) * 1.5 + 0.3
         ln = torch.nn.LayerNorm(C)
         with torch.no_grad():
