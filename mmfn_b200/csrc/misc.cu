@@ -268,6 +268,71 @@ __global__ void subgraph_pool_bwd_kernel(const float* __restrict__ dy, const int
     for (int v = 0; v < V; ++v) dr[(int64_t)v * C] = gr[(int64_t)v * 2 * C] + (v == a ? s : 0.f);
   }
 }
+// C % 4 == 0: four channels per thread, 16-byte loads / stores, 32-bit index arithmetic (G * C / 4 < 2^31)
+__global__ void __launch_bounds__(256)
+subgraph_pool_bwd_vec_kernel(const float4* __restrict__ dy, const int4* __restrict__ arg, int n4, int V, int C4,
+                             float4* __restrict__ dx) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const int g = i / C4, cq = i - g * C4;
+    const float4* gr = dy + (int64_t)g * V * 2 * C4 + cq;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int v = 0; v < V; ++v) { const float4 t = __ldg(gr + (int64_t)v * 2 * C4 + C4); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+    const int4 a = __ldg(arg + i);
+    float4* dr = dx + (int64_t)g * V * C4 + cq;
+#pragma unroll 4
+    for (int v = 0; v < V; ++v) {
+      float4 t = __ldg(gr + (int64_t)v * 2 * C4);
+      if (v == a.x) t.x += s.x;
+      if (v == a.y) t.y += s.y;
+      if (v == a.z) t.z += s.z;
+      if (v == a.w) t.w += s.w;
+      dr[(int64_t)v * C4] = t;
+    }
+  }
+}
+
+// dw (64, 7) += dy^T x for the polyline input layer (lane_subgraph.layers.mlp_0.mlp.0, model_rad.py:253: 7 -> 64): dy (M, 64),
+// x (M, 7), M = polylines x vectors (622 592 rows in BASELINE configs[4]).  Thread = (channel quad, one of 16 row lanes): a
+// 16-byte gradient load + the row's 7 inputs (the same address for the 16 quads of a row: one broadcast transaction) feed
+// 28 FMAs; the row lanes are folded through shared memory, one atomic per element and CTA.  Exact fp32.
+__global__ void __launch_bounds__(256)
+wgrad_n64_k7_kernel(const float4* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw, int64_t M) {
+  __shared__ float red[16][449];
+  const int q = threadIdx.x & 15, rsub = threadIdx.x >> 4;
+  const int64_t rows_per = (M + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = blockIdx.x * rows_per, r1 = min(M, r0 + rows_per);
+  float acc[4][7];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) acc[c][k] = 0.f;
+#pragma unroll 4
+  for (int64_t r = r0 + rsub; r < r1; r += 16) {
+    const float4 g = __ldg(dy + r * 16 + q);
+    const float* xr = x + r * 7;
+    float xv[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) xv[k] = __ldg(xr + k);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      acc[0][k] = fmaf(g.x, xv[k], acc[0][k]); acc[1][k] = fmaf(g.y, xv[k], acc[1][k]);
+      acc[2][k] = fmaf(g.z, xv[k], acc[2][k]); acc[3][k] = fmaf(g.w, xv[k], acc[3][k]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) red[rsub][(q * 4 + c) * 7 + k] = acc[c][k];
+  __syncthreads();
+  for (int e = threadIdx.x; e < 448; e += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += red[i][e];
+    atomicAdd(dw + e, t);
+  }
+}
+
 __global__ void segmax_fwd_kernel(const float* __restrict__ x, int64_t G, int V, int C,
                                   float* __restrict__ out, int* __restrict__ arg) {
   int64_t n = G * C;
@@ -425,9 +490,26 @@ MMFN_API int mmfn_subgraph_pool_fwd(const float* x, int64_t G, int V, int C, flo
 MMFN_API int mmfn_subgraph_pool_bwd(const float* dy, const int* arg, int64_t G, int V, int C, float* dx, cudaStream_t stream) {
   MMFN_CHECK_ARG(dy && dx && arg && G >= 0 && V > 0 && C > 0, "subgraph_pool_bwd: bad args");
   if (G == 0) return 0;
+  if (C % 4 == 0 && G * C / 4 < ((int64_t)1 << 31) && (((uintptr_t)dy | (uintptr_t)arg | (uintptr_t)dx) & 15) == 0) {
+    const int n4 = (int)(G * C / 4);
+    subgraph_pool_bwd_vec_kernel<<<grid_1d(n4, 256), 256, 0, stream>>>((const float4*)dy, (const int4*)arg, n4, V, C / 4, (float4*)dx);
+    return mmfn_launch_status("subgraph_pool_bwd");
+  }
   subgraph_pool_bwd_kernel<<<grid_1d(G * C, 256), 256, 0, stream>>>(dy, arg, G, V, C, dx);
   return mmfn_launch_status("subgraph_pool_bwd");
 }
+// dw (64, 7) += dy^T x: weight gradient of the polyline input layer (7 -> 64, model_rad.py:253 via :263) from dy (M, 64)
+// and x (M, 7), both contiguous; exact fp32, atomic accumulation into dw.
+MMFN_API int mmfn_wgrad_n64_k7(const float* dy, const float* x, float* dw, int64_t M, cudaStream_t stream) {
+  MMFN_CHECK_ARG(dy && x && dw && M >= 0, "wgrad_n64_k7: bad args");
+  MMFN_CHECK_ARG(((uintptr_t)dy & 15) == 0, "wgrad_n64_k7: dy must be 16-byte aligned");
+  if (M == 0) return 0;
+  int64_t ctas = ceil_div64(M, 256);
+  if (ctas > 148 * 4) ctas = 148 * 4;
+  wgrad_n64_k7_kernel<<<(unsigned)ctas, 256, 0, stream>>>((const float4*)dy, x, dw, M);
+  return mmfn_launch_status("wgrad_n64_k7");
+}
+
 MMFN_API int mmfn_segmax_fwd(const float* x, int64_t G, int V, int C, float* out, int* arg, cudaStream_t stream) {
   MMFN_CHECK_ARG(x && out && arg && G >= 0 && V > 0 && C > 0, "segmax_fwd: bad args");
   if (G == 0) return 0;

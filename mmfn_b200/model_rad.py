@@ -309,7 +309,11 @@ class Linear:
         def wgrad():
             if self.db is not None:
                 ops.colsum_(dy, self.db)
-            ops.gemm(dy.t(), x.t(), self.dw, accum=1)
+            if (tuple(self.dw.shape) == (64, 7) and dy.dtype == x.dtype == torch.float32 and dy.shape[0] >= 4096
+                    and dy.is_contiguous() and x.is_contiguous()):
+                ops.wgrad_n64_k7_(dy, x, self.dw)          # polyline input layer: K = 7 is no shape for a GEMM tile
+            else:
+                ops.gemm(dy.t(), x.t(), self.dw, accum=1)
         _Aux.run(wgrad, dy, x)
         dx = None
         if need_dx:

@@ -816,6 +816,14 @@ def segmax_bwd(dout, arg, G, V):
     return dx
 
 
+def wgrad_n64_k7_(dy, x, dw):
+    """dw (64, 7) += dy^T x (polyline input layer): one streaming pass instead of a split-K SIMT GEMM."""
+    M = dy.shape[0]
+    assert dy.is_contiguous() and x.is_contiguous() and dw.is_contiguous() and tuple(dw.shape) == (64, 7)
+    assert tuple(dy.shape) == (M, 64) and tuple(x.shape) == (M, 7) and dy.dtype == x.dtype == dw.dtype == torch.float32
+    lib().wgrad_n64_k7(_p(dy), _p(x), _p(dw), M, _st())
+
+
 # whole-GPT kernels (csrc/gpt_small.cu): "1" = where they beat the per-op chain on B200 (n_embd 64: 1225 -> 908 us fwd+bwd
 # at B=32 bf16, 1037 -> 965 us at B=16 TF32), "2" = also n_embd 128 in bf16 (a wash: 1379 -> 1357 us at B=32, slower at
 # B=16; profiles/r02_gpt_bench_final.json), "0" = off

@@ -389,6 +389,27 @@ def test_segment_max_forward_backward_scalar_and_vector_kernels():
         dx = ops.segmax_bwd(dout.to(DEV), arg, G, V)
         assert torch.equal(dx.view(G, V, C).cpu(), xr.grad)
 
+
+def test_polyline_pool_backward_and_input_layer_weight_gradient():
+    """ops.subgraph_pool_fwd / _bwd ([h | max_v h] of model_rad.py:270-283; 16-byte and scalar backward kernels) against torch
+    autograd, and ops.wgrad_n64_k7_ (weight gradient of the 7 -> 64 polyline input layer) against dy^T x in float64."""
+    from mmfn_b200 import ops
+    for G, V, C in [(41, 9, 64), (7, 19, 64), (5, 9, 6)]:
+        x = torch.randn(G, V, C)
+        xr = x.clone().requires_grad_(True)
+        yr = torch.cat([xr, xr.max(dim=1, keepdim=True).values.expand(-1, V, -1)], dim=-1)
+        dy = torch.randn_like(yr)
+        yr.backward(dy)
+        y, arg = ops.subgraph_pool_fwd(x.view(G * V, C).to(DEV), G, V)
+        close(y.view(G, V, 2 * C), yr, 1e-6)
+        dx = ops.subgraph_pool_bwd(dy.view(G * V, 2 * C).to(DEV), arg, G, V)
+        close(dx.view(G, V, C), xr.grad, 1e-6)
+    for M in (4096, 36864, 5001):
+        dy, xin = torch.randn(M, 64, device=DEV), torch.randn(M, 7, device=DEV)
+        dw = torch.ones(64, 7, device=DEV)
+        ops.wgrad_n64_k7_(dy, xin, dw)
+        close(dw - 1.0, dy.double().t() @ xin.double(), 1e-5)
+
 def test_layernorm_variants():
     from mmfn_b200 import ops
     # rows >= 1024 with C % 128 == 0 take the 16-byte-load parameter-gradient kernel
