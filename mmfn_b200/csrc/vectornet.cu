@@ -209,14 +209,223 @@ int launch_subgraph(const SubgraphParams& p, cudaStream_t stream) {
   return mmfn_launch_status("subgraph_fused_fwd");
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Tensor-core formulation (TF32 configuration): the same sub-graph, the 64-wide linears as warp-level mma.sync m16n8k8
+// TF32 tiles.  A persistent CTA of 16 warps walks tiles of floor(256 / V) whole polylines (252 / 247 node rows); warp =
+// one 16-row m-tile x all 64 channels, so a row's LayerNorm is a reduction over the four lanes of a quad; activations
+// stay in shared memory between layers (fp32, rounded to TF32 as the next layer's A fragments are loaded); the
+// segment max-pool scans the tile's rows in shared memory, and the broadcast half of the next layer's input ([h | m]:
+// the same m for every node of a polyline) is multiplied ONCE per polyline as a (polylines x 64) x (64 x 64) product
+// whose result seeds the accumulators.  The lane-per-node SIMT kernel above spends a 16-byte shared-memory broadcast per
+// four FMAs (1.2 ms for the 622 592 rows of BASELINE configs[4]); here the tile's writes of the saved-for-backward
+// tensors (1.8 KB per row) are what remains.  Same outputs, same arg-max rule (first node on ties).
+constexpr int SGM_THREADS = 512, SGM_TILE = 256, SGM_LD = 68, SGM_LD0 = 12;
+
+__device__ __forceinline__ uint32_t sg_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void sg_mma(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int sgm_smem_words() { return 64 * SGM_LD0 + 4 * 64 * SGM_LD + 9 * HID + SGM_TILE * SGM_LD + 2 * 32 * SGM_LD + SGM_TILE * SGM_LD0; }
+
+template <int V>
+__global__ void __launch_bounds__(SGM_THREADS, 1)
+subgraph_mma_fwd_kernel(SubgraphParams p) {
+  constexpr int PP = SGM_TILE / V;              // polylines per tile (28 / 13)
+  constexpr int ROWS = PP * V;                  // node rows per tile (252 / 247)
+  constexpr int PM = (PP + 15) / 16;            // m-tiles of the per-polyline product
+  constexpr int P = V + 1;
+  extern __shared__ __align__(16) float smf[];
+  uint32_t* W0s = reinterpret_cast<uint32_t*>(smf);          // [64][12]  layer 0 weights, k padded to 8
+  uint32_t* Wab = W0s + 64 * SGM_LD0;                        // [4][64][68]: W1[:, :64], W1[:, 64:], W2[:, :64], W2[:, 64:]
+  float* par = reinterpret_cast<float*>(Wab + 4 * 64 * SGM_LD);   // [3][3][64] bias, gamma, beta
+  float* Hs = par + 9 * HID;                                 // [256][68] activations of the tile
+  float* Ms = Hs + SGM_TILE * SGM_LD;                        // [32][68]  pooled maxima per polyline (rows >= PP stay zero)
+  float* MBs = Ms + 32 * SGM_LD;                             // [32][68]  W[:, 64:] m per polyline
+  uint32_t* Vs = reinterpret_cast<uint32_t*>(MBs + 32 * SGM_LD);  // [256][12] polyline vectors (TF32), k padded to 8
+  for (int i = threadIdx.x; i < 64 * 8; i += SGM_THREADS) { const int n = i >> 3, k = i & 7; W0s[n * SGM_LD0 + k] = k < 7 ? sg_tf32(p.w[0][n * 7 + k]) : 0u; }
+  for (int i = threadIdx.x; i < 2 * 64 * 128; i += SGM_THREADS) {
+    const int m = i >> 13, r = i & 8191, n = r >> 7, k = r & 127;
+    Wab[((m * 2 + (k >> 6)) * 64 + n) * SGM_LD + (k & 63)] = sg_tf32(p.w[m + 1][r]);
+  }
+  for (int i = threadIdx.x; i < 3 * HID; i += SGM_THREADS) {
+    const int l = i / HID, c = i - l * HID;
+    par[(l * 3 + 0) * HID + c] = p.b[l][c];
+    par[(l * 3 + 1) * HID + c] = p.gamma[l][c];
+    par[(l * 3 + 2) * HID + c] = p.beta[l][c];
+  }
+  for (int i = threadIdx.x; i < 2 * 32 * SGM_LD; i += SGM_THREADS) Ms[i] = 0.f;        // Ms and MBs
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int row0 = warp * 16 + g, row1 = row0 + 8;
+  const int pl0 = min(row0 / V, PP - 1), pl1 = min(row1 / V, PP - 1);
+  const long long ntiles = (p.G + PP - 1) / PP;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long g0 = tile * PP;
+    const long long grow0 = g0 * V;                           // global row of tile row 0 (polylines are consecutive)
+    const int npl = (int)min((long long)PP, p.G - g0);        // valid polylines of this tile
+    const int nrows = npl * V;
+    const bool ok0 = row0 < nrows, ok1 = row1 < nrows;
+    __syncthreads();                                          // the previous tile is done with Vs / Hs / Ms
+    // ---- polyline vectorisation (model_rad.py:369-382): node v and v + 1 of the lane
+    if (threadIdx.x < SGM_TILE) {
+      const int r = threadIdx.x;
+      uint32_t* vr = Vs + r * SGM_LD0;
+      if (r < nrows) {
+        const int pl = r / V, v = r - pl * V;
+        const float* a = p.lane + ((g0 + pl) * P + v) * 5;
+        const float xin[7] = {a[0], a[1], a[5], a[6], a[7], a[8], a[9]};
+        float* vo = p.vec + (grow0 + r) * 7;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) { vo[k] = xin[k]; vr[k] = sg_tf32(xin[k]); }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) vr[k] = 0u;
+      }
+      vr[7] = 0u;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int layer = 0; layer < 3; ++layer) {
+      const float* bias = par + (layer * 3 + 0) * HID;
+      const float* gam = par + (layer * 3 + 1) * HID;
+      const float* bet = par + (layer * 3 + 2) * HID;
+      float acc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int c = nt * 8 + 2 * t;
+        float b0 = bias[c], b1 = bias[c + 1];
+        acc[nt][0] = b0; acc[nt][1] = b1; acc[nt][2] = b0; acc[nt][3] = b1;
+        if (layer > 0) {                                      // + W[:, 64:] m of the row's polyline
+          acc[nt][0] += MBs[pl0 * SGM_LD + c]; acc[nt][1] += MBs[pl0 * SGM_LD + c + 1];
+          acc[nt][2] += MBs[pl1 * SGM_LD + c]; acc[nt][3] += MBs[pl1 * SGM_LD + c + 1];
+        }
+      }
+      if (layer == 0) {
+        uint32_t a[4] = {Vs[row0 * SGM_LD0 + t], Vs[row1 * SGM_LD0 + t], Vs[row0 * SGM_LD0 + t + 4], Vs[row1 * SGM_LD0 + t + 4]};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) sg_mma(acc[nt], a, W0s[(nt * 8 + g) * SGM_LD0 + t], W0s[(nt * 8 + g) * SGM_LD0 + t + 4]);
+      } else {
+        const uint32_t* Wa = Wab + (layer - 1) * 2 * 64 * SGM_LD;
+#pragma unroll 2
+        for (int ks = 0; ks < 8; ++ks) {
+          const int k = ks * 8 + t;
+          uint32_t a[4] = {sg_tf32(Hs[row0 * SGM_LD + k]), sg_tf32(Hs[row1 * SGM_LD + k]),
+                           sg_tf32(Hs[row0 * SGM_LD + k + 4]), sg_tf32(Hs[row1 * SGM_LD + k + 4])};
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) sg_mma(acc[nt], a, Wa[(nt * 8 + g) * SGM_LD + k], Wa[(nt * 8 + g) * SGM_LD + k + 4]);
+        }
+      }
+      // ---- epilogue: save y, LayerNorm over the quad's 64 channels (two-pass variance, as ln_fwd_kernel), ReLU,
+      //      h -> shared memory (next layer's operand, max-pool) and -> x_{layer+1}[:, :64]
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = h ? row1 : row0;
+        const bool ok = h ? ok1 : ok0;
+        float s = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) s += acc[nt][2 * h] + acc[nt][2 * h + 1];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        const float mu = s / (float)HID;
+        float q = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) { const float d0 = acc[nt][2 * h] - mu, d1 = acc[nt][2 * h + 1] - mu; q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); }
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 2);
+        const float rs = rsqrtf(q / (float)HID + p.eps);
+        const long long gr = grow0 + row;
+        if (ok && t == 0) { p.mean[layer][gr] = mu; p.rstd[layer][gr] = rs; }
+        float* yo = p.y[layer] + gr * HID;
+        float* xo = (layer == 0 ? p.x1 : p.x2) + gr * 2 * HID;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const int c = nt * 8 + 2 * t;
+          const float y0 = acc[nt][2 * h], y1 = acc[nt][2 * h + 1];
+          const float h0 = fmaxf(fmaf((y0 - mu) * rs, gam[c], bet[c]), 0.f), h1 = fmaxf(fmaf((y1 - mu) * rs, gam[c + 1], bet[c + 1]), 0.f);
+          *reinterpret_cast<float2*>(Hs + row * SGM_LD + c) = make_float2(h0, h1);
+          if (ok) {
+            *reinterpret_cast<float2*>(yo + c) = make_float2(y0, y1);
+            if (layer < 2) *reinterpret_cast<float2*>(xo + c) = make_float2(h0, h1);
+          }
+        }
+      }
+      __syncthreads();
+      // ---- segment max-pool over each polyline's nodes (first node on ties, NaN propagates like the unfused kernels)
+      for (int i = threadIdx.x; i < PP * HID; i += SGM_THREADS) {
+        const int pl = i >> 6, c = i & 63;
+        const float* hr = Hs + pl * V * SGM_LD + c;
+        float best = hr[0];
+        int bi = 0;
+#pragma unroll
+        for (int v = 1; v < V; ++v) { const float tv = hr[v * SGM_LD]; if (tv > best || tv != tv) { best = tv; bi = v; } }
+        Ms[pl * SGM_LD + c] = best;
+        if (pl < npl) {
+          const long long gg = g0 + pl;
+          p.arg[layer][gg * HID + c] = bi;
+          if (layer == 2) {                                   // tok = [m_2 | m_2]; arg-max of the broadcast half is node 0
+            p.tok[gg * 2 * HID + c] = best; p.tok[gg * 2 * HID + HID + c] = best;
+            p.argf[gg * 2 * HID + c] = bi; p.argf[gg * 2 * HID + HID + c] = 0;
+          }
+        }
+      }
+      __syncthreads();
+      if (layer == 2) break;
+      // ---- x_{layer+1}[:, 64:] = m of the row's polyline
+      {
+        float* xo = (layer == 0 ? p.x1 : p.x2) + grow0 * 2 * HID;
+        for (int i = threadIdx.x; i < nrows * 16; i += SGM_THREADS) {
+          const int r = i >> 4, q4 = i & 15;
+          *reinterpret_cast<float4*>(xo + (long long)r * 2 * HID + HID + q4 * 4) = *reinterpret_cast<const float4*>(Ms + (r / V) * SGM_LD + q4 * 4);
+        }
+      }
+      // ---- per-polyline product with the broadcast half of the next layer's weights: MBs = Ms W[:, 64:]^T
+      if (warp < 8 * PM) {
+        const int nt = warp & 7, mt = warp >> 3;
+        const uint32_t* Wb = Wab + (layer * 2 + 1) * 64 * SGM_LD;
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* m0 = Ms + (mt * 16 + g) * SGM_LD;
+        const float* m1 = m0 + 8 * SGM_LD;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const int k = ks * 8 + t;
+          uint32_t a[4] = {sg_tf32(m0[k]), sg_tf32(m1[k]), sg_tf32(m0[k + 4]), sg_tf32(m1[k + 4])};
+          sg_mma(d, a, Wb[(nt * 8 + g) * SGM_LD + k], Wb[(nt * 8 + g) * SGM_LD + k + 4]);
+        }
+        const int c = nt * 8 + 2 * t;
+        *reinterpret_cast<float2*>(MBs + (mt * 16 + g) * SGM_LD + c) = make_float2(d[0], d[1]);
+        *reinterpret_cast<float2*>(MBs + (mt * 16 + g + 8) * SGM_LD + c) = make_float2(d[2], d[3]);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <int V>
+int launch_subgraph_mma(const SubgraphParams& p, cudaStream_t stream) {
+  constexpr int PP = SGM_TILE / V;
+  const int smem = sgm_smem_words() * (int)sizeof(float);
+  cudaError_t ce = cudaFuncSetAttribute(subgraph_mma_fwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (ce != cudaSuccess) { mmfn_set_error("subgraph_fused_fwd: smem attribute: %s", cudaGetErrorString(ce)); return (int)ce; }
+  const long long ntiles = (p.G + PP - 1) / PP;
+  const int grid = (int)(ntiles < 148 ? ntiles : 148);
+  subgraph_mma_fwd_kernel<V><<<grid, SGM_THREADS, smem, stream>>>(p);
+  return mmfn_launch_status("subgraph_fused_fwd");
+}
+
 }  // namespace
 
 // lane: (G, V + 1, 5) polyline nodes; w0 (64,7), w1 / w2 (64,128), biases and LayerNorm parameters (64) of the three
 // Subgraph layers (reference keys lane_subgraph.layers.mlp_{0,1,2}.mlp.{0,1}).  Outputs (caller-allocated): vec (G*V,7);
 // y0..y2 (G*V,64) pre-LayerNorm linear outputs; mean*/rstd* (G*V); x1, x2 (G*V,128) inputs of layers 1 / 2; arg0..arg2
 // (G,64) node index of each pooled maximum; tok (G,128) polyline tokens; argf (G,128) arg-max of the final pool.
-// V in {9, 19} (10- / 20-node lanes): other lane lengths take the unfused kernels.
-MMFN_API int mmfn_subgraph_fused_fwd(const float* lane, int64_t G, int V,
+// V in {9, 19} (10- / 20-node lanes): other lane lengths take the unfused kernels.  tf32 != 0: the linears multiply on the
+// tensor cores (mma.sync TF32, fp32 accumulate) instead of exact fp32 FMAs.
+MMFN_API int mmfn_subgraph_fused_fwd(const float* lane, int64_t G, int V, int tf32,
                                      const float* w0, const float* b0, const float* g0, const float* be0,
                                      const float* w1, const float* b1, const float* g1, const float* be1,
                                      const float* w2, const float* b2, const float* g2, const float* be2,
@@ -238,6 +447,7 @@ MMFN_API int mmfn_subgraph_fused_fwd(const float* lane, int64_t G, int V,
   p.mean[0] = mean0; p.mean[1] = mean1; p.mean[2] = mean2; p.rstd[0] = rstd0; p.rstd[1] = rstd1; p.rstd[2] = rstd2;
   p.x1 = x1; p.x2 = x2; p.arg[0] = arg0; p.arg[1] = arg1; p.arg[2] = arg2; p.tok = tok; p.argf = argf;
   p.G = G; p.eps = eps;
+  if (tf32) return V == 9 ? launch_subgraph_mma<9>(p, stream) : launch_subgraph_mma<19>(p, stream);
   if (V == 9) return launch_subgraph<9>(p, stream);
   return launch_subgraph<19>(p, stream);
 }

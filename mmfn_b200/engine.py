@@ -125,11 +125,12 @@ class TrainEngine:
         self.st.flat_grad.zero_()
         self.rng.add_(1000003)
         self.st.flat_nbt.add_(model._nbt_step())
-        lidar = (b["lidar"] if "lidar" in b else ops.bev_unpack_u8(b["lidar_u8"]) if "lidar_u8" in b
-                 else ops.bev_scatter(b["points"]))
+        # input kernels of the LiDAR / radar branches run inside those branches (callables), not ahead of the image trunk
+        lidar = (b["lidar"] if "lidar" in b else (lambda: ops.bev_unpack_u8(b["lidar_u8"])) if "lidar_u8" in b
+                 else (lambda: ops.bev_scatter(b["points"])))
         radar_adj = b.get("radar_adj")
         if radar_adj is None and "radar_az64" in b:
-            radar_adj = ops.radar_adjacency(b["radar_az64"])
+            radar_adj = lambda: ops.radar_adjacency(b["radar_az64"])
         image = b["rgb_u8"] if "rgb_u8" in b else b["image"]
         # the RGB+LiDAR-only variant (transfuser.TransFuser) has no lane / radar inputs
         lane = b["map_u8"] if model.VARIANT == "img" else b.get("lane")     # model_img: rasterised map image

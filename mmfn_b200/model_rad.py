@@ -773,16 +773,19 @@ class _Net:
         return out
 
     def forward(self, image, lidar, lane, lane_num, radar, radar_adj, target_point, velocity, seed, train):
-        """`lane` is the padded lane tensor (rad / vec) or the rasterised map image (B,3,256,256) (img)."""
+        """`lane` is the padded lane tensor (rad / vec) or the rasterised map image (B,3,256,256) (img).  `lidar` and
+        `radar_adj` may be zero-argument callables (the engine's BEV scatter / histogram unpacking / adjacency kernels):
+        they are then evaluated INSIDE the LiDAR / radar branch, off the image trunk's stream."""
+        val = lambda t: t() if callable(t) else t
         branches = [
             lambda: self.img_layers[0].fwd(self.img_stem.fwd(ops.nchw_to_nhwc(image, self.mean, self.std), train), train),
-            lambda: self.lid_layers[0].fwd(self.lid_stem.fwd(ops.nchw_to_nhwc(lidar), train), train)]
+            lambda: self.lid_layers[0].fwd(self.lid_stem.fwd(ops.nchw_to_nhwc(val(lidar)), train), train)]
         if self.map_stem is not None:          # model_img.py:337-340, :348 -- the map image is NOT ImageNet-normalised
             branches.append(lambda: self.map_layers[0].fwd(self.map_stem.fwd(ops.nchw_to_nhwc(lane), train), train))
         else:
             branches.append(lambda: self.vectornet.fwd(lane, lane_num))
         if self.gat is not None:
-            branches.append(lambda: self.gat.fwd(radar, radar_adj, seed + 900, train))
+            branches.append(lambda: self.gat.fwd(radar, val(radar_adj), seed + 900, train))
         out = self._parallel(*branches)
         img, lid, mp = out[:3]
         for s in range(3):

@@ -938,6 +938,9 @@ FUSE_SUBGRAPH = _os.environ.get("MMFN_FUSE_SUBGRAPH", "1") != "0"
 SUBGRAPH_FUSED_V = (9, 19)       # vectors per polyline the one-launch Subgraph forward is instantiated for
 
 
+SUBGRAPH_MMA = os.environ.get("MMFN_SUBGRAPH_MMA", "1") != "0"   # TF32 configuration: tensor-core sub-graph kernel
+
+
 def subgraph_fused_fwd(lane, layers, eps=1e-5):
     """Polyline Subgraph forward in ONE launch (csrc/vectornet.cu; reference model_rad.py:260-283, :369-382).
     lane (B, L, P, 5); layers = 3 x (W, b, gamma, beta).  -> dict with everything the unfused backward consumes:
@@ -951,7 +954,7 @@ def subgraph_fused_fwd(lane, layers, eps=1e-5):
     o = dict(vec=f(G * V, 7), y=[f(G * V, 64) for _ in range(3)], mean=[f(G * V) for _ in range(3)], rstd=[f(G * V) for _ in range(3)],
              x1=f(G * V, 128), x2=f(G * V, 128), arg=[i(G, 64) for _ in range(3)], tok=f(G, 128), argf=i(G, 128))
     flat = [_p(t) for layer in layers for t in layer]
-    lib().subgraph_fused_fwd(_p(lane), G, V, *flat, _p(o["vec"]), *[_p(t) for t in o["y"]],
+    lib().subgraph_fused_fwd(_p(lane), G, V, int(TF32 and SUBGRAPH_MMA), *flat, _p(o["vec"]), *[_p(t) for t in o["y"]],
                              _p(o["mean"][0]), _p(o["rstd"][0]), _p(o["mean"][1]), _p(o["rstd"][1]), _p(o["mean"][2]), _p(o["rstd"][2]),
                              _p(o["x1"]), _p(o["x2"]), *[t.data_ptr() for t in o["arg"]], _p(o["tok"]), o["argf"].data_ptr(),
                              eps, _st())

@@ -38,7 +38,7 @@ class _NetTF(_Net):
     def forward(self, image, lidar, lane, lane_num, radar, radar_adj, target_point, velocity, seed, train):
         img, lid = self._parallel(
             lambda: self.img_layers[0].fwd(self.img_stem.fwd(ops.nchw_to_nhwc(image, self.mean, self.std), train), train),
-            lambda: self.lid_layers[0].fwd(self.lid_stem.fwd(ops.nchw_to_nhwc(lidar), train), train))
+            lambda: self.lid_layers[0].fwd(self.lid_stem.fwd(ops.nchw_to_nhwc(lidar() if callable(lidar) else lidar), train), train))
         for s in range(3):
             tok = self.gpts[s].fwd([img, lid], velocity, seed, train)
             img, lid = self._parallel(

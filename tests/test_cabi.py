@@ -68,9 +68,9 @@ def test_argument_validation_without_gpu():
         lib().copy2d_f32(P, 4, P, 8, 2, 6, 0, None)
     # one-launch polyline sub-graph: instantiated for 9 / 19 vectors per polyline only
     with pytest.raises(MmfnError, match="V must be 9 or 19"):
-        lib().subgraph_fused_fwd(P, 4, 12, *([P] * 12), *([P] * 17), 1e-5, None)
+        lib().subgraph_fused_fwd(P, 4, 12, 0, *([P] * 12), *([P] * 17), 1e-5, None)
     with pytest.raises(MmfnError, match="null output"):
-        lib().subgraph_fused_fwd(P, 4, 9, *([P] * 12), 0, *([P] * 16), 1e-5, None)
+        lib().subgraph_fused_fwd(P, 4, 9, 0, *([P] * 12), 0, *([P] * 16), 1e-5, None)
     # whole-GPT kernels and the one-launch attention backward: supported geometries only
     with pytest.raises(MmfnError, match="needs C in"):
         lib().gpt_small_fwd(P, 2, 192, 256, 4, 8, 2, P, *([P] * 13), 0.0, 0.0, 0, 1e-5, None)

@@ -673,6 +673,42 @@ def test_config5_vectornet_only_matches_oracle(dev, tf32):
         assert rel < (1e-3 if not tf32 else 3e-2), (k, rel)     # measured 2.7e-4 (fp32: split-K atomics over 20k vectors)
 
 
+@pytest.mark.parametrize("L,P,B", [(128, 10, 3), (256, 20, 2), (7, 10, 3), (5, 20, 1), (256, 20, 9)], ids=["ref-10-node", "bench-20-node", "ragged-10", "ragged-20", "many-tiles"])
+def test_tensor_core_subgraph_forward_matches_simt_kernel(dev, L, P, B):
+    """csrc/vectornet.cu subgraph_mma_fwd_kernel (TF32 mma.sync tiles, 256-row tiles of whole polylines) against the exact
+    fp32 lane-per-node kernel on the same inputs: values within TF32 rounding (3e-3 of each tensor's scale), and the
+    tensors it leaves for the backward are consistent among themselves EXACTLY: x[:, 64:] is the max over the polyline's
+    nodes of x[:, :64], arg points at a node that attains it, tok = [m_2 | m_2]."""
+    from mmfn_b200 import ops
+    model, sd, b = _vectornet_setup(dev, B, L, P, True)
+    vn = model.net.vectornet
+    lane = b["lane"].to(dev)
+    layers = [(lin.w, lin.b, ln.g, ln.b) for lin, ln in vn.sub]
+    G, V = B * L, P - 1
+    try:
+        ops.TF32 = False
+        ref = ops.subgraph_fused_fwd(lane, layers)
+        ops.TF32 = True
+        got = ops.subgraph_fused_fwd(lane, layers)
+    finally:
+        ops.TF32 = True
+
+    def close(a, r, tol=3e-3):
+        err, scale = (a - r).abs().max().item(), max(r.abs().max().item(), 1.0)
+        assert err <= tol * scale, (err, scale)
+    assert torch.equal(got["vec"], ref["vec"])
+    for i in range(3):
+        close(got["y"][i], ref["y"][i]); close(got["mean"][i], ref["mean"][i]); close(got["rstd"][i], ref["rstd"][i], 2e-2)
+        assert (got["arg"][i] == ref["arg"][i]).float().mean().item() > 0.97          # near-ties may resolve differently
+    close(got["x1"], ref["x1"]); close(got["x2"], ref["x2"]); close(got["tok"], ref["tok"])
+    for x, arg in ((got["x1"], got["arg"][0]), (got["x2"], got["arg"][1])):
+        h, m = x[:, :64].view(G, V, 64), x[:, 64:].view(G, V, 64)
+        assert torch.equal(m, h.max(dim=1, keepdim=True).values.expand(-1, V, -1))
+        assert torch.equal(h.gather(1, arg.long().view(G, 1, 64)).squeeze(1), m[:, 0])
+    assert torch.equal(got["tok"][:, :64], got["tok"][:, 64:])
+    assert torch.equal(got["argf"][:, :64], got["arg"][2]) and int(got["argf"][:, 64:].abs().max()) == 0
+
+
 @pytest.mark.parametrize("L,P", [(128, 10), (256, 20), (7, 10), (5, 20)], ids=["ref-10-node", "bench-20-node", "ragged-10", "ragged-20"])
 def test_fused_subgraph_forward_matches_unfused_kernels(dev, L, P):
     """csrc/vectornet.cu (one launch: vectorise + 3 x [Linear, LayerNorm, ReLU, max-pool, concat] + final max) against the
