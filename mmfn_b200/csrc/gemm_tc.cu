@@ -81,6 +81,13 @@ static int persist_wide_tiles() {                        // MMFN_GEMM_PERSIST_25
   if (mode < 0) { const char* v = getenv("MMFN_GEMM_PERSIST_256"); mode = (v && v[0] == '1') ? 1 : 0; }
   return mode;
 }
+static int sm_count();
+// smallest tile count the persistent kernel takes (MMFN_GEMM_PERSIST_MIN; default two tiles per SM)
+static int persist_min_tiles() {
+  static int n = 0;
+  if (!n) { const char* v = getenv("MMFN_GEMM_PERSIST_MIN"); n = v ? atoi(v) : 0; if (n <= 0) n = 2 * sm_count(); }
+  return n;
+}
 static int sm_count() {
   static int n = 0;
   if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
@@ -112,7 +119,7 @@ int run_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, co
   GemmOp<AMN, BMN, 128, EB> op{g.M, g.N, g.K, kb_per, splitk, g.nb1, g.ldc, g.c_sb0, g.c_sb1, g.pa, g.pb};
   {
     const int ntiles = ((g.N + 127) / 128) * ((g.M + tc::TBM - 1) / tc::TBM);
-    if (splitk == 1 && gz == 1 && ntiles >= 2 * sm_count() && e.bn_ws == nullptr && e.trace == nullptr && persist_mode())
+    if (splitk == 1 && gz == 1 && ntiles >= persist_min_tiles() && e.bn_ws == nullptr && e.trace == nullptr && persist_mode())
       return tc::launch_persist<GemmOp<AMN, BMN, 128, EB>, 128>(ta, tb, op, e, ntiles, sm_count(), stream, what);
   }
   return tc::launch<GemmOp<AMN, BMN, 128, EB>, 128, 3, true>(ta, tb, op, e, dim3((g.N + 127) / 128, (g.M + tc::TBM - 1) / tc::TBM, gz), stream, what);

@@ -291,7 +291,7 @@ bn_bwd_dx_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
   }
 }
 
-// ---- small feature maps (M <= 2048 rows: layer 4 at B=16): ONE launch.  Such tensors (<= 4 MB) live in L2, so
+// ---- small feature maps (M <= BN_SMALL_ROWS = 1024 rows: layer 4 at B=16): ONE launch.  Such tensors (<= 4 MB) live in L2, so
 // the two-kernel scheme is pure launch/tail latency.  One CTA owns one channel quad: pass 1 reduces its column over
 // all rows, the CTA publishes the statistics, pass 2 re-reads the column (L2/L1 hits) and writes the result.
 template <bool BWD>
@@ -409,7 +409,8 @@ bn_small_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, con
     }
   }
 }
-constexpr int BN_SMALL_ROWS = 2048;
+// feature maps with at most this many rows take the single-launch kernel (mmfn_set_bn_small_rows; default 1024: at 2048 rows the two-kernel path with statistics from the convolution epilogue measured +1.7 % on the bf16 B = 32 step, 4096 rows on the single-launch kernel -4.5 % at TF32 B = 16)
+static int BN_SMALL_ROWS = 1024;
 
 // ------------------------------------------------------------------ stem tail: BatchNorm -> ReLU -> MaxPool 3x3 / 2
 // The two ResNet stems end in bn1 -> relu -> maxpool (model_rad.py:512-521) on the largest activation of the network
@@ -882,6 +883,16 @@ ln_bwd_param_vec_kernel(const float4* __restrict__ dy, const float4* __restrict_
 }
 
 }  // namespace
+
+// Row threshold below which train-mode BatchNorm forward / backward run as ONE launch (one CTA per channel quad, two
+// passes over an L2-resident column) instead of reduction + streaming kernels.  Returns the previous value in *old
+// (nullable).  Host-side setting, not stream-ordered.
+MMFN_API int mmfn_set_bn_small_rows(int rows, int* old) {
+  MMFN_CHECK_ARG(rows >= 0, "set_bn_small_rows: rows must be >= 0");
+  if (old) *old = BN_SMALL_ROWS;
+  BN_SMALL_ROWS = rows;
+  return 0;
+}
 
 // y_bf16 (nullable): a bf16 twin of y written in the same pass -- the operand of the next bf16 convolution.
 // x,y: (M,C) NHWC rows.  ws: per-stream scratch of at least 34*C + 8 doubles that is ZERO on entry (zero it once

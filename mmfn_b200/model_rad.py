@@ -15,6 +15,7 @@ nn.Module/Parameter bookkeeping.  `loss.backward()` still works for callers that
 autograd.Function around the whole network), but the fast path is engine.TrainEngine.
 """
 import math
+import os
 from collections import deque
 
 import numpy as np
@@ -38,7 +39,7 @@ class _Aux:
     critical path re-joins soon (fork(): attention dK / dV, filter flips) gets its own stream pair so it never
     queues behind leaves.  Inputs are kept alive until join_all() -- no allocator reuse hazards."""
     enabled = True
-    N_LEAF, N_FORK = 4, 2
+    N_LEAF, N_FORK = int(os.environ.get("MMFN_AUX_LEAF", "4")), 2
     pools, used, keep = {}, {}, []
     epoch = 0            # bumped by join_all(): fork events of earlier epochs are already ordered before the caller
 

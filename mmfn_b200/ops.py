@@ -412,7 +412,18 @@ def conv2d_wgrad_(dy, x, dw_krsc, stride, pad):
 # ------------------------------------------------------------------ normalisation
 _ws = {}
 BN_WS_MAX_C = 2048
-BN_SMALL_ROWS = 2048     # norm.cu: feature maps with at most this many rows take the single-launch kernel
+BN_SMALL_ROWS = 1024     # norm.cu: feature maps with at most this many rows take the single-launch kernel
+
+
+def set_bn_small_rows(rows):
+    """Move the single-launch BatchNorm threshold (library + this module's mirror of it)."""
+    global BN_SMALL_ROWS
+    lib().set_bn_small_rows(int(rows), 0)
+    BN_SMALL_ROWS = int(rows)
+
+
+if _os.environ.get("MMFN_BN_SMALL_ROWS"):
+    set_bn_small_rows(int(_os.environ["MMFN_BN_SMALL_ROWS"]))
 
 
 F32, TF32_T, BF16_T = 0, 1, 2                     # MMFN_F32 / MMFN_TF32 / MMFN_BF16 of the header
