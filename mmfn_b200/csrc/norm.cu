@@ -227,7 +227,7 @@ bn_apply_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n4
     o.w = (v.w - m.w) * r.w * g.w + b.w;
     if (res) { const float4 q = __ldg(res + i); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    y[i] = o;
+    if (y) y[i] = o;                                              // null: only the bf16 twin is wanted
     if (y16) y16[i] = mmfn_pack_bf16x4(o.x, o.y, o.z, o.w);       // bf16 twin: the operand of the next convolution
   }
 }
@@ -937,11 +937,13 @@ int mmfn_bn_stats_launch(const float* x, int64_t M, int C, float* mean, float* r
 }
 
 // y = (x - mean) * rstd * gamma + beta (+ res, ReLU) from statistics that already exist (published by the epilogue of
-// mmfn_conv2d_fwd_bn_*): the apply half of mmfn_bn_train_fwd.  y_bf16 (nullable): bf16 twin of y.
+// mmfn_conv2d_fwd_bn_*): the apply half of mmfn_bn_train_fwd.  y_bf16 (nullable): bf16 twin of y; y itself may be null
+// when only the twin is wanted (the activation between the two convolutions of a BasicBlock in the bf16 configuration:
+// its only readers are the next convolution's TMA loads).
 MMFN_API int mmfn_bn_apply(const float* x, float* y, int64_t M, int C, const float* gamma, const float* beta,
                            const float* mean, const float* rstd, const float* res, int relu, void* y_bf16,
                            cudaStream_t stream) {
-  MMFN_CHECK_ARG(x && y && gamma && beta && mean && rstd, "bn_apply: null pointer");
+  MMFN_CHECK_ARG(x && (y || y_bf16) && gamma && beta && mean && rstd, "bn_apply: null pointer");
   MMFN_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0, "bn_apply: C must be a positive multiple of 4");
   MMFN_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)res | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)mean | (uintptr_t)rstd) & 15) == 0 &&
                  ((uintptr_t)y_bf16 & 7) == 0, "bn_apply: alignment");

@@ -122,7 +122,9 @@ class TrainEngine:
         model.train()
         if ops.BF16 and not torch.cuda.is_current_stream_capturing():
             self.st.sync_shadow()                      # eager callers may have touched the fp32 masters; replays rely on AdamW
-        self.st.flat_grad.zero_()
+        # the gradient buffer is first touched by backward: its zeroing rides a side stream under the first fusion
+        # transformer's forward (net.idle_hook) instead of heading the step
+        self.net.idle_hook = self.st.flat_grad.zero_
         self.rng.add_(1000003)
         self.st.flat_nbt.add_(model._nbt_step())
         # input kernels of the LiDAR / radar branches run inside those branches (callables), not ahead of the image trunk
@@ -136,6 +138,7 @@ class TrainEngine:
         lane = b["map_u8"] if model.VARIANT == "img" else b.get("lane")     # model_img: rasterised map image
         pred = self.net.forward(image, lidar, lane, b.get("lane_num"), b.get("radar"), radar_adj,
                                 b["target_point"], b["velocity"], model.seed, True)
+        self.net.idle_hook = None
         loss, dpred = ops.l1_loss(pred, b["gt_waypoints"])
         self.net.backward(dpred)
         self.last_pred = pred

@@ -136,7 +136,9 @@ class ConvBN:
         self.rm, self.rv = st.buf(bn_key + ".running_mean"), st.buf(bn_key + ".running_var")
         self.stride, self.pad = stride, pad
 
-    def fwd(self, x, res=None, relu=True, train=True, no_twin=False):
+    def fwd(self, x, res=None, relu=True, train=True, no_twin=False, only16=False):
+        """only16 (a hint): the caller's only reader of y is a bf16 convolution -- where the BatchNorm-apply kernel runs
+        separately and the backward takes its ReLU mask from z, y is written as bf16 only."""
         self.x, self.relu = x, relu
         self.col, self.direct = None, False
         self.has_res = res is not None
@@ -148,8 +150,10 @@ class ConvBN:
         if train and ops.conv_bn_fusable(xin, win, self.stride, self.pad):
             # batch statistics from the convolution's own epilogue (+ last-CTA finalize): no reduction pass over z
             self.z, self.mean, self.rstd = ops.conv2d_fwd_bn(xin, win, self.stride, self.pad, self.rm, self.rv)
+            only16 = (only16 and ops.BF16 and ops.BF16_ONLY_INNER and ops.BN_MASK_FROM_Z and relu and res is None
+                      and not no_twin)
             self.y = ops.bn_apply(self.z, self.gam, self.bet, self.mean, self.rstd, res=res, relu=relu,
-                                  want16=ops.BF16 and not no_twin)
+                                  want16=ops.BF16 and not no_twin, only16=only16)
             return self.y
         if self.bf:
             self.z = ops.conv2d_fwd(x.h, self.w16, self.stride, self.pad)
@@ -199,7 +203,10 @@ class BasicBlock:
         self.ds = ConvBN(st, prefix + ".downsample.0.weight", prefix + ".downsample.1", stride, 0) if downsample else None
 
     def fwd(self, x, train):
-        a = self.c1.fwd(x, relu=True, train=train)
+        # a is read by conv2 only: bf16-only when conv2 takes the bf16 tensor-core path (same spatial size, stride 1)
+        Ho, Wo = ops.conv_out_hw(x.shape[1], x.shape[2], 3, 3, self.c1.stride, 1)
+        a = self.c1.fwd(x, relu=True, train=train,
+                        only16=train and ops.BF16 and ops.bf16_conv_ok(self.c1.w.shape[0], self.c2.w.shape[0], Ho, Wo))
         idn = self.ds.fwd(x, relu=False, train=train, no_twin=True) if self.ds else x     # residual only: fp32 suffices
         return self.c2.fwd(a, res=idn, relu=True, train=train)
 
@@ -789,6 +796,7 @@ class _Net:
             branches.append(lambda: self.gat.fwd(radar, val(radar_adj), seed + 900, train))
         out = self._parallel(*branches)
         img, lid, mp = out[:3]
+        self._run_idle_hook()
         for s in range(3):
             tok = self.gpts[s].fwd([img, lid, mp], velocity, seed, train)
             img, lid, mp = self._parallel(
@@ -801,6 +809,28 @@ class _Net:
         return self.head.fwd(fused, target_point)
 
     mid_hook = None
+    # Work the step needs before BACKWARD but not for the forward (the engine: zeroing the 420 MB gradient buffer).  It is
+    # issued on its own stream once the stems and layer 1 are done -- the HBM-bound head of the step is over and the
+    # latency-bound first fusion transformer leaves the memory system idle -- and joined at the start of backward().
+    idle_hook = None
+    _idle_done = None
+
+    def _run_idle_hook(self):
+        self._idle_done = None
+        if self.idle_hook is None:
+            return
+        if not self.use_streams:
+            self.idle_hook()
+            return
+        if getattr(self, "_idle_stream", None) is None:
+            self._idle_stream = torch.cuda.Stream(device=self.mean.device, priority=0)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._idle_stream.wait_event(ev)
+        with torch.cuda.stream(self._idle_stream):
+            self.idle_hook()
+            self._idle_done = torch.cuda.Event()
+            self._idle_done.record(self._idle_stream)
 
     def _bucket_done(self, which):
         """Backward has passed a fusion stage: every gradient of params.is_early_bucket() ("early": after the last
@@ -815,6 +845,9 @@ class _Net:
         self._bucket_done("early")
 
     def backward(self, dpred):
+        if self._idle_done is not None:
+            torch.cuda.current_stream().wait_event(self._idle_done)
+            self._idle_done = None
         dfused = self.head.bwd(dpred)
         nmod = 4 if self.gat is not None else 3
         dfe, dtok = ops.pool_sum_bwd(dfused, nmod)

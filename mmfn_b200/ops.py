@@ -242,6 +242,8 @@ def conv2d_fwd(x, w_krsc, stride, pad, res=None):
 
 # BatchNorm backward: ReLU mask recomputed from z (conv -> BN -> ReLU without a residual) / read from the bf16 twin of y
 BN_MASK_FROM_Z = _os.environ.get("MMFN_BN_MASK_Z", "1") != "0"
+# bf16 configuration: the activation between the two convolutions of a BasicBlock exists only as bf16 (no fp32 copy)
+BF16_ONLY_INNER = _os.environ.get("MMFN_BF16_ONLY_INNER", "1") != "0"
 FUSE_BN_STATS = _os.environ.get("MMFN_FUSE_BN", "1") != "0"   # train-mode BatchNorm statistics from the convolution epilogue
 BN_FUSE_MAX_CTAS = int(_os.environ.get("MMFN_FUSE_BN_MAX_CTAS", "512"))
 
@@ -277,12 +279,17 @@ def conv2d_fwd_bn(x, w_krsc, stride, pad, running_mean, running_var, momentum=0.
     return z, mean, rstd
 
 
-def bn_apply(x, gamma, beta, mean, rstd, res=None, relu=False, want16=False):
+def bn_apply(x, gamma, beta, mean, rstd, res=None, relu=False, want16=False, only16=False):
+    """only16: write just the bf16 result (returned as a bf16 tensor that is its own twin): for activations whose only
+    readers are bf16 convolutions."""
     C = x.shape[-1]
     M = x.numel() // C
-    y = torch.empty_like(x)
-    y16 = torch.empty(x.shape, device=x.device, dtype=BF) if want16 else None
+    y = None if only16 else torch.empty_like(x)
+    y16 = torch.empty(x.shape, device=x.device, dtype=BF) if (want16 or only16) else None
     lib().bn_apply(_p(x), _p(y), M, C, _p(gamma), _p(beta), _p(mean), _p(rstd), _p(res), int(relu), _p(y16), _st())
+    if only16:
+        y16.h = y16
+        return y16
     return _with_twin(y, y16)
 
 

@@ -39,6 +39,7 @@ class _NetTF(_Net):
         img, lid = self._parallel(
             lambda: self.img_layers[0].fwd(self.img_stem.fwd(ops.nchw_to_nhwc(image, self.mean, self.std), train), train),
             lambda: self.lid_layers[0].fwd(self.lid_stem.fwd(ops.nchw_to_nhwc(lidar() if callable(lidar) else lidar), train), train))
+        self._run_idle_hook()
         for s in range(3):
             tok = self.gpts[s].fwd([img, lid], velocity, seed, train)
             img, lid = self._parallel(
@@ -49,6 +50,9 @@ class _NetTF(_Net):
         return self.head.fwd(fused, target_point)
 
     def backward(self, dpred):
+        if self._idle_done is not None:
+            torch.cuda.current_stream().wait_event(self._idle_done)
+            self._idle_done = None
         dfused = self.head.bwd(dpred)
         dfe, dtok = ops.pool_sum_bwd(dfused, 2)
         self.gpts[3].bwd(dtok, dfe)
