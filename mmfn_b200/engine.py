@@ -88,6 +88,26 @@ class BatchStager:
         return self.dev_views
 
 
+def batch_inputs(b, lazy=False):
+    """(lidar histogram, radar adjacency) of a device batch in any of its forms: a pre-built `lidar` histogram, the
+    packed loader's `lidar_u8` counts, or a raw `points` sweep; `radar_adj` or the packed loader's float64 azimuths.
+    lazy: zero-argument callables for whatever needs a kernel, so that the network issues it inside the branch that
+    consumes it (off the image trunk's stream)."""
+    if "lidar" in b:
+        lidar = b["lidar"]
+    elif "lidar_u8" in b:
+        lidar = lambda: ops.bev_unpack_u8(b["lidar_u8"])
+    else:
+        lidar = lambda: ops.bev_scatter(b["points"])
+    radar_adj = b.get("radar_adj")
+    if radar_adj is None and "radar_az64" in b:
+        radar_adj = lambda: ops.radar_adjacency(b["radar_az64"])
+    if not lazy:
+        lidar = lidar() if callable(lidar) else lidar
+        radar_adj = radar_adj() if callable(radar_adj) else radar_adj
+    return lidar, radar_adj
+
+
 class TrainEngine:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, process_group=None):
         self.model, self.net, self.st = model, model.net, model.store
@@ -128,11 +148,7 @@ class TrainEngine:
         self.rng.add_(1000003)
         self.st.flat_nbt.add_(model._nbt_step())
         # input kernels of the LiDAR / radar branches run inside those branches (callables), not ahead of the image trunk
-        lidar = (b["lidar"] if "lidar" in b else (lambda: ops.bev_unpack_u8(b["lidar_u8"])) if "lidar_u8" in b
-                 else (lambda: ops.bev_scatter(b["points"])))
-        radar_adj = b.get("radar_adj")
-        if radar_adj is None and "radar_az64" in b:
-            radar_adj = lambda: ops.radar_adjacency(b["radar_az64"])
+        lidar, radar_adj = batch_inputs(b, lazy=True)
         image = b["rgb_u8"] if "rgb_u8" in b else b["image"]
         # the RGB+LiDAR-only variant (transfuser.TransFuser) has no lane / radar inputs
         lane = b["map_u8"] if model.VARIANT == "img" else b.get("lane")     # model_img: rasterised map image

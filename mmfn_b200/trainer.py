@@ -9,7 +9,8 @@
   Trainer.resume(logdir)     the reference's resume branch (:288-302)
 
 Batches come from a DataLoader built on data.PRE_Data + data.collate_single_cpu (or any iterable of collated
-reference batches); they are flattened with data.to_engine_batch, packed into one pinned buffer and moved with a
+reference batches), or from data.PackedLoader (packed shards: already in engine form, histogram as uint8 counts and radar
+azimuths instead of the adjacency matrix -- expanded on the GPU); collated batches are flattened with data.to_engine_batch, packed into one pinned buffer and moved with a
 single H2D copy per step (engine.BatchStager).
 """
 import json
@@ -19,7 +20,7 @@ import torch
 
 from . import data as data_mod
 from . import ops
-from .engine import BatchStager, TrainEngine
+from .engine import BatchStager, TrainEngine, batch_inputs
 from .params import is_unused
 
 
@@ -65,9 +66,9 @@ class Trainer:
         total, n = 0.0, 0
         for data in loader:
             b = self._device_batch(data)
-            lidar = b["lidar"] if "lidar" in b else ops.bev_scatter(b["points"])
+            lidar, radar_adj = batch_inputs(b)                     # histogram / adjacency from any batch form (packed too)
             lane = b["map_u8"] if model.VARIANT == "img" else b.get("lane")
-            pred = model.net.forward(b["rgb_u8"], lidar, lane, b.get("lane_num"), b.get("radar"), b.get("radar_adj"),
+            pred = model.net.forward(b["rgb_u8"], lidar, lane, b.get("lane_num"), b.get("radar"), radar_adj,
                                      b["target_point"], b["velocity"], model.seed, False)
             loss, _ = ops.l1_loss(pred, b["gt_waypoints"], want_grad=False)
             total += float(loss)

@@ -517,7 +517,12 @@ def test_packed_loader_to_engine_path_matches_pickle_loader(dev, tmp_path):
     assert torch.equal(ops.radar_adjacency(db_pk["radar_az64"]), db_ref["radar_adj"])
     for k in ("rgb_u8", "lane", "lane_num", "radar", "velocity", "target_point", "gt_waypoints"):
         assert torch.equal(db_pk[k], db_ref[k]), k
-    eng = TrainEngine(model, lr=1e-4)
+    # Trainer.validate (Engine.validate, phase2_train_net.py:124-183) takes both batch forms
+    from mmfn_b200.trainer import Trainer
+    tr = Trainer(model, lr=1e-4, pad_lanes_to=128)
+    v_ref, v_pk = tr.validate([eb]), tr.validate(loader)
+    assert v_ref > 0 and abs(v_ref - v_pk) <= 1e-6 * v_ref          # same tensors in; atomics order in the reductions
+    eng = tr.engine
     loss_ref = eng.forward_backward(db_ref).item()
     pred_ref = eng.last_pred.clone()
     loss_pk = eng.forward_backward(db_pk).item()
