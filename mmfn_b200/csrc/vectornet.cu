@@ -237,7 +237,7 @@ template <int V>
 __global__ void __launch_bounds__(SGM_THREADS, 1)
 subgraph_mma_fwd_kernel(SubgraphParams p) {
   constexpr int PP = SGM_TILE / V;              // polylines per tile (28 / 13)
-  constexpr int ROWS = PP * V;                  // node rows per tile (252 / 247)
+  static_assert(PP * V <= SGM_TILE && PP <= 32, "tile geometry");   // 252 / 247 node rows per tile
   constexpr int PM = (PP + 15) / 16;            // m-tiles of the per-polyline product
   constexpr int P = V + 1;
   extern __shared__ __align__(16) float smf[];
