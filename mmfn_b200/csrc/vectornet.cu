@@ -211,7 +211,8 @@ int launch_subgraph(const SubgraphParams& p, cudaStream_t stream) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // Tensor-core formulation (TF32 configuration): the same sub-graph, the 64-wide linears as warp-level mma.sync m16n8k8
-// TF32 tiles.  A persistent CTA of 16 warps walks tiles of floor(256 / V) whole polylines (252 / 247 node rows); warp =
+// TF32 tiles.  A persistent CTA holds two groups of 8 warps, each walking tiles of floor(128 / V) whole polylines (126 / 114
+// node rows); warp =
 // one 16-row m-tile x all 64 channels, so a row's LayerNorm is a reduction over the four lanes of a quad; activations
 // stay in shared memory between layers (fp32, rounded to TF32 as the next layer's A fragments are loaded); the
 // segment max-pool scans the tile's rows in shared memory, and the broadcast half of the next layer's input ([h | m]:
@@ -219,7 +220,11 @@ int launch_subgraph(const SubgraphParams& p, cudaStream_t stream) {
 // whose result seeds the accumulators.  The lane-per-node SIMT kernel above spends a 16-byte shared-memory broadcast per
 // four FMAs (1.2 ms for the 622 592 rows of BASELINE configs[4]); here the tile's writes of the saved-for-backward
 // tensors (1.8 KB per row) are what remains.  Same outputs, same arg-max rule (first node on ties).
-constexpr int SGM_THREADS = 512, SGM_TILE = 256, SGM_LD = 68, SGM_LD0 = 12;
+// Two GROUPS of 8 warps per CTA, each walking its own 128-row tiles and synchronising on its own named barrier: the
+// groups drift apart, so one group's MMA phase overlaps the other's store-heavy epilogue (one 16-warp group in lockstep
+// measured 403 us at configs[4] with the DRAM pipe at 35 %).
+constexpr int SGM_THREADS = 512, SGM_GROUP = 256, SGM_TILE = 128, SGM_LD = 68, SGM_LD0 = 12;
+__device__ __forceinline__ void sg_group_sync(int grp) { asm volatile("bar.sync %0, %1;" :: "r"(grp + 1), "n"(SGM_GROUP) : "memory"); }
 
 __device__ __forceinline__ uint32_t sg_tf32(float v) {
   uint32_t r;
@@ -231,23 +236,24 @@ __device__ __forceinline__ void sg_mma(float* d, const uint32_t* a, uint32_t b0,
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-constexpr int sgm_smem_words() { return 64 * SGM_LD0 + 4 * 64 * SGM_LD + 9 * HID + SGM_TILE * SGM_LD + 2 * 32 * SGM_LD + SGM_TILE * SGM_LD0; }
+constexpr int sgm_group_words() { return SGM_TILE * SGM_LD + 2 * 16 * SGM_LD + SGM_TILE * SGM_LD0; }   // Hs, Ms, MBs, Vs of one group
+constexpr int sgm_smem_words() { return 64 * SGM_LD0 + 4 * 64 * SGM_LD + 9 * HID + 2 * sgm_group_words(); }
 
 template <int V>
 __global__ void __launch_bounds__(SGM_THREADS, 1)
 subgraph_mma_fwd_kernel(SubgraphParams p) {
-  constexpr int PP = SGM_TILE / V;              // polylines per tile (28 / 13)
-  static_assert(PP * V <= SGM_TILE && PP <= 32, "tile geometry");   // 252 / 247 node rows per tile
-  constexpr int PM = (PP + 15) / 16;            // m-tiles of the per-polyline product
+  constexpr int PP = SGM_TILE / V;              // polylines per tile (14 / 6)
+  static_assert(PP * V <= SGM_TILE && PP <= 16, "tile geometry");   // 126 / 114 node rows per tile, one m-tile of polylines
   constexpr int P = V + 1;
   extern __shared__ __align__(16) float smf[];
   uint32_t* W0s = reinterpret_cast<uint32_t*>(smf);          // [64][12]  layer 0 weights, k padded to 8
   uint32_t* Wab = W0s + 64 * SGM_LD0;                        // [4][64][68]: W1[:, :64], W1[:, 64:], W2[:, :64], W2[:, 64:]
   float* par = reinterpret_cast<float*>(Wab + 4 * 64 * SGM_LD);   // [3][3][64] bias, gamma, beta
-  float* Hs = par + 9 * HID;                                 // [256][68] activations of the tile
-  float* Ms = Hs + SGM_TILE * SGM_LD;                        // [32][68]  pooled maxima per polyline (rows >= PP stay zero)
-  float* MBs = Ms + 32 * SGM_LD;                             // [32][68]  W[:, 64:] m per polyline
-  uint32_t* Vs = reinterpret_cast<uint32_t*>(MBs + 32 * SGM_LD);  // [256][12] polyline vectors (TF32), k padded to 8
+  const int grp = threadIdx.x / SGM_GROUP, gtid = threadIdx.x - grp * SGM_GROUP;
+  float* Hs = par + 9 * HID + grp * sgm_group_words();       // [128][68] activations of the group's tile
+  float* Ms = Hs + SGM_TILE * SGM_LD;                        // [16][68]  pooled maxima per polyline (rows >= PP stay zero)
+  float* MBs = Ms + 16 * SGM_LD;                             // [16][68]  W[:, 64:] m per polyline
+  uint32_t* Vs = reinterpret_cast<uint32_t*>(MBs + 16 * SGM_LD);  // [128][12] polyline vectors (TF32), k padded to 8
   for (int i = threadIdx.x; i < 64 * 8; i += SGM_THREADS) { const int n = i >> 3, k = i & 7; W0s[n * SGM_LD0 + k] = k < 7 ? sg_tf32(p.w[0][n * 7 + k]) : 0u; }
   for (int i = threadIdx.x; i < 2 * 64 * 128; i += SGM_THREADS) {
     const int m = i >> 13, r = i & 8191, n = r >> 7, k = r & 127;
@@ -259,21 +265,22 @@ subgraph_mma_fwd_kernel(SubgraphParams p) {
     par[(l * 3 + 1) * HID + c] = p.gamma[l][c];
     par[(l * 3 + 2) * HID + c] = p.beta[l][c];
   }
-  for (int i = threadIdx.x; i < 2 * 32 * SGM_LD; i += SGM_THREADS) Ms[i] = 0.f;        // Ms and MBs
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  for (int i = gtid; i < 2 * 16 * SGM_LD; i += SGM_GROUP) Ms[i] = 0.f;                 // Ms and MBs of this group
+  __syncthreads();                                            // weights, parameters staged; from here on the groups run apart
+  const int warp = gtid >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int row0 = warp * 16 + g, row1 = row0 + 8;
   const int pl0 = min(row0 / V, PP - 1), pl1 = min(row1 / V, PP - 1);
   const long long ntiles = (p.G + PP - 1) / PP;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (long long tile = (long long)blockIdx.x * 2 + grp; tile < ntiles; tile += (long long)gridDim.x * 2) {
     const long long g0 = tile * PP;
     const long long grow0 = g0 * V;                           // global row of tile row 0 (polylines are consecutive)
     const int npl = (int)min((long long)PP, p.G - g0);        // valid polylines of this tile
     const int nrows = npl * V;
     const bool ok0 = row0 < nrows, ok1 = row1 < nrows;
-    __syncthreads();                                          // the previous tile is done with Vs / Hs / Ms
+    sg_group_sync(grp);                                       // the previous tile is done with Vs / Hs / Ms
     // ---- polyline vectorisation (model_rad.py:369-382): node v and v + 1 of the lane
-    if (threadIdx.x < SGM_TILE) {
-      const int r = threadIdx.x;
+    if (gtid < SGM_TILE) {
+      const int r = gtid;
       uint32_t* vr = Vs + r * SGM_LD0;
       if (r < nrows) {
         const int pl = r / V, v = r - pl * V;
@@ -288,7 +295,7 @@ subgraph_mma_fwd_kernel(SubgraphParams p) {
       }
       vr[7] = 0u;
     }
-    __syncthreads();
+    sg_group_sync(grp);
 #pragma unroll 1
     for (int layer = 0; layer < 3; ++layer) {
       const float* bias = par + (layer * 3 + 0) * HID;
@@ -354,9 +361,9 @@ subgraph_mma_fwd_kernel(SubgraphParams p) {
           }
         }
       }
-      __syncthreads();
+      sg_group_sync(grp);
       // ---- segment max-pool over each polyline's nodes (first node on ties, NaN propagates like the unfused kernels)
-      for (int i = threadIdx.x; i < PP * HID; i += SGM_THREADS) {
+      for (int i = gtid; i < PP * HID; i += SGM_GROUP) {
         const int pl = i >> 6, c = i & 63;
         const float* hr = Hs + pl * V * SGM_LD + c;
         float best = hr[0];
@@ -373,19 +380,19 @@ subgraph_mma_fwd_kernel(SubgraphParams p) {
           }
         }
       }
-      __syncthreads();
+      sg_group_sync(grp);
       if (layer == 2) break;
       // ---- x_{layer+1}[:, 64:] = m of the row's polyline
       {
         float* xo = (layer == 0 ? p.x1 : p.x2) + grow0 * 2 * HID;
-        for (int i = threadIdx.x; i < nrows * 16; i += SGM_THREADS) {
+        for (int i = gtid; i < nrows * 16; i += SGM_GROUP) {
           const int r = i >> 4, q4 = i & 15;
           *reinterpret_cast<float4*>(xo + (long long)r * 2 * HID + HID + q4 * 4) = *reinterpret_cast<const float4*>(Ms + (r / V) * SGM_LD + q4 * 4);
         }
       }
       // ---- per-polyline product with the broadcast half of the next layer's weights: MBs = Ms W[:, 64:]^T
-      if (warp < 8 * PM) {
-        const int nt = warp & 7, mt = warp >> 3;
+      {
+        const int nt = warp, mt = 0;
         const uint32_t* Wb = Wab + (layer * 2 + 1) * 64 * SGM_LD;
         float d[4] = {0.f, 0.f, 0.f, 0.f};
         const float* m0 = Ms + (mt * 16 + g) * SGM_LD;
@@ -400,7 +407,7 @@ subgraph_mma_fwd_kernel(SubgraphParams p) {
         *reinterpret_cast<float2*>(MBs + (mt * 16 + g) * SGM_LD + c) = make_float2(d[0], d[1]);
         *reinterpret_cast<float2*>(MBs + (mt * 16 + g + 8) * SGM_LD + c) = make_float2(d[2], d[3]);
       }
-      __syncthreads();
+      sg_group_sync(grp);
     }
   }
 }
@@ -411,8 +418,8 @@ int launch_subgraph_mma(const SubgraphParams& p, cudaStream_t stream) {
   const int smem = sgm_smem_words() * (int)sizeof(float);
   cudaError_t ce = cudaFuncSetAttribute(subgraph_mma_fwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (ce != cudaSuccess) { mmfn_set_error("subgraph_fused_fwd: smem attribute: %s", cudaGetErrorString(ce)); return (int)ce; }
-  const long long ntiles = (p.G + PP - 1) / PP;
-  const int grid = (int)(ntiles < 148 ? ntiles : 148);
+  const long long ntiles = (p.G + PP - 1) / PP, need = (ntiles + 1) / 2;     // two tile-walking groups per CTA
+  const int grid = (int)(need < 148 ? need : 148);
   subgraph_mma_fwd_kernel<V><<<grid, SGM_THREADS, smem, stream>>>(p);
   return mmfn_launch_status("subgraph_fused_fwd");
 }
