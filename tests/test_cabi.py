@@ -80,6 +80,35 @@ def test_argument_validation_without_gpu():
         lib().attention_bwd_small_bf16(P, P, P, P, P, 2, 192, 512, 4, None)
     with pytest.raises(MmfnError, match="head size 16 or 32"):
         lib().attention_bwd_small_tf32(P, P, P, P, P, 2, 192, 256, 4, None)
+    # stem kernels, BatchNorm mask modes, loader kernels, skinny weight gradient: argument checks precede every launch
+    with pytest.raises(MmfnError, match="C must be 2 or 3"):
+        lib().conv2d_stem7_fwd(P, P, P, 2, 256, 256, 4, None)
+    with pytest.raises(MmfnError, match="dz alignment"):
+        lib().conv2d_stem7_wgrad(P + 8, 0, P, P, 2, 256, 256, 3, None)
+    with pytest.raises(MmfnError, match="null pointer"):
+        lib().stem_bn_relu_maxpool_fwd(P, 2, 128, 128, 64, P, P, 0, 0, 0.1, 1e-5, P, P, P, 0, P, 0, P, None)      # zmax missing
+    with pytest.raises(MmfnError, match="C % 4 == 0"):
+        lib().stem_bn_relu_maxpool_bwd(P, P, P, P, P, P, P, 2, 128, 128, 62, P, 0, P, P, P, None)
+    with pytest.raises(MmfnError, match="relu_from_z needs beta and no yout"):
+        lib().bn_train_bwd(P, P, P, 0, 1, P, P, P, P, 4096, 64, P, 0, 0, P, P, P, None)
+    with pytest.raises(MmfnError, match="null pointer"):
+        lib().bn_apply(P, 0, 4096, 64, P, P, P, P, 0, 1, 0, None)                      # neither y nor its bf16 twin
+    with pytest.raises(MmfnError, match="bad sizes"):
+        lib().lidar_ego_transform_f64(P, 2, P, P, 1, 1024, None)
+    with pytest.raises(MmfnError, match="n % 4 == 0"):
+        lib().bev_unpack_u8(P, P, 10, None)
+    with pytest.raises(MmfnError, match="bad args"):
+        lib().radar_adjacency_f64(P, P, 0, 81, None)
+    with pytest.raises(MmfnError, match="16-byte aligned"):
+        lib().wgrad_n64_k7(P + 4, P, P, 4096, None)
+    # host-side setting: returns the previous threshold
+    import ctypes
+    old = ctypes.c_int(-1)
+    lib().set_bn_small_rows(2048, ctypes.addressof(old))
+    assert old.value == 1024
+    lib().set_bn_small_rows(old.value, 0)
+    with pytest.raises(MmfnError, match="rows must be >= 0"):
+        lib().set_bn_small_rows(-1, 0)
 
 
 def test_product_never_imports_oracle():
